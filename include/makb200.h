@@ -1,0 +1,92 @@
+/* makb200 — C ABI of the B200-native dense-factorization library (sm_100a).
+ *
+ * Drop-in boundary for MatrixAlgebraKit.jl v0.6.9: every entry point below replaces a
+ * LAPACK (`src/yalapack.jl`, ccall into libblastrampoline) or cuSOLVER
+ * (`ext/MatrixAlgebraKitCUDAExt/yacusolver.jl`) call site on the path
+ * qr_compact!/qr_full!, svd_compact!/svd_trunc!, eigh_full!, left_polar!.
+ * The Julia extension `ext/MatrixAlgebraKitB200Ext` `ccall`s exactly these symbols;
+ * the Python host layer (`matrixalgebrakit.jl_b200/`) binds the same symbols via ctypes.
+ *
+ * Conventions (all from the reference's shims):
+ *  - column-major, unit stride in dim 1, explicit leading dimensions in ELEMENTS
+ *    (`lda = stride(A,2)`, yalapack.jl:173,179; yacusolver.jl:72-74);
+ *  - all matrix/vector pointers are DEVICE pointers; plain sizes are host ints;
+ *  - return value: 0 ok, -i = i-th argument invalid (LAPACK `info<0`, yalapack.jl:193),
+ *    >0 numerical failure / CUDA error (MAKB200_ERR_*). Never throws, never allocates
+ *    device memory: scratch comes from the caller (`*_worksize` query + `work`,`lwork`),
+ *    mirroring CUDA.jl's `with_workspace` (yacusolver.jl:76-90);
+ *  - asynchronous on the handle's stream; no host sync unless documented;
+ *  - dtype: MAKB200_F64 = Float64, MAKB200_C128 = ComplexF64 (interleaved re,im).
+ */
+#ifndef MAKB200_H
+#define MAKB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct makb200_handle makb200_handle_t;
+
+enum { MAKB200_F64 = 0, MAKB200_C128 = 1 };
+enum { MAKB200_QR_COMPACT = 0, MAKB200_QR_FULL = 1 };
+enum { MAKB200_OP_N = 0, MAKB200_OP_T = 1, MAKB200_OP_C = 2 };
+enum { MAKB200_ERR_CUDA = 1000, MAKB200_ERR_WORKSPACE = 1001, MAKB200_ERR_NOCONV = 1002 };
+
+/* -- handle: plays the role of cuSOLVER.dense_handle() (yacusolver.jl:76) ------------ */
+int makb200_create(makb200_handle_t** h, int device);
+int makb200_destroy(makb200_handle_t* h);
+int makb200_set_stream(makb200_handle_t* h, void* cuda_stream);
+int makb200_version(void);
+/* last CUDA error string recorded on this handle (host memory, owned by the library) */
+const char* makb200_last_error(makb200_handle_t* h);
+
+/* -- GEMM building block: C = alpha*op(A)*op(B) + beta*C  (FP64 DMMA tiles) ----------
+ * replaces `mul!` on CuArray -> cuBLAS gemm (implementations/polar.jl:63,88).
+ * alpha/beta: HOST pointers to one scalar of `dtype`. */
+int makb200_gemm(makb200_handle_t* h, int dtype, int opa, int opb, int m, int n, int k,
+                 const void* alpha, const void* A, int lda, const void* B, int ldb,
+                 const void* beta, void* C, int ldc);
+
+/* -- L1 (LAPACK-shaped) QR shims -----------------------------------------------------
+ * makb200_geqrf  replaces geqrf!/geqrt! (yalapack.jl:168-200,303-333; yacusolver.jl:12).
+ *   On exit A holds R (upper) and the Householder vectors (below the diagonal, unit
+ *   diagonal implicit), `tau` the k=min(m,n) scalar factors.  Reflector convention:
+ *   H_j = I - tau_j v v^H with NON-NEGATIVE real R[j,j] (src/common/householder.jl:35-67),
+ *   so the reference's QR gauge (common/gauge.jl:16-25) is already satisfied.
+ * makb200_orgqr   replaces ungqr!/gemqrt!-on-identity (yalapack.jl:550-583,882-928):
+ *   Q (m x ncols, ncols<=m) = first ncols columns of H_1...H_k. */
+size_t makb200_geqrf_worksize(makb200_handle_t* h, int dtype, int m, int n);
+int makb200_geqrf(makb200_handle_t* h, int dtype, int m, int n, void* A, int lda, void* tau,
+                  void* work, size_t lwork);
+size_t makb200_orgqr_worksize(makb200_handle_t* h, int dtype, int m, int ncols, int k);
+int makb200_orgqr(makb200_handle_t* h, int dtype, int m, int ncols, int k, const void* A,
+                  int lda, const void* tau, void* Q, int ldq, void* work, size_t lwork);
+
+/* -- L2 fused QR: qr_householder!(driver, A, Q, R; positive) (implementations/qr.jl:132-188)
+ *   mode COMPACT: Q m x k, R k x n; FULL: Q m x m, R m x n (k = min(m,n)).
+ *   R == NULL or ldr == 0  => "R not requested" (zero-length R, qr.jl:149).
+ *   A is destroyed.  `positive` is accepted for signature parity; the factorization always
+ *   has diag(R) >= 0, which is a valid result for positive=false as well. */
+size_t makb200_qr_worksize(makb200_handle_t* h, int dtype, int mode, int m, int n);
+int makb200_qr(makb200_handle_t* h, int dtype, int mode, int positive, int m, int n, void* A,
+               int lda, void* Q, int ldq, void* R, int ldr, void* work, size_t lwork);
+
+/* -- batched QR of many small blocks (one CTA per block, block resident in shared memory) ---
+ * New capability: semantics = qr_compact!(A_i,(Q_i,R_i)) applied per block
+ * (downstream TensorKit-style block loops call the single-matrix op once per block).
+ * m,n,lda,ldq,ldr: HOST int arrays (Julia knows the block sizes on the host);
+ * A,Q,R: HOST arrays of DEVICE pointers; R may be NULL (or R[i] NULL) = not requested.
+ * Blocks that do not fit one CTA's shared memory are routed through the blocked DMMA path.
+ * info: DEVICE int[batch] or NULL. */
+size_t makb200_qr_batched_worksize(makb200_handle_t* h, int dtype, int batch, const int* m,
+                                   const int* n);
+int makb200_qr_batched(makb200_handle_t* h, int dtype, int batch, const int* m, const int* n,
+                       void* const* A, const int* lda, void* const* Q, const int* ldq,
+                       void* const* R, const int* ldr, int* info, void* work, size_t lwork);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAKB200_H */

@@ -1,0 +1,12 @@
+"""makb200 — B200-native dense factorizations behind MatrixAlgebraKit.jl's algorithm API.
+
+Host layer in Python (the reference's Julia toolchain is absent from this image; the Julia
+extension that binds the same C ABI is in ``ext/MatrixAlgebraKitB200Ext``).  All numerical work
+happens in ``libmakb200.so`` (hand-written sm_100a CUDA); there is no CPU fallback."""
+from . import _lib
+from ._core import (Handle, MakError, as_colmajor, colmajor_empty, colmajor_zeros, is_colmajor, to_device,
+                    to_numpy)
+from .algorithms import *  # noqa: F401,F403
+from .algorithms import (Algorithm, TruncatedAlgorithm, default_algorithm, select_algorithm)
+from .gemm import gemm_
+from .qr import (qr_compact, qr_compact_, qr_compact_batched_, qr_full, qr_full_, qr_householder_)

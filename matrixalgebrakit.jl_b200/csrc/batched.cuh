@@ -1,0 +1,18 @@
+#pragma once
+#include "common.cuh"
+namespace mak {
+template <typename T>
+struct QrBlockDesc {
+    int m, n;
+    T* A; int lda;
+    T* Q; int ldq;
+    T* R; int ldr;   // R == nullptr -> not requested
+};
+// shared-memory elements the one-CTA kernel needs for an m x n block, and the largest it accepts
+size_t batched_qr_smem_elems(int m, int n);
+template <typename T> size_t batched_qr_max_smem_elems();
+int batched_init(makb200_handle* h);
+// descs: DEVICE array; max_smem_elems: max of batched_qr_smem_elems over the batch
+template <typename T>
+int batched_qr_smem(makb200_handle* h, int batch, size_t max_smem_elems, const QrBlockDesc<T>* descs, int* info);
+}  // namespace mak

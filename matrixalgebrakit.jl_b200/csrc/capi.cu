@@ -1,0 +1,235 @@
+// C ABI (include/makb200.h): handle management and argument checking; the numerical work
+// lives in gemm.cu / qr.cu / ...
+#include "common.cuh"
+#include "gemm.cuh"
+#include "qr.cuh"
+#include "batched.cuh"
+#include <vector>
+
+using mak::cplx;
+
+extern "C" {
+
+int makb200_version(void) { return 100; }
+
+int makb200_create(makb200_handle_t** out, int device) {
+    if (!out) return -1;
+    *out = nullptr;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return MAKB200_ERR_CUDA;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return MAKB200_ERR_CUDA;
+    if (prop.major != 10) return MAKB200_ERR_CUDA;  // sm_100a SASS only: fail loudly elsewhere
+    makb200_handle* h = new makb200_handle();
+    h->device = device;
+    h->stream = 0;
+    h->num_sms = prop.multiProcessorCount;
+    h->max_cluster = 8;
+    h->err[0] = 0;
+    int rc = mak::qr_init(h);
+    if (rc == 0) rc = mak::batched_init(h);
+    if (rc != 0) { delete h; return rc; }
+    *out = h;
+    return 0;
+}
+
+int makb200_destroy(makb200_handle_t* h) {
+    if (!h) return -1;
+    delete h;
+    return 0;
+}
+
+int makb200_set_stream(makb200_handle_t* h, void* s) {
+    if (!h) return -1;
+    h->stream = (cudaStream_t)s;
+    return 0;
+}
+
+const char* makb200_last_error(makb200_handle_t* h) { return h ? h->err : "null handle"; }
+
+static bool op_ok(int op) { return op == MAKB200_OP_N || op == MAKB200_OP_T || op == MAKB200_OP_C; }
+
+int makb200_gemm(makb200_handle_t* h, int dtype, int opa, int opb, int m, int n, int k, const void* alpha,
+                 const void* A, int lda, const void* B, int ldb, const void* beta, void* C, int ldc) {
+    if (!h) return -1;
+    if (dtype != MAKB200_F64 && dtype != MAKB200_C128) return -2;
+    if (!op_ok(opa)) return -3;
+    if (!op_ok(opb)) return -4;
+    if (m < 0) return -5;
+    if (n < 0) return -6;
+    if (k < 0) return -7;
+    if (!alpha) return -8;
+    int arows = (opa == MAKB200_OP_N) ? m : k, brows = (opb == MAKB200_OP_N) ? k : n;
+    if (lda < (arows > 1 ? arows : 1)) return -10;
+    if (ldb < (brows > 1 ? brows : 1)) return -12;
+    if (!beta) return -13;
+    if (ldc < (m > 1 ? m : 1)) return -15;
+    if (m == 0 || n == 0) return 0;
+    if ((k > 0 && (!A || !B)) || !C) return -9;
+    cudaError_t e;
+    if (dtype == MAKB200_F64)
+        e = mak::gemm<double>(h->stream, h->num_sms, opa, opb, m, n, k, *(const double*)alpha, (const double*)A, lda,
+                              (const double*)B, ldb, *(const double*)beta, (double*)C, ldc);
+    else
+        e = mak::gemm<cplx>(h->stream, h->num_sms, opa, opb, m, n, k, *(const cplx*)alpha, (const cplx*)A, lda,
+                            (const cplx*)B, ldb, *(const cplx*)beta, (cplx*)C, ldc);
+    if (e != cudaSuccess) return mak::cuda_fail(h, e, "makb200_gemm");
+    return 0;
+}
+
+static bool dtype_ok(int d) { return d == MAKB200_F64 || d == MAKB200_C128; }
+static int maxi(int a, int b) { return a > b ? a : b; }
+
+size_t makb200_qr_worksize(makb200_handle_t* h, int dtype, int mode, int m, int n) {
+    if (!h || !dtype_ok(dtype) || m < 0 || n < 0) return 0;
+    int k = m < n ? m : n, ncq = (mode == MAKB200_QR_FULL) ? m : k;
+    return dtype == MAKB200_F64 ? mak::qr_worksize_t<double>(h, m, n, ncq) : mak::qr_worksize_t<cplx>(h, m, n, ncq);
+}
+
+int makb200_qr(makb200_handle_t* h, int dtype, int mode, int positive, int m, int n, void* A, int lda, void* Q,
+               int ldq, void* R, int ldr, void* work, size_t lwork) {
+    (void)positive;
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (mode != MAKB200_QR_COMPACT && mode != MAKB200_QR_FULL) return -3;
+    if (m < 0) return -5;
+    if (n < 0) return -6;
+    int k = m < n ? m : n, ncq = (mode == MAKB200_QR_FULL) ? m : k;
+    if (lda < maxi(1, m)) return -8;
+    if (ldq < maxi(1, m)) return -10;
+    if (R && ldr > 0 && ldr < maxi(1, ncq)) return -12;
+    if (m == 0) return 0;
+    if ((!A && n > 0) || !Q) return -7;
+    if (Q == A) return -9;  // in-place Q is not provided (qr.jl:150-153 rejects it for R/positive anyway)
+    if (dtype == MAKB200_F64)
+        return mak::qr_fused_t<double>(h, mode, m, n, (double*)A, lda, (double*)Q, ldq, (double*)R, ldr, work, lwork);
+    return mak::qr_fused_t<cplx>(h, mode, m, n, (cplx*)A, lda, (cplx*)Q, ldq, (cplx*)R, ldr, work, lwork);
+}
+
+size_t makb200_geqrf_worksize(makb200_handle_t* h, int dtype, int m, int n) {
+    if (!h || !dtype_ok(dtype) || m < 0 || n < 0) return 0;
+    int k = m < n ? m : n;
+    return dtype == MAKB200_F64 ? mak::qr_worksize_t<double>(h, m, n, k) : mak::qr_worksize_t<cplx>(h, m, n, k);
+}
+
+int makb200_geqrf(makb200_handle_t* h, int dtype, int m, int n, void* A, int lda, void* tau, void* work,
+                  size_t lwork) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (m < 0) return -3;
+    if (n < 0) return -4;
+    if (lda < maxi(1, m)) return -6;
+    if (m == 0 || n == 0) return 0;  // yalapack.jl:177
+    if (!A) return -5;
+    if (!tau) return -7;
+    if (dtype == MAKB200_F64) return mak::geqrf_t<double>(h, m, n, (double*)A, lda, (double*)tau, work, lwork);
+    return mak::geqrf_t<cplx>(h, m, n, (cplx*)A, lda, (cplx*)tau, work, lwork);
+}
+
+size_t makb200_orgqr_worksize(makb200_handle_t* h, int dtype, int m, int ncols, int k) {
+    if (!h || !dtype_ok(dtype) || m < 0 || ncols < 0 || k < 0) return 0;
+    return dtype == MAKB200_F64 ? mak::qr_worksize_t<double>(h, m, k, ncols) : mak::qr_worksize_t<cplx>(h, m, k, ncols);
+}
+
+int makb200_orgqr(makb200_handle_t* h, int dtype, int m, int ncols, int k, const void* A, int lda, const void* tau,
+                  void* Q, int ldq, void* work, size_t lwork) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (m < 0) return -3;
+    if (ncols < 0 || ncols > m) return -4;
+    if (k < 0 || k > m) return -5;
+    if (lda < maxi(1, m)) return -7;
+    if (ldq < maxi(1, m)) return -10;
+    if (m == 0 || ncols == 0) return 0;
+    if (k > 0 && (!A || !tau)) return -6;
+    if (!Q || Q == A) return -9;
+    if (dtype == MAKB200_F64)
+        return mak::orgqr_t<double>(h, m, ncols, k, (const double*)A, lda, (const double*)tau, (double*)Q, ldq, work,
+                                    lwork);
+    return mak::orgqr_t<cplx>(h, m, ncols, k, (const cplx*)A, lda, (const cplx*)tau, (cplx*)Q, ldq, work, lwork);
+}
+
+}  // extern "C"
+
+// ---- batched -----------------------------------------------------------------------
+template <typename T>
+static size_t qr_batched_worksize_t(makb200_handle_t* h, int batch, const int* m, const int* n) {
+    size_t bytes = mak::align_up(sizeof(mak::QrBlockDesc<T>) * (size_t)(batch > 0 ? batch : 1), 256);
+    size_t big = 0;
+    for (int i = 0; i < batch; ++i) {
+        if (mak::batched_qr_smem_elems(m[i], n[i]) > mak::batched_qr_max_smem_elems<T>()) {
+            size_t w = mak::qr_worksize_t<T>(h, m[i], n[i], m[i] < n[i] ? m[i] : n[i]);
+            if (w > big) big = w;
+        }
+    }
+    return bytes + big + 256;
+}
+
+template <typename T>
+static int qr_batched_t(makb200_handle_t* h, int batch, const int* m, const int* n, void* const* A, const int* lda,
+                        void* const* Q, const int* ldq, void* const* R, const int* ldr, int* info, void* work,
+                        size_t lwork) {
+    std::vector<mak::QrBlockDesc<T>> small;
+    std::vector<int> big;
+    small.reserve(batch);
+    size_t max_se = 0;
+    for (int i = 0; i < batch; ++i) {
+        if (m[i] < 0 || n[i] < 0) return -4;
+        size_t se = mak::batched_qr_smem_elems(m[i], n[i]);
+        if (se > mak::batched_qr_max_smem_elems<T>()) { big.push_back(i); continue; }
+        mak::QrBlockDesc<T> d;
+        d.m = m[i]; d.n = n[i];
+        d.A = (T*)A[i]; d.lda = lda[i];
+        d.Q = (T*)Q[i]; d.ldq = ldq[i];
+        d.R = (R && R[i]) ? (T*)R[i] : nullptr; d.ldr = ldr ? ldr[i] : 0;
+        small.push_back(d);
+        if (se > max_se) max_se = se;
+    }
+    mak::Arena ar(work, lwork);
+    mak::QrBlockDesc<T>* ddev = ar.get<mak::QrBlockDesc<T>>(batch > 0 ? batch : 1);
+    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    if (info) MAK_CUDA(h, cudaMemsetAsync(info, 0, sizeof(int) * batch, h->stream));
+    if (!small.empty()) {
+        MAK_CUDA(h, cudaMemcpyAsync(ddev, small.data(), sizeof(mak::QrBlockDesc<T>) * small.size(),
+                                    cudaMemcpyHostToDevice, h->stream));
+        int rc = mak::batched_qr_smem<T>(h, (int)small.size(), max_se, ddev, nullptr);
+        if (rc) return rc;
+    }
+    // blocks too large for one CTA's shared memory take the blocked DMMA path
+    char* wbig = (char*)work + ar.off;
+    size_t lbig = lwork > ar.off ? lwork - ar.off : 0;
+    for (int i : big) {
+        int rc = mak::qr_fused_t<T>(h, MAKB200_QR_COMPACT, m[i], n[i], (T*)A[i], lda[i], (T*)Q[i], ldq[i],
+                                    (R && R[i]) ? (T*)R[i] : nullptr, ldr ? ldr[i] : 0, wbig, lbig);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" {
+
+size_t makb200_qr_batched_worksize(makb200_handle_t* h, int dtype, int batch, const int* m, const int* n) {
+    if (!h || !dtype_ok(dtype) || batch < 0 || (batch > 0 && (!m || !n))) return 0;
+    return dtype == MAKB200_F64 ? qr_batched_worksize_t<double>(h, batch, m, n)
+                                : qr_batched_worksize_t<cplx>(h, batch, m, n);
+}
+
+int makb200_qr_batched(makb200_handle_t* h, int dtype, int batch, const int* m, const int* n, void* const* A,
+                       const int* lda, void* const* Q, const int* ldq, void* const* R, const int* ldr, int* info,
+                       void* work, size_t lwork) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (batch < 0) return -3;
+    if (batch == 0) return 0;
+    if (!m) return -4;
+    if (!n) return -5;
+    if (!A) return -6;
+    if (!lda) return -7;
+    if (!Q) return -8;
+    if (!ldq) return -9;
+    if (dtype == MAKB200_F64) return qr_batched_t<double>(h, batch, m, n, A, lda, Q, ldq, R, ldr, info, work, lwork);
+    return qr_batched_t<cplx>(h, batch, m, n, A, lda, Q, ldq, R, ldr, info, work, lwork);
+}
+
+}  // extern "C"

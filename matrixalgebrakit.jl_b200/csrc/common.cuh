@@ -1,0 +1,176 @@
+// Shared device/host helpers for the makb200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include "../../include/makb200.h"
+
+namespace mak {
+
+// ---------------------------------------------------------------------------------------
+// scalar types: double and an interleaved complex (layout == Julia ComplexF64)
+// ---------------------------------------------------------------------------------------
+struct __align__(16) cplx {
+    double re, im;
+};
+
+template <typename T> struct is_cplx { static constexpr bool value = false; };
+template <> struct is_cplx<cplx> { static constexpr bool value = true; };
+
+__host__ __device__ __forceinline__ double zero_of(double) { return 0.0; }
+__host__ __device__ __forceinline__ cplx zero_of(cplx) { return cplx{0.0, 0.0}; }
+template <typename T> __host__ __device__ __forceinline__ T zero() { return zero_of(T{}); }
+__host__ __device__ __forceinline__ double one_of(double) { return 1.0; }
+__host__ __device__ __forceinline__ cplx one_of(cplx) { return cplx{1.0, 0.0}; }
+template <typename T> __host__ __device__ __forceinline__ T one() { return one_of(T{}); }
+
+__host__ __device__ __forceinline__ double conj_(double a) { return a; }
+__host__ __device__ __forceinline__ cplx conj_(cplx a) { return cplx{a.re, -a.im}; }
+__host__ __device__ __forceinline__ double real_(double a) { return a; }
+__host__ __device__ __forceinline__ double real_(cplx a) { return a.re; }
+__host__ __device__ __forceinline__ double imag_(double) { return 0.0; }
+__host__ __device__ __forceinline__ double imag_(cplx a) { return a.im; }
+__host__ __device__ __forceinline__ double abs2_(double a) { return a * a; }
+__host__ __device__ __forceinline__ double abs2_(cplx a) { return a.re * a.re + a.im * a.im; }
+__host__ __device__ __forceinline__ double add_(double a, double b) { return a + b; }
+__host__ __device__ __forceinline__ cplx add_(cplx a, cplx b) { return cplx{a.re + b.re, a.im + b.im}; }
+__host__ __device__ __forceinline__ double sub_(double a, double b) { return a - b; }
+__host__ __device__ __forceinline__ cplx sub_(cplx a, cplx b) { return cplx{a.re - b.re, a.im - b.im}; }
+__host__ __device__ __forceinline__ double mul_(double a, double b) { return a * b; }
+__host__ __device__ __forceinline__ cplx mul_(cplx a, cplx b) {
+    return cplx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+}
+__host__ __device__ __forceinline__ double neg_(double a) { return -a; }
+__host__ __device__ __forceinline__ cplx neg_(cplx a) { return cplx{-a.re, -a.im}; }
+__host__ __device__ __forceinline__ double scale_(double a, double s) { return a * s; }
+__host__ __device__ __forceinline__ cplx scale_(cplx a, double s) { return cplx{a.re * s, a.im * s}; }
+// a += b*c
+__host__ __device__ __forceinline__ void fma_(double& a, double b, double c) { a = fma(b, c, a); }
+__host__ __device__ __forceinline__ void fma_(cplx& a, cplx b, cplx c) {
+    a.re = fma(b.re, c.re, a.re);
+    a.re = fma(-b.im, c.im, a.re);
+    a.im = fma(b.re, c.im, a.im);
+    a.im = fma(b.im, c.re, a.im);
+}
+// a += conj(b)*c
+__host__ __device__ __forceinline__ void fmac_(double& a, double b, double c) { a = fma(b, c, a); }
+__host__ __device__ __forceinline__ void fmac_(cplx& a, cplx b, cplx c) {
+    a.re = fma(b.re, c.re, a.re);
+    a.re = fma(b.im, c.im, a.re);
+    a.im = fma(b.re, c.im, a.im);
+    a.im = fma(-b.im, c.re, a.im);
+}
+__host__ __device__ __forceinline__ double div_(double a, double b) { return a / b; }
+__host__ __device__ __forceinline__ cplx div_(cplx a, cplx b) {
+    // Smith's algorithm
+    if (fabs(b.re) >= fabs(b.im)) {
+        double r = b.im / b.re, d = b.re + b.im * r;
+        return cplx{(a.re + a.im * r) / d, (a.im - a.re * r) / d};
+    } else {
+        double r = b.re / b.im, d = b.re * r + b.im;
+        return cplx{(a.re * r + a.im) / d, (a.im * r - a.re) / d};
+    }
+}
+__host__ __device__ __forceinline__ double from_real(double r, double) { return r; }
+__host__ __device__ __forceinline__ cplx from_real(double r, cplx) { return cplx{r, 0.0}; }
+template <typename T> __host__ __device__ __forceinline__ T mk(double r) { return from_real(r, T{}); }
+__host__ __device__ __forceinline__ bool is_zero(double a) { return a == 0.0; }
+__host__ __device__ __forceinline__ bool is_zero(cplx a) { return a.re == 0.0 && a.im == 0.0; }
+__host__ __device__ __forceinline__ bool is_one(double a) { return a == 1.0; }
+__host__ __device__ __forceinline__ bool is_one(cplx a) { return a.re == 1.0 && a.im == 0.0; }
+
+// ---------------------------------------------------------------------------------------
+// warp / block reductions (deterministic order)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ cplx warp_sum(cplx v) {
+    v.re = warp_sum(v.re);
+    v.im = warp_sum(v.im);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// block-wide sum; `scratch` must hold >= 32 T; result broadcast to all threads.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    T r = zero<T>();
+    for (int i = 0; i < nw; ++i) r = add_(r, scratch[i]);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------
+}  // namespace mak
+
+struct makb200_handle {
+    int device;
+    cudaStream_t stream;
+    int num_sms;
+    int max_cluster;  // largest usable cluster size for the panel kernel
+    char err[256];
+};
+
+namespace mak {
+
+inline int cuda_fail(makb200_handle* h, cudaError_t e, const char* where) {
+    if (h) snprintf(h->err, sizeof(h->err), "%s: %s", where, cudaGetErrorString(e));
+    return MAKB200_ERR_CUDA;
+}
+#define MAK_CUDA(h, call)                                         \
+    do {                                                          \
+        cudaError_t _e = (call);                                  \
+        if (_e != cudaSuccess) return mak::cuda_fail(h, _e, #call); \
+    } while (0)
+#define MAK_LAUNCH_CHECK(h, name)                                   \
+    do {                                                            \
+        cudaError_t _e = cudaGetLastError();                        \
+        if (_e != cudaSuccess) return mak::cuda_fail(h, _e, name);  \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// bump allocator over the caller-provided workspace
+struct Arena {
+    char* base;
+    size_t cap, off;
+    bool ok;
+    Arena(void* p, size_t n) : base((char*)p), cap(n), off(0), ok(true) {}
+    template <typename T> T* get(size_t count) {
+        size_t bytes = align_up(count * sizeof(T), 256);
+        if (off + bytes > cap || (base == nullptr && bytes > 0)) {
+            ok = false;
+            off += bytes;
+            return nullptr;
+        }
+        T* r = (T*)(base + off);
+        off += bytes;
+        return r;
+    }
+};
+// sizing twin of Arena (no memory)
+struct ArenaSize {
+    size_t off = 0;
+    bool ok = true;
+    template <typename T> T* get(size_t count) {
+        off += align_up(count * sizeof(T), 256);
+        return nullptr;
+    }
+};
+
+}  // namespace mak

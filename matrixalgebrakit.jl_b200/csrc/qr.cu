@@ -1,0 +1,570 @@
+// Blocked Householder QR for sm_100a (geqrf/geqrt + orgqr/gemqrt equivalents).
+//
+//  * panel_kernel: one thread-block CLUSTER factorizes an (mp x ib) panel that stays resident in
+//    the shared memory of the cluster's CTAs (row slabs).  Per column there is exactly one
+//    cluster-wide reduction (partial dot products exchanged through distributed shared memory)
+//    and one cluster barrier; the compact-WY T factor is accumulated on the fly.
+//    Reflector convention: beta = +||x|| (src/common/householder.jl:35-67 of the reference), so
+//    diag(R) >= 0 and the reference's QR gauge (common/gauge.jl:16-25) needs no extra pass.
+//  * everything GEMM-shaped (compact-WY trailing updates, T-factor coupling, Q formation) goes
+//    through the DMMA GEMM in gemm.cu.
+#include <cooperative_groups.h>
+#include <type_traits>
+#include "qr.cuh"
+#include "gemm.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace mak {
+
+constexpr int QR_NB = 128;        // outer block width (K of the trailing-update GEMMs)
+constexpr int IBMAX = 32;         // inner panel width (max)
+constexpr int PANEL_THREADS = 256;
+constexpr size_t PANEL_SLAB_BYTES = 160 * 1024;  // shared-memory budget for the row slab
+
+// stable non-negative-beta reflector scalars: given alpha = x[0], sigma = ||x[1:]||^2
+// returns beta >= 0, tau, scale with v = x[1:]*scale, H = I - tau*[1;v][1;v]^H, H^H x = beta e1.
+template <typename T>
+__host__ __device__ __forceinline__ void larfgp_scalars(T alpha, double sigma, double& beta, T& tau, T& scale) {
+    if (sigma == 0.0 && imag_(alpha) == 0.0 && real_(alpha) >= 0.0) {
+        beta = real_(alpha);
+        tau = zero<T>();
+        scale = zero<T>();
+        return;
+    }
+    beta = sqrt(abs2_(alpha) + sigma);
+    T d;
+    if (real_(alpha) < 0.0) {
+        d = sub_(alpha, mk<T>(beta));
+    } else {
+        // alpha - beta = ((alpha - conj(alpha))*beta - sigma) / (conj(alpha) + beta)
+        T num = sub_(scale_(sub_(alpha, conj_(alpha)), beta), mk<T>(sigma));
+        T den = add_(conj_(alpha), mk<T>(beta));
+        d = div_(num, den);
+    }
+    tau = scale_(neg_(d), 1.0 / beta);
+    scale = div_(one<T>(), d);
+}
+
+// ---------------------------------------------------------------------------------------
+// cluster panel factorization
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(PANEL_THREADS, 1)
+panel_kernel(int mp, int ib, T* __restrict__ A, int lda, T* __restrict__ tau_out, T* __restrict__ Tout,
+             int ldt, int rpc) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = PANEL_THREADS / 32;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* slab = reinterpret_cast<T*>(smem_raw);              // [ib][rpc]
+    T* xch = slab + (size_t)ib * rpc;                       // [2][CS+1][IBMAX]
+    T* coef = xch + 2 * (CS + 1) * IBMAX;                   // [IBMAX]
+    T* zbuf = coef + IBMAX;                                 // [IBMAX]
+    T* Tsm = zbuf + IBMAX;                                  // [IBMAX][IBMAX] (col-major), rank 0 only
+    T* scal = Tsm + IBMAX * IBMAX;                          // [4]: scale, tau, beta
+
+    const int r0 = rank * rpc;
+    const int nr = max(0, min(rpc, mp - r0));
+
+    for (int idx = tid; idx < nr * ib; idx += PANEL_THREADS) {
+        int c = idx / nr, r = idx - c * nr;
+        slab[(size_t)c * rpc + r] = A[(size_t)c * lda + r0 + r];
+    }
+    for (int idx = tid; idx < IBMAX * IBMAX; idx += PANEL_THREADS) Tsm[idx] = zero<T>();
+    __syncthreads();
+    cluster.sync();  // all CTAs resident & initialised before any DSMEM traffic
+
+    for (int j = 0; j < ib; ++j) {
+        const int par = j & 1;
+        const int ls = max(0, j + 1 - r0);  // first local row strictly below the diagonal
+        // ---- partial dot products over own rows: one warp per column l ----
+        const T* cj = slab + (size_t)j * rpc;
+        for (int l = warp; l < ib; l += NW) {
+            const T* cl = slab + (size_t)l * rpc;
+            T s = zero<T>();
+            if (l >= j) {
+                for (int r = ls + lane; r < nr; r += 32) fmac_(s, cj[r], cl[r]);  // conj(a_j) * a_l
+            } else {
+                for (int r = ls + lane; r < nr; r += 32) fmac_(s, cl[r], cj[r]);  // conj(v_l) * a_j
+            }
+            s = warp_sum(s);
+            if (lane < CS) {
+                T* dst = cluster.map_shared_rank(xch, lane);
+                dst[(par * (CS + 1) + rank) * IBMAX + l] = s;
+            }
+        }
+        if (rank == 0) {
+            // broadcast row j of the panel (v_l[j] for l<j, a_jl for l>=j)
+            for (int idx = tid; idx < ib * CS; idx += PANEL_THREADS) {
+                int l = idx % ib, d = idx / ib;
+                T* dst = cluster.map_shared_rank(xch, d);
+                dst[(par * (CS + 1) + CS) * IBMAX + l] = slab[(size_t)l * rpc + j];
+            }
+        }
+        cluster.sync();
+        // ---- reduce, reflector scalars, update coefficients ----
+        if (tid < ib) {
+            const T* xp = xch + par * (CS + 1) * IBMAX;
+            const T* top = xp + CS * IBMAX;
+            T accl = zero<T>(), accj = zero<T>();
+            for (int r = 0; r < CS; ++r) {
+                accl = add_(accl, xp[r * IBMAX + tid]);
+                accj = add_(accj, xp[r * IBMAX + j]);
+            }
+            double beta;
+            T tau, scale;
+            larfgp_scalars<T>(top[j], real_(accj), beta, tau, scale);
+            const int l = tid;
+            if (l > j) {
+                T f = add_(top[l], mul_(conj_(scale), accl));
+                coef[l] = mul_(conj_(tau), f);
+            } else if (l < j) {
+                zbuf[l] = add_(conj_(top[l]), mul_(scale, accl));  // v_l^H v_j
+            } else {
+                scal[0] = scale;
+                scal[1] = tau;
+                scal[2] = mk<T>(beta);
+            }
+        }
+        __syncthreads();
+        const T scale = scal[0], tau = scal[1];
+        // ---- T column j (rank 0): T[0:j, j] = -tau * T[0:j,0:j] * z ----
+        if (rank == 0 && tid < ib) {
+            if (tid < j) {
+                T s = zero<T>();
+                for (int p = tid; p < j; ++p) fma_(s, Tsm[p * IBMAX + tid], zbuf[p]);
+                Tsm[j * IBMAX + tid] = neg_(mul_(tau, s));
+            } else if (tid == j) {
+                Tsm[j * IBMAX + j] = tau;
+                tau_out[j] = tau;
+            }
+        }
+        // ---- apply H_j^H to the remaining columns; scale column j into v ----
+        T* cjw = slab + (size_t)j * rpc;
+        for (int r = ls + tid; r < nr; r += PANEL_THREADS) {
+            T v = mul_(cjw[r], scale);
+            cjw[r] = v;
+            for (int l = j + 1; l < ib; ++l) {
+                T* p = slab + (size_t)l * rpc + r;
+                *p = sub_(*p, mul_(coef[l], v));
+            }
+        }
+        if (rank == 0 && tid < ib) {
+            if (tid > j) {
+                T* p = slab + (size_t)tid * rpc + j;
+                *p = sub_(*p, coef[tid]);
+            } else if (tid == j) {
+                slab[(size_t)j * rpc + j] = scal[2];
+            }
+        }
+        __syncthreads();
+    }
+
+    for (int idx = tid; idx < nr * ib; idx += PANEL_THREADS) {
+        int c = idx / nr, r = idx - c * nr;
+        A[(size_t)c * lda + r0 + r] = slab[(size_t)c * rpc + r];
+    }
+    if (rank == 0 && Tout) {
+        for (int idx = tid; idx < ib * ib; idx += PANEL_THREADS) {
+            int c = idx / ib, r = idx - c * ib;
+            Tout[(size_t)c * ldt + r] = Tsm[c * IBMAX + r];
+        }
+    }
+    cluster.sync();  // no CTA may exit while peers can still address its shared memory
+}
+
+template <typename T>
+static size_t panel_smem_bytes(int ib, int rpc, int cs) {
+    return ((size_t)ib * rpc + 2 * (size_t)(cs + 1) * IBMAX + 2 * IBMAX + IBMAX * IBMAX + 4) * sizeof(T);
+}
+
+template <typename T>
+static cudaError_t launch_panel(makb200_handle* h, int mp, int ib, T* A, int lda, T* tau, T* Tout, int ldt) {
+    // cluster size: ~512 rows per CTA, every CTA must own >= ib rows so that the panel's
+    // top triangle lives in rank 0, and the slab must fit in shared memory.
+    int cs = 1;
+    auto rows_per = [&](int c) { return ((mp + c - 1) / c + 31) / 32 * 32; };
+    while (cs < h->max_cluster && mp / (cs * 2) >= ib &&
+           ((mp + cs - 1) / cs > 512 || (size_t)rows_per(cs) * ib * sizeof(T) > PANEL_SLAB_BYTES))
+        cs *= 2;
+    int rpc = rows_per(cs);
+    if ((size_t)rpc * ib * sizeof(T) > PANEL_SLAB_BYTES) return cudaErrorInvalidValue;  // caller sizes ib
+    size_t smem = panel_smem_bytes<T>(ib, rpc, cs);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs, 1, 1);
+    cfg.blockDim = dim3(PANEL_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, panel_kernel<T>, mp, ib, A, lda, tau, Tout, ldt, rpc);
+}
+
+// inner panel width such that the slab of the tallest panel fits the cluster's shared memory
+template <typename T>
+static int choose_ib(const makb200_handle* h, int m) {
+    int ib = IBMAX;
+    while (ib > 4) {
+        int rpc = ((m + h->max_cluster - 1) / h->max_cluster + 31) / 32 * 32;
+        if ((size_t)rpc * ib * sizeof(T) <= PANEL_SLAB_BYTES) break;
+        ib /= 2;
+    }
+    return ib;
+}
+
+template <typename T>
+static int panel_init(makb200_handle* h) {
+    MAK_CUDA(h, cudaFuncSetAttribute(panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    MAK_CUDA(h, cudaFuncSetAttribute(panel_kernel<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    return 0;
+}
+
+int qr_init(makb200_handle* h) {
+    int rc = panel_init<double>(h);
+    if (rc) return rc;
+    rc = panel_init<cplx>(h);
+    if (rc) return rc;
+    // largest cluster that can be co-scheduled with a full slab
+    int best = 1;
+    for (int cs = 16; cs >= 2; cs /= 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cs, 1, 1);
+        cfg.blockDim = dim3(PANEL_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = PANEL_SLAB_BYTES + 40 * 1024;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int ncl = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, panel_kernel<cplx>, &cfg);
+        if (e == cudaSuccess && ncl > 0) { best = cs; break; }
+        cudaGetLastError();
+    }
+    h->max_cluster = best;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// small helper kernels
+// ---------------------------------------------------------------------------------------
+// Vw (mp x jb, ld ldv) = unit-lower-trapezoidal part of the panel A (explicit 1 / 0)
+// (column c has its diagonal at row c + doff)
+template <typename T>
+__global__ void copy_v_kernel(int mp, int jb, int doff, const T* __restrict__ A, int lda, T* __restrict__ V,
+                              int ldv) {
+    size_t total = (size_t)mp * jb;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(idx % mp), c = (int)(idx / mp);
+        T v = A[(size_t)c * lda + r];
+        if (r < c + doff) v = zero<T>();
+        else if (r == c + doff) v = one<T>();
+        V[(size_t)c * ldv + r] = v;
+    }
+}
+
+template <typename T>
+__global__ void set_identity_kernel(int m, int n, T* __restrict__ Q, int ldq) {
+    size_t total = (size_t)m * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(idx % m), c = (int)(idx / m);
+        Q[(size_t)c * ldq + r] = (r == c) ? one<T>() : zero<T>();
+    }
+}
+
+// R (rr x n) = upper-triangular part of A[0:rr, 0:n]  (uppertriangular! + copyto!, qr.jl:177-181)
+template <typename T>
+__global__ void extract_r_kernel(int rr, int n, int ma, const T* __restrict__ A, int lda, T* __restrict__ R,
+                                 int ldr) {
+    size_t total = (size_t)rr * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(idx % rr), c = (int)(idx / rr);
+        T v = zero<T>();
+        if (r <= c && r < ma) v = A[(size_t)c * lda + r];
+        R[(size_t)c * ldr + r] = v;
+    }
+}
+
+// T[0:i0, i0:i0+ib] = -T[0:i0,0:i0] * G(i0 x ib) * T[i0:i0+ib, i0:i0+ib]; one CTA per column
+template <typename T>
+__global__ void t_couple_kernel(int i0, int ib, T* __restrict__ Tm, int ldt, const T* __restrict__ G, int ldg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* x = reinterpret_cast<T*>(smem_raw);  // [i0]
+    const int c = blockIdx.x;
+    const T* Tb = Tm + (size_t)i0 * ldt + i0;
+    for (int r = threadIdx.x; r < i0; r += blockDim.x) {
+        T s = zero<T>();
+        for (int p = 0; p <= c; ++p) fma_(s, G[(size_t)p * ldg + r], Tb[(size_t)c * ldt + p]);
+        x[r] = s;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < i0; r += blockDim.x) {
+        T s = zero<T>();
+        for (int p = r; p < i0; ++p) fma_(s, Tm[(size_t)p * ldt + r], x[p]);
+        Tm[(size_t)(i0 + c) * ldt + r] = neg_(s);
+    }
+}
+
+static inline int grid_for(size_t total, int num_sms) {
+    size_t b = (total + 255) / 256;
+    size_t cap = (size_t)num_sms * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ---------------------------------------------------------------------------------------
+// blocked driver
+// ---------------------------------------------------------------------------------------
+template <typename T>
+struct QrWork {
+    T* Vw;     // m x nb
+    T* W;      // nb x ncmax
+    T* W2;     // nb x ncmax
+    T* G;      // nb x nb
+    T* Tall;   // nb x nb per outer block
+    T* tau;    // k
+    void* ws;  // split-K scratch
+    size_t ws_bytes;
+    int nb, ib;
+};
+
+template <typename T>
+static size_t splitk_ws_bytes(const makb200_handle* h) {
+    return (size_t)h->num_sms * 128 * 128 * sizeof(double) * (is_cplx<T>::value ? 1 : 1);
+}
+
+template <typename T, typename AR>
+static void qr_carve(const makb200_handle* h, AR& ar, int m, int n, int ncols_q, QrWork<T>* w) {
+    const int k = m < n ? m : n;
+    const int nb = QR_NB;
+    const int ncmax = (n > ncols_q ? n : ncols_q);
+    const int nblk = (k + nb - 1) / nb;
+    w->Vw = ar.template get<T>((size_t)(m > 0 ? m : 1) * nb);
+    w->W = ar.template get<T>((size_t)nb * (ncmax > 0 ? ncmax : 1));
+    w->W2 = ar.template get<T>((size_t)nb * (ncmax > 0 ? ncmax : 1));
+    w->G = ar.template get<T>((size_t)nb * nb);
+    w->Tall = ar.template get<T>((size_t)nb * nb * (nblk > 0 ? nblk : 1));
+    w->tau = ar.template get<T>((size_t)(k > 0 ? k : 1));
+    w->ws_bytes = splitk_ws_bytes<T>(h);
+    w->ws = ar.template get<char>(w->ws_bytes);
+    w->nb = nb;
+}
+
+#define MAK_GEMM(h, ...)                                                \
+    do {                                                                \
+        cudaError_t _e = gemm<T>(__VA_ARGS__);                          \
+        if (_e != cudaSuccess) return cuda_fail(h, _e, "gemm");         \
+    } while (0)
+
+// Apply the block reflector H^H = I - V T^H V^H (trans=true) or H = I - V T V^H (trans=false) to
+// C (mc x nc) from the left.  V: mc x kb (explicit unit-lower-trapezoidal), T: kb x kb upper.
+template <typename T>
+static int apply_block_reflector(makb200_handle* h, bool trans, int mc, int nc, int kb, const T* V, int ldv,
+                                 const T* Tm, int ldt, T* C, int ldc, QrWork<T>& w) {
+    if (mc <= 0 || nc <= 0 || kb <= 0) return 0;
+    cudaStream_t s = h->stream;
+    const T one_ = one<T>(), zero_ = zero<T>(), mone = neg_(one<T>());
+    // W = V^H C   (kb x nc)
+    MAK_GEMM(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, kb, nc, mc, one_, V, ldv, C, ldc, zero_, w.W, kb, w.ws,
+             w.ws_bytes);
+    // W2 = op(T) W
+    MAK_GEMM(h, s, h->num_sms, trans ? MAKB200_OP_C : MAKB200_OP_N, MAKB200_OP_N, kb, nc, kb, one_, Tm, ldt, w.W, kb,
+             zero_, w.W2, kb, nullptr, 0);
+    // C -= V W2
+    MAK_GEMM(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_N, mc, nc, kb, mone, V, ldv, w.W2, kb, one_, C, ldc, nullptr,
+             0);
+    return 0;
+}
+
+// geqrt-style blocked factorization: A -> (V\R), tau, T factors per outer block in w.Tall
+template <typename T>
+static int geqrf_blocked(makb200_handle* h, int m, int n, T* A, int lda, QrWork<T>& w) {
+    const int k = m < n ? m : n;
+    if (k == 0) return 0;
+    cudaStream_t s = h->stream;
+    const int nb = w.nb;
+    const int ib_max = choose_ib<T>(h, m);
+    const int nblk = (k + nb - 1) / nb;
+    MAK_CUDA(h, cudaMemsetAsync(w.Tall, 0, sizeof(T) * (size_t)nb * nb * nblk, s));
+    for (int b = 0; b < nblk; ++b) {
+        const int j0 = b * nb;
+        const int jb = (k - j0 < nb) ? (k - j0) : nb;
+        const int mp = m - j0;
+        T* Ap = A + (size_t)j0 * lda + j0;
+        T* Tb = w.Tall + (size_t)b * nb * nb;
+        for (int i0 = 0; i0 < jb; i0 += ib_max) {
+            const int ib = (jb - i0 < ib_max) ? (jb - i0) : ib_max;
+            T* Ai = Ap + (size_t)i0 * lda + i0;
+            const int mi = mp - i0;
+            cudaError_t e = launch_panel<T>(h, mi, ib, Ai, lda, w.tau + j0 + i0, Tb + (size_t)i0 * nb + i0, nb);
+            if (e != cudaSuccess) return cuda_fail(h, e, "panel_kernel");
+            // explicit V for this inner block into Vw[:, i0:i0+ib] (zeros above the diagonal)
+            copy_v_kernel<T><<<grid_for((size_t)mp * ib, h->num_sms), 256, 0, s>>>(
+                mp, ib, i0, Ap + (size_t)i0 * lda, lda, w.Vw + (size_t)i0 * mp, mp);
+            MAK_LAUNCH_CHECK(h, "copy_v_kernel");
+            const T* Vi = w.Vw + (size_t)i0 * mp + i0;
+            // update the rest of the outer panel
+            const int nci = jb - i0 - ib;
+            if (nci > 0) {
+                int rc = apply_block_reflector<T>(h, true, mi, nci, ib, Vi, mp, Tb + (size_t)i0 * nb + i0, nb,
+                                                  Ai + (size_t)ib * lda, lda, w);
+                if (rc) return rc;
+            }
+            // couple into the outer T: T[0:i0, i0:i0+ib] = -T_a (V_a^H V_i) T_i
+            if (i0 > 0) {
+                const T one_ = one<T>(), zero_ = zero<T>();
+                MAK_GEMM(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, i0, ib, mp, one_, w.Vw, mp,
+                         w.Vw + (size_t)i0 * mp, mp, zero_, w.G, nb, w.ws, w.ws_bytes);
+                t_couple_kernel<T><<<ib, 128, sizeof(T) * i0, s>>>(i0, ib, Tb, nb, w.G, nb);
+                MAK_LAUNCH_CHECK(h, "t_couple_kernel");
+            }
+        }
+        // trailing update with the outer block reflector
+        const int nc = n - j0 - jb;
+        if (nc > 0) {
+            int rc = apply_block_reflector<T>(h, true, mp, nc, jb, w.Vw, mp, Tb, nb, Ap + (size_t)jb * lda, lda, w);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+// Q (m x ncols) = first ncols columns of H_1 ... H_k, from V (in A) and the stored T blocks
+template <typename T>
+static int orgqr_blocked(makb200_handle* h, int m, int ncols, int k, const T* A, int lda, T* Q, int ldq,
+                         QrWork<T>& w) {
+    cudaStream_t s = h->stream;
+    if (m <= 0 || ncols <= 0) return 0;
+    set_identity_kernel<T><<<grid_for((size_t)m * ncols, h->num_sms), 256, 0, s>>>(m, ncols, Q, ldq);
+    MAK_LAUNCH_CHECK(h, "set_identity_kernel");
+    if (k == 0) return 0;
+    const int nb = w.nb;
+    const int nblk = (k + nb - 1) / nb;
+    for (int b = nblk - 1; b >= 0; --b) {
+        const int j0 = b * nb;
+        const int jb = (k - j0 < nb) ? (k - j0) : nb;
+        const int mp = m - j0;
+        const T* Ap = A + (size_t)j0 * lda + j0;
+        const T* Tb = w.Tall + (size_t)b * nb * nb;
+        copy_v_kernel<T><<<grid_for((size_t)mp * jb, h->num_sms), 256, 0, s>>>(mp, jb, 0, Ap, lda, w.Vw, mp);
+        MAK_LAUNCH_CHECK(h, "copy_v_kernel");
+        // all columns j0 .. ncols-1 (own block columns are still [I;0])
+        const int nc = ncols - j0;
+        int rc = apply_block_reflector<T>(h, false, mp, nc, jb, w.Vw, mp, Tb, nb, Q + (size_t)j0 * ldq + j0, ldq, w);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// entry points used by capi.cu
+// ---------------------------------------------------------------------------------------
+template <typename T>
+size_t qr_worksize_t(makb200_handle* h, int m, int n, int ncols_q) {
+    ArenaSize ar;
+    QrWork<T> w;
+    qr_carve<T>(h, ar, m, n, ncols_q, &w);
+    return ar.off + 256;
+}
+
+template <typename T>
+int qr_fused_t(makb200_handle* h, int mode, int m, int n, T* A, int lda, T* Q, int ldq, T* R, int ldr, void* work,
+               size_t lwork) {
+    const int k = m < n ? m : n;
+    const int ncq = (mode == MAKB200_QR_FULL) ? m : k;
+    Arena ar(work, lwork);
+    QrWork<T> w;
+    qr_carve<T>(h, ar, m, n, ncq, &w);
+    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    int rc = geqrf_blocked<T>(h, m, n, A, lda, w);
+    if (rc) return rc;
+    if (R && ldr > 0) {
+        const int rr = ncq;
+        if (rr > 0 && n > 0) {
+            extract_r_kernel<T><<<grid_for((size_t)rr * n, h->num_sms), 256, 0, h->stream>>>(rr, n, m, A, lda, R, ldr);
+            MAK_LAUNCH_CHECK(h, "extract_r_kernel");
+        }
+    }
+    return orgqr_blocked<T>(h, m, ncq, k, A, lda, Q, ldq, w);
+}
+
+template <typename T>
+int geqrf_t(makb200_handle* h, int m, int n, T* A, int lda, T* tau, void* work, size_t lwork) {
+    const int k = m < n ? m : n;
+    Arena ar(work, lwork);
+    QrWork<T> w;
+    qr_carve<T>(h, ar, m, n, k, &w);
+    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    int rc = geqrf_blocked<T>(h, m, n, A, lda, w);
+    if (rc) return rc;
+    if (k > 0) MAK_CUDA(h, cudaMemcpyAsync(tau, w.tau, sizeof(T) * k, cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+
+// rebuild the T factors of every outer block from V and tau (larft), for the L1 orgqr entry
+template <typename T>
+__global__ void larft_diag_kernel(int jb, const T* __restrict__ tau, T* __restrict__ Tm, int ldt,
+                                  const T* __restrict__ G, int ldg) {
+    // single CTA: T[j][j] = tau_j; T[0:j, j] = -tau_j * T[0:j,0:j] * G[0:j, j]   (G = V^H V)
+    for (int j = 0; j < jb; ++j) {
+        T tj = tau[j];
+        for (int i = threadIdx.x; i < j; i += blockDim.x) {
+            T s = zero<T>();
+            for (int p = i; p < j; ++p) fma_(s, Tm[(size_t)p * ldt + i], G[(size_t)j * ldg + p]);
+            Tm[(size_t)j * ldt + i] = neg_(mul_(tj, s));
+        }
+        if (threadIdx.x == 0) Tm[(size_t)j * ldt + j] = tj;
+        __syncthreads();
+    }
+}
+
+template <typename T>
+int orgqr_t(makb200_handle* h, int m, int ncols, int k, const T* A, int lda, const T* tau, T* Q, int ldq, void* work,
+            size_t lwork) {
+    Arena ar(work, lwork);
+    QrWork<T> w;
+    qr_carve<T>(h, ar, m, k, ncols, &w);
+    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    cudaStream_t s = h->stream;
+    const int nb = w.nb;
+    const int nblk = (k + nb - 1) / nb;
+    if (k > 0) {
+        MAK_CUDA(h, cudaMemsetAsync(w.Tall, 0, sizeof(T) * (size_t)nb * nb * nblk, s));
+        for (int b = 0; b < nblk; ++b) {
+            const int j0 = b * nb;
+            const int jb = (k - j0 < nb) ? (k - j0) : nb;
+            const int mp = m - j0;
+            copy_v_kernel<T><<<grid_for((size_t)mp * jb, h->num_sms), 256, 0, s>>>(
+                mp, jb, 0, A + (size_t)j0 * lda + j0, lda, w.Vw, mp);
+            MAK_LAUNCH_CHECK(h, "copy_v_kernel");
+            MAK_GEMM(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, jb, jb, mp, one<T>(), w.Vw, mp, w.Vw, mp, zero<T>(),
+                     w.G, nb, w.ws, w.ws_bytes);
+            larft_diag_kernel<T><<<1, 128, 0, s>>>(jb, tau + j0, w.Tall + (size_t)b * nb * nb, nb, w.G, nb);
+            MAK_LAUNCH_CHECK(h, "larft_diag_kernel");
+        }
+    }
+    return orgqr_blocked<T>(h, m, ncols, k, A, lda, Q, ldq, w);
+}
+
+#define INST(T)                                                                                            \
+    template size_t qr_worksize_t<T>(makb200_handle*, int, int, int);                                      \
+    template int qr_fused_t<T>(makb200_handle*, int, int, int, T*, int, T*, int, T*, int, void*, size_t);  \
+    template int geqrf_t<T>(makb200_handle*, int, int, T*, int, T*, void*, size_t);                        \
+    template int orgqr_t<T>(makb200_handle*, int, int, int, const T*, int, const T*, T*, int, void*, size_t);
+INST(double)
+INST(cplx)
+
+}  // namespace mak

@@ -1,0 +1,146 @@
+"""qr_compact / qr_full on B200 — mirrors src/implementations/qr.jl of the reference:
+``check_input`` (:9-29), ``initialize_output`` (:63-75), ``qr_householder!(driver, A, Q, R;
+positive, pivoted, blocksize)`` (:132-188).  Python has no ``!``: the in-place, preallocated-
+output entry points carry a trailing underscore (``qr_compact_(A, (Q, R), alg)``)."""
+import ctypes as C
+
+import torch
+
+from . import _core, _lib
+from .algorithms import Algorithm, B200, resolve_driver, select_algorithm
+
+
+def _check_matrix(A, name="A"):
+    if not isinstance(A, torch.Tensor) or A.dim() != 2:
+        raise TypeError(f"{name}: 2-d device tensor expected")
+    if not _core.is_colmajor(A):
+        raise ValueError(f"{name}: column-major matrix with unit stride in dim 1 expected (chkstride1)")
+    _core.dtype_code(A)
+
+
+def initialize_output(f, A, alg=None):
+    """``initialize_output(qr_full!/qr_compact!, A, alg)`` (qr.jl:63-75)."""
+    m, n = A.shape
+    k = min(m, n)
+    if f == "qr_full":
+        return (_core.colmajor_empty(m, m, A.dtype, A.device), _core.colmajor_empty(m, n, A.dtype, A.device))
+    return (_core.colmajor_empty(m, k, A.dtype, A.device), _core.colmajor_empty(k, n, A.dtype, A.device))
+
+
+def check_input(f, A, QR, alg=None):
+    """``check_input`` (qr.jl:9-29): DimensionMismatch -> ValueError. A zero-length R means
+    "R not requested" (qr.jl:15,26)."""
+    _check_matrix(A)
+    m, n = A.shape
+    k = min(m, n)
+    Q, R = QR
+    _check_matrix(Q, "Q")
+    nq = m if f == "qr_full" else k
+    if tuple(Q.shape) != (m, nq):
+        raise ValueError(f"Q: size {tuple(Q.shape)} != {(m, nq)}")
+    if Q.dtype != A.dtype:
+        raise TypeError("Q: eltype mismatch")
+    if R is not None and R.numel() > 0:
+        _check_matrix(R, "R")
+        if tuple(R.shape) != (nq, n):
+            raise ValueError(f"R: size {tuple(R.shape)} != {(nq, n)}")
+        if R.dtype != A.dtype:
+            raise TypeError("R: eltype mismatch")
+
+
+def qr_householder_(A, Q, R, driver=None, positive=True, pivoted=False, blocksize=0, mode=_lib.QR_COMPACT):
+    """``qr_householder!(::B200, A, Q, R; positive, pivoted, blocksize)``: one fused C-ABI call
+    (factorization, R extraction and Q formation; the gauge is built into the reflectors)."""
+    driver = resolve_driver(driver, A)
+    assert isinstance(driver, B200)
+    # capability negatives are thrown, not ignored (qr.jl:140-145; tests assert the throw)
+    if pivoted:
+        raise ValueError(f"{driver} does not provide a pivoted QR decomposition")
+    if blocksize not in (0, 1):
+        # the kernels choose their own (two-level) blocking; a user block size is not an option
+        raise ValueError(f"{driver} does not provide a blocked QR decomposition with user block size")
+    if Q.data_ptr() == A.data_ptr() and A.numel() > 0:
+        raise ValueError("inplace Q is not supported by the B200 driver")
+    m, n = A.shape
+    h = _core.Handle.get(A.device)
+    dt = _core.dtype_code(A)
+    compute_r = R is not None and R.numel() > 0
+    lw = h.lib.makb200_qr_worksize(h.h, dt, mode, m, n)
+    work = h.workspace(lw)
+    rc = h.lib.makb200_qr(h.h, dt, mode, int(bool(positive)), m, n, _core.ptr(A), _core.ld(A), _core.ptr(Q),
+                          _core.ld(Q), _core.ptr(R) if compute_r else C.c_void_p(0),
+                          _core.ld(R) if compute_r else 0, _core.ptr(work), work.numel())
+    h.check(rc, "makb200_qr")
+    return Q, R
+
+
+def _alg_kwargs(alg):
+    if not isinstance(alg, Algorithm) or alg.name != "Householder":
+        raise ValueError(f"qr: algorithm {alg} is not available on the B200 driver")
+    return {k: v for k, v in alg.kwargs.items()}
+
+
+def qr_compact_(A, QR=None, alg=None, **kw):
+    """``qr_compact!(A, (Q,R), alg)`` (qr.jl:110-113). Destroys A; returns the objects given."""
+    alg = select_algorithm("qr_compact", A, alg, **kw)
+    if QR is None:
+        QR = initialize_output("qr_compact", A, alg)
+    check_input("qr_compact", A, QR, alg)
+    return qr_householder_(A, QR[0], QR[1], mode=_lib.QR_COMPACT, **_alg_kwargs(alg))
+
+
+def qr_full_(A, QR=None, alg=None, **kw):
+    """``qr_full!(A, (Q,R), alg)`` (qr.jl:106-109)."""
+    alg = select_algorithm("qr_full", A, alg, **kw)
+    if QR is None:
+        QR = initialize_output("qr_full", A, alg)
+    check_input("qr_full", A, QR, alg)
+    return qr_householder_(A, QR[0], QR[1], mode=_lib.QR_FULL, **_alg_kwargs(alg))
+
+
+def copy_input(A):
+    """``copy_input`` (qr.jl:3-4): fresh column-major float copy; integer input is converted."""
+    if not A.dtype.is_floating_point and not A.dtype.is_complex:
+        A = A.to(torch.float64)
+    out = _core.colmajor_empty(A.shape[0], A.shape[1], A.dtype, A.device)
+    out.copy_(A)
+    return out
+
+
+def qr_compact(A, alg=None, **kw):
+    """out-of-place ``qr_compact(A; alg, kw...)``: input untouched (algorithms.jl:355-370)."""
+    return qr_compact_(copy_input(A), None, alg, **kw)
+
+
+def qr_full(A, alg=None, **kw):
+    return qr_full_(copy_input(A), None, alg, **kw)
+
+
+def qr_compact_batched_(As, QRs=None):
+    """Batched ``qr_compact!`` over a list of blocks (new capability; per-block semantics)."""
+    if len(As) == 0:
+        return []
+    dev, dtype = As[0].device, As[0].dtype
+    h = _core.Handle.get(dev)
+    dt = _core.dtype_code(As[0])
+    if QRs is None:
+        QRs = [initialize_output("qr_compact", A) for A in As]
+    b = len(As)
+    IA = C.c_int * b
+    VP = C.c_void_p * b
+    for A, QR in zip(As, QRs):
+        check_input("qr_compact", A, QR)
+    m = IA(*[A.shape[0] for A in As])
+    n = IA(*[A.shape[1] for A in As])
+    lda = IA(*[_core.ld(A) for A in As])
+    ldq = IA(*[_core.ld(Q) for Q, _ in QRs])
+    ldr = IA(*[_core.ld(R) if R is not None and R.numel() else 0 for _, R in QRs])
+    Ap = VP(*[A.data_ptr() for A in As])
+    Qp = VP(*[Q.data_ptr() for Q, _ in QRs])
+    Rp = VP(*[(R.data_ptr() if R is not None and R.numel() else 0) for _, R in QRs])
+    lw = h.lib.makb200_qr_batched_worksize(h.h, dt, b, m, n)
+    work = h.workspace(lw)
+    rc = h.lib.makb200_qr_batched(h.h, dt, b, m, n, Ap, lda, Qp, ldq, Rp, ldr, C.c_void_p(0), _core.ptr(work),
+                                  work.numel())
+    h.check(rc, "makb200_qr_batched")
+    return QRs
