@@ -86,6 +86,27 @@ int makb200_qr_batched(makb200_handle_t* h, int dtype, int batch, const int* m, 
                        void* const* A, const int* lda, void* const* Q, const int* ldq,
                        void* const* R, const int* ldr, int* info, void* work, size_t lwork);
 
+/* -- eigh_full! ------------------------------------------------------------------------
+ * makb200_hermitian_defect: the device half of check_hermitian (implementations/eigh.jl:11-18,
+ *   matrixproperties.jl:150-172; MatrixAlgebraKitCUDAExt.jl:147-152): out2_dev[0] =
+ *   ||(A - A^H)/2||_F^2, out2_dev[1] = max |A_ij| (for default_hermitian_tol, defaults.jl:44).
+ * makb200_eigh: replaces heevd!/heevr! + gaugefix!(eigh_full!) (yalapack.jl:1164-1362,
+ *   yacusolver.jl:766-810, common/gauge.jl:38-45).  Only the upper triangle of A is read
+ *   (uplo='U', yalapack.jl:994,1286); A is destroyed.  W: n real eigenvalues ascending;
+ *   V: n x n eigenvectors (must not alias A).  info_dev: optional DEVICE int, >0 if the
+ *   tridiagonal solver failed to converge.
+ *   Pipeline: blocked Householder tridiagonalisation (HBM-bound column-dot kernel + DMMA her2k),
+ *   tridiagonal divide & conquer (makb200_stedc), compact-WY back-transformation, fused gauge. */
+int makb200_hermitian_defect(makb200_handle_t* h, int dtype, int n, const void* A, int lda,
+                             double* out2_dev);
+size_t makb200_eigh_worksize(makb200_handle_t* h, int dtype, int n);
+int makb200_eigh(makb200_handle_t* h, int dtype, int fixgauge, int n, void* A, int lda, double* W,
+                 void* V, int ldv, void* work, size_t lwork, int* info_dev);
+/* symmetric tridiagonal divide & conquer (stedc class): d[n], e[n-1] -> W ascending, Z n x n */
+size_t makb200_stedc_worksize(makb200_handle_t* h, int n);
+int makb200_stedc(makb200_handle_t* h, int n, const double* d, const double* e, double* W, double* Z,
+                  int ldz, void* work, size_t lwork, int* info_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,3 +10,7 @@ from .algorithms import *  # noqa: F401,F403
 from .algorithms import (Algorithm, TruncatedAlgorithm, default_algorithm, select_algorithm)
 from .gemm import gemm_
 from .qr import (qr_compact, qr_compact_, qr_compact_batched_, qr_full, qr_full_, qr_householder_)
+from .eigh import (DomainError, check_hermitian, eigh_full, eigh_full_, eigh_trunc, eigh_trunc_, eigh_vals,
+                   eigh_vals_)
+from .truncation import (findtruncated, findtruncated_svd, notrunc, select_truncation, trunc_and, trunc_or,
+                         truncerror, truncrank, trunctol)

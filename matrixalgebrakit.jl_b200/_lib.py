@@ -33,6 +33,11 @@ SIGNATURES = {
     "makb200_qr": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _sz]),
     "makb200_qr_batched_worksize": (_sz, [_vp, _i, _i, _ip, _ip]),
     "makb200_qr_batched": (_i, [_vp, _i, _i, _ip, _ip, _vpp, _ip, _vpp, _ip, _vpp, _ip, _vp, _vp, _sz]),
+    "makb200_hermitian_defect": (_i, [_vp, _i, _i, _vp, _i, _vp]),
+    "makb200_eigh_worksize": (_sz, [_vp, _i, _i]),
+    "makb200_eigh": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _sz, _vp]),
+    "makb200_stedc_worksize": (_sz, [_vp, _i]),
+    "makb200_stedc": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmakb200.so")
-SOURCES = ["gemm.cu", "qr.cu", "batched.cu", "capi.cu"]
+SOURCES = ["gemm.cu", "qr.cu", "batched.cu", "stedc.cu", "eigh.cu", "capi.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC"]
 
@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
     if force or procs or not os.path.exists(LIB):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart"]
         subprocess.check_call(cmd)
     return LIB
 

@@ -6,20 +6,6 @@
 
 namespace mak {
 
-template <typename T>
-__host__ __device__ __forceinline__ void larfgp_scalars_b(T alpha, double sigma, double& beta, T& tau, T& scale) {
-    if (sigma == 0.0 && imag_(alpha) == 0.0 && real_(alpha) >= 0.0) {
-        beta = real_(alpha); tau = zero<T>(); scale = zero<T>();
-        return;
-    }
-    beta = sqrt(abs2_(alpha) + sigma);
-    T d;
-    if (real_(alpha) < 0.0) d = sub_(alpha, mk<T>(beta));
-    else d = div_(sub_(scale_(sub_(alpha, conj_(alpha)), beta), mk<T>(sigma)), add_(conj_(alpha), mk<T>(beta)));
-    tau = scale_(neg_(d), 1.0 / beta);
-    scale = div_(one<T>(), d);
-}
-
 constexpr int BQ_THREADS = 256;
 constexpr size_t BQ_SMEM_BYTES = 200 * 1024;
 
@@ -56,7 +42,7 @@ batched_qr_kernel(const QrBlockDesc<T>* __restrict__ descs, int* __restrict__ in
         for (int r = j + 1 + tid; r < m; r += BQ_THREADS) part += abs2_(cj[r]);
         T tot = block_sum<T>(mk<T>(part), red);
         double beta; T tj, scale;
-        larfgp_scalars_b<T>(cj[j], real_(tot), beta, tj, scale);
+        larfgp_scalars<T>(cj[j], real_(tot), beta, tj, scale);
         __syncthreads();  // everyone has read cj[j]
         for (int r = j + 1 + tid; r < m; r += BQ_THREADS) cj[r] = mul_(cj[r], scale);
         if (tid == 0) { cj[j] = mk<T>(beta); tau[j] = tj; }

@@ -4,6 +4,8 @@
 #include "gemm.cuh"
 #include "qr.cuh"
 #include "batched.cuh"
+#include "eigh.cuh"
+#include "stedc.cuh"
 #include <vector>
 
 using mak::cplx;
@@ -230,6 +232,58 @@ int makb200_qr_batched(makb200_handle_t* h, int dtype, int batch, const int* m, 
     if (!ldq) return -9;
     if (dtype == MAKB200_F64) return qr_batched_t<double>(h, batch, m, n, A, lda, Q, ldq, R, ldr, info, work, lwork);
     return qr_batched_t<cplx>(h, batch, m, n, A, lda, Q, ldq, R, ldr, info, work, lwork);
+}
+
+
+// ---- eigh ---------------------------------------------------------------------------
+int makb200_hermitian_defect(makb200_handle_t* h, int dtype, int n, const void* A, int lda, double* out2_dev) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (n < 0) return -3;
+    if (lda < maxi(1, n)) return -5;
+    if (!out2_dev) return -6;
+    if (n > 0 && !A) return -4;
+    if (dtype == MAKB200_F64) return mak::herm_defect_t<double>(h, n, (const double*)A, lda, out2_dev);
+    return mak::herm_defect_t<cplx>(h, n, (const cplx*)A, lda, out2_dev);
+}
+
+size_t makb200_eigh_worksize(makb200_handle_t* h, int dtype, int n) {
+    if (!h || !dtype_ok(dtype) || n < 0) return 0;
+    return dtype == MAKB200_F64 ? mak::eigh_worksize_t<double>(h, n) : mak::eigh_worksize_t<cplx>(h, n);
+}
+
+int makb200_eigh(makb200_handle_t* h, int dtype, int fixgauge, int n, void* A, int lda, double* W, void* V, int ldv,
+                 void* work, size_t lwork, int* info_dev) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (n < 0) return -4;
+    if (lda < maxi(1, n)) return -6;
+    if (ldv < maxi(1, n)) return -9;
+    if (n == 0) return 0;
+    if (!A) return -5;
+    if (!W) return -7;
+    if (!V || V == A) return -8;
+    if (dtype == MAKB200_F64)
+        return mak::eigh_t<double>(h, n, (double*)A, lda, W, (double*)V, ldv, fixgauge, work, lwork, info_dev);
+    return mak::eigh_t<cplx>(h, n, (cplx*)A, lda, W, (cplx*)V, ldv, fixgauge, work, lwork, info_dev);
+}
+
+size_t makb200_stedc_worksize(makb200_handle_t* h, int n) {
+    if (!h || n < 0) return 0;
+    return mak::stedc_worksize(n);
+}
+
+int makb200_stedc(makb200_handle_t* h, int n, const double* d, const double* e, double* W, double* Z, int ldz,
+                  void* work, size_t lwork, int* info_dev) {
+    if (!h) return -1;
+    if (n < 0) return -2;
+    if (ldz < maxi(1, n)) return -7;
+    if (n == 0) return 0;
+    if (!d) return -3;
+    if (n > 1 && !e) return -4;
+    if (!W) return -5;
+    if (!Z) return -6;
+    return mak::stedc(h, n, d, e, W, Z, ldz, work, lwork, info_dev);
 }
 
 }  // extern "C"

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <math.h>
+#include <stdlib.h>
 #include "../../include/makb200.h"
 
 namespace mak {
@@ -81,6 +82,30 @@ __host__ __device__ __forceinline__ bool is_zero(cplx a) { return a.re == 0.0 &&
 __host__ __device__ __forceinline__ bool is_one(double a) { return a == 1.0; }
 __host__ __device__ __forceinline__ bool is_one(cplx a) { return a.re == 1.0 && a.im == 0.0; }
 
+// stable non-negative-beta reflector scalars: given alpha = x[0], sigma = ||x[1:]||^2
+// returns beta >= 0, tau, scale with v = x[1:]*scale, H = I - tau*[1;v][1;v]^H, H^H x = beta e1.
+template <typename T>
+__host__ __device__ __forceinline__ void larfgp_scalars(T alpha, double sigma, double& beta, T& tau, T& scale) {
+    if (sigma == 0.0 && imag_(alpha) == 0.0 && real_(alpha) >= 0.0) {
+        beta = real_(alpha);
+        tau = zero<T>();
+        scale = zero<T>();
+        return;
+    }
+    beta = sqrt(abs2_(alpha) + sigma);
+    T d;
+    if (real_(alpha) < 0.0) {
+        d = sub_(alpha, mk<T>(beta));
+    } else {
+        // alpha - beta = ((alpha - conj(alpha))*beta - sigma) / (conj(alpha) + beta)
+        T num = sub_(scale_(sub_(alpha, conj_(alpha)), beta), mk<T>(sigma));
+        T den = add_(conj_(alpha), mk<T>(beta));
+        d = div_(num, den);
+    }
+    tau = scale_(neg_(d), 1.0 / beta);
+    scale = div_(one<T>(), d);
+}
+
 // ---------------------------------------------------------------------------------------
 // warp / block reductions (deterministic order)
 // ---------------------------------------------------------------------------------------
@@ -142,6 +167,38 @@ inline int cuda_fail(makb200_handle* h, cudaError_t e, const char* where) {
         cudaError_t _e = cudaGetLastError();                        \
         if (_e != cudaSuccess) return mak::cuda_fail(h, _e, name);  \
     } while (0)
+
+// optional phase timing (env MAKB200_PROFILE=1): prints device time per phase to stderr.
+struct PhaseTimer {
+    bool on;
+    cudaStream_t s;
+    cudaEvent_t ev[16];
+    const char* names[16];
+    int n;
+    explicit PhaseTimer(cudaStream_t st) : s(st), n(0) {
+        const char* e = getenv("MAKB200_PROFILE");
+        on = e && e[0] == '1';
+    }
+    void mark(const char* name) {
+        if (!on || n >= 16) return;
+        cudaEventCreate(&ev[n]);
+        cudaEventRecord(ev[n], s);
+        names[n++] = name;
+    }
+    void report(const char* what) {
+        if (!on || n < 2) return;
+        cudaEventSynchronize(ev[n - 1]);
+        fprintf(stderr, "[makb200 profile] %s:", what);
+        for (int i = 1; i < n; ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            fprintf(stderr, " %s=%.3fms", names[i], ms);
+        }
+        fprintf(stderr, "\n");
+        for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+        n = 0;
+    }
+};
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -1,0 +1,507 @@
+// Hermitian eigensolver: eigh_full!  (replaces heevd!/heevr!, yalapack.jl:1164-1362,
+// yacusolver.jl:766-810).
+//   1. mirror the upper triangle (LAPACK is called with uplo='U': only it is read)
+//   2. hetrd: blocked Householder tridiagonalisation; per column two kernels
+//        (a) all column dot products of the step in ONE pass over the trailing matrix
+//            (y = A22 v, W^H v, V^H v, y^H v) — HBM-bound, the dominant kernel;
+//        (b) w, write-back of v, left-looking update of the next column and its norm;
+//      per panel one DMMA GEMM  A22 -= [V W][W V]^H  (her2k as a single K = 2*nb product)
+//   3. stedc (stedc.cu): tridiagonal divide and conquer, GEMM-rich merges
+//   4. back-transform V = Q Z with compact-WY block reflectors (DMMA GEMMs, qr.cu)
+//   5. eigenvector gauge (common/gauge.jl:38-45) fused into one launch
+#include "eigh.cuh"
+#include "gemm.cuh"
+#include "qr.cuh"
+#include "stedc.cuh"
+
+namespace mak {
+
+constexpr int TRD_NB = 64;
+
+// ---------------------------------------------------------------------------------------
+// Hermitian defect and mirroring
+// ---------------------------------------------------------------------------------------
+// out[0] += sum |(A - A^H)/2|^2 ; out[1] = max |A_ij|  (atomics: only used for a threshold test)
+template <typename T>
+__global__ void herm_defect_kernel(int n, const T* __restrict__ A, int lda, double* out) {
+    __shared__ T tile[32][33];
+    __shared__ double red[32];
+    const int bi = blockIdx.x, bj = blockIdx.y;
+    if (bj > bi) return;  // lower block pairs only
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    // tile (bj, bi): rows bj*32.., cols bi*32..  -> stored transposed-access friendly
+    for (int k = ty; k < 32; k += 8) {
+        int r = bj * 32 + tx, c = bi * 32 + k;
+        tile[k][tx] = (r < n && c < n) ? A[(size_t)c * lda + r] : zero<T>();
+    }
+    __syncthreads();
+    double part = 0.0, mx = 0.0;
+    for (int k = ty; k < 32; k += 8) {
+        int r = bi * 32 + tx, c = bj * 32 + k;  // element (r,c) of tile (bi,bj); partner (c,r) = tile[tx][k]
+        if (r < n && c < n) {
+            T a = A[(size_t)c * lda + r];
+            T b = conj_(tile[tx][k]);
+            T dlt = sub_(a, b);
+            double w = (bi == bj) ? 1.0 : 2.0;  // off-diagonal block pairs count twice
+            part += w * 0.25 * abs2_(dlt);
+            mx = fmax(mx, fmax(sqrt(abs2_(a)), sqrt(abs2_(b))));
+        }
+    }
+    const int t = ty * 32 + tx;
+    part = warp_sum(part);
+    mx = warp_max(mx);
+    if ((t & 31) == 0) red[t >> 5] = part;
+    __syncthreads();
+    if (t == 0) {
+        double s = 0.0;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        atomicAdd(out, s);
+    }
+    __syncthreads();
+    if ((t & 31) == 0) red[t >> 5] = mx;
+    __syncthreads();
+    if (t == 0) {
+        double m2 = 0.0;
+        for (int i = 0; i < 8; ++i) m2 = fmax(m2, red[i]);
+        // non-negative doubles order like their bit patterns
+        atomicMax((unsigned long long*)(out + 1), (unsigned long long)__double_as_longlong(m2));
+    }
+}
+
+// lower <- conj(upper); diagonal made real
+template <typename T>
+__global__ void mirror_upper_kernel(int n, T* __restrict__ A, int lda) {
+    __shared__ T tile[32][33];
+    const int bi = blockIdx.x, bj = blockIdx.y;  // upper block (bi <= bj): rows bi*32, cols bj*32
+    if (bi > bj) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int k = ty; k < 32; k += 8) {
+        int r = bi * 32 + tx, c = bj * 32 + k;
+        tile[k][tx] = (r < n && c < n) ? A[(size_t)c * lda + r] : zero<T>();
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        int r = bj * 32 + tx, c = bi * 32 + k;  // lower element (r,c) = conj(upper (c,r)) = conj(tile[tx][k])
+        if (r < n && c < n) {
+            if (r > c) A[(size_t)c * lda + r] = conj_(tile[tx][k]);
+            else if (r == c) A[(size_t)c * lda + r] = mk<T>(real_(tile[tx][k]));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// hetrd
+// ---------------------------------------------------------------------------------------
+template <typename T>
+struct TrdCtx {
+    int n;
+    T* A; int lda;
+    T* P; int ldp;   // panel [V | W | V], each pw columns wide
+    int pw;
+    T* y;            // n
+    T* t;            // 2*TRD_NB : t1 = W^H v, t2 = V^H v
+    double* pn;      // partial tail norms of the current column
+    T* pyv;          // partial y^H v
+    T* tau; double* d; double* e;
+};
+
+constexpr int TRD_K1_THREADS = 256;   // 8 warps x 4 columns
+constexpr int TRD_K1_COLS = 32;
+constexpr int TRD_K2_ROWS = 64;       // rows per CTA, 4 threads (p-groups) per row
+
+// partial tail norms of column c (rows >= c+2), used at panel starts
+template <typename T>
+__global__ void trd_colnorm_kernel(TrdCtx<T> x, int c) {
+    __shared__ double red[32];
+    const int r = c + 1 + blockIdx.x * TRD_K2_ROWS + (threadIdx.x % TRD_K2_ROWS);
+    double part = 0.0;
+    if (threadIdx.x < TRD_K2_ROWS && r < x.n && r >= c + 2) part = abs2_(x.A[(size_t)c * x.lda + r]);
+    double tot = block_sum<double>(part, red);
+    if (threadIdx.x == 0) x.pn[blockIdx.x] = tot;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TRD_K1_THREADS)
+trd_dots_kernel(TrdCtx<T> x, int c, int i, int npn) {
+    __shared__ T redT[32];
+    const int n = x.n, row0 = c + 1, mt = n - row0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // reflector scalars (every thread, identical arithmetic)
+    double sigma = 0.0;
+    for (int q = 0; q < npn; ++q) sigma += x.pn[q];
+    const T* acol = x.A + (size_t)c * x.lda + row0;
+    const T alpha = acol[0];
+    double beta; T tau, scale;
+    larfgp_scalars<T>(alpha, sigma, beta, tau, scale);
+
+    const int ncols = mt + 2 * i;
+    const int q0 = (blockIdx.x * 8 + warp) * 4;
+    const T* col[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int q = q0 + k;
+        if (q < mt) col[k] = x.A + (size_t)(row0 + q) * x.lda + row0;
+        else if (q < mt + i) col[k] = x.P + (size_t)(x.pw + (q - mt)) * x.ldp + row0;
+        else if (q < ncols) col[k] = x.P + (size_t)(q - mt - i) * x.ldp + row0;
+        else col[k] = nullptr;
+    }
+    T acc[4] = {zero<T>(), zero<T>(), zero<T>(), zero<T>()};
+    if (q0 < ncols) {
+        for (int r = lane; r < mt; r += 32) {
+            T vr = (r == 0) ? one<T>() : mul_(acol[r], scale);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (col[k]) fmac_(acc[k], col[k][r], vr);
+        }
+    }
+    T pyv = zero<T>();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        acc[k] = warp_sum(acc[k]);
+        int q = q0 + k;
+        if (lane == 0 && q < ncols) {
+            if (q < mt) {
+                x.y[row0 + q] = acc[k];
+                T vq = (q == 0) ? one<T>() : mul_(acol[q], scale);
+                fmac_(pyv, acc[k], vq);  // conj(y_q) * v_q
+                x.P[(size_t)i * x.ldp + row0 + q] = vq;                  // V(:, i)
+                x.P[(size_t)(2 * x.pw + i) * x.ldp + row0 + q] = vq;     // second copy
+            } else if (q < mt + i) {
+                x.t[q - mt] = acc[k];                 // t1 = W^H v
+            } else {
+                x.t[TRD_NB + (q - mt - i)] = acc[k];  // t2 = V^H v
+            }
+        }
+    }
+    // CTA partial of y^H v (lane 0 of each warp holds its share)
+    __syncthreads();
+    if (lane == 0) redT[warp] = pyv;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T s = zero<T>();
+        for (int w = 0; w < TRD_K1_THREADS / 32; ++w) s = add_(s, redT[w]);
+        x.pyv[blockIdx.x] = s;
+        if (blockIdx.x == 0) {
+            x.tau[c] = tau;
+            x.e[c] = beta;
+            x.d[c] = real_(x.A[(size_t)c * x.lda + c]);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+trd_w_kernel(TrdCtx<T> x, int c, int i, int npyv, int do_next) {
+    __shared__ T sm[4][TRD_K2_ROWS];
+    __shared__ T st[2 * TRD_NB];       // t1, t2
+    __shared__ T srow[2 * TRD_NB + 2]; // conj(W[c1,p]), conj(V[c1,p]) incl. the new column
+    __shared__ T sscal[4];
+    __shared__ double red[32];
+    const int n = x.n, row0 = c + 1;
+    const int tx = threadIdx.x % TRD_K2_ROWS, ty = threadIdx.x / TRD_K2_ROWS;
+    const int r = row0 + blockIdx.x * TRD_K2_ROWS + tx;
+    const bool live = r < n;
+    const T tauc = x.tau[c];
+    for (int p = threadIdx.x; p < i; p += blockDim.x) {
+        st[p] = x.t[p];
+        st[TRD_NB + p] = x.t[TRD_NB + p];
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        // alpha2 = -(tau/2) * w^H v,  w^H v = conj(tau) * (y^H v - t1^H t2 - t2^H t1)
+        const int lane = threadIdx.x;
+        T yhv = zero<T>();
+        for (int q = lane; q < npyv; q += 32) yhv = add_(yhv, x.pyv[q]);
+        T s12 = zero<T>();
+        for (int p = lane; p < i; p += 32) {
+            fmac_(s12, st[p], st[TRD_NB + p]);
+            fmac_(s12, st[TRD_NB + p], st[p]);
+        }
+        // first row of w (row c+1): y - V t1 - W t2
+        T sf = zero<T>();
+        for (int p = lane; p < i; p += 32) {
+            fma_(sf, x.P[(size_t)p * x.ldp + row0], st[p]);
+            fma_(sf, x.P[(size_t)(x.pw + p) * x.ldp + row0], st[TRD_NB + p]);
+        }
+        yhv = warp_sum(yhv);
+        s12 = warp_sum(s12);
+        sf = warp_sum(sf);
+        if (lane == 0) {
+            T whv = mul_(conj_(tauc), sub_(yhv, s12));
+            T alpha2 = neg_(scale_(mul_(tauc, whv), 0.5));
+            T wfirst = add_(mul_(tauc, sub_(x.y[row0], sf)), alpha2);  // v[row0] = 1
+            sscal[0] = alpha2;
+            sscal[1] = wfirst;
+        }
+    }
+    __syncthreads();
+    const T alpha2 = sscal[0], wfirst = sscal[1];
+    // ---- w[r] ----
+    T part = zero<T>();
+    if (live) {
+        for (int p = ty; p < i; p += 4) {
+            fma_(part, x.P[(size_t)p * x.ldp + r], st[p]);
+            fma_(part, x.P[(size_t)(x.pw + p) * x.ldp + r], st[TRD_NB + p]);
+        }
+    }
+    sm[ty][tx] = part;
+    __syncthreads();
+    T vr = zero<T>(), wr = zero<T>();
+    if (live) {
+        T s = add_(add_(sm[0][tx], sm[1][tx]), add_(sm[2][tx], sm[3][tx]));
+        vr = x.P[(size_t)i * x.ldp + r];
+        wr = add_(mul_(tauc, sub_(x.y[r], s)), mul_(alpha2, vr));
+        if (ty == 0) {
+            x.P[(size_t)(x.pw + i) * x.ldp + r] = wr;                              // W(:, i)
+            x.A[(size_t)c * x.lda + r] = (r == row0) ? mk<T>(x.e[c]) : vr;          // reflector storage
+        }
+    }
+    if (!do_next) return;
+    // ---- left-looking update of column c1 = c+1 and its tail norm ----
+    const int c1 = c + 1;
+    for (int p = threadIdx.x; p < i; p += blockDim.x) {
+        srow[p] = conj_(x.P[(size_t)(x.pw + p) * x.ldp + c1]);          // conj(W[c1,p])
+        srow[TRD_NB + 1 + p] = conj_(x.P[(size_t)p * x.ldp + c1]);      // conj(V[c1,p])
+    }
+    __syncthreads();
+    part = zero<T>();
+    if (live) {
+        for (int p = ty; p < i; p += 4) {
+            fma_(part, x.P[(size_t)p * x.ldp + r], srow[p]);
+            fma_(part, x.P[(size_t)(x.pw + p) * x.ldp + r], srow[TRD_NB + 1 + p]);
+        }
+    }
+    sm[ty][tx] = part;
+    __syncthreads();
+    double nrm = 0.0;
+    if (live && ty == 0) {
+        T s = add_(add_(sm[0][tx], sm[1][tx]), add_(sm[2][tx], sm[3][tx]));
+        // new column p = i: V[r,i] conj(W[c1,i]) + W[r,i] conj(V[c1,i]),  V[c1,i] = 1
+        fma_(s, vr, conj_(wfirst));
+        s = add_(s, wr);
+        T a = sub_(x.A[(size_t)c1 * x.lda + r], s);
+        if (r == c1) a = mk<T>(real_(a));
+        x.A[(size_t)c1 * x.lda + r] = a;
+        if (r >= c1 + 2) nrm = abs2_(a);
+    }
+    double tot = block_sum<double>(nrm, red);
+    if (threadIdx.x == 0) x.pn[blockIdx.x] = tot;
+}
+
+template <typename T>
+__global__ void trd_last_d_kernel(TrdCtx<T> x) {
+    x.d[x.n - 1] = real_(x.A[(size_t)(x.n - 1) * x.lda + (x.n - 1)]);
+}
+
+template <typename T, typename AR>
+static void trd_carve(AR& ar, int n, TrdCtx<T>* x) {
+    size_t nn = (size_t)(n > 0 ? n : 1);
+    x->n = n;
+    x->P = ar.template get<T>(nn * 3 * TRD_NB);
+    x->ldp = n > 0 ? n : 1;
+    x->y = ar.template get<T>(nn);
+    x->t = ar.template get<T>(2 * TRD_NB);
+    x->pn = ar.template get<double>(nn / TRD_K2_ROWS + 2);
+    x->pyv = ar.template get<T>((nn + 2 * TRD_NB) / TRD_K1_COLS + 2);
+    x->tau = ar.template get<T>(nn);
+    x->d = ar.template get<double>(nn);
+    x->e = ar.template get<double>(nn);
+}
+
+template <typename T>
+static int hetrd(makb200_handle* h, TrdCtx<T>& x) {
+    const int n = x.n;
+    cudaStream_t s = h->stream;
+    if (n == 1) {
+        trd_last_d_kernel<T><<<1, 1, 0, s>>>(x);
+        return 0;
+    }
+    for (int j0 = 0; j0 < n - 1; j0 += TRD_NB) {
+        const int ncols = (n - 1 - j0 < TRD_NB) ? (n - 1 - j0) : TRD_NB;
+        x.pw = ncols;
+        int npn;  // grid size of whichever kernel produced the partial norms of the current column
+        {
+            int mt = n - j0 - 1;
+            npn = (mt + TRD_K2_ROWS - 1) / TRD_K2_ROWS;
+            trd_colnorm_kernel<T><<<npn, 256, 0, s>>>(x, j0);
+        }
+        for (int i = 0; i < ncols; ++i) {
+            const int c = j0 + i, mt = n - c - 1;
+            const int g2 = (mt + TRD_K2_ROWS - 1) / TRD_K2_ROWS;
+            const int g1 = (mt + 2 * i + TRD_K1_COLS - 1) / TRD_K1_COLS;
+            trd_dots_kernel<T><<<g1, TRD_K1_THREADS, 0, s>>>(x, c, i, npn);
+            const int do_next = (i + 1 < ncols) ? 1 : 0;
+            trd_w_kernel<T><<<g2, 256, 0, s>>>(x, c, i, g1, do_next);
+            npn = g2;
+        }
+        MAK_LAUNCH_CHECK(h, "hetrd column kernels");
+        // trailing update: A[t0:, t0:] -= [V W][W V]^H  (rows >= t0 of the panel)
+        const int t0 = j0 + ncols, mtr = n - t0;
+        if (mtr > 0) {
+            cudaError_t e = gemm<T>(s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, mtr, mtr, 2 * ncols, neg_(one<T>()),
+                                    x.P + t0, x.ldp, x.P + (size_t)ncols * x.ldp + t0, x.ldp, one<T>(),
+                                    x.A + (size_t)t0 * x.lda + t0, x.lda, nullptr, 0);
+            if (e != cudaSuccess) return cuda_fail(h, e, "hetrd gemm");
+        }
+    }
+    trd_last_d_kernel<T><<<1, 1, 0, s>>>(x);
+    MAK_LAUNCH_CHECK(h, "trd_last_d_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// gauge: V[:, j] *= conj(sign(first entry of maximal modulus))   (common/gauge.jl:12-14,38-45)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gauge_cols_kernel(int m, int ncols, T* __restrict__ V, int ldv, T* __restrict__ other, int ldo,
+                                  int other_rows_n) {
+    // one CTA per column; `other` (optional): rows of a second matrix scaled by sign (svd V^H)
+    __shared__ double bv[32];
+    __shared__ int bi[32];
+    __shared__ T sfac;
+    for (int j = blockIdx.x; j < ncols; j += gridDim.x) {
+        T* col = V + (size_t)j * ldv;
+        double best = -1.0;
+        int besti = 0x7fffffff;
+        for (int r = threadIdx.x; r < m; r += blockDim.x) {
+            double a = is_cplx<T>::value ? abs2_(col[r]) : fabs(real_(col[r]));
+            if (a > best) { best = a; besti = r; }  // strict: first maximum wins within a thread
+        }
+        // warp reduce (value desc, index asc)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = besti; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+                if (bv[w] > best || (bv[w] == best && bi[w] < besti)) { best = bv[w]; besti = bi[w]; }
+            T piv = (m > 0 && besti < m) ? col[besti] : zero<T>();
+            double a = sqrt(abs2_(piv));
+            // Julia sign(): 0 at 0 -> the column (all zeros) is zeroed either way; keep it unchanged
+            sfac = (a == 0.0) ? one<T>() : scale_(piv, 1.0 / a);
+        }
+        __syncthreads();
+        const T sg = sfac, csg = conj_(sfac);
+        for (int r = threadIdx.x; r < m; r += blockDim.x) col[r] = mul_(col[r], csg);
+        if (other)
+            for (int q = threadIdx.x; q < other_rows_n; q += blockDim.x) {
+                T* p = other + (size_t)q * ldo + j;
+                *p = mul_(*p, sg);
+            }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+int gauge_columns(makb200_handle* h, int m, int ncols, T* V, int ldv, T* other, int ldo, int other_n) {
+    if (ncols <= 0) return 0;
+    gauge_cols_kernel<T><<<ncols < 4096 ? ncols : 4096, 256, 0, h->stream>>>(m, ncols, V, ldv, other, ldo, other_n);
+    MAK_LAUNCH_CHECK(h, "gauge_cols_kernel");
+    return 0;
+}
+template int gauge_columns<double>(makb200_handle*, int, int, double*, int, double*, int, int);
+template int gauge_columns<cplx>(makb200_handle*, int, int, cplx*, int, cplx*, int, int);
+
+__global__ void real_to_T_kernel(int n, const double* __restrict__ Z, int ldz, cplx* __restrict__ V, int ldv) {
+    size_t total = (size_t)n * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(idx % n), c = (int)(idx / n);
+        V[(size_t)c * ldv + r] = cplx{Z[(size_t)c * ldz + r], 0.0};
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// drivers
+// ---------------------------------------------------------------------------------------
+template <typename T>
+int herm_defect_t(makb200_handle* h, int n, const T* A, int lda, double* out2) {
+    MAK_CUDA(h, cudaMemsetAsync(out2, 0, 2 * sizeof(double), h->stream));
+    if (n <= 0) return 0;
+    int nb = (n + 31) / 32;
+    herm_defect_kernel<T><<<dim3(nb, nb), dim3(32, 8), 0, h->stream>>>(n, A, lda, out2);
+    MAK_LAUNCH_CHECK(h, "herm_defect_kernel");
+    return 0;
+}
+template int herm_defect_t<double>(makb200_handle*, int, const double*, int, double*);
+template int herm_defect_t<cplx>(makb200_handle*, int, const cplx*, int, double*);
+
+template <typename T, typename AR>
+static void eigh_carve(makb200_handle* h, AR& ar, int n, TrdCtx<T>* x, double** Zreal, void** sub, size_t* sub_bytes) {
+    trd_carve<T>(ar, n, x);
+    size_t nn = (size_t)(n > 0 ? n : 1);
+    *Zreal = is_cplx<T>::value ? ar.template get<double>(nn * nn) : nullptr;
+    size_t a = stedc_worksize(n);
+    size_t b = ormqr_worksize_t<T>(h, n > 1 ? n - 1 : 1, n > 1 ? n - 1 : 1, n);
+    *sub_bytes = a > b ? a : b;
+    *sub = ar.template get<char>(*sub_bytes);
+}
+
+template <typename T>
+size_t eigh_worksize_t(makb200_handle* h, int n) {
+    ArenaSize ar;
+    TrdCtx<T> x;
+    double* zr;
+    void* sub;
+    size_t sb;
+    eigh_carve<T>(h, ar, n, &x, &zr, &sub, &sb);
+    return ar.off + 256;
+}
+
+template <typename T>
+int eigh_t(makb200_handle* h, int n, T* A, int lda, double* W, T* V, int ldv, int fixgauge, void* work, size_t lwork,
+           int* info_dev) {
+    if (n <= 0) return 0;
+    cudaStream_t s = h->stream;
+    Arena ar(work, lwork);
+    TrdCtx<T> x;
+    double* Zreal;
+    void* sub;
+    size_t sb;
+    eigh_carve<T>(h, ar, n, &x, &Zreal, &sub, &sb);
+    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    x.A = A;
+    x.lda = lda;
+    int nb32 = (n + 31) / 32;
+    PhaseTimer pt(s);
+    pt.mark("start");
+    mirror_upper_kernel<T><<<dim3(nb32, nb32), dim3(32, 8), 0, s>>>(n, A, lda);
+    MAK_LAUNCH_CHECK(h, "mirror_upper_kernel");
+    int rc = hetrd<T>(h, x);
+    if (rc) return rc;
+    pt.mark("hetrd");
+    double* Z;
+    int ldz;
+    if constexpr (is_cplx<T>::value) { Z = Zreal; ldz = n; }
+    else { Z = V; ldz = ldv; }
+    rc = stedc(h, n, x.d, x.e, W, Z, ldz, sub, sb, info_dev);
+    if (rc) return rc;
+    pt.mark("stedc");
+    if constexpr (is_cplx<T>::value) {
+        size_t total = (size_t)n * n;
+        int blocks = (int)((total + 255) / 256 < (size_t)h->num_sms * 16 ? (total + 255) / 256 : (size_t)h->num_sms * 16);
+        real_to_T_kernel<<<blocks, 256, 0, s>>>(n, Zreal, n, V, ldv);
+        MAK_LAUNCH_CHECK(h, "real_to_T_kernel");
+    }
+    // V[1:, :] <- H_0 ... H_{n-2} V[1:, :]; reflectors = QR-type columns of B = A[1:, 0:n-1]
+    if (n > 1) {
+        rc = ormqr_left_t<T>(h, n - 1, n - 1, A + 1, lda, x.tau, V + 1, ldv, n, sub, sb);
+        if (rc) return rc;
+    }
+    pt.mark("backtransform");
+    if (fixgauge) rc = gauge_columns<T>(h, n, n, V, ldv, (T*)nullptr, 0, 0);
+    pt.mark("gauge");
+    pt.report("eigh");
+    return rc;
+}
+
+template size_t eigh_worksize_t<double>(makb200_handle*, int);
+template size_t eigh_worksize_t<cplx>(makb200_handle*, int);
+template int eigh_t<double>(makb200_handle*, int, double*, int, double*, double*, int, int, void*, size_t, int*);
+template int eigh_t<cplx>(makb200_handle*, int, cplx*, int, double*, cplx*, int, int, void*, size_t, int*);
+
+}  // namespace mak

@@ -1,0 +1,12 @@
+#pragma once
+#include "common.cuh"
+namespace mak {
+template <typename T> int herm_defect_t(makb200_handle* h, int n, const T* A, int lda, double* out2);
+template <typename T> size_t eigh_worksize_t(makb200_handle* h, int n);
+template <typename T>
+int eigh_t(makb200_handle* h, int n, T* A, int lda, double* W, T* V, int ldv, int fixgauge, void* work, size_t lwork,
+           int* info_dev);
+// V[:, j] *= conj(sign(pivot_j)); optional `other` (k x other_n, row j scaled by sign(pivot_j))
+template <typename T>
+int gauge_columns(makb200_handle* h, int m, int ncols, T* V, int ldv, T* other, int ldo, int other_n);
+}  // namespace mak

@@ -22,30 +22,6 @@ constexpr int IBMAX = 32;         // inner panel width (max)
 constexpr int PANEL_THREADS = 256;
 constexpr size_t PANEL_SLAB_BYTES = 160 * 1024;  // shared-memory budget for the row slab
 
-// stable non-negative-beta reflector scalars: given alpha = x[0], sigma = ||x[1:]||^2
-// returns beta >= 0, tau, scale with v = x[1:]*scale, H = I - tau*[1;v][1;v]^H, H^H x = beta e1.
-template <typename T>
-__host__ __device__ __forceinline__ void larfgp_scalars(T alpha, double sigma, double& beta, T& tau, T& scale) {
-    if (sigma == 0.0 && imag_(alpha) == 0.0 && real_(alpha) >= 0.0) {
-        beta = real_(alpha);
-        tau = zero<T>();
-        scale = zero<T>();
-        return;
-    }
-    beta = sqrt(abs2_(alpha) + sigma);
-    T d;
-    if (real_(alpha) < 0.0) {
-        d = sub_(alpha, mk<T>(beta));
-    } else {
-        // alpha - beta = ((alpha - conj(alpha))*beta - sigma) / (conj(alpha) + beta)
-        T num = sub_(scale_(sub_(alpha, conj_(alpha)), beta), mk<T>(sigma));
-        T den = add_(conj_(alpha), mk<T>(beta));
-        d = div_(num, den);
-    }
-    tau = scale_(neg_(d), 1.0 / beta);
-    scale = div_(one<T>(), d);
-}
-
 // ---------------------------------------------------------------------------------------
 // cluster panel factorization
 // ---------------------------------------------------------------------------------------
@@ -489,8 +465,11 @@ int qr_fused_t(makb200_handle* h, int mode, int m, int n, T* A, int lda, T* Q, i
     QrWork<T> w;
     qr_carve<T>(h, ar, m, n, ncq, &w);
     if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    PhaseTimer pt(h->stream);
+    pt.mark("start");
     int rc = geqrf_blocked<T>(h, m, n, A, lda, w);
     if (rc) return rc;
+    pt.mark("geqrf");
     if (R && ldr > 0) {
         const int rr = ncq;
         if (rr > 0 && n > 0) {
@@ -498,7 +477,10 @@ int qr_fused_t(makb200_handle* h, int mode, int m, int n, T* A, int lda, T* Q, i
             MAK_LAUNCH_CHECK(h, "extract_r_kernel");
         }
     }
-    return orgqr_blocked<T>(h, m, ncq, k, A, lda, Q, ldq, w);
+    rc = orgqr_blocked<T>(h, m, ncq, k, A, lda, Q, ldq, w);
+    pt.mark("orgqr");
+    pt.report("qr");
+    return rc;
 }
 
 template <typename T>
@@ -559,11 +541,52 @@ int orgqr_t(makb200_handle* h, int m, int ncols, int k, const T* A, int lda, con
     return orgqr_blocked<T>(h, m, ncols, k, A, lda, Q, ldq, w);
 }
 
+// C (m x nc) <- H_0 ... H_{k-1} C  (ormqr/unmqr 'L','N'): V below the diagonal of A (m x k), tau
+template <typename T>
+size_t ormqr_worksize_t(makb200_handle* h, int m, int k, int nc) {
+    ArenaSize ar;
+    QrWork<T> w;
+    qr_carve<T>(h, ar, m, k, nc, &w);
+    return ar.off + 256;
+}
+
+template <typename T>
+int ormqr_left_t(makb200_handle* h, int m, int k, const T* A, int lda, const T* tau, T* C, int ldc, int nc,
+                 void* work, size_t lwork) {
+    if (m <= 0 || nc <= 0 || k <= 0) return 0;
+    Arena ar(work, lwork);
+    QrWork<T> w;
+    qr_carve<T>(h, ar, m, k, nc, &w);
+    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    cudaStream_t s = h->stream;
+    const int nb = w.nb;
+    const int nblk = (k + nb - 1) / nb;
+    T* Tb = w.Tall;  // one block at a time
+    for (int b = nblk - 1; b >= 0; --b) {
+        const int j0 = b * nb;
+        const int jb = (k - j0 < nb) ? (k - j0) : nb;
+        const int mp = m - j0;
+        copy_v_kernel<T><<<grid_for((size_t)mp * jb, h->num_sms), 256, 0, s>>>(mp, jb, 0, A + (size_t)j0 * lda + j0,
+                                                                                lda, w.Vw, mp);
+        MAK_LAUNCH_CHECK(h, "copy_v_kernel");
+        MAK_CUDA(h, cudaMemsetAsync(Tb, 0, sizeof(T) * (size_t)nb * nb, s));
+        MAK_GEMM(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, jb, jb, mp, one<T>(), w.Vw, mp, w.Vw, mp, zero<T>(), w.G,
+                 nb, w.ws, w.ws_bytes);
+        larft_diag_kernel<T><<<1, 128, 0, s>>>(jb, tau + j0, Tb, nb, w.G, nb);
+        MAK_LAUNCH_CHECK(h, "larft_diag_kernel");
+        int rc = apply_block_reflector<T>(h, false, mp, nc, jb, w.Vw, mp, Tb, nb, C + j0, ldc, w);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 #define INST(T)                                                                                            \
     template size_t qr_worksize_t<T>(makb200_handle*, int, int, int);                                      \
     template int qr_fused_t<T>(makb200_handle*, int, int, int, T*, int, T*, int, T*, int, void*, size_t);  \
     template int geqrf_t<T>(makb200_handle*, int, int, T*, int, T*, void*, size_t);                        \
-    template int orgqr_t<T>(makb200_handle*, int, int, int, const T*, int, const T*, T*, int, void*, size_t);
+    template int orgqr_t<T>(makb200_handle*, int, int, int, const T*, int, const T*, T*, int, void*, size_t); \
+    template size_t ormqr_worksize_t<T>(makb200_handle*, int, int, int);                                   \
+    template int ormqr_left_t<T>(makb200_handle*, int, int, const T*, int, const T*, T*, int, int, void*, size_t);
 INST(double)
 INST(cplx)
 

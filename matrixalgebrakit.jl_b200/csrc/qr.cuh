@@ -10,4 +10,9 @@ template <typename T> int geqrf_t(makb200_handle* h, int m, int n, T* A, int lda
 template <typename T>
 int orgqr_t(makb200_handle* h, int m, int ncols, int k, const T* A, int lda, const T* tau, T* Q, int ldq, void* work,
             size_t lwork);
+template <typename T> size_t ormqr_worksize_t(makb200_handle* h, int m, int k, int nc);
+template <typename T>
+int ormqr_left_t(makb200_handle* h, int m, int k, const T* A, int lda, const T* tau, T* C, int ldc, int nc, void* work,
+                 size_t lwork);
+// stable non-negative-beta reflector (shared with eigh.cu)
 }  // namespace mak

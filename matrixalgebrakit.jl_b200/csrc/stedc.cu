@@ -1,0 +1,343 @@
+// Tridiagonal divide-and-conquer eigensolver on the device (kernels around stedc_core.h).
+// All merges of one tree level run in the same launches (grid.y = merge index); the
+// eigenvector updates of a level are one grouped DMMA GEMM whose dimensions (the non-deflated
+// counts) are produced on the device, so the whole solver runs without a host round trip.
+#include "stedc.cuh"
+#include "stedc_core.h"
+#include "gemm.cuh"
+#include <vector>
+
+namespace mak {
+using namespace dc;
+
+struct DcBuffers {
+    Ctx ctx;
+    Merge* merges;                 // per level slice
+    GemmProblem<double>* gemms;    // 2 per merge
+    double* E;
+    double* rho_cut;               // per cut position
+    double* sgn_cut;
+    double* scale;                 // [1]
+    int* info;                     // [1]
+};
+
+__global__ void dc_scale_kernel(int n, const double* __restrict__ d, const double* __restrict__ e, double* D,
+                                double* E, double* scale) {
+    __shared__ double red[32];
+    double m = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, fabs(d[i]));
+    for (int i = threadIdx.x; i < n - 1; i += blockDim.x) m = fmax(m, fabs(e[i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t = fmax(t, red[i]);
+    double sc = t > 0.0 ? t : 1.0;
+    if (threadIdx.x == 0) *scale = sc;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) D[i] = d[i] / sc;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) E[i] = (i < n - 1) ? e[i] / sc : 0.0;
+}
+
+// tear the matrix at every leaf boundary (cuts are >= DC_LEAF/2 apart, so no two touch one entry)
+__global__ void dc_tear_kernel(int ncut, const int* __restrict__ cuts, double* D, const double* __restrict__ E,
+                               double* rho_cut, double* sgn_cut) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncut) return;
+    int c = cuts[i];
+    double e = E[c - 1];
+    double a = fabs(e);
+    rho_cut[c] = a;
+    sgn_cut[c] = e < 0.0 ? -1.0 : 1.0;
+    D[c - 1] -= a;
+    D[c] -= a;
+}
+
+// one thread per leaf (serial implicit QL on <= 32 x 32)
+__global__ void dc_leaf_kernel(int nleaf, const int* __restrict__ bnd, double* D, const double* __restrict__ E,
+                               double* Z, int ldz, int* info) {
+    int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= nleaf) return;
+    int lo = bnd[leaf], sz = bnd[leaf + 1] - lo;
+    double dd[DC_LEAF + 1], ee[DC_LEAF + 1];
+    for (int k = 0; k < sz; ++k) { dd[k] = D[lo + k]; ee[k] = (k + 1 < sz) ? E[lo + k] : 0.0; }
+    double* Zb = Z + (size_t)lo * ldz + lo;
+    for (int c = 0; c < sz; ++c)
+        for (int r = 0; r < sz; ++r) Zb[(size_t)c * ldz + r] = (r == c) ? 1.0 : 0.0;
+    int rc = leaf_ql(sz, dd, ee, Zb, ldz);
+    if (rc) atomicExch(info, 1);
+    for (int k = 0; k < sz; ++k) D[lo + k] = dd[k];
+}
+
+__global__ void dc_merge_init_kernel(int nm, Merge* mg, const double* __restrict__ rho_cut,
+                                     const double* __restrict__ sgn_cut) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nm) return;
+    mg[i].rho = 2.0 * rho_cut[mg[i].mid];
+    mg[i].sgn = sgn_cut[mg[i].mid];
+    mg[i].K = 0; mg[i].k1 = mg[i].k2 = mg[i].k3 = 0; mg[i].nrot = 0;
+}
+
+__global__ void dc_z_rank_kernel(Ctx c, const Merge* __restrict__ mgs, const double* __restrict__ Z, int ldz,
+                                 int phase) {
+    const Merge mg = mgs[blockIdx.y];
+    const int N = mg.hi - mg.lo;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        if (phase == 0) merge_z_item(c, mg, Z, ldz, i);
+        else merge_rank_item(c, mg, i);
+    }
+}
+
+__global__ void dc_deflate_kernel(Ctx c, Merge* mgs, GemmProblem<double>* gp, const double* Pack, int ldp,
+                                  const double* S, int lds, double* Tmp, int ldt) {
+    if (threadIdx.x != 0) return;
+    Merge mg = mgs[blockIdx.x];
+    deflate_scan(c, mg);
+    mgs[blockIdx.x] = mg;
+    const int lo = mg.lo, mid = mg.mid, N1 = mg.mid - mg.lo, N2 = mg.hi - mg.mid, K = mg.K;
+    const int k12 = mg.k1 + mg.k2, k23 = mg.k2 + mg.k3;
+    GemmProblem<double> p;
+    p.alpha = 1.0; p.beta = 0.0; p.conja = 0; p.conjb = 0;
+    // top rows: Tmp[lo:mid, lo:lo+K] = Pack[lo:mid, lo:lo+k12] * S[lo:lo+k12, lo:lo+K]
+    p.m = N1; p.n = K; p.k = k12;
+    p.A = Pack + (size_t)lo * ldp + lo; p.lda = ldp;
+    p.B = S + (size_t)lo * lds + lo; p.ldb = lds;
+    p.C = Tmp + (size_t)lo * ldt + lo; p.ldc = ldt;
+    gp[2 * blockIdx.x] = p;
+    // bottom rows: Tmp[mid:hi, lo:lo+K] = Pack[mid:hi, lo:lo+k23] * S[lo+k1:lo+K, lo:lo+K]
+    p.m = N2; p.n = K; p.k = k23;
+    p.A = Pack + (size_t)lo * ldp + mid;
+    p.B = S + (size_t)lo * lds + lo + mg.k1;
+    p.C = Tmp + (size_t)lo * ldt + mid;
+    gp[2 * blockIdx.x + 1] = p;
+}
+
+__global__ void dc_rotate_kernel(Ctx c, const Merge* __restrict__ mgs, double* Z, int ldz) {
+    const Merge mg = mgs[blockIdx.y];
+    if (mg.nrot == 0) return;
+    const int N = mg.hi - mg.lo;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < N; r += gridDim.x * blockDim.x)
+        rotate_row_item(c, mg, Z, ldz, r);
+}
+
+__global__ void dc_secular_kernel(Ctx c, const Merge* __restrict__ mgs) {
+    const Merge mg = mgs[blockIdx.y];
+    const int lo = mg.lo, K = mg.K;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < K; j += gridDim.x * blockDim.x)
+        secular_root(K, j, c.dl + lo, c.zl + lo, mg.rho, c.tau + lo + j, c.orig + lo + j);
+}
+
+__global__ void dc_zhat_pos_kernel(Ctx c, const Merge* __restrict__ mgs) {
+    const Merge mg = mgs[blockIdx.y];
+    const int lo = mg.lo, K = mg.K, N = mg.hi - mg.lo;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+        if (j < K) zhat_item(K, c.dl + lo, c.zl + lo, mg.rho, c.tau + lo, c.orig + lo, c.zhat + lo, j);
+        final_pos_item(c, mg, j);
+    }
+}
+
+// S column j (one CTA per column): S[rowpos[i], j] = zhat_i / (d_i - lambda_j), normalised
+__global__ void dc_svec_kernel(Ctx c, const Merge* __restrict__ mgs, double* S, int lds) {
+    __shared__ double red[32];
+    const Merge mg = mgs[blockIdx.y];
+    const int lo = mg.lo, K = mg.K;
+    for (int j = blockIdx.x; j < K; j += gridDim.x) {
+        double part = 0.0;
+        for (int i = threadIdx.x; i < K; i += blockDim.x) {
+            double v = c.zhat[lo + i] / sec_delta(c.dl + lo, c.tau + lo, c.orig + lo, i, j);
+            part += v * v;
+        }
+        double tot = block_sum<double>(part, red);
+        double inv = 1.0 / sqrt(tot);
+        double* col = S + (size_t)(lo + j) * lds + lo;
+        for (int i = threadIdx.x; i < K; i += blockDim.x) {
+            double v = c.zhat[lo + i] / sec_delta(c.dl + lo, c.tau + lo, c.orig + lo, i, j);
+            col[c.rowpos[lo + i]] = v * inv;
+        }
+        __syncthreads();
+    }
+}
+
+// pack non-deflated columns (type-grouped) and copy deflated columns to their final place
+__global__ void dc_pack_kernel(Ctx c, const Merge* __restrict__ mgs, const double* __restrict__ Zin, int ldi,
+                               double* Pack, int ldp, double* Zout, int ldo) {
+    const Merge mg = mgs[blockIdx.z];
+    const int lo = mg.lo, N = mg.hi - mg.lo, N1 = mg.mid - mg.lo, K = mg.K;
+    for (int j = blockIdx.y; j < N; j += gridDim.y) {
+        const int sc = c.src[lo + j], t = c.ctype[lo + j];
+        const double* col = Zin + (size_t)(lo + sc) * ldi + lo;
+        if (j < K) {
+            const int p = c.rowpos[lo + j];
+            double* ptop = Pack + (size_t)(lo + p) * ldp + lo;
+            double* pbot = Pack + (size_t)(lo + p - mg.k1) * ldp + lo;
+            for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < N; r += gridDim.x * blockDim.x) {
+                if (r < N1) { if (t != 3) ptop[r] = col[r]; }
+                else { if (t != 1) pbot[r] = col[r]; }
+            }
+        } else {
+            double* dst = Zout + (size_t)(lo + c.pos[lo + j]) * ldo + lo;
+            for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < N; r += gridDim.x * blockDim.x) {
+                bool top = r < N1;
+                dst[r] = ((t == 1 && !top) || (t == 3 && top)) ? 0.0 : col[r];
+            }
+        }
+    }
+}
+
+__global__ void dc_scatter_kernel(Ctx c, const Merge* __restrict__ mgs, const double* __restrict__ Tmp, int ldt,
+                                  double* Zout, int ldo) {
+    const Merge mg = mgs[blockIdx.z];
+    const int lo = mg.lo, N = mg.hi - mg.lo, K = mg.K;
+    for (int j = blockIdx.y; j < K; j += gridDim.y) {
+        const double* srcc = Tmp + (size_t)(lo + j) * ldt + lo;
+        double* dst = Zout + (size_t)(lo + c.pos[lo + j]) * ldo + lo;
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < N; r += gridDim.x * blockDim.x) dst[r] = srcc[r];
+    }
+}
+
+__global__ void dc_finish_kernel(int n, const double* __restrict__ D, const double* __restrict__ scale, double* w) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) w[i] = D[i] * (*scale);
+}
+
+__global__ void dc_copy_kernel(int n, const double* __restrict__ src, int lds, double* dst, int ldd) {
+    size_t total = (size_t)n * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(idx % n), cidx = (int)(idx / n);
+        dst[(size_t)cidx * ldd + r] = src[(size_t)cidx * lds + r];
+    }
+}
+
+static int dc_levels(int n) {
+    int L = 0;
+    while ((n + (1 << L) - 1) / (1 << L) > DC_LEAF) ++L;
+    return L;
+}
+
+template <typename AR>
+static void stedc_carve(AR& ar, int n, DcBuffers* b, double** Zw, double** Pack, double** S, int** bnd_dev,
+                        int** cuts_dev) {
+    const int L = dc_levels(n), nleaf = 1 << L;
+    size_t nn = (size_t)(n > 0 ? n : 1);
+    b->ctx.n = n;
+    b->ctx.D = ar.template get<double>(nn);
+    b->ctx.Dn = ar.template get<double>(nn);
+    b->ctx.z = ar.template get<double>(nn);
+    b->ctx.perm = ar.template get<int>(nn);
+    b->ctx.dl = ar.template get<double>(nn);
+    b->ctx.zl = ar.template get<double>(nn);
+    b->ctx.src = ar.template get<int>(nn);
+    b->ctx.ctype = ar.template get<int>(nn);
+    b->ctx.rowpos = ar.template get<int>(nn);
+    b->ctx.rot_p = ar.template get<int>(nn);
+    b->ctx.rot_q = ar.template get<int>(nn);
+    b->ctx.rot_c = ar.template get<double>(nn);
+    b->ctx.rot_s = ar.template get<double>(nn);
+    b->ctx.rot_tp = ar.template get<int>(nn);
+    b->ctx.rot_tq = ar.template get<int>(nn);
+    b->ctx.tau = ar.template get<double>(nn);
+    b->ctx.orig = ar.template get<int>(nn);
+    b->ctx.zhat = ar.template get<double>(nn);
+    b->ctx.pos = ar.template get<int>(nn);
+    b->merges = ar.template get<Merge>((size_t)nleaf);
+    b->gemms = ar.template get<GemmProblem<double>>((size_t)nleaf);
+    b->E = ar.template get<double>(nn);
+    b->rho_cut = ar.template get<double>(nn + 1);
+    b->sgn_cut = ar.template get<double>(nn + 1);
+    b->scale = ar.template get<double>(4);
+    b->info = ar.template get<int>(4);
+    *bnd_dev = ar.template get<int>((size_t)nleaf + 1);
+    *cuts_dev = ar.template get<int>((size_t)nleaf);
+    *Zw = ar.template get<double>(nn * nn);
+    *Pack = ar.template get<double>(nn * nn);
+    *S = ar.template get<double>(nn * nn);
+}
+
+size_t stedc_worksize(int n) {
+    ArenaSize ar;
+    DcBuffers b;
+    double *a, *p, *s;
+    int *bd, *cd;
+    stedc_carve(ar, n, &b, &a, &p, &s, &bd, &cd);
+    return ar.off + 256;
+}
+
+int stedc(makb200_handle* h, int n, const double* d, const double* e, double* w, double* Z, int ldz, void* work,
+          size_t lwork, int* info_dev) {
+    if (n <= 0) return 0;
+    cudaStream_t st = h->stream;
+    Arena ar(work, lwork);
+    DcBuffers b;
+    double *Zw, *Pack, *S;
+    int *bnd_dev, *cuts_dev;
+    stedc_carve(ar, n, &b, &Zw, &Pack, &S, &bnd_dev, &cuts_dev);
+    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    const int L = dc_levels(n), nleaf = 1 << L;
+    std::vector<int> bnd(nleaf + 1), cuts;
+    for (int i = 0; i <= nleaf; ++i) bnd[i] = (int)((long long)i * n / nleaf);
+    for (int i = 1; i < nleaf; ++i) cuts.push_back(bnd[i]);
+    MAK_CUDA(h, cudaMemcpyAsync(bnd_dev, bnd.data(), sizeof(int) * (nleaf + 1), cudaMemcpyHostToDevice, st));
+    if (!cuts.empty())
+        MAK_CUDA(h, cudaMemcpyAsync(cuts_dev, cuts.data(), sizeof(int) * cuts.size(), cudaMemcpyHostToDevice, st));
+    MAK_CUDA(h, cudaMemsetAsync(b.info, 0, sizeof(int) * 4, st));
+
+    dc_scale_kernel<<<1, 1024, 0, st>>>(n, d, e, b.ctx.D, b.E, b.scale);
+    if (!cuts.empty())
+        dc_tear_kernel<<<(int)(cuts.size() + 127) / 128, 128, 0, st>>>((int)cuts.size(), cuts_dev, b.ctx.D, b.E,
+                                                                        b.rho_cut, b.sgn_cut);
+    // ping-pong so that the last level lands in the caller's Z
+    const int ldw = n;
+    double* Zin = (L % 2 == 0) ? Z : Zw;
+    int ldi = (L % 2 == 0) ? ldz : ldw;
+    double* Zout = (L % 2 == 0) ? Zw : Z;
+    int ldo = (L % 2 == 0) ? ldw : ldz;
+    dc_leaf_kernel<<<(nleaf + 31) / 32, 32, 0, st>>>(nleaf, bnd_dev, b.ctx.D, b.E, Zin, ldi, b.info);
+    MAK_LAUNCH_CHECK(h, "dc_leaf_kernel");
+
+    std::vector<Merge> hm;
+    for (int lev = 1; lev <= L; ++lev) {
+        const int step = 1 << lev, nm = nleaf / step;
+        hm.assign(nm, Merge{});
+        int maxN = 0, maxH = 0;
+        for (int i = 0; i < nm; ++i) {
+            hm[i].lo = bnd[i * step];
+            hm[i].mid = bnd[i * step + step / 2];
+            hm[i].hi = bnd[(i + 1) * step];
+            maxN = std::max(maxN, hm[i].hi - hm[i].lo);
+            maxH = std::max(maxH, std::max(hm[i].mid - hm[i].lo, hm[i].hi - hm[i].mid));
+        }
+        // the (pageable) host vector is consumed before cudaMemcpyAsync returns
+        MAK_CUDA(h, cudaMemcpyAsync(b.merges, hm.data(), sizeof(Merge) * nm, cudaMemcpyHostToDevice, st));
+        dc_merge_init_kernel<<<(nm + 127) / 128, 128, 0, st>>>(nm, b.merges, b.rho_cut, b.sgn_cut);
+        const int bx = std::max(1, std::min((maxN + 255) / 256, 64));
+        dim3 g2(bx, nm);
+        dc_z_rank_kernel<<<g2, 256, 0, st>>>(b.ctx, b.merges, Zin, ldi, 0);
+        dc_z_rank_kernel<<<g2, 256, 0, st>>>(b.ctx, b.merges, Zin, ldi, 1);
+        // Tmp (GEMM output) aliases Zin: its columns have been packed / copied before the GEMM runs
+        dc_deflate_kernel<<<nm, 32, 0, st>>>(b.ctx, b.merges, b.gemms, Pack, n, S, n, Zin, ldi);
+        dc_rotate_kernel<<<g2, 256, 0, st>>>(b.ctx, b.merges, Zin, ldi);
+        dim3 gs(std::max(1, std::min((maxN + 127) / 128, 128)), nm);
+        dc_secular_kernel<<<gs, 128, 0, st>>>(b.ctx, b.merges);
+        dc_zhat_pos_kernel<<<gs, 128, 0, st>>>(b.ctx, b.merges);
+        dim3 gv(std::min(maxN, 4096), nm);
+        dc_svec_kernel<<<gv, 256, 0, st>>>(b.ctx, b.merges, S, n);
+        dim3 gp(std::max(1, std::min((maxN + 255) / 256, 8)), std::min(maxN, 8192), nm);
+        // grid.z is limited to 65535 merges per launch, far above n / DC_LEAF for any n that fits
+        dc_pack_kernel<<<gp, 256, 0, st>>>(b.ctx, b.merges, Zin, ldi, Pack, n, Zout, ldo);
+        MAK_LAUNCH_CHECK(h, "dc_pack_kernel");
+        cudaError_t ge = gemm_grouped<double>(st, MAKB200_OP_N, MAKB200_OP_N, 2 * nm, maxH, maxN, b.gemms);
+        if (ge != cudaSuccess) return cuda_fail(h, ge, "dc gemm_grouped");
+        dc_scatter_kernel<<<gp, 256, 0, st>>>(b.ctx, b.merges, Zin, ldi, Zout, ldo);
+        MAK_LAUNCH_CHECK(h, "dc_scatter_kernel");
+        std::swap(Zin, Zout);
+        std::swap(ldi, ldo);
+        std::swap(b.ctx.D, b.ctx.Dn);
+    }
+    // after the swaps Zin is the caller's Z
+    dc_finish_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, b.ctx.D, b.scale, w);
+    MAK_LAUNCH_CHECK(h, "dc_finish_kernel");
+    if (info_dev) MAK_CUDA(h, cudaMemcpyAsync(info_dev, b.info, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+}  // namespace mak

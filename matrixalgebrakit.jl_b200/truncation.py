@@ -1,0 +1,173 @@
+"""Truncation strategies — host side, as in the reference (src/interface/truncation.jl:37-275,
+src/implementations/truncation.jl:45-174).  The values vector is short (k reals): the index
+search runs on a host copy, like the reference's GPU path (MatrixAlgebraKitCUDAExt.jl:64-66)."""
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+
+@dataclass(frozen=True)
+class NoTruncation:
+    pass
+
+
+@dataclass(frozen=True)
+class TruncationByOrder:
+    howmany: int
+    rev: bool = True
+
+
+@dataclass(frozen=True)
+class TruncationByValue:
+    atol: float = 0.0
+    rtol: float = 0.0
+    p: float = 2
+    keep_below: bool = False
+
+
+@dataclass(frozen=True)
+class TruncationByError:
+    atol: float = 0.0
+    rtol: float = 0.0
+    p: float = 2
+
+
+@dataclass(frozen=True)
+class TruncationIntersection:
+    components: tuple
+
+    def __and__(self, other):
+        return TruncationIntersection(self.components + (other,))
+
+
+@dataclass(frozen=True)
+class TruncationUnion:
+    components: tuple
+
+
+def notrunc():
+    return NoTruncation()
+
+
+def truncrank(howmany, rev=True):
+    return TruncationByOrder(int(howmany), rev)
+
+
+def trunctol(atol=0.0, rtol=0.0, p=2, keep_below=False):
+    return TruncationByValue(float(atol), float(rtol), p, keep_below)
+
+
+def truncerror(atol=0.0, rtol=0.0, p=2):
+    return TruncationByError(float(atol), float(rtol), p)
+
+
+def trunc_and(*c):
+    return TruncationIntersection(tuple(c))
+
+
+def trunc_or(*c):
+    if any(isinstance(x, NoTruncation) for x in c):
+        return NoTruncation()  # notrunc is absorbing for | (test/common/truncate.jl:88-89)
+    return TruncationUnion(tuple(c))
+
+
+def select_truncation(trunc):
+    """``select_truncation`` / ``TruncationStrategy(; atol, rtol, maxrank, minrank, maxerror)``
+    (src/interface/truncation.jl:37-66)."""
+    if trunc is None:
+        return NoTruncation()
+    if isinstance(trunc, dict):
+        allowed = {"atol", "rtol", "maxrank", "minrank", "maxerror"}
+        bad = set(trunc) - allowed
+        if bad:
+            raise ValueError(f"unknown truncation keyword(s) {sorted(bad)}")
+        comps = []
+        if trunc.get("atol") is not None or trunc.get("rtol") is not None:
+            comps.append(trunctol(trunc.get("atol") or 0.0, trunc.get("rtol") or 0.0))
+        if trunc.get("maxrank") is not None:
+            comps.append(truncrank(trunc["maxrank"]))
+        if trunc.get("maxerror") is not None:
+            comps.append(truncerror(atol=trunc["maxerror"]))
+        s = NoTruncation() if not comps else (comps[0] if len(comps) == 1 else trunc_and(*comps))
+        if trunc.get("minrank") is not None:
+            s = truncrank(trunc["minrank"]) if not comps else trunc_or(s, truncrank(trunc["minrank"]))
+        return s
+    return trunc
+
+
+def _pnorm(v, p):
+    v = np.abs(v)
+    if p == 2:
+        return float(np.sqrt(np.sum(v * v)))
+    if np.isinf(p):
+        return float(v.max()) if v.size else 0.0
+    return float(np.sum(v ** p) ** (1.0 / p))
+
+
+def _truncerr_rank(vals_desc, s):
+    vp = np.abs(vals_desc) ** s.p
+    Np = float(vp.sum())
+    ep = max(s.atol ** s.p, s.rtol ** s.p * Np)
+    if ep >= Np:
+        return 0
+    cs = np.cumsum(vp[::-1])
+    return len(vals_desc) - int(np.argmax(cs >= ep))
+
+
+def _find(values, s, svd):
+    n = len(values)
+    if isinstance(s, NoTruncation):
+        return np.arange(n)
+    if isinstance(s, TruncationByOrder):
+        hm = min(s.howmany, n)
+        if svd:
+            return np.arange(hm) if s.rev else np.arange(n - hm, n)
+        order = np.argsort(-np.abs(values) if s.rev else np.abs(values), kind="stable")
+        return order[:hm]
+    if isinstance(s, TruncationByValue):
+        thr = max(s.atol, s.rtol * _pnorm(values, s.p))
+        if svd:
+            if s.keep_below:
+                i = int(np.searchsorted(-np.abs(values), -thr, side="left"))
+                return np.arange(i, n)
+            i = int(np.searchsorted(-np.abs(values), -thr, side="right"))
+            return np.arange(i)
+        m = (np.abs(values) <= thr) if s.keep_below else (np.abs(values) >= thr)
+        return np.nonzero(m)[0]
+    if isinstance(s, TruncationByError):
+        if svd:
+            return np.arange(_truncerr_rank(values, s))
+        order = np.argsort(-np.abs(values), kind="stable")
+        return order[: _truncerr_rank(values[order], s)]
+    if isinstance(s, (TruncationIntersection, TruncationUnion)):
+        sets = [set(int(i) for i in _find(values, c, svd)) for c in s.components]
+        if not sets:
+            return np.arange(n) if isinstance(s, TruncationIntersection) else np.arange(0)
+        out = set.intersection(*sets) if isinstance(s, TruncationIntersection) else set.union(*sets)
+        return np.array(sorted(out), dtype=np.int64)
+    raise ValueError(f"unknown truncation strategy {s}")
+
+
+def _host(values):
+    return values.detach().cpu().numpy() if isinstance(values, torch.Tensor) else np.asarray(values)
+
+
+def findtruncated(values, strategy):
+    """generic ``findtruncated`` (implementations/truncation.jl:48-83); 0-based indices."""
+    ind = _find(_host(values).astype(np.float64), strategy, svd=False)
+    return torch.as_tensor(ind, dtype=torch.long, device=values.device if isinstance(values, torch.Tensor) else "cpu")
+
+
+def findtruncated_svd(values, strategy):
+    """``findtruncated_svd`` (implementations/truncation.jl:54-58,69-79,86-102): assumes the
+    values are sorted descending."""
+    ind = _find(_host(values).astype(np.float64), strategy, svd=True)
+    return torch.as_tensor(ind, dtype=torch.long, device=values.device if isinstance(values, torch.Tensor) else "cpu")
+
+
+def truncation_error_(values, ind):
+    """``truncation_error!`` (implementations/truncation.jl:168-174): zero the kept entries
+    in place, return the 2-norm of the rest (a device scalar read)."""
+    values[ind] = 0.0
+    return float(torch.linalg.vector_norm(values).item())

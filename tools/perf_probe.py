@@ -62,5 +62,38 @@ def main():
                     print(f"   torch.linalg.qr (cuSOLVER): {timeit(tq, reps=3, warm=1):.3f} ms")
 
 
+
+
+def eigh_probe():
+    import time
+    for dtype in ("f64", "c128"):
+        for n in (1024, 4096, 8192):
+            if dtype == "c128" and n == 8192 and "big" not in sys.argv: continue
+            G = randdev(n, n, dtype)
+            A0 = ((G + G.conj().t()) / 2).t().contiguous().t()
+            A = makb200.colmajor_empty(n, n, A0.dtype, A0.device)
+            D, V = makb200.eigh.initialize_output(A)
+            def run():
+                A.copy_(A0)
+                makb200.eigh_full_(A, (D, V))
+            def cp():
+                A.copy_(A0)
+            ms = timeit(run, reps=3, warm=1) - timeit(cp, reps=3, warm=1)
+            c = 4 if dtype == "c128" else 1
+            fl = c * 10.0 * n ** 3 / 3
+            print(f"eigh_full {dtype} n={n}: {ms:.2f} ms  {fl/ms/1e9:.2f} TF/s", flush=True)
+            w = D.cpu().numpy()
+            if n <= 4096:
+                An, Vn = makb200.to_numpy(A0), makb200.to_numpy(V)
+                print("   resid", np.linalg.norm(An @ Vn - Vn * w) / np.linalg.norm(An), "orth", O.orth_err(Vn), "tol", O.tol_for(n))
+            t0 = time.time(); torch.linalg.eigh(A0); torch.cuda.synchronize(); t1 = time.time()
+            torch.linalg.eigh(A0); torch.cuda.synchronize(); t2 = time.time()
+            print(f"   torch.linalg.eigh (cuSOLVER syevd): {(t2-t1)*1e3:.1f} ms")
+
+
+if "eigh" in sys.argv[1:]:
+    eigh_probe()
+
 if __name__ == "__main__":
-    main()
+    if any(a in ("gemm", "qr") for a in sys.argv[1:]) or len(sys.argv) == 1:
+        main()
