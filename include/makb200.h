@@ -42,6 +42,15 @@ int makb200_version(void);
 /* last CUDA error string recorded on this handle (host memory, owned by the library) */
 const char* makb200_last_error(makb200_handle_t* h);
 
+/* -- instrumentation for bench.py (no effect on results) -------------------------------------
+ * makb200_launch_count: kernels launched by this library in this process so far.
+ * makb200_kernel_timing(1): bracket the dominant kernels with CUDA events on the launching
+ *   stream; makb200_kernel_time(which, &ms, &launches) collects and resets
+ *   (which = 0: tridiagonalisation column-dot kernel, 1: DMMA GEMM). */
+unsigned long long makb200_launch_count(void);
+int makb200_kernel_timing(int enable);
+int makb200_kernel_time(int which, double* ms, int* launches);
+
 /* -- GEMM building block: C = alpha*op(A)*op(B) + beta*C  (FP64 DMMA tiles) ----------
  * replaces `mul!` on CuArray -> cuBLAS gemm (implementations/polar.jl:63,88).
  * alpha/beta: HOST pointers to one scalar of `dtype`. */
@@ -106,6 +115,27 @@ int makb200_eigh(makb200_handle_t* h, int dtype, int fixgauge, int n, void* A, i
 size_t makb200_stedc_worksize(makb200_handle_t* h, int n);
 int makb200_stedc(makb200_handle_t* h, int n, const double* d, const double* e, double* W, double* Z,
                   int ldz, void* work, size_t lwork, int* info_dev);
+
+/* -- left_polar! (QDWH) ---------------------------------------------------------------------
+ * New algorithm `B200_QDWH` (the reference has PolarViaSVD / PolarNewton, implementations/
+ * polar.jl:59-166; contract = its result: A = W P, W isometric m x n, P Hermitian PSD n x n).
+ * m >= n required (polar.jl:9-10).  P == NULL or ldp == 0: P not requested (zero-length P,
+ * polar.jl:14,64,102).  l0: lower bound for sigma_min(A/||A||_F), <= 0 selects eps (valid for
+ * every kappa <= 1e16).  A is destroyed.  iters_host: optional HOST int (QDWH steps scheduled). */
+size_t makb200_polar_worksize(makb200_handle_t* h, int dtype, int m, int n);
+int makb200_polar_qdwh(makb200_handle_t* h, int dtype, int m, int n, void* A, int lda, void* W,
+                       int ldw, void* P, int ldp, double l0, int maxiter, void* work, size_t lwork,
+                       int* iters_host, int* info_dev);
+
+/* -- svd_compact! / svd_vals! ----------------------------------------------------------------
+ * replaces gesdd!/gesvd!/gesvdp! + gaugefix!(svd_compact!) (yalapack.jl:1959-2202,
+ * yacusolver.jl:101-181, common/gauge.jl:69-77).  Algorithm: QDWH polar + Hermitian D&C
+ * (the reference's `SVDViaPolar` tag).  U m x k, S k (descending, >= 0), Vh k x n, k = min(m,n);
+ * U == Vh == NULL: values only (job 'N').  m < n handled through A^H (svd.jl:134-142). */
+size_t makb200_svd_worksize(makb200_handle_t* h, int dtype, int m, int n);
+int makb200_svd(makb200_handle_t* h, int dtype, int fixgauge, int m, int n, void* A, int lda, double* S,
+                void* U, int ldu, void* Vh, int ldvh, double l0, void* work, size_t lwork,
+                int* info_dev);
 
 #ifdef __cplusplus
 }

@@ -14,3 +14,7 @@ from .eigh import (DomainError, check_hermitian, eigh_full, eigh_full_, eigh_tru
                    eigh_vals_)
 from .truncation import (findtruncated, findtruncated_svd, notrunc, select_truncation, trunc_and, trunc_or,
                          truncerror, truncrank, trunctol)
+from .polar import left_polar, left_polar_
+from .svd import (svd_compact, svd_compact_, svd_trunc, svd_trunc_, svd_trunc_no_error, svd_trunc_no_error_,
+                  svd_vals, svd_vals_)
+from . import eigh, polar, qr, svd, truncation  # noqa: E402,F401

@@ -24,6 +24,9 @@ SIGNATURES = {
     "makb200_destroy": (_i, [_vp]),
     "makb200_set_stream": (_i, [_vp, _vp]),
     "makb200_last_error": (C.c_char_p, [_vp]),
+    "makb200_launch_count": (C.c_ulonglong, []),
+    "makb200_kernel_timing": (_i, [_i]),
+    "makb200_kernel_time": (_i, [_i, C.POINTER(C.c_double), _ip]),
     "makb200_gemm": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i]),
     "makb200_geqrf_worksize": (_sz, [_vp, _i, _i, _i]),
     "makb200_geqrf": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _sz]),
@@ -38,6 +41,10 @@ SIGNATURES = {
     "makb200_eigh": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _sz, _vp]),
     "makb200_stedc_worksize": (_sz, [_vp, _i]),
     "makb200_stedc": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    "makb200_polar_worksize": (_sz, [_vp, _i, _i, _i]),
+    "makb200_polar_qdwh": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, C.c_double, _i, _vp, _sz, _ip, _vp]),
+    "makb200_svd_worksize": (_sz, [_vp, _i, _i, _i]),
+    "makb200_svd": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, C.c_double, _vp, _sz, _vp]),
 }
 
 _lib = None

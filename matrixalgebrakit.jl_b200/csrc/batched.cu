@@ -115,6 +115,7 @@ int batched_qr_smem(makb200_handle* h, int batch, size_t max_smem_elems, const Q
     size_t smem = (max_smem_elems + 64) * sizeof(T);
     if (smem > BQ_SMEM_BYTES) return MAKB200_ERR_WORKSPACE;
     batched_qr_kernel<T><<<batch, BQ_THREADS, smem, h->stream>>>(descs, info);
+    count_launch();
     MAK_LAUNCH_CHECK(h, "batched_qr_kernel");
     return 0;
 }

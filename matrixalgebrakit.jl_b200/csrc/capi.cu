@@ -6,6 +6,7 @@
 #include "batched.cuh"
 #include "eigh.cuh"
 #include "stedc.cuh"
+#include "polar.cuh"
 #include <vector>
 
 using mak::cplx;
@@ -31,6 +32,7 @@ int makb200_create(makb200_handle_t** out, int device) {
     h->err[0] = 0;
     int rc = mak::qr_init(h);
     if (rc == 0) rc = mak::batched_init(h);
+    if (rc == 0) rc = mak::polar_init(h);
     if (rc != 0) { delete h; return rc; }
     *out = h;
     return 0;
@@ -49,6 +51,24 @@ int makb200_set_stream(makb200_handle_t* h, void* s) {
 }
 
 const char* makb200_last_error(makb200_handle_t* h) { return h ? h->err : "null handle"; }
+
+unsigned long long makb200_launch_count(void) { return mak::g_launches; }
+
+int makb200_kernel_timing(int enable) {
+    mak::g_clock_dots.on = enable != 0;
+    mak::g_clock_gemm.on = enable != 0;
+    mak::g_clock_dots.n = 0;
+    mak::g_clock_gemm.n = 0;
+    return 0;
+}
+
+int makb200_kernel_time(int which, double* ms, int* launches) {
+    if (!ms || !launches) return -2;
+    if (which == 0) mak::g_clock_dots.collect(ms, launches);
+    else if (which == 1) mak::g_clock_gemm.collect(ms, launches);
+    else return -1;
+    return 0;
+}
 
 static bool op_ok(int op) { return op == MAKB200_OP_N || op == MAKB200_OP_T || op == MAKB200_OP_C; }
 
@@ -284,6 +304,62 @@ int makb200_stedc(makb200_handle_t* h, int n, const double* d, const double* e, 
     if (!W) return -5;
     if (!Z) return -6;
     return mak::stedc(h, n, d, e, W, Z, ldz, work, lwork, info_dev);
+}
+
+
+// ---- polar / svd ---------------------------------------------------------------------
+static double qdwh_l0(double l0) { return (l0 > 0.0 && l0 < 1.0) ? l0 : 2.2e-16; }
+
+size_t makb200_polar_worksize(makb200_handle_t* h, int dtype, int m, int n) {
+    if (!h || !dtype_ok(dtype) || m < 0 || n < 0 || m < n) return 0;
+    return dtype == MAKB200_F64 ? mak::polar_worksize_t<double>(h, m, n) : mak::polar_worksize_t<cplx>(h, m, n);
+}
+
+int makb200_polar_qdwh(makb200_handle_t* h, int dtype, int m, int n, void* A, int lda, void* W, int ldw, void* P,
+                       int ldp, double l0, int maxiter, void* work, size_t lwork, int* iters_host, int* info_dev) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (m < 0) return -3;
+    if (n < 0 || n > m) return -4;  // `left_polar!` requires m >= n (implementations/polar.jl:9-10)
+    if (lda < maxi(1, m)) return -6;
+    if (ldw < maxi(1, m)) return -8;
+    if (P && ldp > 0 && ldp < maxi(1, n)) return -10;
+    if (m == 0 || n == 0) return 0;
+    if (!A) return -5;
+    if (!W || W == A) return -7;
+    if (maxiter <= 0) maxiter = 12;
+    if (dtype == MAKB200_F64)
+        return mak::polar_qdwh_t<double>(h, m, n, (double*)A, lda, (double*)W, ldw, (double*)P, ldp, qdwh_l0(l0),
+                                         maxiter, work, lwork, iters_host, info_dev);
+    return mak::polar_qdwh_t<cplx>(h, m, n, (cplx*)A, lda, (cplx*)W, ldw, (cplx*)P, ldp, qdwh_l0(l0), maxiter, work,
+                                   lwork, iters_host, info_dev);
+}
+
+size_t makb200_svd_worksize(makb200_handle_t* h, int dtype, int m, int n) {
+    if (!h || !dtype_ok(dtype) || m < 0 || n < 0) return 0;
+    return dtype == MAKB200_F64 ? mak::svd_worksize_t<double>(h, m, n) : mak::svd_worksize_t<cplx>(h, m, n);
+}
+
+int makb200_svd(makb200_handle_t* h, int dtype, int fixgauge, int m, int n, void* A, int lda, double* S, void* U,
+                int ldu, void* Vh, int ldvh, double l0, void* work, size_t lwork, int* info_dev) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (m < 0) return -4;
+    if (n < 0) return -5;
+    int k = m < n ? m : n;
+    if (lda < maxi(1, m)) return -7;
+    if (U && ldu < maxi(1, m)) return -10;
+    if (Vh && ldvh < maxi(1, k)) return -12;
+    if ((U == nullptr) != (Vh == nullptr)) return -11;  // both or neither (job 'S' or 'N', yalapack.jl:2105-2127)
+    if (m == 0 || n == 0) return 0;                       // empty: the host layer fills identities (svd.jl:197)
+    if (!A) return -6;
+    if (!S) return -8;
+    if (U == A || Vh == A) return -9;
+    if (dtype == MAKB200_F64)
+        return mak::svd_t<double>(h, m, n, (double*)A, lda, S, (double*)U, ldu, (double*)Vh, ldvh, fixgauge,
+                                  qdwh_l0(l0), work, lwork, info_dev);
+    return mak::svd_t<cplx>(h, m, n, (cplx*)A, lda, S, (cplx*)U, ldu, (cplx*)Vh, ldvh, fixgauge, qdwh_l0(l0), work,
+                            lwork, info_dev);
 }
 
 }  // extern "C"

@@ -168,6 +168,47 @@ inline int cuda_fail(makb200_handle* h, cudaError_t e, const char* where) {
         if (_e != cudaSuccess) return mak::cuda_fail(h, _e, name);  \
     } while (0)
 
+// process-wide count of kernels launched by this library (bench.py reports it as gpu_launches)
+extern unsigned long long g_launches;
+inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }
+
+// per-kernel-class device-time accumulation for the roofline line of bench.py
+// (enabled through makb200_kernel_timing(1); CUDA events on the launching stream)
+struct KernelClock {
+    bool on = false;
+    static constexpr int MAXEV = 1 << 16;
+    cudaEvent_t* ev = nullptr;  // pairs
+    int n = 0;
+    void begin(cudaStream_t s) {
+        if (!on || n + 2 > MAXEV) return;
+        if (!ev) {
+            ev = (cudaEvent_t*)malloc(sizeof(cudaEvent_t) * MAXEV);
+            for (int i = 0; i < MAXEV; ++i) cudaEventCreate(&ev[i]);
+        }
+        cudaEventRecord(ev[n], s);
+    }
+    void end(cudaStream_t s) {
+        if (!on || n + 2 > MAXEV || !ev) return;
+        cudaEventRecord(ev[n + 1], s);
+        n += 2;
+    }
+    // total milliseconds and launch count since the last reset (synchronises)
+    void collect(double* ms, int* launches) {
+        double t = 0;
+        for (int i = 0; i + 1 < n; i += 2) {
+            cudaEventSynchronize(ev[i + 1]);
+            float f = 0;
+            cudaEventElapsedTime(&f, ev[i], ev[i + 1]);
+            t += f;
+        }
+        *ms = t;
+        *launches = n / 2;
+        n = 0;
+    }
+};
+extern KernelClock g_clock_dots;  // trd_dots_kernel (dominant kernel of eigh_full!)
+extern KernelClock g_clock_gemm;  // DMMA GEMM launches
+
 // optional phase timing (env MAKB200_PROFILE=1): prints device time per phase to stderr.
 struct PhaseTimer {
     bool on;

@@ -324,14 +324,18 @@ static int hetrd(makb200_handle* h, TrdCtx<T>& x) {
             int mt = n - j0 - 1;
             npn = (mt + TRD_K2_ROWS - 1) / TRD_K2_ROWS;
             trd_colnorm_kernel<T><<<npn, 256, 0, s>>>(x, j0);
+            count_launch();
         }
         for (int i = 0; i < ncols; ++i) {
             const int c = j0 + i, mt = n - c - 1;
             const int g2 = (mt + TRD_K2_ROWS - 1) / TRD_K2_ROWS;
             const int g1 = (mt + 2 * i + TRD_K1_COLS - 1) / TRD_K1_COLS;
+            g_clock_dots.begin(s);
             trd_dots_kernel<T><<<g1, TRD_K1_THREADS, 0, s>>>(x, c, i, npn);
+            g_clock_dots.end(s);
             const int do_next = (i + 1 < ncols) ? 1 : 0;
             trd_w_kernel<T><<<g2, 256, 0, s>>>(x, c, i, g1, do_next);
+            count_launch(2);
             npn = g2;
         }
         MAK_LAUNCH_CHECK(h, "hetrd column kernels");
@@ -493,6 +497,7 @@ int eigh_t(makb200_handle* h, int n, T* A, int lda, double* W, T* V, int ldv, in
         if (rc) return rc;
     }
     pt.mark("backtransform");
+    count_launch(3);  // mirror, last_d, gauge
     if (fixgauge) rc = gauge_columns<T>(h, n, n, V, ldv, (T*)nullptr, 0, 0);
     pt.mark("gauge");
     pt.report("eigh");

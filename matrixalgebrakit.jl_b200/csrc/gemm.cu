@@ -3,6 +3,10 @@
 
 namespace mak {
 
+unsigned long long g_launches = 0;
+KernelClock g_clock_dots;
+KernelClock g_clock_gemm;
+
 // ---------------------------------------------------------------------------------------
 // tile configuration
 // ---------------------------------------------------------------------------------------
@@ -286,7 +290,10 @@ static cudaError_t launch(cudaStream_t stream, dim3 grid, const GemmProblem<T>& 
         if (e != cudaSuccess) return e;
         configured = true;
     }
+    g_clock_gemm.begin(stream);
     gemm_kernel<T, TA, TB><<<grid, GEMM_THREADS, smem, stream>>>(p, plist, splitk, ws);
+    g_clock_gemm.end(stream);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -332,6 +339,7 @@ cudaError_t gemm(cudaStream_t stream, int num_sms, int opa, int opb, int m, int 
         size_t total = (size_t)m * n;
         int blocks = (int)min((size_t)num_sms * 8, (total + 255) / 256);
         splitk_reduce_kernel<T><<<blocks, 256, 0, stream>>>(m, n, splitk, (const T*)ws, alpha, beta, Cm, ldc);
+        count_launch();
         e = cudaGetLastError();
     }
     return e;

@@ -1,0 +1,581 @@
+// left_polar! by QDWH (Nakatsukasa, Bai, Gygi 2010; Nakatsukasa & Higham 2013) and
+// svd_compact! = polar + eigh (the reference's `SVDViaPolar` tag, cuSOLVER gesvdp class).
+//
+// The reference has no QDWH (its polar is PolarViaSVD / PolarNewton, implementations/polar.jl:
+// 59-166); the contract is the reference's RESULT: W isometric, P Hermitian PSD, A = W P.
+// Every step is GEMM-shaped and runs on the DMMA GEMM:
+//   QR-type iteration   (c > 100):  [sqrt(c) X; I] = [Q1;Q2] R,  X <- (b/c) X + (a-b/c)/sqrt(c) Q1 Q2^H
+//   Cholesky iteration  (c <= 100): Z = I + c X^H X = L L^H,     X <- (b/c) X + (a-b/c) (X L^-H) L^-1
+// The iteration schedule (a,b,c per step) depends only on the scalar lower bound l0 and is
+// computed on the host, so the device loop runs without a host round trip.
+#include "polar.cuh"
+#include "eigh.cuh"
+#include "gemm.cuh"
+#include "qr.cuh"
+#include <vector>
+
+namespace mak {
+
+template <typename T> struct CholNB { static constexpr int value = 128; };
+template <> struct CholNB<cplx> { static constexpr int value = 64; };
+
+#define MAK_GEMM2(h, ...)                                              \
+    do {                                                               \
+        cudaError_t _e = gemm<T>(__VA_ARGS__);                         \
+        if (_e != cudaSuccess) return cuda_fail(h, _e, "gemm");        \
+    } while (0)
+
+static inline int grid_for2(size_t total, int num_sms) {
+    size_t b = (total + 255) / 256, cap = (size_t)num_sms * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ---------------------------------------------------------------------------------------
+// elementwise helpers
+// ---------------------------------------------------------------------------------------
+// out[0] = sum |A_ij|^2 (deterministic two-stage reduction: partials then a single block)
+template <typename T>
+__global__ void fro2_partial_kernel(int m, int n, const T* __restrict__ A, int lda, double* __restrict__ partial) {
+    __shared__ double red[32];
+    size_t total = (size_t)m * n;
+    double s = 0.0;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(idx % m), c = (int)(idx / m);
+        s += abs2_(A[(size_t)c * lda + r]);
+    }
+    double t = block_sum<double>(s, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+__global__ void fro2_final_kernel(int np, const double* __restrict__ partial, double* out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) s += partial[i];
+    double t = block_sum<double>(s, red);
+    if (threadIdx.x == 0) out[0] = t;
+}
+
+// X = A / sqrt(norm2[0])   (X0 = A / ||A||_F); a zero matrix is copied unchanged
+template <typename T>
+__global__ void scale_copy_kernel(int m, int n, const T* __restrict__ A, int lda, T* __restrict__ X, int ldx,
+                                  const double* __restrict__ norm2) {
+    const double nn = norm2[0];
+    const double inv = nn > 0.0 ? 1.0 / sqrt(nn) : 1.0;
+    size_t total = (size_t)m * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(idx % m), c = (int)(idx / m);
+        X[(size_t)c * ldx + r] = scale_(A[(size_t)c * lda + r], inv);
+    }
+}
+
+// B = [sqrt(c) X ; I]  ((m+n) x n)
+template <typename T>
+__global__ void stack_kernel(int m, int n, const T* __restrict__ X, int ldx, T* __restrict__ B, int ldb, double sc) {
+    size_t total = (size_t)(m + n) * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(idx % (m + n)), c = (int)(idx / (m + n));
+        T v;
+        if (r < m) v = scale_(X[(size_t)c * ldx + r], sc);
+        else v = (r - m == c) ? one<T>() : zero<T>();
+        B[(size_t)c * ldb + r] = v;
+    }
+}
+
+// Z = I  (n x n)
+template <typename T>
+__global__ void eye_kernel(int n, T* __restrict__ Z, int ldz) {
+    size_t total = (size_t)n * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(idx % n), c = (int)(idx / n);
+        Z[(size_t)c * ldz + r] = (r == c) ? one<T>() : zero<T>();
+    }
+}
+
+// X = alpha*X + beta*Y
+template <typename T>
+__global__ void axpby_kernel(int m, int n, double alpha, T* __restrict__ X, int ldx, double beta,
+                             const T* __restrict__ Y, int ldy) {
+    size_t total = (size_t)m * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(idx % m), c = (int)(idx / m);
+        T* px = X + (size_t)c * ldx + r;
+        *px = add_(scale_(*px, alpha), scale_(Y[(size_t)c * ldy + r], beta));
+    }
+}
+
+template <typename T>
+__global__ void copy2d_kernel(int m, int n, const T* __restrict__ S, int lds, T* __restrict__ D, int ldd) {
+    size_t total = (size_t)m * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(idx % m), c = (int)(idx / m);
+        D[(size_t)c * ldd + r] = S[(size_t)c * lds + r];
+    }
+}
+
+// P = (H + H^H)/2, tiled so both sides are coalesced (project_hermitian!, one launch)
+template <typename T>
+__global__ void symmetrize_kernel(int n, const T* __restrict__ H, int ldh, T* __restrict__ P, int ldp) {
+    __shared__ T tile[32][33];
+    const int bi = blockIdx.x, bj = blockIdx.y, tx = threadIdx.x, ty = threadIdx.y;
+    for (int k = ty; k < 32; k += 8) {
+        int r = bj * 32 + tx, c = bi * 32 + k;
+        tile[k][tx] = (r < n && c < n) ? H[(size_t)c * ldh + r] : zero<T>();
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        int r = bi * 32 + tx, c = bj * 32 + k;
+        if (r < n && c < n) {
+            T a = H[(size_t)c * ldh + r];
+            T b = conj_(tile[tx][k]);
+            T v = scale_(add_(a, b), 0.5);
+            if (r == c) v = mk<T>(real_(v));
+            P[(size_t)c * ldp + r] = v;
+        }
+    }
+}
+
+// D = S^H  (S: m x n  ->  D: n x m)
+template <typename T>
+__global__ void adjoint_kernel(int m, int n, const T* __restrict__ S, int lds, T* __restrict__ D, int ldd) {
+    __shared__ T tile[32][33];
+    const int bi = blockIdx.x, bj = blockIdx.y, tx = threadIdx.x, ty = threadIdx.y;
+    for (int k = ty; k < 32; k += 8) {
+        int r = bi * 32 + tx, c = bj * 32 + k;
+        tile[k][tx] = (r < m && c < n) ? S[(size_t)c * lds + r] : zero<T>();
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        int r = bj * 32 + tx, c = bi * 32 + k;  // D[r, c] = conj(S[c, r]) = conj(tile[tx][k])
+        if (r < n && c < m) D[(size_t)c * ldd + r] = conj_(tile[tx][k]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Cholesky building blocks
+// ---------------------------------------------------------------------------------------
+// one CTA: L = chol(Zblk) (nb x nb, lower) and Linv = L^-1; both written with zeros above the
+// diagonal.  info[0] set to 1 if a pivot is not positive.
+template <typename T>
+__global__ void __launch_bounds__(256)
+potf2_inv_kernel(int nb, const T* __restrict__ Zb, int ldz, T* __restrict__ Lb, int ldl, T* __restrict__ Linv,
+                 int ldi, int* info) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* S = reinterpret_cast<T*>(smem_raw);  // [nb][nb+1] column-major: S[c*(nb+1)+r]
+    const int lds = nb + 1, tid = threadIdx.x;
+    for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
+        int c = idx / nb, r = idx - c * nb;
+        S[c * lds + r] = (r >= c) ? Zb[(size_t)c * ldz + r] : zero<T>();
+    }
+    __syncthreads();
+    for (int k = 0; k < nb; ++k) {
+        if (tid == 0) {
+            double akk = real_(S[k * lds + k]);
+            if (!(akk > 0.0)) { atomicExch(info, 1); akk = 1.0; }
+            S[k * lds + k] = mk<T>(sqrt(akk));
+        }
+        __syncthreads();
+        const double inv = 1.0 / real_(S[k * lds + k]);
+        for (int r = k + 1 + tid; r < nb; r += blockDim.x) S[k * lds + r] = scale_(S[k * lds + r], inv);
+        __syncthreads();
+        // trailing lower triangle: S[r][c] -= S[r][k] * conj(S[c][k]),  k < c <= r
+        const int w = nb - k - 1;
+        for (int idx = tid; idx < w * w; idx += blockDim.x) {
+            int c = k + 1 + idx / w, r = k + 1 + idx % w;
+            if (r >= c) {
+                T v = S[c * lds + r];
+                v = sub_(v, mul_(S[k * lds + r], conj_(S[k * lds + c])));
+                S[c * lds + r] = v;
+            }
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
+        int c = idx / nb, r = idx - c * nb;
+        Lb[(size_t)c * ldl + r] = (r >= c) ? S[c * lds + r] : zero<T>();
+    }
+    // inverse: thread c solves L x = e_c by forward substitution (x overwrites nothing in S)
+    for (int c = tid; c < nb; c += blockDim.x) {
+        T* out = Linv + (size_t)c * ldi;
+        for (int r = 0; r < c; ++r) out[r] = zero<T>();
+        out[c] = mk<T>(1.0 / real_(S[c * lds + c]));
+        for (int r = c + 1; r < nb; ++r) {
+            T s = zero<T>();
+            for (int p = c; p < r; ++p) fma_(s, S[p * lds + r], out[p]);
+            out[r] = scale_(neg_(s), 1.0 / real_(S[r * lds + r]));
+        }
+    }
+}
+
+template <typename T>
+static int potf2_init(makb200_handle* h) {
+    constexpr int nb = CholNB<T>::value;
+    MAK_CUDA(h, cudaFuncSetAttribute(potf2_inv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(T) * nb * (nb + 1))));
+    return 0;
+}
+
+int polar_init(makb200_handle* h) {
+    int rc = potf2_init<double>(h);
+    if (rc) return rc;
+    return potf2_init<cplx>(h);
+}
+
+// left-looking blocked Cholesky: Z (n x n Hermitian, lower part read, destroyed) -> L (lower; only
+// blocks strictly below the block diagonal are referenced later) and Linv (nb x nb per block)
+template <typename T>
+static int potrf_blocked(makb200_handle* h, int n, T* Z, int ldz, T* L, int ldl, T* Linv, int* info) {
+    constexpr int nb = CholNB<T>::value;
+    cudaStream_t s = h->stream;
+    const T one_ = one<T>(), zero_ = zero<T>(), mone = neg_(one<T>());
+    for (int j0 = 0, b = 0; j0 < n; j0 += nb, ++b) {
+        const int jb = (n - j0 < nb) ? (n - j0) : nb;
+        if (j0 > 0)
+            MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, n - j0, jb, j0, mone, L + j0, ldl, L + j0, ldl,
+                      one_, Z + (size_t)j0 * ldz + j0, ldz, nullptr, 0);
+        potf2_inv_kernel<T><<<1, 256, sizeof(T) * jb * (jb + 1), s>>>(jb, Z + (size_t)j0 * ldz + j0, ldz,
+                                                                      L + (size_t)j0 * ldl + j0, ldl,
+                                                                      Linv + (size_t)b * nb * nb, nb, info);
+        count_launch();
+        MAK_LAUNCH_CHECK(h, "potf2_inv_kernel");
+        const int mr = n - j0 - jb;
+        if (mr > 0)
+            MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, mr, jb, jb, one_, Z + (size_t)j0 * ldz + j0 + jb,
+                      ldz, Linv + (size_t)b * nb * nb, nb, zero_, L + (size_t)j0 * ldl + j0 + jb, ldl, nullptr, 0);
+    }
+    return 0;
+}
+
+// Y = X L^-H (conjtrans) or Y = X L^-1, X m x n untouched, Tmp m x nb scratch
+template <typename T>
+static int trsm_right(makb200_handle* h, bool conjtrans, int m, int n, const T* X, int ldx, const T* L, int ldl,
+                      const T* Linv, T* Y, int ldy, T* Tmp) {
+    constexpr int nb = CholNB<T>::value;
+    cudaStream_t s = h->stream;
+    const T one_ = one<T>(), zero_ = zero<T>(), mone = neg_(one<T>());
+    const int nblk = (n + nb - 1) / nb;
+    for (int bb = 0; bb < nblk; ++bb) {
+        const int b = conjtrans ? bb : (nblk - 1 - bb);
+        const int j0 = b * nb, jb = (n - j0 < nb) ? (n - j0) : nb;
+        copy2d_kernel<T><<<grid_for2((size_t)m * jb, h->num_sms), 256, 0, s>>>(m, jb, X + (size_t)j0 * ldx, ldx, Tmp, m);
+        count_launch();
+        if (conjtrans) {
+            // (Y L^H)_j = sum_{i<=j} Y_i L_ji^H
+            if (j0 > 0)
+                MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, m, jb, j0, mone, Y, ldy, L + j0, ldl, one_, Tmp,
+                          m, nullptr, 0);
+            MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, m, jb, jb, one_, Tmp, m,
+                      Linv + (size_t)b * nb * nb, nb, zero_, Y + (size_t)j0 * ldy, ldy, nullptr, 0);
+        } else {
+            // (Y L)_j = sum_{i>=j} Y_i L_ij
+            const int j1 = j0 + jb, rest = n - j1;
+            if (rest > 0)
+                MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_N, m, jb, rest, mone, Y + (size_t)j1 * ldy, ldy,
+                          L + (size_t)j0 * ldl + j1, ldl, one_, Tmp, m, nullptr, 0);
+            MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_N, m, jb, jb, one_, Tmp, m,
+                      Linv + (size_t)b * nb * nb, nb, zero_, Y + (size_t)j0 * ldy, ldy, nullptr, 0);
+        }
+    }
+    MAK_LAUNCH_CHECK(h, "trsm_right");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// QDWH
+// ---------------------------------------------------------------------------------------
+struct QdwhStep { double a, b, c; bool qr; };
+
+static std::vector<QdwhStep> qdwh_schedule(double l, int maxiter) {
+    std::vector<QdwhStep> v;
+    for (int it = 0; it < maxiter; ++it) {
+        if (fabs(1.0 - l) <= 1e-15) {
+            // one Halley step past the nominal convergence point costs little and polishes X^H X = I
+            if (!v.empty() && v.back().c > 3.0 + 1e-6) v.push_back(QdwhStep{3.0, 1.0, 3.0, false});
+            break;
+        }
+        double l2 = l * l;
+        double dd = cbrt(4.0 * (1.0 - l2) / (l2 * l2));
+        double a = sqrt(1.0 + dd) + 0.5 * sqrt(8.0 - 4.0 * dd + 8.0 * (2.0 - l2) / (l2 * sqrt(1.0 + dd)));
+        double b = (a - 1.0) * (a - 1.0) / 4.0, c = a + b - 1.0;
+        v.push_back(QdwhStep{a, b, c, c > 100.0});
+        l = l * (a + b * l2) / (1.0 + c * l2);
+        if (l > 1.0) l = 1.0;
+    }
+    return v;
+}
+
+template <typename T>
+struct PolarWork {
+    T *X, *B, *Q, *Z, *L, *Linv, *Y, *Y2, *Tmp, *R0, *Q0;
+    double* scal;      // [8]
+    double* partial;   // [1024]
+    int* info;
+    void* sub;         // QR workspace
+    size_t sub_bytes;
+};
+
+template <typename T, typename AR>
+static void polar_carve(makb200_handle* h, AR& ar, int m, int n, bool tall, PolarWork<T>* w) {
+    constexpr int nb = CholNB<T>::value;
+    const int ms = tall ? n : m;  // rows of the iterated matrix
+    size_t nn = (size_t)(n > 0 ? n : 1), mm = (size_t)(ms > 0 ? ms : 1);
+    w->X = ar.template get<T>(mm * nn);
+    w->B = ar.template get<T>((mm + nn) * nn);
+    w->Q = ar.template get<T>((mm + nn) * nn);
+    w->Z = ar.template get<T>(nn * nn);
+    w->L = ar.template get<T>(nn * nn);
+    w->Linv = ar.template get<T>((size_t)nb * nb * ((nn + nb - 1) / nb));
+    w->Y = ar.template get<T>(mm * nn);
+    w->Y2 = ar.template get<T>(mm * nn);
+    w->Tmp = ar.template get<T>(mm * nb);
+    w->R0 = tall ? ar.template get<T>(nn * nn) : nullptr;
+    w->Q0 = tall ? ar.template get<T>((size_t)m * nn) : nullptr;
+    w->scal = ar.template get<double>(8);
+    w->partial = ar.template get<double>(1024);
+    w->info = ar.template get<int>(4);
+    size_t a = qr_worksize_t<T>(h, (int)(mm + nn), n, n);
+    size_t b = tall ? qr_worksize_t<T>(h, m, n, n) : 0;
+    w->sub_bytes = a > b ? a : b;
+    w->sub = ar.template get<char>(w->sub_bytes);
+}
+
+static inline bool polar_tall(int m, int n) { return m > n + n / 8; }
+
+template <typename T>
+size_t polar_worksize_t(makb200_handle* h, int m, int n) {
+    ArenaSize ar;
+    PolarWork<T> w;
+    polar_carve<T>(h, ar, m, n, polar_tall(m, n), &w);
+    return ar.off + 256;
+}
+
+// polar factor of a (ms x n, ms >= n) matrix held in w.X (already scaled so that ||X||_2 <= 1)
+template <typename T>
+static int qdwh_iterate(makb200_handle* h, int ms, int n, PolarWork<T>& w, double l0, int maxiter, int* iters_out) {
+    cudaStream_t s = h->stream;
+    std::vector<QdwhStep> sched = qdwh_schedule(l0, maxiter);
+    if (iters_out) *iters_out = (int)sched.size();
+    for (const QdwhStep& st : sched) {
+        if (st.qr) {
+            const int mb = ms + n;
+            stack_kernel<T><<<grid_for2((size_t)mb * n, h->num_sms), 256, 0, s>>>(ms, n, w.X, ms, w.B, mb, sqrt(st.c));
+            count_launch();
+            MAK_LAUNCH_CHECK(h, "stack_kernel");
+            int rc = qr_fused_t<T>(h, MAKB200_QR_COMPACT, mb, n, w.B, mb, w.Q, mb, (T*)nullptr, 0, w.sub, w.sub_bytes);
+            if (rc) return rc;
+            const double al = (st.a - st.b / st.c) / sqrt(st.c), be = st.b / st.c;
+            MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, ms, n, n, mk<T>(al), w.Q, mb, w.Q + ms, mb,
+                      mk<T>(be), w.X, ms, nullptr, 0);
+        } else {
+            eye_kernel<T><<<grid_for2((size_t)n * n, h->num_sms), 256, 0, s>>>(n, w.Z, n);
+            count_launch();
+            MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, n, n, ms, mk<T>(st.c), w.X, ms, w.X, ms, one<T>(),
+                      w.Z, n, nullptr, 0);
+            int rc = potrf_blocked<T>(h, n, w.Z, n, w.L, n, w.Linv, w.info);
+            if (rc) return rc;
+            rc = trsm_right<T>(h, true, ms, n, w.X, ms, w.L, n, w.Linv, w.Y, ms, w.Tmp);
+            if (rc) return rc;
+            rc = trsm_right<T>(h, false, ms, n, w.Y, ms, w.L, n, w.Linv, w.Y2, ms, w.Tmp);
+            if (rc) return rc;
+            axpby_kernel<T><<<grid_for2((size_t)ms * n, h->num_sms), 256, 0, s>>>(ms, n, st.b / st.c, w.X, ms,
+                                                                                  st.a - st.b / st.c, w.Y2, ms);
+            count_launch();
+            MAK_LAUNCH_CHECK(h, "axpby_kernel");
+        }
+    }
+    return 0;
+}
+
+template <typename T>
+int polar_qdwh_t(makb200_handle* h, int m, int n, T* A, int lda, T* W, int ldw, T* P, int ldp, double l0,
+                 int maxiter, void* work, size_t lwork, int* iters_host, int* info_dev) {
+    if (n <= 0 || m <= 0) return 0;
+    cudaStream_t s = h->stream;
+    const bool tall = polar_tall(m, n);
+    Arena ar(work, lwork);
+    PolarWork<T> w;
+    polar_carve<T>(h, ar, m, n, tall, &w);
+    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    MAK_CUDA(h, cudaMemsetAsync(w.info, 0, sizeof(int) * 4, s));
+    PhaseTimer pt(s);
+    pt.mark("start");
+    const T* src = A;
+    int lds = lda, ms = m;
+    if (tall) {
+        // A = Q0 R0 first (as PolarNewton does, implementations/polar.jl:131-135); iterate on R0
+        int rc = qr_fused_t<T>(h, MAKB200_QR_COMPACT, m, n, A, lda, w.Q0, m, w.R0, n, w.sub, w.sub_bytes);
+        if (rc) return rc;
+        src = w.R0; lds = n; ms = n;
+    }
+    const int np = grid_for2((size_t)ms * n, h->num_sms) < 1024 ? grid_for2((size_t)ms * n, h->num_sms) : 1024;
+    fro2_partial_kernel<T><<<np, 256, 0, s>>>(ms, n, src, lds, w.partial);
+    fro2_final_kernel<<<1, 256, 0, s>>>(np, w.partial, w.scal);
+    scale_copy_kernel<T><<<grid_for2((size_t)ms * n, h->num_sms), 256, 0, s>>>(ms, n, src, lds, w.X, ms, w.scal);
+    count_launch(3);
+    MAK_LAUNCH_CHECK(h, "scale_copy_kernel");
+    pt.mark("prep");
+    int rc = qdwh_iterate<T>(h, ms, n, w, l0, maxiter, iters_host);
+    if (rc) return rc;
+    pt.mark("qdwh");
+    // W, P
+    if (tall) {
+        MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_N, m, n, n, one<T>(), w.Q0, m, w.X, n, zero<T>(), W, ldw,
+                  nullptr, 0);
+    } else {
+        copy2d_kernel<T><<<grid_for2((size_t)m * n, h->num_sms), 256, 0, s>>>(m, n, w.X, ms, W, ldw);
+        count_launch();
+    }
+    if (P && ldp > 0) {
+        // P = sym(W^H A) = sym(X^H src)   (project_hermitian!, polar.jl:108)
+        MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, n, n, ms, one<T>(), w.X, ms, src, lds, zero<T>(), w.Z, n,
+                  nullptr, 0);
+        int nb32 = (n + 31) / 32;
+        symmetrize_kernel<T><<<dim3(nb32, nb32), dim3(32, 8), 0, s>>>(n, w.Z, n, P, ldp);
+        count_launch();
+        MAK_LAUNCH_CHECK(h, "symmetrize_kernel");
+    }
+    pt.mark("WP");
+    pt.report("polar");
+    if (info_dev) MAK_CUDA(h, cudaMemcpyAsync(info_dev, w.info, sizeof(int), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// SVD via polar + eigh
+// ---------------------------------------------------------------------------------------
+// S[j] = max(w[n-1-j], 0);  Vh[j, :] = conj(V[:, n-1-j])   (descending order)
+template <typename T>
+__global__ void svd_reorder_kernel(int n, int k, const double* __restrict__ w, const T* __restrict__ V, int ldv,
+                                   double* __restrict__ S, T* __restrict__ Vh, int ldvh) {
+    __shared__ T tile[32][33];
+    const int bi = blockIdx.x, bj = blockIdx.y, tx = threadIdx.x, ty = threadIdx.y;
+    // tile of V: rows bi*32.. (index i), source columns n-1-(bj*32+kk)
+    for (int kk = ty; kk < 32; kk += 8) {
+        int i = bi * 32 + tx, j = bj * 32 + kk;
+        tile[kk][tx] = (i < n && j < k) ? V[(size_t)(n - 1 - j) * ldv + i] : zero<T>();
+    }
+    __syncthreads();
+    for (int kk = ty; kk < 32; kk += 8) {
+        int j = bj * 32 + tx, i = bi * 32 + kk;  // Vh[j, i] = conj(V[i, n-1-j]) = conj(tile[tx][kk])
+        if (j < k && i < n && Vh) Vh[(size_t)i * ldvh + j] = conj_(tile[tx][kk]);
+    }
+    if (bi == 0 && ty == 0) {
+        int j = bj * 32 + tx;
+        if (j < k) { double v = w[n - 1 - j]; S[j] = v > 0.0 ? v : 0.0; }
+    }
+}
+
+template <typename T>
+struct SvdWork {
+    T *Wp, *P, *V, *At, *Ut, *Vht;
+    double* wv;
+    void* sub;
+    size_t sub_bytes;
+};
+
+template <typename T, typename AR>
+static void svd_carve(makb200_handle* h, AR& ar, int m, int n, SvdWork<T>* w) {
+    const bool wide = m < n;
+    const int mm = wide ? n : m, nn = wide ? m : n;  // work on the tall orientation
+    size_t N = (size_t)(nn > 0 ? nn : 1), M = (size_t)(mm > 0 ? mm : 1);
+    w->Wp = ar.template get<T>(M * N);
+    w->P = ar.template get<T>(N * N);
+    w->V = ar.template get<T>(N * N);
+    w->wv = ar.template get<double>(N);
+    w->At = wide ? ar.template get<T>(M * N) : nullptr;
+    w->Ut = wide ? ar.template get<T>(M * N) : nullptr;
+    w->Vht = wide ? ar.template get<T>(N * N) : nullptr;
+    size_t a = polar_worksize_t<T>(h, mm, nn);
+    size_t b = eigh_worksize_t<T>(h, nn);
+    w->sub_bytes = a > b ? a : b;
+    w->sub = ar.template get<char>(w->sub_bytes);
+}
+
+template <typename T>
+size_t svd_worksize_t(makb200_handle* h, int m, int n) {
+    ArenaSize ar;
+    SvdWork<T> w;
+    svd_carve<T>(h, ar, m, n, &w);
+    return ar.off + 256;
+}
+
+// tall/square core: A (m x n, m >= n) -> U (m x n), S (n), Vh (n x n); U/Vh may be null (values)
+template <typename T>
+static int svd_tall(makb200_handle* h, int m, int n, T* A, int lda, double* S, T* U, int ldu, T* Vh, int ldvh,
+                    int fixgauge, double l0, SvdWork<T>& w, int* info_dev) {
+    cudaStream_t s = h->stream;
+    int iters = 0;
+    PhaseTimer pt(s);
+    pt.mark("start");
+    int rc = polar_qdwh_t<T>(h, m, n, A, lda, w.Wp, m, w.P, n, l0, 12, w.sub, w.sub_bytes, &iters, info_dev);
+    if (rc) return rc;
+    pt.mark("polar");
+    rc = eigh_t<T>(h, n, w.P, n, w.wv, w.V, n, 0, w.sub, w.sub_bytes, nullptr);
+    if (rc) return rc;
+    pt.mark("eigh");
+    const bool vectors = (U != nullptr && Vh != nullptr);
+    int nb32 = (n + 31) / 32;
+    T* Vh_eff = vectors ? Vh : nullptr;
+    svd_reorder_kernel<T><<<dim3(nb32, nb32), dim3(32, 8), 0, s>>>(n, n, w.wv, w.V, n, S, Vh_eff, ldvh);
+    count_launch();
+    MAK_LAUNCH_CHECK(h, "svd_reorder_kernel");
+    if (vectors) {
+        // U = W * V_desc = W * Vh^H
+        MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, m, n, n, one<T>(), w.Wp, m, Vh, ldvh, zero<T>(), U, ldu,
+                  nullptr, 0);
+        if (fixgauge) {
+            rc = gauge_columns<T>(h, m, n, U, ldu, Vh, ldvh, n);
+            if (rc) return rc;
+        }
+    }
+    pt.mark("UV");
+    pt.report("svd");
+    return 0;
+}
+
+template <typename T>
+int svd_t(makb200_handle* h, int m, int n, T* A, int lda, double* S, T* U, int ldu, T* Vh, int ldvh, int fixgauge,
+          double l0, void* work, size_t lwork, int* info_dev) {
+    if (m <= 0 || n <= 0) return 0;
+    cudaStream_t s = h->stream;
+    Arena ar(work, lwork);
+    SvdWork<T> w;
+    svd_carve<T>(h, ar, m, n, &w);
+    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    if (m >= n) return svd_tall<T>(h, m, n, A, lda, S, U, ldu, Vh, ldvh, fixgauge, l0, w, info_dev);
+    // wide: SVD of A^H (svd_via_adjoint!, implementations/svd.jl:134-142): A^H = U' S V'^H
+    //   => A = V' S U'^H : U = (Vh')^H (m x m), Vh = (U')^H (m x n)
+    const bool vectors = (U != nullptr && Vh != nullptr);
+    dim3 g((m + 31) / 32, (n + 31) / 32);
+    adjoint_kernel<T><<<g, dim3(32, 8), 0, s>>>(m, n, A, lda, w.At, n);
+    count_launch();
+    int rc = svd_tall<T>(h, n, m, w.At, n, S, vectors ? w.Ut : nullptr, n, vectors ? w.Vht : nullptr, m, 0, l0, w,
+                         info_dev);
+    if (rc) return rc;
+    if (vectors) {
+        dim3 g1((m + 31) / 32, (m + 31) / 32);
+        adjoint_kernel<T><<<g1, dim3(32, 8), 0, s>>>(m, m, w.Vht, m, U, ldu);
+        dim3 g2((n + 31) / 32, (m + 31) / 32);
+        adjoint_kernel<T><<<g2, dim3(32, 8), 0, s>>>(n, m, w.Ut, n, Vh, ldvh);
+        count_launch(2);
+        MAK_LAUNCH_CHECK(h, "adjoint_kernel");
+        if (fixgauge) return gauge_columns<T>(h, m, m, U, ldu, Vh, ldvh, n);
+    }
+    return 0;
+}
+
+#define INSTP(T)                                                                                             \
+    template size_t polar_worksize_t<T>(makb200_handle*, int, int);                                          \
+    template int polar_qdwh_t<T>(makb200_handle*, int, int, T*, int, T*, int, T*, int, double, int, void*,   \
+                                 size_t, int*, int*);                                                        \
+    template size_t svd_worksize_t<T>(makb200_handle*, int, int);                                            \
+    template int svd_t<T>(makb200_handle*, int, int, T*, int, double*, T*, int, T*, int, int, double, void*, \
+                          size_t, int*);
+INSTP(double)
+INSTP(cplx)
+
+}  // namespace mak

@@ -1,0 +1,14 @@
+#pragma once
+#include "common.cuh"
+namespace mak {
+int polar_init(makb200_handle* h);
+template <typename T> size_t polar_worksize_t(makb200_handle* h, int m, int n);
+// l0: lower bound on sigma_min(A / ||A||_F); iters_host (optional, HOST) receives the step count
+template <typename T>
+int polar_qdwh_t(makb200_handle* h, int m, int n, T* A, int lda, T* W, int ldw, T* P, int ldp, double l0,
+                 int maxiter, void* work, size_t lwork, int* iters_host, int* info_dev);
+template <typename T> size_t svd_worksize_t(makb200_handle* h, int m, int n);
+template <typename T>
+int svd_t(makb200_handle* h, int m, int n, T* A, int lda, double* S, T* U, int ldu, T* Vh, int ldvh, int fixgauge,
+          double l0, void* work, size_t lwork, int* info_dev);
+}  // namespace mak

@@ -182,6 +182,7 @@ static cudaError_t launch_panel(makb200_handle* h, int mp, int ib, T* A, int lda
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    count_launch();
     return cudaLaunchKernelEx(&cfg, panel_kernel<T>, mp, ib, A, lda, tau, Tout, ldt, rpc);
 }
 
@@ -390,7 +391,8 @@ static int geqrf_blocked(makb200_handle* h, int m, int n, T* A, int lda, QrWork<
             // explicit V for this inner block into Vw[:, i0:i0+ib] (zeros above the diagonal)
             copy_v_kernel<T><<<grid_for((size_t)mp * ib, h->num_sms), 256, 0, s>>>(
                 mp, ib, i0, Ap + (size_t)i0 * lda, lda, w.Vw + (size_t)i0 * mp, mp);
-            MAK_LAUNCH_CHECK(h, "copy_v_kernel");
+            count_launch();
+    MAK_LAUNCH_CHECK(h, "copy_v_kernel");
             const T* Vi = w.Vw + (size_t)i0 * mp + i0;
             // update the rest of the outer panel
             const int nci = jb - i0 - ib;
@@ -405,6 +407,7 @@ static int geqrf_blocked(makb200_handle* h, int m, int n, T* A, int lda, QrWork<
                 MAK_GEMM(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, i0, ib, mp, one_, w.Vw, mp,
                          w.Vw + (size_t)i0 * mp, mp, zero_, w.G, nb, w.ws, w.ws_bytes);
                 t_couple_kernel<T><<<ib, 128, sizeof(T) * i0, s>>>(i0, ib, Tb, nb, w.G, nb);
+                count_launch();
                 MAK_LAUNCH_CHECK(h, "t_couple_kernel");
             }
         }
@@ -425,6 +428,7 @@ static int orgqr_blocked(makb200_handle* h, int m, int ncols, int k, const T* A,
     cudaStream_t s = h->stream;
     if (m <= 0 || ncols <= 0) return 0;
     set_identity_kernel<T><<<grid_for((size_t)m * ncols, h->num_sms), 256, 0, s>>>(m, ncols, Q, ldq);
+    count_launch();
     MAK_LAUNCH_CHECK(h, "set_identity_kernel");
     if (k == 0) return 0;
     const int nb = w.nb;
@@ -436,7 +440,8 @@ static int orgqr_blocked(makb200_handle* h, int m, int ncols, int k, const T* A,
         const T* Ap = A + (size_t)j0 * lda + j0;
         const T* Tb = w.Tall + (size_t)b * nb * nb;
         copy_v_kernel<T><<<grid_for((size_t)mp * jb, h->num_sms), 256, 0, s>>>(mp, jb, 0, Ap, lda, w.Vw, mp);
-        MAK_LAUNCH_CHECK(h, "copy_v_kernel");
+        count_launch();
+    MAK_LAUNCH_CHECK(h, "copy_v_kernel");
         // all columns j0 .. ncols-1 (own block columns are still [I;0])
         const int nc = ncols - j0;
         int rc = apply_block_reflector<T>(h, false, mp, nc, jb, w.Vw, mp, Tb, nb, Q + (size_t)j0 * ldq + j0, ldq, w);
@@ -474,6 +479,7 @@ int qr_fused_t(makb200_handle* h, int mode, int m, int n, T* A, int lda, T* Q, i
         const int rr = ncq;
         if (rr > 0 && n > 0) {
             extract_r_kernel<T><<<grid_for((size_t)rr * n, h->num_sms), 256, 0, h->stream>>>(rr, n, m, A, lda, R, ldr);
+            count_launch();
             MAK_LAUNCH_CHECK(h, "extract_r_kernel");
         }
     }
@@ -531,11 +537,13 @@ int orgqr_t(makb200_handle* h, int m, int ncols, int k, const T* A, int lda, con
             const int mp = m - j0;
             copy_v_kernel<T><<<grid_for((size_t)mp * jb, h->num_sms), 256, 0, s>>>(
                 mp, jb, 0, A + (size_t)j0 * lda + j0, lda, w.Vw, mp);
-            MAK_LAUNCH_CHECK(h, "copy_v_kernel");
+            count_launch();
+    MAK_LAUNCH_CHECK(h, "copy_v_kernel");
             MAK_GEMM(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, jb, jb, mp, one<T>(), w.Vw, mp, w.Vw, mp, zero<T>(),
                      w.G, nb, w.ws, w.ws_bytes);
             larft_diag_kernel<T><<<1, 128, 0, s>>>(jb, tau + j0, w.Tall + (size_t)b * nb * nb, nb, w.G, nb);
-            MAK_LAUNCH_CHECK(h, "larft_diag_kernel");
+            count_launch();
+        MAK_LAUNCH_CHECK(h, "larft_diag_kernel");
         }
     }
     return orgqr_blocked<T>(h, m, ncols, k, A, lda, Q, ldq, w);
@@ -568,11 +576,13 @@ int ormqr_left_t(makb200_handle* h, int m, int k, const T* A, int lda, const T* 
         const int mp = m - j0;
         copy_v_kernel<T><<<grid_for((size_t)mp * jb, h->num_sms), 256, 0, s>>>(mp, jb, 0, A + (size_t)j0 * lda + j0,
                                                                                 lda, w.Vw, mp);
-        MAK_LAUNCH_CHECK(h, "copy_v_kernel");
+        count_launch();
+    MAK_LAUNCH_CHECK(h, "copy_v_kernel");
         MAK_CUDA(h, cudaMemsetAsync(Tb, 0, sizeof(T) * (size_t)nb * nb, s));
         MAK_GEMM(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, jb, jb, mp, one<T>(), w.Vw, mp, w.Vw, mp, zero<T>(), w.G,
                  nb, w.ws, w.ws_bytes);
         larft_diag_kernel<T><<<1, 128, 0, s>>>(jb, tau + j0, Tb, nb, w.G, nb);
+        count_launch();
         MAK_LAUNCH_CHECK(h, "larft_diag_kernel");
         int rc = apply_block_reflector<T>(h, false, mp, nc, jb, w.Vw, mp, Tb, nb, C + j0, ldc, w);
         if (rc) return rc;

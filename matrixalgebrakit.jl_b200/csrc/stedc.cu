@@ -292,6 +292,7 @@ int stedc(makb200_handle* h, int n, const double* d, const double* e, double* w,
     double* Zout = (L % 2 == 0) ? Zw : Z;
     int ldo = (L % 2 == 0) ? ldw : ldz;
     dc_leaf_kernel<<<(nleaf + 31) / 32, 32, 0, st>>>(nleaf, bnd_dev, b.ctx.D, b.E, Zin, ldi, b.info);
+    count_launch(4);  // scale, tear, leaf, finish
     MAK_LAUNCH_CHECK(h, "dc_leaf_kernel");
 
     std::vector<Merge> hm;
@@ -329,6 +330,7 @@ int stedc(makb200_handle* h, int n, const double* d, const double* e, double* w,
         if (ge != cudaSuccess) return cuda_fail(h, ge, "dc gemm_grouped");
         dc_scatter_kernel<<<gp, 256, 0, st>>>(b.ctx, b.merges, Zin, ldi, Zout, ldo);
         MAK_LAUNCH_CHECK(h, "dc_scatter_kernel");
+        count_launch(10);  // the ten non-GEMM kernels of this level
         std::swap(Zin, Zout);
         std::swap(ldi, ldo);
         std::swap(b.ctx.D, b.ctx.Dn);

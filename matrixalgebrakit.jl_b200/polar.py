@@ -1,0 +1,76 @@
+"""left_polar on B200 — mirrors src/implementations/polar.jl: ``check_input`` (:6-17),
+``initialize_output`` (:33-38), ``left_polar!(A, (W,P), alg)`` (:59-70,99-111).  The B200
+algorithm is ``B200_QDWH`` (new); ``PolarViaSVD`` is provided on top of the B200 SVD."""
+import ctypes as C
+
+import torch
+
+from . import _core
+from .algorithms import Algorithm, select_algorithm
+
+
+def initialize_output(A):
+    m, n = A.shape
+    return (_core.colmajor_empty(m, n, A.dtype, A.device), _core.colmajor_empty(n, n, A.dtype, A.device))
+
+
+def check_input(A, WP):
+    m, n = A.shape
+    if m < n:
+        raise ValueError("`left_polar!` requires a matrix A with at least as many rows as columns")  # polar.jl:9-10
+    if not _core.is_colmajor(A):
+        raise ValueError("A: column-major matrix expected")
+    _core.dtype_code(A)
+    W, P = WP
+    if tuple(W.shape) != (m, n) or W.dtype != A.dtype or not _core.is_colmajor(W):
+        raise ValueError(f"W: {m} x {n} column-major matrix expected")
+    if P is not None and P.numel() > 0:
+        if tuple(P.shape) != (n, n) or P.dtype != A.dtype or not _core.is_colmajor(P):
+            raise ValueError(f"P: {n} x {n} column-major matrix (or an empty one) expected")
+
+
+def left_polar_(A, WP=None, alg=None, **kw):
+    """``left_polar!(A, (W,P), alg)``; a zero-length P means "skip P" (polar.jl:14,64,102)."""
+    alg = select_algorithm("left_polar", A, alg, **kw)
+    if WP is None:
+        WP = initialize_output(A)
+    check_input(A, WP)
+    W, P = WP
+    if isinstance(alg, Algorithm) and alg.name == "PolarViaSVD":
+        return _left_polar_via_svd_(A, W, P, alg)
+    if not isinstance(alg, Algorithm) or alg.name != "QDWH":
+        raise ValueError(f"left_polar: algorithm {alg} is not provided by the B200 driver")
+    m, n = A.shape
+    if m == 0 or n == 0:
+        return W, P
+    h = _core.Handle.get(A.device)
+    dt = _core.dtype_code(A)
+    want_p = P is not None and P.numel() > 0
+    lw = h.lib.makb200_polar_worksize(h.h, dt, m, n)
+    work = h.workspace(lw)
+    iters = C.c_int(0)
+    rc = h.lib.makb200_polar_qdwh(h.h, dt, m, n, _core.ptr(A), _core.ld(A), _core.ptr(W), _core.ld(W),
+                                  _core.ptr(P) if want_p else C.c_void_p(0), _core.ld(P) if want_p else 0,
+                                  float(alg.get("tol") or 0.0) * 0.0 + float(alg.get("l0", 0.0) or 0.0),
+                                  int(alg.get("maxiter") or 0), _core.ptr(work), work.numel(), C.byref(iters),
+                                  C.c_void_p(0))
+    h.check(rc, "makb200_polar_qdwh")
+    return W, P
+
+
+def _left_polar_via_svd_(A, W, P, alg):
+    """``PolarViaSVD`` recipe (polar.jl:59-70) on the B200 SVD and DMMA GEMM."""
+    from .gemm import gemm_
+    from .svd import svd_compact_
+    U, S, Vh = svd_compact_(A, None, alg.get("svd_alg"))
+    gemm_(W, U, Vh)
+    if P is not None and P.numel() > 0:
+        B = _core.colmajor_empty(Vh.shape[0], Vh.shape[1], Vh.dtype, Vh.device)
+        B.copy_(Vh * torch.sqrt(S).to(Vh.dtype)[:, None])
+        gemm_(P, B, B, opa="C", opb="N")
+    return W, P
+
+
+def left_polar(A, alg=None, **kw):
+    from .qr import copy_input
+    return left_polar_(copy_input(A), None, alg, **kw)

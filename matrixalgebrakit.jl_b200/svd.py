@@ -1,0 +1,143 @@
+"""svd_compact / svd_vals / svd_trunc on B200 — mirrors src/implementations/svd.jl:
+``check_input`` (:23-35), ``initialize_output`` (:81-88), ``svd_compact_<alg>!(driver, A, U, S, Vh;
+fixgauge)`` (:196-201), ``svd_vals`` (:214-219), ``svd_trunc!`` / ``svd_trunc_no_error!`` (:226-237).
+S is held as the vector of the ``Diagonal`` (``diagview(S)``)."""
+import ctypes as C
+
+import torch
+
+from . import _core
+from .algorithms import Algorithm, TruncatedAlgorithm, resolve_driver, select_algorithm
+from .truncation import findtruncated_svd, select_truncation, truncation_error_
+
+
+def initialize_output(A):
+    m, n = A.shape
+    k = min(m, n)
+    return (_core.colmajor_empty(m, k, A.dtype, A.device), torch.empty(k, dtype=torch.float64, device=A.device),
+            _core.colmajor_empty(k, n, A.dtype, A.device))
+
+
+def check_input(A, USVh):
+    if not _core.is_colmajor(A):
+        raise ValueError("A: column-major matrix expected")
+    _core.dtype_code(A)
+    m, n = A.shape
+    k = min(m, n)
+    U, S, Vh = USVh
+    if tuple(U.shape) != (m, k) or U.dtype != A.dtype or not _core.is_colmajor(U):
+        raise ValueError(f"U: {m} x {k} column-major matrix expected")
+    if S.dim() != 1 or S.shape[0] != k or S.dtype != torch.float64:
+        raise ValueError("S: real vector (diagview of the Diagonal) of length min(m,n) expected")
+    if tuple(Vh.shape) != (k, n) or Vh.dtype != A.dtype or not _core.is_colmajor(Vh):
+        raise ValueError(f"Vh: {k} x {n} column-major matrix expected")
+
+
+def _alg_ok(alg):
+    if not isinstance(alg, Algorithm) or alg.name != "SVDViaPolar":
+        raise ValueError(f"svd: algorithm {alg} is not provided by the B200 driver (use SVDViaPolar)")
+    resolve_driver(alg.get("driver"), None)
+
+
+def _gesvdp_(A, S, U, Vh, fixgauge):
+    h = _core.Handle.get(A.device)
+    m, n = A.shape
+    dt = _core.dtype_code(A)
+    lw = h.lib.makb200_svd_worksize(h.h, dt, m, n)
+    work = h.workspace(lw)
+    vec = U is not None
+    rc = h.lib.makb200_svd(h.h, dt, int(bool(fixgauge)), m, n, _core.ptr(A), _core.ld(A), _core.ptr(S),
+                           _core.ptr(U) if vec else C.c_void_p(0), _core.ld(U) if vec else 0,
+                           _core.ptr(Vh) if vec else C.c_void_p(0), _core.ld(Vh) if vec else 0, 0.0,
+                           _core.ptr(work), work.numel(), C.c_void_p(0))
+    h.check(rc, "makb200_svd")
+
+
+def svd_compact_(A, USVh=None, alg=None, **kw):
+    """``svd_compact!(A, (U,S,Vh), alg)`` (svd.jl:169-172,196-201). Destroys A."""
+    alg = select_algorithm("svd_compact", A, alg, **kw)
+    _alg_ok(alg)
+    if USVh is None:
+        USVh = initialize_output(A)
+    check_input(A, USVh)
+    U, S, Vh = USVh
+    if A.numel() == 0:  # svd.jl:197: one!(U), zero!(S), one!(Vh)
+        U.zero_(); Vh.zero_(); S.zero_()
+        if U.numel():
+            U.diagonal().fill_(1)
+        if Vh.numel():
+            Vh.diagonal().fill_(1)
+        return U, S, Vh
+    _gesvdp_(A, S, U, Vh, alg.get("fixgauge", True))
+    return U, S, Vh
+
+
+def svd_vals_(A, S=None, alg=None, **kw):
+    """``svd_vals!`` (svd.jl:214-219): job 'N'."""
+    alg = select_algorithm("svd_vals", A, alg, **kw)
+    _alg_ok(alg)
+    k = min(A.shape)
+    if S is None:
+        S = torch.empty(k, dtype=torch.float64, device=A.device)
+    if A.numel() == 0:
+        return S.zero_()
+    _core.dtype_code(A)
+    _gesvdp_(A, S, None, None, False)
+    return S
+
+
+def _copy_input(A):
+    from .qr import copy_input
+    return copy_input(A)
+
+
+def svd_compact(A, alg=None, **kw):
+    return svd_compact_(_copy_input(A), None, alg, **kw)
+
+
+def svd_vals(A, alg=None, **kw):
+    return svd_vals_(_copy_input(A), None, alg, **kw)
+
+
+def _select_trunc_alg(A, alg, trunc, kw):
+    """``select_algorithm(svd_trunc!, A, alg; trunc, kw...)`` (interface/svd.jl:181-192)."""
+    if isinstance(alg, TruncatedAlgorithm):
+        if trunc is not None:
+            raise ValueError("`trunc` can't be specified when `alg` is a `TruncatedAlgorithm`")
+        return alg
+    return TruncatedAlgorithm(select_algorithm("svd_compact", A, alg, **kw), select_truncation(trunc))
+
+
+def _truncate(U, S, Vh, strategy):
+    ind = findtruncated_svd(S, strategy)
+    Ut = _core.colmajor_empty(U.shape[0], len(ind), U.dtype, U.device)
+    Ut.copy_(U[:, ind])
+    Vt = _core.colmajor_empty(len(ind), Vh.shape[1], Vh.dtype, Vh.device)
+    Vt.copy_(Vh[ind, :])
+    return (Ut, S[ind].clone(), Vt), ind
+
+
+def svd_trunc_no_error_(A, USVh=None, alg=None, trunc=None, **kw):
+    """``svd_trunc_no_error!`` (svd.jl:226-230): no device->host read of the error."""
+    talg = _select_trunc_alg(A, alg, trunc, kw)
+    U, S, Vh = svd_compact_(A, USVh, talg.alg)
+    out, _ = _truncate(U, S, Vh, talg.trunc)
+    return out
+
+
+def svd_trunc_(A, USVh=None, alg=None, trunc=None, **kw):
+    """``svd_trunc!`` (svd.jl:232-237): full compact SVD, slice, eps = norm of the discarded
+    values; clobbers the untruncated S (truncation.jl:171-174)."""
+    talg = _select_trunc_alg(A, alg, trunc, kw)
+    U, S, Vh = svd_compact_(A, USVh, talg.alg)
+    out, ind = _truncate(U, S, Vh, talg.trunc)
+    eps_ = truncation_error_(S, ind)
+    return out + (eps_,)
+
+
+def svd_trunc(A, alg=None, trunc=None, **kw):
+    return svd_trunc_(_copy_input(A), None, alg, trunc, **kw)
+
+
+def svd_trunc_no_error(A, alg=None, trunc=None, **kw):
+    return svd_trunc_no_error_(_copy_input(A), None, alg, trunc, **kw)

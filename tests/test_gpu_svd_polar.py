@@ -1,0 +1,160 @@
+"""svd_compact!/svd_trunc!/left_polar! on B200 vs the LAPACK-replay oracle.
+Tolerances (north_star): ||A - U S Vh||/||A||, ||U^H U - I||_F, ||Vh Vh^H - I||_F,
+max|s - s_oracle|/s_1, ||W P - A||/||A||, ||W^H W - I||_F <= 10*n*eps, n = max(m, n)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mak_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _svd(A_np, **kw):
+    import makb200
+    A = makb200.to_device(A_np)
+    U, S, Vh = makb200.svd_compact(A, **kw)
+    torch.cuda.synchronize()
+    assert np.array_equal(makb200.to_numpy(A), A_np)
+    return makb200.to_numpy(U), S.cpu().numpy(), makb200.to_numpy(Vh)
+
+
+def _check_svd(A, U, S, Vh, vec_cmp=True):
+    m, n = A.shape
+    k = min(m, n)
+    tol = O.tol_for(m, n)
+    Uo, So, Vho = O.svd_compact(A)
+    assert U.shape == (m, k) and S.shape == (k,) and Vh.shape == (k, n)
+    assert np.all(S >= 0) and np.all(np.diff(S) <= 0)
+    assert np.max(np.abs(S - So)) / So[0] <= tol
+    assert O.rel_resid(A, U * S, Vh) <= tol
+    assert O.orth_err(U) <= tol
+    assert O.orth_err(Vh, "right") <= tol
+    piv = O._argmaxabs_cols(U)
+    assert np.all(piv.real > 0) and np.all(np.abs(piv.imag) <= 1e-15)
+    if vec_cmp and m > 1:
+        gap = np.minimum(np.abs(np.diff(So, prepend=np.inf)), np.abs(np.diff(So, append=-np.inf)))
+        gap = np.minimum(gap, So) if m != n else gap
+        err = np.maximum(np.linalg.norm(U - Uo, axis=0), np.linalg.norm(Vh - Vho, axis=1))
+        mod = np.abs(Uo)
+        top2 = np.sort(mod, axis=0)[-2:]
+        tie = (top2[1] - top2[0]) < 1e-8
+        assert np.all((err <= 200 * max(m, n) * O.EPS * So[0] / gap + 1e-12) | tie)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("m,n", [(54, 37), (54, 54), (37, 54), (1, 1), (3, 2), (200, 200), (300, 130), (130, 300),
+                                 (513, 513)])
+def test_svd_compact_vs_oracle(m, n, dtype):
+    A = O.randn_matrix(m, n, dtype, seed=123 + m + n)
+    U, S, Vh = _svd(A)
+    _check_svd(A, U, S, Vh)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("m,n", [(0, 5), (5, 0), (0, 0)])
+def test_svd_empty(m, n, dtype):
+    # test/decompositions/svd.jl:22, svd.jl:197
+    import makb200
+    A = makb200.to_device(O.randn_matrix(m, n, dtype, 1))
+    U, S, Vh = makb200.svd_compact(A)
+    k = min(m, n)
+    assert tuple(U.shape) == (m, k) and tuple(Vh.shape) == (k, n) and S.numel() == k
+
+
+def test_svd_graded_and_vals():
+    import makb200
+    n = 128
+    Uq, _ = O.qr_compact(O.randn_matrix(n, n, "f64", 5))
+    Vq, _ = O.qr_compact(O.randn_matrix(n, n, "f64", 6))
+    sv = 10.0 ** (-12 * np.arange(n) / n)
+    A = (Uq * sv) @ Vq
+    U, S, Vh = _svd(A)
+    tol = O.tol_for(n)
+    assert np.max(np.abs(S - sv)) / sv[0] <= tol
+    assert O.rel_resid(A, U * S, Vh) <= tol and O.orth_err(U) <= tol and O.orth_err(Vh, "right") <= tol
+    Sv = makb200.svd_vals(makb200.to_device(A)).cpu().numpy()
+    assert np.max(np.abs(Sv - sv)) / sv[0] <= tol
+    U2, S2, Vh2 = makb200.svd_compact(makb200.to_device(A), fixgauge=False)
+    assert O.rel_resid(A, makb200.to_numpy(U2) * S2.cpu().numpy(), makb200.to_numpy(Vh2)) <= tol
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_svd_trunc_vs_oracle(dtype):
+    import makb200
+    A0 = O.randn_matrix(54, 37, dtype, seed=9)
+    S0 = O.svd_vals(A0)
+    r = 17
+    U, S, Vh, eps = makb200.svd_trunc(makb200.to_device(A0), trunc=makb200.truncrank(r))
+    Uo, So, Vho, epso = O.svd_trunc(A0, O.truncrank(r))
+    Un, Sn, Vn = makb200.to_numpy(U), S.cpu().numpy(), makb200.to_numpy(Vh)
+    assert Un.shape == (54, r) and Vn.shape == (r, 37)
+    np.testing.assert_allclose(Sn, S0[:r], rtol=1e-12)
+    np.testing.assert_allclose(eps, epso, rtol=1e-10)
+    np.testing.assert_allclose(np.linalg.norm(A0 - (Un * Sn) @ Vn, 2), S0[r], rtol=1e-9)
+    assert np.linalg.norm(Un - Uo) < 1e-9 and np.linalg.norm(Vn - Vho) < 1e-9
+    # equivalence of the strategies (svd.jl:156-197)
+    for tr in (makb200.trunctol(atol=S0[r] + 1e-9), makb200.truncerror(atol=np.linalg.norm(S0[r:]) + 1e-9),
+               {"maxrank": r}):
+        U2, S2, Vh2 = makb200.svd_trunc_no_error(makb200.to_device(A0), trunc=tr)
+        assert S2.numel() == r
+    # fixed spectrum fixture (svd.jl:198-254)
+    Uq, _ = O.qr_compact(O.randn_matrix(4, 4, dtype, 1))
+    Vq, _ = O.qr_compact(O.randn_matrix(4, 4, dtype, 2))
+    Sd = np.array([0.9, 0.3, 0.1, 0.01])
+    A4 = (Uq * Sd) @ Vq
+    for tr, keep in (({"rtol": 0.2, "maxrank": 1}, 1), ({"rtol": 0.2, "maxrank": 3}, 2), ({"rtol": 0.5, "minrank": 3}, 3),
+                     ({"rtol": 0.2, "minrank": 1}, 2), (makb200.trunctol(atol=0.2), 2)):
+        U4, S4, V4, e4 = makb200.svd_trunc(makb200.to_device(A4), trunc=tr)
+        np.testing.assert_allclose(S4.cpu().numpy(), Sd[:keep], rtol=1e-12)
+        np.testing.assert_allclose(e4, np.linalg.norm(Sd[keep:]), rtol=1e-10)
+    with pytest.raises(ValueError):
+        talg = makb200.TruncatedAlgorithm(makb200.SVDViaPolar(), makb200.trunctol(atol=0.2))
+        makb200.svd_trunc(makb200.to_device(A4), alg=talg, trunc={"maxrank": 2})
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("m,n", [(54, 37), (54, 54), (200, 200), (400, 150), (1, 1), (600, 600)])
+def test_left_polar_vs_oracle(m, n, dtype):
+    import makb200
+    A0 = O.randn_matrix(m, n, dtype, seed=123 + m)
+    A = makb200.to_device(A0)
+    W, P = makb200.left_polar(A)
+    torch.cuda.synchronize()
+    Wn, Pn = makb200.to_numpy(W), makb200.to_numpy(P)
+    Wo, Po = O.left_polar(A0)
+    tol = O.tol_for(m, n)
+    assert O.rel_resid(A0, Wn, Pn) <= tol
+    assert O.orth_err(Wn) <= tol
+    assert np.array_equal(Pn, Pn.conj().T)
+    assert np.linalg.eigvalsh(Pn).min() > 0
+    cond = np.linalg.cond(A0)
+    assert np.linalg.norm(Wn - Wo) <= 50 * tol * max(1.0, cond / 100)
+    assert np.linalg.norm(Pn - Po) / np.linalg.norm(Po) <= 50 * tol
+
+
+def test_left_polar_skip_p_identity_and_errors():
+    import makb200
+    A0 = O.randn_matrix(54, 37, "c128", seed=3)
+    W = makb200.colmajor_empty(54, 37, torch.complex128, "cuda")
+    P = makb200.colmajor_empty(37, 37, torch.complex128, "cuda")
+    W2, P2 = makb200.left_polar_(makb200.to_device(A0), (W, P))
+    assert W2 is W and P2 is P          # test/testsuite/decompositions/polar.jl:30-31
+    Wn = makb200.to_numpy(W)
+    Pe = makb200.colmajor_empty(0, 0, torch.complex128, "cuda")
+    W3, _ = makb200.left_polar_(makb200.to_device(A0), (makb200.colmajor_empty(54, 37, torch.complex128, "cuda"), Pe))
+    assert np.linalg.norm(makb200.to_numpy(W3) - Wn) < 1e-12
+    with pytest.raises(ValueError):
+        makb200.left_polar(makb200.to_device(O.randn_matrix(3, 5)))
+    # PolarViaSVD on the B200 SVD gives the same factors
+    W4, P4 = makb200.left_polar(makb200.to_device(A0), alg=makb200.PolarViaSVD())
+    assert np.linalg.norm(makb200.to_numpy(W4) - Wn) < 1e-11
+    assert np.linalg.norm(makb200.to_numpy(P4) - makb200.to_numpy(P)) < 1e-11
+    # ill-conditioned (kappa = 1e10): still an isometry with a small residual
+    n = 100
+    Uq, _ = O.qr_compact(O.randn_matrix(n, n, "f64", 5))
+    Vq, _ = O.qr_compact(O.randn_matrix(n, n, "f64", 6))
+    A1 = (Uq * 10.0 ** (-10 * np.arange(n) / n)) @ Vq
+    W5, P5 = makb200.left_polar(makb200.to_device(A1))
+    W5, P5 = makb200.to_numpy(W5), makb200.to_numpy(P5)
+    assert O.orth_err(W5) <= O.tol_for(n) and O.rel_resid(A1, W5, P5) <= O.tol_for(n)
