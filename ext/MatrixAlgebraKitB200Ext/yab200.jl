@@ -1,0 +1,171 @@
+# YAB200 — "yet another" thin binding layer, the B200 twin of YACUSOLVER
+# (ext/MatrixAlgebraKitCUDAExt/yacusolver.jl of the reference).  Zero numerical logic: every
+# function is argument checking + one `ccall` into libmakb200 (include/makb200.h).
+#
+# NOTE: this file cannot be executed in the build environment (no Julia in the image); the
+# executable twin of this binding is matrixalgebrakit.jl_b200/_lib.py (ctypes, same symbols).
+module YAB200
+
+using CUDA
+using CUDA: CuPtr, CuMatrix, CuVector, StridedCuMatrix, StridedCuVector
+using LinearAlgebra: BlasFloat, checksquare, chkstride1
+
+const libmakb200 = get(ENV, "MAKB200_LIB", "libmakb200")
+const B200Float = Union{Float64, ComplexF64}
+
+const MAKB200_F64, MAKB200_C128 = Cint(0), Cint(1)
+const QR_COMPACT, QR_FULL = Cint(0), Cint(1)
+dtypecode(::Type{Float64}) = MAKB200_F64
+dtypecode(::Type{ComplexF64}) = MAKB200_C128
+
+# ---- handle: one per task/device, like cuSOLVER.dense_handle() (yacusolver.jl:76) ------------
+const HANDLES = Dict{Tuple{Int, UInt}, Ptr{Cvoid}}()
+function handle()
+    dev = CUDA.deviceid(CUDA.device())
+    key = (dev, objectid(current_task()))
+    h = get!(HANDLES, key) do
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:makb200_create, libmakb200), Cint, (Ref{Ptr{Cvoid}}, Cint), ref, dev)
+        rc == 0 || error("makb200_create failed with code $rc (needs an sm_100 device)")
+        ref[]
+    end
+    ccall((:makb200_set_stream, libmakb200), Cint, (Ptr{Cvoid}, CUDA.CUstream), h, CUDA.stream())
+    return h
+end
+
+function chkargsok(rc::Cint, what)
+    rc == 0 && return nothing
+    rc < 0 && throw(ArgumentError("$what: invalid value in argument $(-rc)"))  # LAPACK info < 0
+    msg = unsafe_string(ccall((:makb200_last_error, libmakb200), Cstring, (Ptr{Cvoid},), handle()))
+    error("$what failed with code $rc: $msg")
+end
+
+# workspace: caller-provided, borrowed from CUDA.jl's pool for the duration of the call
+with_workspace(f, nbytes) = (buf = CuVector{UInt8}(undef, max(nbytes, 1)); try f(buf) finally CUDA.unsafe_free!(buf) end)
+
+# ---- QR: qr_householder!(::B200, A, Q, R) in one fused call ------------------------------------
+function qr!(A::StridedCuMatrix{T}, Q::StridedCuMatrix{T}, R::StridedCuMatrix{T}; full::Bool, positive::Bool) where {T <: B200Float}
+    chkstride1(A, Q)
+    m, n = size(A)
+    h = handle()
+    mode = full ? QR_FULL : QR_COMPACT
+    lw = ccall((:makb200_qr_worksize, libmakb200), Csize_t, (Ptr{Cvoid}, Cint, Cint, Cint, Cint), h, dtypecode(T), mode, m, n)
+    computeR = length(R) > 0
+    with_workspace(lw) do work
+        rc = ccall((:makb200_qr, libmakb200), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, CuPtr{T}, Cint, CuPtr{T}, Cint, CuPtr{T}, Cint, CuPtr{UInt8}, Csize_t),
+            h, dtypecode(T), mode, positive, m, n, A, max(1, stride(A, 2)), Q, max(1, stride(Q, 2)),
+            computeR ? pointer(R) : CU_NULL, computeR ? max(1, stride(R, 2)) : 0, work, lw)
+        chkargsok(rc, "makb200_qr")
+    end
+    return Q, R
+end
+
+# ---- L1 shims: geqrf! / ungqr! (same call shapes as YACUSOLVER, yacusolver.jl:12-14) ----------
+function geqrf!(A::StridedCuMatrix{T}, tau::StridedCuVector{T} = similar(A, min(size(A)...))) where {T <: B200Float}
+    m, n = size(A)
+    h = handle()
+    lw = ccall((:makb200_geqrf_worksize, libmakb200), Csize_t, (Ptr{Cvoid}, Cint, Cint, Cint), h, dtypecode(T), m, n)
+    with_workspace(lw) do work
+        rc = ccall((:makb200_geqrf, libmakb200), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Cint, CuPtr{T}, Cint, CuPtr{T}, CuPtr{UInt8}, Csize_t),
+            h, dtypecode(T), m, n, A, max(1, stride(A, 2)), tau, work, lw)
+        chkargsok(rc, "makb200_geqrf")
+    end
+    return A, tau
+end
+
+function ungqr!(A::StridedCuMatrix{T}, tau::StridedCuVector{T}, Q::StridedCuMatrix{T}) where {T <: B200Float}
+    m, k = size(A, 1), length(tau)
+    ncols = size(Q, 2)
+    h = handle()
+    lw = ccall((:makb200_orgqr_worksize, libmakb200), Csize_t, (Ptr{Cvoid}, Cint, Cint, Cint, Cint), h, dtypecode(T), m, ncols, k)
+    with_workspace(lw) do work
+        rc = ccall((:makb200_orgqr, libmakb200), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Cint, Cint, CuPtr{T}, Cint, CuPtr{T}, CuPtr{T}, Cint, CuPtr{UInt8}, Csize_t),
+            h, dtypecode(T), m, ncols, k, A, max(1, stride(A, 2)), tau, Q, max(1, stride(Q, 2)), work, lw)
+        chkargsok(rc, "makb200_orgqr")
+    end
+    return Q
+end
+
+# ---- eigh: heevd!(A, W, V) (yacusolver.jl:766-810 call shape) -----------------------------------
+function heevd!(A::StridedCuMatrix{T}, W::StridedCuVector{Float64}, V::StridedCuMatrix{T}; fixgauge::Bool = false) where {T <: B200Float}
+    n = checksquare(A)
+    h = handle()
+    lw = ccall((:makb200_eigh_worksize, libmakb200), Csize_t, (Ptr{Cvoid}, Cint, Cint), h, dtypecode(T), n)
+    with_workspace(lw) do work
+        rc = ccall((:makb200_eigh, libmakb200), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Cint, CuPtr{T}, Cint, CuPtr{Float64}, CuPtr{T}, Cint, CuPtr{UInt8}, Csize_t, CuPtr{Cint}),
+            h, dtypecode(T), fixgauge, n, A, max(1, stride(A, 2)), W, V, max(1, stride(V, 2)), work, lw, CU_NULL)
+        chkargsok(rc, "makb200_eigh")
+    end
+    return W, V
+end
+
+# (||(A-A')/2||_F^2, max|A_ij|) in one pass: device half of check_hermitian
+function hermitian_defect(A::StridedCuMatrix{T}) where {T <: B200Float}
+    n = checksquare(A)
+    out = CUDA.zeros(Float64, 2)
+    rc = ccall((:makb200_hermitian_defect, libmakb200), Cint, (Ptr{Cvoid}, Cint, Cint, CuPtr{T}, Cint, CuPtr{Float64}),
+        handle(), dtypecode(T), n, A, max(1, stride(A, 2)), out)
+    chkargsok(rc, "makb200_hermitian_defect")
+    d2, mx = Array(out)
+    return sqrt(d2), mx
+end
+
+# ---- svd: gesvdp!(A, S, U, Vᴴ) (QDWH + eigh; yacusolver.jl:101-181 call shape) ------------------
+function gesvdp!(A::StridedCuMatrix{T}, S::StridedCuVector{Float64}, U::StridedCuMatrix{T}, Vᴴ::StridedCuMatrix{T};
+        fixgauge::Bool = false, l0::Float64 = 0.0) where {T <: B200Float}
+    m, n = size(A)
+    vectors = length(U) > 0 && length(Vᴴ) > 0   # job 'N' when both are empty (yalapack.jl:2105-2106)
+    h = handle()
+    lw = ccall((:makb200_svd_worksize, libmakb200), Csize_t, (Ptr{Cvoid}, Cint, Cint, Cint), h, dtypecode(T), m, n)
+    with_workspace(lw) do work
+        rc = ccall((:makb200_svd, libmakb200), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Cint, Cint, CuPtr{T}, Cint, CuPtr{Float64}, CuPtr{T}, Cint, CuPtr{T}, Cint, Cdouble, CuPtr{UInt8}, Csize_t, CuPtr{Cint}),
+            h, dtypecode(T), fixgauge, m, n, A, max(1, stride(A, 2)), S,
+            vectors ? pointer(U) : CU_NULL, vectors ? max(1, stride(U, 2)) : 0,
+            vectors ? pointer(Vᴴ) : CU_NULL, vectors ? max(1, stride(Vᴴ, 2)) : 0, l0, work, lw, CU_NULL)
+        chkargsok(rc, "makb200_svd")
+    end
+    return S, U, Vᴴ
+end
+
+# ---- polar: QDWH ----------------------------------------------------------------------------------
+function polar_qdwh!(A::StridedCuMatrix{T}, W::StridedCuMatrix{T}, P::StridedCuMatrix{T}; l0::Float64 = 0.0, maxiter::Int = 12) where {T <: B200Float}
+    m, n = size(A)
+    wantP = length(P) > 0
+    h = handle()
+    lw = ccall((:makb200_polar_worksize, libmakb200), Csize_t, (Ptr{Cvoid}, Cint, Cint, Cint), h, dtypecode(T), m, n)
+    iters = Ref{Cint}(0)
+    with_workspace(lw) do work
+        rc = ccall((:makb200_polar_qdwh, libmakb200), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Cint, CuPtr{T}, Cint, CuPtr{T}, Cint, CuPtr{T}, Cint, Cdouble, Cint, CuPtr{UInt8}, Csize_t, Ref{Cint}, CuPtr{Cint}),
+            h, dtypecode(T), m, n, A, max(1, stride(A, 2)), W, max(1, stride(W, 2)),
+            wantP ? pointer(P) : CU_NULL, wantP ? max(1, stride(P, 2)) : 0, l0, maxiter, work, lw, iters, CU_NULL)
+        chkargsok(rc, "makb200_polar_qdwh")
+    end
+    return W, P
+end
+
+# ---- batched qr_compact! over a vector of blocks ---------------------------------------------------
+function qr_batched!(As::Vector{<:StridedCuMatrix{T}}, Qs::Vector{<:StridedCuMatrix{T}}, Rs::Vector{<:StridedCuMatrix{T}}) where {T <: B200Float}
+    b = length(As)
+    m = Cint[size(A, 1) for A in As]; n = Cint[size(A, 2) for A in As]
+    lda = Cint[max(1, stride(A, 2)) for A in As]; ldq = Cint[max(1, stride(Q, 2)) for Q in Qs]
+    ldr = Cint[length(R) > 0 ? max(1, stride(R, 2)) : 0 for R in Rs]
+    Ap = CuPtr{T}[pointer(A) for A in As]; Qp = CuPtr{T}[pointer(Q) for Q in Qs]
+    Rp = CuPtr{T}[length(R) > 0 ? pointer(R) : CU_NULL for R in Rs]
+    h = handle()
+    lw = ccall((:makb200_qr_batched_worksize, libmakb200), Csize_t, (Ptr{Cvoid}, Cint, Cint, Ptr{Cint}, Ptr{Cint}), h, dtypecode(T), b, m, n)
+    with_workspace(lw) do work
+        rc = ccall((:makb200_qr_batched, libmakb200), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Ptr{Cint}, Ptr{Cint}, Ptr{CuPtr{T}}, Ptr{Cint}, Ptr{CuPtr{T}}, Ptr{Cint}, Ptr{CuPtr{T}}, Ptr{Cint}, CuPtr{Cint}, CuPtr{UInt8}, Csize_t),
+            h, dtypecode(T), b, m, n, Ap, lda, Qp, ldq, Rp, ldr, CU_NULL, work, lw)
+        chkargsok(rc, "makb200_qr_batched")
+    end
+    return Qs, Rs
+end
+
+end # module

@@ -97,3 +97,32 @@ if "eigh" in sys.argv[1:]:
 if __name__ == "__main__":
     if any(a in ("gemm", "qr") for a in sys.argv[1:]) or len(sys.argv) == 1:
         main()
+
+
+def svd_probe():
+    for dtype in ("f64",):
+        for n in (2048, 4096, 8192):
+            A0 = randdev(n, n, dtype)
+            A = makb200.colmajor_empty(n, n, A0.dtype, A0.device)
+            USV = makb200.svd.initialize_output(A)
+            def run():
+                A.copy_(A0)
+                makb200.svd_compact_(A, USV)
+            ms = timeit(run, reps=2, warm=1)
+            fl = 20.0 * n ** 3 / 3
+            print(f"svd_compact {dtype} n={n}: {ms:.2f} ms  {fl/ms/1e9:.2f} TF/s", flush=True)
+            WP = makb200.polar.initialize_output(A)
+            def runp():
+                A.copy_(A0)
+                makb200.left_polar_(A, WP)
+            ms = timeit(runp, reps=2, warm=1)
+            print(f"left_polar {dtype} n={n}: {ms:.2f} ms", flush=True)
+            if n <= 4096:
+                import time
+                torch.linalg.svd(A0); torch.cuda.synchronize(); t1 = time.time()
+                torch.linalg.svd(A0); torch.cuda.synchronize(); t2 = time.time()
+                print(f"   torch.linalg.svd (cuSOLVER gesvdj/gesvd): {(t2-t1)*1e3:.1f} ms")
+
+
+if "svd" in sys.argv[1:]:
+    svd_probe()
