@@ -137,6 +137,16 @@ int makb200_svd(makb200_handle_t* h, int dtype, int fixgauge, int m, int n, void
                 void* U, int ldu, void* Vh, int ldvh, double l0, void* work, size_t lwork,
                 int* info_dev);
 
+/* -- TSQR building block: local tall-skinny QR of one row shard ------------------------------
+ * New capability: qr_compact! of a row-sharded m x n matrix (m >> n) =
+ * local factorization per rank + binary-tree reduction of the n x n R factors over NCCL (host
+ * layer: matrixalgebrakit.jl_b200/tsqr.py).  The local step is CholeskyQR2 on the DMMA GEMM
+ * (Gram matrix, blocked Cholesky, blocked TRSM, twice); requires kappa(A) <~ 1e7, reports a
+ * Cholesky breakdown in info_dev.  A is overwritten; Q m x n; R n x n upper, diag(R) > 0. */
+size_t makb200_tsqr_local_worksize(makb200_handle_t* h, int dtype, int m, int n);
+int makb200_tsqr_local(makb200_handle_t* h, int dtype, int m, int n, void* A, int lda, void* Q,
+                       int ldq, void* R, int ldr, void* work, size_t lwork, int* info_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,3 +18,4 @@ from .polar import left_polar, left_polar_
 from .svd import (svd_compact, svd_compact_, svd_trunc, svd_trunc_, svd_trunc_no_error, svd_trunc_no_error_,
                   svd_vals, svd_vals_)
 from . import eigh, polar, qr, svd, truncation  # noqa: E402,F401
+from .tsqr import tsqr_

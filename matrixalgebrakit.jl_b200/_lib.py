@@ -45,6 +45,8 @@ SIGNATURES = {
     "makb200_polar_qdwh": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, C.c_double, _i, _vp, _sz, _ip, _vp]),
     "makb200_svd_worksize": (_sz, [_vp, _i, _i, _i]),
     "makb200_svd": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, C.c_double, _vp, _sz, _vp]),
+    "makb200_tsqr_local_worksize": (_sz, [_vp, _i, _i, _i]),
+    "makb200_tsqr_local": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _sz, _vp]),
 }
 
 _lib = None

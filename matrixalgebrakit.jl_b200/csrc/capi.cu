@@ -362,4 +362,28 @@ int makb200_svd(makb200_handle_t* h, int dtype, int fixgauge, int m, int n, void
                             lwork, info_dev);
 }
 
+
+// ---- tall-skinny local QR for TSQR ------------------------------------------------------
+size_t makb200_tsqr_local_worksize(makb200_handle_t* h, int dtype, int m, int n) {
+    if (!h || !dtype_ok(dtype) || m < 0 || n < 0) return 0;
+    return dtype == MAKB200_F64 ? mak::cholqr2_worksize_t<double>(h, m, n) : mak::cholqr2_worksize_t<cplx>(h, m, n);
+}
+
+int makb200_tsqr_local(makb200_handle_t* h, int dtype, int m, int n, void* A, int lda, void* Q, int ldq, void* R,
+                       int ldr, void* work, size_t lwork, int* info_dev) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (m < 0) return -3;
+    if (n < 0 || n > m) return -4;
+    if (lda < maxi(1, m)) return -6;
+    if (ldq < maxi(1, m)) return -8;
+    if (R && ldr > 0 && ldr < maxi(1, n)) return -10;
+    if (m == 0 || n == 0) return 0;
+    if (!A) return -5;
+    if (!Q || Q == A) return -7;
+    if (dtype == MAKB200_F64)
+        return mak::cholqr2_t<double>(h, m, n, (double*)A, lda, (double*)Q, ldq, (double*)R, ldr, work, lwork, info_dev);
+    return mak::cholqr2_t<cplx>(h, m, n, (cplx*)A, lda, (cplx*)Q, ldq, (cplx*)R, ldr, work, lwork, info_dev);
+}
+
 }  // extern "C"

@@ -568,13 +568,130 @@ int svd_t(makb200_handle* h, int m, int n, T* A, int lda, double* S, T* U, int l
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// tall-skinny local QR for TSQR: CholeskyQR2 (Fukaya et al. 2014) on the DMMA GEMM
+//   G = A^H A = L L^H,  Q1 = A L^-H;  G2 = Q1^H Q1 = L2 L2^H,  Q = Q1 L2^-H,  R = L2^H L^H
+// Two passes make ||Q^H Q - I|| = O(eps) provided kappa(A) <~ 1e7 (first Cholesky must succeed;
+// info_dev reports a breakdown).  diag(R) > 0 by construction, i.e. the QR gauge holds.
+// A (m x n) is overwritten (scratch for the second pass); rows are processed in slabs so the
+// scratch stays small for m in the tens of millions.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void rmul_upper_kernel(int n, const T* __restrict__ L2, const T* __restrict__ L1, T* __restrict__ R, int ldr) {
+    // R = L2^H * L1^H  (both upper triangular after the adjoint); one thread per entry
+    int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (r >= n || c >= n) return;
+    T s = zero<T>();
+    if (r <= c)
+        for (int p = r; p <= c; ++p) {
+            // (L2^H)[r,p] = conj(L2[p,r]); (L1^H)[p,c] = conj(L1[c,p])
+            T a = conj_(L2[(size_t)r * n + p]), b = conj_(L1[(size_t)p * n + c]);
+            fma_(s, a, b);
+        }
+    R[(size_t)c * ldr + r] = s;
+}
+
+template <typename T>
+__global__ void lower_clean_kernel(int n, T* __restrict__ L) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (r < n && c < n && r < c) L[(size_t)c * n + r] = zero<T>();
+}
+
+constexpr int CQR_SLAB = 1 << 20;
+
+template <typename T>
+struct CqrWork {
+    T *G, *L1, *L2, *Linv, *Tmp;
+    int* info;
+    void* ws;
+    size_t ws_bytes;
+};
+
+template <typename T, typename AR>
+static void cqr_carve(makb200_handle* h, AR& ar, int m, int n, CqrWork<T>* w) {
+    constexpr int nb = CholNB<T>::value;
+    size_t nn = (size_t)(n > 0 ? n : 1);
+    size_t slab = (size_t)(m < CQR_SLAB ? (m > 0 ? m : 1) : CQR_SLAB);
+    w->G = ar.template get<T>(nn * nn);
+    w->L1 = ar.template get<T>(nn * nn);
+    w->L2 = ar.template get<T>(nn * nn);
+    w->Linv = ar.template get<T>((size_t)nb * nb * ((nn + nb - 1) / nb));
+    w->Tmp = ar.template get<T>(slab * nb);
+    w->info = ar.template get<int>(4);
+    w->ws_bytes = (size_t)h->num_sms * 128 * 128 * sizeof(double);
+    w->ws = ar.template get<char>(w->ws_bytes);
+}
+
+template <typename T>
+size_t cholqr2_worksize_t(makb200_handle* h, int m, int n) {
+    ArenaSize ar;
+    CqrWork<T> w;
+    cqr_carve<T>(h, ar, m, n, &w);
+    return ar.off + 256;
+}
+
+template <typename T>
+static int cholqr_pass(makb200_handle* h, int m, int n, const T* X, int ldx, T* Y, int ldy, T* L, CqrWork<T>& w) {
+    cudaStream_t s = h->stream;
+    // G = X^H X (split-K over the long dimension)
+    MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, n, n, m, one<T>(), X, ldx, X, ldx, zero<T>(), w.G, n, w.ws,
+              w.ws_bytes);
+    int rc = potrf_blocked<T>(h, n, w.G, n, L, n, w.Linv, w.info);
+    if (rc) return rc;
+    for (int r0 = 0; r0 < m; r0 += CQR_SLAB) {
+        int mr = (m - r0 < CQR_SLAB) ? (m - r0) : CQR_SLAB;
+        rc = trsm_right<T>(h, true, mr, n, X + r0, ldx, L, n, w.Linv, Y + r0, ldy, w.Tmp);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+template <typename T>
+int cholqr2_t(makb200_handle* h, int m, int n, T* A, int lda, T* Q, int ldq, T* R, int ldr, void* work, size_t lwork,
+              int* info_dev) {
+    if (m <= 0 || n <= 0) return 0;
+    cudaStream_t s = h->stream;
+    Arena ar(work, lwork);
+    CqrWork<T> w;
+    cqr_carve<T>(h, ar, m, n, &w);
+    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    MAK_CUDA(h, cudaMemsetAsync(w.info, 0, sizeof(int) * 4, s));
+    PhaseTimer pt(s);
+    pt.mark("start");
+    int rc = cholqr_pass<T>(h, m, n, A, lda, Q, ldq, w.L1, w);   // Q1 -> Q
+    if (rc) return rc;
+    pt.mark("pass1");
+    rc = cholqr_pass<T>(h, m, n, Q, ldq, A, lda, w.L2, w);       // Q2 -> A
+    if (rc) return rc;
+    pt.mark("pass2");
+    copy2d_kernel<T><<<grid_for2((size_t)m * n, h->num_sms), 256, 0, s>>>(m, n, A, lda, Q, ldq);
+    count_launch();
+    if (R && ldr > 0) {
+        // the diagonal blocks of L were written with zeros above the diagonal by potf2; blocks
+        // above the block diagonal were never written: clean before the triangular product
+        dim3 g((n + 127) / 128, n);
+        lower_clean_kernel<T><<<g, 128, 0, s>>>(n, w.L1);
+        lower_clean_kernel<T><<<g, 128, 0, s>>>(n, w.L2);
+        rmul_upper_kernel<T><<<g, 128, 0, s>>>(n, w.L2, w.L1, R, ldr);
+        count_launch(3);
+    }
+    MAK_LAUNCH_CHECK(h, "cholqr2 tail");
+    pt.mark("finish");
+    pt.report("cholqr2");
+    if (info_dev) MAK_CUDA(h, cudaMemcpyAsync(info_dev, w.info, sizeof(int), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
 #define INSTP(T)                                                                                             \
     template size_t polar_worksize_t<T>(makb200_handle*, int, int);                                          \
     template int polar_qdwh_t<T>(makb200_handle*, int, int, T*, int, T*, int, T*, int, double, int, void*,   \
                                  size_t, int*, int*);                                                        \
     template size_t svd_worksize_t<T>(makb200_handle*, int, int);                                            \
     template int svd_t<T>(makb200_handle*, int, int, T*, int, double*, T*, int, T*, int, int, double, void*, \
-                          size_t, int*);
+                          size_t, int*);                                                                     \
+    template size_t cholqr2_worksize_t<T>(makb200_handle*, int, int);                                        \
+    template int cholqr2_t<T>(makb200_handle*, int, int, T*, int, T*, int, T*, int, void*, size_t, int*);
 INSTP(double)
 INSTP(cplx)
 

@@ -11,4 +11,9 @@ template <typename T> size_t svd_worksize_t(makb200_handle* h, int m, int n);
 template <typename T>
 int svd_t(makb200_handle* h, int m, int n, T* A, int lda, double* S, T* U, int ldu, T* Vh, int ldvh, int fixgauge,
           double l0, void* work, size_t lwork, int* info_dev);
+// tall-skinny local QR (CholeskyQR2) used by TSQR; A is overwritten, diag(R) > 0
+template <typename T> size_t cholqr2_worksize_t(makb200_handle* h, int m, int n);
+template <typename T>
+int cholqr2_t(makb200_handle* h, int m, int n, T* A, int lda, T* Q, int ldq, T* R, int ldr, void* work, size_t lwork,
+              int* info_dev);
 }  // namespace mak
