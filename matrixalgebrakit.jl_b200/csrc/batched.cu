@@ -101,10 +101,175 @@ batched_qr_kernel(const QrBlockDesc<T>* __restrict__ descs, int* __restrict__ in
     if (tid == 0 && info) info[blockIdx.x] = 0;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// batched svd_compact!: one CTA per block, one-sided (Hestenes) Jacobi with a round-robin
+// parallel ordering; G (= A or A^H, tall orientation) and the accumulated V live in shared
+// memory.  Epilogue: sort descending, normalise, reference SVD gauge (common/gauge.jl:69-77).
+// ---------------------------------------------------------------------------------------
+constexpr int BS_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(BS_THREADS)
+batched_svd_kernel(const SvdBlockDesc<T>* __restrict__ descs, int* __restrict__ info, int max_sweeps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SvdBlockDesc<T> d = descs[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = BS_THREADS / 32;
+    const bool tr = d.m < d.n;                 // work on A^H when wide
+    const int mm = tr ? d.n : d.m, nn = tr ? d.m : d.n;   // G is mm x nn, mm >= nn
+    if (nn <= 0) { if (tid == 0 && info) info[blockIdx.x] = 0; return; }
+    const int ldg = mm | 1, ldv = nn | 1;
+    T* G = reinterpret_cast<T*>(smem_raw);     // ldg x nn
+    T* V = G + (size_t)ldg * nn;               // ldv x nn
+    double* sig = reinterpret_cast<double*>(V + (size_t)ldv * nn);  // nn
+    int* perm = reinterpret_cast<int*>(sig + nn);                   // nn
+    __shared__ int s_rot;
+
+    for (int idx = tid; idx < mm * nn; idx += BS_THREADS) {
+        int c = idx / mm, r = idx - c * mm;
+        G[(size_t)c * ldg + r] = tr ? conj_(d.A[(size_t)r * d.lda + c]) : d.A[(size_t)c * d.lda + r];
+    }
+    for (int idx = tid; idx < nn * nn; idx += BS_THREADS) {
+        int c = idx / nn, r = idx - c * nn;
+        V[(size_t)c * ldv + r] = (r == c) ? one<T>() : zero<T>();
+    }
+    __syncthreads();
+
+    const int ne = (nn + 1) & ~1;  // players (padded to even)
+    const double tol = 4.0 * 2.220446049250313e-16;
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        if (tid == 0) s_rot = 0;
+        __syncthreads();
+        for (int step = 0; step < ne - 1; ++step) {
+            for (int k = warp; k < ne / 2; k += NW) {
+                int p, q;
+                if (k == 0) { p = ne - 1; q = step; }
+                else { p = (step + k) % (ne - 1); q = (step - k + (ne - 1)) % (ne - 1); }
+                if (p > q) { int t = p; p = q; q = t; }
+                if (q >= nn) continue;  // padding player
+                T* x = G + (size_t)p * ldg;
+                T* y = G + (size_t)q * ldg;
+                double al = 0.0, be = 0.0;
+                T ga = zero<T>();
+                for (int r = lane; r < mm; r += 32) {
+                    T xv = x[r], yv = y[r];
+                    al += abs2_(xv); be += abs2_(yv);
+                    fmac_(ga, xv, yv);  // x^H y
+                }
+                al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
+                double ag = sqrt(abs2_(ga));
+                if (ag > tol * sqrt(al * be) && ag > 0.0) {
+                    if (lane == 0) s_rot = 1;
+                    double zeta = (be - al) / (2.0 * ag);
+                    double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                    T ph = scale_(conj_(ga), 1.0 / ag);  // e^{-i phi}
+                    T sph = scale_(ph, s), cph = scale_(ph, c);
+                    for (int r = lane; r < mm; r += 32) {
+                        T xv = x[r], yv = y[r];
+                        x[r] = sub_(scale_(xv, c), mul_(sph, yv));
+                        y[r] = add_(scale_(xv, s), mul_(cph, yv));
+                    }
+                    T* vx = V + (size_t)p * ldv;
+                    T* vy = V + (size_t)q * ldv;
+                    for (int r = lane; r < nn; r += 32) {
+                        T xv = vx[r], yv = vy[r];
+                        vx[r] = sub_(scale_(xv, c), mul_(sph, yv));
+                        vy[r] = add_(scale_(xv, s), mul_(cph, yv));
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (s_rot == 0) break;
+        __syncthreads();
+    }
+    // singular values and descending order (stable rank by counting)
+    for (int j = warp; j < nn; j += NW) {
+        double a = 0.0;
+        for (int r = lane; r < mm; r += 32) a += abs2_(G[(size_t)j * ldg + r]);
+        a = warp_sum(a);
+        if (lane == 0) sig[j] = sqrt(a);
+    }
+    __syncthreads();
+    for (int j = tid; j < nn; j += BS_THREADS) {
+        int rank = 0;
+        double sj = sig[j];
+        for (int i = 0; i < nn; ++i) rank += (sig[i] > sj) || (sig[i] == sj && i < j);
+        perm[rank] = j;
+    }
+    __syncthreads();
+    // outputs: one warp per singular triplet
+    for (int j = warp; j < nn; j += NW) {
+        const int src = perm[j];
+        const double sj = sig[src];
+        const double inv = sj > 0.0 ? 1.0 / sj : 0.0;
+        const T* g = G + (size_t)src * ldg;   // sigma * (left vector of the tall problem)
+        const T* v = V + (size_t)src * ldv;   // right vector of the tall problem
+        // U column of the ORIGINAL problem: tall -> g/sigma (length m); wide -> v (length m)
+        const int ulen = d.m;
+        // gauge: first entry of maximal modulus of the U column
+        double best = -1.0; int bi = 0x7fffffff;
+        for (int r = lane; r < ulen; r += 32) {
+            T uv = tr ? v[r] : scale_(g[r], inv);
+            double a = abs2_(uv);
+            if (a > best) { best = a; bi = r; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        T ph = one<T>();
+        if (d.fixgauge && best > 0.0) {
+            T piv = tr ? v[bi] : scale_(g[bi], inv);
+            ph = scale_(piv, 1.0 / sqrt(abs2_(piv)));  // sign(pivot)
+        }
+        const T cph = conj_(ph);
+        if (lane == 0) d.S[j] = sj;
+        if (d.U) {
+            for (int r = lane; r < d.m; r += 32) {
+                T uv = tr ? v[r] : scale_(g[r], inv);
+                d.U[(size_t)j * d.ldu + r] = mul_(uv, cph);
+            }
+            for (int c = lane; c < d.n; c += 32) {
+                // Vh[j, c] = conj(right vector of the original problem)[c] * sign
+                T rv = tr ? scale_(g[c], inv) : v[c];
+                d.Vh[(size_t)c * d.ldvh + j] = mul_(conj_(rv), ph);
+            }
+        }
+    }
+    if (tid == 0 && info) info[blockIdx.x] = (sweep >= max_sweeps) ? 1 : 0;
+}
+
+size_t batched_svd_smem_bytes(int m, int n, size_t elem) {
+    int mm = m < n ? n : m, nn = m < n ? m : n;
+    return ((size_t)(mm | 1) * nn + (size_t)(nn | 1) * nn) * elem + (size_t)nn * 12 + 64;
+}
+size_t batched_svd_max_smem_bytes() { return BQ_SMEM_BYTES; }
+
+template <typename T>
+int batched_svd_smem(makb200_handle* h, int batch, size_t max_smem_bytes, const SvdBlockDesc<T>* descs, int* info) {
+    if (batch <= 0) return 0;
+    if (max_smem_bytes > BQ_SMEM_BYTES) return MAKB200_ERR_WORKSPACE;
+    batched_svd_kernel<T><<<batch, BS_THREADS, max_smem_bytes, h->stream>>>(descs, info, 40);
+    count_launch();
+    MAK_LAUNCH_CHECK(h, "batched_svd_kernel");
+    return 0;
+}
+template int batched_svd_smem<double>(makb200_handle*, int, size_t, const SvdBlockDesc<double>*, int*);
+template int batched_svd_smem<cplx>(makb200_handle*, int, size_t, const SvdBlockDesc<cplx>*, int*);
+
 int batched_init(makb200_handle* h) {
     MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)BQ_SMEM_BYTES));
     MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_kernel<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)BQ_SMEM_BYTES));
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_svd_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)BQ_SMEM_BYTES));
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_svd_kernel<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)BQ_SMEM_BYTES));
     return 0;
 }

@@ -15,4 +15,16 @@ int batched_init(makb200_handle* h);
 // descs: DEVICE array; max_smem_elems: max of batched_qr_smem_elems over the batch
 template <typename T>
 int batched_qr_smem(makb200_handle* h, int batch, size_t max_smem_elems, const QrBlockDesc<T>* descs, int* info);
+template <typename T>
+struct SvdBlockDesc {
+    int m, n, fixgauge;
+    const T* A; int lda;
+    double* S;
+    T* U; int ldu;     // U == nullptr -> values only
+    T* Vh; int ldvh;
+};
+size_t batched_svd_smem_bytes(int m, int n, size_t elem);
+size_t batched_svd_max_smem_bytes();
+template <typename T>
+int batched_svd_smem(makb200_handle* h, int batch, size_t max_smem_bytes, const SvdBlockDesc<T>* descs, int* info);
 }  // namespace mak

@@ -387,3 +387,84 @@ int makb200_tsqr_local(makb200_handle_t* h, int dtype, int m, int n, void* A, in
 }
 
 }  // extern "C"
+
+// ---- batched svd --------------------------------------------------------------------------
+template <typename T>
+static int svd_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int* m, const int* n, void* const* A,
+                         const int* lda, void* const* S, void* const* U, const int* ldu, void* const* Vh,
+                         const int* ldvh, int* info, void* work, size_t lwork) {
+    std::vector<mak::SvdBlockDesc<T>> small;
+    std::vector<int> big;
+    size_t max_b = 0;
+    for (int i = 0; i < batch; ++i) {
+        if (m[i] < 0 || n[i] < 0) return -5;
+        if (m[i] == 0 || n[i] == 0) continue;
+        size_t sb = mak::batched_svd_smem_bytes(m[i], n[i], sizeof(T));
+        if (sb > mak::batched_svd_max_smem_bytes()) { big.push_back(i); continue; }
+        mak::SvdBlockDesc<T> d;
+        d.m = m[i]; d.n = n[i]; d.fixgauge = fixgauge;
+        d.A = (const T*)A[i]; d.lda = lda[i];
+        d.S = (double*)S[i];
+        d.U = U ? (T*)U[i] : nullptr; d.ldu = ldu ? ldu[i] : 0;
+        d.Vh = Vh ? (T*)Vh[i] : nullptr; d.ldvh = ldvh ? ldvh[i] : 0;
+        if (!d.U || !d.Vh) { d.U = nullptr; d.Vh = nullptr; }
+        small.push_back(d);
+        if (sb > max_b) max_b = sb;
+    }
+    mak::Arena ar(work, lwork);
+    mak::SvdBlockDesc<T>* ddev = ar.get<mak::SvdBlockDesc<T>>(batch > 0 ? batch : 1);
+    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    if (info) MAK_CUDA(h, cudaMemsetAsync(info, 0, sizeof(int) * batch, h->stream));
+    if (!small.empty()) {
+        MAK_CUDA(h, cudaMemcpyAsync(ddev, small.data(), sizeof(mak::SvdBlockDesc<T>) * small.size(),
+                                    cudaMemcpyHostToDevice, h->stream));
+        int rc = mak::batched_svd_smem<T>(h, (int)small.size(), max_b, ddev, nullptr);
+        if (rc) return rc;
+    }
+    // blocks too large for one CTA's shared memory: QDWH + D&C path, one block at a time
+    char* wbig = (char*)work + ar.off;
+    size_t lbig = lwork > ar.off ? lwork - ar.off : 0;
+    for (int i : big) {
+        int rc = mak::svd_t<T>(h, m[i], n[i], (T*)A[i], lda[i], (double*)S[i], U ? (T*)U[i] : nullptr, ldu ? ldu[i] : 0,
+                               Vh ? (T*)Vh[i] : nullptr, ldvh ? ldvh[i] : 0, fixgauge, 2.2e-16, wbig, lbig, nullptr);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" {
+
+size_t makb200_svd_batched_worksize(makb200_handle_t* h, int dtype, int batch, const int* m, const int* n) {
+    if (!h || !dtype_ok(dtype) || batch < 0 || (batch > 0 && (!m || !n))) return 0;
+    size_t esz = dtype == MAKB200_F64 ? sizeof(double) : sizeof(cplx);
+    size_t bytes = mak::align_up(sizeof(mak::SvdBlockDesc<cplx>) * (size_t)(batch > 0 ? batch : 1), 256), big = 0;
+    for (int i = 0; i < batch; ++i) {
+        if (m[i] <= 0 || n[i] <= 0) continue;
+        if (mak::batched_svd_smem_bytes(m[i], n[i], esz) > mak::batched_svd_max_smem_bytes()) {
+            size_t w = dtype == MAKB200_F64 ? mak::svd_worksize_t<double>(h, m[i], n[i])
+                                            : mak::svd_worksize_t<cplx>(h, m[i], n[i]);
+            if (w > big) big = w;
+        }
+    }
+    return bytes + big + 256;
+}
+
+int makb200_svd_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch, const int* m, const int* n,
+                        void* const* A, const int* lda, void* const* S, void* const* U, const int* ldu,
+                        void* const* Vh, const int* ldvh, int* info, void* work, size_t lwork) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (batch < 0) return -4;
+    if (batch == 0) return 0;
+    if (!m) return -5;
+    if (!n) return -6;
+    if (!A) return -7;
+    if (!lda) return -8;
+    if (!S) return -9;
+    if ((U == nullptr) != (Vh == nullptr)) return -10;
+    if (dtype == MAKB200_F64)
+        return svd_batched_t<double>(h, fixgauge, batch, m, n, A, lda, S, U, ldu, Vh, ldvh, info, work, lwork);
+    return svd_batched_t<cplx>(h, fixgauge, batch, m, n, A, lda, S, U, ldu, Vh, ldvh, info, work, lwork);
+}
+
+}  // extern "C"
