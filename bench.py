@@ -48,6 +48,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def fp64_peak():
+    """FP64 tensor (DMMA) denominator: MEASURED_PEAKS.json carries no FP64 figure, so the measured
+    cuBLAS DGEMM 8192^3 rate on this pool's B200 (profiles/fp64_peak.json, tools/peak_fp64.py) is
+    used; fallback = the 36.2 TF/s measured in round 1."""
+    p = os.path.join(ROOT, "profiles", "fp64_peak.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["dgemm_tflops"]), "measured cuBLAS DGEMM 8192^3 (profiles/fp64_peak.json)"
+    return 36.2, "round-1 measurement of cuBLAS DGEMM 8192^3 (no FP64 entry in MEASURED_PEAKS.json)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
 
@@ -252,7 +263,8 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    for _ in range(max(args.warmup, 3)):
+    nwarm = max(args.warmup, 3) if not os.environ.get("MAKB200_BENCH_UNDER_NCU") else args.warmup
+    for _ in range(nwarm):
         step_dev()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -277,24 +289,43 @@ def run_ours(args):
 
     # roofline of the dominant kernel (tridiagonalisation column-dot kernel, HBM-bound): one extra
     # step with CUDA events around every launch of that kernel (not part of `value`)
-    roofline = None
-    if "eigh" in ops:
-        lib.makb200_kernel_timing(1)
-        A.copy_(dev_in["eigh"])
-        makb200.eigh_full_(A, outs["eigh"])
-        torch.cuda.synchronize()
-        kms, kl = ctypes.c_double(), ctypes.c_int()
-        lib.makb200_kernel_time(0, ctypes.byref(kms), ctypes.byref(kl))
-        lib.makb200_kernel_timing(0)
-        # algorithmic bytes: every stored element of the trailing matrix is read once per column step
-        alg_bytes = 8.0 * sum(float(n - c - 1) ** 2 for c in range(n - 1))
-        peak, how = peaks()
-        ach = alg_bytes / (kms.value * 1e-3) / 1e9 if kms.value > 0 else None
-        roofline = {"kernel": "trd_dots_kernel<double>", "bound": "hbm", "achieved": ach, "peak": peak,
-                    "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": None,
-                    "launches_per_step": kl.value, "avg_launch_ms": kms.value / max(kl.value, 1),
-                    "bytes_per_launch_avg": alg_bytes / max(kl.value, 1), "kernel_share_of_step": kms.value / (ms / args.steps),
-                    "peak_source": how}
+    # roofline of the dominant kernel: one extra step with CUDA events around every launch of the two
+    # candidate kernels (not part of `value`): the tridiagonalisation column-dot kernel (HBM-bound)
+    # and the DMMA GEMM (FP64 tensor-bound)
+    lib.makb200_kernel_timing(1)
+    step_dev()
+    torch.cuda.synchronize()
+    kms, kl = ctypes.c_double(), ctypes.c_int()
+    lib.makb200_kernel_time(0, ctypes.byref(kms), ctypes.byref(kl))
+    gms, gl = ctypes.c_double(), ctypes.c_int()
+    lib.makb200_kernel_time(1, ctypes.byref(gms), ctypes.byref(gl))
+    gflops = float(lib.makb200_gemm_flops())
+    lib.makb200_kernel_timing(0)
+    step_ms = ms / args.steps
+    hbm_peak, how = peaks()
+    cands = []
+    if kl.value > 0:
+        # algorithmic bytes: every stored element of the trailing matrix is read once per column step,
+        # for each tridiagonalisation in the step (eigh itself, and the eigh inside svd)
+        ntrd = sum(1 for o in ops if o in ("eigh", "svd"))
+        alg_bytes = ntrd * 8.0 * sum(float(n - c - 1) ** 2 for c in range(n - 1))
+        ach = alg_bytes / (kms.value * 1e-3) / 1e9
+        cands.append({"kernel": "trd_dots_kernel<double>", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+                      "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "launches_per_step": kl.value,
+                      "avg_launch_ms": kms.value / kl.value, "alg_bytes_per_launch": alg_bytes / kl.value,
+                      "kernel_share_of_step": kms.value / step_ms, "peak_source": how})
+    if gl.value > 0:
+        pk = fp64_peak()
+        ach = gflops / (gms.value * 1e-3) / 1e12
+        cands.append({"kernel": "gemm_kernel<double> (DMMA m8n8k4)", "bound": "tensor", "achieved": ach,
+                      "peak": pk[0], "unit": "TFLOP/s", "frac": ach / pk[0], "traffic": None,
+                      "launches_per_step": gl.value, "avg_launch_ms": gms.value / gl.value,
+                      "alg_flops_per_launch": gflops / gl.value, "kernel_share_of_step": gms.value / step_ms,
+                      "peak_source": pk[1]})
+    cands.sort(key=lambda c: -c["kernel_share_of_step"])
+    roofline = cands[0] if cands else None
+    if roofline and len(cands) > 1:
+        roofline["second_kernel"] = cands[1]
 
     if rank != 0:
         if world > 1:
@@ -307,7 +338,7 @@ def run_ours(args):
         cpu = {"value": g, "unit": "GFLOP/s", "cores": threads_info(), "kind": "port", "sample": desc, "seconds": s}
     line = {
         "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": nwarm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{'+'.join(o + ('_full!' if o == 'eigh' else '_compact!') for o in ops)} {n}x{n} Float64 "
                                "(BASELINE configs[1]); per-rank replica when n_gpus>1",
@@ -329,7 +360,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--n", type=int, default=8192)
-    ap.add_argument("--ops", default="eigh")
+    ap.add_argument("--ops", default="eigh,svd")
     ap.add_argument("--cpu-n", type=int, default=4096, help="size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -50,6 +50,8 @@ const char* makb200_last_error(makb200_handle_t* h);
 unsigned long long makb200_launch_count(void);
 int makb200_kernel_timing(int enable);
 int makb200_kernel_time(int which, double* ms, int* launches);
+/* real flops (2mnk, x4 for complex) issued through the DMMA GEMM since makb200_kernel_timing() */
+double makb200_gemm_flops(void);
 
 /* -- GEMM building block: C = alpha*op(A)*op(B) + beta*C  (FP64 DMMA tiles) ----------
  * replaces `mul!` on CuArray -> cuBLAS gemm (implementations/polar.jl:63,88).
@@ -146,6 +148,19 @@ int makb200_svd(makb200_handle_t* h, int dtype, int fixgauge, int m, int n, void
 size_t makb200_tsqr_local_worksize(makb200_handle_t* h, int dtype, int m, int n);
 int makb200_tsqr_local(makb200_handle_t* h, int dtype, int m, int n, void* A, int lda, void* Q,
                        int ldq, void* R, int ldr, void* work, size_t lwork, int* info_dev);
+
+/* -- batched svd_compact! of many small blocks -------------------------------------------------
+ * New capability (reference: commented-out gesvdjBatched stubs yacusolver.jl:506-569).
+ * Semantics = svd_compact!(A_i,(U_i,S_i,Vh_i)) per block incl. the SVD gauge.  One CTA per block,
+ * one-sided Jacobi in shared memory; blocks that do not fit are routed through makb200_svd.
+ * m,n,lda,ldu,ldvh: HOST int arrays; A,S,U,Vh: HOST arrays of DEVICE pointers (U == Vh == NULL:
+ * values only).  Small blocks are NOT destroyed; routed large blocks are.  info: DEVICE int[batch]. */
+size_t makb200_svd_batched_worksize(makb200_handle_t* h, int dtype, int batch, const int* m,
+                                    const int* n);
+int makb200_svd_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch, const int* m,
+                        const int* n, void* const* A, const int* lda, void* const* S, void* const* U,
+                        const int* ldu, void* const* Vh, const int* ldvh, int* info, void* work,
+                        size_t lwork);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,7 @@ SIGNATURES = {
     "makb200_launch_count": (C.c_ulonglong, []),
     "makb200_kernel_timing": (_i, [_i]),
     "makb200_kernel_time": (_i, [_i, C.POINTER(C.c_double), _ip]),
+    "makb200_gemm_flops": (C.c_double, []),
     "makb200_gemm": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i]),
     "makb200_geqrf_worksize": (_sz, [_vp, _i, _i, _i]),
     "makb200_geqrf": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _sz]),
@@ -47,6 +48,8 @@ SIGNATURES = {
     "makb200_svd": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, C.c_double, _vp, _sz, _vp]),
     "makb200_tsqr_local_worksize": (_sz, [_vp, _i, _i, _i]),
     "makb200_tsqr_local": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _sz, _vp]),
+    "makb200_svd_batched_worksize": (_sz, [_vp, _i, _i, _ip, _ip]),
+    "makb200_svd_batched": (_i, [_vp, _i, _i, _i, _ip, _ip, _vpp, _ip, _vpp, _vpp, _ip, _vpp, _ip, _vp, _vp, _sz]),
 }
 
 _lib = None

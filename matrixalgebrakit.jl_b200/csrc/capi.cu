@@ -59,8 +59,11 @@ int makb200_kernel_timing(int enable) {
     mak::g_clock_gemm.on = enable != 0;
     mak::g_clock_dots.n = 0;
     mak::g_clock_gemm.n = 0;
+    mak::g_gemm_flops = 0.0;
     return 0;
 }
+
+double makb200_gemm_flops(void) { return mak::g_gemm_flops; }
 
 int makb200_kernel_time(int which, double* ms, int* launches) {
     if (!ms || !launches) return -2;

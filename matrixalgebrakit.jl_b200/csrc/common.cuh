@@ -170,6 +170,7 @@ inline int cuda_fail(makb200_handle* h, cudaError_t e, const char* where) {
 
 // process-wide count of kernels launched by this library (bench.py reports it as gpu_launches)
 extern unsigned long long g_launches;
+extern double g_gemm_flops;
 inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }
 
 // per-kernel-class device-time accumulation for the roofline line of bench.py

@@ -4,6 +4,7 @@
 namespace mak {
 
 unsigned long long g_launches = 0;
+double g_gemm_flops = 0.0;  // real flops issued through gemm() since the last makb200_kernel_timing()
 KernelClock g_clock_dots;
 KernelClock g_clock_gemm;
 
@@ -333,6 +334,7 @@ cudaError_t gemm(cudaStream_t stream, int num_sms, int opa, int opb, int m, int 
         if (splitk < 2) splitk = 1;
     }
     grid.z = splitk;
+    g_gemm_flops += 2.0 * (double)m * (double)n * (double)k * (is_cplx<T>::value ? 4.0 : 1.0);
     cudaError_t e = dispatch<T>(stream, opa != MAKB200_OP_N, opb != MAKB200_OP_N, grid, p, nullptr, splitk, (T*)ws);
     if (e != cudaSuccess) return e;
     if (splitk > 1) {

@@ -141,3 +141,43 @@ def svd_trunc(A, alg=None, trunc=None, **kw):
 
 def svd_trunc_no_error(A, alg=None, trunc=None, **kw):
     return svd_trunc_no_error_(_copy_input(A), None, alg, trunc, **kw)
+
+
+def svd_compact_batched_(As, USVhs=None, fixgauge=True):
+    """Batched ``svd_compact!`` over a list of blocks (new capability; per-block semantics)."""
+    if len(As) == 0:
+        return []
+    h = _core.Handle.get(As[0].device)
+    dt = _core.dtype_code(As[0])
+    if USVhs is None:
+        USVhs = [initialize_output(A) for A in As]
+    for A, o in zip(As, USVhs):
+        check_input(A, o)
+    b = len(As)
+    IA, VP = C.c_int * b, C.c_void_p * b
+    m = IA(*[A.shape[0] for A in As])
+    n = IA(*[A.shape[1] for A in As])
+    lda = IA(*[_core.ld(A) for A in As])
+    ldu = IA(*[_core.ld(o[0]) for o in USVhs])
+    ldv = IA(*[_core.ld(o[2]) for o in USVhs])
+    Ap = VP(*[A.data_ptr() for A in As])
+    Sp = VP(*[o[1].data_ptr() for o in USVhs])
+    Up = VP(*[o[0].data_ptr() for o in USVhs])
+    Vp = VP(*[o[2].data_ptr() for o in USVhs])
+    lw = h.lib.makb200_svd_batched_worksize(h.h, dt, b, m, n)
+    work = h.workspace(lw)
+    rc = h.lib.makb200_svd_batched(h.h, dt, int(bool(fixgauge)), b, m, n, Ap, lda, Sp, Up, ldu, Vp, ldv,
+                                   C.c_void_p(0), _core.ptr(work), work.numel())
+    h.check(rc, "makb200_svd_batched")
+    return USVhs
+
+
+def svd_trunc_batched_(As, trunc, USVhs=None):
+    """Batched ``svd_trunc!``: batched compact SVD, then the reference's per-block slice and error."""
+    strategy = select_truncation(trunc)
+    outs = svd_compact_batched_(As, USVhs)
+    res = []
+    for U, S, Vh in outs:
+        (Ut, St, Vt), ind = _truncate(U, S, Vh, strategy)
+        res.append((Ut, St, Vt, ind))
+    return res

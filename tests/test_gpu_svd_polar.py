@@ -158,3 +158,21 @@ def test_left_polar_skip_p_identity_and_errors():
     W5, P5 = makb200.left_polar(makb200.to_device(A1))
     W5, P5 = makb200.to_numpy(W5), makb200.to_numpy(P5)
     assert O.orth_err(W5) <= O.tol_for(n) and O.rel_resid(A1, W5, P5) <= O.tol_for(n)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_svd_batched_vs_oracle(dtype):
+    import makb200
+    rng = np.random.default_rng(7)
+    sizes = [(16, 16), (17, 9), (9, 17), (32, 32), (54, 37), (37, 54), (64, 64), (1, 1), (70, 70), (150, 120)]
+    sizes += [(int(s), int(s)) for s in rng.integers(16, 72, size=24)]
+    As0 = [O.randn_matrix(m, n, dtype, seed=300 + i) for i, (m, n) in enumerate(sizes)]
+    outs = makb200.svd_compact_batched_([makb200.to_device(a) for a in As0])
+    torch.cuda.synchronize()
+    for a, (U, S, Vh) in zip(As0, outs):
+        _check_svd(a, makb200.to_numpy(U), S.cpu().numpy(), makb200.to_numpy(Vh))
+    tr = makb200.svd_trunc_batched_([makb200.to_device(a) for a in As0[:6]], makb200.truncrank(5))
+    for a, (U, S, Vh, ind) in zip(As0[:6], tr):
+        So = O.svd_vals(a)
+        k = min(5, len(So))
+        np.testing.assert_allclose(S.cpu().numpy(), So[:k], rtol=1e-11)

@@ -1,0 +1,95 @@
+"""BASELINE configs[2]: batched block-sparse qr_compact! / svd_trunc! of ComplexF64 blocks, sizes 16-512
+(log-uniform), distributed over ranks by LPT (longest processing time first).
+  python tools/batched_bench.py [nblocks] [maxdim]           (1 GPU)
+  torchrun ... tools/batched_bench.py [nblocks] [maxdim]     (N GPUs, no data-path collective)
+Reports per size bucket: blocks/s, algorithmic GB/s (HBM fraction) and GFLOP/s."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import makb200
+
+rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+nblocks = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+maxdim = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+ops = (sys.argv[3] if len(sys.argv) > 3 else "qr,svd").split(",")
+
+rng = np.random.Generator(np.random.PCG64(4))
+dims = np.rint(16 * 32 ** rng.random(nblocks)).astype(int)
+dims = dims[dims <= maxdim]
+# LPT partition on cost ~ n^3
+order = np.argsort(-dims.astype(np.float64) ** 3, kind="stable")
+loads = np.zeros(world); owner = np.zeros(len(dims), dtype=int)
+for i in order:
+    r = int(np.argmin(loads)); owner[i] = r; loads[r] += float(dims[i]) ** 3
+mine = dims[owner == rank]
+imbalance = float(loads.max() / loads.mean())
+g = torch.Generator(device=dev); g.manual_seed(4 + rank)
+As0 = [torch.randn((n, n), dtype=torch.complex128, device=dev, generator=g).t() for n in mine]
+buckets = [(16, 32), (33, 64), (65, 128), (129, 256), (257, 512)]
+
+
+def run(op, idx):
+    blocks = [As0[i] for i in idx]
+    As = [makb200.colmajor_empty(a.shape[0], a.shape[1], a.dtype, dev) for a in blocks]
+    if op == "qr":
+        outs = [makb200.qr.initialize_output("qr_compact", a) for a in As]
+        fn = lambda: makb200.qr_compact_batched_(As, outs)
+    else:
+        outs = [makb200.svd.initialize_output(a) for a in As]
+        fn = lambda: makb200.svd_compact_batched_(As, outs)
+    ts = []
+    for it in range(3):
+        for a, b in zip(As, blocks):
+            a.copy_(b)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts[1:]))
+
+
+res = {}
+for op in ops:
+    for lo, hi in buckets:
+        idx = [i for i, n in enumerate(mine) if lo <= n <= hi]
+        if not idx:
+            continue
+        if op == "svd" and lo > 128 and len(idx) > 64:
+            idx = idx[:64]          # large-block SVD goes through the single-matrix path: bounded sample
+        if op == "qr" and lo > 128 and len(idx) > 512:
+            idx = idx[:512]
+        ms = run(op, idx)
+        ns = np.array([mine[i] for i in idx], dtype=np.float64)
+        byt = 16 * 3 * (ns ** 2).sum() + (8 * ns.sum() if op == "svd" else 0)
+        fl = 4 * ((8.0 / 3) if op == "qr" else (20.0 / 3)) * (ns ** 3).sum()
+        res[f"{op}_{lo}-{hi}"] = {"blocks": len(idx), "ms": ms, "blocks_per_s": len(idx) / ms * 1e3,
+                                  "alg_GBs": byt / ms / 1e6, "hbm_frac": byt / ms / 1e6 / 6555.8,
+                                  "alg_GFLOPs": fl / ms / 1e6}
+if world > 1:
+    gathered = [None] * world
+    dist.all_gather_object(gathered, res)
+else:
+    gathered = [res]
+if rank == 0:
+    agg = {}
+    for k in gathered[0]:
+        ms = max(g[k]["ms"] for g in gathered if k in g)
+        nb = sum(g[k]["blocks"] for g in gathered if k in g)
+        agg[k] = {"blocks": nb, "ms_max_over_ranks": ms, "blocks_per_s": nb / ms * 1e3,
+                  "alg_GBs": sum(g[k]["alg_GBs"] * g[k]["ms"] for g in gathered if k in g) / ms,
+                  "alg_GFLOPs": sum(g[k]["alg_GFLOPs"] * g[k]["ms"] for g in gathered if k in g) / ms}
+        agg[k]["hbm_frac_per_gpu"] = agg[k]["alg_GBs"] / world / 6555.8
+    print(json.dumps({"workload": f"batched c128 blocks n={len(dims)} dims 16-{maxdim}", "n_gpus": world,
+                      "lpt_imbalance": imbalance, "buckets": agg}, indent=1))
+if world > 1:
+    dist.destroy_process_group()
