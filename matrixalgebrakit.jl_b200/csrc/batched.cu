@@ -103,6 +103,125 @@ batched_qr_kernel(const QrBlockDesc<T>* __restrict__ descs, int* __restrict__ in
 
 
 // ---------------------------------------------------------------------------------------
+// warp-per-block QR for tiny blocks (m, n <= 32): lane = column, the column lives in registers
+// (RMAX rows, compile-time indexed), reflector vectors are broadcast with warp shuffles.
+// No shared memory, no block barrier: this is the HBM-bound end of the batched config.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double shfl_(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ cplx shfl_(cplx v, int src) {
+    return cplx{__shfl_sync(0xffffffffu, v.re, src), __shfl_sync(0xffffffffu, v.im, src)};
+}
+
+template <typename T, int RMAX>
+__global__ void __launch_bounds__(128)
+batched_qr_warp_kernel(const QrBlockDesc<T>* __restrict__ descs, int batch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int blk = blockIdx.x * 4 + warp;
+    if (blk >= batch) return;
+    const QrBlockDesc<T> d = descs[blk];
+    const int m = d.m, n = d.n, k = m < n ? m : n;
+    T a[RMAX];
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) a[r] = (r < m && lane < n) ? d.A[(size_t)lane * d.lda + r] : zero<T>();
+    T mytau = zero<T>();
+    // ---- factorization ----
+    for (int j = 0; j < k; ++j) {
+        // every lane forms the scalars of ITS column; lane j's are the ones used
+        double sig = 0.0;
+        T ajj = zero<T>();
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            if (r > j) sig += abs2_(a[r]);
+            if (r == j) ajj = a[r];
+        }
+        double beta; T tau, scale;
+        larfgp_scalars<T>(ajj, sig, beta, tau, scale);
+        tau = shfl_(tau, j);
+        scale = shfl_(scale, j);
+        beta = __shfl_sync(0xffffffffu, beta, j);
+        // dot = w^H a_l,  w = [1; v],  v_r = a_j[r] * scale
+        T dot = ajj;
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            T vr = mul_(shfl_(a[r], j), scale);
+            if (r > j) fmac_(dot, vr, a[r]);
+        }
+        const T f = mul_(conj_(tau), dot);
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            T vr = mul_(shfl_(a[r], j), scale);   // lane j still holds the unscaled column
+            if (lane > j) {
+                if (r > j) a[r] = sub_(a[r], mul_(f, vr));
+                else if (r == j) a[r] = sub_(a[r], f);
+            }
+        }
+        if (lane == j) {
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                if (r > j) a[r] = mul_(a[r], scale);
+                else if (r == j) a[r] = mk<T>(beta);
+            }
+            mytau = tau;
+        }
+    }
+    // ---- R out ----
+    if (d.R && lane < n) {
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r)
+            if (r < k) d.R[(size_t)lane * d.ldr + r] = (r <= lane) ? a[r] : zero<T>();
+    }
+    // ---- Q in place (columns 0..k-1), backward accumulation ----
+    for (int j = k - 1; j >= 0; --j) {
+        const T tau = shfl_(mytau, j);
+        T dot = zero<T>();
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            T vr = shfl_(a[r], j);
+            if (r > j) fmac_(dot, vr, a[r]);
+            else if (r == j) dot = add_(dot, a[r]);   // rows <= j of later columns were zeroed below
+        }
+        const T f = mul_(tau, dot);
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            T vr = shfl_(a[r], j);
+            if (lane > j && lane < k) {
+                if (r > j) a[r] = sub_(a[r], mul_(f, vr));
+                else if (r == j) a[r] = sub_(a[r], f);
+            }
+        }
+        if (lane == j) {
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                if (r > j) a[r] = neg_(mul_(tau, a[r]));
+                else if (r == j) a[r] = sub_(one<T>(), tau);
+                else a[r] = zero<T>();
+            }
+        }
+        // columns l > j still hold R entries in rows <= j until their own turn has passed: they
+        // were processed earlier in this backward loop and zeroed above, so nothing to do here
+    }
+    if (lane < k) {
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r)
+            if (r < m) d.Q[(size_t)lane * d.ldq + r] = a[r];
+    }
+}
+
+template <typename T>
+int batched_qr_warp(makb200_handle* h, int batch, int rmax, const QrBlockDesc<T>* descs) {
+    if (batch <= 0) return 0;
+    const int grid = (batch + 3) / 4;
+    if (rmax <= 16) batched_qr_warp_kernel<T, 16><<<grid, 128, 0, h->stream>>>(descs, batch);
+    else if (rmax <= 24) batched_qr_warp_kernel<T, 24><<<grid, 128, 0, h->stream>>>(descs, batch);
+    else batched_qr_warp_kernel<T, 32><<<grid, 128, 0, h->stream>>>(descs, batch);
+    count_launch();
+    MAK_LAUNCH_CHECK(h, "batched_qr_warp_kernel");
+    return 0;
+}
+template int batched_qr_warp<double>(makb200_handle*, int, int, const QrBlockDesc<double>*);
+template int batched_qr_warp<cplx>(makb200_handle*, int, int, const QrBlockDesc<cplx>*);
+
+// ---------------------------------------------------------------------------------------
 // batched svd_compact!: one CTA per block, one-sided (Hestenes) Jacobi with a round-robin
 // parallel ordering; G (= A or A^H, tall orientation) and the accumulated V live in shared
 // memory.  Epilogue: sort descending, normalise, reference SVD gauge (common/gauge.jl:69-77).

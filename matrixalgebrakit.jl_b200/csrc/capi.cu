@@ -30,6 +30,18 @@ int makb200_create(makb200_handle_t** out, int device) {
     h->num_sms = prop.multiProcessorCount;
     h->max_cluster = 8;
     h->err[0] = 0;
+    {
+        // high-priority auxiliary stream: latency-bound panel kernels must be able to claim SMs while
+        // bulk GEMMs of the caller's (default-priority) stream are still draining
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        if (cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, greatest) != cudaSuccess) {
+            delete h;
+            return MAKB200_ERR_CUDA;
+        }
+    }
+    for (int i = 0; i < 8; ++i)
+        if (cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return MAKB200_ERR_CUDA; }
     int rc = mak::qr_init(h);
     if (rc == 0) rc = mak::batched_init(h);
     if (rc == 0) rc = mak::polar_init(h);
@@ -40,6 +52,8 @@ int makb200_create(makb200_handle_t** out, int device) {
 
 int makb200_destroy(makb200_handle_t* h) {
     if (!h) return -1;
+    cudaStreamDestroy(h->aux_stream);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
     delete h;
     return 0;
 }
@@ -195,31 +209,41 @@ template <typename T>
 static int qr_batched_t(makb200_handle_t* h, int batch, const int* m, const int* n, void* const* A, const int* lda,
                         void* const* Q, const int* ldq, void* const* R, const int* ldr, int* info, void* work,
                         size_t lwork) {
-    std::vector<mak::QrBlockDesc<T>> small;
+    // size classes: warp kernel (m,n <= 32; three row capacities), CTA kernel (fits shared memory), big
+    std::vector<mak::QrBlockDesc<T>> cls[4];
     std::vector<int> big;
-    small.reserve(batch);
     size_t max_se = 0;
     for (int i = 0; i < batch; ++i) {
         if (m[i] < 0 || n[i] < 0) return -4;
+        if (m[i] == 0) continue;
         size_t se = mak::batched_qr_smem_elems(m[i], n[i]);
-        if (se > mak::batched_qr_max_smem_elems<T>()) { big.push_back(i); continue; }
         mak::QrBlockDesc<T> d;
         d.m = m[i]; d.n = n[i];
         d.A = (T*)A[i]; d.lda = lda[i];
         d.Q = (T*)Q[i]; d.ldq = ldq[i];
         d.R = (R && R[i]) ? (T*)R[i] : nullptr; d.ldr = ldr ? ldr[i] : 0;
-        small.push_back(d);
-        if (se > max_se) max_se = se;
+        if (m[i] <= 32 && n[i] <= 32 && n[i] > 0) {
+            cls[m[i] <= 16 ? 0 : (m[i] <= 24 ? 1 : 2)].push_back(d);
+        } else if (se <= mak::batched_qr_max_smem_elems<T>()) {
+            cls[3].push_back(d);
+            if (se > max_se) max_se = se;
+        } else {
+            big.push_back(i);
+        }
     }
     mak::Arena ar(work, lwork);
     mak::QrBlockDesc<T>* ddev = ar.get<mak::QrBlockDesc<T>>(batch > 0 ? batch : 1);
     if (!ar.ok) return MAKB200_ERR_WORKSPACE;
     if (info) MAK_CUDA(h, cudaMemsetAsync(info, 0, sizeof(int) * batch, h->stream));
-    if (!small.empty()) {
-        MAK_CUDA(h, cudaMemcpyAsync(ddev, small.data(), sizeof(mak::QrBlockDesc<T>) * small.size(),
+    size_t off = 0;
+    for (int cidx = 0; cidx < 4; ++cidx) {
+        if (cls[cidx].empty()) continue;
+        MAK_CUDA(h, cudaMemcpyAsync(ddev + off, cls[cidx].data(), sizeof(mak::QrBlockDesc<T>) * cls[cidx].size(),
                                     cudaMemcpyHostToDevice, h->stream));
-        int rc = mak::batched_qr_smem<T>(h, (int)small.size(), max_se, ddev, nullptr);
+        int rc = cidx < 3 ? mak::batched_qr_warp<T>(h, (int)cls[cidx].size(), cidx == 0 ? 16 : (cidx == 1 ? 24 : 32), ddev + off)
+                          : mak::batched_qr_smem<T>(h, (int)cls[cidx].size(), max_se, ddev + off, nullptr);
         if (rc) return rc;
+        off += cls[cidx].size();
     }
     // blocks too large for one CTA's shared memory take the blocked DMMA path
     char* wbig = (char*)work + ar.off;

@@ -148,6 +148,8 @@ struct makb200_handle {
     cudaStream_t stream;
     int num_sms;
     int max_cluster;  // largest usable cluster size for the panel kernel
+    cudaStream_t aux_stream;   // internal second stream (look-ahead in the blocked QR)
+    cudaEvent_t ev[8];         // fork/join and look-ahead events
     char err[256];
 };
 
@@ -214,15 +216,15 @@ extern KernelClock g_clock_gemm;  // DMMA GEMM launches
 struct PhaseTimer {
     bool on;
     cudaStream_t s;
-    cudaEvent_t ev[16];
-    const char* names[16];
+    cudaEvent_t ev[48];
+    const char* names[48];
     int n;
     explicit PhaseTimer(cudaStream_t st) : s(st), n(0) {
         const char* e = getenv("MAKB200_PROFILE");
         on = e && e[0] == '1';
     }
     void mark(const char* name) {
-        if (!on || n >= 16) return;
+        if (!on || n >= 48) return;
         cudaEventCreate(&ev[n]);
         cudaEventRecord(ev[n], s);
         names[n++] = name;

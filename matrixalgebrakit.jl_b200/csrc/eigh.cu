@@ -98,7 +98,10 @@ struct TrdCtx {
     T* A; int lda;
     T* P; int ldp;   // panel [V | W | V], each pw columns wide
     int pw;
-    T* y;            // n
+    T* y;            // [nstrips][maxseg][CW] : column parts of y = A22 v per (strip, row segment)
+    int maxseg;
+    int seg;         // rows per segment
+    T* ypart; int ldy;  // [nstrips][n] : row parts of y, one slice per column strip
     T* t;            // 2*TRD_NB : t1 = W^H v, t2 = V^H v
     double* pn;      // partial tail norms of the current column
     T* pyv;          // partial y^H v
@@ -189,6 +192,200 @@ trd_dots_kernel(TrdCtx<T> x, int c, int i, int npn) {
     }
 }
 
+// Symmetric single-pass kernel: reads only the LOWER triangle of the trailing matrix (half the
+// HBM traffic of a full gemv).  CTA b owns the column strip [cb, cb+CW) and streams it once:
+// lane = row, registers hold one partial dot product per strip column (column part, reduced at
+// the end) while the row part of the strip goes to ypart[b][r] (summed over strips by trd_w_kernel).
+// v^H A22 v (needed for the rank-2 correction) is accumulated on the fly.  CTAs beyond the strips
+// do the panel dot products W^H v, V^H v.
+constexpr int TRD_SEG_MIN = 512;  // smallest row segment (sizes the partial buffers)
+// rows per CTA of a column strip (balances the triangular work); env override for tuning
+static int trd_seg() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MAKB200_TRD_SEG");
+        v = e ? atoi(e) : 2048;
+        if (v < TRD_SEG_MIN) v = TRD_SEG_MIN;
+        v = (v + 31) / 32 * 32;
+    }
+    return v;
+}
+template <typename T> struct SymvCW { static constexpr int value = 16; };
+template <> struct SymvCW<cplx> { static constexpr int value = 8; };
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+trd_symv_kernel(TrdCtx<T> x, int c, int i, int npn, int nstrips) {
+    constexpr int CW = SymvCW<T>::value;
+    const int SEG = x.seg;
+    const int sgi = blockIdx.y;
+    const int slot = sgi * gridDim.x + blockIdx.x;
+    __shared__ T s_vc[CW];
+    __shared__ T s_col[8][CW];
+    __shared__ double s_q[8];
+    const int n = x.n, row0 = c + 1, mt = n - row0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // tail norm of the column: partials summed by warp 0 in a fixed order (identical in every CTA)
+    __shared__ double s_sigma;
+    if (warp == 0) {
+        double sg = 0.0;
+        for (int q = lane; q < npn; q += 32) sg += x.pn[q];
+        sg = warp_sum(sg);
+        if (lane == 0) s_sigma = sg;
+    }
+    __syncthreads();
+    const double sigma = s_sigma;
+    const T* acol = x.A + (size_t)c * x.lda + row0;
+    const T alpha = acol[0];
+    double beta; T tau, scale;
+    larfgp_scalars<T>(alpha, sigma, beta, tau, scale);
+
+    if ((int)blockIdx.x >= nstrips) {
+        if (sgi > 0) { if (tid == 0) x.pyv[slot] = zero<T>(); return; }
+        // ---- panel columns: t1 = W^H v, t2 = V^H v ----
+        const int q0 = (((int)blockIdx.x - nstrips) * 8 + warp) * 4;
+        const T* col[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int q = q0 + k;
+            if (q < i) col[k] = x.P + (size_t)(x.pw + q) * x.ldp + row0;
+            else if (q < 2 * i) col[k] = x.P + (size_t)(q - i) * x.ldp + row0;
+            else col[k] = nullptr;
+        }
+        T acc[4] = {zero<T>(), zero<T>(), zero<T>(), zero<T>()};
+        if (q0 < 2 * i) {
+            for (int r = lane; r < mt; r += 32) {
+                T vr = (r == 0) ? one<T>() : mul_(acol[r], scale);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (col[k]) fmac_(acc[k], col[k][r], vr);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            acc[k] = warp_sum(acc[k]);
+            int q = q0 + k;
+            if (lane == 0 && q < 2 * i) {
+                if (q < i) x.t[q] = acc[k];
+                else x.t[TRD_NB + (q - i)] = acc[k];
+            }
+        }
+        if (tid == 0) x.pyv[slot] = zero<T>();
+        return;
+    }
+
+    const int cb = blockIdx.x * CW;
+    const int cw = (mt - cb < CW) ? (mt - cb) : CW;
+    const int rs = cb + sgi * SEG;                         // this CTA's row segment of the strip
+    if (rs >= mt) { if (tid == 0) x.pyv[slot] = zero<T>(); return; }
+    const int re = (rs + SEG < mt) ? (rs + SEG) : mt;
+    if (tid < CW) {
+        T vq = zero<T>();
+        if (tid < cw) {
+            int r = cb + tid;
+            vq = (r == 0) ? one<T>() : mul_(acol[r], scale);
+            if (sgi == 0) {
+                x.P[(size_t)i * x.ldp + row0 + r] = vq;                  // V(:, i)
+                x.P[(size_t)(2 * x.pw + i) * x.ldp + row0 + r] = vq;     // second copy
+            }
+        }
+        s_vc[tid] = vq;
+    }
+    __syncthreads();
+    T colacc[CW];
+#pragma unroll
+    for (int k = 0; k < CW; ++k) colacc[k] = zero<T>();
+    double qacc = 0.0;
+    const T* Ab = x.A + (size_t)(row0 + cb) * x.lda + row0;  // A22(:, cb), local row index
+    T* Yp = x.ypart + (size_t)blockIdx.x * x.ldy + row0;
+    for (int rt = rs + 32 * warp; rt < re; rt += 256) {
+        const int r = rt + lane;
+        if (r >= re) continue;
+        const T vr = (r == 0) ? one<T>() : mul_(acol[r], scale);
+        T rowoff = zero<T>();
+        double ad = 0.0;
+        if (rt >= cb + CW && cw == CW) {
+            // strictly below the diagonal block of a full strip: batches of CW/2 independent loads
+            // per lane (register budget for two resident CTAs per SM), then two FMAs per element
+            constexpr int HB = CW;
+#pragma unroll
+            for (int hb = 0; hb < 1; ++hb) {
+                T av[HB];
+#pragma unroll
+                for (int k = 0; k < HB; ++k) av[k] = Ab[(size_t)(hb * HB + k) * x.lda + r];
+#pragma unroll
+                for (int k = 0; k < HB; ++k) {
+                    fma_(rowoff, av[k], s_vc[hb * HB + k]);
+                    fmac_(colacc[hb * HB + k], av[k], vr);
+                }
+            }
+        } else if (rt >= cb + CW) {
+#pragma unroll
+            for (int k = 0; k < CW; ++k) {
+                if (k < cw) {
+                    T a = Ab[(size_t)k * x.lda + r];
+                    fma_(rowoff, a, s_vc[k]);
+                    fmac_(colacc[k], a, vr);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < CW; ++k) {
+                const int cc = cb + k;
+                if (k < cw) {
+                    if (r > cc) {
+                        T a = Ab[(size_t)k * x.lda + r];
+                        fma_(rowoff, a, s_vc[k]);
+                        fmac_(colacc[k], a, vr);
+                    } else if (r == cc) {
+                        ad = real_(Ab[(size_t)k * x.lda + r]);  // Hermitian: real diagonal
+                    }
+                }
+            }
+        }
+        Yp[r] = add_(rowoff, scale_(vr, ad));
+        T cv = zero<T>();
+        fmac_(cv, vr, rowoff);               // conj(v_r) * (off-diagonal row part)
+        qacc += 2.0 * real_(cv) + ad * abs2_(vr);
+    }
+    // column parts: reduce over lanes, then over warps
+#pragma unroll
+    for (int k = 0; k < CW; ++k) {
+        T v = warp_sum(colacc[k]);
+        if (lane == 0) s_col[warp][k] = v;
+    }
+    qacc = warp_sum(qacc);
+    if (lane == 0) s_q[warp] = qacc;
+    __syncthreads();
+    if (tid < cw) {
+        T v = zero<T>();
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v = add_(v, s_col[w][tid]);
+        x.y[((size_t)blockIdx.x * x.maxseg + sgi) * CW + tid] = v;
+    }
+    if (tid == 0) {
+        double q = 0.0;
+        for (int w = 0; w < 8; ++w) q += s_q[w];
+        x.pyv[slot] = mk<T>(q);   // v^H A22 v is real
+        if (blockIdx.x == 0 && sgi == 0) {
+            x.tau[c] = tau;
+            x.e[c] = beta;
+            x.d[c] = real_(x.A[(size_t)c * x.lda + c]);
+        }
+    }
+}
+
+// column part of y for global row r: sum over the row segments of the strip that owns column r
+template <typename T>
+__device__ __forceinline__ T trd_ycol(const TrdCtx<T>& x, int row0, int mt, int r) {
+    constexpr int CW = SymvCW<T>::value;
+    const int rl = r - row0, b = rl / CW, k = rl - b * CW;
+    const int nseg = (mt - b * CW + x.seg - 1) / x.seg;
+    T s = zero<T>();
+    for (int sg = 0; sg < nseg; ++sg) s = add_(s, x.y[((size_t)b * x.maxseg + sg) * CW + k]);
+    return s;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 trd_w_kernel(TrdCtx<T> x, int c, int i, int npyv, int do_next) {
@@ -217,8 +414,9 @@ trd_w_kernel(TrdCtx<T> x, int c, int i, int npyv, int do_next) {
             fmac_(s12, st[p], st[TRD_NB + p]);
             fmac_(s12, st[TRD_NB + p], st[p]);
         }
-        // first row of w (row c+1): y - V t1 - W t2
+        // first row of w (row c+1): y - V t1 - W t2, y[row0] = column part + row part of strip 0
         T sf = zero<T>();
+        if (lane == 0) sf = neg_(x.ypart[row0]);
         for (int p = lane; p < i; p += 32) {
             fma_(sf, x.P[(size_t)p * x.ldp + row0], st[p]);
             fma_(sf, x.P[(size_t)(x.pw + p) * x.ldp + row0], st[TRD_NB + p]);
@@ -229,7 +427,7 @@ trd_w_kernel(TrdCtx<T> x, int c, int i, int npyv, int do_next) {
         if (lane == 0) {
             T whv = mul_(conj_(tauc), sub_(yhv, s12));
             T alpha2 = neg_(scale_(mul_(tauc, whv), 0.5));
-            T wfirst = add_(mul_(tauc, sub_(x.y[row0], sf)), alpha2);  // v[row0] = 1
+            T wfirst = add_(mul_(tauc, sub_(trd_ycol<T>(x, row0, n - row0, row0), sf)), alpha2);  // v[row0] = 1
             sscal[0] = alpha2;
             sscal[1] = wfirst;
         }
@@ -243,6 +441,9 @@ trd_w_kernel(TrdCtx<T> x, int c, int i, int npyv, int do_next) {
             fma_(part, x.P[(size_t)p * x.ldp + r], st[p]);
             fma_(part, x.P[(size_t)(x.pw + p) * x.ldp + r], st[TRD_NB + p]);
         }
+        // row parts of y from every strip at or left of this row (subtracted: w = tau (y - part))
+        const int nsb = (r - row0) / SymvCW<T>::value + 1;
+        for (int b = ty; b < nsb; b += 4) part = sub_(part, x.ypart[(size_t)b * x.ldy + r]);
     }
     sm[ty][tx] = part;
     __syncthreads();
@@ -250,7 +451,7 @@ trd_w_kernel(TrdCtx<T> x, int c, int i, int npyv, int do_next) {
     if (live) {
         T s = add_(add_(sm[0][tx], sm[1][tx]), add_(sm[2][tx], sm[3][tx]));
         vr = x.P[(size_t)i * x.ldp + r];
-        wr = add_(mul_(tauc, sub_(x.y[r], s)), mul_(alpha2, vr));
+        wr = add_(mul_(tauc, sub_(trd_ycol<T>(x, row0, n - row0, r), s)), mul_(alpha2, vr));
         if (ty == 0) {
             x.P[(size_t)(x.pw + i) * x.ldp + r] = wr;                              // W(:, i)
             x.A[(size_t)c * x.lda + r] = (r == row0) ? mk<T>(x.e[c]) : vr;          // reflector storage
@@ -299,10 +500,14 @@ static void trd_carve(AR& ar, int n, TrdCtx<T>* x) {
     x->n = n;
     x->P = ar.template get<T>(nn * 3 * TRD_NB);
     x->ldp = n > 0 ? n : 1;
-    x->y = ar.template get<T>(nn);
+    x->maxseg = (int)((nn + TRD_SEG_MIN - 1) / TRD_SEG_MIN);
+    x->seg = trd_seg();
+    x->y = ar.template get<T>((nn + SymvCW<T>::value) * (size_t)x->maxseg);
+    x->ldy = n > 0 ? n : 1;
+    x->ypart = ar.template get<T>(nn * ((nn + SymvCW<T>::value - 1) / SymvCW<T>::value));
     x->t = ar.template get<T>(2 * TRD_NB);
     x->pn = ar.template get<double>(nn / TRD_K2_ROWS + 2);
-    x->pyv = ar.template get<T>((nn + 2 * TRD_NB) / TRD_K1_COLS + 2);
+    x->pyv = ar.template get<T>((nn / SymvCW<T>::value + 2 * TRD_NB / 32 + 8) * (size_t)(x->maxseg + 1));
     x->tau = ar.template get<T>(nn);
     x->d = ar.template get<double>(nn);
     x->e = ar.template get<double>(nn);
@@ -329,9 +534,11 @@ static int hetrd(makb200_handle* h, TrdCtx<T>& x) {
         for (int i = 0; i < ncols; ++i) {
             const int c = j0 + i, mt = n - c - 1;
             const int g2 = (mt + TRD_K2_ROWS - 1) / TRD_K2_ROWS;
-            const int g1 = (mt + 2 * i + TRD_K1_COLS - 1) / TRD_K1_COLS;
+            const int nstrips = (mt + SymvCW<T>::value - 1) / SymvCW<T>::value;
+            const int gx = nstrips + (2 * i + 31) / 32, gy = (mt + x.seg - 1) / x.seg;
+            const int g1 = gx * gy;  // pyv slots written by this launch
             g_clock_dots.begin(s);
-            trd_dots_kernel<T><<<g1, TRD_K1_THREADS, 0, s>>>(x, c, i, npn);
+            trd_symv_kernel<T><<<dim3(gx, gy), 256, 0, s>>>(x, c, i, npn, nstrips);
             g_clock_dots.end(s);
             const int do_next = (i + 1 < ncols) ? 1 : 0;
             trd_w_kernel<T><<<g2, 256, 0, s>>>(x, c, i, g1, do_next);
@@ -342,9 +549,10 @@ static int hetrd(makb200_handle* h, TrdCtx<T>& x) {
         // trailing update: A[t0:, t0:] -= [V W][W V]^H  (rows >= t0 of the panel)
         const int t0 = j0 + ncols, mtr = n - t0;
         if (mtr > 0) {
+            // only the lower triangle of the trailing matrix is ever read: skip tiles above it
             cudaError_t e = gemm<T>(s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, mtr, mtr, 2 * ncols, neg_(one<T>()),
                                     x.P + t0, x.ldp, x.P + (size_t)ncols * x.ldp + t0, x.ldp, one<T>(),
-                                    x.A + (size_t)t0 * x.lda + t0, x.lda, nullptr, 0);
+                                    x.A + (size_t)t0 * x.lda + t0, x.lda, nullptr, 0, true);
             if (e != cudaSuccess) return cuda_fail(h, e, "hetrd gemm");
         }
     }

@@ -11,30 +11,33 @@ KernelClock g_clock_gemm;
 // ---------------------------------------------------------------------------------------
 // tile configuration
 // ---------------------------------------------------------------------------------------
-template <typename T> struct Cfg;
-template <> struct Cfg<double> {
-    static constexpr int BM = 128, BN = 128, BK = 16, WM = 64, WN = 32, STAGES = 4;
+// Config<T, V>: V = 0 default; V = 1 alternative (512 threads, 32x32 warp tiles) for f64
+template <typename T, int V> struct Cfg;
+template <> struct Cfg<double, 0> {
+    static constexpr int BM = 128, BN = 128, BK = 16, WM = 64, WN = 32, STAGES = 4, THREADS = 256;
     // strides (in elements) chosen so that the 16 lanes of a half-warp hit 16 distinct
     // 8-byte banks for both fragment patterns: S == 4 (mod 8)
     static constexpr int SA_MN = BM + 4, SB_MN = BN + 4, S_K = BK + 4;
 };
-template <> struct Cfg<cplx> {
-    static constexpr int BM = 64, BN = 128, BK = 8, WM = 32, WN = 32, STAGES = 4;
+template <> struct Cfg<double, 1> {
+    static constexpr int BM = 128, BN = 128, BK = 16, WM = 32, WN = 32, STAGES = 4, THREADS = 512;
+    static constexpr int SA_MN = BM + 4, SB_MN = BN + 4, S_K = BK + 4;
+};
+template <> struct Cfg<cplx, 0> {
+    static constexpr int BM = 64, BN = 128, BK = 8, WM = 32, WN = 32, STAGES = 4, THREADS = 256;
     // 16-byte elements: quarter-warp (8 lanes) must hit 8 distinct 16-byte banks:
     // [k][mn] layout needs S == 2 (mod 4), [mn][k] layout needs S == 4 (mod 8)
     static constexpr int SA_MN = BM + 2, SB_MN = BN + 2, S_K = BK + 4;
 };
-constexpr int GEMM_THREADS = 256;
+template <> struct Cfg<cplx, 1> : Cfg<cplx, 0> {};
 
-template <typename T, bool TA> struct ATile {
-    using C = Cfg<T>;
+template <typename T, typename C, bool TA> struct ATile {
     static constexpr int STRIDE = TA ? C::S_K : C::SA_MN;
     static constexpr int ROWS = TA ? C::BM : C::BK;
     static constexpr int CONTIG = TA ? C::BK : C::BM;
     static constexpr int ELEMS = STRIDE * ROWS;
 };
-template <typename T, bool TB> struct BTile {
-    using C = Cfg<T>;
+template <typename T, typename C, bool TB> struct BTile {
     static constexpr int STRIDE = TB ? C::SB_MN : C::S_K;
     static constexpr int ROWS = TB ? C::BK : C::BN;
     static constexpr int CONTIG = TB ? C::BN : C::BK;
@@ -62,7 +65,7 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 
 // Load a CONTIG x ROWS tile: element (c, r) <- g[(c0+c) + (r0+r)*ld] if in range else 0,
 // stored at smem[r*STRIDE + c].
-template <typename T, int CONTIG, int ROWS, int STRIDE>
+template <typename T, int GEMM_THREADS, int CONTIG, int ROWS, int STRIDE>
 __device__ __forceinline__ void load_tile(T* smem, const T* __restrict__ g, int ld, int c0, int r0,
                                           int cmax, int rmax, bool vec16) {
     if constexpr (is_cplx<T>::value) {
@@ -112,13 +115,12 @@ template <typename T> struct Acc;
 template <> struct Acc<double> { double c0, c1; };
 template <> struct Acc<cplx> { double r0, r1, i0, i1; };
 
-template <typename T, bool TA, bool TB>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <typename T, typename C, bool TA, bool TB>
+__global__ void __launch_bounds__(C::THREADS, 1)
 gemm_kernel(const GemmProblem<T> p0, const GemmProblem<T>* __restrict__ plist, int splitk,
             T* __restrict__ ws) {
-    using C = Cfg<T>;
-    using AT = ATile<T, TA>;
-    using BT = BTile<T, TB>;
+    using AT = ATile<T, C, TA>;
+    using BT = BTile<T, C, TB>;
     constexpr int BM = C::BM, BN = C::BN, BK = C::BK, WM = C::WM, WN = C::WN, ST = C::STAGES;
     constexpr int MT = WM / 8, NT = WN / 8;
     constexpr int WARPS_M = BM / WM;
@@ -131,6 +133,7 @@ gemm_kernel(const GemmProblem<T> p0, const GemmProblem<T>* __restrict__ plist, i
     const int M = p.m, N = p.n, K = p.k;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     if (M <= 0 || N <= 0 || m0 >= M || n0 >= N) return;
+    if (p.lower && n0 >= m0 + BM) return;  // tile entirely above the diagonal
 
     int ktiles = K > 0 ? (K + BK - 1) / BK : 0;
     int kt_beg = 0, kt_end = ktiles;
@@ -156,10 +159,10 @@ gemm_kernel(const GemmProblem<T> p0, const GemmProblem<T>* __restrict__ plist, i
         const int k0 = kt * BK;
         T* a = sA + stage * AT::ELEMS;
         T* b = sB + stage * BT::ELEMS;
-        if constexpr (TA) load_tile<T, AT::CONTIG, AT::ROWS, AT::STRIDE>(a, p.A, p.lda, k0, m0, K, M, vecA);
-        else load_tile<T, AT::CONTIG, AT::ROWS, AT::STRIDE>(a, p.A, p.lda, m0, k0, M, K, vecA);
-        if constexpr (TB) load_tile<T, BT::CONTIG, BT::ROWS, BT::STRIDE>(b, p.B, p.ldb, n0, k0, N, K, vecB);
-        else load_tile<T, BT::CONTIG, BT::ROWS, BT::STRIDE>(b, p.B, p.ldb, k0, n0, K, N, vecB);
+        if constexpr (TA) load_tile<T, C::THREADS, AT::CONTIG, AT::ROWS, AT::STRIDE>(a, p.A, p.lda, k0, m0, K, M, vecA);
+        else load_tile<T, C::THREADS, AT::CONTIG, AT::ROWS, AT::STRIDE>(a, p.A, p.lda, m0, k0, M, K, vecA);
+        if constexpr (TB) load_tile<T, C::THREADS, BT::CONTIG, BT::ROWS, BT::STRIDE>(b, p.B, p.ldb, n0, k0, N, K, vecB);
+        else load_tile<T, C::THREADS, BT::CONTIG, BT::ROWS, BT::STRIDE>(b, p.B, p.ldb, k0, n0, K, N, vecB);
     };
 
     Acc<T> acc[MT][NT];
@@ -279,39 +282,53 @@ __global__ void scale_c_kernel(int M, int N, T beta, T* __restrict__ Cm, int ldc
     }
 }
 
-template <typename T, bool TA, bool TB>
+static int gemm_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MAKB200_GEMM_VARIANT"); v = e ? atoi(e) : 1; if (v != 0) v = 1; }
+    return v;
+}
+
+template <typename T, typename C, bool TA, bool TB>
 static cudaError_t launch(cudaStream_t stream, dim3 grid, const GemmProblem<T>& p,
                           const GemmProblem<T>* plist, int splitk, T* ws) {
-    using C = Cfg<T>;
-    constexpr size_t smem = (size_t)C::STAGES * (ATile<T, TA>::ELEMS + BTile<T, TB>::ELEMS) * sizeof(T);
+    constexpr size_t smem = (size_t)C::STAGES * (ATile<T, C, TA>::ELEMS + BTile<T, C, TB>::ELEMS) * sizeof(T);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<T, TA, TB>,
+        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<T, C, TA, TB>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     g_clock_gemm.begin(stream);
-    gemm_kernel<T, TA, TB><<<grid, GEMM_THREADS, smem, stream>>>(p, plist, splitk, ws);
+    gemm_kernel<T, C, TA, TB><<<grid, C::THREADS, smem, stream>>>(p, plist, splitk, ws);
     g_clock_gemm.end(stream);
     count_launch();
     return cudaGetLastError();
 }
 
+template <typename T, typename C>
+static cudaError_t dispatch2(cudaStream_t stream, bool ta, bool tb, dim3 grid, const GemmProblem<T>& p,
+                             const GemmProblem<T>* plist, int splitk, T* ws) {
+    if (!ta && !tb) return launch<T, C, false, false>(stream, grid, p, plist, splitk, ws);
+    if (ta && !tb) return launch<T, C, true, false>(stream, grid, p, plist, splitk, ws);
+    if (!ta && tb) return launch<T, C, false, true>(stream, grid, p, plist, splitk, ws);
+    return launch<T, C, true, true>(stream, grid, p, plist, splitk, ws);
+}
+
 template <typename T>
 static cudaError_t dispatch(cudaStream_t stream, bool ta, bool tb, dim3 grid, const GemmProblem<T>& p,
                             const GemmProblem<T>* plist, int splitk, T* ws) {
-    if (!ta && !tb) return launch<T, false, false>(stream, grid, p, plist, splitk, ws);
-    if (ta && !tb) return launch<T, true, false>(stream, grid, p, plist, splitk, ws);
-    if (!ta && tb) return launch<T, false, true>(stream, grid, p, plist, splitk, ws);
-    return launch<T, true, true>(stream, grid, p, plist, splitk, ws);
+    if constexpr (!is_cplx<T>::value) {
+        if (gemm_variant() == 1) return dispatch2<T, Cfg<T, 1>>(stream, ta, tb, grid, p, plist, splitk, ws);
+    }
+    return dispatch2<T, Cfg<T, 0>>(stream, ta, tb, grid, p, plist, splitk, ws);
 }
 
 template <typename T>
 cudaError_t gemm(cudaStream_t stream, int num_sms, int opa, int opb, int m, int n, int k, T alpha,
                  const T* A, int lda, const T* B, int ldb, T beta, T* Cm, int ldc, void* ws,
-                 size_t ws_bytes) {
-    using C = Cfg<T>;
+                 size_t ws_bytes, bool lower) {
+    using C = Cfg<T, 0>;  // both variants share the CTA tile
     if (m <= 0 || n <= 0) return cudaSuccess;
     if (k <= 0 || is_zero(alpha)) {
         if (is_one(beta)) return cudaSuccess;
@@ -323,6 +340,7 @@ cudaError_t gemm(cudaStream_t stream, int num_sms, int opa, int opb, int m, int 
     p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = Cm; p.ldc = ldc;
     p.alpha = alpha; p.beta = beta;
     p.conja = (opa == MAKB200_OP_C); p.conjb = (opb == MAKB200_OP_C);
+    p.lower = lower ? 1 : 0;
     dim3 grid((m + C::BM - 1) / C::BM, (n + C::BN - 1) / C::BN, 1);
     // split-K when the output grid cannot fill the machine and K is long
     int splitk = 1;
@@ -350,7 +368,7 @@ cudaError_t gemm(cudaStream_t stream, int num_sms, int opa, int opb, int m, int 
 template <typename T>
 cudaError_t gemm_grouped(cudaStream_t stream, int opa, int opb, int count, int max_m, int max_n,
                          const GemmProblem<T>* problems_dev) {
-    using C = Cfg<T>;
+    using C = Cfg<T, 0>;
     if (count <= 0 || max_m <= 0 || max_n <= 0) return cudaSuccess;
     dim3 grid((max_m + C::BM - 1) / C::BM, (max_n + C::BN - 1) / C::BN, count);
     GemmProblem<T> dummy{};
@@ -358,9 +376,9 @@ cudaError_t gemm_grouped(cudaStream_t stream, int opa, int opb, int count, int m
 }
 
 template cudaError_t gemm<double>(cudaStream_t, int, int, int, int, int, int, double, const double*, int,
-                                  const double*, int, double, double*, int, void*, size_t);
+                                  const double*, int, double, double*, int, void*, size_t, bool);
 template cudaError_t gemm<cplx>(cudaStream_t, int, int, int, int, int, int, cplx, const cplx*, int, const cplx*,
-                                int, cplx, cplx*, int, void*, size_t);
+                                int, cplx, cplx*, int, void*, size_t, bool);
 template cudaError_t gemm_grouped<double>(cudaStream_t, int, int, int, int, int, const GemmProblem<double>*);
 template cudaError_t gemm_grouped<cplx>(cudaStream_t, int, int, int, int, int, const GemmProblem<cplx>*);
 

@@ -20,6 +20,7 @@ struct GemmProblem {
     int ldc;
     T alpha, beta;
     int conja, conjb;
+    int lower;  // 1: C is only needed on/below the diagonal (tiles above are skipped)
 };
 
 // Host-side launcher.  opa/opb: MAKB200_OP_{N,T,C}.  `ws`/`ws_bytes`: optional split-K
@@ -27,7 +28,7 @@ struct GemmProblem {
 template <typename T>
 cudaError_t gemm(cudaStream_t stream, int num_sms, int opa, int opb, int m, int n, int k, T alpha,
                  const T* A, int lda, const T* B, int ldb, T beta, T* C, int ldc,
-                 void* ws = nullptr, size_t ws_bytes = 0);
+                 void* ws = nullptr, size_t ws_bytes = 0, bool lower = false);
 
 // Grouped launch: `count` problems described in DEVICE memory (dims may be produced on the
 // device by an earlier kernel); max_m/max_n are host upper bounds used to size the grid.

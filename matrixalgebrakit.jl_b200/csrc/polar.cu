@@ -160,45 +160,81 @@ __global__ void adjoint_kernel(int m, int n, const T* __restrict__ S, int lds, T
 // ---------------------------------------------------------------------------------------
 // one CTA: L = chol(Zblk) (nb x nb, lower) and Linv = L^-1; both written with zeros above the
 // diagonal.  info[0] set to 1 if a pivot is not positive.
-template <typename T>
+// The block is held in REGISTERS, 2-D cyclic over a 16 x 16 thread grid (thread (ti,tj) owns rows
+// ti+16a, columns tj+16b); per column k: pivot -> scaled column to shared memory -> rank-1 update
+// of the register tile.  Two block barriers per column, no shared-memory traffic for the matrix.
+template <typename T, int NB>
 __global__ void __launch_bounds__(256)
 potf2_inv_kernel(int nb, const T* __restrict__ Zb, int ldz, T* __restrict__ Lb, int ldl, T* __restrict__ Linv,
                  int ldi, int* info) {
+    constexpr int E = NB / 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* S = reinterpret_cast<T*>(smem_raw);  // [nb][nb+1] column-major: S[c*(nb+1)+r]
-    const int lds = nb + 1, tid = threadIdx.x;
-    for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
-        int c = idx / nb, r = idx - c * nb;
-        S[c * lds + r] = (r >= c) ? Zb[(size_t)c * ldz + r] : zero<T>();
-    }
-    __syncthreads();
-    for (int k = 0; k < nb; ++k) {
-        if (tid == 0) {
-            double akk = real_(S[k * lds + k]);
-            if (!(akk > 0.0)) { atomicExch(info, 1); akk = 1.0; }
-            S[k * lds + k] = mk<T>(sqrt(akk));
+    T* S = reinterpret_cast<T*>(smem_raw);  // [NB][NB+1] column-major: S[c*(NB+1)+r] (L for the inverse)
+    __shared__ T s_col[NB];
+    __shared__ double s_piv;
+    const int lds = NB + 1, tid = threadIdx.x, ti = tid & 15, tj = tid >> 4;
+    T a[E][E];
+#pragma unroll
+    for (int ia = 0; ia < E; ++ia)
+#pragma unroll
+        for (int ib = 0; ib < E; ++ib) {
+            const int r = ti + 16 * ia, c = tj + 16 * ib;
+            a[ia][ib] = (r < nb && c < nb && r >= c) ? Zb[(size_t)c * ldz + r] : zero<T>();
         }
-        __syncthreads();
-        const double inv = 1.0 / real_(S[k * lds + k]);
-        for (int r = k + 1 + tid; r < nb; r += blockDim.x) S[k * lds + r] = scale_(S[k * lds + r], inv);
-        __syncthreads();
-        // trailing lower triangle: S[r][c] -= S[r][k] * conj(S[c][k]),  k < c <= r
-        const int w = nb - k - 1;
-        for (int idx = tid; idx < w * w; idx += blockDim.x) {
-            int c = k + 1 + idx / w, r = k + 1 + idx % w;
-            if (r >= c) {
-                T v = S[c * lds + r];
-                v = sub_(v, mul_(S[k * lds + r], conj_(S[k * lds + c])));
-                S[c * lds + r] = v;
+#pragma unroll
+    for (int kb = 0; kb < E; ++kb) {
+        for (int kk = 0; kk < 16; ++kk) {
+            const int k = kb * 16 + kk;
+            if (k >= nb) break;
+            if (ti == kk && tj == kk) {
+                double akk = real_(a[kb][kb]);
+                if (!(akk > 0.0)) { atomicExch(info, 1); akk = 1.0; }
+                s_piv = sqrt(akk);
+            }
+            __syncthreads();
+            const double piv = s_piv, inv = 1.0 / piv;
+            if (tj == kk) {
+#pragma unroll
+                for (int ia = 0; ia < E; ++ia) {
+                    const int r = ti + 16 * ia;
+                    if (r > k) {
+                        T v = scale_(a[ia][kb], inv);
+                        a[ia][kb] = v;
+                        s_col[r] = v;
+                    } else if (r == k) {
+                        a[ia][kb] = mk<T>(piv);
+                    }
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int ia = 0; ia < E; ++ia) {
+                const int r = ti + 16 * ia;
+                if (r > k && r < nb) {
+                    const T lr = s_col[r];
+#pragma unroll
+                    for (int ib = 0; ib < E; ++ib) {
+                        const int c = tj + 16 * ib;
+                        if (c > k && c <= r) a[ia][ib] = sub_(a[ia][ib], mul_(lr, conj_(s_col[c])));
+                    }
+                }
             }
         }
-        __syncthreads();
     }
-    for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
-        int c = idx / nb, r = idx - c * nb;
-        Lb[(size_t)c * ldl + r] = (r >= c) ? S[c * lds + r] : zero<T>();
-    }
-    // inverse: thread c solves L x = e_c by forward substitution (x overwrites nothing in S)
+    __syncthreads();
+#pragma unroll
+    for (int ia = 0; ia < E; ++ia)
+#pragma unroll
+        for (int ib = 0; ib < E; ++ib) {
+            const int r = ti + 16 * ia, c = tj + 16 * ib;
+            if (r < nb && c < nb) {
+                T v = (r >= c) ? a[ia][ib] : zero<T>();
+                S[c * lds + r] = v;
+                Lb[(size_t)c * ldl + r] = v;
+            }
+        }
+    __syncthreads();
+    // inverse: thread c solves L x = e_c by forward substitution
     for (int c = tid; c < nb; c += blockDim.x) {
         T* out = Linv + (size_t)c * ldi;
         for (int r = 0; r < c; ++r) out[r] = zero<T>();
@@ -214,7 +250,7 @@ potf2_inv_kernel(int nb, const T* __restrict__ Zb, int ldz, T* __restrict__ Lb, 
 template <typename T>
 static int potf2_init(makb200_handle* h) {
     constexpr int nb = CholNB<T>::value;
-    MAK_CUDA(h, cudaFuncSetAttribute(potf2_inv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MAK_CUDA(h, cudaFuncSetAttribute(potf2_inv_kernel<T, nb>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(sizeof(T) * nb * (nb + 1))));
     return 0;
 }
@@ -228,7 +264,8 @@ int polar_init(makb200_handle* h) {
 // left-looking blocked Cholesky: Z (n x n Hermitian, lower part read, destroyed) -> L (lower; only
 // blocks strictly below the block diagonal are referenced later) and Linv (nb x nb per block)
 template <typename T>
-static int potrf_blocked(makb200_handle* h, int n, T* Z, int ldz, T* L, int ldl, T* Linv, int* info) {
+static int potrf_blocked(makb200_handle* h, int n, T* Z, int ldz, T* L, int ldl, T* Linv, int* info,
+                         void* ws = nullptr, size_t ws_bytes = 0) {
     constexpr int nb = CholNB<T>::value;
     cudaStream_t s = h->stream;
     const T one_ = one<T>(), zero_ = zero<T>(), mone = neg_(one<T>());
@@ -236,8 +273,8 @@ static int potrf_blocked(makb200_handle* h, int n, T* Z, int ldz, T* L, int ldl,
         const int jb = (n - j0 < nb) ? (n - j0) : nb;
         if (j0 > 0)
             MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, n - j0, jb, j0, mone, L + j0, ldl, L + j0, ldl,
-                      one_, Z + (size_t)j0 * ldz + j0, ldz, nullptr, 0);
-        potf2_inv_kernel<T><<<1, 256, sizeof(T) * jb * (jb + 1), s>>>(jb, Z + (size_t)j0 * ldz + j0, ldz,
+                      one_, Z + (size_t)j0 * ldz + j0, ldz, ws, ws_bytes);
+        potf2_inv_kernel<T, nb><<<1, 256, sizeof(T) * nb * (nb + 1), s>>>(jb, Z + (size_t)j0 * ldz + j0, ldz,
                                                                       L + (size_t)j0 * ldl + j0, ldl,
                                                                       Linv + (size_t)b * nb * nb, nb, info);
         count_launch();
@@ -253,7 +290,7 @@ static int potrf_blocked(makb200_handle* h, int n, T* Z, int ldz, T* L, int ldl,
 // Y = X L^-H (conjtrans) or Y = X L^-1, X m x n untouched, Tmp m x nb scratch
 template <typename T>
 static int trsm_right(makb200_handle* h, bool conjtrans, int m, int n, const T* X, int ldx, const T* L, int ldl,
-                      const T* Linv, T* Y, int ldy, T* Tmp) {
+                      const T* Linv, T* Y, int ldy, T* Tmp, void* ws = nullptr, size_t ws_bytes = 0) {
     constexpr int nb = CholNB<T>::value;
     cudaStream_t s = h->stream;
     const T one_ = one<T>(), zero_ = zero<T>(), mone = neg_(one<T>());
@@ -267,7 +304,7 @@ static int trsm_right(makb200_handle* h, bool conjtrans, int m, int n, const T* 
             // (Y L^H)_j = sum_{i<=j} Y_i L_ji^H
             if (j0 > 0)
                 MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, m, jb, j0, mone, Y, ldy, L + j0, ldl, one_, Tmp,
-                          m, nullptr, 0);
+                          m, ws, ws_bytes);
             MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, m, jb, jb, one_, Tmp, m,
                       Linv + (size_t)b * nb * nb, nb, zero_, Y + (size_t)j0 * ldy, ldy, nullptr, 0);
         } else {
@@ -275,7 +312,7 @@ static int trsm_right(makb200_handle* h, bool conjtrans, int m, int n, const T* 
             const int j1 = j0 + jb, rest = n - j1;
             if (rest > 0)
                 MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_N, m, jb, rest, mone, Y + (size_t)j1 * ldy, ldy,
-                          L + (size_t)j0 * ldl + j1, ldl, one_, Tmp, m, nullptr, 0);
+                          L + (size_t)j0 * ldl + j1, ldl, one_, Tmp, m, ws, ws_bytes);
             MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_N, m, jb, jb, one_, Tmp, m,
                       Linv + (size_t)b * nb * nb, nb, zero_, Y + (size_t)j0 * ldy, ldy, nullptr, 0);
         }
@@ -288,6 +325,7 @@ static int trsm_right(makb200_handle* h, bool conjtrans, int m, int n, const T* 
 // QDWH
 // ---------------------------------------------------------------------------------------
 struct QdwhStep { double a, b, c; bool qr; };
+constexpr double QDWH_CHOLQR_MAX_C = 1e12;
 
 static std::vector<QdwhStep> qdwh_schedule(double l, int maxiter) {
     std::vector<QdwhStep> v;
@@ -316,6 +354,8 @@ struct PolarWork {
     int* info;
     void* sub;         // QR workspace
     size_t sub_bytes;
+    void* ws;          // split-K scratch for the skinny GEMMs of potrf / trsm
+    size_t ws_bytes;
 };
 
 template <typename T, typename AR>
@@ -331,7 +371,7 @@ static void polar_carve(makb200_handle* h, AR& ar, int m, int n, bool tall, Pola
     w->Linv = ar.template get<T>((size_t)nb * nb * ((nn + nb - 1) / nb));
     w->Y = ar.template get<T>(mm * nn);
     w->Y2 = ar.template get<T>(mm * nn);
-    w->Tmp = ar.template get<T>(mm * nb);
+    w->Tmp = ar.template get<T>((mm + nn) * nb);
     w->R0 = tall ? ar.template get<T>(nn * nn) : nullptr;
     w->Q0 = tall ? ar.template get<T>((size_t)m * nn) : nullptr;
     w->scal = ar.template get<double>(8);
@@ -341,6 +381,8 @@ static void polar_carve(makb200_handle* h, AR& ar, int m, int n, bool tall, Pola
     size_t b = tall ? qr_worksize_t<T>(h, m, n, n) : 0;
     w->sub_bytes = a > b ? a : b;
     w->sub = ar.template get<char>(w->sub_bytes);
+    w->ws_bytes = (size_t)h->num_sms * 128 * 128 * sizeof(double);
+    w->ws = ar.template get<char>(w->ws_bytes);
 }
 
 static inline bool polar_tall(int m, int n) { return m > n + n / 8; }
@@ -359,34 +401,67 @@ static int qdwh_iterate(makb200_handle* h, int ms, int n, PolarWork<T>& w, doubl
     cudaStream_t s = h->stream;
     std::vector<QdwhStep> sched = qdwh_schedule(l0, maxiter);
     if (iters_out) *iters_out = (int)sched.size();
+    PhaseTimer pt(s);
+    pt.mark("start");
     for (const QdwhStep& st : sched) {
         if (st.qr) {
             const int mb = ms + n;
             stack_kernel<T><<<grid_for2((size_t)mb * n, h->num_sms), 256, 0, s>>>(ms, n, w.X, ms, w.B, mb, sqrt(st.c));
             count_launch();
             MAK_LAUNCH_CHECK(h, "stack_kernel");
-            int rc = qr_fused_t<T>(h, MAKB200_QR_COMPACT, mb, n, w.B, mb, w.Q, mb, (T*)nullptr, 0, w.sub, w.sub_bytes);
-            if (rc) return rc;
+            const T* Qf;
+            if (st.c <= QDWH_CHOLQR_MAX_C) {
+                // cond([sqrt(c)X; I]) <= sqrt(1+c) <= 1e6: the orthonormal basis can be formed by
+                // CholeskyQR2 (all DMMA GEMMs) instead of Householder QR.
+                // pass 1: Z = B^H B = c X^H X + I (lower), L1, Q' = B L1^-H
+                eye_kernel<T><<<grid_for2((size_t)n * n, h->num_sms), 256, 0, s>>>(n, w.Z, n);
+                count_launch();
+                MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, n, n, ms, mk<T>(st.c), w.X, ms, w.X, ms,
+                          one<T>(), w.Z, n, nullptr, 0, true);
+                int rc = potrf_blocked<T>(h, n, w.Z, n, w.L, n, w.Linv, w.info, w.ws, w.ws_bytes);
+                if (rc) return rc;
+                rc = trsm_right<T>(h, true, mb, n, w.B, mb, w.L, n, w.Linv, w.Q, mb, w.Tmp, w.ws, w.ws_bytes);
+                if (rc) return rc;
+                // pass 2: Z = Q'^H Q' (lower), L2, Q = Q' L2^-H  (into B's storage)
+                MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, n, n, mb, one<T>(), w.Q, mb, w.Q, mb, zero<T>(),
+                          w.Z, n, nullptr, 0, true);
+                rc = potrf_blocked<T>(h, n, w.Z, n, w.L, n, w.Linv, w.info, w.ws, w.ws_bytes);
+                if (rc) return rc;
+                rc = trsm_right<T>(h, true, mb, n, w.Q, mb, w.L, n, w.Linv, w.B, mb, w.Tmp, w.ws, w.ws_bytes);
+                if (rc) return rc;
+                Qf = w.B;
+            } else {
+                int rc = qr_fused_t<T>(h, MAKB200_QR_COMPACT, mb, n, w.B, mb, w.Q, mb, (T*)nullptr, 0, w.sub,
+                                       w.sub_bytes);
+                if (rc) return rc;
+                Qf = w.Q;
+            }
             const double al = (st.a - st.b / st.c) / sqrt(st.c), be = st.b / st.c;
-            MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, ms, n, n, mk<T>(al), w.Q, mb, w.Q + ms, mb,
+            MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, ms, n, n, mk<T>(al), Qf, mb, Qf + ms, mb,
                       mk<T>(be), w.X, ms, nullptr, 0);
+            pt.mark(st.c <= QDWH_CHOLQR_MAX_C ? "cholqrstep" : "qrstep");
         } else {
             eye_kernel<T><<<grid_for2((size_t)n * n, h->num_sms), 256, 0, s>>>(n, w.Z, n);
             count_launch();
+            // Z is Hermitian and only its lower triangle is read by potrf: skip the tiles above it
             MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, n, n, ms, mk<T>(st.c), w.X, ms, w.X, ms, one<T>(),
-                      w.Z, n, nullptr, 0);
-            int rc = potrf_blocked<T>(h, n, w.Z, n, w.L, n, w.Linv, w.info);
+                      w.Z, n, nullptr, 0, true);
+            pt.mark("gram");
+            int rc = potrf_blocked<T>(h, n, w.Z, n, w.L, n, w.Linv, w.info, w.ws, w.ws_bytes);
             if (rc) return rc;
-            rc = trsm_right<T>(h, true, ms, n, w.X, ms, w.L, n, w.Linv, w.Y, ms, w.Tmp);
+            pt.mark("potrf");
+            rc = trsm_right<T>(h, true, ms, n, w.X, ms, w.L, n, w.Linv, w.Y, ms, w.Tmp, w.ws, w.ws_bytes);
             if (rc) return rc;
-            rc = trsm_right<T>(h, false, ms, n, w.Y, ms, w.L, n, w.Linv, w.Y2, ms, w.Tmp);
+            rc = trsm_right<T>(h, false, ms, n, w.Y, ms, w.L, n, w.Linv, w.Y2, ms, w.Tmp, w.ws, w.ws_bytes);
             if (rc) return rc;
+            pt.mark("trsm2");
             axpby_kernel<T><<<grid_for2((size_t)ms * n, h->num_sms), 256, 0, s>>>(ms, n, st.b / st.c, w.X, ms,
                                                                                   st.a - st.b / st.c, w.Y2, ms);
             count_launch();
             MAK_LAUNCH_CHECK(h, "axpby_kernel");
         }
     }
+    pt.report("qdwh steps");
     return 0;
 }
 

@@ -17,9 +17,18 @@ namespace cg = cooperative_groups;
 
 namespace mak {
 
-constexpr int QR_NB = 128;        // outer block width (K of the trailing-update GEMMs)
+constexpr int QR_NB_MAX = 128;    // outer block width (K of the trailing-update GEMMs)
+static int qr_nb() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MAKB200_QR_NB");
+        v = e ? atoi(e) : QR_NB_MAX;
+        if (v != 32 && v != 64 && v != 128) v = QR_NB_MAX;
+    }
+    return v;
+}
 constexpr int IBMAX = 32;         // inner panel width (max)
-constexpr int PANEL_THREADS = 256;
+constexpr int PANEL_THREADS = 512;
 constexpr size_t PANEL_SLAB_BYTES = 160 * 1024;  // shared-memory budget for the row slab
 
 // ---------------------------------------------------------------------------------------
@@ -57,20 +66,27 @@ panel_kernel(int mp, int ib, T* __restrict__ A, int lda, T* __restrict__ tau_out
     for (int j = 0; j < ib; ++j) {
         const int par = j & 1;
         const int ls = max(0, j + 1 - r0);  // first local row strictly below the diagonal
-        // ---- partial dot products over own rows: one warp per column l ----
+        // ---- partial dot products over own rows: one warp per pair of columns (shared a_j loads) ----
         const T* cj = slab + (size_t)j * rpc;
-        for (int l = warp; l < ib; l += NW) {
-            const T* cl = slab + (size_t)l * rpc;
-            T s = zero<T>();
-            if (l >= j) {
-                for (int r = ls + lane; r < nr; r += 32) fmac_(s, cj[r], cl[r]);  // conj(a_j) * a_l
-            } else {
-                for (int r = ls + lane; r < nr; r += 32) fmac_(s, cl[r], cj[r]);  // conj(v_l) * a_j
+        for (int l0 = 2 * warp; l0 < ib; l0 += 2 * NW) {
+            const int l1 = l0 + 1;
+            const bool has1 = l1 < ib;
+            const T* c0 = slab + (size_t)l0 * rpc;
+            const T* c1 = slab + (size_t)(has1 ? l1 : l0) * rpc;
+            T s0 = zero<T>(), s1 = zero<T>();
+            // l >= j: conj(a_j) * a_l ; l < j: conj(v_l) * a_j
+            const bool f0 = l0 >= j, f1 = l1 >= j;
+            for (int r = ls + lane; r < nr; r += 32) {
+                const T aj = cj[r], x0 = c0[r], x1 = c1[r];
+                if (f0) fmac_(s0, aj, x0); else fmac_(s0, x0, aj);
+                if (f1) fmac_(s1, aj, x1); else fmac_(s1, x1, aj);
             }
-            s = warp_sum(s);
+            s0 = warp_sum(s0);
+            s1 = warp_sum(s1);
             if (lane < CS) {
                 T* dst = cluster.map_shared_rank(xch, lane);
-                dst[(par * (CS + 1) + rank) * IBMAX + l] = s;
+                dst[(par * (CS + 1) + rank) * IBMAX + l0] = s0;
+                if (has1) dst[(par * (CS + 1) + rank) * IBMAX + l1] = s1;
             }
         }
         if (rank == 0) {
@@ -165,7 +181,7 @@ static cudaError_t launch_panel(makb200_handle* h, int mp, int ib, T* A, int lda
     int cs = 1;
     auto rows_per = [&](int c) { return ((mp + c - 1) / c + 31) / 32 * 32; };
     while (cs < h->max_cluster && mp / (cs * 2) >= ib &&
-           ((mp + cs - 1) / cs > 512 || (size_t)rows_per(cs) * ib * sizeof(T) > PANEL_SLAB_BYTES))
+           ((mp + cs - 1) / cs > 256 || (size_t)rows_per(cs) * ib * sizeof(T) > PANEL_SLAB_BYTES))
         cs *= 2;
     int rpc = rows_per(cs);
     if ((size_t)rpc * ib * sizeof(T) > PANEL_SLAB_BYTES) return cudaErrorInvalidValue;  // caller sizes ib
@@ -316,6 +332,11 @@ struct QrWork {
     void* ws;  // split-K scratch
     size_t ws_bytes;
     int nb, ib;
+    // second set for the look-ahead stream (trailing update of block b overlaps panel b+1)
+    T* Vw2;
+    T* W_b;
+    T* W2_b;
+    void* ws_b;
 };
 
 template <typename T>
@@ -326,7 +347,7 @@ static size_t splitk_ws_bytes(const makb200_handle* h) {
 template <typename T, typename AR>
 static void qr_carve(const makb200_handle* h, AR& ar, int m, int n, int ncols_q, QrWork<T>* w) {
     const int k = m < n ? m : n;
-    const int nb = QR_NB;
+    const int nb = qr_nb();
     const int ncmax = (n > ncols_q ? n : ncols_q);
     const int nblk = (k + nb - 1) / nb;
     w->Vw = ar.template get<T>((size_t)(m > 0 ? m : 1) * nb);
@@ -338,6 +359,10 @@ static void qr_carve(const makb200_handle* h, AR& ar, int m, int n, int ncols_q,
     w->ws_bytes = splitk_ws_bytes<T>(h);
     w->ws = ar.template get<char>(w->ws_bytes);
     w->nb = nb;
+    w->Vw2 = ar.template get<T>((size_t)(m > 0 ? m : 1) * nb);
+    w->W_b = ar.template get<T>((size_t)nb * (ncmax > 0 ? ncmax : 1));
+    w->W2_b = ar.template get<T>((size_t)nb * (ncmax > 0 ? ncmax : 1));
+    w->ws_b = ar.template get<char>(w->ws_bytes);
 }
 
 #define MAK_GEMM(h, ...)                                                \
@@ -366,22 +391,48 @@ static int apply_block_reflector(makb200_handle* h, bool trans, int mc, int nc, 
     return 0;
 }
 
-// geqrt-style blocked factorization: A -> (V\R), tau, T factors per outer block in w.Tall
+// geqrt-style blocked factorization: A -> (V\R), tau, T factors per outer block in w.Tall.
+// Look-ahead: the panel stage of block b+1 (latency-bound cluster kernels on <= 16 SMs) runs on the
+// caller's stream while the bulk of block b's trailing update (DMMA GEMMs) runs on the handle's
+// auxiliary stream; only the next panel's columns are updated in the panel stream's critical path.
+static bool qr_lookahead() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MAKB200_QR_LOOKAHEAD"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
 template <typename T>
 static int geqrf_blocked(makb200_handle* h, int m, int n, T* A, int lda, QrWork<T>& w) {
     const int k = m < n ? m : n;
     if (k == 0) return 0;
-    cudaStream_t s = h->stream;
+    // panel chain on the high-priority auxiliary stream, bulk updates on the caller's stream
+    cudaStream_t sMain = h->stream;
+    struct Restore { makb200_handle* h; cudaStream_t s; ~Restore() { h->stream = s; } } restore{h, sMain};
+    const bool la_on = qr_lookahead() && ((k + w.nb - 1) / w.nb) > 1;
+    cudaStream_t sP = la_on ? h->aux_stream : sMain, sG = sMain;
     const int nb = w.nb;
     const int ib_max = choose_ib<T>(h, m);
     const int nblk = (k + nb - 1) / nb;
-    MAK_CUDA(h, cudaMemsetAsync(w.Tall, 0, sizeof(T) * (size_t)nb * nb * nblk, s));
+    const bool la = la_on;
+    if (la) {  // fork: the auxiliary stream starts after everything already queued on the caller's
+        MAK_CUDA(h, cudaEventRecord(h->ev[0], sMain));
+        MAK_CUDA(h, cudaStreamWaitEvent(sP, h->ev[0], 0));
+    }
+    MAK_CUDA(h, cudaMemsetAsync(w.Tall, 0, sizeof(T) * (size_t)nb * nb * nblk, sP));
+    // panel-stream and update-stream views of the workspace
+    QrWork<T> wP = w, wG = w;
+    wG.W = w.W_b; wG.W2 = w.W2_b; wG.ws = w.ws_b;
+    int rc = 0;
     for (int b = 0; b < nblk; ++b) {
         const int j0 = b * nb;
         const int jb = (k - j0 < nb) ? (k - j0) : nb;
         const int mp = m - j0;
         T* Ap = A + (size_t)j0 * lda + j0;
         T* Tb = w.Tall + (size_t)b * nb * nb;
+        T* Vw = (la && (b & 1)) ? w.Vw2 : w.Vw;
+        cudaEvent_t evP = h->ev[1 + (b & 1)], evG = h->ev[3 + (b & 1)], evGprev = h->ev[3 + ((b + 1) & 1)];
+        h->stream = sP;
+        cudaStream_t s = sP;
         for (int i0 = 0; i0 < jb; i0 += ib_max) {
             const int ib = (jb - i0 < ib_max) ? (jb - i0) : ib_max;
             T* Ai = Ap + (size_t)i0 * lda + i0;
@@ -390,22 +441,22 @@ static int geqrf_blocked(makb200_handle* h, int m, int n, T* A, int lda, QrWork<
             if (e != cudaSuccess) return cuda_fail(h, e, "panel_kernel");
             // explicit V for this inner block into Vw[:, i0:i0+ib] (zeros above the diagonal)
             copy_v_kernel<T><<<grid_for((size_t)mp * ib, h->num_sms), 256, 0, s>>>(
-                mp, ib, i0, Ap + (size_t)i0 * lda, lda, w.Vw + (size_t)i0 * mp, mp);
+                mp, ib, i0, Ap + (size_t)i0 * lda, lda, Vw + (size_t)i0 * mp, mp);
             count_launch();
-    MAK_LAUNCH_CHECK(h, "copy_v_kernel");
-            const T* Vi = w.Vw + (size_t)i0 * mp + i0;
+            MAK_LAUNCH_CHECK(h, "copy_v_kernel");
+            const T* Vi = Vw + (size_t)i0 * mp + i0;
             // update the rest of the outer panel
             const int nci = jb - i0 - ib;
             if (nci > 0) {
-                int rc = apply_block_reflector<T>(h, true, mi, nci, ib, Vi, mp, Tb + (size_t)i0 * nb + i0, nb,
-                                                  Ai + (size_t)ib * lda, lda, w);
+                rc = apply_block_reflector<T>(h, true, mi, nci, ib, Vi, mp, Tb + (size_t)i0 * nb + i0, nb,
+                                              Ai + (size_t)ib * lda, lda, wP);
                 if (rc) return rc;
             }
             // couple into the outer T: T[0:i0, i0:i0+ib] = -T_a (V_a^H V_i) T_i
             if (i0 > 0) {
                 const T one_ = one<T>(), zero_ = zero<T>();
-                MAK_GEMM(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, i0, ib, mp, one_, w.Vw, mp,
-                         w.Vw + (size_t)i0 * mp, mp, zero_, w.G, nb, w.ws, w.ws_bytes);
+                MAK_GEMM(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, i0, ib, mp, one_, Vw, mp,
+                         Vw + (size_t)i0 * mp, mp, zero_, w.G, nb, wP.ws, wP.ws_bytes);
                 t_couple_kernel<T><<<ib, 128, sizeof(T) * i0, s>>>(i0, ib, Tb, nb, w.G, nb);
                 count_launch();
                 MAK_LAUNCH_CHECK(h, "t_couple_kernel");
@@ -413,10 +464,32 @@ static int geqrf_blocked(makb200_handle* h, int m, int n, T* A, int lda, QrWork<
         }
         // trailing update with the outer block reflector
         const int nc = n - j0 - jb;
-        if (nc > 0) {
-            int rc = apply_block_reflector<T>(h, true, mp, nc, jb, w.Vw, mp, Tb, nb, Ap + (size_t)jb * lda, lda, w);
+        if (nc <= 0) continue;
+        if (!la) {
+            rc = apply_block_reflector<T>(h, true, mp, nc, jb, Vw, mp, Tb, nb, Ap + (size_t)jb * lda, lda, wP);
             if (rc) return rc;
+            continue;
         }
+        MAK_CUDA(h, cudaEventRecord(evP, sP));
+        const int n1 = nc < nb ? nc : nb;  // the next panel's columns: critical path, panel stream
+        const int n2 = nc - n1;            // the rest: auxiliary stream, overlaps the next panel stage
+        if (n2 > 0) {
+            MAK_CUDA(h, cudaStreamWaitEvent(sG, evP, 0));
+            h->stream = sG;
+            rc = apply_block_reflector<T>(h, true, mp, n2, jb, Vw, mp, Tb, nb, Ap + (size_t)(jb + n1) * lda, lda, wG);
+            h->stream = sP;
+            if (rc) return rc;
+            MAK_CUDA(h, cudaEventRecord(evG, sG));
+        }
+        // the next panel's columns were last written by the previous block's bulk update
+        if (b > 0) MAK_CUDA(h, cudaStreamWaitEvent(sP, evGprev, 0));
+        rc = apply_block_reflector<T>(h, true, mp, n1, jb, Vw, mp, Tb, nb, Ap + (size_t)jb * lda, lda, wP);
+        if (rc) return rc;
+    }
+    h->stream = sMain;
+    if (la) {  // join: the caller's stream continues after the panel chain has drained
+        MAK_CUDA(h, cudaEventRecord(h->ev[5], sP));
+        MAK_CUDA(h, cudaStreamWaitEvent(sMain, h->ev[5], 0));
     }
     return 0;
 }

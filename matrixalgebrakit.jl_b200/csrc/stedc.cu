@@ -96,7 +96,7 @@ __global__ void dc_deflate_kernel(Ctx c, Merge* mgs, GemmProblem<double>* gp, co
     const int lo = mg.lo, mid = mg.mid, N1 = mg.mid - mg.lo, N2 = mg.hi - mg.mid, K = mg.K;
     const int k12 = mg.k1 + mg.k2, k23 = mg.k2 + mg.k3;
     GemmProblem<double> p;
-    p.alpha = 1.0; p.beta = 0.0; p.conja = 0; p.conjb = 0;
+    p.alpha = 1.0; p.beta = 0.0; p.conja = 0; p.conjb = 0; p.lower = 0;
     // top rows: Tmp[lo:mid, lo:lo+K] = Pack[lo:mid, lo:lo+k12] * S[lo:lo+k12, lo:lo+K]
     p.m = N1; p.n = K; p.k = k12;
     p.A = Pack + (size_t)lo * ldp + lo; p.lda = ldp;
