@@ -20,3 +20,5 @@ from .svd import (svd_compact, svd_compact_, svd_trunc, svd_trunc_, svd_trunc_no
 from . import eigh, polar, qr, svd, truncation  # noqa: E402,F401
 from .tsqr import tsqr_
 from .svd import svd_compact_batched_, svd_trunc_batched_
+from .qr import BatchedQRPlan
+from .svd import BatchedSVDPlan

@@ -40,8 +40,12 @@ int makb200_create(makb200_handle_t** out, int device) {
             return MAKB200_ERR_CUDA;
         }
     }
-    for (int i = 0; i < 8; ++i)
+    h->no_lookahead = false;
+    for (int i = 0; i < 8; ++i) {
         if (cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return MAKB200_ERR_CUDA; }
+        if (cudaEventCreateWithFlags(&h->pool_ev[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return MAKB200_ERR_CUDA; }
+        if (cudaStreamCreateWithFlags(&h->pool[i], cudaStreamNonBlocking) != cudaSuccess) { delete h; return MAKB200_ERR_CUDA; }
+    }
     int rc = mak::qr_init(h);
     if (rc == 0) rc = mak::batched_init(h);
     if (rc == 0) rc = mak::polar_init(h);
@@ -53,7 +57,7 @@ int makb200_create(makb200_handle_t** out, int device) {
 int makb200_destroy(makb200_handle_t* h) {
     if (!h) return -1;
     cudaStreamDestroy(h->aux_stream);
-    for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 8; ++i) { cudaEventDestroy(h->ev[i]); cudaEventDestroy(h->pool_ev[i]); cudaStreamDestroy(h->pool[i]); }
     delete h;
     return 0;
 }
@@ -71,6 +75,8 @@ unsigned long long makb200_launch_count(void) { return mak::g_launches; }
 int makb200_kernel_timing(int enable) {
     mak::g_clock_dots.on = enable != 0;
     mak::g_clock_gemm.on = enable != 0;
+    mak::g_clock_w.on = enable != 0;
+    mak::g_clock_w.n = 0;
     mak::g_clock_dots.n = 0;
     mak::g_clock_gemm.n = 0;
     mak::g_gemm_flops = 0.0;
@@ -83,6 +89,7 @@ int makb200_kernel_time(int which, double* ms, int* launches) {
     if (!ms || !launches) return -2;
     if (which == 0) mak::g_clock_dots.collect(ms, launches);
     else if (which == 1) mak::g_clock_gemm.collect(ms, launches);
+    else if (which == 2) mak::g_clock_w.collect(ms, launches);
     else return -1;
     return 0;
 }
@@ -192,6 +199,34 @@ int makb200_orgqr(makb200_handle_t* h, int dtype, int m, int ncols, int k, const
 }  // extern "C"
 
 // ---- batched -----------------------------------------------------------------------
+// Run `fn(slot_work, slot_lwork, i)` for every index in `big` round-robin over the handle's stream
+// pool (the per-block paths are launch-latency bound, so independent blocks overlap almost freely).
+constexpr int NPOOL = 8;
+template <typename F>
+static int run_pooled(makb200_handle_t* h, const std::vector<int>& big, char* work, size_t lwork, F fn) {
+    if (big.empty()) return 0;
+    cudaStream_t main = h->stream;
+    const int np = (int)big.size() < NPOOL ? (int)big.size() : NPOOL;
+    const size_t slice = (lwork / np) & ~(size_t)255;
+    MAK_CUDA(h, cudaEventRecord(h->pool_ev[0], main));
+    for (int s = 0; s < np; ++s) MAK_CUDA(h, cudaStreamWaitEvent(h->pool[s], h->pool_ev[0], 0));
+    h->no_lookahead = true;
+    int rc = 0;
+    for (size_t idx = 0; idx < big.size() && rc == 0; ++idx) {
+        const int s = (int)(idx % np);
+        h->stream = h->pool[s];
+        rc = fn(work + s * slice, slice, big[idx]);
+    }
+    h->stream = main;
+    h->no_lookahead = false;
+    if (rc) return rc;
+    for (int s = 0; s < np; ++s) {
+        MAK_CUDA(h, cudaEventRecord(h->pool_ev[s], h->pool[s]));
+        MAK_CUDA(h, cudaStreamWaitEvent(main, h->pool_ev[s], 0));
+    }
+    return 0;
+}
+
 template <typename T>
 static size_t qr_batched_worksize_t(makb200_handle_t* h, int batch, const int* m, const int* n) {
     size_t bytes = mak::align_up(sizeof(mak::QrBlockDesc<T>) * (size_t)(batch > 0 ? batch : 1), 256);
@@ -202,7 +237,7 @@ static size_t qr_batched_worksize_t(makb200_handle_t* h, int batch, const int* m
             if (w > big) big = w;
         }
     }
-    return bytes + big + 256;
+    return bytes + (big + 512) * NPOOL + 256;
 }
 
 template <typename T>
@@ -248,12 +283,10 @@ static int qr_batched_t(makb200_handle_t* h, int batch, const int* m, const int*
     // blocks too large for one CTA's shared memory take the blocked DMMA path
     char* wbig = (char*)work + ar.off;
     size_t lbig = lwork > ar.off ? lwork - ar.off : 0;
-    for (int i : big) {
-        int rc = mak::qr_fused_t<T>(h, MAKB200_QR_COMPACT, m[i], n[i], (T*)A[i], lda[i], (T*)Q[i], ldq[i],
-                                    (R && R[i]) ? (T*)R[i] : nullptr, ldr ? ldr[i] : 0, wbig, lbig);
-        if (rc) return rc;
-    }
-    return 0;
+    return run_pooled(h, big, wbig, lbig, [&](char* w, size_t lw, int i) {
+        return mak::qr_fused_t<T>(h, MAKB200_QR_COMPACT, m[i], n[i], (T*)A[i], lda[i], (T*)Q[i], ldq[i],
+                                  (R && R[i]) ? (T*)R[i] : nullptr, ldr ? ldr[i] : 0, w, lw);
+    });
 }
 
 extern "C" {
@@ -451,12 +484,10 @@ static int svd_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int
     // blocks too large for one CTA's shared memory: QDWH + D&C path, one block at a time
     char* wbig = (char*)work + ar.off;
     size_t lbig = lwork > ar.off ? lwork - ar.off : 0;
-    for (int i : big) {
-        int rc = mak::svd_t<T>(h, m[i], n[i], (T*)A[i], lda[i], (double*)S[i], U ? (T*)U[i] : nullptr, ldu ? ldu[i] : 0,
-                               Vh ? (T*)Vh[i] : nullptr, ldvh ? ldvh[i] : 0, fixgauge, 2.2e-16, wbig, lbig, nullptr);
-        if (rc) return rc;
-    }
-    return 0;
+    return run_pooled(h, big, wbig, lbig, [&](char* w, size_t lw, int i) {
+        return mak::svd_t<T>(h, m[i], n[i], (T*)A[i], lda[i], (double*)S[i], U ? (T*)U[i] : nullptr, ldu ? ldu[i] : 0,
+                             Vh ? (T*)Vh[i] : nullptr, ldvh ? ldvh[i] : 0, fixgauge, 2.2e-16, w, lw, nullptr);
+    });
 }
 
 extern "C" {
@@ -473,7 +504,7 @@ size_t makb200_svd_batched_worksize(makb200_handle_t* h, int dtype, int batch, c
             if (w > big) big = w;
         }
     }
-    return bytes + big + 256;
+    return bytes + (big + 512) * NPOOL + 256;
 }
 
 int makb200_svd_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch, const int* m, const int* n,

@@ -150,6 +150,9 @@ struct makb200_handle {
     int max_cluster;  // largest usable cluster size for the panel kernel
     cudaStream_t aux_stream;   // internal second stream (look-ahead in the blocked QR)
     cudaEvent_t ev[8];         // fork/join and look-ahead events
+    cudaStream_t pool[8];      // stream pool: mid-size blocks of a batch run concurrently
+    cudaEvent_t pool_ev[8];
+    bool no_lookahead;         // set while a pooled call is in flight (aux stream/events are shared)
     char err[256];
 };
 
@@ -211,6 +214,7 @@ struct KernelClock {
 };
 extern KernelClock g_clock_dots;  // trd_dots_kernel (dominant kernel of eigh_full!)
 extern KernelClock g_clock_gemm;  // DMMA GEMM launches
+extern KernelClock g_clock_w;     // trd_w_kernel
 
 // optional phase timing (env MAKB200_PROFILE=1): prints device time per phase to stderr.
 struct PhaseTimer {

@@ -9,6 +9,8 @@
 //   3. stedc (stedc.cu): tridiagonal divide and conquer, GEMM-rich merges
 //   4. back-transform V = Q Z with compact-WY block reflectors (DMMA GEMMs, qr.cu)
 //   5. eigenvector gauge (common/gauge.jl:38-45) fused into one launch
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include "eigh.cuh"
 #include "gemm.cuh"
 #include "qr.cuh"
@@ -375,6 +377,258 @@ trd_symv_kernel(TrdCtx<T> x, int c, int i, int npn, int nstrips) {
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// TMA-fed variant of the symmetric column kernel.  A dedicated producer warp streams the strip
+// through a 3-stage shared-memory ring with cp.async.bulk.tensor (2-D tiled tensor map over A,
+// 256 rows x CW columns = 32 KB per stage, zero register cost, ~190 KB of loads in flight per SM
+// with two resident CTAs); eight consumer warps do the two FMAs per element from shared memory.
+// mbarrier full/empty handshakes replace block barriers in the main loop.
+// ---------------------------------------------------------------------------------------
+constexpr int TMA_ROWS = 256;   // matrix rows per stage
+constexpr int TMA_NST = 3;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+            "r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(288, 2)
+trd_symv_tma_kernel(const __grid_constant__ CUtensorMap tmap, TrdCtx<T> x, int c, int i, int npn, int nstrips) {
+    constexpr int CW = SymvCW<T>::value;
+    constexpr int NBOX = sizeof(T) / 8;            // boxes (of 256 doubles x CW) per stage
+    constexpr int RB = TMA_ROWS / NBOX;            // matrix rows per box
+    constexpr unsigned STAGE_BYTES = TMA_ROWS * CW * sizeof(T);
+    const int SEG = x.seg;
+    const int sgi = blockIdx.y;
+    const int slot = sgi * gridDim.x + blockIdx.x;
+    __shared__ T s_vc[CW];
+    __shared__ T s_col[8][CW];
+    __shared__ double s_q[8];
+    __shared__ double s_sigma;
+    __shared__ __align__(8) uint64_t full_bar[TMA_NST], empty_bar[TMA_NST];
+    extern __shared__ __align__(128) unsigned char tma_smem_raw[];
+    unsigned char* tma_smem = tma_smem_raw + ((128u - (smem_u32(tma_smem_raw) & 127u)) & 127u);  // TMA dst alignment
+    const int n = x.n, row0 = c + 1, mt = n - row0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) {
+        double sg = 0.0;
+        for (int q = lane; q < npn; q += 32) sg += x.pn[q];
+        sg = warp_sum(sg);
+        if (lane == 0) s_sigma = sg;
+    }
+    if (tid == 32) {
+        for (int st = 0; st < TMA_NST; ++st) { mbar_init(&full_bar[st], 1); mbar_init(&empty_bar[st], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const double sigma = s_sigma;
+    const T* acol = x.A + (size_t)c * x.lda + row0;
+    const T alpha = acol[0];
+    double beta; T tau, scale;
+    larfgp_scalars<T>(alpha, sigma, beta, tau, scale);
+
+    if ((int)blockIdx.x >= nstrips) {
+        if (sgi > 0 || warp == 8) { if (tid == 0 && sgi > 0) x.pyv[slot] = zero<T>(); return; }
+        // ---- panel columns: t1 = W^H v, t2 = V^H v ----
+        const int q0 = (((int)blockIdx.x - nstrips) * 8 + warp) * 4;
+        const T* col[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int q = q0 + k;
+            if (q < i) col[k] = x.P + (size_t)(x.pw + q) * x.ldp + row0;
+            else if (q < 2 * i) col[k] = x.P + (size_t)(q - i) * x.ldp + row0;
+            else col[k] = nullptr;
+        }
+        T acc[4] = {zero<T>(), zero<T>(), zero<T>(), zero<T>()};
+        if (q0 < 2 * i) {
+            for (int r = lane; r < mt; r += 32) {
+                T vr = (r == 0) ? one<T>() : mul_(acol[r], scale);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (col[k]) fmac_(acc[k], col[k][r], vr);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            acc[k] = warp_sum(acc[k]);
+            int q = q0 + k;
+            if (lane == 0 && q < 2 * i) {
+                if (q < i) x.t[q] = acc[k];
+                else x.t[TRD_NB + (q - i)] = acc[k];
+            }
+        }
+        if (tid == 0) x.pyv[slot] = zero<T>();
+        return;
+    }
+
+    const int cb = blockIdx.x * CW;
+    const int cw = (mt - cb < CW) ? (mt - cb) : CW;
+    const int rs = cb + sgi * SEG;
+    if (rs >= mt) { if (tid == 0) x.pyv[slot] = zero<T>(); return; }
+    const int re = (rs + SEG < mt) ? (rs + SEG) : mt;
+    if (tid < CW) {
+        T vq = zero<T>();
+        if (tid < cw) {
+            int r = cb + tid;
+            vq = (r == 0) ? one<T>() : mul_(acol[r], scale);
+            if (sgi == 0) {
+                x.P[(size_t)i * x.ldp + row0 + r] = vq;
+                x.P[(size_t)(2 * x.pw + i) * x.ldp + row0 + r] = vq;
+            }
+        }
+        s_vc[tid] = vq;
+    }
+    __syncthreads();
+    // TMA needs a 16-byte aligned box start: for 8-byte elements an odd global row is reached by
+    // starting one row early and masking that row
+    const int shift = (NBOX == 1) ? ((row0 + rs) & 1) : 0;
+    const int ntile = (re - rs + shift + TMA_ROWS - 1) / TMA_ROWS;
+    T colacc[CW];
+#pragma unroll
+    for (int k = 0; k < CW; ++k) colacc[k] = zero<T>();
+    double qacc = 0.0;
+    if (warp == 8) {
+        // ---- producer: one lane streams the strip through the ring ----
+        if (lane == 0) {
+            for (int t = 0; t < ntile; ++t) {
+                const int st = t % TMA_NST, use = t / TMA_NST;
+                if (use > 0) mbar_wait(&empty_bar[st], (unsigned)((use - 1) & 1));
+                mbar_expect_tx(&full_bar[st], STAGE_BYTES);
+                unsigned char* dst = tma_smem + (size_t)st * STAGE_BYTES;
+                const int grow = (row0 + rs - shift + t * TMA_ROWS) * NBOX;   // row coordinate in doubles
+#pragma unroll
+                for (int bx = 0; bx < NBOX; ++bx)
+                    tma_load_2d(dst + (size_t)bx * (STAGE_BYTES / NBOX), &tmap, &full_bar[st], grow + bx * 256,
+                                row0 + cb);
+            }
+        }
+    } else {
+        // ---- consumers: warp w owns rows 32w..32w+31 of every tile ----
+        T* Yp = x.ypart + (size_t)blockIdx.x * x.ldy + row0;
+        for (int t = 0; t < ntile; ++t) {
+            const int st = t % TMA_NST, use = t / TMA_NST;
+            mbar_wait(&full_bar[st], (unsigned)(use & 1));
+            const T* tile = reinterpret_cast<const T*>(tma_smem + (size_t)st * STAGE_BYTES);
+            const int rr = 32 * warp + lane;                 // row inside the tile
+            const int rt = rs - shift + t * TMA_ROWS + 32 * warp;    // first row of this warp's slice
+            const int r = rt + lane;
+            // element (rr, k): box rr / RB, row rr % RB inside it
+            const T* src = tile + (size_t)(rr / RB) * (CW * RB) + (rr % RB);
+            if (r < re && r >= rs) {
+                const T vr = (r == 0) ? one<T>() : mul_(acol[r], scale);
+                T rowoff = zero<T>();
+                double ad = 0.0;
+                if (rt >= cb + CW && cw == CW) {
+#pragma unroll
+                    for (int k = 0; k < CW; ++k) {
+                        const T a = src[k * RB];
+                        fma_(rowoff, a, s_vc[k]);
+                        fmac_(colacc[k], a, vr);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < CW; ++k) {
+                        const int cc = cb + k;
+                        if (k < cw) {
+                            if (r > cc) {
+                                const T a = src[k * RB];
+                                fma_(rowoff, a, s_vc[k]);
+                                fmac_(colacc[k], a, vr);
+                            } else if (r == cc) {
+                                ad = real_(src[k * RB]);
+                            }
+                        }
+                    }
+                }
+                Yp[r] = add_(rowoff, scale_(vr, ad));
+                T cv = zero<T>();
+                fmac_(cv, vr, rowoff);
+                qacc += 2.0 * real_(cv) + ad * abs2_(vr);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[st]);
+        }
+#pragma unroll
+        for (int k = 0; k < CW; ++k) {
+            T v = warp_sum(colacc[k]);
+            if (lane == 0) s_col[warp][k] = v;
+        }
+        qacc = warp_sum(qacc);
+        if (lane == 0) s_q[warp] = qacc;
+    }
+    __syncthreads();
+    if (tid < cw) {
+        T v = zero<T>();
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v = add_(v, s_col[w][tid]);
+        x.y[((size_t)blockIdx.x * x.maxseg + sgi) * CW + tid] = v;
+    }
+    if (tid == 0) {
+        double q = 0.0;
+        for (int w = 0; w < 8; ++w) q += s_q[w];
+        x.pyv[slot] = mk<T>(q);
+        if (blockIdx.x == 0 && sgi == 0) {
+            x.tau[c] = tau;
+            x.e[c] = beta;
+            x.d[c] = real_(x.A[(size_t)c * x.lda + c]);
+        }
+    }
+}
+
+// host: 2-D tiled tensor map over A viewed as doubles (rows = n * sizeof(T)/8 contiguous, n columns)
+template <typename T>
+static bool make_symv_tmap(CUtensorMap* tm, const T* A, int n, int lda) {
+    static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            enc = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    }
+    // measured on B200 (round 1): the register-landing kernel is ~8 % faster than the TMA ring for this
+    // access pattern, so TMA is opt-in (MAKB200_SYMV_TMA=1)
+    const char* e = getenv("MAKB200_SYMV_TMA");
+    if (!(e && e[0] == '1')) return false;
+    if (!enc) return false;
+    if ((reinterpret_cast<uintptr_t>(A) & 15) != 0) return false;
+    if (((size_t)lda * sizeof(T)) % 16 != 0) return false;
+    constexpr int NBOX = sizeof(T) / 8;
+    cuuint64_t gdim[2] = {(cuuint64_t)n * NBOX, (cuuint64_t)n};
+    cuuint64_t gstr[1] = {(cuuint64_t)lda * sizeof(T)};
+    cuuint32_t box[2] = {256, (cuuint32_t)SymvCW<T>::value};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)A, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 // column part of y for global row r: sum over the row segments of the strip that owns column r
 template <typename T>
 __device__ __forceinline__ T trd_ycol(const TrdCtx<T>& x, int row0, int mt, int r) {
@@ -386,27 +640,36 @@ __device__ __forceinline__ T trd_ycol(const TrdCtx<T>& x, int row0, int mt, int 
     return s;
 }
 
+// 288 threads: warps 0..7 make ONE pass over the panel rows (V[r,p], W[r,p] feed both the w update
+// and the left-looking update of the next column) and sum the row parts of y; warp 8 computes the
+// step's scalars (y^H v, alpha2, first row of w) concurrently.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(288)
 trd_w_kernel(TrdCtx<T> x, int c, int i, int npyv, int do_next) {
     __shared__ T sm[4][TRD_K2_ROWS];
+    __shared__ T sm2[4][TRD_K2_ROWS];
     __shared__ T st[2 * TRD_NB];       // t1, t2
-    __shared__ T srow[2 * TRD_NB + 2]; // conj(W[c1,p]), conj(V[c1,p]) incl. the new column
+    __shared__ T srow[2 * TRD_NB + 2]; // conj(W[c1,p]), conj(V[c1,p])
     __shared__ T sscal[4];
     __shared__ double red[32];
-    const int n = x.n, row0 = c + 1;
-    const int tx = threadIdx.x % TRD_K2_ROWS, ty = threadIdx.x / TRD_K2_ROWS;
+    const int n = x.n, row0 = c + 1, c1 = c + 1;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const bool scalar_warp = (warp == 8);
+    const int tx = tid % TRD_K2_ROWS, ty = (tid / TRD_K2_ROWS) & 3;
     const int r = row0 + blockIdx.x * TRD_K2_ROWS + tx;
-    const bool live = r < n;
+    const bool live = !scalar_warp && r < n;
     const T tauc = x.tau[c];
-    for (int p = threadIdx.x; p < i; p += blockDim.x) {
+    for (int p = tid; p < i; p += blockDim.x) {
         st[p] = x.t[p];
         st[TRD_NB + p] = x.t[TRD_NB + p];
+        srow[p] = conj_(x.P[(size_t)(x.pw + p) * x.ldp + c1]);          // conj(W[c1,p])
+        srow[TRD_NB + 1 + p] = conj_(x.P[(size_t)p * x.ldp + c1]);      // conj(V[c1,p])
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
+    T part = zero<T>(), part2 = zero<T>();
+    if (scalar_warp) {
         // alpha2 = -(tau/2) * w^H v,  w^H v = conj(tau) * (y^H v - t1^H t2 - t2^H t1)
-        const int lane = threadIdx.x;
+        const int lane = tid & 31;
         T yhv = zero<T>();
         for (int q = lane; q < npyv; q += 32) yhv = add_(yhv, x.pyv[q]);
         T s12 = zero<T>();
@@ -431,62 +694,42 @@ trd_w_kernel(TrdCtx<T> x, int c, int i, int npyv, int do_next) {
             sscal[0] = alpha2;
             sscal[1] = wfirst;
         }
-    }
-    __syncthreads();
-    const T alpha2 = sscal[0], wfirst = sscal[1];
-    // ---- w[r] ----
-    T part = zero<T>();
-    if (live) {
+    } else if (live) {
         for (int p = ty; p < i; p += 4) {
-            fma_(part, x.P[(size_t)p * x.ldp + r], st[p]);
-            fma_(part, x.P[(size_t)(x.pw + p) * x.ldp + r], st[TRD_NB + p]);
+            const T vp = x.P[(size_t)p * x.ldp + r], wp = x.P[(size_t)(x.pw + p) * x.ldp + r];
+            fma_(part, vp, st[p]);
+            fma_(part, wp, st[TRD_NB + p]);
+            fma_(part2, vp, srow[p]);
+            fma_(part2, wp, srow[TRD_NB + 1 + p]);
         }
         // row parts of y from every strip at or left of this row (subtracted: w = tau (y - part))
         const int nsb = (r - row0) / SymvCW<T>::value + 1;
         for (int b = ty; b < nsb; b += 4) part = sub_(part, x.ypart[(size_t)b * x.ldy + r]);
     }
-    sm[ty][tx] = part;
+    if (!scalar_warp) { sm[ty][tx] = part; sm2[ty][tx] = part2; }
     __syncthreads();
-    T vr = zero<T>(), wr = zero<T>();
-    if (live) {
-        T s = add_(add_(sm[0][tx], sm[1][tx]), add_(sm[2][tx], sm[3][tx]));
-        vr = x.P[(size_t)i * x.ldp + r];
-        wr = add_(mul_(tauc, sub_(trd_ycol<T>(x, row0, n - row0, r), s)), mul_(alpha2, vr));
-        if (ty == 0) {
-            x.P[(size_t)(x.pw + i) * x.ldp + r] = wr;                              // W(:, i)
-            x.A[(size_t)c * x.lda + r] = (r == row0) ? mk<T>(x.e[c]) : vr;          // reflector storage
+    const T alpha2 = sscal[0], wfirst = sscal[1];
+    double nrm = 0.0;
+    if (live && ty == 0) {
+        const T s = add_(add_(sm[0][tx], sm[1][tx]), add_(sm[2][tx], sm[3][tx]));
+        const T vr = x.P[(size_t)i * x.ldp + r];
+        const T wr = add_(mul_(tauc, sub_(trd_ycol<T>(x, row0, n - row0, r), s)), mul_(alpha2, vr));
+        x.P[(size_t)(x.pw + i) * x.ldp + r] = wr;                              // W(:, i)
+        x.A[(size_t)c * x.lda + r] = (r == row0) ? mk<T>(x.e[c]) : vr;          // reflector storage
+        if (do_next) {
+            // left-looking update of column c1 = c+1: previous panel columns + the new one
+            T s2 = add_(add_(sm2[0][tx], sm2[1][tx]), add_(sm2[2][tx], sm2[3][tx]));
+            fma_(s2, vr, conj_(wfirst));   // V[r,i] conj(W[c1,i])
+            s2 = add_(s2, wr);             // W[r,i] conj(V[c1,i]), V[c1,i] = 1
+            T a = sub_(x.A[(size_t)c1 * x.lda + r], s2);
+            if (r == c1) a = mk<T>(real_(a));
+            x.A[(size_t)c1 * x.lda + r] = a;
+            if (r >= c1 + 2) nrm = abs2_(a);
         }
     }
     if (!do_next) return;
-    // ---- left-looking update of column c1 = c+1 and its tail norm ----
-    const int c1 = c + 1;
-    for (int p = threadIdx.x; p < i; p += blockDim.x) {
-        srow[p] = conj_(x.P[(size_t)(x.pw + p) * x.ldp + c1]);          // conj(W[c1,p])
-        srow[TRD_NB + 1 + p] = conj_(x.P[(size_t)p * x.ldp + c1]);      // conj(V[c1,p])
-    }
-    __syncthreads();
-    part = zero<T>();
-    if (live) {
-        for (int p = ty; p < i; p += 4) {
-            fma_(part, x.P[(size_t)p * x.ldp + r], srow[p]);
-            fma_(part, x.P[(size_t)(x.pw + p) * x.ldp + r], srow[TRD_NB + 1 + p]);
-        }
-    }
-    sm[ty][tx] = part;
-    __syncthreads();
-    double nrm = 0.0;
-    if (live && ty == 0) {
-        T s = add_(add_(sm[0][tx], sm[1][tx]), add_(sm[2][tx], sm[3][tx]));
-        // new column p = i: V[r,i] conj(W[c1,i]) + W[r,i] conj(V[c1,i]),  V[c1,i] = 1
-        fma_(s, vr, conj_(wfirst));
-        s = add_(s, wr);
-        T a = sub_(x.A[(size_t)c1 * x.lda + r], s);
-        if (r == c1) a = mk<T>(real_(a));
-        x.A[(size_t)c1 * x.lda + r] = a;
-        if (r >= c1 + 2) nrm = abs2_(a);
-    }
     double tot = block_sum<double>(nrm, red);
-    if (threadIdx.x == 0) x.pn[blockIdx.x] = tot;
+    if (tid == 0) x.pn[blockIdx.x] = tot;
 }
 
 template <typename T>
@@ -517,6 +760,15 @@ template <typename T>
 static int hetrd(makb200_handle* h, TrdCtx<T>& x) {
     const int n = x.n;
     cudaStream_t s = h->stream;
+    CUtensorMap tmap;
+    const bool use_tma = make_symv_tmap<T>(&tmap, x.A, n, x.lda);
+    constexpr size_t tma_smem_bytes = (size_t)TMA_NST * TMA_ROWS * SymvCW<T>::value * sizeof(T) + 128;
+    static bool tma_configured = false;
+    if (use_tma && !tma_configured) {
+        MAK_CUDA(h, cudaFuncSetAttribute(trd_symv_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)tma_smem_bytes));
+        tma_configured = true;
+    }
     if (n == 1) {
         trd_last_d_kernel<T><<<1, 1, 0, s>>>(x);
         return 0;
@@ -538,10 +790,13 @@ static int hetrd(makb200_handle* h, TrdCtx<T>& x) {
             const int gx = nstrips + (2 * i + 31) / 32, gy = (mt + x.seg - 1) / x.seg;
             const int g1 = gx * gy;  // pyv slots written by this launch
             g_clock_dots.begin(s);
-            trd_symv_kernel<T><<<dim3(gx, gy), 256, 0, s>>>(x, c, i, npn, nstrips);
+            if (use_tma) trd_symv_tma_kernel<T><<<dim3(gx, gy), 288, tma_smem_bytes, s>>>(tmap, x, c, i, npn, nstrips);
+            else trd_symv_kernel<T><<<dim3(gx, gy), 256, 0, s>>>(x, c, i, npn, nstrips);
             g_clock_dots.end(s);
             const int do_next = (i + 1 < ncols) ? 1 : 0;
-            trd_w_kernel<T><<<g2, 256, 0, s>>>(x, c, i, g1, do_next);
+            g_clock_w.begin(s);
+            trd_w_kernel<T><<<g2, 288, 0, s>>>(x, c, i, g1, do_next);
+            g_clock_w.end(s);
             count_launch(2);
             npn = g2;
         }

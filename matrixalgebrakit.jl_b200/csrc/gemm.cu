@@ -7,6 +7,7 @@ unsigned long long g_launches = 0;
 double g_gemm_flops = 0.0;  // real flops issued through gemm() since the last makb200_kernel_timing()
 KernelClock g_clock_dots;
 KernelClock g_clock_gemm;
+KernelClock g_clock_w;
 
 // ---------------------------------------------------------------------------------------
 // tile configuration

@@ -408,7 +408,7 @@ static int geqrf_blocked(makb200_handle* h, int m, int n, T* A, int lda, QrWork<
     // panel chain on the high-priority auxiliary stream, bulk updates on the caller's stream
     cudaStream_t sMain = h->stream;
     struct Restore { makb200_handle* h; cudaStream_t s; ~Restore() { h->stream = s; } } restore{h, sMain};
-    const bool la_on = qr_lookahead() && ((k + w.nb - 1) / w.nb) > 1;
+    const bool la_on = qr_lookahead() && !h->no_lookahead && ((k + w.nb - 1) / w.nb) > 1;
     cudaStream_t sP = la_on ? h->aux_stream : sMain, sG = sMain;
     const int nb = w.nb;
     const int ib_max = choose_ib<T>(h, m);

@@ -116,31 +116,41 @@ def qr_full(A, alg=None, **kw):
     return qr_full_(copy_input(A), None, alg, **kw)
 
 
+class BatchedQRPlan:
+    """Argument arrays of a batched ``qr_compact!`` built once (block sizes, leading dimensions and
+    device pointers are fixed for a block-sparse tensor across many calls); ``run()`` is a single
+    C-ABI call."""
+
+    def __init__(self, As, QRs=None):
+        self.As = As
+        self.h = _core.Handle.get(As[0].device)
+        self.dt = _core.dtype_code(As[0])
+        self.QRs = QRs if QRs is not None else [initialize_output("qr_compact", A) for A in As]
+        b = self.b = len(As)
+        IA, VP = C.c_int * b, C.c_void_p * b
+        for A, QR in zip(As, self.QRs):
+            check_input("qr_compact", A, QR)
+        self.m = IA(*[A.shape[0] for A in As])
+        self.n = IA(*[A.shape[1] for A in As])
+        self.lda = IA(*[_core.ld(A) for A in As])
+        self.ldq = IA(*[_core.ld(Q) for Q, _ in self.QRs])
+        self.ldr = IA(*[_core.ld(R) if R is not None and R.numel() else 0 for _, R in self.QRs])
+        self.Ap = VP(*[A.data_ptr() for A in As])
+        self.Qp = VP(*[Q.data_ptr() for Q, _ in self.QRs])
+        self.Rp = VP(*[(R.data_ptr() if R is not None and R.numel() else 0) for _, R in self.QRs])
+        self.lw = self.h.lib.makb200_qr_batched_worksize(self.h.h, self.dt, b, self.m, self.n)
+
+    def run(self):
+        h = _core.Handle.get(self.As[0].device)
+        work = h.workspace(self.lw)
+        rc = h.lib.makb200_qr_batched(h.h, self.dt, self.b, self.m, self.n, self.Ap, self.lda, self.Qp, self.ldq,
+                                      self.Rp, self.ldr, C.c_void_p(0), _core.ptr(work), work.numel())
+        h.check(rc, "makb200_qr_batched")
+        return self.QRs
+
+
 def qr_compact_batched_(As, QRs=None):
     """Batched ``qr_compact!`` over a list of blocks (new capability; per-block semantics)."""
     if len(As) == 0:
         return []
-    dev, dtype = As[0].device, As[0].dtype
-    h = _core.Handle.get(dev)
-    dt = _core.dtype_code(As[0])
-    if QRs is None:
-        QRs = [initialize_output("qr_compact", A) for A in As]
-    b = len(As)
-    IA = C.c_int * b
-    VP = C.c_void_p * b
-    for A, QR in zip(As, QRs):
-        check_input("qr_compact", A, QR)
-    m = IA(*[A.shape[0] for A in As])
-    n = IA(*[A.shape[1] for A in As])
-    lda = IA(*[_core.ld(A) for A in As])
-    ldq = IA(*[_core.ld(Q) for Q, _ in QRs])
-    ldr = IA(*[_core.ld(R) if R is not None and R.numel() else 0 for _, R in QRs])
-    Ap = VP(*[A.data_ptr() for A in As])
-    Qp = VP(*[Q.data_ptr() for Q, _ in QRs])
-    Rp = VP(*[(R.data_ptr() if R is not None and R.numel() else 0) for _, R in QRs])
-    lw = h.lib.makb200_qr_batched_worksize(h.h, dt, b, m, n)
-    work = h.workspace(lw)
-    rc = h.lib.makb200_qr_batched(h.h, dt, b, m, n, Ap, lda, Qp, ldq, Rp, ldr, C.c_void_p(0), _core.ptr(work),
-                                  work.numel())
-    h.check(rc, "makb200_qr_batched")
-    return QRs
+    return BatchedQRPlan(As, QRs).run()

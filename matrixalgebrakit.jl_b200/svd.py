@@ -143,33 +143,45 @@ def svd_trunc_no_error(A, alg=None, trunc=None, **kw):
     return svd_trunc_no_error_(_copy_input(A), None, alg, trunc, **kw)
 
 
+class BatchedSVDPlan:
+    """Argument arrays of a batched ``svd_compact!`` built once; ``run()`` is one C-ABI call."""
+
+    def __init__(self, As, USVhs=None, fixgauge=True):
+        self.As = As
+        self.h = _core.Handle.get(As[0].device)
+        self.dt = _core.dtype_code(As[0])
+        self.outs = USVhs if USVhs is not None else [initialize_output(A) for A in As]
+        for A, o in zip(As, self.outs):
+            check_input(A, o)
+        b = self.b = len(As)
+        self.fixgauge = int(bool(fixgauge))
+        IA, VP = C.c_int * b, C.c_void_p * b
+        self.m = IA(*[A.shape[0] for A in As])
+        self.n = IA(*[A.shape[1] for A in As])
+        self.lda = IA(*[_core.ld(A) for A in As])
+        self.ldu = IA(*[_core.ld(o[0]) for o in self.outs])
+        self.ldv = IA(*[_core.ld(o[2]) for o in self.outs])
+        self.Ap = VP(*[A.data_ptr() for A in As])
+        self.Sp = VP(*[o[1].data_ptr() for o in self.outs])
+        self.Up = VP(*[o[0].data_ptr() for o in self.outs])
+        self.Vp = VP(*[o[2].data_ptr() for o in self.outs])
+        self.lw = self.h.lib.makb200_svd_batched_worksize(self.h.h, self.dt, b, self.m, self.n)
+
+    def run(self):
+        h = _core.Handle.get(self.As[0].device)
+        work = h.workspace(self.lw)
+        rc = h.lib.makb200_svd_batched(h.h, self.dt, self.fixgauge, self.b, self.m, self.n, self.Ap, self.lda,
+                                       self.Sp, self.Up, self.ldu, self.Vp, self.ldv, C.c_void_p(0),
+                                       _core.ptr(work), work.numel())
+        h.check(rc, "makb200_svd_batched")
+        return self.outs
+
+
 def svd_compact_batched_(As, USVhs=None, fixgauge=True):
     """Batched ``svd_compact!`` over a list of blocks (new capability; per-block semantics)."""
     if len(As) == 0:
         return []
-    h = _core.Handle.get(As[0].device)
-    dt = _core.dtype_code(As[0])
-    if USVhs is None:
-        USVhs = [initialize_output(A) for A in As]
-    for A, o in zip(As, USVhs):
-        check_input(A, o)
-    b = len(As)
-    IA, VP = C.c_int * b, C.c_void_p * b
-    m = IA(*[A.shape[0] for A in As])
-    n = IA(*[A.shape[1] for A in As])
-    lda = IA(*[_core.ld(A) for A in As])
-    ldu = IA(*[_core.ld(o[0]) for o in USVhs])
-    ldv = IA(*[_core.ld(o[2]) for o in USVhs])
-    Ap = VP(*[A.data_ptr() for A in As])
-    Sp = VP(*[o[1].data_ptr() for o in USVhs])
-    Up = VP(*[o[0].data_ptr() for o in USVhs])
-    Vp = VP(*[o[2].data_ptr() for o in USVhs])
-    lw = h.lib.makb200_svd_batched_worksize(h.h, dt, b, m, n)
-    work = h.workspace(lw)
-    rc = h.lib.makb200_svd_batched(h.h, dt, int(bool(fixgauge)), b, m, n, Ap, lda, Sp, Up, ldu, Vp, ldv,
-                                   C.c_void_p(0), _core.ptr(work), work.numel())
-    h.check(rc, "makb200_svd_batched")
-    return USVhs
+    return BatchedSVDPlan(As, USVhs, fixgauge).run()
 
 
 def svd_trunc_batched_(As, trunc, USVhs=None):

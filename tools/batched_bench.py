@@ -42,11 +42,10 @@ def run(op, idx):
     blocks = [As0[i] for i in idx]
     As = [makb200.colmajor_empty(a.shape[0], a.shape[1], a.dtype, dev) for a in blocks]
     if op == "qr":
-        outs = [makb200.qr.initialize_output("qr_compact", a) for a in As]
-        fn = lambda: makb200.qr_compact_batched_(As, outs)
+        plan = makb200.BatchedQRPlan(As)     # argument arrays built once (sizes/pointers are fixed)
     else:
-        outs = [makb200.svd.initialize_output(a) for a in As]
-        fn = lambda: makb200.svd_compact_batched_(As, outs)
+        plan = makb200.BatchedSVDPlan(As)
+    fn = plan.run
     ts = []
     for it in range(3):
         for a, b in zip(As, blocks):

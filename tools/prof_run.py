@@ -23,4 +23,18 @@ elif op == "eigh":
         A.copy_(H)
         makb200.eigh_full_(A, (D, V))
 torch.cuda.synchronize()
+if os.environ.get("KTIME"):
+    import ctypes
+    lib = makb200._lib.load()
+    lib.makb200_kernel_timing(1)
+    if op == "eigh":
+        A.copy_(H); makb200.eigh_full_(A, (D, V))
+    else:
+        A.copy_(G); makb200.qr_compact_(A, (Q, R))
+    torch.cuda.synchronize()
+    for which, nm in ((0, "symv"), (1, "gemm"), (2, "w")):
+        ms, nl = ctypes.c_double(), ctypes.c_int()
+        lib.makb200_kernel_time(which, ctypes.byref(ms), ctypes.byref(nl))
+        print(f"[ktime] {nm}: {ms.value:.2f} ms over {nl.value} launches, gemm_flops={lib.makb200_gemm_flops():.3e}")
+    lib.makb200_kernel_timing(0)
 print("done")
