@@ -162,6 +162,12 @@ int makb200_svd_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch,
                         const int* ldu, void* const* Vh, const int* ldvh, int* info, void* work,
                         size_t lwork);
 
+/* -- adjoint: B (n x m) = A^H.  Used by the LQ family, which every GPU driver of the reference
+ * routes through QR of the adjoint (lq_via_qr!, implementations/lq.jl:130-131,303-327), and by
+ * svd_via_adjoint! (implementations/svd.jl:134-142). */
+int makb200_adjoint(makb200_handle_t* h, int dtype, int m, int n, const void* A, int lda, void* B,
+                    int ldb);
+
 #ifdef __cplusplus
 }
 #endif

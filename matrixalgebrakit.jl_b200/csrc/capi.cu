@@ -525,4 +525,20 @@ int makb200_svd_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch,
     return svd_batched_t<cplx>(h, fixgauge, batch, m, n, A, lda, S, U, ldu, Vh, ldvh, info, work, lwork);
 }
 
+
+// ---- adjoint (lq_via_qr!, svd_via_adjoint!) -----------------------------------------------
+int makb200_adjoint(makb200_handle_t* h, int dtype, int m, int n, const void* A, int lda, void* B, int ldb) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (m < 0) return -3;
+    if (n < 0) return -4;
+    if (lda < maxi(1, m)) return -6;
+    if (ldb < maxi(1, n)) return -8;
+    if (m == 0 || n == 0) return 0;
+    if (!A) return -5;
+    if (!B || B == A) return -7;
+    if (dtype == MAKB200_F64) return mak::adjoint_t<double>(h, m, n, (const double*)A, lda, (double*)B, ldb);
+    return mak::adjoint_t<cplx>(h, m, n, (const cplx*)A, lda, (cplx*)B, ldb);
+}
+
 }  // extern "C"

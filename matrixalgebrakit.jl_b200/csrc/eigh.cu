@@ -206,7 +206,7 @@ static int trd_seg() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("MAKB200_TRD_SEG");
-        v = e ? atoi(e) : 2048;
+        v = e ? atoi(e) : 1024;
         if (v < TRD_SEG_MIN) v = TRD_SEG_MIN;
         v = (v + 31) / 32 * 32;
     }
@@ -222,21 +222,16 @@ trd_symv_kernel(TrdCtx<T> x, int c, int i, int npn, int nstrips) {
     const int SEG = x.seg;
     const int sgi = blockIdx.y;
     const int slot = sgi * gridDim.x + blockIdx.x;
-    __shared__ T s_vc[CW];
+    __shared__ T s_vcw[8][CW];   // per-warp copy of v over the strip columns (no block barrier needed)
     __shared__ T s_col[8][CW];
     __shared__ double s_q[8];
     const int n = x.n, row0 = c + 1, mt = n - row0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // tail norm of the column: partials summed by warp 0 in a fixed order (identical in every CTA)
-    __shared__ double s_sigma;
-    if (warp == 0) {
-        double sg = 0.0;
-        for (int q = lane; q < npn; q += 32) sg += x.pn[q];
-        sg = warp_sum(sg);
-        if (lane == 0) s_sigma = sg;
-    }
-    __syncthreads();
-    const double sigma = s_sigma;
+    // tail norm of the column: every warp sums the partials itself in the same fixed order (identical
+    // result in every warp of every CTA, and no block barrier before the first load is issued)
+    double sigma = 0.0;
+    for (int q = lane; q < npn; q += 32) sigma += x.pn[q];
+    sigma = warp_sum(sigma);
     const T* acol = x.A + (size_t)c * x.lda + row0;
     const T alpha = acol[0];
     double beta; T tau, scale;
@@ -281,19 +276,20 @@ trd_symv_kernel(TrdCtx<T> x, int c, int i, int npn, int nstrips) {
     const int rs = cb + sgi * SEG;                         // this CTA's row segment of the strip
     if (rs >= mt) { if (tid == 0) x.pyv[slot] = zero<T>(); return; }
     const int re = (rs + SEG < mt) ? (rs + SEG) : mt;
-    if (tid < CW) {
+    T* s_vc = s_vcw[warp];
+    if (lane < CW) {
         T vq = zero<T>();
-        if (tid < cw) {
-            int r = cb + tid;
+        if (lane < cw) {
+            int r = cb + lane;
             vq = (r == 0) ? one<T>() : mul_(acol[r], scale);
-            if (sgi == 0) {
+            if (sgi == 0 && warp == 0) {
                 x.P[(size_t)i * x.ldp + row0 + r] = vq;                  // V(:, i)
                 x.P[(size_t)(2 * x.pw + i) * x.ldp + row0 + r] = vq;     // second copy
             }
         }
-        s_vc[tid] = vq;
+        s_vc[lane] = vq;
     }
-    __syncthreads();
+    __syncwarp();
     T colacc[CW];
 #pragma unroll
     for (int k = 0; k < CW; ++k) colacc[k] = zero<T>();

@@ -758,6 +758,18 @@ int cholqr2_t(makb200_handle* h, int m, int n, T* A, int lda, T* Q, int ldq, T* 
     return 0;
 }
 
+template <typename T>
+int adjoint_t(makb200_handle* h, int m, int n, const T* A, int lda, T* B, int ldb) {
+    if (m <= 0 || n <= 0) return 0;
+    dim3 g((m + 31) / 32, (n + 31) / 32);
+    adjoint_kernel<T><<<g, dim3(32, 8), 0, h->stream>>>(m, n, A, lda, B, ldb);
+    count_launch();
+    MAK_LAUNCH_CHECK(h, "adjoint_kernel");
+    return 0;
+}
+template int adjoint_t<double>(makb200_handle*, int, int, const double*, int, double*, int);
+template int adjoint_t<cplx>(makb200_handle*, int, int, const cplx*, int, cplx*, int);
+
 #define INSTP(T)                                                                                             \
     template size_t polar_worksize_t<T>(makb200_handle*, int, int);                                          \
     template int polar_qdwh_t<T>(makb200_handle*, int, int, T*, int, T*, int, T*, int, double, int, void*,   \

@@ -16,4 +16,6 @@ template <typename T> size_t cholqr2_worksize_t(makb200_handle* h, int m, int n)
 template <typename T>
 int cholqr2_t(makb200_handle* h, int m, int n, T* A, int lda, T* Q, int ldq, T* R, int ldr, void* work, size_t lwork,
               int* info_dev);
+// B (n x m) = A^H for A (m x n); tiled, coalesced on both sides
+template <typename T> int adjoint_t(makb200_handle* h, int m, int n, const T* A, int lda, T* B, int ldb);
 }  // namespace mak

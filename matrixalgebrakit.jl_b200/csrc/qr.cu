@@ -576,20 +576,42 @@ int geqrf_t(makb200_handle* h, int m, int n, T* A, int lda, T* tau, void* work, 
 }
 
 // rebuild the T factors of every outer block from V and tau (larft), for the L1 orgqr entry
+// T (jb x jb, upper) from G = V^H V and tau:  T^-1 = diag(1/tau) + striu(G)  =>  column j of T by
+// back substitution  x_j = tau_j,  x_i = -tau_i * sum_{p=i+1..j} G[i,p] x_p   (no division: tau_i = 0
+// gives a zero row, as larft does).  One thread per column, strictly-upper G packed in shared memory.
 template <typename T>
 __global__ void larft_diag_kernel(int jb, const T* __restrict__ tau, T* __restrict__ Tm, int ldt,
                                   const T* __restrict__ G, int ldg) {
-    // single CTA: T[j][j] = tau_j; T[0:j, j] = -tau_j * T[0:j,0:j] * G[0:j, j]   (G = V^H V)
-    for (int j = 0; j < jb; ++j) {
-        T tj = tau[j];
-        for (int i = threadIdx.x; i < j; i += blockDim.x) {
-            T s = zero<T>();
-            for (int p = i; p < j; ++p) fma_(s, Tm[(size_t)p * ldt + i], G[(size_t)j * ldg + p]);
-            Tm[(size_t)j * ldt + i] = neg_(mul_(tj, s));
-        }
-        if (threadIdx.x == 0) Tm[(size_t)j * ldt + j] = tj;
-        __syncthreads();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* Gs = reinterpret_cast<T*>(smem_raw);          // packed: (i,p), i<p  ->  p(p-1)/2 + i
+    T* ts = Gs + (size_t)jb * (jb - 1) / 2;          // tau
+    for (int idx = threadIdx.x; idx < jb * jb; idx += blockDim.x) {
+        int p = idx / jb, i = idx - p * jb;
+        if (i < p) Gs[(size_t)p * (p - 1) / 2 + i] = G[(size_t)p * ldg + i];
     }
+    for (int j = threadIdx.x; j < jb; j += blockDim.x) ts[j] = tau[j];
+    __syncthreads();
+    for (int j = threadIdx.x; j < jb; j += blockDim.x) {
+        T* col = Tm + (size_t)j * ldt;
+        col[j] = ts[j];
+        for (int i = j - 1; i >= 0; --i) {
+            T s = zero<T>();
+            for (int p = i + 1; p <= j; ++p) fma_(s, Gs[(size_t)p * (p - 1) / 2 + i], col[p]);
+            col[i] = neg_(mul_(ts[i], s));
+        }
+    }
+}
+template <typename T> static size_t larft_smem(int jb) { return sizeof(T) * ((size_t)jb * (jb - 1) / 2 + jb + 2); }
+template <typename T>
+static cudaError_t larft_launch(cudaStream_t s, int jb, const T* tau, T* Tm, int ldt, const T* G, int ldg) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(larft_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    larft_diag_kernel<T><<<1, 128, larft_smem<T>(jb), s>>>(jb, tau, Tm, ldt, G, ldg);
+    return cudaGetLastError();
 }
 
 template <typename T>
@@ -614,7 +636,7 @@ int orgqr_t(makb200_handle* h, int m, int ncols, int k, const T* A, int lda, con
     MAK_LAUNCH_CHECK(h, "copy_v_kernel");
             MAK_GEMM(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, jb, jb, mp, one<T>(), w.Vw, mp, w.Vw, mp, zero<T>(),
                      w.G, nb, w.ws, w.ws_bytes);
-            larft_diag_kernel<T><<<1, 128, 0, s>>>(jb, tau + j0, w.Tall + (size_t)b * nb * nb, nb, w.G, nb);
+            larft_diag_kernel<T><<<1, 128, larft_smem<T>(jb), s>>>(jb, tau + j0, w.Tall + (size_t)b * nb * nb, nb, w.G, nb);
             count_launch();
         MAK_LAUNCH_CHECK(h, "larft_diag_kernel");
         }
@@ -654,9 +676,11 @@ int ormqr_left_t(makb200_handle* h, int m, int k, const T* A, int lda, const T* 
         MAK_CUDA(h, cudaMemsetAsync(Tb, 0, sizeof(T) * (size_t)nb * nb, s));
         MAK_GEMM(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, jb, jb, mp, one<T>(), w.Vw, mp, w.Vw, mp, zero<T>(), w.G,
                  nb, w.ws, w.ws_bytes);
-        larft_diag_kernel<T><<<1, 128, 0, s>>>(jb, tau + j0, Tb, nb, w.G, nb);
+        {
+            cudaError_t e = larft_launch<T>(s, jb, tau + j0, Tb, nb, w.G, nb);
+            if (e != cudaSuccess) return cuda_fail(h, e, "larft_diag_kernel");
+        }
         count_launch();
-        MAK_LAUNCH_CHECK(h, "larft_diag_kernel");
         int rc = apply_block_reflector<T>(h, false, mp, nc, jb, w.Vw, mp, Tb, nb, C + j0, ldc, w);
         if (rc) return rc;
     }

@@ -52,20 +52,93 @@ __global__ void dc_tear_kernel(int ncut, const int* __restrict__ cuts, double* D
     D[c] -= a;
 }
 
-// one thread per leaf (serial implicit QL on <= 32 x 32)
-__global__ void dc_leaf_kernel(int nleaf, const int* __restrict__ bnd, double* D, const double* __restrict__ E,
-                               double* Z, int ldz, int* info) {
-    int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+// one WARP per leaf: lane 0 runs the implicit-QL scalar recurrence (same arithmetic as
+// dc::leaf_ql in stedc_core.h) on d/e held in shared memory and broadcasts each plane rotation;
+// lane r applies it to row r of the leaf's eigenvector block, also held in shared memory.
+constexpr int LEAF_WARPS = 4;
+__global__ void __launch_bounds__(LEAF_WARPS * 32)
+dc_leaf_kernel(int nleaf, const int* __restrict__ bnd, double* D, const double* __restrict__ E, double* Z, int ldz,
+               int* info) {
+    __shared__ double sZ[LEAF_WARPS][DC_LEAF][DC_LEAF + 1];
+    __shared__ double sd[LEAF_WARPS][DC_LEAF + 1], se[LEAF_WARPS][DC_LEAF + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int leaf = blockIdx.x * LEAF_WARPS + warp;
     if (leaf >= nleaf) return;
-    int lo = bnd[leaf], sz = bnd[leaf + 1] - lo;
-    double dd[DC_LEAF + 1], ee[DC_LEAF + 1];
-    for (int k = 0; k < sz; ++k) { dd[k] = D[lo + k]; ee[k] = (k + 1 < sz) ? E[lo + k] : 0.0; }
-    double* Zb = Z + (size_t)lo * ldz + lo;
-    for (int c = 0; c < sz; ++c)
-        for (int r = 0; r < sz; ++r) Zb[(size_t)c * ldz + r] = (r == c) ? 1.0 : 0.0;
-    int rc = leaf_ql(sz, dd, ee, Zb, ldz);
-    if (rc) atomicExch(info, 1);
-    for (int k = 0; k < sz; ++k) D[lo + k] = dd[k];
+    const int lo = bnd[leaf], n = bnd[leaf + 1] - lo;
+    double* d = sd[warp];
+    double* e = se[warp];
+    double (*z)[DC_LEAF + 1] = sZ[warp];
+    if (lane < n) { d[lane] = D[lo + lane]; e[lane] = (lane + 1 < n) ? E[lo + lane] : 0.0; }
+    for (int c = 0; c < n; ++c) z[lane][c] = (lane == c) ? 1.0 : 0.0;   // z[row][col]
+    __syncwarp();
+    int fail = 0;
+    for (int l = 0; l < n && !fail; ++l) {
+        int iter = 0;
+        while (true) {
+            // lane 0 decides; everybody follows
+            int m = l;
+            if (lane == 0) {
+                for (m = l; m < n - 1; ++m) {
+                    double dd = fabs(d[m]) + fabs(d[m + 1]);
+                    if (fabs(e[m]) <= DC_EPS * dd) break;
+                }
+            }
+            m = __shfl_sync(0xffffffffu, m, 0);
+            if (m == l) break;
+            if (iter++ == 60) { fail = 1; break; }
+            double g = 0.0, r = 0.0, s = 1.0, c = 1.0, p = 0.0;
+            if (lane == 0) {
+                g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                r = hypot(g, 1.0);
+                g = d[m] - d[l] + e[l] / (g + copysign(r, g));
+            }
+            int i, brk = 0;
+            for (i = m - 1; i >= l; --i) {
+                if (lane == 0) {
+                    double f = s * e[i], b = c * e[i];
+                    r = hypot(f, g);
+                    e[i + 1] = r;
+                    if (r == 0.0) {
+                        d[i + 1] -= p;
+                        e[m] = 0.0;
+                        brk = 1;
+                    } else {
+                        s = f / r;
+                        c = g / r;
+                        g = d[i + 1] - p;
+                        r = (d[i] - g) * s + 2.0 * c * b;
+                        p = s * r;
+                        d[i + 1] = g + p;
+                        g = c * r - b;
+                    }
+                }
+                brk = __shfl_sync(0xffffffffu, brk, 0);
+                if (brk) break;
+                const double sb = __shfl_sync(0xffffffffu, s, 0), cb = __shfl_sync(0xffffffffu, c, 0);
+                if (lane < n) {
+                    const double f2 = z[lane][i + 1];
+                    z[lane][i + 1] = sb * z[lane][i] + cb * f2;
+                    z[lane][i] = cb * z[lane][i] - sb * f2;
+                }
+            }
+            if (brk) continue;
+            if (lane == 0) { d[l] -= p; e[l] = g; e[m] = 0.0; }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    if (fail && lane == 0) atomicExch(info, 1);
+    // ascending order: rank by counting (stable), then write columns in sorted order
+    int rank = 0;
+    double mine = (lane < n) ? d[lane] : 0.0;
+    for (int j = 0; j < n; ++j) rank += (lane < n) && ((d[j] < mine) || (d[j] == mine && j < lane));
+    __syncwarp();
+    if (lane < n) D[lo + rank] = mine;
+    // column `lane` of z goes to column `rank`; lanes write their column (rows contiguous in global)
+    if (lane < n) {
+        double* dst = Z + (size_t)(lo + rank) * ldz + lo;
+        for (int r = 0; r < n; ++r) dst[r] = z[r][lane];
+    }
 }
 
 __global__ void dc_merge_init_kernel(int nm, Merge* mg, const double* __restrict__ rho_cut,
@@ -291,7 +364,10 @@ int stedc(makb200_handle* h, int n, const double* d, const double* e, double* w,
     int ldi = (L % 2 == 0) ? ldz : ldw;
     double* Zout = (L % 2 == 0) ? Zw : Z;
     int ldo = (L % 2 == 0) ? ldw : ldz;
-    dc_leaf_kernel<<<(nleaf + 31) / 32, 32, 0, st>>>(nleaf, bnd_dev, b.ctx.D, b.E, Zin, ldi, b.info);
+    PhaseTimer pt(st);
+    pt.mark("start");
+    dc_leaf_kernel<<<(nleaf + LEAF_WARPS - 1) / LEAF_WARPS, LEAF_WARPS * 32, 0, st>>>(nleaf, bnd_dev, b.ctx.D, b.E, Zin, ldi, b.info);
+    pt.mark("leaf");
     count_launch(4);  // scale, tear, leaf, finish
     MAK_LAUNCH_CHECK(h, "dc_leaf_kernel");
 
@@ -334,7 +410,9 @@ int stedc(makb200_handle* h, int n, const double* d, const double* e, double* w,
         std::swap(Zin, Zout);
         std::swap(ldi, ldo);
         std::swap(b.ctx.D, b.ctx.Dn);
+        pt.mark("level");
     }
+    pt.report("stedc");
     // after the swaps Zin is the caller's Z
     dc_finish_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, b.ctx.D, b.scale, w);
     MAK_LAUNCH_CHECK(h, "dc_finish_kernel");
