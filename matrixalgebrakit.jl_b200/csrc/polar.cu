@@ -13,6 +13,7 @@
 #include "gemm.cuh"
 #include "qr.cuh"
 #include <vector>
+#include <cmath>
 
 namespace mak {
 
@@ -114,6 +115,76 @@ __global__ void copy2d_kernel(int m, int n, const T* __restrict__ S, int lds, T*
          idx += (size_t)gridDim.x * blockDim.x) {
         int r = (int)(idx % m), c = (int)(idx / m);
         D[(size_t)c * ldd + r] = S[(size_t)c * lds + r];
+    }
+}
+
+// X *= factor / sqrt(val[0])   (val on the device: no host round trip)
+template <typename T>
+__global__ void scale_by_dev_kernel(int m, int n, T* __restrict__ X, int ldx, const double* __restrict__ val,
+                                    double factor) {
+    const double v = val[0];
+    const double f = (v > 0.0 && isfinite(v)) ? factor / sqrt(v) : 1.0;
+    size_t total = (size_t)m * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(idx % m), c = (int)(idx / m);
+        T* p = X + (size_t)c * ldx + r;
+        *p = scale_(*p, f);
+    }
+}
+
+__global__ void sqrt_dev_kernel(double* v) { v[0] = sqrt(v[0]); }
+
+// deterministic +-1 entries (Hutchinson probes / power-iteration start): hash of the index
+template <typename T>
+__global__ void rademacher_kernel(int m, int n, T* __restrict__ G, int ldg, unsigned seed) {
+    size_t total = (size_t)m * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        unsigned hsh = (unsigned)idx * 2654435761u + seed;
+        hsh ^= hsh >> 16; hsh *= 0x85ebca6bu; hsh ^= hsh >> 13; hsh *= 0xc2b2ae35u; hsh ^= hsh >> 16;
+        int r = (int)(idx % m), c = (int)(idx / m);
+        G[(size_t)c * ldg + r] = mk<T>((hsh & 1u) ? 1.0 : -1.0);
+    }
+}
+
+// y[c] = sum_r conj(Z[r,c]) v[r]  (= (Z v)[c] for Hermitian Z): one warp per column, coalesced
+template <typename T>
+__global__ void herm_matvec_kernel(int n, const T* __restrict__ Z, int ldz, const T* __restrict__ v, T* __restrict__ y) {
+    const int lane = threadIdx.x & 31, c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    const T* col = Z + (size_t)c * ldz;
+    T s = zero<T>();
+    for (int r = lane; r < n; r += 32) fmac_(s, col[r], v[r]);
+    s = warp_sum(s);
+    if (lane == 0) y[c] = s;
+}
+
+// Z *= factor / val[0]  (all n x n entries)
+template <typename T>
+__global__ void scale_by_dev_lin_kernel(int n, T* __restrict__ Z, int ldz, const double* __restrict__ val, double factor) {
+    const double v = val[0];
+    const double f = (v > 0.0 && isfinite(v)) ? factor / v : 1.0;
+    size_t total = (size_t)n * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(idx % n), c = (int)(idx / n);
+        T* p = Z + (size_t)c * ldz + r;
+        *p = scale_(*p, f);
+    }
+}
+
+// Z (lower part) = I + c * Z0   (reuses the Gram matrix X^H X computed for the estimate)
+template <typename T>
+__global__ void eye_plus_scaled_kernel(int n, T* __restrict__ Z, int ldz, const T* __restrict__ Z0, int ld0, double c) {
+    size_t total = (size_t)n * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(idx % n), cc = (int)(idx / n);
+        if (r < cc) continue;
+        T v = scale_(Z0[(size_t)cc * ld0 + r], c);
+        if (r == cc) v = add_(v, one<T>());
+        Z[(size_t)cc * ldz + r] = v;
     }
 }
 
@@ -397,12 +468,27 @@ size_t polar_worksize_t(makb200_handle* h, int m, int n) {
 
 // polar factor of a (ms x n, ms >= n) matrix held in w.X (already scaled so that ||X||_2 <= 1)
 template <typename T>
-static int qdwh_iterate(makb200_handle* h, int ms, int n, PolarWork<T>& w, double l0, int maxiter, int* iters_out) {
+static int qdwh_iterate(makb200_handle* h, int ms, int n, PolarWork<T>& w, double l0, int maxiter, int* iters_out,
+                        const T* Z0 = nullptr) {
     cudaStream_t s = h->stream;
     std::vector<QdwhStep> sched = qdwh_schedule(l0, maxiter);
     if (iters_out) *iters_out = (int)sched.size();
     PhaseTimer pt(s);
     pt.mark("start");
+    bool first = true;
+    auto gram = [&](double c) -> int {
+        // Z (lower) = I + c X^H X; the first step reuses the Gram matrix of the estimate
+        if (first && Z0) {
+            eye_plus_scaled_kernel<T><<<grid_for2((size_t)n * n, h->num_sms), 256, 0, s>>>(n, w.Z, n, Z0, n, c);
+            count_launch();
+            return 0;
+        }
+        eye_kernel<T><<<grid_for2((size_t)n * n, h->num_sms), 256, 0, s>>>(n, w.Z, n);
+        count_launch();
+        MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, n, n, ms, mk<T>(c), w.X, ms, w.X, ms, one<T>(), w.Z, n,
+                  nullptr, 0, true);
+        return 0;
+    };
     for (const QdwhStep& st : sched) {
         if (st.qr) {
             const int mb = ms + n;
@@ -414,11 +500,9 @@ static int qdwh_iterate(makb200_handle* h, int ms, int n, PolarWork<T>& w, doubl
                 // cond([sqrt(c)X; I]) <= sqrt(1+c) <= 1e6: the orthonormal basis can be formed by
                 // CholeskyQR2 (all DMMA GEMMs) instead of Householder QR.
                 // pass 1: Z = B^H B = c X^H X + I (lower), L1, Q' = B L1^-H
-                eye_kernel<T><<<grid_for2((size_t)n * n, h->num_sms), 256, 0, s>>>(n, w.Z, n);
-                count_launch();
-                MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, n, n, ms, mk<T>(st.c), w.X, ms, w.X, ms,
-                          one<T>(), w.Z, n, nullptr, 0, true);
-                int rc = potrf_blocked<T>(h, n, w.Z, n, w.L, n, w.Linv, w.info, w.ws, w.ws_bytes);
+                int rc = gram(st.c);
+                if (rc) return rc;
+                rc = potrf_blocked<T>(h, n, w.Z, n, w.L, n, w.Linv, w.info, w.ws, w.ws_bytes);
                 if (rc) return rc;
                 rc = trsm_right<T>(h, true, mb, n, w.B, mb, w.L, n, w.Linv, w.Q, mb, w.Tmp, w.ws, w.ws_bytes);
                 if (rc) return rc;
@@ -441,13 +525,11 @@ static int qdwh_iterate(makb200_handle* h, int ms, int n, PolarWork<T>& w, doubl
                       mk<T>(be), w.X, ms, nullptr, 0);
             pt.mark(st.c <= QDWH_CHOLQR_MAX_C ? "cholqrstep" : "qrstep");
         } else {
-            eye_kernel<T><<<grid_for2((size_t)n * n, h->num_sms), 256, 0, s>>>(n, w.Z, n);
-            count_launch();
-            // Z is Hermitian and only its lower triangle is read by potrf: skip the tiles above it
-            MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, n, n, ms, mk<T>(st.c), w.X, ms, w.X, ms, one<T>(),
-                      w.Z, n, nullptr, 0, true);
+            // Z is Hermitian and only its lower triangle is read by potrf: tiles above it are skipped
+            int rc = gram(st.c);
+            if (rc) return rc;
             pt.mark("gram");
-            int rc = potrf_blocked<T>(h, n, w.Z, n, w.L, n, w.Linv, w.info, w.ws, w.ws_bytes);
+            rc = potrf_blocked<T>(h, n, w.Z, n, w.L, n, w.Linv, w.info, w.ws, w.ws_bytes);
             if (rc) return rc;
             pt.mark("potrf");
             rc = trsm_right<T>(h, true, ms, n, w.X, ms, w.L, n, w.Linv, w.Y, ms, w.Tmp, w.ws, w.ws_bytes);
@@ -460,6 +542,7 @@ static int qdwh_iterate(makb200_handle* h, int ms, int n, PolarWork<T>& w, doubl
             count_launch();
             MAK_LAUNCH_CHECK(h, "axpby_kernel");
         }
+        first = false;
     }
     pt.report("qdwh steps");
     return 0;
@@ -493,7 +576,72 @@ int polar_qdwh_t(makb200_handle* h, int m, int n, T* A, int lda, T* W, int ldw, 
     count_launch(3);
     MAK_LAUNCH_CHECK(h, "scale_copy_kernel");
     pt.mark("prep");
-    int rc = qdwh_iterate<T>(h, ms, n, w, l0, maxiter, iters_host);
+    // ---- scaling and conditioning estimates (large matrices, default l0 only) -------------------
+    //  sigma_max: 8 power iterations on X^H X through skinny GEMMs -> X /= 1.1 sigma_max (on device)
+    //  sigma_min: Z0 = X^H X = L L^H, tr(Z0^-1) = ||L^-1||_F^2 by Hutchinson (8 probes)
+    //             => sigma_min >= 1/sqrt(tr); l0 = 0.3/sqrt(tr_est).  One device->host read.
+    //  Falls back to l0 = eps (valid for any kappa <= 1e16) if the Cholesky of Z0 breaks down.
+    const T* Z0 = nullptr;
+    static const bool est_on = []() { const char* e = getenv("MAKB200_QDWH_ESTIMATE"); return !(e && e[0] == '0'); }();
+    if (est_on && l0 <= 2.3e-16 && n >= 1024) {
+        const T one_ = one<T>(), zero_ = zero<T>();
+        // Z0 = X^H X (full Hermitian: the power iteration needs both triangles) in Y2's storage
+        T* Z0w = w.Y2;
+        MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, n, n, ms, one_, w.X, ms, w.X, ms, zero_, Z0w, n, nullptr, 0);
+        pt.mark("est_gram");
+        T* v = w.Tmp;                 // n
+        T* y = w.Tmp + n;             // n
+        rademacher_kernel<T><<<grid_for2((size_t)n, h->num_sms), 256, 0, s>>>(n, 1, v, n, 12345u);
+        count_launch();
+        const int mvgrid = (n + 7) / 8;
+        for (int it = 0; it < 10; ++it) {
+            // y = Z0 v ; lambda ~ ||y|| for unit v ; v = y / ||y||
+            herm_matvec_kernel<T><<<mvgrid, 256, 0, s>>>(n, Z0w, n, v, y);
+            fro2_partial_kernel<T><<<32, 256, 0, s>>>(n, 1, y, n, w.partial);
+            fro2_final_kernel<<<1, 256, 0, s>>>(32, w.partial, w.scal + 1);
+            scale_copy_kernel<T><<<grid_for2((size_t)n, h->num_sms), 256, 0, s>>>(n, 1, y, n, v, n, w.scal + 1);
+            count_launch(4);
+        }
+        // after the loop scal[1] = ||Z0 v||^2 for the last unit v, i.e. (lambda_max estimate)^2:
+        // sigma_max^2 ~ sqrt(scal[1]).  X /= 1.1 sigma_max  and  Z0 /= 1.21 sigma_max^2
+        fro2_final_kernel<<<1, 256, 0, s>>>(32, w.partial, w.scal + 1);
+        sqrt_dev_kernel<<<1, 1, 0, s>>>(w.scal + 1);   // scal[1] <- lambda_max estimate = sigma_max^2
+        scale_by_dev_kernel<T><<<grid_for2((size_t)ms * n, h->num_sms), 256, 0, s>>>(ms, n, w.X, ms, w.scal + 1, 1.0 / 1.1);
+        scale_by_dev_lin_kernel<T><<<grid_for2((size_t)n * n, h->num_sms), 256, 0, s>>>(n, Z0w, n, w.scal + 1, 1.0 / 1.21);
+        count_launch(4);
+        pt.mark("est_power");
+        copy2d_kernel<T><<<grid_for2((size_t)n * n, h->num_sms), 256, 0, s>>>(n, n, Z0w, n, w.Z, n);
+        count_launch();
+        int rc0 = potrf_blocked<T>(h, n, w.Z, n, w.L, n, w.Linv, w.info + 1, w.ws, w.ws_bytes);
+        if (rc0) return rc0;
+        pt.mark("est_potrf");
+        constexpr int NPROBE = 8;
+        T* Gp = w.Y;                               // NPROBE x n probes, then NPROBE x n solution
+        T* Yp = w.Y + (size_t)NPROBE * n;
+        rademacher_kernel<T><<<grid_for2((size_t)NPROBE * n, h->num_sms), 256, 0, s>>>(NPROBE, n, Gp, NPROBE, 777u);
+        count_launch();
+        rc0 = trsm_right<T>(h, true, NPROBE, n, Gp, NPROBE, w.L, n, w.Linv, Yp, NPROBE, w.Tmp, nullptr, 0);
+        if (rc0) return rc0;
+        fro2_partial_kernel<T><<<64, 256, 0, s>>>(NPROBE, n, Yp, NPROBE, w.partial);
+        fro2_final_kernel<<<1, 256, 0, s>>>(64, w.partial, w.scal + 2);
+        count_launch(2);
+        double hs[4];
+        int hinfo[2];
+        MAK_CUDA(h, cudaMemcpyAsync(hs, w.scal, sizeof(double) * 3, cudaMemcpyDeviceToHost, s));
+        MAK_CUDA(h, cudaMemcpyAsync(hinfo, w.info, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+        MAK_CUDA(h, cudaStreamSynchronize(s));
+        const double tr = hs[2] / NPROBE;
+        if (hinfo[1] == 0 && tr > 0.0 && std::isfinite(tr)) {
+            double est = 0.3 / sqrt(tr);
+            if (est > 1e-7) {   // kappa small enough for the Gram-based estimate to be meaningful
+                l0 = est < 0.9 ? est : 0.9;
+                Z0 = Z0w;
+            }
+        }
+        pt.mark("est_probe");
+        if (pt.on) fprintf(stderr, "[makb200 profile] qdwh estimate: sigma_max^2(X0)=%.3e tr=%.3e l0=%.3e info=%d\n", hs[1], tr, l0, hinfo[1]);
+    }
+    int rc = qdwh_iterate<T>(h, ms, n, w, l0, maxiter, iters_host, Z0);
     if (rc) return rc;
     pt.mark("qdwh");
     // W, P
