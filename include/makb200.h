@@ -162,6 +162,18 @@ int makb200_svd_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch,
                         const int* ldu, void* const* Vh, const int* ldvh, int* info, void* work,
                         size_t lwork);
 
+/* -- batched eigh_full! / eigh_vals! of many small Hermitian blocks ---------------------------
+ * New capability (reference: commented-out heevjBatched stubs, yacusolver.jl:571-649; per-block
+ * semantics = eigh_full!(A_i,(D_i,V_i)) incl. the eigh gauge, implementations/eigh.jl:123-156).
+ * One CTA per block, two-sided Jacobi in shared memory (uplo='U' is read, A is NOT destroyed);
+ * blocks that do not fit are routed through makb200_eigh (those ARE destroyed).
+ * n,lda,ldv: HOST int arrays; A,W,V: HOST arrays of DEVICE pointers (V == NULL: values only, then
+ * every block must fit the shared-memory kernel).  info: DEVICE int[batch] or NULL. */
+size_t makb200_eigh_batched_worksize(makb200_handle_t* h, int dtype, int batch, const int* n);
+int makb200_eigh_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch, const int* n,
+                         void* const* A, const int* lda, void* const* W, void* const* V,
+                         const int* ldv, int* info, void* work, size_t lwork);
+
 /* -- adjoint: B (n x m) = A^H.  Used by the LQ family, which every GPU driver of the reference
  * routes through QR of the adjoint (lq_via_qr!, implementations/lq.jl:130-131,303-327), and by
  * svd_via_adjoint! (implementations/svd.jl:134-142). */

@@ -22,5 +22,6 @@ from .tsqr import tsqr_
 from .svd import svd_compact_batched_, svd_trunc_batched_
 from .qr import BatchedQRPlan
 from .svd import BatchedSVDPlan
+from .eigh import BatchedEighPlan, eigh_full_batched_
 from .orthnull import (adjoint_, left_null, left_null_, left_orth, left_orth_, lq_compact, lq_compact_, lq_full, lq_full_,
                        lq_null, lq_null_, qr_null, qr_null_, right_null, right_null_, right_orth, right_orth_)

@@ -381,6 +381,230 @@ int batched_svd_smem(makb200_handle* h, int batch, size_t max_smem_bytes, const 
 template int batched_svd_smem<double>(makb200_handle*, int, size_t, const SvdBlockDesc<double>*, int*);
 template int batched_svd_smem<cplx>(makb200_handle*, int, size_t, const SvdBlockDesc<cplx>*, int*);
 
+// ---------------------------------------------------------------------------------------
+// batched eigh_full!: one CTA per block, two-sided (classical) Jacobi with the same round-robin
+// parallel ordering; A (mirrored from its upper triangle, LAPACK uplo='U' semantics of
+// eigh.jl:150-156) and the accumulated V live in shared memory.  Per round: rotation parameters of
+// all disjoint pairs from the current (a_pp, a_qq, a_pq), column rotations of A and V, barrier, row
+// rotations of A, barrier.  Epilogue: ascending sort, reference eigh gauge (common/gauge.jl:38-45).
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(BS_THREADS)
+batched_eigh_kernel(const EighBlockDesc<T>* __restrict__ descs, int* __restrict__ info, int max_sweeps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const EighBlockDesc<T> d = descs[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = BS_THREADS / 32;
+    const int n = d.n;
+    if (n <= 0) return;
+    const int ld = n | 1;
+    T* S = reinterpret_cast<T*>(smem_raw);      // ld x n
+    T* V = S + (size_t)ld * n;                  // ld x n
+    const int hp = (n + 1) / 2 + 1;
+    T* rph = V + (size_t)ld * n;                // [hp] e^{-i phi} per pair
+    double* lam = reinterpret_cast<double*>(rph + hp);   // n
+    double* rc = lam + n;                       // [hp] c
+    double* rs = rc + hp;                       // [hp] s
+    int* perm = reinterpret_cast<int*>(rs + hp);
+    __shared__ double s_red[32];
+    __shared__ int s_rot, s_big;
+
+    double part = 0.0;
+    for (int idx = tid; idx < n * n; idx += BS_THREADS) {
+        int c = idx / n, r = idx - c * n;
+        T v;
+        if (r < c) v = d.A[(size_t)c * d.lda + r];
+        else if (r > c) v = conj_(d.A[(size_t)r * d.lda + c]);
+        else v = mk<T>(real_(d.A[(size_t)c * d.lda + c]));
+        S[(size_t)c * ld + r] = v;
+        V[(size_t)c * ld + r] = (r == c) ? one<T>() : zero<T>();
+        part += abs2_(v);
+    }
+    const double fro = sqrt(block_sum<double>(part, s_red));
+    __syncthreads();
+    const double EPS = 2.220446049250313e-16;
+    const double thr = 0.5 * EPS * fro, thr_big = 4.0 * EPS * fro;
+
+    const int ne = (n + 1) & ~1;
+    int sweep = 0;
+    bool converged = (fro == 0.0);
+    for (; sweep < max_sweeps && !converged; ++sweep) {
+        if (tid == 0) { s_rot = 0; s_big = 0; }
+        __syncthreads();
+        for (int step = 0; step < ne - 1; ++step) {
+            // ---- rotation parameters + column rotations ----
+            for (int k = warp; k < ne / 2; k += NW) {
+                int p, q;
+                if (k == 0) { p = ne - 1; q = step; }
+                else { p = (step + k) % (ne - 1); q = (step - k + (ne - 1)) % (ne - 1); }
+                if (p > q) { int t = p; p = q; q = t; }
+                double c = 1.0, s = 0.0;
+                T ph = one<T>();
+                if (q < n) {
+                    const T g = S[(size_t)q * ld + p];           // a_pq
+                    const double ag = sqrt(abs2_(g));
+                    if (ag > thr) {
+                        const double al = real_(S[(size_t)p * ld + p]), be = real_(S[(size_t)q * ld + q]);
+                        const double zeta = (be - al) / (2.0 * ag);
+                        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                        c = 1.0 / sqrt(1.0 + t * t); s = c * t;
+                        ph = scale_(conj_(g), 1.0 / ag);         // e^{-i phi}
+                        if (lane == 0) { s_rot = 1; if (ag > thr_big) s_big = 1; }
+                    }
+                }
+                __syncwarp();   // every lane has read the pivot entries before any lane rotates them
+                if (lane == 0) { rc[k] = c; rs[k] = s; rph[k] = ph; }
+                if (s != 0.0) {
+                    const T sph = scale_(ph, s), cph = scale_(ph, c);
+                    T* x = S + (size_t)p * ld; T* y = S + (size_t)q * ld;
+                    T* vx = V + (size_t)p * ld; T* vy = V + (size_t)q * ld;
+                    for (int r = lane; r < n; r += 32) {
+                        T xv = x[r], yv = y[r];
+                        x[r] = sub_(scale_(xv, c), mul_(sph, yv));
+                        y[r] = add_(scale_(xv, s), mul_(cph, yv));
+                        xv = vx[r]; yv = vy[r];
+                        vx[r] = sub_(scale_(xv, c), mul_(sph, yv));
+                        vy[r] = add_(scale_(xv, s), mul_(cph, yv));
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- row rotations: A[p,:] = c A[p,:] - s e^{i phi} A[q,:],  A[q,:] = s A[p,:] + c e^{i phi} A[q,:]
+            for (int k = warp; k < ne / 2; k += NW) {
+                const double s = rs[k];
+                if (s == 0.0) continue;
+                int p, q;
+                if (k == 0) { p = ne - 1; q = step; }
+                else { p = (step + k) % (ne - 1); q = (step - k + (ne - 1)) % (ne - 1); }
+                if (p > q) { int t = p; p = q; q = t; }
+                const double c = rc[k];
+                const T phc = conj_(rph[k]);
+                const T sph = scale_(phc, s), cph = scale_(phc, c);
+                for (int col = lane; col < n; col += 32) {
+                    T* cp = S + (size_t)col * ld;
+                    T xv = cp[p], yv = cp[q];
+                    cp[p] = sub_(scale_(xv, c), mul_(sph, yv));
+                    cp[q] = add_(scale_(xv, s), mul_(cph, yv));
+                }
+            }
+            __syncthreads();
+            // the pivots are now (numerically) zero and the diagonal is real: make both exact
+            for (int k = tid; k < ne / 2; k += BS_THREADS) {
+                if (rs[k] == 0.0) continue;
+                int p, q;
+                if (k == 0) { p = ne - 1; q = step; }
+                else { p = (step + k) % (ne - 1); q = (step - k + (ne - 1)) % (ne - 1); }
+                if (p > q) { int t = p; p = q; q = t; }
+                S[(size_t)q * ld + p] = zero<T>();
+                S[(size_t)p * ld + q] = zero<T>();
+                S[(size_t)p * ld + p] = mk<T>(real_(S[(size_t)p * ld + p]));
+                S[(size_t)q * ld + q] = mk<T>(real_(S[(size_t)q * ld + q]));
+            }
+            __syncthreads();
+        }
+        // converged when a sweep made no rotation, or (after a few sweeps) only noise-level ones
+        if (s_rot == 0 || (sweep >= 5 && s_big == 0)) converged = true;
+        __syncthreads();
+    }
+    for (int j = tid; j < n; j += BS_THREADS) lam[j] = real_(S[(size_t)j * ld + j]);
+    __syncthreads();
+    // The accumulated product of ~sweeps*n^2/2 rotations drifts from unitarity by ~eps*sqrt(sweeps*n)
+    // per column; one Newton-Schulz step V <- V (3I - V^H V)/2 restores it to rounding level.
+    // S is free now: S <- (I - V^H V)/2.
+    if (d.V) {
+        for (int idx = tid; idx < n * n; idx += BS_THREADS) {
+            const int i = idx % n, j = idx / n;
+            if (i > j) continue;
+            const T* vi = V + (size_t)i * ld;
+            const T* vj = V + (size_t)j * ld;
+            T e = zero<T>();
+            for (int r = 0; r < n; ++r) fmac_(e, vi[r], vj[r]);
+            e = scale_(e, -0.5);
+            if (i == j) e = mk<T>(0.5 + real_(e));
+            S[(size_t)j * ld + i] = e;
+            if (i != j) S[(size_t)i * ld + j] = conj_(e);
+        }
+        __syncthreads();
+        constexpr int KQ = 4;   // n <= 128 columns per row = 4 per lane
+        for (int r = warp; r < n; r += NW) {
+            T v[KQ], acc[KQ];
+#pragma unroll
+            for (int qd = 0; qd < KQ; ++qd) {
+                const int c = lane + 32 * qd;
+                v[qd] = (c < n) ? V[(size_t)c * ld + r] : zero<T>();
+                acc[qd] = v[qd];
+            }
+            for (int k = 0; k < n; ++k) {
+                T vk = zero<T>();
+#pragma unroll
+                for (int qd = 0; qd < KQ; ++qd)
+                    if ((k >> 5) == qd) vk = v[qd];
+                vk = shfl_(vk, k & 31);
+                const T* Dk = S + k;   // row k of D: D[k, c] = S[c*ld + k]
+#pragma unroll
+                for (int qd = 0; qd < KQ; ++qd) {
+                    const int c = lane + 32 * qd;
+                    if (c < n) fma_(acc[qd], vk, Dk[(size_t)c * ld]);
+                }
+            }
+#pragma unroll
+            for (int qd = 0; qd < KQ; ++qd) {
+                const int c = lane + 32 * qd;
+                if (c < n) V[(size_t)c * ld + r] = acc[qd];
+            }
+        }
+        __syncthreads();
+    }
+    for (int j = tid; j < n; j += BS_THREADS) {
+        int rank = 0;
+        const double lj = lam[j];
+        for (int i = 0; i < n; ++i) rank += (lam[i] < lj) || (lam[i] == lj && i < j);
+        perm[rank] = j;
+    }
+    __syncthreads();
+    for (int j = warp; j < n; j += NW) {
+        const int src = perm[j];
+        const T* v = V + (size_t)src * ld;
+        if (lane == 0) d.W[j] = lam[src];
+        if (!d.V) continue;
+        double best = -1.0; int bi = 0x7fffffff;
+        for (int r = lane; r < n; r += 32) {
+            double a = abs2_(v[r]);
+            if (a > best) { best = a; bi = r; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        T cph = one<T>();
+        if (d.fixgauge && best > 0.0) {
+            T piv = v[bi];
+            cph = conj_(scale_(piv, 1.0 / sqrt(abs2_(piv))));
+        }
+        for (int r = lane; r < n; r += 32) d.V[(size_t)j * d.ldv + r] = mul_(v[r], cph);
+    }
+    if (tid == 0 && info) info[blockIdx.x] = converged ? 0 : 1;
+}
+
+size_t batched_eigh_smem_bytes(int n, size_t elem) {
+    size_t ld = (size_t)(n | 1), hp = (size_t)(n + 1) / 2 + 1;
+    return 2 * ld * n * elem + hp * elem + (size_t)n * 8 + 2 * hp * 8 + (size_t)n * 4 + 64;
+}
+size_t batched_eigh_max_smem_bytes() { return BQ_SMEM_BYTES; }
+
+template <typename T>
+int batched_eigh_smem(makb200_handle* h, int batch, size_t max_smem_bytes, const EighBlockDesc<T>* descs, int* info) {
+    if (batch <= 0) return 0;
+    if (max_smem_bytes > BQ_SMEM_BYTES) return MAKB200_ERR_WORKSPACE;
+    batched_eigh_kernel<T><<<batch, BS_THREADS, max_smem_bytes, h->stream>>>(descs, info, 30);
+    count_launch();
+    MAK_LAUNCH_CHECK(h, "batched_eigh_kernel");
+    return 0;
+}
+template int batched_eigh_smem<double>(makb200_handle*, int, size_t, const EighBlockDesc<double>*, int*);
+template int batched_eigh_smem<cplx>(makb200_handle*, int, size_t, const EighBlockDesc<cplx>*, int*);
+
 int batched_init(makb200_handle* h) {
     MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)BQ_SMEM_BYTES));
@@ -389,6 +613,10 @@ int batched_init(makb200_handle* h) {
     MAK_CUDA(h, cudaFuncSetAttribute(batched_svd_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)BQ_SMEM_BYTES));
     MAK_CUDA(h, cudaFuncSetAttribute(batched_svd_kernel<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)BQ_SMEM_BYTES));
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_eigh_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)BQ_SMEM_BYTES));
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_eigh_kernel<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)BQ_SMEM_BYTES));
     return 0;
 }

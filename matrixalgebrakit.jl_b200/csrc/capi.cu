@@ -8,6 +8,7 @@
 #include "stedc.cuh"
 #include "polar.cuh"
 #include <vector>
+#include <algorithm>
 
 using mak::cplx;
 
@@ -41,6 +42,9 @@ int makb200_create(makb200_handle_t** out, int device) {
         }
     }
     h->no_lookahead = false;
+    h->stage = nullptr;
+    h->stage_bytes = 0;
+    if (cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming) != cudaSuccess) { delete h; return MAKB200_ERR_CUDA; }
     for (int i = 0; i < 8; ++i) {
         if (cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return MAKB200_ERR_CUDA; }
         if (cudaEventCreateWithFlags(&h->pool_ev[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return MAKB200_ERR_CUDA; }
@@ -48,6 +52,7 @@ int makb200_create(makb200_handle_t** out, int device) {
     }
     int rc = mak::qr_init(h);
     if (rc == 0) rc = mak::batched_init(h);
+    if (rc == 0) rc = mak::batched_blocked_init(h);
     if (rc == 0) rc = mak::polar_init(h);
     if (rc != 0) { delete h; return rc; }
     *out = h;
@@ -57,6 +62,8 @@ int makb200_create(makb200_handle_t** out, int device) {
 int makb200_destroy(makb200_handle_t* h) {
     if (!h) return -1;
     cudaStreamDestroy(h->aux_stream);
+    cudaEventDestroy(h->stage_ev);
+    if (h->stage) cudaFreeHost(h->stage);
     for (int i = 0; i < 8; ++i) { cudaEventDestroy(h->ev[i]); cudaEventDestroy(h->pool_ev[i]); cudaStreamDestroy(h->pool[i]); }
     delete h;
     return 0;
@@ -227,63 +234,152 @@ static int run_pooled(makb200_handle_t* h, const std::vector<int>& big, char* wo
     return 0;
 }
 
+// size classes of a batched QR: three warp-kernel classes (m,n <= 32 by row capacity), the one-CTA
+// shared-memory kernel, the lock-step blocked path (panel fits one CTA), and per-block "big"
 template <typename T>
-static size_t qr_batched_worksize_t(makb200_handle_t* h, int batch, const int* m, const int* n) {
-    size_t bytes = mak::align_up(sizeof(mak::QrBlockDesc<T>) * (size_t)(batch > 0 ? batch : 1), 256);
-    size_t big = 0;
+struct QrClasses {
+    std::vector<int> warp[3], smem, blocked, big;
+    size_t max_se = 0;
+    std::vector<mak::BqrStep> steps;   // column steps of the blocked class (sorted by k descending)
+};
+static int bqr_min_dim() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MAKB200_BQR_MIN_DIM"); v = e ? atoi(e) : 96; if (v < 33) v = 33; }
+    return v;
+}
+template <typename T>
+static int classify_qr(int batch, const int* m, const int* n, QrClasses<T>& c) {
     for (int i = 0; i < batch; ++i) {
-        if (mak::batched_qr_smem_elems(m[i], n[i]) > mak::batched_qr_max_smem_elems<T>()) {
-            size_t w = mak::qr_worksize_t<T>(h, m[i], n[i], m[i] < n[i] ? m[i] : n[i]);
-            if (w > big) big = w;
+        if (m[i] < 0 || n[i] < 0) return -4;
+        if (m[i] == 0) continue;
+        const int k = m[i] < n[i] ? m[i] : n[i];
+        size_t se = mak::batched_qr_smem_elems(m[i], n[i]);
+        const bool fits_smem = se <= mak::batched_qr_max_smem_elems<T>();
+        if (m[i] <= 32 && n[i] <= 32 && n[i] > 0) {
+            c.warp[m[i] <= 16 ? 0 : (m[i] <= 24 ? 1 : 2)].push_back(i);
+        } else if (fits_smem && (k < bqr_min_dim() || !mak::bqr_fits<T>(m[i], n[i]))) {
+            c.smem.push_back(i);
+            if (se > c.max_se) c.max_se = se;
+        } else if (n[i] > 0 && mak::bqr_fits<T>(m[i], n[i])) {
+            c.blocked.push_back(i);
+        } else {
+            c.big.push_back(i);
         }
     }
-    return bytes + (big + 512) * NPOOL + 256;
+    std::stable_sort(c.blocked.begin(), c.blocked.end(), [&](int a, int b) {
+        return (m[a] < n[a] ? m[a] : n[a]) > (m[b] < n[b] ? m[b] : n[b]);
+    });
+    std::vector<int> ms, ns, ks;
+    for (int i : c.blocked) { ms.push_back(m[i]); ns.push_back(n[i]); ks.push_back(m[i] < n[i] ? m[i] : n[i]); }
+    c.steps = mak::bqr_steps<T>(ms, ns, ks);
+    return 0;
+}
+template <typename T>
+static int bqr_nsteps_of(const std::vector<mak::BqrStep>& steps, int k) {
+    int c = 0;
+    for (const auto& st : steps) if (st.j0 < k) ++c;
+    return c;
+}
+
+template <typename T>
+static size_t qr_batched_worksize_t(makb200_handle_t* h, int batch, const int* m, const int* n) {
+    QrClasses<T> c;
+    if (classify_qr<T>(batch, m, n, c)) return 0;
+    const size_t nb_ = (size_t)(batch > 0 ? batch : 1);
+    size_t bytes = mak::align_up(sizeof(mak::QrBlockDesc<T>) * nb_, 256) + mak::align_up(sizeof(mak::BqrBlock<T>) * nb_, 256) +
+                   mak::align_up(sizeof(mak::GemmProblem<T>) * 3 * nb_, 256);
+    size_t welems = 0;
+    for (int i : c.blocked) {
+        const int k = m[i] < n[i] ? m[i] : n[i];
+        welems += mak::bqr_block_work_elems<T>(m[i], n[i], k, bqr_nsteps_of<T>(c.steps, k));
+    }
+    bytes += mak::align_up(welems * sizeof(T), 256);
+    size_t big = 0;
+    for (int i : c.big) {
+        size_t w = mak::qr_worksize_t<T>(h, m[i], n[i], m[i] < n[i] ? m[i] : n[i]);
+        if (w > big) big = w;
+    }
+    return bytes + (c.big.empty() ? 0 : (big + 512) * NPOOL) + 1024;
 }
 
 template <typename T>
 static int qr_batched_t(makb200_handle_t* h, int batch, const int* m, const int* n, void* const* A, const int* lda,
                         void* const* Q, const int* ldq, void* const* R, const int* ldr, int* info, void* work,
                         size_t lwork) {
-    // size classes: warp kernel (m,n <= 32; three row capacities), CTA kernel (fits shared memory), big
-    std::vector<mak::QrBlockDesc<T>> cls[4];
-    std::vector<int> big;
-    size_t max_se = 0;
-    for (int i = 0; i < batch; ++i) {
-        if (m[i] < 0 || n[i] < 0) return -4;
-        if (m[i] == 0) continue;
-        size_t se = mak::batched_qr_smem_elems(m[i], n[i]);
+    QrClasses<T> c;
+    int rcc = classify_qr<T>(batch, m, n, c);
+    if (rcc) return rcc;
+    const size_t nb_ = (size_t)(batch > 0 ? batch : 1);
+    mak::Arena ar(work, lwork);
+    mak::QrBlockDesc<T>* ddev = ar.get<mak::QrBlockDesc<T>>(nb_);
+    mak::BqrBlock<T>* bdev = ar.get<mak::BqrBlock<T>>(nb_);
+    mak::GemmProblem<T>* pdev = ar.get<mak::GemmProblem<T>>(3 * nb_);
+    size_t welems = 0;
+    for (int i : c.blocked) {
+        const int k = m[i] < n[i] ? m[i] : n[i];
+        welems += mak::bqr_block_work_elems<T>(m[i], n[i], k, bqr_nsteps_of<T>(c.steps, k));
+    }
+    T* wblk = ar.get<T>(welems);
+    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    if (info) MAK_CUDA(h, cudaMemsetAsync(info, 0, sizeof(int) * batch, h->stream));
+
+    // descriptors of every class, one pinned staging upload
+    std::vector<mak::QrBlockDesc<T>> descs;
+    descs.reserve(batch);
+    auto push_desc = [&](int i) {
         mak::QrBlockDesc<T> d;
         d.m = m[i]; d.n = n[i];
         d.A = (T*)A[i]; d.lda = lda[i];
         d.Q = (T*)Q[i]; d.ldq = ldq[i];
         d.R = (R && R[i]) ? (T*)R[i] : nullptr; d.ldr = ldr ? ldr[i] : 0;
-        if (m[i] <= 32 && n[i] <= 32 && n[i] > 0) {
-            cls[m[i] <= 16 ? 0 : (m[i] <= 24 ? 1 : 2)].push_back(d);
-        } else if (se <= mak::batched_qr_max_smem_elems<T>()) {
-            cls[3].push_back(d);
-            if (se > max_se) max_se = se;
-        } else {
-            big.push_back(i);
+        descs.push_back(d);
+    };
+    for (int cl = 0; cl < 3; ++cl) for (int i : c.warp[cl]) push_desc(i);
+    for (int i : c.smem) push_desc(i);
+    std::vector<mak::BqrBlock<T>> bl;
+    bl.reserve(c.blocked.size());
+    {
+        auto up = [](size_t e) { return (e + 15) / 16 * 16; };
+        T* p = wblk;
+        for (int i : c.blocked) {
+            const int k = m[i] < n[i] ? m[i] : n[i];
+            const size_t wc = (size_t)(n[i] > k ? n[i] : k);
+            mak::BqrBlock<T> b;
+            b.m = m[i]; b.n = n[i]; b.k = k;
+            b.A = (T*)A[i]; b.lda = lda[i];
+            b.Q = (T*)Q[i]; b.ldq = ldq[i];
+            b.R = (R && R[i]) ? (T*)R[i] : nullptr; b.ldr = ldr ? ldr[i] : 0;
+            b.Vw = p; p += up((size_t)m[i] * mak::BQR_NB);
+            b.W = p;  p += up((size_t)mak::BQR_NB * wc);
+            b.W2 = p; p += up((size_t)mak::BQR_NB * wc);
+            b.Tf = p; p += up((size_t)mak::BQR_NB * mak::BQR_NB * bqr_nsteps_of<T>(c.steps, k));
+            bl.push_back(b);
         }
     }
-    mak::Arena ar(work, lwork);
-    mak::QrBlockDesc<T>* ddev = ar.get<mak::QrBlockDesc<T>>(batch > 0 ? batch : 1);
-    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
-    if (info) MAK_CUDA(h, cudaMemsetAsync(info, 0, sizeof(int) * batch, h->stream));
-    size_t off = 0;
-    for (int cidx = 0; cidx < 4; ++cidx) {
-        if (cls[cidx].empty()) continue;
-        MAK_CUDA(h, cudaMemcpyAsync(ddev + off, cls[cidx].data(), sizeof(mak::QrBlockDesc<T>) * cls[cidx].size(),
-                                    cudaMemcpyHostToDevice, h->stream));
-        int rc = cidx < 3 ? mak::batched_qr_warp<T>(h, (int)cls[cidx].size(), cidx == 0 ? 16 : (cidx == 1 ? 24 : 32), ddev + off)
-                          : mak::batched_qr_smem<T>(h, (int)cls[cidx].size(), max_se, ddev + off, nullptr);
-        if (rc) return rc;
-        off += cls[cidx].size();
+    {
+        mak::Stager st(h, descs.size() * sizeof(mak::QrBlockDesc<T>) + bl.size() * sizeof(mak::BqrBlock<T>) + 1024);
+        MAK_CUDA(h, st.put(ddev, descs.data(), descs.size() * sizeof(mak::QrBlockDesc<T>), h->stream));
+        MAK_CUDA(h, st.put(bdev, bl.data(), bl.size() * sizeof(mak::BqrBlock<T>), h->stream));
     }
-    // blocks too large for one CTA's shared memory take the blocked DMMA path
+    size_t off = 0;
+    for (int cl = 0; cl < 3; ++cl) {
+        if (c.warp[cl].empty()) continue;
+        int rc = mak::batched_qr_warp<T>(h, (int)c.warp[cl].size(), cl == 0 ? 16 : (cl == 1 ? 24 : 32), ddev + off);
+        if (rc) return rc;
+        off += c.warp[cl].size();
+    }
+    if (!c.smem.empty()) {
+        int rc = mak::batched_qr_smem<T>(h, (int)c.smem.size(), c.max_se, ddev + off, nullptr);
+        if (rc) return rc;
+    }
+    if (!bl.empty()) {
+        int rc = mak::batched_qr_blocked<T>(h, (int)bl.size(), bdev, c.steps, pdev);
+        if (rc) return rc;
+    }
+    // blocks whose panel does not fit one CTA take the single-matrix blocked DMMA path
     char* wbig = (char*)work + ar.off;
     size_t lbig = lwork > ar.off ? lwork - ar.off : 0;
-    return run_pooled(h, big, wbig, lbig, [&](char* w, size_t lw, int i) {
+    return run_pooled(h, c.big, wbig, lbig, [&](char* w, size_t lw, int i) {
         return mak::qr_fused_t<T>(h, MAKB200_QR_COMPACT, m[i], n[i], (T*)A[i], lda[i], (T*)Q[i], ldq[i],
                                   (R && R[i]) ? (T*)R[i] : nullptr, ldr ? ldr[i] : 0, w, lw);
     });
@@ -525,6 +621,86 @@ int makb200_svd_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch,
     return svd_batched_t<cplx>(h, fixgauge, batch, m, n, A, lda, S, U, ldu, Vh, ldvh, info, work, lwork);
 }
 
+
+}  // extern "C"
+
+// ---- batched eigh -------------------------------------------------------------------------
+template <typename T>
+static int eigh_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int* n, void* const* A, const int* lda,
+                          void* const* W, void* const* V, const int* ldv, int* info, void* work, size_t lwork) {
+    std::vector<mak::EighBlockDesc<T>> small;
+    std::vector<int> big;
+    size_t max_b = 0;
+    for (int i = 0; i < batch; ++i) {
+        if (n[i] < 0) return -5;
+        if (n[i] == 0) continue;
+        size_t sb = mak::batched_eigh_smem_bytes(n[i], sizeof(T));
+        if (sb > mak::batched_eigh_max_smem_bytes()) { big.push_back(i); continue; }
+        mak::EighBlockDesc<T> d;
+        d.n = n[i]; d.fixgauge = fixgauge;
+        d.A = (const T*)A[i]; d.lda = lda[i];
+        d.W = (double*)W[i];
+        d.V = V ? (T*)V[i] : nullptr; d.ldv = ldv ? ldv[i] : 0;
+        small.push_back(d);
+        if (sb > max_b) max_b = sb;
+    }
+    mak::Arena ar(work, lwork);
+    mak::EighBlockDesc<T>* ddev = ar.get<mak::EighBlockDesc<T>>(batch > 0 ? batch : 1);
+    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    if (info) MAK_CUDA(h, cudaMemsetAsync(info, 0, sizeof(int) * batch, h->stream));
+    if (!small.empty()) {
+        {
+            mak::Stager st(h, small.size() * sizeof(mak::EighBlockDesc<T>) + 512);
+            MAK_CUDA(h, st.put(ddev, small.data(), small.size() * sizeof(mak::EighBlockDesc<T>), h->stream));
+        }
+        int rc = mak::batched_eigh_smem<T>(h, (int)small.size(), max_b, ddev, nullptr);
+        if (rc) return rc;
+    }
+    if (!big.empty() && !V) return -9;   // the single-matrix path always forms vectors
+    char* wbig = (char*)work + ar.off;
+    size_t lbig = lwork > ar.off ? lwork - ar.off : 0;
+    return run_pooled(h, big, wbig, lbig, [&](char* w, size_t lw, int i) {
+        return mak::eigh_t<T>(h, n[i], (T*)A[i], lda[i], (double*)W[i], (T*)V[i], ldv[i], fixgauge, w, lw, nullptr);
+    });
+}
+
+extern "C" {
+
+size_t makb200_eigh_batched_worksize(makb200_handle_t* h, int dtype, int batch, const int* n) {
+    if (!h || !dtype_ok(dtype) || batch < 0 || (batch > 0 && !n)) return 0;
+    size_t esz = dtype == MAKB200_F64 ? sizeof(double) : sizeof(cplx);
+    size_t bytes = mak::align_up(sizeof(mak::EighBlockDesc<cplx>) * (size_t)(batch > 0 ? batch : 1), 256), big = 0;
+    bool any = false;
+    for (int i = 0; i < batch; ++i) {
+        if (n[i] <= 0) continue;
+        if (mak::batched_eigh_smem_bytes(n[i], esz) > mak::batched_eigh_max_smem_bytes()) {
+            size_t w = dtype == MAKB200_F64 ? mak::eigh_worksize_t<double>(h, n[i]) : mak::eigh_worksize_t<cplx>(h, n[i]);
+            if (w > big) big = w;
+            any = true;
+        }
+    }
+    return bytes + (any ? (big + 512) * NPOOL : 0) + 256;
+}
+
+int makb200_eigh_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch, const int* n, void* const* A,
+                         const int* lda, void* const* W, void* const* V, const int* ldv, int* info, void* work,
+                         size_t lwork) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (batch < 0) return -4;
+    if (batch == 0) return 0;
+    if (!n) return -5;
+    if (!A) return -6;
+    if (!lda) return -7;
+    if (!W) return -8;
+    if (V && !ldv) return -10;
+    if (dtype == MAKB200_F64) return eigh_batched_t<double>(h, fixgauge, batch, n, A, lda, W, V, ldv, info, work, lwork);
+    return eigh_batched_t<cplx>(h, fixgauge, batch, n, A, lda, W, V, ldv, info, work, lwork);
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ---- adjoint (lq_via_qr!, svd_via_adjoint!) -----------------------------------------------
 int makb200_adjoint(makb200_handle_t* h, int dtype, int m, int n, const void* A, int lda, void* B, int ldb) {

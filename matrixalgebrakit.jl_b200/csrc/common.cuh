@@ -153,6 +153,9 @@ struct makb200_handle {
     cudaStream_t pool[8];      // stream pool: mid-size blocks of a batch run concurrently
     cudaEvent_t pool_ev[8];
     bool no_lookahead;         // set while a pooled call is in flight (aux stream/events are shared)
+    void* stage;               // pinned host staging for descriptor uploads (batched entry points)
+    size_t stage_bytes;
+    cudaEvent_t stage_ev;      // recorded after the last upload out of `stage`
     char err[256];
 };
 
@@ -249,6 +252,34 @@ struct PhaseTimer {
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Descriptor upload through the handle's pinned staging buffer: no pageable-memory staging inside
+// the driver, no stream synchronisation; the only wait is on the previous call's last upload.
+struct Stager {
+    makb200_handle* h;
+    size_t off;
+    bool ok;
+    Stager(makb200_handle* hh, size_t total) : h(hh), off(0), ok(true) {
+        cudaEventSynchronize(h->stage_ev);
+        if (total > h->stage_bytes) {
+            if (h->stage) cudaFreeHost(h->stage);
+            h->stage = nullptr;
+            h->stage_bytes = 0;
+            size_t want = align_up(total + total / 2 + 4096, 4096);
+            if (cudaMallocHost(&h->stage, want) != cudaSuccess) { ok = false; cudaGetLastError(); return; }
+            h->stage_bytes = want;
+        }
+    }
+    cudaError_t put(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t s) {
+        if (bytes == 0) return cudaSuccess;
+        if (!ok || off + bytes > h->stage_bytes) return cudaErrorMemoryAllocation;
+        char* p = (char*)h->stage + off;
+        memcpy(p, src_host, bytes);
+        off += align_up(bytes, 256);
+        return cudaMemcpyAsync(dst_dev, p, bytes, cudaMemcpyHostToDevice, s);
+    }
+    ~Stager() { cudaEventRecord(h->stage_ev, h->stream); }
+};
 
 // bump allocator over the caller-provided workspace
 struct Arena {

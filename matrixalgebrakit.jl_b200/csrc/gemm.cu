@@ -31,6 +31,19 @@ template <> struct Cfg<cplx, 0> {
     static constexpr int SA_MN = BM + 2, SB_MN = BN + 2, S_K = BK + 4;
 };
 template <> struct Cfg<cplx, 1> : Cfg<cplx, 0> {};
+// V = 2: small tiles, 128 threads, several resident CTAs per SM -- for the grouped launches of the
+// batched paths (thousands of small problems with short K: latency is hidden by co-resident CTAs,
+// not by a deep pipeline)
+template <> struct Cfg<double, 2> {
+    static constexpr int BM = 64, BN = 64, BK = 16, WM = 32, WN = 32, STAGES = 3, THREADS = 128, MINB = 4;
+    static constexpr int SA_MN = BM + 4, SB_MN = BN + 4, S_K = BK + 4;
+};
+template <> struct Cfg<cplx, 2> {
+    static constexpr int BM = 64, BN = 64, BK = 8, WM = 32, WN = 32, STAGES = 3, THREADS = 128, MINB = 3;
+    static constexpr int SA_MN = BM + 2, SB_MN = BN + 2, S_K = BK + 4;
+};
+template <typename C, typename = void> struct MinBlocks { static constexpr int value = 1; };
+template <typename C> struct MinBlocks<C, decltype((void)C::MINB)> { static constexpr int value = C::MINB; };
 
 template <typename T, typename C, bool TA> struct ATile {
     static constexpr int STRIDE = TA ? C::S_K : C::SA_MN;
@@ -117,7 +130,7 @@ template <> struct Acc<double> { double c0, c1; };
 template <> struct Acc<cplx> { double r0, r1, i0, i1; };
 
 template <typename T, typename C, bool TA, bool TB>
-__global__ void __launch_bounds__(C::THREADS, 1)
+__global__ void __launch_bounds__(C::THREADS, MinBlocks<C>::value)
 gemm_kernel(const GemmProblem<T> p0, const GemmProblem<T>* __restrict__ plist, int splitk,
             T* __restrict__ ws) {
     using AT = ATile<T, C, TA>;
@@ -369,10 +382,16 @@ cudaError_t gemm(cudaStream_t stream, int num_sms, int opa, int opb, int m, int 
 template <typename T>
 cudaError_t gemm_grouped(cudaStream_t stream, int opa, int opb, int count, int max_m, int max_n,
                          const GemmProblem<T>* problems_dev) {
-    using C = Cfg<T, 0>;
     if (count <= 0 || max_m <= 0 || max_n <= 0) return cudaSuccess;
-    dim3 grid((max_m + C::BM - 1) / C::BM, (max_n + C::BN - 1) / C::BN, count);
     GemmProblem<T> dummy{};
+    static const bool small = []() { const char* e = getenv("MAKB200_GROUPED_SMALL"); return !(e && e[0] == '0'); }();
+    if (small) {
+        using C = Cfg<T, 2>;
+        dim3 grid((max_m + C::BM - 1) / C::BM, (max_n + C::BN - 1) / C::BN, count);
+        return dispatch2<T, C>(stream, opa != MAKB200_OP_N, opb != MAKB200_OP_N, grid, dummy, problems_dev, 1, nullptr);
+    }
+    using C = Cfg<T, 0>;
+    dim3 grid((max_m + C::BM - 1) / C::BM, (max_n + C::BN - 1) / C::BN, count);
     return dispatch<T>(stream, opa != MAKB200_OP_N, opb != MAKB200_OP_N, grid, dummy, problems_dev, 1, nullptr);
 }
 

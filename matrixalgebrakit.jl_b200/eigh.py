@@ -145,3 +145,42 @@ def eigh_trunc_(A, DV=None, alg=None, trunc=None, **kw):
 
 def eigh_trunc(A, alg=None, trunc=None, **kw):
     return eigh_trunc_(copy_input(A), None, alg, trunc, **kw)
+
+
+class BatchedEighPlan:
+    """Argument arrays of a batched ``eigh_full!`` built once; ``run()`` is one C-ABI call
+    (one CTA per block, two-sided Jacobi in shared memory; large blocks routed per block)."""
+
+    def __init__(self, As, DVs=None, fixgauge=True, check=False):
+        self.As = As
+        self.h = _core.Handle.get(As[0].device)
+        self.dt = _core.dtype_code(As[0])
+        self.DVs = DVs if DVs is not None else [initialize_output(A) for A in As]
+        for A, DV in zip(As, self.DVs):
+            check_input(A, DV, None, check=check)
+        b = self.b = len(As)
+        IA, VP = C.c_int * b, C.c_void_p * b
+        self.fixgauge = int(bool(fixgauge))
+        self.n = IA(*[A.shape[0] for A in As])
+        self.lda = IA(*[_core.ld(A) for A in As])
+        self.ldv = IA(*[_core.ld(V) for _, V in self.DVs])
+        self.Ap = VP(*[A.data_ptr() for A in As])
+        self.Wp = VP(*[D.data_ptr() for D, _ in self.DVs])
+        self.Vp = VP(*[V.data_ptr() for _, V in self.DVs])
+        self.lw = self.h.lib.makb200_eigh_batched_worksize(self.h.h, self.dt, b, self.n)
+
+    def run(self):
+        h = _core.Handle.get(self.As[0].device)
+        work = h.workspace(self.lw)
+        rc = h.lib.makb200_eigh_batched(h.h, self.dt, self.fixgauge, self.b, self.n, self.Ap, self.lda, self.Wp,
+                                        self.Vp, self.ldv, C.c_void_p(0), _core.ptr(work), work.numel())
+        h.check(rc, "makb200_eigh_batched")
+        return self.DVs
+
+
+def eigh_full_batched_(As, DVs=None, fixgauge=True, check=True):
+    """Batched ``eigh_full!`` over a list of Hermitian blocks (per-block semantics of eigh.jl:123-156;
+    ``check`` runs the reference's Hermitian pre-check per block)."""
+    if len(As) == 0:
+        return []
+    return BatchedEighPlan(As, DVs, fixgauge, check).run()

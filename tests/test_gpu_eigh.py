@@ -149,3 +149,32 @@ def test_stedc_vs_scipy(case):
     assert np.max(np.abs(w - wref)) / nrm <= tol
     assert np.linalg.norm(T @ Zn - Zn * w) / nrm <= tol
     assert O.orth_err(Zn) <= tol
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_eigh_batched_vs_oracle(dtype):
+    """Batched eigh_full! (one CTA per block, two-sided Jacobi): per-block results vs the LAPACK oracle,
+    incl. degenerate / zero / identity / +-pair spectra, only the upper triangle read, inputs intact,
+    and blocks too large for shared memory routed through the single-matrix path."""
+    import makb200
+    rng = np.random.default_rng(9)
+    ns = [1, 2, 3, 16, 17, 31, 32, 33, 54, 64, 75, 79] + [int(v) for v in rng.integers(16, 79, size=20)]
+    ns += [130]  # routed (does not fit one CTA)
+    As0 = [O.rand_hermitian(n, dtype, seed=500 + i) for i, n in enumerate(ns)]
+    Q, _ = O.qr_compact(O.randn_matrix(40, 40, dtype, seed=3))
+    specials = [np.zeros((24, 24)), np.eye(30), (Q * np.repeat([-1.0, 1.0], 20)) @ Q.conj().T,
+                (Q * np.repeat(np.arange(4.0), 10)) @ Q.conj().T, (Q * 10.0 ** (-12 * np.arange(40) / 40)) @ Q.conj().T]
+    for S in specials:
+        S = (S + S.conj().T) / 2
+        As0.append(S.astype(np.complex128) if dtype == "c128" else np.ascontiguousarray(S.real))
+    As = [makb200.to_device(a) for a in As0]
+    # garbage in the strictly lower triangle of one block must be ignored (uplo='U')
+    junk = As0[8].copy()
+    junk[np.tril_indices(junk.shape[0], -1)] = 7.0
+    As[8] = makb200.to_device(junk)
+    DVs = makb200.eigh_full_batched_(As, check=False)
+    torch.cuda.synchronize()
+    for i, (a, (D, V)) in enumerate(zip(As0, DVs)):
+        if a.shape[0] <= 79 and i != 8:
+            assert np.array_equal(makb200.to_numpy(As[i]), a)   # small blocks are not destroyed
+        _check(a, D.cpu().numpy(), makb200.to_numpy(V), vec_cmp=(i < len(ns)))

@@ -137,3 +137,36 @@ def test_qr_batched_vs_oracle(dtype):
         Qn, Rn = makb200.to_numpy(Q), makb200.to_numpy(R)
         Qo, Ro = O.qr_compact(a)
         _check(a, Qn, Rn, Qo, Ro)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_qr_batched_blocked_lockstep(dtype):
+    """Mid-size ragged blocks (lock-step blocked path of batched_blocked.cu): tall, wide, square, widths
+    that are not multiples of the column step, graded columns, a zero block, and a strided view."""
+    import makb200
+    sizes = [(96, 96), (97, 101), (130, 130), (200, 150), (150, 200), (257, 257), (300, 100), (100, 300),
+             (512, 512), (333, 129), (128, 128), (99, 160)]
+    As0 = [O.randn_matrix(m, n, dtype, seed=300 + i) for i, (m, n) in enumerate(sizes)]
+    As0[2] = As0[2] * (10.0 ** (-12 * np.arange(130) / 130))[None, :]   # graded columns
+    As0[4] = np.zeros_like(As0[4])                                      # zero block
+    As = [makb200.to_device(a) for a in As0]
+    # strided view: lda != m
+    big = makb200.to_device(O.randn_matrix(260, 140, dtype, seed=399))
+    As.append(big[10:210, 5:135]); As0.append(makb200.to_numpy(big)[10:210, 5:135].copy())
+    QRs = makb200.qr_compact_batched_(As)
+    torch.cuda.synchronize()
+    for idx, (a, (Q, R)) in enumerate(zip(As0, QRs)):
+        Qn, Rn = makb200.to_numpy(Q), makb200.to_numpy(R)
+        m, n = a.shape
+        tol = O.tol_for(m, n)
+        assert np.allclose(np.tril(Rn, -1), 0)
+        assert np.all(np.real(np.diagonal(Rn)) >= 0) and np.allclose(np.imag(np.diagonal(Rn)), 0)
+        if idx == 4:
+            assert np.allclose(Rn, 0) and O.orth_err(Qn) <= tol
+            continue
+        assert O.rel_resid(a, Qn, Rn) <= tol
+        assert O.orth_err(Qn) <= tol
+        if idx != 2 and m >= n:
+            Qo, Ro = O.qr_compact(a)
+            assert np.linalg.norm(Rn - Ro) <= 100 * tol * np.linalg.norm(Ro)
+            assert np.linalg.norm(Qn - Qo) <= 100 * tol * np.sqrt(n)

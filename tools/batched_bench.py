@@ -38,11 +38,15 @@ As0 = [torch.randn((n, n), dtype=torch.complex128, device=dev, generator=g).t() 
 buckets = [(16, 32), (33, 64), (65, 128), (129, 256), (257, 512)]
 
 
-def run(op, idx):
-    blocks = [As0[i] for i in idx]
+def run(op, idx, rep=1):
+    blocks = [As0[i] for i in idx] * rep
+    if op == "eigh":
+        blocks = [(a + a.conj().t()) for a in blocks]
     As = [makb200.colmajor_empty(a.shape[0], a.shape[1], a.dtype, dev) for a in blocks]
     if op == "qr":
         plan = makb200.BatchedQRPlan(As)     # argument arrays built once (sizes/pointers are fixed)
+    elif op == "eigh":
+        plan = makb200.BatchedEighPlan(As)
     else:
         plan = makb200.BatchedSVDPlan(As)
     fn = plan.run
@@ -63,17 +67,25 @@ for op in ops:
         idx = [i for i, n in enumerate(mine) if lo <= n <= hi]
         if not idx:
             continue
-        if op == "svd" and lo > 128 and len(idx) > 64:
-            idx = idx[:64]          # large-block SVD goes through the single-matrix path: bounded sample
-        if op == "qr" and lo > 128 and len(idx) > 512:
-            idx = idx[:512]
-        ms = run(op, idx)
-        ns = np.array([mine[i] for i in idx], dtype=np.float64)
-        byt = 16 * 3 * (ns ** 2).sum() + (8 * ns.sum() if op == "svd" else 0)
-        fl = 4 * ((8.0 / 3) if op == "qr" else (20.0 / 3)) * (ns ** 3).sum()
-        res[f"{op}_{lo}-{hi}"] = {"blocks": len(idx), "ms": ms, "blocks_per_s": len(idx) / ms * 1e3,
+        if op in ("svd", "eigh") and lo > 64 and len(idx) > 64:
+            idx = idx[:64]          # large-block SVD/eigh go through the single-matrix path: bounded sample
+        # the smallest bucket is replicated so that the launch carries enough bytes to show the
+        # steady-state HBM fraction (4151 blocks are only ~0.1 GB = 17 us at HBM speed)
+        rep = 16 if (hi <= 32 and len(idx) * 16 <= 80000) else 1
+        ms = run(op, idx, rep)
+        ns = np.array([mine[i] for i in idx] * rep, dtype=np.float64)
+        if op == "qr":
+            byt = 16 * 3 * (ns ** 2).sum()
+            fl = 4 * (8.0 / 3) * (ns ** 3).sum()
+        elif op == "svd":
+            byt = 16 * 3 * (ns ** 2).sum() + 8 * ns.sum()
+            fl = 4 * (20.0 / 3) * (ns ** 3).sum()
+        else:
+            byt = 16 * 2 * (ns ** 2).sum() + 8 * ns.sum()
+            fl = 4 * (10.0 / 3) * (ns ** 3).sum()
+        res[f"{op}_{lo}-{hi}"] = {"blocks": len(ns), "ms": ms, "blocks_per_s": len(ns) / ms * 1e3,
                                   "alg_GBs": byt / ms / 1e6, "hbm_frac": byt / ms / 1e6 / 6555.8,
-                                  "alg_GFLOPs": fl / ms / 1e6}
+                                  "alg_GFLOPs": fl / ms / 1e6, "replicated": rep}
 if world > 1:
     gathered = [None] * world
     dist.all_gather_object(gathered, res)
