@@ -97,6 +97,19 @@ int makb200_qr_batched(makb200_handle_t* h, int dtype, int batch, const int* m, 
                        void* const* A, const int* lda, void* const* Q, const int* ldq,
                        void* const* R, const int* ldr, int* info, void* work, size_t lwork);
 
+/* Plan form of makb200_qr_batched for block structures that are reused across calls (a block-sparse
+ * tensor keeps its sectors): create() classifies the blocks, carves `work` and uploads the
+ * descriptors once (asynchronously on the handle's stream); run() only launches kernels.
+ * `work` (makb200_qr_batched_worksize bytes) and all block pointers must stay valid while the
+ * plan lives.  info: DEVICE int[batch] or NULL. */
+typedef struct makb200_qr_batched_plan makb200_qr_batched_plan_t;
+int makb200_qr_batched_plan_create(makb200_handle_t* h, int dtype, int batch, const int* m, const int* n,
+                                   void* const* A, const int* lda, void* const* Q, const int* ldq,
+                                   void* const* R, const int* ldr, void* work, size_t lwork,
+                                   makb200_qr_batched_plan_t** plan);
+int makb200_qr_batched_plan_run(makb200_handle_t* h, makb200_qr_batched_plan_t* plan, int* info);
+int makb200_qr_batched_plan_destroy(makb200_qr_batched_plan_t* plan);
+
 /* -- eigh_full! ------------------------------------------------------------------------
  * makb200_hermitian_defect: the device half of check_hermitian (implementations/eigh.jl:11-18,
  *   matrixproperties.jl:150-172; MatrixAlgebraKitCUDAExt.jl:147-152): out2_dev[0] =

@@ -37,6 +37,10 @@ SIGNATURES = {
     "makb200_qr": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _sz]),
     "makb200_qr_batched_worksize": (_sz, [_vp, _i, _i, _ip, _ip]),
     "makb200_qr_batched": (_i, [_vp, _i, _i, _ip, _ip, _vpp, _ip, _vpp, _ip, _vpp, _ip, _vp, _vp, _sz]),
+    "makb200_qr_batched_plan_create": (_i, [_vp, _i, _i, _ip, _ip, _vpp, _ip, _vpp, _ip, _vpp, _ip, _vp, _sz,
+                                            C.POINTER(C.c_void_p)]),
+    "makb200_qr_batched_plan_run": (_i, [_vp, _vp, _vp]),
+    "makb200_qr_batched_plan_destroy": (_i, [_vp]),
     "makb200_hermitian_defect": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "makb200_eigh_worksize": (_sz, [_vp, _i, _i]),
     "makb200_eigh": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _sz, _vp]),

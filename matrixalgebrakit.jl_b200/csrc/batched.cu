@@ -10,210 +10,224 @@ constexpr int BQ_THREADS = 256;
 constexpr size_t BQ_SMEM_BYTES = 200 * 1024;
 
 // shared-memory elements a block needs: padded tile + tau
-size_t batched_qr_smem_elems(int m, int n) { return (size_t)(m | 1) * n + (m < n ? m : n) + 1; }
+size_t batched_qr_smem_elems(int m, int n) { return (size_t)(m | 1) * n + (m < n ? m : n) + 1 + (size_t)n; }
 template <typename T> size_t batched_qr_max_smem_elems() { return BQ_SMEM_BYTES / sizeof(T) - 64; }
 template size_t batched_qr_max_smem_elems<double>();
 template size_t batched_qr_max_smem_elems<cplx>();
 
-template <typename T>
-__global__ void __launch_bounds__(BQ_THREADS)
+// NT threads per block (64 / 128 / 256 by size class, so that small blocks get many resident CTAs).
+// One block barrier per column: the reflector scalars are formed redundantly by every warp from the
+// tail norm that the warp updating column j+1 produced in step j; column j is scaled into v after
+// the barrier by one warp while the others already work on step j+1 (it is not read again before
+// the Q phase).  In the Q phase the v -> q conversion of column j+1 is done by the warp that owns it
+// at the start of step j, which removes the second barrier there as well.
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT)
 batched_qr_kernel(const QrBlockDesc<T>* __restrict__ descs, int* __restrict__ info) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const QrBlockDesc<T> d = descs[blockIdx.x];
     const int m = d.m, n = d.n, k = m < n ? m : n;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = BQ_THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
     if (m <= 0 || n < 0) { if (tid == 0 && info) info[blockIdx.x] = 0; return; }
     const int lds = m | 1;  // odd leading dimension
     T* S = reinterpret_cast<T*>(smem_raw);        // lds x n
     T* tau = S + (size_t)lds * n;                 // k
-    T* red = tau + (k > 0 ? k : 1);               // 32
-    T* scal = red + 32;                           // 4
+    double* sig = reinterpret_cast<double*>(tau + (k > 0 ? k : 1));   // n tail norms^2
 
-    for (int idx = tid; idx < m * n; idx += BQ_THREADS) {
-        int c = idx / m, r = idx - c * m;
-        S[(size_t)c * lds + r] = d.A[(size_t)c * d.lda + r];
+    for (int c = warp; c < n; c += NW) {
+        const T* src = d.A + (size_t)c * d.lda;
+        T* dst = S + (size_t)c * lds;
+        double part = 0.0;
+        for (int r = lane; r < m; r += 32) {
+            const T v = src[r];
+            dst[r] = v;
+            if (r > 0) part += abs2_(v);
+        }
+        if (c == 0) { part = warp_sum(part); if (lane == 0) sig[0] = part; }
     }
     __syncthreads();
 
     // ---- factorization: S -> V \ R ----
     for (int j = 0; j < k; ++j) {
         T* cj = S + (size_t)j * lds;
-        double part = 0.0;
-        for (int r = j + 1 + tid; r < m; r += BQ_THREADS) part += abs2_(cj[r]);
-        T tot = block_sum<T>(mk<T>(part), red);
         double beta; T tj, scale;
-        larfgp_scalars<T>(cj[j], real_(tot), beta, tj, scale);
-        __syncthreads();  // everyone has read cj[j]
-        for (int r = j + 1 + tid; r < m; r += BQ_THREADS) cj[r] = mul_(cj[r], scale);
-        if (tid == 0) { cj[j] = mk<T>(beta); tau[j] = tj; }
-        __syncthreads();
-        // apply H_j^H to columns l > j: one warp per column
+        larfgp_scalars<T>(cj[j], sig[j], beta, tj, scale);
         const T ctau = conj_(tj);
         for (int l = j + 1 + warp; l < n; l += NW) {
             T* cl = S + (size_t)l * lds;
-            T s = zero<T>();
-            for (int r = j + 1 + lane; r < m; r += 32) fmac_(s, cj[r], cl[r]);
-            s = warp_sum(s);
-            T f = mul_(ctau, add_(cl[j], s));
-            __syncwarp();
-            for (int r = j + 1 + lane; r < m; r += 32) cl[r] = sub_(cl[r], mul_(f, cj[r]));
-            if (lane == 0) cl[j] = sub_(cl[j], f);
+            const T clj = cl[j];
+            T s0 = zero<T>(), s1 = zero<T>();
+            int r = j + 1 + lane;
+            for (; r + 32 < m; r += 64) {
+                fmac_(s0, mul_(cj[r], scale), cl[r]);
+                fmac_(s1, mul_(cj[r + 32], scale), cl[r + 32]);
+            }
+            if (r < m) fmac_(s0, mul_(cj[r], scale), cl[r]);
+            const T s = warp_sum(add_(s0, s1));
+            const T f = mul_(ctau, add_(clj, s));
+            double nrm = 0.0;
+            for (r = j + 1 + lane; r < m; r += 32) {
+                const T x = sub_(cl[r], mul_(f, mul_(cj[r], scale)));
+                cl[r] = x;
+                if (r > j + 1) nrm += abs2_(x);
+            }
+            if (l == j + 1) { nrm = warp_sum(nrm); if (lane == 0) sig[j + 1] = nrm; }
+            if (lane == 0) cl[j] = sub_(clj, f);
         }
         __syncthreads();
-    }
-
-    // ---- R out (upper triangle, zeros below) ----
-    if (d.R) {
-        for (int idx = tid; idx < k * n; idx += BQ_THREADS) {
-            int c = idx / k, r = idx - c * k;
-            d.R[(size_t)c * d.ldr + r] = (r <= c) ? S[(size_t)c * lds + r] : zero<T>();
+        if (warp == j % NW) {
+            for (int r = j + 1 + lane; r < m; r += 32) cj[r] = mul_(cj[r], scale);
+            if (lane == 0) { cj[j] = mk<T>(beta); tau[j] = tj; }
         }
     }
     __syncthreads();
 
+    // ---- R out (upper triangle, zeros below) ----
+    if (d.R) {
+        for (int c = warp; c < n; c += NW)
+            for (int r = lane; r < k; r += 32) d.R[(size_t)c * d.ldr + r] = (r <= c) ? S[(size_t)c * lds + r] : zero<T>();
+    }
+    __syncthreads();
+
     // ---- form Q (m x k) in place over V, backward accumulation (org2r) ----
-    for (int j = k - 1; j >= 0; --j) {
-        T* cj = S + (size_t)j * lds;
+    auto to_q = [&](int c) {   // column c: v-form -> H_c e_c = e_c - tau_c [0; 1; v]   (one warp)
+        T* cc = S + (size_t)c * lds;
+        const T tc = tau[c];
+        for (int r = lane; r < m; r += 32) {
+            T x;
+            if (r < c) x = zero<T>();
+            else if (r == c) x = sub_(one<T>(), tc);
+            else x = neg_(mul_(tc, cc[r]));
+            cc[r] = x;
+        }
+        __syncwarp();
+    };
+    for (int j = k - 2; j >= 0; --j) {
+        const T* cj = S + (size_t)j * lds;
         const T tj = tau[j];
-        // apply H_j to columns l in (j, k): Q[j:, l] -= tau * w (w^H Q[j:, l]); rows < j of those
-        // columns are already final
+        if (warp == 0) to_q(j + 1);
         for (int l = j + 1 + warp; l < k; l += NW) {
             T* cl = S + (size_t)l * lds;
-            T s = zero<T>();
-            for (int r = j + 1 + lane; r < m; r += 32) fmac_(s, cj[r], cl[r]);
-            s = warp_sum(s);
-            T f = mul_(tj, add_(cl[j], s));
-            __syncwarp();
-            for (int r = j + 1 + lane; r < m; r += 32) cl[r] = sub_(cl[r], mul_(f, cj[r]));
-            if (lane == 0) cl[j] = sub_(cl[j], f);
+            const T clj = cl[j];
+            T s0 = zero<T>(), s1 = zero<T>();
+            int r = j + 1 + lane;
+            for (; r + 32 < m; r += 64) { fmac_(s0, cj[r], cl[r]); fmac_(s1, cj[r + 32], cl[r + 32]); }
+            if (r < m) fmac_(s0, cj[r], cl[r]);
+            const T s = warp_sum(add_(s0, s1));
+            const T f = mul_(tj, add_(clj, s));
+            for (r = j + 1 + lane; r < m; r += 32) cl[r] = sub_(cl[r], mul_(f, cj[r]));
+            if (lane == 0) cl[j] = sub_(clj, f);
         }
         __syncthreads();
-        // column j itself: H_j e_j = e_j - tau * w
-        for (int r = j + 1 + tid; r < m; r += BQ_THREADS) cj[r] = neg_(mul_(tj, cj[r]));
-        for (int r = tid; r < j; r += BQ_THREADS) cj[r] = zero<T>();
-        if (tid == 0) cj[j] = sub_(one<T>(), tj);
-        __syncthreads();
     }
-    for (int idx = tid; idx < m * k; idx += BQ_THREADS) {
-        int c = idx / m, r = idx - c * m;
-        d.Q[(size_t)c * d.ldq + r] = S[(size_t)c * lds + r];
-    }
+    if (warp == 0 && k > 0) to_q(0);
+    __syncthreads();
+    for (int c = warp; c < k; c += NW)
+        for (int r = lane; r < m; r += 32) d.Q[(size_t)c * d.ldq + r] = S[(size_t)c * lds + r];
     if (tid == 0 && info) info[blockIdx.x] = 0;
 }
 
 
 // ---------------------------------------------------------------------------------------
-// warp-per-block QR for tiny blocks (m, n <= 32): lane = column, the column lives in registers
-// (RMAX rows, compile-time indexed), reflector vectors are broadcast with warp shuffles.
-// No shared memory, no block barrier: this is the HBM-bound end of the batched config.
+// warp-per-block QR for tiny blocks (m, n <= 32): four blocks per 128-thread CTA, each warp owns
+// one block in its own shared-memory region.  lane = column for the reflector application (every
+// lane accumulates ITS column's dot product serially over the rows: no cross-lane reduction, the
+// reflector entries are shared-memory broadcasts), lane = row for loads/stores and the scaling of
+// v.  No block barrier at all.  This is the HBM end of the batched config: at n ~ 24 ComplexF64
+// the arithmetic intensity (2/9 n flop/B) equals the machine balance, so FP64 issue and HBM bound
+// the kernel together.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ double shfl_(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ cplx shfl_(cplx v, int src) {
     return cplx{__shfl_sync(0xffffffffu, v.re, src), __shfl_sync(0xffffffffu, v.im, src)};
 }
 
-template <typename T, int RMAX>
+template <typename T>
 __global__ void __launch_bounds__(128)
-batched_qr_warp_kernel(const QrBlockDesc<T>* __restrict__ descs, int batch) {
+batched_qr_warp_kernel(const QrBlockDesc<T>* __restrict__ descs, int batch, int cap_elems) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int blk = blockIdx.x * 4 + warp;
     if (blk >= batch) return;
     const QrBlockDesc<T> d = descs[blk];
     const int m = d.m, n = d.n, k = m < n ? m : n;
-    T a[RMAX];
-#pragma unroll
-    for (int r = 0; r < RMAX; ++r) a[r] = (r < m && lane < n) ? d.A[(size_t)lane * d.lda + r] : zero<T>();
+    const int lds = m | 1;
+    T* S = reinterpret_cast<T*>(smem_raw) + (size_t)warp * cap_elems;
+    // load (lane = row), tail norms of every column (lane = column)
+    for (int c = 0; c < n; ++c)
+        if (lane < m) S[c * lds + lane] = d.A[(size_t)c * d.lda + lane];
+    __syncwarp();
+    T* mycol = S + (lane < n ? lane : 0) * lds;
+    double mynrm = 0.0;
+    for (int r = 1; r < m; ++r) mynrm += abs2_(mycol[r]);
     T mytau = zero<T>();
     // ---- factorization ----
     for (int j = 0; j < k; ++j) {
-        // every lane forms the scalars of ITS column; lane j's are the ones used
-        double sig = 0.0;
-        T ajj = zero<T>();
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
-            if (r > j) sig += abs2_(a[r]);
-            if (r == j) ajj = a[r];
-        }
+        T* cj = S + j * lds;
+        const double sg = __shfl_sync(0xffffffffu, mynrm, j);
         double beta; T tau, scale;
-        larfgp_scalars<T>(ajj, sig, beta, tau, scale);
-        tau = shfl_(tau, j);
-        scale = shfl_(scale, j);
-        beta = __shfl_sync(0xffffffffu, beta, j);
-        // dot = w^H a_l,  w = [1; v],  v_r = a_j[r] * scale
-        T dot = ajj;
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
-            T vr = mul_(shfl_(a[r], j), scale);
-            if (r > j) fmac_(dot, vr, a[r]);
-        }
-        const T f = mul_(conj_(tau), dot);
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
-            T vr = mul_(shfl_(a[r], j), scale);   // lane j still holds the unscaled column
-            if (lane > j) {
-                if (r > j) a[r] = sub_(a[r], mul_(f, vr));
-                else if (r == j) a[r] = sub_(a[r], f);
+        larfgp_scalars<T>(cj[j], sg, beta, tau, scale);
+        __syncwarp();
+        if (lane > j && lane < m) cj[lane] = mul_(cj[lane], scale);   // v in place
+        if (lane == j) { cj[j] = mk<T>(beta); mytau = tau; }
+        __syncwarp();
+        if (lane > j && lane < n) {
+            T s0 = mycol[j], s1 = zero<T>();
+            int r = j + 1;
+            for (; r + 1 < m; r += 2) { fmac_(s0, cj[r], mycol[r]); fmac_(s1, cj[r + 1], mycol[r + 1]); }
+            if (r < m) fmac_(s0, cj[r], mycol[r]);
+            const T f = mul_(conj_(tau), add_(s0, s1));
+            mycol[j] = sub_(mycol[j], f);
+            double nrm = 0.0;
+            for (r = j + 1; r < m; ++r) {
+                const T x = sub_(mycol[r], mul_(f, cj[r]));
+                mycol[r] = x;
+                if (r > j + 1) nrm += abs2_(x);
             }
+            mynrm = nrm;   // tail norm below row j+1: consumed when this lane's column is the pivot
         }
-        if (lane == j) {
-#pragma unroll
-            for (int r = 0; r < RMAX; ++r) {
-                if (r > j) a[r] = mul_(a[r], scale);
-                else if (r == j) a[r] = mk<T>(beta);
-            }
-            mytau = tau;
-        }
+        __syncwarp();
     }
-    // ---- R out ----
-    if (d.R && lane < n) {
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r)
-            if (r < k) d.R[(size_t)lane * d.ldr + r] = (r <= lane) ? a[r] : zero<T>();
+    // ---- R out (lane = row) ----
+    if (d.R) {
+        for (int c = 0; c < n; ++c)
+            if (lane < k) d.R[(size_t)c * d.ldr + lane] = (lane <= c) ? S[c * lds + lane] : zero<T>();
     }
+    __syncwarp();
     // ---- Q in place (columns 0..k-1), backward accumulation ----
     for (int j = k - 1; j >= 0; --j) {
+        T* cj = S + j * lds;
         const T tau = shfl_(mytau, j);
-        T dot = zero<T>();
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
-            T vr = shfl_(a[r], j);
-            if (r > j) fmac_(dot, vr, a[r]);
-            else if (r == j) dot = add_(dot, a[r]);   // rows <= j of later columns were zeroed below
+        if (lane > j && lane < k) {
+            T s0 = mycol[j], s1 = zero<T>();
+            int r = j + 1;
+            for (; r + 1 < m; r += 2) { fmac_(s0, cj[r], mycol[r]); fmac_(s1, cj[r + 1], mycol[r + 1]); }
+            if (r < m) fmac_(s0, cj[r], mycol[r]);
+            const T f = mul_(tau, add_(s0, s1));
+            mycol[j] = sub_(mycol[j], f);
+            for (r = j + 1; r < m; ++r) mycol[r] = sub_(mycol[r], mul_(f, cj[r]));
         }
-        const T f = mul_(tau, dot);
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
-            T vr = shfl_(a[r], j);
-            if (lane > j && lane < k) {
-                if (r > j) a[r] = sub_(a[r], mul_(f, vr));
-                else if (r == j) a[r] = sub_(a[r], f);
-            }
+        __syncwarp();
+        if (lane < m) {
+            T x;
+            if (lane < j) x = zero<T>();
+            else if (lane == j) x = sub_(one<T>(), tau);
+            else x = neg_(mul_(tau, cj[lane]));
+            cj[lane] = x;
         }
-        if (lane == j) {
-#pragma unroll
-            for (int r = 0; r < RMAX; ++r) {
-                if (r > j) a[r] = neg_(mul_(tau, a[r]));
-                else if (r == j) a[r] = sub_(one<T>(), tau);
-                else a[r] = zero<T>();
-            }
-        }
-        // columns l > j still hold R entries in rows <= j until their own turn has passed: they
-        // were processed earlier in this backward loop and zeroed above, so nothing to do here
+        __syncwarp();
     }
-    if (lane < k) {
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r)
-            if (r < m) d.Q[(size_t)lane * d.ldq + r] = a[r];
-    }
+    for (int c = 0; c < k; ++c)
+        if (lane < m) d.Q[(size_t)c * d.ldq + lane] = S[c * lds + lane];
 }
 
 template <typename T>
-int batched_qr_warp(makb200_handle* h, int batch, int rmax, const QrBlockDesc<T>* descs) {
+int batched_qr_warp(makb200_handle* h, int batch, int cap_elems, const QrBlockDesc<T>* descs) {
     if (batch <= 0) return 0;
     const int grid = (batch + 3) / 4;
-    if (rmax <= 16) batched_qr_warp_kernel<T, 16><<<grid, 128, 0, h->stream>>>(descs, batch);
-    else if (rmax <= 24) batched_qr_warp_kernel<T, 24><<<grid, 128, 0, h->stream>>>(descs, batch);
-    else batched_qr_warp_kernel<T, 32><<<grid, 128, 0, h->stream>>>(descs, batch);
+    const size_t smem = 4 * (size_t)cap_elems * sizeof(T);
+    batched_qr_warp_kernel<T><<<grid, 128, smem, h->stream>>>(descs, batch, cap_elems);
     count_launch();
     MAK_LAUNCH_CHECK(h, "batched_qr_warp_kernel");
     return 0;
@@ -228,12 +242,12 @@ template int batched_qr_warp<cplx>(makb200_handle*, int, int, const QrBlockDesc<
 // ---------------------------------------------------------------------------------------
 constexpr int BS_THREADS = 256;
 
-template <typename T>
-__global__ void __launch_bounds__(BS_THREADS)
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT)
 batched_svd_kernel(const SvdBlockDesc<T>* __restrict__ descs, int* __restrict__ info, int max_sweeps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SvdBlockDesc<T> d = descs[blockIdx.x];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = BS_THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = NT / 32;
     const bool tr = d.m < d.n;                 // work on A^H when wide
     const int mm = tr ? d.n : d.m, nn = tr ? d.m : d.n;   // G is mm x nn, mm >= nn
     if (nn <= 0) { if (tid == 0 && info) info[blockIdx.x] = 0; return; }
@@ -244,11 +258,11 @@ batched_svd_kernel(const SvdBlockDesc<T>* __restrict__ descs, int* __restrict__ 
     int* perm = reinterpret_cast<int*>(sig + nn);                   // nn
     __shared__ int s_rot;
 
-    for (int idx = tid; idx < mm * nn; idx += BS_THREADS) {
+    for (int idx = tid; idx < mm * nn; idx += NT) {
         int c = idx / mm, r = idx - c * mm;
         G[(size_t)c * ldg + r] = tr ? conj_(d.A[(size_t)r * d.lda + c]) : d.A[(size_t)c * d.lda + r];
     }
-    for (int idx = tid; idx < nn * nn; idx += BS_THREADS) {
+    for (int idx = tid; idx < nn * nn; idx += NT) {
         int c = idx / nn, r = idx - c * nn;
         V[(size_t)c * ldv + r] = (r == c) ? one<T>() : zero<T>();
     }
@@ -312,7 +326,7 @@ batched_svd_kernel(const SvdBlockDesc<T>* __restrict__ descs, int* __restrict__ 
         if (lane == 0) sig[j] = sqrt(a);
     }
     __syncthreads();
-    for (int j = tid; j < nn; j += BS_THREADS) {
+    for (int j = tid; j < nn; j += NT) {
         int rank = 0;
         double sj = sig[j];
         for (int i = 0; i < nn; ++i) rank += (sig[i] > sj) || (sig[i] == sj && i < j);
@@ -373,7 +387,8 @@ template <typename T>
 int batched_svd_smem(makb200_handle* h, int batch, size_t max_smem_bytes, const SvdBlockDesc<T>* descs, int* info) {
     if (batch <= 0) return 0;
     if (max_smem_bytes > BQ_SMEM_BYTES) return MAKB200_ERR_WORKSPACE;
-    batched_svd_kernel<T><<<batch, BS_THREADS, max_smem_bytes, h->stream>>>(descs, info, 40);
+    if (max_smem_bytes <= 40 * 1024) batched_svd_kernel<T, 128><<<batch, 128, max_smem_bytes, h->stream>>>(descs, info, 40);
+    else batched_svd_kernel<T, 256><<<batch, 256, max_smem_bytes, h->stream>>>(descs, info, 40);
     count_launch();
     MAK_LAUNCH_CHECK(h, "batched_svd_kernel");
     return 0;
@@ -388,12 +403,12 @@ template int batched_svd_smem<cplx>(makb200_handle*, int, size_t, const SvdBlock
 // all disjoint pairs from the current (a_pp, a_qq, a_pq), column rotations of A and V, barrier, row
 // rotations of A, barrier.  Epilogue: ascending sort, reference eigh gauge (common/gauge.jl:38-45).
 // ---------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(BS_THREADS)
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT)
 batched_eigh_kernel(const EighBlockDesc<T>* __restrict__ descs, int* __restrict__ info, int max_sweeps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const EighBlockDesc<T> d = descs[blockIdx.x];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = BS_THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = NT / 32;
     const int n = d.n;
     if (n <= 0) return;
     const int ld = n | 1;
@@ -409,7 +424,7 @@ batched_eigh_kernel(const EighBlockDesc<T>* __restrict__ descs, int* __restrict_
     __shared__ int s_rot, s_big;
 
     double part = 0.0;
-    for (int idx = tid; idx < n * n; idx += BS_THREADS) {
+    for (int idx = tid; idx < n * n; idx += NT) {
         int c = idx / n, r = idx - c * n;
         T v;
         if (r < c) v = d.A[(size_t)c * d.lda + r];
@@ -488,7 +503,7 @@ batched_eigh_kernel(const EighBlockDesc<T>* __restrict__ descs, int* __restrict_
             }
             __syncthreads();
             // the pivots are now (numerically) zero and the diagonal is real: make both exact
-            for (int k = tid; k < ne / 2; k += BS_THREADS) {
+            for (int k = tid; k < ne / 2; k += NT) {
                 if (rs[k] == 0.0) continue;
                 int p, q;
                 if (k == 0) { p = ne - 1; q = step; }
@@ -505,13 +520,13 @@ batched_eigh_kernel(const EighBlockDesc<T>* __restrict__ descs, int* __restrict_
         if (s_rot == 0 || (sweep >= 5 && s_big == 0)) converged = true;
         __syncthreads();
     }
-    for (int j = tid; j < n; j += BS_THREADS) lam[j] = real_(S[(size_t)j * ld + j]);
+    for (int j = tid; j < n; j += NT) lam[j] = real_(S[(size_t)j * ld + j]);
     __syncthreads();
     // The accumulated product of ~sweeps*n^2/2 rotations drifts from unitarity by ~eps*sqrt(sweeps*n)
     // per column; one Newton-Schulz step V <- V (3I - V^H V)/2 restores it to rounding level.
     // S is free now: S <- (I - V^H V)/2.
     if (d.V) {
-        for (int idx = tid; idx < n * n; idx += BS_THREADS) {
+        for (int idx = tid; idx < n * n; idx += NT) {
             const int i = idx % n, j = idx / n;
             if (i > j) continue;
             const T* vi = V + (size_t)i * ld;
@@ -554,7 +569,7 @@ batched_eigh_kernel(const EighBlockDesc<T>* __restrict__ descs, int* __restrict_
         }
         __syncthreads();
     }
-    for (int j = tid; j < n; j += BS_THREADS) {
+    for (int j = tid; j < n; j += NT) {
         int rank = 0;
         const double lj = lam[j];
         for (int i = 0; i < n; ++i) rank += (lam[i] < lj) || (lam[i] == lj && i < j);
@@ -597,7 +612,8 @@ template <typename T>
 int batched_eigh_smem(makb200_handle* h, int batch, size_t max_smem_bytes, const EighBlockDesc<T>* descs, int* info) {
     if (batch <= 0) return 0;
     if (max_smem_bytes > BQ_SMEM_BYTES) return MAKB200_ERR_WORKSPACE;
-    batched_eigh_kernel<T><<<batch, BS_THREADS, max_smem_bytes, h->stream>>>(descs, info, 30);
+    if (max_smem_bytes <= 40 * 1024) batched_eigh_kernel<T, 128><<<batch, 128, max_smem_bytes, h->stream>>>(descs, info, 30);
+    else batched_eigh_kernel<T, 256><<<batch, 256, max_smem_bytes, h->stream>>>(descs, info, 30);
     count_launch();
     MAK_LAUNCH_CHECK(h, "batched_eigh_kernel");
     return 0;
@@ -606,17 +622,35 @@ template int batched_eigh_smem<double>(makb200_handle*, int, size_t, const EighB
 template int batched_eigh_smem<cplx>(makb200_handle*, int, size_t, const EighBlockDesc<cplx>*, int*);
 
 int batched_init(makb200_handle* h) {
-    MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_warp_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_warp_kernel<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_kernel<double, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)BQ_SMEM_BYTES));
-    MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_kernel<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_kernel<double, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)BQ_SMEM_BYTES));
-    MAK_CUDA(h, cudaFuncSetAttribute(batched_svd_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_kernel<double, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)BQ_SMEM_BYTES));
-    MAK_CUDA(h, cudaFuncSetAttribute(batched_svd_kernel<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_kernel<cplx, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)BQ_SMEM_BYTES));
-    MAK_CUDA(h, cudaFuncSetAttribute(batched_eigh_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_kernel<cplx, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)BQ_SMEM_BYTES));
-    MAK_CUDA(h, cudaFuncSetAttribute(batched_eigh_kernel<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_kernel<cplx, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)BQ_SMEM_BYTES));
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_svd_kernel<double, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)BQ_SMEM_BYTES));
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_svd_kernel<double, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)BQ_SMEM_BYTES));
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_svd_kernel<cplx, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)BQ_SMEM_BYTES));
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_svd_kernel<cplx, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)BQ_SMEM_BYTES));
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_eigh_kernel<double, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)BQ_SMEM_BYTES));
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_eigh_kernel<double, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)BQ_SMEM_BYTES));
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_eigh_kernel<cplx, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)BQ_SMEM_BYTES));
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_eigh_kernel<cplx, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)BQ_SMEM_BYTES));
     return 0;
 }
@@ -626,7 +660,10 @@ int batched_qr_smem(makb200_handle* h, int batch, size_t max_smem_elems, const Q
     if (batch <= 0) return 0;
     size_t smem = (max_smem_elems + 64) * sizeof(T);
     if (smem > BQ_SMEM_BYTES) return MAKB200_ERR_WORKSPACE;
-    batched_qr_kernel<T><<<batch, BQ_THREADS, smem, h->stream>>>(descs, info);
+    // threads by size class: small blocks -> small CTAs, many of them resident per SM
+    if (smem <= 24 * 1024) batched_qr_kernel<T, 64><<<batch, 64, smem, h->stream>>>(descs, info);
+    else if (smem <= 72 * 1024) batched_qr_kernel<T, 128><<<batch, 128, smem, h->stream>>>(descs, info);
+    else batched_qr_kernel<T, 256><<<batch, 256, smem, h->stream>>>(descs, info);
     count_launch();
     MAK_LAUNCH_CHECK(h, "batched_qr_kernel");
     return 0;

@@ -15,8 +15,8 @@ int batched_init(makb200_handle* h);
 // descs: DEVICE array; max_smem_elems: max of batched_qr_smem_elems over the batch
 template <typename T>
 int batched_qr_smem(makb200_handle* h, int batch, size_t max_smem_elems, const QrBlockDesc<T>* descs, int* info);
-// tiny blocks (m, n <= 32): one warp per block, rmax in {16, 24, 32} = row capacity of the variant
-template <typename T> int batched_qr_warp(makb200_handle* h, int batch, int rmax, const QrBlockDesc<T>* descs);
+// tiny blocks (m, n <= 32): one warp per block; cap_elems = max over the class of (m|1)*n (per-warp smem)
+template <typename T> int batched_qr_warp(makb200_handle* h, int batch, int cap_elems, const QrBlockDesc<T>* descs);
 template <typename T>
 struct SvdBlockDesc {
     int m, n, fixgauge;

@@ -238,10 +238,16 @@ static int run_pooled(makb200_handle_t* h, const std::vector<int>& big, char* wo
 // shared-memory kernel, the lock-step blocked path (panel fits one CTA), and per-block "big"
 template <typename T>
 struct QrClasses {
-    std::vector<int> warp[3], smem, blocked, big;
-    size_t max_se = 0;
+    std::vector<int> warp[3], smem[3], blocked, big;   // smem[]: by shared-memory footprint (CTA size class)
+    size_t max_se[3] = {0, 0, 0};
+    int warp_cap[3] = {0, 0, 0};                       // per-warp shared-memory elements of each warp class
     std::vector<mak::BqrStep> steps;   // column steps of the blocked class (sorted by k descending)
 };
+static int bqr_warp_max() {   // largest dimension served by the warp-per-block register kernel
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MAKB200_BQR_WARP_MAX"); v = e ? atoi(e) : 32; if (v > 32) v = 32; }
+    return v;
+}
 static int bqr_min_dim() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("MAKB200_BQR_MIN_DIM"); v = e ? atoi(e) : 96; if (v < 33) v = 33; }
@@ -255,11 +261,17 @@ static int classify_qr(int batch, const int* m, const int* n, QrClasses<T>& c) {
         const int k = m[i] < n[i] ? m[i] : n[i];
         size_t se = mak::batched_qr_smem_elems(m[i], n[i]);
         const bool fits_smem = se <= mak::batched_qr_max_smem_elems<T>();
-        if (m[i] <= 32 && n[i] <= 32 && n[i] > 0) {
-            c.warp[m[i] <= 16 ? 0 : (m[i] <= 24 ? 1 : 2)].push_back(i);
+        if (m[i] <= bqr_warp_max() && n[i] <= bqr_warp_max() && n[i] > 0) {
+            const int big_ = m[i] > n[i] ? m[i] : n[i];
+            const int wc = big_ <= 16 ? 0 : (big_ <= 24 ? 1 : 2);
+            c.warp[wc].push_back(i);
+            const int ce = (m[i] | 1) * n[i];
+            if (ce > c.warp_cap[wc]) c.warp_cap[wc] = ce;
         } else if (fits_smem && (k < bqr_min_dim() || !mak::bqr_fits<T>(m[i], n[i]))) {
-            c.smem.push_back(i);
-            if (se > c.max_se) c.max_se = se;
+            const size_t bytes = (se + 64) * sizeof(T);
+            const int cl = bytes <= 24 * 1024 ? 0 : (bytes <= 72 * 1024 ? 1 : 2);
+            c.smem[cl].push_back(i);
+            if (se > c.max_se[cl]) c.max_se[cl] = se;
         } else if (n[i] > 0 && mak::bqr_fits<T>(m[i], n[i])) {
             c.blocked.push_back(i);
         } else {
@@ -302,18 +314,66 @@ static size_t qr_batched_worksize_t(makb200_handle_t* h, int batch, const int* m
     return bytes + (c.big.empty() ? 0 : (big + 512) * NPOOL) + 1024;
 }
 
+// A batched-QR plan: classification, workspace carving and the descriptor upload done once;
+// run() only launches.  (Block-sparse tensors keep their block structure across many calls.)
+struct makb200_qr_batched_plan {
+    int dtype;
+    virtual ~makb200_qr_batched_plan() {}
+    virtual int run(makb200_handle_t* h, int* info) = 0;
+};
 template <typename T>
-static int qr_batched_t(makb200_handle_t* h, int batch, const int* m, const int* n, void* const* A, const int* lda,
-                        void* const* Q, const int* ldq, void* const* R, const int* ldr, int* info, void* work,
-                        size_t lwork) {
+struct QrPlan : makb200_qr_batched_plan {
     QrClasses<T> c;
+    int batch = 0;
+    mak::QrBlockDesc<T>* ddev = nullptr;
+    mak::BqrBlock<T>* bdev = nullptr;
+    mak::GemmProblem<T>* pdev = nullptr;
+    size_t nblocked = 0;
+    char* wbig = nullptr;
+    size_t lbig = 0;
+    std::vector<int> m, n, lda, ldq, ldr;   // host copies for the per-block "big" path
+    std::vector<void*> A, Q, R;
+
+    int run(makb200_handle_t* h, int* info) override {
+        if (info) MAK_CUDA(h, cudaMemsetAsync(info, 0, sizeof(int) * batch, h->stream));
+        size_t off = 0;
+        for (int cl = 0; cl < 3; ++cl) {
+            if (c.warp[cl].empty()) continue;
+            int rc = mak::batched_qr_warp<T>(h, (int)c.warp[cl].size(), c.warp_cap[cl], ddev + off);
+            if (rc) return rc;
+            off += c.warp[cl].size();
+        }
+        for (int cl = 0; cl < 3; ++cl) {
+            if (c.smem[cl].empty()) continue;
+            int rc = mak::batched_qr_smem<T>(h, (int)c.smem[cl].size(), c.max_se[cl], ddev + off, nullptr);
+            if (rc) return rc;
+            off += c.smem[cl].size();
+        }
+        if (nblocked) {
+            int rc = mak::batched_qr_blocked<T>(h, (int)nblocked, bdev, c.steps, pdev);
+            if (rc) return rc;
+        }
+        // blocks whose panel does not fit one CTA take the single-matrix blocked DMMA path
+        return run_pooled(h, c.big, wbig, lbig, [&](char* w, size_t lw, int i) {
+            return mak::qr_fused_t<T>(h, MAKB200_QR_COMPACT, m[i], n[i], (T*)A[i], lda[i], (T*)Q[i], ldq[i],
+                                      R[i] ? (T*)R[i] : nullptr, ldr[i], w, lw);
+        });
+    }
+};
+
+template <typename T>
+static int qr_plan_build(makb200_handle_t* h, int batch, const int* m, const int* n, void* const* A, const int* lda,
+                         void* const* Q, const int* ldq, void* const* R, const int* ldr, void* work, size_t lwork,
+                         QrPlan<T>* pl) {
+    QrClasses<T>& c = pl->c;
     int rcc = classify_qr<T>(batch, m, n, c);
     if (rcc) return rcc;
+    pl->batch = batch;
     const size_t nb_ = (size_t)(batch > 0 ? batch : 1);
     mak::Arena ar(work, lwork);
-    mak::QrBlockDesc<T>* ddev = ar.get<mak::QrBlockDesc<T>>(nb_);
-    mak::BqrBlock<T>* bdev = ar.get<mak::BqrBlock<T>>(nb_);
-    mak::GemmProblem<T>* pdev = ar.get<mak::GemmProblem<T>>(3 * nb_);
+    pl->ddev = ar.get<mak::QrBlockDesc<T>>(nb_);
+    pl->bdev = ar.get<mak::BqrBlock<T>>(nb_);
+    pl->pdev = ar.get<mak::GemmProblem<T>>(3 * nb_);
     size_t welems = 0;
     for (int i : c.blocked) {
         const int k = m[i] < n[i] ? m[i] : n[i];
@@ -321,8 +381,17 @@ static int qr_batched_t(makb200_handle_t* h, int batch, const int* m, const int*
     }
     T* wblk = ar.get<T>(welems);
     if (!ar.ok) return MAKB200_ERR_WORKSPACE;
-    if (info) MAK_CUDA(h, cudaMemsetAsync(info, 0, sizeof(int) * batch, h->stream));
-
+    pl->wbig = (char*)work + ar.off;
+    pl->lbig = lwork > ar.off ? lwork - ar.off : 0;
+    if (!c.big.empty()) {
+        pl->m.assign(m, m + batch); pl->n.assign(n, n + batch);
+        pl->lda.assign(lda, lda + batch); pl->ldq.assign(ldq, ldq + batch);
+        pl->ldr.assign(batch, 0);
+        pl->A.assign(A, A + batch); pl->Q.assign(Q, Q + batch); pl->R.assign(batch, nullptr);
+        for (int i = 0; i < batch; ++i) {
+            if (R && R[i] && ldr) { pl->R[i] = R[i]; pl->ldr[i] = ldr[i]; }
+        }
+    }
     // descriptors of every class, one pinned staging upload
     std::vector<mak::QrBlockDesc<T>> descs;
     descs.reserve(batch);
@@ -335,7 +404,7 @@ static int qr_batched_t(makb200_handle_t* h, int batch, const int* m, const int*
         descs.push_back(d);
     };
     for (int cl = 0; cl < 3; ++cl) for (int i : c.warp[cl]) push_desc(i);
-    for (int i : c.smem) push_desc(i);
+    for (int cl = 0; cl < 3; ++cl) for (int i : c.smem[cl]) push_desc(i);
     std::vector<mak::BqrBlock<T>> bl;
     bl.reserve(c.blocked.size());
     {
@@ -356,33 +425,23 @@ static int qr_batched_t(makb200_handle_t* h, int batch, const int* m, const int*
             bl.push_back(b);
         }
     }
+    pl->nblocked = bl.size();
     {
         mak::Stager st(h, descs.size() * sizeof(mak::QrBlockDesc<T>) + bl.size() * sizeof(mak::BqrBlock<T>) + 1024);
-        MAK_CUDA(h, st.put(ddev, descs.data(), descs.size() * sizeof(mak::QrBlockDesc<T>), h->stream));
-        MAK_CUDA(h, st.put(bdev, bl.data(), bl.size() * sizeof(mak::BqrBlock<T>), h->stream));
+        MAK_CUDA(h, st.put(pl->ddev, descs.data(), descs.size() * sizeof(mak::QrBlockDesc<T>), h->stream));
+        MAK_CUDA(h, st.put(pl->bdev, bl.data(), bl.size() * sizeof(mak::BqrBlock<T>), h->stream));
     }
-    size_t off = 0;
-    for (int cl = 0; cl < 3; ++cl) {
-        if (c.warp[cl].empty()) continue;
-        int rc = mak::batched_qr_warp<T>(h, (int)c.warp[cl].size(), cl == 0 ? 16 : (cl == 1 ? 24 : 32), ddev + off);
-        if (rc) return rc;
-        off += c.warp[cl].size();
-    }
-    if (!c.smem.empty()) {
-        int rc = mak::batched_qr_smem<T>(h, (int)c.smem.size(), c.max_se, ddev + off, nullptr);
-        if (rc) return rc;
-    }
-    if (!bl.empty()) {
-        int rc = mak::batched_qr_blocked<T>(h, (int)bl.size(), bdev, c.steps, pdev);
-        if (rc) return rc;
-    }
-    // blocks whose panel does not fit one CTA take the single-matrix blocked DMMA path
-    char* wbig = (char*)work + ar.off;
-    size_t lbig = lwork > ar.off ? lwork - ar.off : 0;
-    return run_pooled(h, c.big, wbig, lbig, [&](char* w, size_t lw, int i) {
-        return mak::qr_fused_t<T>(h, MAKB200_QR_COMPACT, m[i], n[i], (T*)A[i], lda[i], (T*)Q[i], ldq[i],
-                                  (R && R[i]) ? (T*)R[i] : nullptr, ldr ? ldr[i] : 0, w, lw);
-    });
+    return 0;
+}
+
+template <typename T>
+static int qr_batched_t(makb200_handle_t* h, int batch, const int* m, const int* n, void* const* A, const int* lda,
+                        void* const* Q, const int* ldq, void* const* R, const int* ldr, int* info, void* work,
+                        size_t lwork) {
+    QrPlan<T> pl;
+    int rc = qr_plan_build<T>(h, batch, m, n, A, lda, Q, ldq, R, ldr, work, lwork, &pl);
+    if (rc) return rc;
+    return pl.run(h, info);
 }
 
 extern "C" {
@@ -408,6 +467,49 @@ int makb200_qr_batched(makb200_handle_t* h, int dtype, int batch, const int* m, 
     if (!ldq) return -9;
     if (dtype == MAKB200_F64) return qr_batched_t<double>(h, batch, m, n, A, lda, Q, ldq, R, ldr, info, work, lwork);
     return qr_batched_t<cplx>(h, batch, m, n, A, lda, Q, ldq, R, ldr, info, work, lwork);
+}
+
+
+int makb200_qr_batched_plan_create(makb200_handle_t* h, int dtype, int batch, const int* m, const int* n,
+                                   void* const* A, const int* lda, void* const* Q, const int* ldq, void* const* R,
+                                   const int* ldr, void* work, size_t lwork, makb200_qr_batched_plan_t** plan) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (batch <= 0) return -3;
+    if (!m) return -4;
+    if (!n) return -5;
+    if (!A) return -6;
+    if (!lda) return -7;
+    if (!Q) return -8;
+    if (!ldq) return -9;
+    if (!plan) return -14;
+    *plan = nullptr;
+    int rc;
+    if (dtype == MAKB200_F64) {
+        auto* pl = new QrPlan<double>();
+        pl->dtype = dtype;
+        rc = qr_plan_build<double>(h, batch, m, n, A, lda, Q, ldq, R, ldr, work, lwork, pl);
+        if (rc) { delete pl; return rc; }
+        *plan = pl;
+    } else {
+        auto* pl = new QrPlan<cplx>();
+        pl->dtype = dtype;
+        rc = qr_plan_build<cplx>(h, batch, m, n, A, lda, Q, ldq, R, ldr, work, lwork, pl);
+        if (rc) { delete pl; return rc; }
+        *plan = pl;
+    }
+    return 0;
+}
+
+int makb200_qr_batched_plan_run(makb200_handle_t* h, makb200_qr_batched_plan_t* plan, int* info) {
+    if (!h) return -1;
+    if (!plan) return -2;
+    return plan->run(h, info);
+}
+
+int makb200_qr_batched_plan_destroy(makb200_qr_batched_plan_t* plan) {
+    delete plan;
+    return 0;
 }
 
 
@@ -549,9 +651,9 @@ template <typename T>
 static int svd_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int* m, const int* n, void* const* A,
                          const int* lda, void* const* S, void* const* U, const int* ldu, void* const* Vh,
                          const int* ldvh, int* info, void* work, size_t lwork) {
-    std::vector<mak::SvdBlockDesc<T>> small;
+    std::vector<mak::SvdBlockDesc<T>> small, small2;   // small: <= 40 KB of shared memory (128-thread CTAs)
     std::vector<int> big;
-    size_t max_b = 0;
+    size_t max_b = 0, max_b2 = 0;
     for (int i = 0; i < batch; ++i) {
         if (m[i] < 0 || n[i] < 0) return -5;
         if (m[i] == 0 || n[i] == 0) continue;
@@ -564,17 +666,22 @@ static int svd_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int
         d.U = U ? (T*)U[i] : nullptr; d.ldu = ldu ? ldu[i] : 0;
         d.Vh = Vh ? (T*)Vh[i] : nullptr; d.ldvh = ldvh ? ldvh[i] : 0;
         if (!d.U || !d.Vh) { d.U = nullptr; d.Vh = nullptr; }
-        small.push_back(d);
-        if (sb > max_b) max_b = sb;
+        if (sb <= 40 * 1024) { small.push_back(d); if (sb > max_b) max_b = sb; }
+        else { small2.push_back(d); if (sb > max_b2) max_b2 = sb; }
     }
     mak::Arena ar(work, lwork);
     mak::SvdBlockDesc<T>* ddev = ar.get<mak::SvdBlockDesc<T>>(batch > 0 ? batch : 1);
     if (!ar.ok) return MAKB200_ERR_WORKSPACE;
     if (info) MAK_CUDA(h, cudaMemsetAsync(info, 0, sizeof(int) * batch, h->stream));
-    if (!small.empty()) {
-        MAK_CUDA(h, cudaMemcpyAsync(ddev, small.data(), sizeof(mak::SvdBlockDesc<T>) * small.size(),
-                                    cudaMemcpyHostToDevice, h->stream));
+    if (!small.empty() || !small2.empty()) {
+        {
+            mak::Stager st(h, (small.size() + small2.size()) * sizeof(mak::SvdBlockDesc<T>) + 1024);
+            MAK_CUDA(h, st.put(ddev, small.data(), small.size() * sizeof(mak::SvdBlockDesc<T>), h->stream));
+            MAK_CUDA(h, st.put(ddev + small.size(), small2.data(), small2.size() * sizeof(mak::SvdBlockDesc<T>), h->stream));
+        }
         int rc = mak::batched_svd_smem<T>(h, (int)small.size(), max_b, ddev, nullptr);
+        if (rc) return rc;
+        rc = mak::batched_svd_smem<T>(h, (int)small2.size(), max_b2, ddev + small.size(), nullptr);
         if (rc) return rc;
     }
     // blocks too large for one CTA's shared memory: QDWH + D&C path, one block at a time
@@ -628,9 +735,9 @@ int makb200_svd_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch,
 template <typename T>
 static int eigh_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int* n, void* const* A, const int* lda,
                           void* const* W, void* const* V, const int* ldv, int* info, void* work, size_t lwork) {
-    std::vector<mak::EighBlockDesc<T>> small;
+    std::vector<mak::EighBlockDesc<T>> small, small2;
     std::vector<int> big;
-    size_t max_b = 0;
+    size_t max_b = 0, max_b2 = 0;
     for (int i = 0; i < batch; ++i) {
         if (n[i] < 0) return -5;
         if (n[i] == 0) continue;
@@ -641,19 +748,22 @@ static int eigh_batched_t(makb200_handle_t* h, int fixgauge, int batch, const in
         d.A = (const T*)A[i]; d.lda = lda[i];
         d.W = (double*)W[i];
         d.V = V ? (T*)V[i] : nullptr; d.ldv = ldv ? ldv[i] : 0;
-        small.push_back(d);
-        if (sb > max_b) max_b = sb;
+        if (sb <= 40 * 1024) { small.push_back(d); if (sb > max_b) max_b = sb; }
+        else { small2.push_back(d); if (sb > max_b2) max_b2 = sb; }
     }
     mak::Arena ar(work, lwork);
     mak::EighBlockDesc<T>* ddev = ar.get<mak::EighBlockDesc<T>>(batch > 0 ? batch : 1);
     if (!ar.ok) return MAKB200_ERR_WORKSPACE;
     if (info) MAK_CUDA(h, cudaMemsetAsync(info, 0, sizeof(int) * batch, h->stream));
-    if (!small.empty()) {
+    if (!small.empty() || !small2.empty()) {
         {
-            mak::Stager st(h, small.size() * sizeof(mak::EighBlockDesc<T>) + 512);
+            mak::Stager st(h, (small.size() + small2.size()) * sizeof(mak::EighBlockDesc<T>) + 1024);
             MAK_CUDA(h, st.put(ddev, small.data(), small.size() * sizeof(mak::EighBlockDesc<T>), h->stream));
+            MAK_CUDA(h, st.put(ddev + small.size(), small2.data(), small2.size() * sizeof(mak::EighBlockDesc<T>), h->stream));
         }
         int rc = mak::batched_eigh_smem<T>(h, (int)small.size(), max_b, ddev, nullptr);
+        if (rc) return rc;
+        rc = mak::batched_eigh_smem<T>(h, (int)small2.size(), max_b2, ddev + small.size(), nullptr);
         if (rc) return rc;
     }
     if (!big.empty() && !V) return -9;   // the single-matrix path always forms vectors

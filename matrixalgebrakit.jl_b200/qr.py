@@ -139,14 +139,26 @@ class BatchedQRPlan:
         self.Qp = VP(*[Q.data_ptr() for Q, _ in self.QRs])
         self.Rp = VP(*[(R.data_ptr() if R is not None and R.numel() else 0) for _, R in self.QRs])
         self.lw = self.h.lib.makb200_qr_batched_worksize(self.h.h, self.dt, b, self.m, self.n)
+        # the plan owns its workspace (descriptors live there between runs)
+        self.work = torch.empty(max(int(self.lw), 256), dtype=torch.uint8, device=As[0].device)
+        self.plan = C.c_void_p(0)
+        rc = self.h.lib.makb200_qr_batched_plan_create(self.h.h, self.dt, b, self.m, self.n, self.Ap, self.lda, self.Qp,
+                                                       self.ldq, self.Rp, self.ldr, _core.ptr(self.work),
+                                                       self.work.numel(), C.byref(self.plan))
+        self.h.check(rc, "makb200_qr_batched_plan_create")
 
     def run(self):
-        h = _core.Handle.get(self.As[0].device)
-        work = h.workspace(self.lw)
-        rc = h.lib.makb200_qr_batched(h.h, self.dt, self.b, self.m, self.n, self.Ap, self.lda, self.Qp, self.ldq,
-                                      self.Rp, self.ldr, C.c_void_p(0), _core.ptr(work), work.numel())
-        h.check(rc, "makb200_qr_batched")
+        rc = self.h.lib.makb200_qr_batched_plan_run(self.h.h, self.plan, C.c_void_p(0))
+        self.h.check(rc, "makb200_qr_batched_plan_run")
         return self.QRs
+
+    def __del__(self):
+        try:
+            if getattr(self, "plan", None) is not None and self.plan.value:
+                self.h.lib.makb200_qr_batched_plan_destroy(self.plan)
+                self.plan = C.c_void_p(0)
+        except Exception:
+            pass
 
 
 def qr_compact_batched_(As, QRs=None):
