@@ -323,6 +323,21 @@ def run_ours(args):
                       "launches_per_step": gl.value, "avg_launch_ms": gms.value / gl.value,
                       "alg_flops_per_launch": gflops / gl.value, "kernel_share_of_step": gms.value / step_ms,
                       "peak_source": pk[1]})
+    # DRAM traffic per launch of the same kernels from the committed ncu capture of this command
+    # (tools/traffic_summ.py -> profiles/traffic.json); None when no capture exists for the kernel
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tk = json.load(f)["kernels"]
+        for c in cands:
+            key = "gemm_kernel" if c["kernel"].startswith("gemm_kernel") else "trd_symv_kernel"
+            if key in tk and n == 8192 and set(ops) == {"eigh", "svd"}:
+                c["traffic"] = tk[key]["dram_bytes_per_launch"]
+                c["traffic_source"] = ("profiles/traffic.json: ncu dram__bytes_read+write, mean per launch over "
+                                       + tk[key].get("sample", "one step"))
+                if "alg_bytes_per_launch_same_sample" in tk[key]:
+                    c["traffic_alg_bytes_same_launches"] = tk[key]["alg_bytes_per_launch_same_sample"]
+    except (OSError, KeyError, ValueError):
+        pass
     cands.sort(key=lambda c: -c["kernel_share_of_step"])
     roofline = cands[0] if cands else None
     if roofline and len(cands) > 1:

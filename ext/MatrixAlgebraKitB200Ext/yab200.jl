@@ -168,4 +168,95 @@ function qr_batched!(As::Vector{<:StridedCuMatrix{T}}, Qs::Vector{<:StridedCuMat
     return Qs, Rs
 end
 
+# ---- batched QR plan: block structure classified and uploaded once, run! only launches ------------
+mutable struct QRBatchedPlan{T}
+    ptr::Ptr{Cvoid}
+    work::CuVector{UInt8}          # owned by the plan: descriptors live there between runs
+    keep::Any                      # the block arrays (their pointers are baked into the plan)
+end
+function qr_batched_plan(As::Vector{<:StridedCuMatrix{T}}, Qs::Vector{<:StridedCuMatrix{T}}, Rs::Vector{<:StridedCuMatrix{T}}) where {T <: B200Float}
+    b = length(As)
+    m = Cint[size(A, 1) for A in As]; n = Cint[size(A, 2) for A in As]
+    lda = Cint[max(1, stride(A, 2)) for A in As]; ldq = Cint[max(1, stride(Q, 2)) for Q in Qs]
+    ldr = Cint[length(R) > 0 ? max(1, stride(R, 2)) : 0 for R in Rs]
+    Ap = CuPtr{T}[pointer(A) for A in As]; Qp = CuPtr{T}[pointer(Q) for Q in Qs]
+    Rp = CuPtr{T}[length(R) > 0 ? pointer(R) : CU_NULL for R in Rs]
+    h = handle()
+    lw = ccall((:makb200_qr_batched_worksize, libmakb200), Csize_t, (Ptr{Cvoid}, Cint, Cint, Ptr{Cint}, Ptr{Cint}), h, dtypecode(T), b, m, n)
+    work = CuVector{UInt8}(undef, max(lw, 256))
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:makb200_qr_batched_plan_create, libmakb200), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Ptr{Cint}, Ptr{Cint}, Ptr{CuPtr{T}}, Ptr{Cint}, Ptr{CuPtr{T}}, Ptr{Cint}, Ptr{CuPtr{T}}, Ptr{Cint}, CuPtr{UInt8}, Csize_t, Ref{Ptr{Cvoid}}),
+        h, dtypecode(T), b, m, n, Ap, lda, Qp, ldq, Rp, ldr, work, length(work), ref)
+    chkargsok(rc, "makb200_qr_batched_plan_create")
+    plan = QRBatchedPlan{T}(ref[], work, (As, Qs, Rs))
+    finalizer(p -> ccall((:makb200_qr_batched_plan_destroy, libmakb200), Cint, (Ptr{Cvoid},), p.ptr), plan)
+    return plan
+end
+function run!(plan::QRBatchedPlan)
+    rc = ccall((:makb200_qr_batched_plan_run, libmakb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, CuPtr{Cint}), handle(), plan.ptr, CU_NULL)
+    chkargsok(rc, "makb200_qr_batched_plan_run")
+    return plan.keep[2], plan.keep[3]
+end
+
+# ---- batched svd_compact! / eigh_full! over a vector of blocks (per-block semantics incl. gauge) ---
+function svd_batched!(As::Vector{<:StridedCuMatrix{T}}, Us::Vector{<:StridedCuMatrix{T}}, Ss::Vector{<:StridedCuVector{Float64}},
+        Vhs::Vector{<:StridedCuMatrix{T}}; fixgauge::Bool = true) where {T <: B200Float}
+    b = length(As)
+    m = Cint[size(A, 1) for A in As]; n = Cint[size(A, 2) for A in As]
+    lda = Cint[max(1, stride(A, 2)) for A in As]; ldu = Cint[max(1, stride(U, 2)) for U in Us]
+    ldvh = Cint[max(1, stride(V, 2)) for V in Vhs]
+    Ap = CuPtr{T}[pointer(A) for A in As]; Up = CuPtr{T}[pointer(U) for U in Us]
+    Sp = CuPtr{Float64}[pointer(S) for S in Ss]; Vp = CuPtr{T}[pointer(V) for V in Vhs]
+    h = handle()
+    lw = ccall((:makb200_svd_batched_worksize, libmakb200), Csize_t, (Ptr{Cvoid}, Cint, Cint, Ptr{Cint}, Ptr{Cint}), h, dtypecode(T), b, m, n)
+    with_workspace(lw) do work
+        rc = ccall((:makb200_svd_batched, libmakb200), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cint}, Ptr{Cint}, Ptr{CuPtr{T}}, Ptr{Cint}, Ptr{CuPtr{Float64}}, Ptr{CuPtr{T}}, Ptr{Cint},
+             Ptr{CuPtr{T}}, Ptr{Cint}, CuPtr{Cint}, CuPtr{UInt8}, Csize_t),
+            h, dtypecode(T), fixgauge, b, m, n, Ap, lda, Sp, Up, ldu, Vp, ldvh, CU_NULL, work, lw)
+        chkargsok(rc, "makb200_svd_batched")
+    end
+    return Us, Ss, Vhs
+end
+function eigh_batched!(As::Vector{<:StridedCuMatrix{T}}, Ws::Vector{<:StridedCuVector{Float64}}, Vs::Vector{<:StridedCuMatrix{T}};
+        fixgauge::Bool = true) where {T <: B200Float}
+    b = length(As)
+    n = Cint[checksquare(A) for A in As]
+    lda = Cint[max(1, stride(A, 2)) for A in As]; ldv = Cint[max(1, stride(V, 2)) for V in Vs]
+    Ap = CuPtr{T}[pointer(A) for A in As]; Wp = CuPtr{Float64}[pointer(W) for W in Ws]; Vp = CuPtr{T}[pointer(V) for V in Vs]
+    h = handle()
+    lw = ccall((:makb200_eigh_batched_worksize, libmakb200), Csize_t, (Ptr{Cvoid}, Cint, Cint, Ptr{Cint}), h, dtypecode(T), b, n)
+    with_workspace(lw) do work
+        rc = ccall((:makb200_eigh_batched, libmakb200), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cint}, Ptr{CuPtr{T}}, Ptr{Cint}, Ptr{CuPtr{Float64}}, Ptr{CuPtr{T}}, Ptr{Cint}, CuPtr{Cint},
+             CuPtr{UInt8}, Csize_t),
+            h, dtypecode(T), fixgauge, b, n, Ap, lda, Wp, Vp, ldv, CU_NULL, work, lw)
+        chkargsok(rc, "makb200_eigh_batched")
+    end
+    return Ws, Vs
+end
+
+# ---- TSQR local step (row shard of a tall-skinny matrix) and adjoint (lq_via_qr!, svd_via_adjoint!) -
+function tsqr_local!(A::StridedCuMatrix{T}, Q::StridedCuMatrix{T}, R::StridedCuMatrix{T}) where {T <: B200Float}
+    m, n = size(A); h = handle()
+    lw = ccall((:makb200_tsqr_local_worksize, libmakb200), Csize_t, (Ptr{Cvoid}, Cint, Cint, Cint), h, dtypecode(T), m, n)
+    info = CUDA.zeros(Cint, 1)
+    with_workspace(lw) do work
+        rc = ccall((:makb200_tsqr_local, libmakb200), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Cint, CuPtr{T}, Cint, CuPtr{T}, Cint, CuPtr{T}, Cint, CuPtr{UInt8}, Csize_t, CuPtr{Cint}),
+            h, dtypecode(T), m, n, A, max(1, stride(A, 2)), Q, max(1, stride(Q, 2)), R, max(1, stride(R, 2)), work, lw, info)
+        chkargsok(rc, "makb200_tsqr_local")
+    end
+    return Q, R, info        # info[1] != 0: Cholesky breakdown (kappa too large for CholeskyQR2); read lazily
+end
+function adjoint!(B::StridedCuMatrix{T}, A::StridedCuMatrix{T}) where {T <: B200Float}
+    m, n = size(A)
+    size(B) == (n, m) || throw(DimensionMismatch("adjoint!: B must be $n x $m"))
+    rc = ccall((:makb200_adjoint, libmakb200), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, CuPtr{T}, Cint, CuPtr{T}, Cint),
+        handle(), dtypecode(T), m, n, A, max(1, stride(A, 2)), B, max(1, stride(B, 2)))
+    chkargsok(rc, "makb200_adjoint")
+    return B
+end
+
 end # module

@@ -25,3 +25,5 @@ from .svd import BatchedSVDPlan
 from .eigh import BatchedEighPlan, eigh_full_batched_
 from .orthnull import (adjoint_, left_null, left_null_, left_orth, left_orth_, lq_compact, lq_compact_, lq_full, lq_full_,
                        lq_null, lq_null_, qr_null, qr_null_, right_null, right_null_, right_orth, right_orth_)
+from . import partition  # noqa: E402,F401
+from .partition import gather_block_info, lpt_partition, my_blocks  # noqa: E402,F401

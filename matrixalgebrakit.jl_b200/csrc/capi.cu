@@ -9,6 +9,9 @@
 #include "polar.cuh"
 #include <vector>
 #include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <thread>
 
 using mak::cplx;
 
@@ -45,8 +48,9 @@ int makb200_create(makb200_handle_t** out, int device) {
     h->stage = nullptr;
     h->stage_bytes = 0;
     if (cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming) != cudaSuccess) { delete h; return MAKB200_ERR_CUDA; }
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 8; ++i)
         if (cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return MAKB200_ERR_CUDA; }
+    for (int i = 0; i < MAK_NPOOL; ++i) {
         if (cudaEventCreateWithFlags(&h->pool_ev[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return MAKB200_ERR_CUDA; }
         if (cudaStreamCreateWithFlags(&h->pool[i], cudaStreamNonBlocking) != cudaSuccess) { delete h; return MAKB200_ERR_CUDA; }
     }
@@ -64,7 +68,8 @@ int makb200_destroy(makb200_handle_t* h) {
     cudaStreamDestroy(h->aux_stream);
     cudaEventDestroy(h->stage_ev);
     if (h->stage) cudaFreeHost(h->stage);
-    for (int i = 0; i < 8; ++i) { cudaEventDestroy(h->ev[i]); cudaEventDestroy(h->pool_ev[i]); cudaStreamDestroy(h->pool[i]); }
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < MAK_NPOOL; ++i) { cudaEventDestroy(h->pool_ev[i]); cudaStreamDestroy(h->pool[i]); }
     delete h;
     return 0;
 }
@@ -208,21 +213,84 @@ int makb200_orgqr(makb200_handle_t* h, int dtype, int m, int ncols, int k, const
 // ---- batched -----------------------------------------------------------------------
 // Run `fn(slot_work, slot_lwork, i)` for every index in `big` round-robin over the handle's stream
 // pool (the per-block paths are launch-latency bound, so independent blocks overlap almost freely).
-constexpr int NPOOL = 8;
+constexpr int NPOOL = MAK_NPOOL;
+static int env_int(const char* name, int dflt, int lo, int hi) {
+    const char* e = getenv(name);
+    int v = e ? atoi(e) : dflt;
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+static int pool_streams() { static int v = env_int("MAKB200_POOL_STREAMS", 32, 1, NPOOL); return v; }
+static int pool_threads() {   // host threads feeding the stream pool (1 = single-threaded round robin)
+    static int v = -1;
+    if (v < 0) {
+        v = env_int("MAKB200_POOL_THREADS", 16, 1, NPOOL);
+        unsigned hc = std::thread::hardware_concurrency();
+        if (hc > 0 && (unsigned)v > hc) v = (int)hc;
+    }
+    return v;
+}
+// Workspace of a pooled call: one slice per stream.
+static size_t pooled_worksize(size_t per_block, size_t nbig) {
+    const size_t np = nbig < (size_t)pool_streams() ? nbig : (size_t)pool_streams();
+    return (per_block + 512) * np;
+}
+
 template <typename F>
 static int run_pooled(makb200_handle_t* h, const std::vector<int>& big, char* work, size_t lwork, F fn) {
     if (big.empty()) return 0;
     cudaStream_t main = h->stream;
-    const int np = (int)big.size() < NPOOL ? (int)big.size() : NPOOL;
+    const int np = (int)big.size() < pool_streams() ? (int)big.size() : pool_streams();
     const size_t slice = (lwork / np) & ~(size_t)255;
     MAK_CUDA(h, cudaEventRecord(h->pool_ev[0], main));
     for (int s = 0; s < np; ++s) MAK_CUDA(h, cudaStreamWaitEvent(h->pool[s], h->pool_ev[0], 0));
     h->no_lookahead = true;
     int rc = 0;
-    for (size_t idx = 0; idx < big.size() && rc == 0; ++idx) {
-        const int s = (int)(idx % np);
-        h->stream = h->pool[s];
-        rc = fn(work + s * slice, slice, big[idx]);
+    // The per-block paths are serial chains of thousands of tiny launches: one stream keeps only a
+    // sliver of the GPU busy and ONE host thread cannot feed many streams (~2 us per launch).  So the
+    // pool has up to 32 streams fed by up to 16 host threads; thread t owns streams t, t+nt, ... and
+    // alternates between them block by block, each stream with its own workspace slice and each thread
+    // with a private copy of the handle.  Blocks are handed out dynamically.  The first block runs on
+    // the calling thread so that every lazily configured kernel attribute is set before the fan-out.
+    const bool timing = mak::g_clock_gemm.on || mak::g_clock_dots.on || mak::g_clock_w.on ||
+                        (getenv("MAKB200_PROFILE") && getenv("MAKB200_PROFILE")[0] == '1');
+    const int nthreads = timing ? 1 : (pool_threads() < np ? pool_threads() : np);
+    size_t first = 0;
+    if (nthreads > 1) {
+        h->stream = h->pool[0];
+        rc = fn(h, work, slice, big[0]);
+        first = 1;
+    }
+    if (nthreads > 1 && rc == 0 && big.size() > 1) {
+        std::atomic<size_t> next(first);
+        std::vector<int> rcs(nthreads, 0);
+        std::vector<makb200_handle> hs(nthreads, *h);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t) {
+            hs[t].no_lookahead = true;
+            hs[t].err[0] = 0;
+            th.emplace_back([&, t]() {
+                if (cudaSetDevice(h->device) != cudaSuccess) { rcs[t] = MAKB200_ERR_CUDA; return; }
+                int s = t;
+                for (;;) {
+                    const size_t idx = next.fetch_add(1);
+                    if (idx >= big.size()) break;
+                    hs[t].stream = h->pool[s];
+                    const int r = fn(&hs[t], work + s * slice, slice, big[idx]);
+                    if (r) { rcs[t] = r; break; }
+                    s += nthreads;
+                    if (s >= np) s = t;
+                }
+            });
+        }
+        for (auto& x : th) x.join();
+        for (int t = 0; t < nthreads && rc == 0; ++t)
+            if (rcs[t]) { rc = rcs[t]; memcpy(h->err, hs[t].err, sizeof(h->err)); }
+    } else if (rc == 0) {
+        for (size_t idx = first; idx < big.size() && rc == 0; ++idx) {
+            const int s = (int)(idx % np);
+            h->stream = h->pool[s];
+            rc = fn(h, work + s * slice, slice, big[idx]);
+        }
     }
     h->stream = main;
     h->no_lookahead = false;
@@ -241,7 +309,7 @@ struct QrClasses {
     std::vector<int> warp[3], smem[3], blocked, big;   // smem[]: by shared-memory footprint (CTA size class)
     size_t max_se[3] = {0, 0, 0};
     int warp_cap[3] = {0, 0, 0};                       // per-warp shared-memory elements of each warp class
-    std::vector<mak::BqrStep> steps;   // column steps of the blocked class (sorted by k descending)
+    mak::BqrSchedule sched;            // two-level column schedule of the blocked class (sorted by k descending)
 };
 static int bqr_warp_max() {   // largest dimension served by the warp-per-block register kernel
     static int v = -1;
@@ -283,27 +351,20 @@ static int classify_qr(int batch, const int* m, const int* n, QrClasses<T>& c) {
     });
     std::vector<int> ms, ns, ks;
     for (int i : c.blocked) { ms.push_back(m[i]); ns.push_back(n[i]); ks.push_back(m[i] < n[i] ? m[i] : n[i]); }
-    c.steps = mak::bqr_steps<T>(ms, ns, ks);
+    c.sched = mak::bqr_schedule<T>(ms, ns, ks);
     return 0;
 }
-template <typename T>
-static int bqr_nsteps_of(const std::vector<mak::BqrStep>& steps, int k) {
-    int c = 0;
-    for (const auto& st : steps) if (st.j0 < k) ++c;
-    return c;
-}
-
 template <typename T>
 static size_t qr_batched_worksize_t(makb200_handle_t* h, int batch, const int* m, const int* n) {
     QrClasses<T> c;
     if (classify_qr<T>(batch, m, n, c)) return 0;
     const size_t nb_ = (size_t)(batch > 0 ? batch : 1);
     size_t bytes = mak::align_up(sizeof(mak::QrBlockDesc<T>) * nb_, 256) + mak::align_up(sizeof(mak::BqrBlock<T>) * nb_, 256) +
-                   mak::align_up(sizeof(mak::GemmProblem<T>) * 3 * nb_, 256);
+                   mak::align_up(sizeof(mak::GemmProblem<T>) * 4 * nb_, 256);
     size_t welems = 0;
     for (int i : c.blocked) {
         const int k = m[i] < n[i] ? m[i] : n[i];
-        welems += mak::bqr_block_work_elems<T>(m[i], n[i], k, bqr_nsteps_of<T>(c.steps, k));
+        welems += mak::bqr_block_work_elems<T>(c.sched, m[i], n[i], k);
     }
     bytes += mak::align_up(welems * sizeof(T), 256);
     size_t big = 0;
@@ -311,7 +372,7 @@ static size_t qr_batched_worksize_t(makb200_handle_t* h, int batch, const int* m
         size_t w = mak::qr_worksize_t<T>(h, m[i], n[i], m[i] < n[i] ? m[i] : n[i]);
         if (w > big) big = w;
     }
-    return bytes + (c.big.empty() ? 0 : (big + 512) * NPOOL) + 1024;
+    return bytes + (c.big.empty() ? 0 : pooled_worksize(big, c.big.size())) + 1024;
 }
 
 // A batched-QR plan: classification, workspace carving and the descriptor upload done once;
@@ -350,12 +411,12 @@ struct QrPlan : makb200_qr_batched_plan {
             off += c.smem[cl].size();
         }
         if (nblocked) {
-            int rc = mak::batched_qr_blocked<T>(h, (int)nblocked, bdev, c.steps, pdev);
+            int rc = mak::batched_qr_blocked<T>(h, (int)nblocked, bdev, c.sched, pdev);
             if (rc) return rc;
         }
         // blocks whose panel does not fit one CTA take the single-matrix blocked DMMA path
-        return run_pooled(h, c.big, wbig, lbig, [&](char* w, size_t lw, int i) {
-            return mak::qr_fused_t<T>(h, MAKB200_QR_COMPACT, m[i], n[i], (T*)A[i], lda[i], (T*)Q[i], ldq[i],
+        return run_pooled(h, c.big, wbig, lbig, [&](makb200_handle_t* hh, char* w, size_t lw, int i) {
+            return mak::qr_fused_t<T>(hh, MAKB200_QR_COMPACT, m[i], n[i], (T*)A[i], lda[i], (T*)Q[i], ldq[i],
                                       R[i] ? (T*)R[i] : nullptr, ldr[i], w, lw);
         });
     }
@@ -373,11 +434,11 @@ static int qr_plan_build(makb200_handle_t* h, int batch, const int* m, const int
     mak::Arena ar(work, lwork);
     pl->ddev = ar.get<mak::QrBlockDesc<T>>(nb_);
     pl->bdev = ar.get<mak::BqrBlock<T>>(nb_);
-    pl->pdev = ar.get<mak::GemmProblem<T>>(3 * nb_);
+    pl->pdev = ar.get<mak::GemmProblem<T>>(4 * nb_);
     size_t welems = 0;
     for (int i : c.blocked) {
         const int k = m[i] < n[i] ? m[i] : n[i];
-        welems += mak::bqr_block_work_elems<T>(m[i], n[i], k, bqr_nsteps_of<T>(c.steps, k));
+        welems += mak::bqr_block_work_elems<T>(c.sched, m[i], n[i], k);
     }
     T* wblk = ar.get<T>(welems);
     if (!ar.ok) return MAKB200_ERR_WORKSPACE;
@@ -408,20 +469,15 @@ static int qr_plan_build(makb200_handle_t* h, int batch, const int* m, const int
     std::vector<mak::BqrBlock<T>> bl;
     bl.reserve(c.blocked.size());
     {
-        auto up = [](size_t e) { return (e + 15) / 16 * 16; };
         T* p = wblk;
         for (int i : c.blocked) {
             const int k = m[i] < n[i] ? m[i] : n[i];
-            const size_t wc = (size_t)(n[i] > k ? n[i] : k);
             mak::BqrBlock<T> b;
             b.m = m[i]; b.n = n[i]; b.k = k;
             b.A = (T*)A[i]; b.lda = lda[i];
             b.Q = (T*)Q[i]; b.ldq = ldq[i];
             b.R = (R && R[i]) ? (T*)R[i] : nullptr; b.ldr = ldr ? ldr[i] : 0;
-            b.Vw = p; p += up((size_t)m[i] * mak::BQR_NB);
-            b.W = p;  p += up((size_t)mak::BQR_NB * wc);
-            b.W2 = p; p += up((size_t)mak::BQR_NB * wc);
-            b.Tf = p; p += up((size_t)mak::BQR_NB * mak::BQR_NB * bqr_nsteps_of<T>(c.steps, k));
+            mak::bqr_carve_block<T>(c.sched, b, p);
             bl.push_back(b);
         }
     }
@@ -687,8 +743,8 @@ static int svd_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int
     // blocks too large for one CTA's shared memory: QDWH + D&C path, one block at a time
     char* wbig = (char*)work + ar.off;
     size_t lbig = lwork > ar.off ? lwork - ar.off : 0;
-    return run_pooled(h, big, wbig, lbig, [&](char* w, size_t lw, int i) {
-        return mak::svd_t<T>(h, m[i], n[i], (T*)A[i], lda[i], (double*)S[i], U ? (T*)U[i] : nullptr, ldu ? ldu[i] : 0,
+    return run_pooled(h, big, wbig, lbig, [&](makb200_handle_t* hh, char* w, size_t lw, int i) {
+        return mak::svd_t<T>(hh, m[i], n[i], (T*)A[i], lda[i], (double*)S[i], U ? (T*)U[i] : nullptr, ldu ? ldu[i] : 0,
                              Vh ? (T*)Vh[i] : nullptr, ldvh ? ldvh[i] : 0, fixgauge, 2.2e-16, w, lw, nullptr);
     });
 }
@@ -698,16 +754,17 @@ extern "C" {
 size_t makb200_svd_batched_worksize(makb200_handle_t* h, int dtype, int batch, const int* m, const int* n) {
     if (!h || !dtype_ok(dtype) || batch < 0 || (batch > 0 && (!m || !n))) return 0;
     size_t esz = dtype == MAKB200_F64 ? sizeof(double) : sizeof(cplx);
-    size_t bytes = mak::align_up(sizeof(mak::SvdBlockDesc<cplx>) * (size_t)(batch > 0 ? batch : 1), 256), big = 0;
+    size_t bytes = mak::align_up(sizeof(mak::SvdBlockDesc<cplx>) * (size_t)(batch > 0 ? batch : 1), 256), big = 0, nbig = 0;
     for (int i = 0; i < batch; ++i) {
         if (m[i] <= 0 || n[i] <= 0) continue;
         if (mak::batched_svd_smem_bytes(m[i], n[i], esz) > mak::batched_svd_max_smem_bytes()) {
             size_t w = dtype == MAKB200_F64 ? mak::svd_worksize_t<double>(h, m[i], n[i])
                                             : mak::svd_worksize_t<cplx>(h, m[i], n[i]);
             if (w > big) big = w;
+            ++nbig;
         }
     }
-    return bytes + (big + 512) * NPOOL + 256;
+    return bytes + pooled_worksize(big, nbig) + 256;
 }
 
 int makb200_svd_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch, const int* m, const int* n,
@@ -769,8 +826,8 @@ static int eigh_batched_t(makb200_handle_t* h, int fixgauge, int batch, const in
     if (!big.empty() && !V) return -9;   // the single-matrix path always forms vectors
     char* wbig = (char*)work + ar.off;
     size_t lbig = lwork > ar.off ? lwork - ar.off : 0;
-    return run_pooled(h, big, wbig, lbig, [&](char* w, size_t lw, int i) {
-        return mak::eigh_t<T>(h, n[i], (T*)A[i], lda[i], (double*)W[i], (T*)V[i], ldv[i], fixgauge, w, lw, nullptr);
+    return run_pooled(h, big, wbig, lbig, [&](makb200_handle_t* hh, char* w, size_t lw, int i) {
+        return mak::eigh_t<T>(hh, n[i], (T*)A[i], lda[i], (double*)W[i], (T*)V[i], ldv[i], fixgauge, w, lw, nullptr);
     });
 }
 
@@ -779,7 +836,7 @@ extern "C" {
 size_t makb200_eigh_batched_worksize(makb200_handle_t* h, int dtype, int batch, const int* n) {
     if (!h || !dtype_ok(dtype) || batch < 0 || (batch > 0 && !n)) return 0;
     size_t esz = dtype == MAKB200_F64 ? sizeof(double) : sizeof(cplx);
-    size_t bytes = mak::align_up(sizeof(mak::EighBlockDesc<cplx>) * (size_t)(batch > 0 ? batch : 1), 256), big = 0;
+    size_t bytes = mak::align_up(sizeof(mak::EighBlockDesc<cplx>) * (size_t)(batch > 0 ? batch : 1), 256), big = 0, nbig = 0;
     bool any = false;
     for (int i = 0; i < batch; ++i) {
         if (n[i] <= 0) continue;
@@ -787,9 +844,10 @@ size_t makb200_eigh_batched_worksize(makb200_handle_t* h, int dtype, int batch, 
             size_t w = dtype == MAKB200_F64 ? mak::eigh_worksize_t<double>(h, n[i]) : mak::eigh_worksize_t<cplx>(h, n[i]);
             if (w > big) big = w;
             any = true;
+            ++nbig;
         }
     }
-    return bytes + (any ? (big + 512) * NPOOL : 0) + 256;
+    return bytes + (any ? pooled_worksize(big, nbig) : 0) + 256;
 }
 
 int makb200_eigh_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch, const int* n, void* const* A,

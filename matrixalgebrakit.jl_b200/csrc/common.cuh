@@ -143,6 +143,7 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
 // ---------------------------------------------------------------------------------------
 }  // namespace mak
 
+constexpr int MAK_NPOOL = 32;
 struct makb200_handle {
     int device;
     cudaStream_t stream;
@@ -150,8 +151,8 @@ struct makb200_handle {
     int max_cluster;  // largest usable cluster size for the panel kernel
     cudaStream_t aux_stream;   // internal second stream (look-ahead in the blocked QR)
     cudaEvent_t ev[8];         // fork/join and look-ahead events
-    cudaStream_t pool[8];      // stream pool: mid-size blocks of a batch run concurrently
-    cudaEvent_t pool_ev[8];
+    cudaStream_t pool[32];     // stream pool: mid-size blocks of a batch run concurrently (MAK_NPOOL)
+    cudaEvent_t pool_ev[32];
     bool no_lookahead;         // set while a pooled call is in flight (aux stream/events are shared)
     void* stage;               // pinned host staging for descriptor uploads (batched entry points)
     size_t stage_bytes;
@@ -179,7 +180,7 @@ inline int cuda_fail(makb200_handle* h, cudaError_t e, const char* where) {
 // process-wide count of kernels launched by this library (bench.py reports it as gpu_launches)
 extern unsigned long long g_launches;
 extern double g_gemm_flops;
-inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }
+inline void count_launch(int n = 1) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }  // pooled host threads
 
 // per-kernel-class device-time accumulation for the roofline line of bench.py
 // (enabled through makb200_kernel_timing(1); CUDA events on the launching stream)

@@ -366,7 +366,7 @@ cudaError_t gemm(cudaStream_t stream, int num_sms, int opa, int opb, int m, int 
         if (splitk < 2) splitk = 1;
     }
     grid.z = splitk;
-    g_gemm_flops += 2.0 * (double)m * (double)n * (double)k * (is_cplx<T>::value ? 4.0 : 1.0);
+    if (g_clock_gemm.on) g_gemm_flops += 2.0 * (double)m * (double)n * (double)k * (is_cplx<T>::value ? 4.0 : 1.0);
     cudaError_t e = dispatch<T>(stream, opa != MAKB200_OP_N, opb != MAKB200_OP_N, grid, p, nullptr, splitk, (T*)ws);
     if (e != cudaSuccess) return e;
     if (splitk > 1) {

@@ -178,3 +178,16 @@ def test_eigh_batched_vs_oracle(dtype):
         if a.shape[0] <= 79 and i != 8:
             assert np.array_equal(makb200.to_numpy(As[i]), a)   # small blocks are not destroyed
         _check(a, D.cpu().numpy(), makb200.to_numpy(V), vec_cmp=(i < len(ns)))
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_eigh_batched_pooled_threads(dtype):
+    """Blocks beyond the one-CTA limit fan out over the stream pool, one host thread per stream."""
+    import makb200
+    rng = np.random.default_rng(12)
+    ns = [int(v) for v in rng.integers(90, 220, size=20)] + [20, 48]
+    As0 = [O.rand_hermitian(n, dtype, seed=800 + i) for i, n in enumerate(ns)]
+    DVs = makb200.eigh_full_batched_([makb200.to_device(a) for a in As0], check=False)
+    torch.cuda.synchronize()
+    for a, (D, V) in zip(As0, DVs):
+        _check(a, D.cpu().numpy(), makb200.to_numpy(V), vec_cmp=False)

@@ -176,3 +176,19 @@ def test_svd_batched_vs_oracle(dtype):
         So = O.svd_vals(a)
         k = min(5, len(So))
         np.testing.assert_allclose(S.cpu().numpy(), So[:k], rtol=1e-11)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_svd_batched_pooled_threads(dtype):
+    """Many blocks too large for the one-CTA kernel: they fan out over the stream pool with one host
+    thread per stream (capi.cu: run_pooled); ragged sizes so the threads finish out of order."""
+    import makb200
+    rng = np.random.default_rng(11)
+    dims = [int(v) for v in rng.integers(90, 200, size=20)]
+    sizes = [(d, d) for d in dims[:14]] + [(d, d - 30) for d in dims[14:17]] + [(d - 30, d) for d in dims[17:]]
+    sizes += [(24, 24), (40, 33)]          # small ones mixed in (one-CTA Jacobi kernel)
+    As0 = [O.randn_matrix(m, n, dtype, seed=700 + i) for i, (m, n) in enumerate(sizes)]
+    outs = makb200.svd_compact_batched_([makb200.to_device(a) for a in As0])
+    torch.cuda.synchronize()
+    for a, (U, S, Vh) in zip(As0, outs):
+        _check_svd(a, makb200.to_numpy(U), S.cpu().numpy(), makb200.to_numpy(Vh), vec_cmp=False)

@@ -26,13 +26,9 @@ ops = (sys.argv[3] if len(sys.argv) > 3 else "qr,svd").split(",")
 rng = np.random.Generator(np.random.PCG64(4))
 dims = np.rint(16 * 32 ** rng.random(nblocks)).astype(int)
 dims = dims[dims <= maxdim]
-# LPT partition on cost ~ n^3
-order = np.argsort(-dims.astype(np.float64) ** 3, kind="stable")
-loads = np.zeros(world); owner = np.zeros(len(dims), dtype=int)
-for i in order:
-    r = int(np.argmin(loads)); owner[i] = r; loads[r] += float(dims[i]) ** 3
+# LPT partition (makb200.partition): no data-path collective
+owner, imbalance = makb200.lpt_partition([(int(n), int(n)) for n in dims], world)
 mine = dims[owner == rank]
-imbalance = float(loads.max() / loads.mean())
 g = torch.Generator(device=dev); g.manual_seed(4 + rank)
 As0 = [torch.randn((n, n), dtype=torch.complex128, device=dev, generator=g).t() for n in mine]
 buckets = [(16, 32), (33, 64), (65, 128), (129, 256), (257, 512)]
