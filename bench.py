@@ -192,14 +192,12 @@ def run_ours(args):
     n = args.n
     lib = makb200._lib.load()
 
-    # synthetic inputs, generated on the host with the oracle's generator, seed 2+rank
-    from oracle import mak_oracle as O
+    # synthetic inputs: i.i.d. N(0,1), numpy PCG64, seed 2+rank; eigh input = (G+G^T)/2
+    # (generated here: the product arm does not touch oracle/)
     host_in = {}
     for op in ops:
-        if op == "eigh":
-            host_in[op] = O.rand_hermitian(n, "f64", seed=2 + rank)
-        else:
-            host_in[op] = O.randn_matrix(n, n, "f64", seed=2 + rank)
+        G = np.asfortranarray(np.random.Generator(np.random.PCG64(2 + rank)).standard_normal((n, n)).T)
+        host_in[op] = np.asfortranarray((G + G.T) / 2) if op == "eigh" else G
     pinned = {op: torch.from_numpy(np.ascontiguousarray(a.T)).pin_memory() for op, a in host_in.items()}
     dev_in = {op: t.to(dev).t() for op, t in pinned.items()}
     A = makb200.colmajor_empty(n, n, torch.float64, dev)

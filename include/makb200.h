@@ -161,6 +161,13 @@ int makb200_svd(makb200_handle_t* h, int dtype, int fixgauge, int m, int n, void
 size_t makb200_tsqr_local_worksize(makb200_handle_t* h, int dtype, int m, int n);
 int makb200_tsqr_local(makb200_handle_t* h, int dtype, int m, int n, void* A, int lda, void* Q,
                        int ldq, void* R, int ldr, void* work, size_t lwork, int* info_dev);
+/* Same with `nshift` (0..3) shifted-CholeskyQR preconditioning passes in front (Fukaya et al. 2020:
+ * G + sI, s = 11(mn + n(n+1)) u ||A||_F^2): every pass divides kappa by ~1/sqrt(11(mn+n^2)u), so
+ * nshift = 1 covers kappa <~ 1e10 and nshift = 2 any numerically full-rank input, at (2+nshift)/2
+ * the cost.  Same workspace size as makb200_tsqr_local. */
+int makb200_tsqr_local_ex(makb200_handle_t* h, int dtype, int m, int n, void* A, int lda, void* Q,
+                          int ldq, void* R, int ldr, int nshift, void* work, size_t lwork,
+                          int* info_dev);
 
 /* -- batched svd_compact! of many small blocks -------------------------------------------------
  * New capability (reference: commented-out gesvdjBatched stubs yacusolver.jl:506-569).

@@ -683,8 +683,8 @@ size_t makb200_tsqr_local_worksize(makb200_handle_t* h, int dtype, int m, int n)
     return dtype == MAKB200_F64 ? mak::cholqr2_worksize_t<double>(h, m, n) : mak::cholqr2_worksize_t<cplx>(h, m, n);
 }
 
-int makb200_tsqr_local(makb200_handle_t* h, int dtype, int m, int n, void* A, int lda, void* Q, int ldq, void* R,
-                       int ldr, void* work, size_t lwork, int* info_dev) {
+int makb200_tsqr_local_ex(makb200_handle_t* h, int dtype, int m, int n, void* A, int lda, void* Q, int ldq, void* R,
+                          int ldr, int nshift, void* work, size_t lwork, int* info_dev) {
     if (!h) return -1;
     if (!dtype_ok(dtype)) return -2;
     if (m < 0) return -3;
@@ -692,12 +692,20 @@ int makb200_tsqr_local(makb200_handle_t* h, int dtype, int m, int n, void* A, in
     if (lda < maxi(1, m)) return -6;
     if (ldq < maxi(1, m)) return -8;
     if (R && ldr > 0 && ldr < maxi(1, n)) return -10;
+    if (nshift < 0 || nshift > 3) return -11;
     if (m == 0 || n == 0) return 0;
     if (!A) return -5;
     if (!Q || Q == A) return -7;
     if (dtype == MAKB200_F64)
-        return mak::cholqr2_t<double>(h, m, n, (double*)A, lda, (double*)Q, ldq, (double*)R, ldr, work, lwork, info_dev);
-    return mak::cholqr2_t<cplx>(h, m, n, (cplx*)A, lda, (cplx*)Q, ldq, (cplx*)R, ldr, work, lwork, info_dev);
+        return mak::cholqr2_t<double>(h, m, n, (double*)A, lda, (double*)Q, ldq, (double*)R, ldr, work, lwork, info_dev,
+                                      nshift);
+    return mak::cholqr2_t<cplx>(h, m, n, (cplx*)A, lda, (cplx*)Q, ldq, (cplx*)R, ldr, work, lwork, info_dev, nshift);
+}
+
+int makb200_tsqr_local(makb200_handle_t* h, int dtype, int m, int n, void* A, int lda, void* Q, int ldq, void* R,
+                       int ldr, void* work, size_t lwork, int* info_dev) {
+    int rc = makb200_tsqr_local_ex(h, dtype, m, n, A, lda, Q, ldq, R, ldr, 0, work, lwork, info_dev);
+    return rc == -11 ? -1 : (rc <= -12 ? rc + 1 : rc);
 }
 
 }  // extern "C"

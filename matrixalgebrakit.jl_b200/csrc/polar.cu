@@ -398,7 +398,11 @@ static int trsm_right(makb200_handle* h, bool conjtrans, int m, int n, const T* 
 struct QdwhStep { double a, b, c; bool qr; };
 constexpr double QDWH_CHOLQR_MAX_C = 1e12;
 
-static std::vector<QdwhStep> qdwh_schedule(double l, int maxiter) {
+// QR-type step when c > cmax.  The Cholesky-type step forms X Z^-1 with kappa(Z) <= 1 + c, i.e. an error of
+// ~ c*eps in X; the classical threshold is c > 100.  The parity bound on this path is 10*n*eps, so for
+// large n the threshold is raised to n/8 (error <= n*eps/8): on Gaussian 8192^2 input the second
+// iteration (c ~ 2e2) becomes a Cholesky step, 90 ms instead of 227 ms.
+static std::vector<QdwhStep> qdwh_schedule(double l, int maxiter, double cmax = 100.0) {
     std::vector<QdwhStep> v;
     for (int it = 0; it < maxiter; ++it) {
         if (fabs(1.0 - l) <= 1e-15) {
@@ -410,7 +414,7 @@ static std::vector<QdwhStep> qdwh_schedule(double l, int maxiter) {
         double dd = cbrt(4.0 * (1.0 - l2) / (l2 * l2));
         double a = sqrt(1.0 + dd) + 0.5 * sqrt(8.0 - 4.0 * dd + 8.0 * (2.0 - l2) / (l2 * sqrt(1.0 + dd)));
         double b = (a - 1.0) * (a - 1.0) / 4.0, c = a + b - 1.0;
-        v.push_back(QdwhStep{a, b, c, c > 100.0});
+        v.push_back(QdwhStep{a, b, c, c > cmax});
         l = l * (a + b * l2) / (1.0 + c * l2);
         if (l > 1.0) l = 1.0;
     }
@@ -471,7 +475,9 @@ template <typename T>
 static int qdwh_iterate(makb200_handle* h, int ms, int n, PolarWork<T>& w, double l0, int maxiter, int* iters_out,
                         const T* Z0 = nullptr) {
     cudaStream_t s = h->stream;
-    std::vector<QdwhStep> sched = qdwh_schedule(l0, maxiter);
+    static const bool raise_c = []() { const char* e = getenv("MAKB200_QDWH_CMAX_N8"); return !(e && e[0] == '0'); }();
+    const double cmax = (raise_c && n / 8.0 > 100.0) ? n / 8.0 : 100.0;
+    std::vector<QdwhStep> sched = qdwh_schedule(l0, maxiter, cmax);
     if (iters_out) *iters_out = (int)sched.size();
     PhaseTimer pt(s);
     pt.mark("start");
@@ -821,11 +827,49 @@ __global__ void lower_clean_kernel(int n, T* __restrict__ L) {
     if (r < n && c < n && r < c) L[(size_t)c * n + r] = zero<T>();
 }
 
+// shifted CholeskyQR (Fukaya, Kannan, Nakatsukasa, Yamamoto, Yanagisawa 2020): G += s I with
+// s = coef * trace(G), coef = 11 (mn + n(n+1)) u  (trace(G) = ||X||_F^2 >= ||X||_2^2).  One CTA.
+template <typename T>
+__global__ void add_shift_kernel(int n, T* __restrict__ G, double coef) {
+    __shared__ double red[256];
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) t += real_(G[(size_t)i * n + i]);
+    red[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    const double sft = coef * red[0];
+    for (int i = threadIdx.x; i < n; i += 256) {
+        T* d = G + (size_t)i * n + i;
+        *d = add_(*d, mk<T>(sft));
+    }
+}
+// R (upper, ld n) = L^H
+template <typename T>
+__global__ void upper_from_lower_kernel(int n, const T* __restrict__ L, T* __restrict__ R) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (r >= n || c >= n) return;
+    R[(size_t)c * n + r] = (r <= c) ? conj_(L[(size_t)r * n + c]) : zero<T>();
+}
+// Rout (upper, ld ldo) = L^H * Rin   (L lower, Rin upper with ld n)
+template <typename T>
+__global__ void rmul_upper2_kernel(int n, const T* __restrict__ L, const T* __restrict__ Rin, T* __restrict__ Rout,
+                                   int ldo) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (r >= n || c >= n) return;
+    T s = zero<T>();
+    if (r <= c)
+        for (int p = r; p <= c; ++p) fma_(s, conj_(L[(size_t)r * n + p]), Rin[(size_t)c * n + p]);
+    Rout[(size_t)c * ldo + r] = s;
+}
+
 constexpr int CQR_SLAB = 1 << 20;
 
 template <typename T>
 struct CqrWork {
-    T *G, *L1, *L2, *Linv, *Tmp;
+    T *G, *L1, *L2, *R2, *Linv, *Tmp;
     int* info;
     void* ws;
     size_t ws_bytes;
@@ -839,6 +883,7 @@ static void cqr_carve(makb200_handle* h, AR& ar, int m, int n, CqrWork<T>* w) {
     w->G = ar.template get<T>(nn * nn);
     w->L1 = ar.template get<T>(nn * nn);
     w->L2 = ar.template get<T>(nn * nn);
+    w->R2 = ar.template get<T>(nn * nn);
     w->Linv = ar.template get<T>((size_t)nb * nb * ((nn + nb - 1) / nb));
     w->Tmp = ar.template get<T>(slab * nb);
     w->info = ar.template get<int>(4);
@@ -855,11 +900,16 @@ size_t cholqr2_worksize_t(makb200_handle* h, int m, int n) {
 }
 
 template <typename T>
-static int cholqr_pass(makb200_handle* h, int m, int n, const T* X, int ldx, T* Y, int ldy, T* L, CqrWork<T>& w) {
+static int cholqr_pass(makb200_handle* h, int m, int n, const T* X, int ldx, T* Y, int ldy, T* L, CqrWork<T>& w,
+                       double shift_coef = 0.0) {
     cudaStream_t s = h->stream;
     // G = X^H X (split-K over the long dimension)
     MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, n, n, m, one<T>(), X, ldx, X, ldx, zero<T>(), w.G, n, w.ws,
               w.ws_bytes);
+    if (shift_coef > 0.0) {
+        add_shift_kernel<T><<<1, 256, 0, s>>>(n, w.G, shift_coef);
+        count_launch();
+    }
     int rc = potrf_blocked<T>(h, n, w.G, n, L, n, w.Linv, w.info);
     if (rc) return rc;
     for (int r0 = 0; r0 < m; r0 += CQR_SLAB) {
@@ -872,7 +922,7 @@ static int cholqr_pass(makb200_handle* h, int m, int n, const T* X, int ldx, T* 
 
 template <typename T>
 int cholqr2_t(makb200_handle* h, int m, int n, T* A, int lda, T* Q, int ldq, T* R, int ldr, void* work, size_t lwork,
-              int* info_dev) {
+              int* info_dev, int nshift) {
     if (m <= 0 || n <= 0) return 0;
     cudaStream_t s = h->stream;
     Arena ar(work, lwork);
@@ -882,6 +932,47 @@ int cholqr2_t(makb200_handle* h, int m, int n, T* A, int lda, T* Q, int ldq, T* 
     MAK_CUDA(h, cudaMemsetAsync(w.info, 0, sizeof(int) * 4, s));
     PhaseTimer pt(s);
     pt.mark("start");
+    if (nshift > 0) {
+        // shifted CholeskyQR: `nshift` preconditioning passes with G + sI (each divides kappa by
+        // ~1/sqrt(coef)), then the two plain passes.  R = L_last^H ... L_0^H accumulated pass by pass.
+        const double u = 1.1102230246251565e-16;
+        const double coef = 11.0 * ((double)m * n + (double)n * (n + 1)) * u;
+        const int npass = nshift + 2;
+        T* src = A; int lds = lda;
+        T* dst = Q; int ldd = ldq;
+        T* Racc = nullptr;
+        dim3 g((n + 127) / 128, n);
+        for (int p = 0; p < npass; ++p) {
+            int rc = cholqr_pass<T>(h, m, n, src, lds, dst, ldd, w.L1, w, p < nshift ? coef : 0.0);
+            if (rc) return rc;
+            lower_clean_kernel<T><<<g, 128, 0, s>>>(n, w.L1);
+            if (p == 0) {
+                Racc = w.L2;
+                upper_from_lower_kernel<T><<<g, 128, 0, s>>>(n, w.L1, Racc);
+            } else {
+                T* Rn = (Racc == w.L2) ? w.R2 : w.L2;
+                rmul_upper2_kernel<T><<<g, 128, 0, s>>>(n, w.L1, Racc, Rn, n);
+                Racc = Rn;
+            }
+            count_launch(2);
+            T* t = src; src = dst; dst = t;
+            int tl = lds; lds = ldd; ldd = tl;
+        }
+        // after the swap `src` holds the last result
+        if (src != Q) {
+            copy2d_kernel<T><<<grid_for2((size_t)m * n, h->num_sms), 256, 0, s>>>(m, n, src, lds, Q, ldq);
+            count_launch();
+        }
+        if (R && ldr > 0) {
+            copy2d_kernel<T><<<grid_for2((size_t)n * n, h->num_sms), 256, 0, s>>>(n, n, Racc, n, R, ldr);
+            count_launch();
+        }
+        MAK_LAUNCH_CHECK(h, "shifted cholqr tail");
+        pt.mark("shifted");
+        pt.report("cholqr3");
+        if (info_dev) MAK_CUDA(h, cudaMemcpyAsync(info_dev, w.info, sizeof(int), cudaMemcpyDeviceToDevice, s));
+        return 0;
+    }
     int rc = cholqr_pass<T>(h, m, n, A, lda, Q, ldq, w.L1, w);   // Q1 -> Q
     if (rc) return rc;
     pt.mark("pass1");
@@ -926,7 +1017,7 @@ template int adjoint_t<cplx>(makb200_handle*, int, int, const cplx*, int, cplx*,
     template int svd_t<T>(makb200_handle*, int, int, T*, int, double*, T*, int, T*, int, int, double, void*, \
                           size_t, int*);                                                                     \
     template size_t cholqr2_worksize_t<T>(makb200_handle*, int, int);                                        \
-    template int cholqr2_t<T>(makb200_handle*, int, int, T*, int, T*, int, T*, int, void*, size_t, int*);
+    template int cholqr2_t<T>(makb200_handle*, int, int, T*, int, T*, int, T*, int, void*, size_t, int*, int);
 INSTP(double)
 INSTP(cplx)
 

@@ -11,11 +11,12 @@ template <typename T> size_t svd_worksize_t(makb200_handle* h, int m, int n);
 template <typename T>
 int svd_t(makb200_handle* h, int m, int n, T* A, int lda, double* S, T* U, int ldu, T* Vh, int ldvh, int fixgauge,
           double l0, void* work, size_t lwork, int* info_dev);
-// tall-skinny local QR (CholeskyQR2) used by TSQR; A is overwritten, diag(R) > 0
+// tall-skinny local QR (CholeskyQR2; nshift > 0: shifted CholeskyQR with that many preconditioning
+// passes) used by TSQR; A is overwritten, diag(R) > 0
 template <typename T> size_t cholqr2_worksize_t(makb200_handle* h, int m, int n);
 template <typename T>
 int cholqr2_t(makb200_handle* h, int m, int n, T* A, int lda, T* Q, int ldq, T* R, int ldr, void* work, size_t lwork,
-              int* info_dev);
+              int* info_dev, int nshift = 0);
 // B (n x m) = A^H for A (m x n); tiled, coalesced on both sides
 template <typename T> int adjoint_t(makb200_handle* h, int m, int n, const T* A, int lda, T* B, int ldb);
 }  // namespace mak

@@ -20,7 +20,11 @@ from . import _core
 
 
 class _CudaOps:
-    """Numerical steps of TSQR on libmakb200 (no CPU fallback)."""
+    """Numerical steps of TSQR on libmakb200 (no CPU fallback).  ``nshift`` > 0 selects the shifted
+    CholeskyQR local step (``makb200_tsqr_local_ex``) for ill-conditioned shards."""
+
+    def __init__(self, nshift=0):
+        self.nshift = int(nshift)
 
     def local_qr(self, A):
         m, n = A.shape
@@ -31,16 +35,18 @@ class _CudaOps:
         info = torch.zeros(1, dtype=torch.int32, device=A.device)
         lw = h.lib.makb200_tsqr_local_worksize(h.h, dt, m, n)
         work = h.workspace(lw)
-        rc = h.lib.makb200_tsqr_local(h.h, dt, m, n, _core.ptr(A), _core.ld(A), _core.ptr(Q), _core.ld(Q),
-                                      _core.ptr(R), _core.ld(R), _core.ptr(work), work.numel(), _core.ptr(info))
-        h.check(rc, "makb200_tsqr_local")
+        rc = h.lib.makb200_tsqr_local_ex(h.h, dt, m, n, _core.ptr(A), _core.ld(A), _core.ptr(Q), _core.ld(Q),
+                                         _core.ptr(R), _core.ld(R), self.nshift, _core.ptr(work), work.numel(),
+                                         _core.ptr(info))
+        h.check(rc, "makb200_tsqr_local_ex")
         self._info = info
         return Q, R
 
     def check(self):
         if int(self._info.item()) != 0:
             raise _core.MakError("tsqr: Cholesky breakdown in the local factorization (matrix too ill-conditioned "
-                                 "for CholeskyQR2, kappa >~ 1e7)")
+                                 "for CholeskyQR2, kappa >~ 1e7): call tsqr_(A, robust=True) on a fresh copy "
+                                 "(the input was destroyed)")
 
     def small_qr(self, S):
         from .qr import qr_compact_
@@ -79,10 +85,15 @@ def _recv(buf, src, group):
     return buf
 
 
-def tsqr_(A_local, group=None, ops=None, check=True):
+def tsqr_(A_local, group=None, ops=None, check=True, robust=False):
     """Row-sharded ``qr_compact!``: every rank passes its (m_loc x n) shard (destroyed) and gets
-    back (Q_local, R) with R identical on all ranks, diag(R) >= 0."""
-    ops = ops or _CudaOps()
+    back (Q_local, R) with R identical on all ranks, diag(R) >= 0.
+
+    ``robust=True`` (or an int 1..3 = number of preconditioning passes) runs the local step as
+    shifted CholeskyQR (2 extra passes by default): any numerically full-rank shard, at twice the
+    cost of the default CholeskyQR2 (kappa <~ 1e7)."""
+    if ops is None:
+        ops = _CudaOps(nshift=(2 if robust is True else int(robust)))
     n = A_local.shape[1]
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
