@@ -219,13 +219,20 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
     int v = e ? atoi(e) : dflt;
     return v < lo ? lo : (v > hi ? hi : v);
 }
-static int pool_streams() { static int v = env_int("MAKB200_POOL_STREAMS", 32, 1, NPOOL); return v; }
+// measured on B200 (round 1, 257-512 c128 blocks): 8 streams / 8 threads 229 svd/s, 561 eigh/s;
+// 32 streams / 16 threads 176 / 351 (driver lock contention) -> defaults 8 / 8
+static int pool_streams() { static int v = env_int("MAKB200_POOL_STREAMS", 8, 1, NPOOL); return v; }
 static int pool_threads() {   // host threads feeding the stream pool (1 = single-threaded round robin)
     static int v = -1;
     if (v < 0) {
-        v = env_int("MAKB200_POOL_THREADS", 16, 1, NPOOL);
+        v = env_int("MAKB200_POOL_THREADS", 8, 1, NPOOL);
         unsigned hc = std::thread::hardware_concurrency();
-        if (hc > 0 && (unsigned)v > hc) v = (int)hc;
+        const int lws = env_int("LOCAL_WORLD_SIZE", 1, 1, 1024);   // ranks sharing this host (torchrun)
+        if (hc > 0) {
+            int cap = (int)hc / lws;
+            if (cap < 1) cap = 1;
+            if (v > cap) v = cap;
+        }
     }
     return v;
 }
@@ -318,7 +325,7 @@ static int bqr_warp_max() {   // largest dimension served by the warp-per-block 
 }
 static int bqr_min_dim() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("MAKB200_BQR_MIN_DIM"); v = e ? atoi(e) : 96; if (v < 33) v = 33; }
+    if (v < 0) { const char* e = getenv("MAKB200_BQR_MIN_DIM"); v = e ? atoi(e) : 65; if (v < 33) v = 33; }   // 65 measured: 65-128 bucket 16.1 -> 12.8 ms vs 96
     return v;
 }
 template <typename T>
