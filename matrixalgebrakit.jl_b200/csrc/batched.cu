@@ -222,9 +222,134 @@ batched_qr_warp_kernel(const QrBlockDesc<T>* __restrict__ descs, int batch, int 
         if (lane < m) d.Q[(size_t)c * d.ldq + lane] = S[c * lds + lane];
 }
 
+// Register-resident variant (opt-in, MAKB200_BQR_WARP_REG=1): lane = column and the column LIVES in
+// registers (M = compile-time row capacity); the pivot column is published raw to a per-warp
+// shared-memory vector (one STS by the pivot lane, broadcast LDS by the others) and the reflector's
+// `scale` is folded into the two scalars of the step, so a (row, step) costs 10 DFMA + 3 LSU
+// wavefronts instead of the 14 LSU wavefronts that bound the shared-memory version.
+template <typename T, int M>
+__global__ void __launch_bounds__(128)
+batched_qr_warp_reg_kernel(const QrBlockDesc<T>* __restrict__ descs, int batch) {
+    __shared__ T vsm[4][M];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int blk = blockIdx.x * 4 + warp;
+    if (blk >= batch) return;
+    const QrBlockDesc<T> d = descs[blk];
+    const int m = d.m, n = d.n, k = m < n ? m : n;
+    T* vs = vsm[warp];
+    T col[M];
+    {
+        const T* src = d.A + (size_t)(lane < n ? lane : 0) * d.lda;
+#pragma unroll
+        for (int r = 0; r < M; ++r) col[r] = (lane < n && r < m) ? src[r] : zero<T>();
+    }
+    T mytau = zero<T>(), myscale = zero<T>();
+    // ---- factorization ----
+    for (int j = 0; j < k; ++j) {
+        double sig = 0.0;
+        T piv = zero<T>();
+#pragma unroll
+        for (int r = 0; r < M; ++r) {
+            if (r > j) sig += abs2_(col[r]);
+            if (r == j) piv = col[r];
+        }
+        sig = __shfl_sync(0xffffffffu, sig, j);
+        const T alpha = shfl_(piv, j);
+        double beta; T tau, scale;
+        larfgp_scalars<T>(alpha, sig, beta, tau, scale);
+        if (lane == j) {
+#pragma unroll
+            for (int r = 0; r < M; ++r) {
+                if (r > j) vs[r] = col[r];
+                if (r == j) col[r] = mk<T>(beta);
+            }
+            mytau = tau; myscale = scale;
+        }
+        __syncwarp();
+        if (lane > j && lane < n) {
+            T s0 = zero<T>(), s1 = zero<T>();
+#pragma unroll
+            for (int r = 0; r < M; ++r)
+                if (r > j) { if (r & 1) fmac_(s1, vs[r], col[r]); else fmac_(s0, vs[r], col[r]); }
+            // s = c_j + conj(scale) * sum conj(a_r) c_r ;  f = conj(tau) s ;  g = f * scale
+            T sdot = add_(s0, s1), st = piv;
+            fmac_(st, scale, sdot);
+            const T f = mul_(conj_(tau), st), g = mul_(f, scale);
+#pragma unroll
+            for (int r = 0; r < M; ++r) {
+                if (r == j) col[r] = sub_(col[r], f);
+                if (r > j) col[r] = sub_(col[r], mul_(g, vs[r]));
+            }
+        }
+        __syncwarp();
+    }
+    // ---- R out: lane = column, rows 0..k-1 ----
+    if (d.R && lane < n) {
+        T* dst = d.R + (size_t)lane * d.ldr;
+#pragma unroll
+        for (int r = 0; r < M; ++r)
+            if (r < k) dst[r] = (r <= lane) ? col[r] : zero<T>();
+    }
+    // ---- Q in place (columns 0..k-1), backward accumulation; v_j = scale_j * (raw column below j) ----
+    for (int j = k - 1; j >= 0; --j) {
+        const T tau = shfl_(mytau, j), scale = shfl_(myscale, j);
+        if (lane == j) {
+#pragma unroll
+            for (int r = 0; r < M; ++r)
+                if (r > j) vs[r] = col[r];
+        }
+        __syncwarp();
+        if (lane > j && lane < k) {
+            T s0 = zero<T>(), s1 = zero<T>(), qj = zero<T>();
+#pragma unroll
+            for (int r = 0; r < M; ++r) {
+                if (r == j) qj = col[r];
+                if (r > j) { if (r & 1) fmac_(s1, vs[r], col[r]); else fmac_(s0, vs[r], col[r]); }
+            }
+            T sdot = add_(s0, s1), st = qj;
+            fmac_(st, scale, sdot);
+            const T f = mul_(tau, st), g = mul_(f, scale);
+#pragma unroll
+            for (int r = 0; r < M; ++r) {
+                if (r == j) col[r] = sub_(col[r], f);
+                if (r > j) col[r] = sub_(col[r], mul_(g, vs[r]));
+            }
+        } else if (lane == j) {
+            const T ts = neg_(mul_(tau, scale));
+#pragma unroll
+            for (int r = 0; r < M; ++r) {
+                if (r < j) col[r] = zero<T>();
+                else if (r == j) col[r] = sub_(one<T>(), tau);
+                else col[r] = mul_(ts, col[r]);
+            }
+        }
+        __syncwarp();
+    }
+    if (lane < k) {
+        T* dst = d.Q + (size_t)lane * d.ldq;
+#pragma unroll
+        for (int r = 0; r < M; ++r)
+            if (r < m) dst[r] = col[r];
+    }
+}
+
+static bool bqr_warp_reg() {
+    static const bool v = []() { const char* e = getenv("MAKB200_BQR_WARP_REG"); return e && e[0] == '1'; }();
+    return v;
+}
+
 template <typename T>
-int batched_qr_warp(makb200_handle* h, int batch, int cap_elems, const QrBlockDesc<T>* descs) {
+int batched_qr_warp(makb200_handle* h, int batch, int cap_elems, const QrBlockDesc<T>* descs, int rmax) {
     if (batch <= 0) return 0;
+    if (bqr_warp_reg()) {
+        const int grid = (batch + 3) / 4;
+        if (rmax <= 16) batched_qr_warp_reg_kernel<T, 16><<<grid, 128, 0, h->stream>>>(descs, batch);
+        else if (rmax <= 24) batched_qr_warp_reg_kernel<T, 24><<<grid, 128, 0, h->stream>>>(descs, batch);
+        else batched_qr_warp_reg_kernel<T, 32><<<grid, 128, 0, h->stream>>>(descs, batch);
+        count_launch();
+        MAK_LAUNCH_CHECK(h, "batched_qr_warp_reg_kernel");
+        return 0;
+    }
     const int grid = (batch + 3) / 4;
     const size_t smem = 4 * (size_t)cap_elems * sizeof(T);
     batched_qr_warp_kernel<T><<<grid, 128, smem, h->stream>>>(descs, batch, cap_elems);
@@ -232,8 +357,8 @@ int batched_qr_warp(makb200_handle* h, int batch, int cap_elems, const QrBlockDe
     MAK_LAUNCH_CHECK(h, "batched_qr_warp_kernel");
     return 0;
 }
-template int batched_qr_warp<double>(makb200_handle*, int, int, const QrBlockDesc<double>*);
-template int batched_qr_warp<cplx>(makb200_handle*, int, int, const QrBlockDesc<cplx>*);
+template int batched_qr_warp<double>(makb200_handle*, int, int, const QrBlockDesc<double>*, int);
+template int batched_qr_warp<cplx>(makb200_handle*, int, int, const QrBlockDesc<cplx>*, int);
 
 // ---------------------------------------------------------------------------------------
 // batched svd_compact!: one CTA per block, one-sided (Hestenes) Jacobi with a round-robin

@@ -16,7 +16,8 @@ int batched_init(makb200_handle* h);
 template <typename T>
 int batched_qr_smem(makb200_handle* h, int batch, size_t max_smem_elems, const QrBlockDesc<T>* descs, int* info);
 // tiny blocks (m, n <= 32): one warp per block; cap_elems = max over the class of (m|1)*n (per-warp smem)
-template <typename T> int batched_qr_warp(makb200_handle* h, int batch, int cap_elems, const QrBlockDesc<T>* descs);
+// rmax = row/column capacity of the class (16, 24 or 32): selects the register-resident variant's instantiation
+template <typename T> int batched_qr_warp(makb200_handle* h, int batch, int cap_elems, const QrBlockDesc<T>* descs, int rmax);
 template <typename T>
 struct SvdBlockDesc {
     int m, n, fixgauge;

@@ -407,7 +407,7 @@ struct QrPlan : makb200_qr_batched_plan {
         size_t off = 0;
         for (int cl = 0; cl < 3; ++cl) {
             if (c.warp[cl].empty()) continue;
-            int rc = mak::batched_qr_warp<T>(h, (int)c.warp[cl].size(), c.warp_cap[cl], ddev + off);
+            int rc = mak::batched_qr_warp<T>(h, (int)c.warp[cl].size(), c.warp_cap[cl], ddev + off, cl == 0 ? 16 : (cl == 1 ? 24 : 32));
             if (rc) return rc;
             off += c.warp[cl].size();
         }

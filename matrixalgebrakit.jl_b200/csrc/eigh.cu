@@ -112,7 +112,8 @@ struct TrdCtx {
 
 constexpr int TRD_K1_THREADS = 256;   // 8 warps x 4 columns
 constexpr int TRD_K1_COLS = 32;
-constexpr int TRD_K2_ROWS = 64;       // rows per CTA, 4 threads (p-groups) per row
+constexpr int TRD_K2_ROWS = 32;       // rows per CTA of trd_w_kernel (64 left the GPU under-filled: mt/64 < 148 CTAs)
+constexpr int TRD_K2_NG = 256 / TRD_K2_ROWS;   // threads (p-groups) per row
 
 // partial tail norms of column c (rows >= c+2), used at panel starts
 template <typename T>
@@ -642,8 +643,8 @@ __device__ __forceinline__ T trd_ycol(const TrdCtx<T>& x, int row0, int mt, int 
 template <typename T>
 __global__ void __launch_bounds__(288)
 trd_w_kernel(TrdCtx<T> x, int c, int i, int npyv, int do_next) {
-    __shared__ T sm[4][TRD_K2_ROWS];
-    __shared__ T sm2[4][TRD_K2_ROWS];
+    __shared__ T sm[TRD_K2_NG][TRD_K2_ROWS];
+    __shared__ T sm2[TRD_K2_NG][TRD_K2_ROWS];
     __shared__ T st[2 * TRD_NB];       // t1, t2
     __shared__ T srow[2 * TRD_NB + 2]; // conj(W[c1,p]), conj(V[c1,p])
     __shared__ T sscal[4];
@@ -651,7 +652,7 @@ trd_w_kernel(TrdCtx<T> x, int c, int i, int npyv, int do_next) {
     const int n = x.n, row0 = c + 1, c1 = c + 1;
     const int tid = threadIdx.x, warp = tid >> 5;
     const bool scalar_warp = (warp == 8);
-    const int tx = tid % TRD_K2_ROWS, ty = (tid / TRD_K2_ROWS) & 3;
+    const int tx = tid % TRD_K2_ROWS, ty = (tid / TRD_K2_ROWS) % TRD_K2_NG;
     const int r = row0 + blockIdx.x * TRD_K2_ROWS + tx;
     const bool live = !scalar_warp && r < n;
     const T tauc = x.tau[c];
@@ -691,30 +692,46 @@ trd_w_kernel(TrdCtx<T> x, int c, int i, int npyv, int do_next) {
             sscal[1] = wfirst;
         }
     } else if (live) {
-        for (int p = ty; p < i; p += 4) {
+        for (int p = ty; p < i; p += TRD_K2_NG) {
             const T vp = x.P[(size_t)p * x.ldp + r], wp = x.P[(size_t)(x.pw + p) * x.ldp + r];
             fma_(part, vp, st[p]);
             fma_(part, wp, st[TRD_NB + p]);
             fma_(part2, vp, srow[p]);
             fma_(part2, wp, srow[TRD_NB + 1 + p]);
         }
-        // row parts of y from every strip at or left of this row (subtracted: w = tau (y - part))
+        // row parts of y from every strip at or left of this row (subtracted: w = tau (y - part)).
+        // Up to n/16 strips per row: four independent accumulators keep four loads in flight per
+        // thread (the serial version made the bottom-row CTAs the critical path of the launch).
         const int nsb = (r - row0) / SymvCW<T>::value + 1;
-        for (int b = ty; b < nsb; b += 4) part = sub_(part, x.ypart[(size_t)b * x.ldy + r]);
+        const T* yp = x.ypart + r;
+        T y0 = zero<T>(), y1 = zero<T>(), y2 = zero<T>(), y3 = zero<T>();
+        int b = ty;
+        for (; b + 3 * TRD_K2_NG < nsb; b += 4 * TRD_K2_NG) {
+            y0 = add_(y0, yp[(size_t)b * x.ldy]);
+            y1 = add_(y1, yp[(size_t)(b + TRD_K2_NG) * x.ldy]);
+            y2 = add_(y2, yp[(size_t)(b + 2 * TRD_K2_NG) * x.ldy]);
+            y3 = add_(y3, yp[(size_t)(b + 3 * TRD_K2_NG) * x.ldy]);
+        }
+        for (; b < nsb; b += TRD_K2_NG) y0 = add_(y0, yp[(size_t)b * x.ldy]);
+        part = sub_(part, add_(add_(y0, y1), add_(y2, y3)));
     }
     if (!scalar_warp) { sm[ty][tx] = part; sm2[ty][tx] = part2; }
     __syncthreads();
     const T alpha2 = sscal[0], wfirst = sscal[1];
     double nrm = 0.0;
     if (live && ty == 0) {
-        const T s = add_(add_(sm[0][tx], sm[1][tx]), add_(sm[2][tx], sm[3][tx]));
+        T s = sm[0][tx];
+#pragma unroll
+        for (int g = 1; g < TRD_K2_NG; ++g) s = add_(s, sm[g][tx]);
         const T vr = x.P[(size_t)i * x.ldp + r];
         const T wr = add_(mul_(tauc, sub_(trd_ycol<T>(x, row0, n - row0, r), s)), mul_(alpha2, vr));
         x.P[(size_t)(x.pw + i) * x.ldp + r] = wr;                              // W(:, i)
         x.A[(size_t)c * x.lda + r] = (r == row0) ? mk<T>(x.e[c]) : vr;          // reflector storage
         if (do_next) {
             // left-looking update of column c1 = c+1: previous panel columns + the new one
-            T s2 = add_(add_(sm2[0][tx], sm2[1][tx]), add_(sm2[2][tx], sm2[3][tx]));
+            T s2 = sm2[0][tx];
+#pragma unroll
+            for (int g = 1; g < TRD_K2_NG; ++g) s2 = add_(s2, sm2[g][tx]);
             fma_(s2, vr, conj_(wfirst));   // V[r,i] conj(W[c1,i])
             s2 = add_(s2, wr);             // W[r,i] conj(V[c1,i]), V[c1,i] = 1
             T a = sub_(x.A[(size_t)c1 * x.lda + r], s2);

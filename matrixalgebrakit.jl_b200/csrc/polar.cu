@@ -626,7 +626,7 @@ int polar_qdwh_t(makb200_handle* h, int m, int n, T* A, int lda, T* W, int ldw, 
         T* Yp = w.Y + (size_t)NPROBE * n;
         rademacher_kernel<T><<<grid_for2((size_t)NPROBE * n, h->num_sms), 256, 0, s>>>(NPROBE, n, Gp, NPROBE, 777u);
         count_launch();
-        rc0 = trsm_right<T>(h, true, NPROBE, n, Gp, NPROBE, w.L, n, w.Linv, Yp, NPROBE, w.Tmp, nullptr, 0);
+        rc0 = trsm_right<T>(h, true, NPROBE, n, Gp, NPROBE, w.L, n, w.Linv, Yp, NPROBE, w.Tmp, w.ws, w.ws_bytes);   // split-K: 8-row products with K up to n
         if (rc0) return rc0;
         fro2_partial_kernel<T><<<64, 256, 0, s>>>(NPROBE, n, Yp, NPROBE, w.partial);
         fro2_final_kernel<<<1, 256, 0, s>>>(64, w.partial, w.scal + 2);
