@@ -103,6 +103,7 @@ struct TrdCtx {
     T* y;            // [nstrips][maxseg][CW] : column parts of y = A22 v per (strip, row segment)
     int maxseg;
     int seg;         // rows per segment
+    int prefetch;    // 1: symv CTAs prefetch their strip into L2 before waiting on the previous kernel (PDL)
     T* ypart; int ldy;  // [nstrips][n] : row parts of y, one slice per column strip
     T* t;            // 2*TRD_NB : t1 = W^H v, t2 = V^H v
     double* pn;      // partial tail norms of the current column
@@ -114,6 +115,35 @@ constexpr int TRD_K1_THREADS = 256;   // 8 warps x 4 columns
 constexpr int TRD_K1_COLS = 32;
 constexpr int TRD_K2_ROWS = 32;       // rows per CTA of trd_w_kernel (64 left the GPU under-filled: mt/64 < 148 CTAs)
 constexpr int TRD_K2_NG = 256 / TRD_K2_ROWS;   // threads (p-groups) per row
+
+// Programmatic dependent launch (default on, MAKB200_PDL=0 disables): the two kernels of a column are launched with
+// programmatic stream serialization, so the CTAs of the next launch are scheduled while the previous
+// grid drains; every kernel first waits for its prerequisite grid to complete and flush (so no read
+// or write is reordered across the dependency), then lets its own dependent launch.  Without the
+// launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait_then_trigger() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+static bool trd_pdl() {
+    // measured on B200 (round 1, eigh 8192 f64): hetrd 406 -> 379 ms; MAKB200_PDL=0 disables
+    static const bool v = []() { const char* e = getenv("MAKB200_PDL"); return !(e && e[0] == '0'); }();
+    return v;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 // partial tail norms of column c (rows >= c+2), used at panel starts
 template <typename T>
@@ -222,6 +252,31 @@ trd_symv_kernel(TrdCtx<T> x, int c, int i, int npn, int nstrips) {
     constexpr int CW = SymvCW<T>::value;
     const int SEG = x.seg;
     const int sgi = blockIdx.y;
+    // Under programmatic dependent launch this CTA may be resident while the previous kernel (the w
+    // kernel of column c-1) is still running.  The trailing matrix it is about to stream is not touched
+    // by that kernel, so pull this CTA's part of the strip into L2 before waiting on the dependency:
+    // the first wave of the launch (296 CTAs x 128 KB = 39 MB, fits L2) then starts from L2 hits.
+    // prefetch has no architectural effect, so this is safe even when the prerequisite is the panel GEMM.
+    if (x.prefetch && (int)blockIdx.x < nstrips) {
+        const int row0p = c + 1, mtp = x.n - row0p, cbp = blockIdx.x * CW;
+        const int cwp = (mtp - cbp < CW) ? (mtp - cbp) : CW;
+        const int rsp = cbp + sgi * SEG;
+        const int rep = (rsp + SEG < mtp) ? (rsp + SEG) : mtp;
+        constexpr int PER_LINE = 128 / (int)sizeof(T);
+        const int ln = threadIdx.x & 31, wp = threadIdx.x >> 5;
+        if ((ln % PER_LINE) == 0) {
+            const T* Abp = x.A + (size_t)(row0p + cbp) * x.lda + row0p;
+            for (int rt = rsp + 32 * wp; rt < rep; rt += 256) {
+                const int r = rt + ln;
+                if (r < rep) {
+#pragma unroll
+                    for (int k = 0; k < CW; ++k)
+                        if (k < cwp) asm volatile("prefetch.global.L2 [%0];" ::"l"(Abp + (size_t)k * x.lda + r));
+                }
+            }
+        }
+    }
+    pdl_wait_then_trigger();
     const int slot = sgi * gridDim.x + blockIdx.x;
     __shared__ T s_vcw[8][CW];   // per-warp copy of v over the strip columns (no block barrier needed)
     __shared__ T s_col[8][CW];
@@ -643,6 +698,7 @@ __device__ __forceinline__ T trd_ycol(const TrdCtx<T>& x, int row0, int mt, int 
 template <typename T>
 __global__ void __launch_bounds__(288)
 trd_w_kernel(TrdCtx<T> x, int c, int i, int npyv, int do_next) {
+    pdl_wait_then_trigger();
     __shared__ T sm[TRD_K2_NG][TRD_K2_ROWS];
     __shared__ T sm2[TRD_K2_NG][TRD_K2_ROWS];
     __shared__ T st[2 * TRD_NB];       // t1, t2
@@ -700,20 +756,25 @@ trd_w_kernel(TrdCtx<T> x, int c, int i, int npyv, int do_next) {
             fma_(part2, wp, srow[TRD_NB + 1 + p]);
         }
         // row parts of y from every strip at or left of this row (subtracted: w = tau (y - part)).
-        // Up to n/16 strips per row: four independent accumulators keep four loads in flight per
-        // thread (the serial version made the bottom-row CTAs the critical path of the launch).
+        // Up to n/16 strips per row (the bottom-row CTAs are the critical path of the launch).
         const int nsb = (r - row0) / SymvCW<T>::value + 1;
         const T* yp = x.ypart + r;
-        T y0 = zero<T>(), y1 = zero<T>(), y2 = zero<T>(), y3 = zero<T>();
+        // eight independent partial sums: the launch is bound by loads in flight per SM, not by bytes
+        constexpr int YU = 8;
+        T ya[YU];
+#pragma unroll
+        for (int u = 0; u < YU; ++u) ya[u] = zero<T>();
         int b = ty;
-        for (; b + 3 * TRD_K2_NG < nsb; b += 4 * TRD_K2_NG) {
-            y0 = add_(y0, yp[(size_t)b * x.ldy]);
-            y1 = add_(y1, yp[(size_t)(b + TRD_K2_NG) * x.ldy]);
-            y2 = add_(y2, yp[(size_t)(b + 2 * TRD_K2_NG) * x.ldy]);
-            y3 = add_(y3, yp[(size_t)(b + 3 * TRD_K2_NG) * x.ldy]);
+        for (; b + (YU - 1) * TRD_K2_NG < nsb; b += YU * TRD_K2_NG) {
+#pragma unroll
+            for (int u = 0; u < YU; ++u) ya[u] = add_(ya[u], yp[(size_t)(b + u * TRD_K2_NG) * x.ldy]);
         }
-        for (; b < nsb; b += TRD_K2_NG) y0 = add_(y0, yp[(size_t)b * x.ldy]);
-        part = sub_(part, add_(add_(y0, y1), add_(y2, y3)));
+        for (; b < nsb; b += TRD_K2_NG) ya[0] = add_(ya[0], yp[(size_t)b * x.ldy]);
+#pragma unroll
+        for (int u = YU / 2; u > 0; u >>= 1)
+#pragma unroll
+            for (int v = 0; v < u; ++v) ya[v] = add_(ya[v], ya[v + u]);
+        part = sub_(part, ya[0]);
     }
     if (!scalar_warp) { sm[ty][tx] = part; sm2[ty][tx] = part2; }
     __syncthreads();
@@ -758,6 +819,10 @@ static void trd_carve(AR& ar, int n, TrdCtx<T>* x) {
     x->ldp = n > 0 ? n : 1;
     x->maxseg = (int)((nn + TRD_SEG_MIN - 1) / TRD_SEG_MIN);
     x->seg = trd_seg();
+    {
+        static const bool pf = []() { const char* e = getenv("MAKB200_SYMV_PREFETCH"); return e && e[0] == '1'; }();   // measured: 380 vs 375 ms hetrd -> opt-in
+        x->prefetch = (pf && trd_pdl()) ? 1 : 0;
+    }
     x->y = ar.template get<T>((nn + SymvCW<T>::value) * (size_t)x->maxseg);
     x->ldy = n > 0 ? n : 1;
     x->ypart = ar.template get<T>(nn * ((nn + SymvCW<T>::value - 1) / SymvCW<T>::value));
@@ -803,12 +868,19 @@ static int hetrd(makb200_handle* h, TrdCtx<T>& x) {
             const int gx = nstrips + (2 * i + 31) / 32, gy = (mt + x.seg - 1) / x.seg;
             const int g1 = gx * gy;  // pyv slots written by this launch
             g_clock_dots.begin(s);
+            const bool pdl = trd_pdl() && !use_tma && !g_clock_dots.on;
             if (use_tma) trd_symv_tma_kernel<T><<<dim3(gx, gy), 288, tma_smem_bytes, s>>>(tmap, x, c, i, npn, nstrips);
-            else trd_symv_kernel<T><<<dim3(gx, gy), 256, 0, s>>>(x, c, i, npn, nstrips);
+            else if (pdl) {
+                cudaError_t e = launch_pdl(trd_symv_kernel<T>, dim3(gx, gy), dim3(256), 0, s, x, c, i, npn, nstrips);
+                if (e != cudaSuccess) return cuda_fail(h, e, "trd_symv_kernel (PDL)");
+            } else trd_symv_kernel<T><<<dim3(gx, gy), 256, 0, s>>>(x, c, i, npn, nstrips);
             g_clock_dots.end(s);
             const int do_next = (i + 1 < ncols) ? 1 : 0;
             g_clock_w.begin(s);
-            trd_w_kernel<T><<<g2, 288, 0, s>>>(x, c, i, g1, do_next);
+            if (pdl) {
+                cudaError_t e = launch_pdl(trd_w_kernel<T>, dim3(g2), dim3(288), 0, s, x, c, i, g1, do_next);
+                if (e != cudaSuccess) return cuda_fail(h, e, "trd_w_kernel (PDL)");
+            } else trd_w_kernel<T><<<g2, 288, 0, s>>>(x, c, i, g1, do_next);
             g_clock_w.end(s);
             count_launch(2);
             npn = g2;
