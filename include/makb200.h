@@ -200,6 +200,16 @@ int makb200_eigh_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch
 int makb200_adjoint(makb200_handle_t* h, int dtype, int m, int n, const void* A, int lda, void* B,
                     int ldb);
 
+/* -- EXPERIMENTAL (round 1): second stage of a two-stage Hermitian tridiagonalisation ------------
+ * Band (lower bandwidth b <= 64) -> real symmetric tridiagonal by bulge chasing, T = Q2^H B Q2
+ * (what LAPACK's ?hbtrd / the sb2st stage of ?hetrd_2stage do; replaces nothing in the reference yet:
+ * eigh_full! still runs the one-stage reduction).  A: n x n, only the lower band is read.  d[n],
+ * e[n-1]: DEVICE doubles.  V2 (ldv x n), tau2 (ldt x n, ldt >= ceil(n/b)+1): the chase reflectors in
+ * the layout of csrc/sbr_core.h (sweep s in column s).  All pointers DEVICE. */
+size_t makb200_sbr_chase_worksize(makb200_handle_t* h, int dtype, int n, int b);
+int makb200_sbr_chase(makb200_handle_t* h, int dtype, int n, int b, const void* A, int lda, double* d,
+                      double* e, void* V2, int ldv, void* tau2, int ldt, void* work, size_t lwork);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,8 @@ SIGNATURES = {
     "makb200_svd": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, C.c_double, _vp, _sz, _vp]),
     "makb200_tsqr_local_worksize": (_sz, [_vp, _i, _i, _i]),
     "makb200_tsqr_local": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _sz, _vp]),
+    "makb200_sbr_chase_worksize": (_sz, [_vp, _i, _i, _i]),
+    "makb200_sbr_chase": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _sz]),
     "makb200_tsqr_local_ex": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _sz, _vp]),
     "makb200_eigh_batched_worksize": (_sz, [_vp, _i, _i, _ip]),
     "makb200_eigh_batched": (_i, [_vp, _i, _i, _i, _ip, _vpp, _ip, _vpp, _vpp, _ip, _vp, _vp, _sz]),

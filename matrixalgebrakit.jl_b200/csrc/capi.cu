@@ -7,6 +7,7 @@
 #include "eigh.cuh"
 #include "stedc.cuh"
 #include "polar.cuh"
+#include "sbr.cuh"
 #include <vector>
 #include <algorithm>
 #include <atomic>
@@ -898,6 +899,36 @@ int makb200_adjoint(makb200_handle_t* h, int dtype, int m, int n, const void* A,
     if (!B || B == A) return -7;
     if (dtype == MAKB200_F64) return mak::adjoint_t<double>(h, m, n, (const double*)A, lda, (double*)B, ldb);
     return mak::adjoint_t<cplx>(h, m, n, (const cplx*)A, lda, (cplx*)B, ldb);
+}
+
+}  // extern "C"
+
+extern "C" {
+
+// ---- experimental: second stage of the two-stage tridiagonalisation (band -> tridiagonal) ----------
+size_t makb200_sbr_chase_worksize(makb200_handle_t* h, int dtype, int n, int b) {
+    if (!h || !dtype_ok(dtype) || n < 0 || b < 1) return 0;
+    return dtype == MAKB200_F64 ? mak::sbr_chase_worksize_t<double>(n, b) : mak::sbr_chase_worksize_t<cplx>(n, b);
+}
+
+int makb200_sbr_chase(makb200_handle_t* h, int dtype, int n, int b, const void* A, int lda, double* d, double* e,
+                      void* V2, int ldv, void* tau2, int ldt, void* work, size_t lwork) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (n < 0) return -3;
+    if (b < 1 || b > 64) return -4;
+    if (lda < maxi(1, n)) return -6;
+    if (ldv < maxi(1, n)) return -10;
+    if (ldt < (n + b - 1) / b + 1) return -12;
+    if (n == 0) return 0;
+    if (!A) return -5;
+    if (!d) return -7;
+    if (n > 1 && !e) return -8;
+    if (!V2) return -9;
+    if (!tau2) return -11;
+    if (dtype == MAKB200_F64)
+        return mak::sbr_chase_t<double>(h, n, b, (const double*)A, lda, d, e, (double*)V2, ldv, (double*)tau2, ldt, work, lwork);
+    return mak::sbr_chase_t<cplx>(h, n, b, (const cplx*)A, lda, d, e, (cplx*)V2, ldv, (cplx*)tau2, ldt, work, lwork);
 }
 
 }  // extern "C"

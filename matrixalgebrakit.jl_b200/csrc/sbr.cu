@@ -1,0 +1,257 @@
+// Second stage of the two-stage Hermitian tridiagonalisation: band (lower bandwidth b) -> tridiagonal
+// by bulge chasing.  EXPERIMENTAL in round 1: exposed through makb200_sbr_chase for bring-up and
+// timing; eigh_full! still uses the one-stage reduction.
+//
+// Geometry, task order and the independence rule come from sbr_core.h (validated on the CPU by
+// tests/test_sbr_core_cpu.py): task (s, k) of sweep s touches the b x b off-diagonal block at
+// (r0, r0 - b) and the diagonal block at r0 = s + 1 + k b; tasks with equal 2 s + k are independent.
+// One launch per wavefront, one CTA per task, both blocks resident in shared memory; consecutive
+// wavefronts are chained with programmatic dependent launch.  The band (2 b x n) stays L2-resident
+// (8 MB at n = 8192, b = 64), so the stage is launch/latency bound, not HBM bound.
+#include "sbr.cuh"
+#include "sbr_core.h"
+
+namespace mak {
+
+constexpr int SBR_THREADS = 256;
+constexpr int SBR_BMAX = 64;   // both blocks of a ComplexF64 task fit shared memory (2 x 64 x 65 x 16 B = 133 KB)
+
+// AB[(i-j) + j*ldab] = A[i, j] for 0 <= i-j <= b, zero for b < i-j < ldab; diagonal made real
+template <typename T>
+__global__ void band_pack_kernel(int n, int b, const T* __restrict__ A, int lda, T* __restrict__ AB, int ldab) {
+    const int j = blockIdx.x;
+    for (int d = threadIdx.x; d < ldab; d += blockDim.x) {
+        const int i = j + d;
+        T v = zero<T>();
+        if (d <= b && i < n) v = A[(size_t)j * lda + i];
+        if (d == 0) v = mk<T>(real_(v));
+        AB[(size_t)j * ldab + d] = v;
+    }
+}
+
+template <typename T>
+__global__ void band_diag_kernel(int n, const T* __restrict__ AB, int ldab, double* __restrict__ d, double* __restrict__ e) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    d[j] = real_(AB[(size_t)j * ldab]);
+    if (j + 1 < n) e[j] = real_(AB[(size_t)j * ldab + 1]);
+}
+
+__device__ __forceinline__ void sbr_pdl() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// all tasks of wavefront t: CTA q handles k = (t & 1) + 2 q, s = (t - k) / 2
+template <typename T>
+__global__ void __launch_bounds__(SBR_THREADS)
+chase_wave_kernel(int n, int b, T* __restrict__ AB, int ldab, T* __restrict__ V2, int ldv, T* __restrict__ tau2, int ldt,
+                  int t) {
+    sbr_pdl();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int k = (t & 1) + 2 * (int)blockIdx.x;
+    const int s = (t - k) / 2;
+    if (k > t || s > n - 2 || k >= sbr::sweep_ntasks(n, b, s)) return;
+    const sbr::Task tk = sbr::task_geometry(n, b, s, k);
+    const int L = tk.L, Lp = tk.Lp, r0 = tk.r0, c0 = tk.c0;
+    if (L <= 0) return;
+    const int tid = threadIdx.x;
+    const int ldg = b + 1;                       // odd leading dimension: conflict-free row and column walks
+    T* G = reinterpret_cast<T*>(smem_raw);       // [Lp][ldg]  (column-major: G[i + j*ldg])
+    T* D = G + (size_t)b * ldg;                  // [L][ldg]   full Hermitian
+    T* v = D + (size_t)b * ldg;                  // [b] new reflector
+    T* vp = v + b;                               // [b] previous reflector
+    T* pw = vp + b;                              // [b] p / w of the two-sided update
+    T* ps = pw + b;                              // [256] partial sums
+    T* ps2 = ps + SBR_THREADS;                   // [256] partial sums
+    __shared__ T red[32];
+    __shared__ double redd[32];
+
+    // ---- load ----
+    // column c of the band storage holds rows c .. c+ldab-1 contiguously
+    if (k > 0) {
+        for (int idx = tid; idx < L * Lp; idx += SBR_THREADS) {
+            const int i = idx % L, j = idx / L;
+            G[i + j * ldg] = AB[(size_t)(c0 + j) * ldab + (r0 + i - c0 - j)];
+        }
+        for (int j = tid; j < Lp; j += SBR_THREADS) vp[j] = V2[(size_t)s * ldv + c0 + j];
+    } else {
+        for (int i = tid; i < L; i += SBR_THREADS) G[i] = AB[(size_t)s * ldab + (r0 + i - s)];   // column s
+    }
+    for (int idx = tid; idx < L * L; idx += SBR_THREADS) {
+        const int i = idx % L, j = idx / L;
+        T x;
+        if (i >= j) x = AB[(size_t)(r0 + j) * ldab + (i - j)];
+        else x = conj_(AB[(size_t)(r0 + i) * ldab + (j - i)]);
+        D[i + j * ldg] = x;
+    }
+    __syncthreads();
+
+    // Work split: the 256 threads form NQ groups of RG (= 32 or 64 >= b) threads; thread (i, q) owns row
+    // (or column) i and the q-th slice of the other index, partial sums meet in shared memory.
+    const int RG = (b <= 32) ? 32 : 64, NQ = SBR_THREADS / RG;
+    const int i = tid % RG, q = tid / RG;
+
+    // ---- G <- G H_prev (k >= 1) ----
+    if (k > 0) {
+        const T taup = tau2[(size_t)s * ldt + (k - 1)];
+        if (!is_zero(taup)) {   // uniform
+            const int jw = (Lp + NQ - 1) / NQ, j0 = q * jw, j1 = min(Lp, j0 + jw);
+            T g = zero<T>();
+            if (i < L)
+                for (int j = j0; j < j1; ++j) fma_(g, G[i + j * ldg], vp[j]);
+            ps[q * RG + i] = g;
+            __syncthreads();
+            if (i < L) {
+                T gs = zero<T>();
+                for (int qq = 0; qq < NQ; ++qq) gs = add_(gs, ps[qq * RG + i]);
+                gs = mul_(taup, gs);
+                for (int j = j0; j < j1; ++j) G[i + j * ldg] = sub_(G[i + j * ldg], mul_(gs, conj_(vp[j])));
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- reflector from column 0 of G ----
+    double part = 0.0;
+    if (tid >= 1 && tid < L) part = abs2_(G[tid]);
+    const double sigma = block_sum<double>(part, redd);
+    double beta; T tau, scale;
+    larfgp_scalars<T>(G[0], sigma, beta, tau, scale);
+    __syncthreads();
+    if (tid < L) {
+        v[tid] = (tid == 0) ? one<T>() : mul_(G[tid], scale);
+        G[tid] = (tid == 0) ? mk<T>(beta) : zero<T>();
+    }
+    __syncthreads();
+
+    if (!is_zero(tau)) {   // uniform
+        // ---- G <- H^H G on columns 1 .. Lp-1 (k >= 1): thread (j, q) owns column j, row slice q ----
+        const int iw = (L + NQ - 1) / NQ, i0 = q * iw, i1 = min(L, i0 + iw);
+        if (k > 0) {
+            T dsum = zero<T>();
+            if (i >= 1 && i < Lp)
+                for (int r = i0; r < i1; ++r) fmac_(dsum, v[r], G[r + i * ldg]);
+            ps[q * RG + i] = dsum;
+        }
+        // ---- p = D v (row i, column slice q) ----
+        {
+            T p = zero<T>();
+            if (i < L)
+                for (int j = i0; j < i1; ++j) fma_(p, D[i + j * ldg], v[j]);
+            ps2[q * RG + i] = p;
+        }
+        __syncthreads();
+        if (k > 0 && i >= 1 && i < Lp) {
+            T dsum = zero<T>();
+            for (int qq = 0; qq < NQ; ++qq) dsum = add_(dsum, ps[qq * RG + i]);
+            dsum = mul_(conj_(tau), dsum);
+            for (int r = i0; r < i1; ++r) G[r + i * ldg] = sub_(G[r + i * ldg], mul_(v[r], dsum));
+        }
+        T p = zero<T>();
+        if (tid < L)
+            for (int qq = 0; qq < NQ; ++qq) p = add_(p, ps2[qq * RG + tid]);
+        T a = zero<T>();
+        if (tid < L) fmac_(a, v[tid], p);
+        const T alpha = block_sum<T>(a, red);     // v^H D v (real)
+        const double half = 0.5 * abs2_(tau) * real_(alpha);
+        if (tid < L) pw[tid] = sub_(mul_(tau, p), scale_(v[tid], half));
+        __syncthreads();
+        // ---- D <- D - v w^H - w v^H (row i, column slice q) ----
+        if (i < L) {
+            const T vi = v[i], wi = pw[i];
+            for (int j = i0; j < i1; ++j) {
+                T x = D[i + j * ldg];
+                x = sub_(x, mul_(vi, conj_(pw[j])));
+                x = sub_(x, mul_(wi, conj_(v[j])));
+                if (j == i) x = mk<T>(real_(x));
+                D[i + j * ldg] = x;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- store ----
+    if (k > 0) {
+        for (int idx = tid; idx < L * Lp; idx += SBR_THREADS) {
+            const int i = idx % L, j = idx / L;
+            AB[(size_t)(c0 + j) * ldab + (r0 + i - c0 - j)] = G[i + j * ldg];
+        }
+    } else {
+        for (int i = tid; i < L; i += SBR_THREADS) AB[(size_t)s * ldab + (r0 + i - s)] = G[i];
+    }
+    for (int idx = tid; idx < L * L; idx += SBR_THREADS) {
+        const int i = idx % L, j = idx / L;
+        if (i >= j) AB[(size_t)(r0 + j) * ldab + (i - j)] = D[i + j * ldg];
+    }
+    for (int i = tid; i < L; i += SBR_THREADS) V2[(size_t)s * ldv + r0 + i] = v[i];
+    if (tid == 0) tau2[(size_t)s * ldt + k] = tau;
+}
+
+template <typename T>
+static size_t chase_smem_bytes(int b) { return ((size_t)2 * b * (b + 1) + 3 * (size_t)b + 2 * SBR_THREADS + 8) * sizeof(T); }
+
+template <typename T>
+size_t sbr_chase_worksize_t(int n, int b) {
+    return align_up((size_t)2 * b * (size_t)(n > 0 ? n : 1) * sizeof(T), 256) + 256;
+}
+
+template <typename T>
+int sbr_chase_t(makb200_handle* h, int n, int b, const T* A, int lda, double* d, double* e, T* V2, int ldv, T* tau2,
+                int ldt, void* work, size_t lwork) {
+    if (n <= 0) return 0;
+    if (b < 1 || b > SBR_BMAX) return -4;
+    cudaStream_t s = h->stream;
+    Arena ar(work, lwork);
+    const int ldab = 2 * b;
+    T* AB = ar.get<T>((size_t)ldab * n);
+    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    static bool configured = false;
+    if (!configured) {
+        MAK_CUDA(h, cudaFuncSetAttribute(chase_wave_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)chase_smem_bytes<double>(SBR_BMAX)));
+        MAK_CUDA(h, cudaFuncSetAttribute(chase_wave_kernel<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)chase_smem_bytes<cplx>(SBR_BMAX)));
+        configured = true;
+    }
+    MAK_CUDA(h, cudaMemsetAsync(V2, 0, sizeof(T) * (size_t)ldv * n, s));
+    MAK_CUDA(h, cudaMemsetAsync(tau2, 0, sizeof(T) * (size_t)ldt * n, s));
+    band_pack_kernel<T><<<n, 128, 0, s>>>(n, b, A, lda, AB, ldab);
+    count_launch();
+    MAK_LAUNCH_CHECK(h, "band_pack_kernel");
+    if (n >= 2) {
+        const int kmax = (n - 1 + b - 1) / b;                 // tasks of sweep 0
+        const int grid = kmax / 2 + 2;
+        const int tmax = sbr::wavefront(n - 2, 0);             // last sweep has one task
+        // the last wavefront that holds any task: sweeps near the end have one task each, so 2(n-2) is the maximum
+        const size_t smem = chase_smem_bytes<T>(b);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(SBR_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        for (int t = 0; t <= tmax; ++t) {
+            cudaError_t err = cudaLaunchKernelEx(&cfg, chase_wave_kernel<T>, n, b, AB, ldab, V2, ldv, tau2, ldt, t);
+            if (err != cudaSuccess) return cuda_fail(h, err, "chase_wave_kernel");
+        }
+        count_launch(tmax + 1);
+    }
+    band_diag_kernel<T><<<(n + 255) / 256, 256, 0, s>>>(n, AB, ldab, d, e);
+    count_launch();
+    MAK_LAUNCH_CHECK(h, "band_diag_kernel");
+    return 0;
+}
+
+template size_t sbr_chase_worksize_t<double>(int, int);
+template size_t sbr_chase_worksize_t<cplx>(int, int);
+template int sbr_chase_t<double>(makb200_handle*, int, int, const double*, int, double*, double*, double*, int, double*,
+                                 int, void*, size_t);
+template int sbr_chase_t<cplx>(makb200_handle*, int, int, const cplx*, int, double*, double*, cplx*, int, cplx*, int,
+                               void*, size_t);
+
+}  // namespace mak
