@@ -210,6 +210,17 @@ size_t makb200_sbr_chase_worksize(makb200_handle_t* h, int dtype, int n, int b);
 int makb200_sbr_chase(makb200_handle_t* h, int dtype, int n, int b, const void* A, int lda, double* d,
                       double* e, void* V2, int ldv, void* tau2, int ldt, void* work, size_t lwork);
 
+/* EXPERIMENTAL: first stage, dense -> band (what ?hetrd_he2hb does).  A: FULL n x n Hermitian (both
+ * triangles), overwritten: lower band (width b) = Q1^H A Q1, reflectors below the band (QR-type columns
+ * of A[b:, 0:n-b]); tau1: DEVICE, n entries. */
+size_t makb200_sy2sb_worksize(makb200_handle_t* h, int dtype, int n, int b);
+int makb200_sy2sb(makb200_handle_t* h, int dtype, int n, int b, void* A, int lda, void* tau1, void* work,
+                  size_t lwork);
+/* EXPERIMENTAL: Z (n x ncols) <- Q2 Z with the reflectors of makb200_sbr_chase, diamond blocks of g sweeps. */
+size_t makb200_sbr_apply_q2_worksize(makb200_handle_t* h, int dtype, int n, int b, int g, int ncols);
+int makb200_sbr_apply_q2(makb200_handle_t* h, int dtype, int n, int b, int g, const void* V2, int ldv,
+                         const void* tau2, int ldt, void* Z, int ldz, int ncols, void* work, size_t lwork);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,4 +27,4 @@ from .orthnull import (adjoint_, left_null, left_null_, left_orth, left_orth_, l
                        lq_null, lq_null_, qr_null, qr_null_, right_null, right_null_, right_orth, right_orth_)
 from . import partition  # noqa: E402,F401
 from .partition import gather_block_info, lpt_partition, my_blocks  # noqa: E402,F401
-from .sbr import sbr_chase_  # noqa: E402,F401  (experimental)
+from .sbr import sbr_apply_q2_, sbr_chase_, sy2sb_  # noqa: E402,F401  (experimental)

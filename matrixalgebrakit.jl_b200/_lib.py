@@ -54,6 +54,10 @@ SIGNATURES = {
     "makb200_tsqr_local": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _sz, _vp]),
     "makb200_sbr_chase_worksize": (_sz, [_vp, _i, _i, _i]),
     "makb200_sbr_chase": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _sz]),
+    "makb200_sy2sb_worksize": (_sz, [_vp, _i, _i, _i]),
+    "makb200_sy2sb": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _sz]),
+    "makb200_sbr_apply_q2_worksize": (_sz, [_vp, _i, _i, _i, _i, _i]),
+    "makb200_sbr_apply_q2": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _sz]),
     "makb200_tsqr_local_ex": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _sz, _vp]),
     "makb200_eigh_batched_worksize": (_sz, [_vp, _i, _i, _ip]),
     "makb200_eigh_batched": (_i, [_vp, _i, _i, _i, _ip, _vpp, _ip, _vpp, _vpp, _ip, _vp, _vp, _sz]),

@@ -931,4 +931,49 @@ int makb200_sbr_chase(makb200_handle_t* h, int dtype, int n, int b, const void* 
     return mak::sbr_chase_t<cplx>(h, n, b, (const cplx*)A, lda, d, e, (cplx*)V2, ldv, (cplx*)tau2, ldt, work, lwork);
 }
 
+
+// ---- experimental: first stage (dense -> band) and the Q2 application, exposed for bring-up ----------
+size_t makb200_sy2sb_worksize(makb200_handle_t* h, int dtype, int n, int b) {
+    if (!h || !dtype_ok(dtype) || n < 0 || b < 1) return 0;
+    return dtype == MAKB200_F64 ? mak::sy2sb_worksize_t<double>(h, n, b) : mak::sy2sb_worksize_t<cplx>(h, n, b);
+}
+int makb200_sy2sb(makb200_handle_t* h, int dtype, int n, int b, void* A, int lda, void* tau1, void* work, size_t lwork) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (n < 0) return -3;
+    if (b < 1 || b > 128) return -4;
+    if (lda < maxi(1, n)) return -6;
+    if (n == 0) return 0;
+    if (!A) return -5;
+    if (!tau1) return -7;
+    if (dtype == MAKB200_F64) return mak::sy2sb_t<double>(h, n, b, (double*)A, lda, (double*)tau1, work, lwork);
+    return mak::sy2sb_t<cplx>(h, n, b, (cplx*)A, lda, (cplx*)tau1, work, lwork);
+}
+size_t makb200_sbr_apply_q2_worksize(makb200_handle_t* h, int dtype, int n, int b, int g, int ncols) {
+    if (!h || !dtype_ok(dtype) || n < 0 || b < 1 || g < 1) return 0;
+    return dtype == MAKB200_F64 ? mak::sbr_apply_q2_worksize_t<double>(n, b, g, ncols)
+                                : mak::sbr_apply_q2_worksize_t<cplx>(n, b, g, ncols);
+}
+int makb200_sbr_apply_q2(makb200_handle_t* h, int dtype, int n, int b, int g, const void* V2, int ldv, const void* tau2,
+                         int ldt, void* Z, int ldz, int ncols, void* work, size_t lwork) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (n < 0) return -3;
+    if (b < 1 || b > 64) return -4;
+    if (g < 1 || g > 128) return -5;
+    if (ldv < maxi(1, n)) return -7;
+    if (ldt < (n + b - 1) / b + 1) return -9;
+    if (ldz < maxi(1, n)) return -11;
+    if (ncols < 0) return -12;
+    if (n == 0 || ncols == 0) return 0;
+    if (!V2) return -6;
+    if (!tau2) return -8;
+    if (!Z) return -10;
+    if (dtype == MAKB200_F64)
+        return mak::sbr_apply_q2_t<double>(h, n, b, g, (const double*)V2, ldv, (const double*)tau2, ldt, (double*)Z, ldz,
+                                           ncols, work, lwork);
+    return mak::sbr_apply_q2_t<cplx>(h, n, b, g, (const cplx*)V2, ldv, (const cplx*)tau2, ldt, (cplx*)Z, ldz, ncols, work,
+                                     lwork);
+}
+
 }  // extern "C"

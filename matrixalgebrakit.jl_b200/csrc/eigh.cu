@@ -12,6 +12,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include "eigh.cuh"
+#include "sbr.cuh"
 #include "gemm.cuh"
 #include "qr.cuh"
 #include "stedc.cuh"
@@ -982,14 +983,54 @@ int herm_defect_t(makb200_handle* h, int n, const T* A, int lda, double* out2) {
 template int herm_defect_t<double>(makb200_handle*, int, const double*, int, double*);
 template int herm_defect_t<cplx>(makb200_handle*, int, const cplx*, int, double*);
 
+// EXPERIMENTAL two-stage path (MAKB200_EIGH_TWOSTAGE=<bandwidth 8..64>, "1" = 64; default off):
+// dense -> band (sy2sb, qr.cu) -> tridiagonal (bulge chasing, sbr.cu) -> D&C -> Q2 (diamond blocks)
+// -> Q1 (compact-WY back-transform).  Round-2 item 1 of DESIGN.md section 7; every stage is
+// parity-tested on its own, the assembled path is opt-in until it beats the one-stage reduction.
+static int eigh_twostage_b() {
+    static const int v = []() {
+        const char* e = getenv("MAKB200_EIGH_TWOSTAGE");
+        if (!e || e[0] == '0') return 0;
+        int b = atoi(e);
+        if (b == 1) b = 64;
+        if (b < 8) b = 8;
+        if (b > 64) b = 64;
+        return b;
+    }();
+    return v;
+}
+template <typename T>
+struct TwoStageWork {
+    T* tau1;   // n
+    T* V2;     // n x n
+    T* tau2;   // ldt x n
+    int ldt;
+};
+
 template <typename T, typename AR>
-static void eigh_carve(makb200_handle* h, AR& ar, int n, TrdCtx<T>* x, double** Zreal, void** sub, size_t* sub_bytes) {
+static void eigh_carve(makb200_handle* h, AR& ar, int n, TrdCtx<T>* x, double** Zreal, void** sub, size_t* sub_bytes,
+                       TwoStageWork<T>* ts = nullptr) {
     trd_carve<T>(ar, n, x);
     size_t nn = (size_t)(n > 0 ? n : 1);
     *Zreal = is_cplx<T>::value ? ar.template get<double>(nn * nn) : nullptr;
     size_t a = stedc_worksize(n);
     size_t b = ormqr_worksize_t<T>(h, n > 1 ? n - 1 : 1, n > 1 ? n - 1 : 1, n);
     *sub_bytes = a > b ? a : b;
+    const int b2 = eigh_twostage_b();
+    if (b2 > 0 && n > 2 * b2) {
+        TwoStageWork<T> tmp;
+        TwoStageWork<T>* t = ts ? ts : &tmp;
+        t->ldt = (n + b2 - 1) / b2 + 1;
+        t->tau1 = ar.template get<T>(nn);
+        t->V2 = ar.template get<T>(nn * nn);
+        t->tau2 = ar.template get<T>((size_t)t->ldt * nn);
+        size_t c = sy2sb_worksize_t<T>(h, n, b2), d = sbr_chase_worksize_t<T>(n, b2),
+               e = sbr_apply_q2_worksize_t<T>(n, b2, b2, n), f = ormqr_worksize_t<T>(h, n - b2, n - b2, n);
+        if (c > *sub_bytes) *sub_bytes = c;
+        if (d > *sub_bytes) *sub_bytes = d;
+        if (e > *sub_bytes) *sub_bytes = e;
+        if (f > *sub_bytes) *sub_bytes = f;
+    }
     *sub = ar.template get<char>(*sub_bytes);
 }
 
@@ -1014,7 +1055,8 @@ int eigh_t(makb200_handle* h, int n, T* A, int lda, double* W, T* V, int ldv, in
     double* Zreal;
     void* sub;
     size_t sb;
-    eigh_carve<T>(h, ar, n, &x, &Zreal, &sub, &sb);
+    TwoStageWork<T> ts;
+    eigh_carve<T>(h, ar, n, &x, &Zreal, &sub, &sb, &ts);
     if (!ar.ok) return MAKB200_ERR_WORKSPACE;
     x.A = A;
     x.lda = lda;
@@ -1023,9 +1065,21 @@ int eigh_t(makb200_handle* h, int n, T* A, int lda, double* W, T* V, int ldv, in
     pt.mark("start");
     mirror_upper_kernel<T><<<dim3(nb32, nb32), dim3(32, 8), 0, s>>>(n, A, lda);
     MAK_LAUNCH_CHECK(h, "mirror_upper_kernel");
-    int rc = hetrd<T>(h, x);
-    if (rc) return rc;
-    pt.mark("hetrd");
+    const int b2 = eigh_twostage_b();
+    const bool two_stage = b2 > 0 && n > 2 * b2;
+    int rc;
+    if (two_stage) {
+        rc = sy2sb_t<T>(h, n, b2, A, lda, ts.tau1, sub, sb);
+        if (rc) return rc;
+        pt.mark("sy2sb");
+        rc = sbr_chase_t<T>(h, n, b2, A, lda, x.d, x.e, ts.V2, n, ts.tau2, ts.ldt, sub, sb);
+        if (rc) return rc;
+        pt.mark("chase");
+    } else {
+        rc = hetrd<T>(h, x);
+        if (rc) return rc;
+        pt.mark("hetrd");
+    }
     double* Z;
     int ldz;
     if constexpr (is_cplx<T>::value) { Z = Zreal; ldz = n; }
@@ -1039,8 +1093,17 @@ int eigh_t(makb200_handle* h, int n, T* A, int lda, double* W, T* V, int ldv, in
         real_to_T_kernel<<<blocks, 256, 0, s>>>(n, Zreal, n, V, ldv);
         MAK_LAUNCH_CHECK(h, "real_to_T_kernel");
     }
-    // V[1:, :] <- H_0 ... H_{n-2} V[1:, :]; reflectors = QR-type columns of B = A[1:, 0:n-1]
-    if (n > 1) {
+    if (two_stage) {
+        // X = Q1 Q2 Z: chase reflectors in diamond blocks, then the stage-1 block reflectors
+        // (QR-type columns of A[b:, 0:n-b])
+        rc = sbr_apply_q2_t<T>(h, n, b2, b2, ts.V2, n, ts.tau2, ts.ldt, V, ldv, n, sub, sb);
+        if (rc) return rc;
+        pt.mark("q2");
+        rc = ormqr_left_t<T>(h, n - b2, n - b2, A + b2, lda, ts.tau1, V + b2, ldv, n, sub, sb);
+        if (rc) return rc;
+        pt.mark("q1");
+    } else if (n > 1) {
+        // V[1:, :] <- H_0 ... H_{n-2} V[1:, :]; reflectors = QR-type columns of B = A[1:, 0:n-1]
         rc = ormqr_left_t<T>(h, n - 1, n - 1, A + 1, lda, x.tau, V + 1, ldv, n, sub, sb);
         if (rc) return rc;
     }

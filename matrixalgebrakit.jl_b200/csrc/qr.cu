@@ -687,7 +687,85 @@ int ormqr_left_t(makb200_handle* h, int m, int k, const T* A, int lda, const T* 
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// EXPERIMENTAL (round 1): first stage of the two-stage Hermitian tridiagonalisation, dense -> band
+// (lower bandwidth b), in place on a FULL Hermitian matrix (both triangles valid and kept valid):
+// for every column panel the block below the band is QR-factorized (cluster panel kernel), and the
+// trailing matrix gets the two-sided update  A22 <- Q^H A22 Q = A22 - W V^H - V W^H  with
+//   Y = A22 V,  X = Y T,  W = X - 1/2 V (T^H (V^H X))
+// all DMMA GEMMs (the rank-2b update as ONE product [V W][W V]^H).  On exit the lower band of A holds
+// B = Q1^H A Q1, the reflectors sit below the band (QR-type columns of A[b:, 0:n-b]) with tau1[n-b].
+// ---------------------------------------------------------------------------------------
+template <typename T>
+struct Sy2sbWork {
+    QrWork<T> qr;
+    T* PB;     // (n-b) x 3b : [V | W | V]
+    T* Y;      // (n-b) x b
+    T* M;      // b x b
+    T* M2;     // b x b
+};
+template <typename T, typename AR>
+static void sy2sb_carve(const makb200_handle* h, AR& ar, int n, int b, Sy2sbWork<T>* w) {
+    const int m = n > b ? n - b : 1;
+    qr_carve<T>(h, ar, m, b, b, &w->qr);
+    w->PB = ar.template get<T>((size_t)m * 3 * b);
+    w->Y = ar.template get<T>((size_t)m * b);
+    w->M = ar.template get<T>((size_t)b * b);
+    w->M2 = ar.template get<T>((size_t)b * b);
+}
+template <typename T>
+size_t sy2sb_worksize_t(makb200_handle* h, int n, int b) {
+    ArenaSize ar;
+    Sy2sbWork<T> w;
+    sy2sb_carve<T>(h, ar, n, b, &w);
+    return ar.off + 256;
+}
+template <typename T>
+int sy2sb_t(makb200_handle* h, int n, int b, T* A, int lda, T* tau1, void* work, size_t lwork) {
+    if (n <= 0) return 0;
+    if (b < 1 || b > qr_nb()) return -3;
+    Arena ar(work, lwork);
+    Sy2sbWork<T> w;
+    sy2sb_carve<T>(h, ar, n, b, &w);
+    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    cudaStream_t s = h->stream;
+    const int nb = w.qr.nb;
+    const T one_ = one<T>(), zero_ = zero<T>(), mone = neg_(one<T>());
+    MAK_CUDA(h, cudaMemsetAsync(tau1, 0, sizeof(T) * (size_t)n, s));
+    const bool la_save = h->no_lookahead;
+    h->no_lookahead = true;   // single-block panels: keep everything on the caller's stream
+    struct Restore { makb200_handle* h; bool v; ~Restore() { h->no_lookahead = v; } } restore{h, la_save};
+    for (int j0 = 0; j0 + b < n; j0 += b) {
+        const int mp = n - j0 - b, kb = mp < b ? mp : b;
+        T* P = A + (size_t)j0 * lda + (j0 + b);
+        int rc = geqrf_blocked<T>(h, mp, b, P, lda, w.qr);       // V -> qr.Vw (mp x kb, ld mp), T -> qr.Tall (ld nb)
+        if (rc) return rc;
+        MAK_CUDA(h, cudaMemcpyAsync(tau1 + j0, w.qr.tau, sizeof(T) * kb, cudaMemcpyDeviceToDevice, s));
+        const T* V = w.qr.Vw;
+        const T* Tm = w.qr.Tall;
+        T* A22 = A + (size_t)(j0 + b) * lda + (j0 + b);
+        T* PB0 = w.PB, *PB1 = w.PB + (size_t)kb * mp, *PB2 = w.PB + (size_t)2 * kb * mp;
+        MAK_CUDA(h, cudaMemcpyAsync(PB0, V, sizeof(T) * (size_t)mp * kb, cudaMemcpyDeviceToDevice, s));
+        MAK_CUDA(h, cudaMemcpyAsync(PB2, V, sizeof(T) * (size_t)mp * kb, cudaMemcpyDeviceToDevice, s));
+        // Y = A22 V ; X = Y T (into the W slot) ; M = V^H X ; M2 = T^H M ; W = X - 1/2 V M2
+        MAK_GEMM(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_N, mp, kb, mp, one_, A22, lda, V, mp, zero_, w.Y, mp,
+                 w.qr.ws, w.qr.ws_bytes);
+        MAK_GEMM(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_N, mp, kb, kb, one_, w.Y, mp, Tm, nb, zero_, PB1, mp, nullptr, 0);
+        MAK_GEMM(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, kb, kb, mp, one_, V, mp, PB1, mp, zero_, w.M, b, w.qr.ws,
+                 w.qr.ws_bytes);
+        MAK_GEMM(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, kb, kb, kb, one_, Tm, nb, w.M, b, zero_, w.M2, b, nullptr, 0);
+        MAK_GEMM(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_N, mp, kb, kb, mk<T>(-0.5), V, mp, w.M2, b, one_, PB1, mp,
+                 nullptr, 0);
+        // A22 -= [V W] [W V]^H
+        MAK_GEMM(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, mp, mp, 2 * kb, mone, PB0, mp, PB1, mp, one_, A22, lda,
+                 nullptr, 0);
+    }
+    return 0;
+}
+
 #define INST(T)                                                                                            \
+    template size_t sy2sb_worksize_t<T>(makb200_handle*, int, int);                                        \
+    template int sy2sb_t<T>(makb200_handle*, int, int, T*, int, T*, void*, size_t);                        \
     template size_t qr_worksize_t<T>(makb200_handle*, int, int, int);                                      \
     template int qr_fused_t<T>(makb200_handle*, int, int, int, T*, int, T*, int, T*, int, void*, size_t);  \
     template int geqrf_t<T>(makb200_handle*, int, int, T*, int, T*, void*, size_t);                        \

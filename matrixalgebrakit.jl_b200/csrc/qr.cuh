@@ -14,5 +14,7 @@ template <typename T> size_t ormqr_worksize_t(makb200_handle* h, int m, int k, i
 template <typename T>
 int ormqr_left_t(makb200_handle* h, int m, int k, const T* A, int lda, const T* tau, T* C, int ldc, int nc, void* work,
                  size_t lwork);
-// stable non-negative-beta reflector (shared with eigh.cu)
+// EXPERIMENTAL: dense -> band (first stage of the two-stage tridiagonalisation); A full Hermitian, in place
+template <typename T> size_t sy2sb_worksize_t(makb200_handle* h, int n, int b);
+template <typename T> int sy2sb_t(makb200_handle* h, int n, int b, T* A, int lda, T* tau1, void* work, size_t lwork);
 }  // namespace mak

@@ -10,6 +10,8 @@
 // (8 MB at n = 8192, b = 64), so the stage is launch/latency bound, not HBM bound.
 #include "sbr.cuh"
 #include "sbr_core.h"
+#include "gemm.cuh"
+#include <vector>
 
 namespace mak {
 
@@ -247,6 +249,159 @@ int sbr_chase_t(makb200_handle* h, int n, int b, const T* A, int lda, double* d,
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// Q2 application: Z <- Q2 Z with the diamond blocking of sbr_core.h.  Every block (group of g sweeps,
+// chase position k) becomes a compact-WY pair (V parallelogram, T); blocks of one diamond wavefront
+// are independent and go through three grouped DMMA GEMMs (W = V^H Z_rows, W2 = T W, Z_rows -= V W2).
+// ---------------------------------------------------------------------------------------
+struct Q2BlockDesc {
+    int s0, ns, base, rows, k, pad;
+    size_t voff, toff;   // element offsets into the V / T pools
+};
+
+// one CTA per block: explicit parallelogram V (rows x ns, ld = ldvb) and T (ns x ns upper, ld = g)
+template <typename T>
+__global__ void __launch_bounds__(128)
+q2_build_kernel(int n, int b, int g, int ldvb, const T* __restrict__ V2, int ldv, const T* __restrict__ tau2, int ldt,
+                const Q2BlockDesc* __restrict__ descs, T* __restrict__ Vpool, T* __restrict__ Tpool) {
+    __shared__ T z[128];
+    const Q2BlockDesc d = descs[blockIdx.x];
+    T* V = Vpool + d.voff;
+    T* Tm = Tpool + d.toff;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < ldvb * d.ns; idx += 128) V[idx] = zero<T>();
+    for (int idx = tid; idx < g * g; idx += 128) Tm[idx] = zero<T>();
+    __syncthreads();
+    for (int j = 0; j < d.ns; ++j) {
+        const sbr::Task t = sbr::task_geometry(n, b, d.s0 + j, d.k);
+        const T* v = V2 + (size_t)(d.s0 + j) * ldv + t.r0;
+        for (int i = tid; i < t.L; i += 128) V[(size_t)j * ldvb + (t.r0 - d.base) + i] = v[i];
+    }
+    __syncthreads();
+    for (int j = 0; j < d.ns; ++j) {
+        const T tj = tau2[(size_t)(d.s0 + j) * ldt + d.k];
+        if (tid < j) {
+            T a = zero<T>();
+            for (int r = 0; r < d.rows; ++r) fmac_(a, V[(size_t)tid * ldvb + r], V[(size_t)j * ldvb + r]);
+            z[tid] = a;
+        }
+        __syncthreads();
+        if (tid < j) {
+            T acc = zero<T>();
+            for (int p = tid; p < j; ++p) fma_(acc, Tm[(size_t)p * g + tid], z[p]);
+            Tm[(size_t)j * g + tid] = neg_(mul_(tj, acc));
+        } else if (tid == j) {
+            Tm[(size_t)j * g + j] = tj;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+size_t sbr_apply_q2_worksize_t(int n, int b, int g, int ncols) {
+    if (n < 2) return 256;
+    const int ngroups = (n - 1 + g - 1) / g, kmax = (n - 1 + b - 1) / b;
+    size_t nblocks = 0, maxwave = 0;
+    std::vector<size_t> wave(ngroups + kmax + 1, 0);
+    for (int grp = 0; grp < ngroups; ++grp)
+        for (int k = 0; k < kmax; ++k)
+            if (sbr::dblock_geometry(n, b, g, grp, k).ns > 0) { ++nblocks; ++wave[sbr::diamond_wavefront(ngroups, grp, k)]; }
+    for (size_t w : wave) maxwave = w > maxwave ? w : maxwave;
+    size_t bytes = align_up(nblocks * sizeof(Q2BlockDesc), 256) + 3 * align_up(nblocks * sizeof(GemmProblem<T>), 256) +
+                   align_up(nblocks * (size_t)(b + g) * g * sizeof(T), 256) + align_up(nblocks * (size_t)g * g * sizeof(T), 256) +
+                   2 * align_up(maxwave * (size_t)g * (size_t)(ncols > 0 ? ncols : 1) * sizeof(T), 256);
+    return bytes + 1024;
+}
+
+template <typename T>
+int sbr_apply_q2_t(makb200_handle* h, int n, int b, int g, const T* V2, int ldv, const T* tau2, int ldt, T* Z, int ldz,
+                   int ncols, void* work, size_t lwork) {
+    if (n < 2 || ncols <= 0) return 0;
+    if (g < 1 || g > 128 || b < 1) return -4;
+    cudaStream_t s = h->stream;
+    const int ngroups = (n - 1 + g - 1) / g, kmax = (n - 1 + b - 1) / b, ldvb = b + g;
+    // blocks ordered by diamond wavefront
+    std::vector<std::vector<Q2BlockDesc>> waves(ngroups + kmax + 1);
+    size_t nblocks = 0, maxwave = 0;
+    for (int grp = 0; grp < ngroups; ++grp)
+        for (int k = 0; k < kmax; ++k) {
+            const sbr::DBlock d = sbr::dblock_geometry(n, b, g, grp, k);
+            if (d.ns <= 0) continue;
+            Q2BlockDesc q{d.s0, d.ns, d.base, d.rows, k, 0, 0, 0};
+            waves[sbr::diamond_wavefront(ngroups, grp, k)].push_back(q);
+            ++nblocks;
+        }
+    for (auto& w : waves) maxwave = w.size() > maxwave ? w.size() : maxwave;
+    Arena ar(work, lwork);
+    Q2BlockDesc* ddev = ar.get<Q2BlockDesc>(nblocks);
+    GemmProblem<T>* P1 = ar.get<GemmProblem<T>>(nblocks);
+    GemmProblem<T>* P2 = ar.get<GemmProblem<T>>(nblocks);
+    GemmProblem<T>* P3 = ar.get<GemmProblem<T>>(nblocks);
+    T* Vpool = ar.get<T>(nblocks * (size_t)ldvb * g);
+    T* Tpool = ar.get<T>(nblocks * (size_t)g * g);
+    T* Wb = ar.get<T>(maxwave * (size_t)g * ncols);
+    T* W2b = ar.get<T>(maxwave * (size_t)g * ncols);
+    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    std::vector<Q2BlockDesc> descs;
+    std::vector<GemmProblem<T>> p1, p2, p3;
+    descs.reserve(nblocks); p1.reserve(nblocks); p2.reserve(nblocks); p3.reserve(nblocks);
+    std::vector<size_t> wstart;
+    for (auto& w : waves) {
+        wstart.push_back(descs.size());
+        for (size_t iw = 0; iw < w.size(); ++iw) {
+            Q2BlockDesc q = w[iw];
+            q.voff = descs.size() * (size_t)ldvb * g;
+            q.toff = descs.size() * (size_t)g * g;
+            descs.push_back(q);
+            T* Vb = Vpool + q.voff;
+            T* Tb = Tpool + q.toff;
+            T* Wi = Wb + iw * (size_t)g * ncols;
+            T* W2i = W2b + iw * (size_t)g * ncols;
+            T* Zr = Z + q.base;
+            GemmProblem<T> p;
+            p.lower = 0;
+            p.m = q.ns; p.n = ncols; p.k = q.rows;                       // W = V^H Z_rows
+            p.A = Vb; p.lda = ldvb; p.B = Zr; p.ldb = ldz; p.C = Wi; p.ldc = g;
+            p.alpha = one<T>(); p.beta = zero<T>(); p.conja = 1; p.conjb = 0;
+            p1.push_back(p);
+            p.k = q.ns;                                                  // W2 = T W
+            p.A = Tb; p.lda = g; p.B = Wi; p.ldb = g; p.C = W2i; p.ldc = g; p.conja = 0;
+            p2.push_back(p);
+            p.m = q.rows; p.k = q.ns;                                    // Z_rows -= V W2
+            p.A = Vb; p.lda = ldvb; p.B = W2i; p.ldb = g; p.C = Zr; p.ldc = ldz;
+            p.alpha = neg_(one<T>()); p.beta = one<T>();
+            p3.push_back(p);
+        }
+    }
+    wstart.push_back(descs.size());
+    {
+        Stager st(h, nblocks * (sizeof(Q2BlockDesc) + 3 * sizeof(GemmProblem<T>)) + 4096);
+        MAK_CUDA(h, st.put(ddev, descs.data(), nblocks * sizeof(Q2BlockDesc), s));
+        MAK_CUDA(h, st.put(P1, p1.data(), nblocks * sizeof(GemmProblem<T>), s));
+        MAK_CUDA(h, st.put(P2, p2.data(), nblocks * sizeof(GemmProblem<T>), s));
+        MAK_CUDA(h, st.put(P3, p3.data(), nblocks * sizeof(GemmProblem<T>), s));
+    }
+    q2_build_kernel<T><<<(unsigned)nblocks, 128, 0, s>>>(n, b, g, ldvb, V2, ldv, tau2, ldt, ddev, Vpool, Tpool);
+    count_launch();
+    MAK_LAUNCH_CHECK(h, "q2_build_kernel");
+    for (size_t u = 0; u + 1 < wstart.size(); ++u) {
+        const int cnt = (int)(wstart[u + 1] - wstart[u]);
+        if (cnt <= 0) continue;
+        const size_t o = wstart[u];
+        cudaError_t e = gemm_grouped<T>(s, MAKB200_OP_C, MAKB200_OP_N, cnt, g, ncols, P1 + o);
+        if (e == cudaSuccess) e = gemm_grouped<T>(s, MAKB200_OP_N, MAKB200_OP_N, cnt, g, ncols, P2 + o);
+        if (e == cudaSuccess) e = gemm_grouped<T>(s, MAKB200_OP_N, MAKB200_OP_N, cnt, b + g, ncols, P3 + o);
+        if (e != cudaSuccess) return cuda_fail(h, e, "gemm_grouped (Q2)");
+    }
+    return 0;
+}
+
+template size_t sbr_apply_q2_worksize_t<double>(int, int, int, int);
+template size_t sbr_apply_q2_worksize_t<cplx>(int, int, int, int);
+template int sbr_apply_q2_t<double>(makb200_handle*, int, int, int, const double*, int, const double*, int, double*, int,
+                                    int, void*, size_t);
+template int sbr_apply_q2_t<cplx>(makb200_handle*, int, int, int, const cplx*, int, const cplx*, int, cplx*, int, int,
+                                  void*, size_t);
 template size_t sbr_chase_worksize_t<double>(int, int);
 template size_t sbr_chase_worksize_t<cplx>(int, int);
 template int sbr_chase_t<double>(makb200_handle*, int, int, const double*, int, double*, double*, double*, int, double*,
