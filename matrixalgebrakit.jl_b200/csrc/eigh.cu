@@ -999,6 +999,14 @@ static int eigh_twostage_b() {
     }();
     return v;
 }
+// sweeps per diamond block of the Q2 application (<= bandwidth); MAKB200_Q2_G overrides
+static int eigh_twostage_g(int b) {
+    static const int v = []() { const char* e = getenv("MAKB200_Q2_G"); return e ? atoi(e) : 0; }();
+    int g = v > 0 ? v : b;
+    if (g > b) g = b;
+    if (g < 1) g = 1;
+    return g;
+}
 template <typename T>
 struct TwoStageWork {
     T* tau1;   // n
@@ -1025,7 +1033,7 @@ static void eigh_carve(makb200_handle* h, AR& ar, int n, TrdCtx<T>* x, double** 
         t->V2 = ar.template get<T>(nn * nn);
         t->tau2 = ar.template get<T>((size_t)t->ldt * nn);
         size_t c = sy2sb_worksize_t<T>(h, n, b2), d = sbr_chase_worksize_t<T>(n, b2),
-               e = sbr_apply_q2_worksize_t<T>(n, b2, b2, n), f = ormqr_worksize_t<T>(h, n - b2, n - b2, n);
+               e = sbr_apply_q2_worksize_t<T>(n, b2, eigh_twostage_g(b2), n), f = ormqr_worksize_t<T>(h, n - b2, n - b2, n);
         if (c > *sub_bytes) *sub_bytes = c;
         if (d > *sub_bytes) *sub_bytes = d;
         if (e > *sub_bytes) *sub_bytes = e;
@@ -1096,7 +1104,7 @@ int eigh_t(makb200_handle* h, int n, T* A, int lda, double* W, T* V, int ldv, in
     if (two_stage) {
         // X = Q1 Q2 Z: chase reflectors in diamond blocks, then the stage-1 block reflectors
         // (QR-type columns of A[b:, 0:n-b])
-        rc = sbr_apply_q2_t<T>(h, n, b2, b2, ts.V2, n, ts.tau2, ts.ldt, V, ldv, n, sub, sb);
+        rc = sbr_apply_q2_t<T>(h, n, b2, eigh_twostage_g(b2), ts.V2, n, ts.tau2, ts.ldt, V, ldv, n, sub, sb);
         if (rc) return rc;
         pt.mark("q2");
         rc = ormqr_left_t<T>(h, n - b2, n - b2, A + b2, lda, ts.tau1, V + b2, ldv, n, sub, sb);

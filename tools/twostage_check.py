@@ -37,7 +37,7 @@ def host_q2(V2, tau2, n, b, Z):
     return X
 
 
-for dtype in ("f64", "c128"):
+for dtype in (() if os.environ.get("SKIP_SMALL") else ("f64", "c128")):
     for n in (150, 333):
         A0 = herm(n, dtype, n)
         w0 = np.linalg.eigvalsh(A0)
