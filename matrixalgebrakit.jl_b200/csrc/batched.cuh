@@ -1,13 +1,7 @@
 #pragma once
 #include "common.cuh"
+#include "batched_desc.h"
 namespace mak {
-template <typename T>
-struct QrBlockDesc {
-    int m, n;
-    T* A; int lda;
-    T* Q; int ldq;
-    T* R; int ldr;   // R == nullptr -> not requested
-};
 // shared-memory elements the one-CTA kernel needs for an m x n block, and the largest it accepts
 size_t batched_qr_smem_elems(int m, int n);
 template <typename T> size_t batched_qr_max_smem_elems();
@@ -18,21 +12,6 @@ int batched_qr_smem(makb200_handle* h, int batch, size_t max_smem_elems, const Q
 // tiny blocks (m, n <= 32): one warp per block; cap_elems = max over the class of (m|1)*n (per-warp smem)
 // rmax = row/column capacity of the class (16, 24 or 32): selects the register-resident variant's instantiation
 template <typename T> int batched_qr_warp(makb200_handle* h, int batch, int cap_elems, const QrBlockDesc<T>* descs, int rmax);
-template <typename T>
-struct SvdBlockDesc {
-    int m, n, fixgauge;
-    const T* A; int lda;
-    double* S;
-    T* U; int ldu;     // U == nullptr -> values only
-    T* Vh; int ldvh;
-};
-template <typename T>
-struct EighBlockDesc {
-    int n, fixgauge;
-    const T* A; int lda;
-    double* W;
-    T* V; int ldv;     // V == nullptr -> values only
-};
 size_t batched_eigh_smem_bytes(int n, size_t elem);
 size_t batched_eigh_max_smem_bytes();
 template <typename T>

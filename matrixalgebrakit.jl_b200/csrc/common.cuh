@@ -8,40 +8,9 @@
 #include <stdlib.h>
 #include "../../include/makb200.h"
 #include "scalar.h"
+#include "devutil.cuh"
 
 namespace mak {
-
-// ---------------------------------------------------------------------------------------
-// warp / block reductions (deterministic order)
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ cplx warp_sum(cplx v) {
-    v.re = warp_sum(v.re);
-    v.im = warp_sum(v.im);
-    return v;
-}
-__device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
-// block-wide sum; `scratch` must hold >= 32 T; result broadcast to all threads.
-template <typename T>
-__device__ __forceinline__ T block_sum(T v, T* scratch) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    v = warp_sum(v);
-    __syncthreads();
-    if (lane == 0) scratch[w] = v;
-    __syncthreads();
-    T r = zero<T>();
-    for (int i = 0; i < nw; ++i) r = add_(r, scratch[i]);
-    return r;
-}
 
 // ---------------------------------------------------------------------------------------
 // handle
