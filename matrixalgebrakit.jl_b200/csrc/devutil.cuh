@@ -47,3 +47,32 @@ __device__ __forceinline__ cplx shfl_(cplx v, int src) {
 }
 
 }  // namespace mak
+
+// ---------------------------------------------------------------------------------------
+// inter-CTA flags of the persistent kernels (gpu-scope release/acquire, L2-only loads of data that
+// other CTAs of the SAME launch produce).  Under MAK_EMU memory is sequentially consistent and a
+// polling loop must yield to the other fibers (MAK_SPIN_PAUSE comes from cuda_emu.h).
+// ---------------------------------------------------------------------------------------
+namespace mak {
+#ifdef MAK_EMU
+inline int ld_acquire_gpu(const int* p) { return *(const volatile int*)p; }
+inline void st_release_gpu(int* p, int v) { *(volatile int*)p = v; }
+inline double ld_cg(const double* p) { return *p; }
+inline cplx ld_cg(const cplx* p) { return *p; }
+#else
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double ld_cg(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ cplx ld_cg(const cplx* p) {
+    const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+    return cplx{v.x, v.y};
+}
+#define MAK_SPIN_PAUSE() __nanosleep(32)
+#endif
+}  // namespace mak

@@ -10,7 +10,9 @@
 // (8 MB at n = 8192, b = 64), so the stage is launch/latency bound, not HBM bound.
 #include "sbr.cuh"
 #include "sbr_core.h"
+#include "sbr_chase_persistent.cuh"
 #include "gemm.cuh"
+#include <cstdlib>
 #include <vector>
 
 namespace mak {
@@ -32,10 +34,13 @@ __global__ void band_pack_kernel(int n, int b, const T* __restrict__ A, int lda,
 }
 
 template <typename T>
-__global__ void band_diag_kernel(int n, const T* __restrict__ AB, int ldab, double* __restrict__ d, double* __restrict__ e) {
+__global__ void band_diag_kernel(int n, const T* __restrict__ AB, int ldab, double* __restrict__ d, double* __restrict__ e,
+                                 const int* __restrict__ abort_flag) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    d[j] = real_(AB[(size_t)j * ldab]);
+    // a persistent chase that gave up (progress wait timed out) must not look like a result
+    const bool bad = abort_flag != nullptr && *abort_flag != 0;
+    d[j] = bad ? __longlong_as_double(0x7ff8000000000000LL) : real_(AB[(size_t)j * ldab]);
     if (j + 1 < n) e[j] = real_(AB[(size_t)j * ldab + 1]);
 }
 
@@ -195,7 +200,49 @@ static size_t chase_smem_bytes(int b) { return ((size_t)2 * b * (b + 1) + 3 * (s
 
 template <typename T>
 size_t sbr_chase_worksize_t(int n, int b) {
-    return align_up((size_t)2 * b * (size_t)(n > 0 ? n : 1) * sizeof(T), 256) + 256;
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    return align_up((size_t)2 * b * nn * sizeof(T), 256) + align_up((nn + 1) * sizeof(int), 256) + 256;   // band + progress counters
+}
+
+// opt-in (MAKB200_CHASE_PERSISTENT=1): one cooperative launch instead of one launch per wavefront
+static bool chase_persistent_enabled() {
+    const char* e = getenv("MAKB200_CHASE_PERSISTENT");
+    return e && e[0] == '1';
+}
+
+// Round-2 bring-up: logic validated on the CPU emulator (tests/test_emu_kernels_cpu.py), not yet timed on a B200.
+template <typename T>
+static int chase_persistent_launch(makb200_handle* h, int n, int b, T* AB, int ldab, T* V2, int ldv, T* tau2, int ldt,
+                                   int* prog) {
+    cudaStream_t s = h->stream;
+    const size_t smem = chase_persistent_smem_elems(b) * sizeof(T);
+    MAK_CUDA(h, cudaFuncSetAttribute(chase_persistent_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, nsm = 0, occ = 0;
+    MAK_CUDA(h, cudaGetDevice(&dev));
+    MAK_CUDA(h, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    MAK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chase_persistent_kernel<T>, SBRP_THREADS, smem));
+    if (occ < 1) return MAKB200_ERR_WORKSPACE;
+    // sweep s+1 trails sweep s by two tasks: at most ntasks(0)/2 + 1 sweeps are ever in flight
+    const int inflight = sbr::sweep_ntasks(n, b, 0) / 2 + 2;
+    int grid = nsm * occ;
+    if (grid > inflight) grid = inflight;
+    if (grid > n - 1) grid = n - 1;
+    if (const char* e = getenv("MAKB200_CHASE_GRID")) { const int g = atoi(e); if (g >= 1 && g < grid) grid = g; }
+    MAK_CUDA(h, cudaMemsetAsync(prog, 0, sizeof(int) * (size_t)(n + 1), s));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(SBRP_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;   // all CTAs resident or the launch fails: the progress waits cannot deadlock
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t err = cudaLaunchKernelEx(&cfg, chase_persistent_kernel<T>, n, b, AB, ldab, V2, ldv, tau2, ldt, prog);
+    if (err != cudaSuccess) return cuda_fail(h, err, "chase_persistent_kernel");
+    count_launch();
+    return 0;
 }
 
 template <typename T>
@@ -207,6 +254,7 @@ int sbr_chase_t(makb200_handle* h, int n, int b, const T* A, int lda, double* d,
     Arena ar(work, lwork);
     const int ldab = 2 * b;
     T* AB = ar.get<T>((size_t)ldab * n);
+    int* prog = ar.get<int>((size_t)n + 1);
     if (!ar.ok) return MAKB200_ERR_WORKSPACE;
     static bool configured = false;
     if (!configured) {
@@ -221,7 +269,11 @@ int sbr_chase_t(makb200_handle* h, int n, int b, const T* A, int lda, double* d,
     band_pack_kernel<T><<<n, 128, 0, s>>>(n, b, A, lda, AB, ldab);
     count_launch();
     MAK_LAUNCH_CHECK(h, "band_pack_kernel");
-    if (n >= 2) {
+    const bool persistent = n >= 2 && chase_persistent_enabled();
+    if (persistent) {
+        const int rc = chase_persistent_launch<T>(h, n, b, AB, ldab, V2, ldv, tau2, ldt, prog);
+        if (rc != 0) return rc;
+    } else if (n >= 2) {
         const int kmax = (n - 1 + b - 1) / b;                 // tasks of sweep 0
         const int grid = kmax / 2 + 2;
         const int tmax = sbr::wavefront(n - 2, 0);             // last sweep has one task
@@ -243,7 +295,7 @@ int sbr_chase_t(makb200_handle* h, int n, int b, const T* A, int lda, double* d,
         }
         count_launch(tmax + 1);
     }
-    band_diag_kernel<T><<<(n + 255) / 256, 256, 0, s>>>(n, AB, ldab, d, e);
+    band_diag_kernel<T><<<(n + 255) / 256, 256, 0, s>>>(n, AB, ldab, d, e, persistent ? prog + n : nullptr);
     count_launch();
     MAK_LAUNCH_CHECK(h, "band_diag_kernel");
     return 0;

@@ -60,6 +60,8 @@ struct Block {
     int cur = -1;
     std::function<void()> body;
     uint64_t progress = 0;
+    emu_dim3 bidx;                           // co-resident launches: this block's blockIdx
+    std::vector<unsigned char> dyn;          // co-resident launches: this block's dynamic shared memory
 };
 
 inline Block* g_blk = nullptr;
@@ -76,13 +78,16 @@ inline void set_order(int order, uint64_t seed = 1) {
 }
 inline Fiber& cur() { return g_blk->fibers[g_blk->cur]; }
 inline void yield_() { swapcontext(&cur().ctx, &g_blk->sched); }
+inline uint64_t g_progress = 0;    // co-resident launches: barrier arrivals/releases and finished fibers of ALL blocks
 inline void bar_release(Bar& b) {
     b.arrived = 0;
     b.gen++;
     g_blk->progress++;
+    g_progress++;
 }
 inline void bar_wait(Bar& b) {
     b.arrived++;
+    g_progress++;
     if (b.arrived >= b.expected) {
         bar_release(b);
         return;
@@ -100,13 +105,14 @@ inline void trampoline() {
     Fiber& f = cur();
     f.done = true;
     B.progress++;
+    g_progress++;
     B.warp_alive[f.warp] &= ~(1u << f.lane);
     bar_drop(B.block_bar);
     bar_drop(B.warp_bars[f.warp]);
     swapcontext(&f.ctx, &B.sched);
 }
 
-inline unsigned char* dyn_smem() { return g_dyn_smem.data(); }
+inline unsigned char* dyn_smem() { return (g_blk && !g_blk->dyn.empty()) ? g_blk->dyn.data() : g_dyn_smem.data(); }
 
 // run ONE block of `nthreads` threads
 inline void run_block(dim3 bdim, const std::function<void()>& body) {
@@ -174,6 +180,77 @@ inline void launch(K kernel, dim3 grid, dim3 block, size_t smem_bytes, Args... a
             }
 }
 
+// launch_coresident<<<grid, block, smem>>>: ALL blocks are live at once (what a persistent kernel with
+// inter-CTA flags needs: one block at a time would spin forever).  Every pass visits every live fiber
+// of every block in forward / reverse / random order; a thread that polls global memory must call
+// MAK_SPIN_PAUSE() (= emu::spin_pause, a yield) inside its loop.  Kernels launched this way may use
+// dynamic shared memory only (`__shared__` statics are one per process here).  A full pass without a
+// barrier arrival, a barrier release or a finished fiber is a deadlock (pollers change nothing).
+inline void spin_pause() { yield_(); }
+template <typename K, typename... Args>
+inline void launch_coresident(K kernel, dim3 grid, dim3 block, size_t smem_bytes, Args... args) {
+    g_gridDim = grid;
+    g_blockDim = block;
+    const int nb = (int)(grid.x * grid.y * grid.z);
+    const int nt = (int)(block.x * block.y * block.z), nw = (nt + 31) / 32;
+    constexpr size_t CO_STACK = 64 * 1024;
+    std::vector<Block> blocks(nb);
+    std::vector<char*> stacks((size_t)nb * nt);
+    for (int bi = 0; bi < nb; ++bi) {
+        Block& B = blocks[bi];
+        B.bidx = dim3(bi % grid.x, (bi / grid.x) % grid.y, bi / (grid.x * grid.y));
+        B.dyn.assign(smem_bytes + 64, 0);
+        B.fibers.resize(nt);
+        B.warp_bars.resize(nw);
+        B.warp_alive.assign(nw, 0u);
+        B.warp_slots.assign((size_t)nw * 32 * 16, 0);
+        B.block_bar.expected = nt;
+        B.body = [&]() { kernel(args...); };
+        for (int t = 0; t < nt; ++t) {
+            Fiber& f = B.fibers[t];
+            f.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+            f.lane = t & 31;
+            f.warp = t >> 5;
+            B.warp_bars[f.warp].expected++;
+            B.warp_alive[f.warp] |= 1u << f.lane;
+            f.stack = stacks[(size_t)bi * nt + t] = (char*)malloc(CO_STACK);
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = f.stack;
+            f.ctx.uc_stack.ss_size = CO_STACK;
+            f.ctx.uc_link = &B.sched;
+            makecontext(&f.ctx, (void (*)())trampoline, 0);
+        }
+    }
+    const int total = nb * nt;
+    std::vector<int> order(total);
+    for (int i = 0; i < total; ++i) order[i] = i;
+    int remaining = total;
+    while (remaining > 0) {
+        if (g_order == 1) {
+            for (int i = 0; i < total; ++i) order[i] = total - 1 - i;
+        } else if (g_order == 2) {
+            std::shuffle(order.begin(), order.end(), g_rng);
+        }
+        const uint64_t before = g_progress;
+        for (int i = 0; i < total; ++i) {
+            Block& B = blocks[order[i] / nt];
+            Fiber& f = B.fibers[order[i] % nt];
+            if (f.done) continue;
+            g_blk = &B;
+            g_blockIdx = B.bidx;
+            B.cur = order[i] % nt;
+            swapcontext(&B.sched, &f.ctx);
+            if (f.done) --remaining;
+        }
+        if (remaining > 0 && g_progress == before) {
+            fprintf(stderr, "cuda_emu: DEADLOCK in a co-resident launch: %d threads poll or wait and nothing changes\n", remaining);
+            abort();
+        }
+    }
+    for (char* st : stacks) free(st);
+    g_blk = nullptr;
+}
+
 // ---- warp collectives ------------------------------------------------------------------------
 template <typename T>
 inline T exchange(T v, int src_lane) {
@@ -220,6 +297,7 @@ inline void dmma(double& d0, double& d1, double a, double b) {
 
 inline void __syncthreads() { emu::bar_wait(emu::g_blk->block_bar); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::bar_wait(emu::g_blk->warp_bars[emu::cur().warp]); }
+#define MAK_SPIN_PAUSE() emu::spin_pause()
 inline void __threadfence() {}
 inline void __threadfence_block() {}
 

@@ -3,6 +3,7 @@
 // tests/test_emu_kernels_cpu.py.  Test infrastructure only.
 #include "cuda_emu.h"
 #include "../../matrixalgebrakit.jl_b200/csrc/batched_qr_warp.cuh"
+#include "../../matrixalgebrakit.jl_b200/csrc/sbr_chase_persistent.cuh"
 
 using mak::cplx;
 
@@ -65,4 +66,22 @@ extern "C" int emu_selftest(int nthreads, double* out, const double* Am, const d
     emu::set_order(order, seed);
     emu::launch(emu_selftest_kernel, dim3(1), dim3(nthreads), 0, out, Am, Bm, Cm);
     return 0;
+}
+
+// persistent bulge chasing: `grid` co-resident CTAs of 256 fibers; AB is the 2b x n band storage (in/out),
+// V2 (ldv x n), tau2 (ldt x n) zero-initialised by the caller.  Returns prog[n] (non-zero: a consumer gave up).
+template <typename T>
+static int run_chase_persistent(int n, int b, T* AB, int ldab, T* V2, int ldv, T* tau2, int ldt, int grid) {
+    std::vector<int> prog(n + 1, 0);
+    emu::launch_coresident(mak::chase_persistent_kernel<T>, dim3(grid), dim3(mak::SBRP_THREADS),
+                           mak::chase_persistent_smem_elems(b) * sizeof(T), n, b, AB, ldab, V2, ldv, tau2, ldt, prog.data());
+    for (int s = 0; s <= n - 2; ++s)
+        if (prog[s] != mak::sbr::sweep_ntasks(n, b, s)) return -(s + 1);
+    return prog[n];
+}
+extern "C" int emu_chase_persistent(int dt, int n, int b, void* AB, int ldab, void* V2, int ldv, void* tau2, int ldt,
+                                    int grid, int order, uint64_t seed) {
+    emu::set_order(order, seed);
+    return dt == 0 ? run_chase_persistent<double>(n, b, (double*)AB, ldab, (double*)V2, ldv, (double*)tau2, ldt, grid)
+                   : run_chase_persistent<cplx>(n, b, (cplx*)AB, ldab, (cplx*)V2, ldv, (cplx*)tau2, ldt, grid);
 }

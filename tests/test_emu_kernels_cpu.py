@@ -106,3 +106,64 @@ def test_existing_warp_qr_kernels_in_emulation(lib, dtype, variant):
         _check_qr(As, Qs, Rs)
     Qs, Rs = _run_bqr(lib, variant, As, 0, 0, want_r=False)
     _check_qr(As, Qs, Rs)
+
+
+# ---- persistent bulge chasing (csrc/sbr_chase_persistent.cuh): all CTAs co-resident as fibers ----
+@pytest.fixture(scope="module")
+def sbr_lib():
+    out = os.path.join(tempfile.mkdtemp(), "sbr_host.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out,
+                           os.path.join(ROOT, "tests", "cpu_harness", "sbr_host.cpp")])
+    return ctypes.CDLL(out)
+
+
+def _band_matrix(n, b, dtype, seed):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((n, n))
+    if dtype == "c128":
+        A = A + 1j * rng.standard_normal((n, n))
+    A = (A + A.conj().T) / 2
+    i, j = np.indices((n, n))
+    A[np.abs(i - j) > b] = 0
+    return np.asfortranarray(A)
+
+
+def _band_pack(A, b):
+    n = A.shape[0]
+    AB = np.zeros((2 * b, n), dtype=A.dtype, order="F")
+    for j in range(n):
+        hi = min(n, j + b + 1)
+        AB[:hi - j, j] = A[j:hi, j]
+        AB[0, j] = AB[0, j].real
+    return AB
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("n,b,grid", [(33, 4, 3), (40, 8, 5), (19, 3, 24), (50, 16, 2), (9, 4, 1), (2, 4, 4), (70, 33, 3)])
+def test_emu_chase_persistent(lib, sbr_lib, dtype, n, b, grid):
+    from scipy.linalg import eigh_tridiagonal
+    A = _band_matrix(n, b, dtype, seed=n + b)
+    dt = 1 if dtype == "c128" else 0
+    ldt = (n + b - 1) // b + 1
+    # sequential reference (sbr_core.h task bodies in generation order)
+    d0, e0 = np.zeros(n), np.zeros(max(n - 1, 1))
+    V0 = np.zeros((n, n), dtype=A.dtype, order="F")
+    t0 = np.zeros((ldt, n), dtype=A.dtype, order="F")
+    bad = sbr_lib.sbr_host_chase(dt, n, b, _vp(A), n, _vp(d0), _vp(e0), _vp(V0), _vp(t0), ldt, 0, 0)
+    assert bad == 0
+    ev = np.linalg.eigvalsh(A)
+    scale = max(np.abs(ev).max(), 1.0)
+    for order, seed in ORDERS:
+        AB = _band_pack(A, b)
+        V2 = np.zeros((n, n), dtype=A.dtype, order="F")
+        tau2 = np.zeros((ldt, n), dtype=A.dtype, order="F")
+        rc = lib.emu_chase_persistent(dt, n, b, _vp(AB), 2 * b, _vp(V2), n, _vp(tau2), ldt, grid, order,
+                                      ctypes.c_uint64(seed))
+        assert rc == 0
+        assert np.all(AB[2:, :] == 0), "fill below the first subdiagonal"
+        assert np.all(AB[:2, :].imag == 0) if dt else True
+        d, e = AB[0, :].real.copy(), AB[1, :n - 1].real.copy()
+        w = eigh_tridiagonal(d, e, eigvals_only=True) if n > 1 else d
+        assert np.abs(w - ev).max() <= 50 * n * EPS * scale
+        assert np.abs(d - d0).max() <= 1e-11 * scale and np.abs(e - e0[:n - 1]).max() <= 1e-11 * scale
+        assert np.abs(V2 - V0).max() <= 1e-10 and np.abs(tau2 - t0).max() <= 1e-10
