@@ -76,3 +76,38 @@ __device__ __forceinline__ cplx ld_cg(const cplx* p) {
 #define MAK_SPIN_PAUSE() __nanosleep(32)
 #endif
 }  // namespace mak
+
+// ---------------------------------------------------------------------------------------
+// FP64 tensor-core tile product D(8x8) += A(8x4) B(4x8) (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4).
+// Lane l holds a = A[l/4][l%4], b = B[l%4][l/4], d0/d1 = D[l/4][2(l%4) + {0,1}].
+// ---------------------------------------------------------------------------------------
+namespace mak {
+#ifdef MAK_EMU
+inline void dmma_f64(double& d0, double& d1, double a, double b) { emu::dmma(d0, d1, a, b); }
+#else
+__device__ __forceinline__ void dmma_f64(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+#endif
+// accumulator of one 8x8 tile per lane and acc += a*b on the fragments (complex: four real products)
+template <typename T> struct TileAcc;
+template <> struct TileAcc<double> { double c0, c1; };
+template <> struct TileAcc<cplx> { double r0, r1, i0, i1; };
+__device__ __forceinline__ void tile_zero(TileAcc<double>& a) { a.c0 = a.c1 = 0.0; }
+__device__ __forceinline__ void tile_zero(TileAcc<cplx>& a) { a.r0 = a.r1 = a.i0 = a.i1 = 0.0; }
+__device__ __forceinline__ void tile_set(TileAcc<double>& a, double x0, double x1) { a.c0 = x0; a.c1 = x1; }
+__device__ __forceinline__ void tile_set(TileAcc<cplx>& a, cplx x0, cplx x1) { a.r0 = x0.re; a.r1 = x1.re; a.i0 = x0.im; a.i1 = x1.im; }
+__device__ __forceinline__ double tile_get0(const TileAcc<double>& a) { return a.c0; }
+__device__ __forceinline__ double tile_get1(const TileAcc<double>& a) { return a.c1; }
+__device__ __forceinline__ cplx tile_get0(const TileAcc<cplx>& a) { return cplx{a.r0, a.i0}; }
+__device__ __forceinline__ cplx tile_get1(const TileAcc<cplx>& a) { return cplx{a.r1, a.i1}; }
+__device__ __forceinline__ void tile_mma(TileAcc<double>& acc, double a, double b) { dmma_f64(acc.c0, acc.c1, a, b); }
+__device__ __forceinline__ void tile_mma(TileAcc<cplx>& acc, cplx a, cplx b) {
+    dmma_f64(acc.r0, acc.r1, a.re, b.re);
+    dmma_f64(acc.r0, acc.r1, -a.im, b.im);
+    dmma_f64(acc.i0, acc.i1, a.re, b.im);
+    dmma_f64(acc.i0, acc.i1, a.im, b.re);
+}
+}  // namespace mak

@@ -11,6 +11,7 @@
 #include "sbr.cuh"
 #include "sbr_core.h"
 #include "sbr_chase_persistent.cuh"
+#include "sbr_q2_slab.cuh"
 #include "gemm.cuh"
 #include <cstdlib>
 #include <vector>
@@ -306,10 +307,18 @@ int sbr_chase_t(makb200_handle* h, int n, int b, const T* A, int lda, double* d,
 // chase position k) becomes a compact-WY pair (V parallelogram, T); blocks of one diamond wavefront
 // are independent and go through three grouped DMMA GEMMs (W = V^H Z_rows, W2 = T W, Z_rows -= V W2).
 // ---------------------------------------------------------------------------------------
-struct Q2BlockDesc {
-    int s0, ns, base, rows, k, pad;
-    size_t voff, toff;   // element offsets into the V / T pools
-};
+// Q2BlockDesc: sbr_q2_slab.cuh
+
+// opt-in (MAKB200_Q2_FUSED=1): one CTA per column slab of Z walks every diamond block (sbr_q2_slab.cuh)
+static bool q2_fused_enabled() {
+    const char* e = getenv("MAKB200_Q2_FUSED");
+    return e && e[0] == '1';
+}
+static int q2_fused_cw() {
+    const char* e = getenv("MAKB200_Q2_CW");
+    return (e && atoi(e) == 32) ? 32 : 64;
+}
+static bool q2_fused_ok(int b, int g) { return b % 8 == 0 && g % 8 == 0 && g <= b && g <= 64; }
 
 // one CTA per block: explicit parallelogram V (rows x ns, ld = ldvb) and T (ns x ns upper, ld = g)
 template <typename T>
@@ -361,7 +370,8 @@ size_t sbr_apply_q2_worksize_t(int n, int b, int g, int ncols) {
     for (size_t w : wave) maxwave = w > maxwave ? w : maxwave;
     size_t bytes = align_up(nblocks * sizeof(Q2BlockDesc), 256) + 3 * align_up(nblocks * sizeof(GemmProblem<T>), 256) +
                    align_up(nblocks * (size_t)(b + g) * g * sizeof(T), 256) + align_up(nblocks * (size_t)g * g * sizeof(T), 256) +
-                   2 * align_up(maxwave * (size_t)g * (size_t)(ncols > 0 ? ncols : 1) * sizeof(T), 256);
+                   2 * align_up(maxwave * (size_t)g * (size_t)(ncols > 0 ? ncols : 1) * sizeof(T), 256) +
+                   align_up((size_t)ngroups * kmax * sizeof(int), 256);   // blkmap of the fused slab kernel
     return bytes + 1024;
 }
 
@@ -393,6 +403,7 @@ int sbr_apply_q2_t(makb200_handle* h, int n, int b, int g, const T* V2, int ldv,
     T* Tpool = ar.get<T>(nblocks * (size_t)g * g);
     T* Wb = ar.get<T>(maxwave * (size_t)g * ncols);
     T* W2b = ar.get<T>(maxwave * (size_t)g * ncols);
+    int* blkmap = ar.get<int>((size_t)ngroups * kmax);
     if (!ar.ok) return MAKB200_ERR_WORKSPACE;
     std::vector<Q2BlockDesc> descs;
     std::vector<GemmProblem<T>> p1, p2, p3;
@@ -436,6 +447,26 @@ int sbr_apply_q2_t(makb200_handle* h, int n, int b, int g, const T* V2, int ldv,
     q2_build_kernel<T><<<(unsigned)nblocks, 128, 0, s>>>(n, b, g, ldvb, V2, ldv, tau2, ldt, ddev, Vpool, Tpool);
     count_launch();
     MAK_LAUNCH_CHECK(h, "q2_build_kernel");
+    if (q2_fused_enabled() && q2_fused_ok(b, g)) {
+        // Round-2 bring-up: logic validated on the CPU emulator, not yet timed on a B200.
+        const int cw = q2_fused_cw();
+        const Q2SlabSmem sm = q2_slab_smem(b, g, cw);
+        const size_t smem = sm.total * sizeof(T);
+        if (smem <= 227 * 1024) {
+            std::vector<int> map((size_t)ngroups * kmax, -1);
+            for (size_t i = 0; i < descs.size(); ++i) map[(size_t)(descs[i].s0 / g) * kmax + descs[i].k] = (int)i;
+            {
+                Stager st(h, map.size() * sizeof(int) + 1024);
+                MAK_CUDA(h, st.put(blkmap, map.data(), map.size() * sizeof(int), s));
+            }
+            MAK_CUDA(h, cudaFuncSetAttribute(q2_slab_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            q2_slab_kernel<T><<<(ncols + cw - 1) / cw, Q2S_THREADS, smem, s>>>(n, b, g, cw, ngroups, kmax, blkmap, ddev, Vpool,
+                                                                              Tpool, Z, ldz, ncols);
+            count_launch();
+            MAK_LAUNCH_CHECK(h, "q2_slab_kernel");
+            return 0;
+        }
+    }
     for (size_t u = 0; u + 1 < wstart.size(); ++u) {
         const int cnt = (int)(wstart[u + 1] - wstart[u]);
         if (cnt <= 0) continue;

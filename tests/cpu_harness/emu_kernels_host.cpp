@@ -4,6 +4,7 @@
 #include "cuda_emu.h"
 #include "../../matrixalgebrakit.jl_b200/csrc/batched_qr_warp.cuh"
 #include "../../matrixalgebrakit.jl_b200/csrc/sbr_chase_persistent.cuh"
+#include "../../matrixalgebrakit.jl_b200/csrc/sbr_q2_slab.cuh"
 
 using mak::cplx;
 
@@ -84,4 +85,40 @@ extern "C" int emu_chase_persistent(int dt, int n, int b, void* AB, int ldab, vo
     emu::set_order(order, seed);
     return dt == 0 ? run_chase_persistent<double>(n, b, (double*)AB, ldab, (double*)V2, ldv, (double*)tau2, ldt, grid)
                    : run_chase_persistent<cplx>(n, b, (cplx*)AB, ldab, (cplx*)V2, ldv, (cplx*)tau2, ldt, grid);
+}
+
+// fused Q2 application (csrc/sbr_q2_slab.cuh): the V/T pools are built with sbr_core.h's dblock_build in the
+// layout of q2_build_kernel (V: ld b+g, zero filled; T: ld g), blocks listed in (grp, k) order.
+template <typename T>
+static int run_q2_slab(int n, int b, int g, int cw, const T* V2, int ldv, const T* tau2, int ldt, T* Z, int ldz, int ncols) {
+    if (n < 2) return 0;
+    const int ngroups = (n - 1 + g - 1) / g, kmax = (n - 1 + b - 1) / b, ldvb = b + g;
+    mak::sbr::Q2Store<T> Q{ldv, ldt, const_cast<T*>(V2), const_cast<T*>(tau2)};
+    std::vector<mak::Q2BlockDesc> descs;
+    std::vector<int> map((size_t)ngroups * kmax, -1);
+    for (int grp = 0; grp < ngroups; ++grp)
+        for (int k = 0; k < kmax; ++k) {
+            const mak::sbr::DBlock d = mak::sbr::dblock_geometry(n, b, g, grp, k);
+            if (d.ns <= 0) continue;
+            mak::Q2BlockDesc q{d.s0, d.ns, d.base, d.rows, k, 0, descs.size() * (size_t)ldvb * g, descs.size() * (size_t)g * g};
+            map[(size_t)grp * kmax + k] = (int)descs.size();
+            descs.push_back(q);
+        }
+    std::vector<T> Vpool(descs.size() * (size_t)ldvb * g, mak::zero<T>()), Tpool(descs.size() * (size_t)g * g, mak::zero<T>());
+    for (auto& q : descs) {
+        const mak::sbr::DBlock d{q.s0, q.ns, q.base, q.rows};
+        mak::sbr::dblock_build<T>(n, b, Q, d, q.k, Vpool.data() + q.voff, ldvb, Tpool.data() + q.toff, g);
+        // dblock_build zeroes only d.rows rows of the ns columns: the pool is zero-initialised, as q2_build_kernel leaves it
+    }
+    const mak::Q2SlabSmem sm = mak::q2_slab_smem(b, g, cw);
+    emu::launch(mak::q2_slab_kernel<T>, dim3((ncols + cw - 1) / cw), dim3(mak::Q2S_THREADS), sm.total * sizeof(T), n, b, g, cw,
+                ngroups, kmax, (const int*)map.data(), (const mak::Q2BlockDesc*)descs.data(), (const T*)Vpool.data(),
+                (const T*)Tpool.data(), Z, ldz, ncols);
+    return 0;
+}
+extern "C" int emu_q2_slab(int dt, int n, int b, int g, int cw, const void* V2, int ldv, const void* tau2, int ldt, void* Z,
+                           int ldz, int ncols, int order, uint64_t seed) {
+    emu::set_order(order, seed);
+    return dt == 0 ? run_q2_slab<double>(n, b, g, cw, (const double*)V2, ldv, (const double*)tau2, ldt, (double*)Z, ldz, ncols)
+                   : run_q2_slab<cplx>(n, b, g, cw, (const cplx*)V2, ldv, (const cplx*)tau2, ldt, (cplx*)Z, ldz, ncols);
 }

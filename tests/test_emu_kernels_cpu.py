@@ -167,3 +167,27 @@ def test_emu_chase_persistent(lib, sbr_lib, dtype, n, b, grid):
         assert np.abs(w - ev).max() <= 50 * n * EPS * scale
         assert np.abs(d - d0).max() <= 1e-11 * scale and np.abs(e - e0[:n - 1]).max() <= 1e-11 * scale
         assert np.abs(V2 - V0).max() <= 1e-10 and np.abs(tau2 - t0).max() <= 1e-10
+
+
+# ---- fused Q2 application (csrc/sbr_q2_slab.cuh): DMMA fragments, 2b-row ring, zero skipping ----
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("n,b,g,cw,ncols", [(50, 8, 8, 32, 40), (45, 16, 8, 32, 32), (61, 8, 8, 64, 70), (40, 16, 16, 64, 9),
+                                             (2, 8, 8, 32, 5), (9, 8, 8, 32, 33)])
+def test_emu_q2_slab(lib, sbr_lib, dtype, n, b, g, cw, ncols):
+    A = _band_matrix(n, b, dtype, seed=3 * n + b)
+    dt = 1 if dtype == "c128" else 0
+    ldt = (n + b - 1) // b + 1
+    d0, e0 = np.zeros(n), np.zeros(max(n - 1, 1))
+    V2 = np.zeros((n, n), dtype=A.dtype, order="F")
+    tau2 = np.zeros((ldt, n), dtype=A.dtype, order="F")
+    assert sbr_lib.sbr_host_chase(dt, n, b, _vp(A), n, _vp(d0), _vp(e0), _vp(V2), _vp(tau2), ldt, 0, 0) == 0
+    Z0 = np.asfortranarray(O.randn_matrix(n, ncols, dtype, seed=n))
+    Xref = Z0.copy(order="F")
+    assert sbr_lib.sbr_host_apply_q2(dt, n, b, _vp(V2), _vp(tau2), ldt, _vp(Xref), n, ncols, 0, 1, 0) == 0
+    for order, seed in ORDERS:
+        X = Z0.copy(order="F")
+        assert lib.emu_q2_slab(dt, n, b, g, cw, _vp(V2), n, _vp(tau2), ldt, _vp(X), n, ncols, order,
+                               ctypes.c_uint64(seed)) == 0
+        assert np.abs(X - Xref).max() <= 200 * n * EPS * max(np.abs(Xref).max(), 1.0)
+    # Q2 is unitary: the fused result keeps column norms
+    assert np.allclose(np.linalg.norm(X, axis=0), np.linalg.norm(Z0, axis=0), rtol=1e-12)

@@ -52,3 +52,60 @@ def test_persistent_chase_matches_wave_kernel(persistent_chase, n, b, dtype):
     w = eigh_tridiagonal(d.cpu().numpy(), e.cpu().numpy(), eigvals_only=True)
     wref = np.linalg.eigvalsh(A)
     assert np.abs(w - wref).max() / np.abs(wref).max() <= 10 * n * EPS
+
+
+def _apply_q2_host(V2, tau2, n, b, Z):
+    X = Z.astype(V2.dtype).copy()
+    for s in range(n - 2, -1, -1):
+        nt = (n - 1 - s + b - 1) // b
+        for k in range(nt - 1, -1, -1):
+            r0 = s + 1 + k * b
+            L = min(b, n - r0)
+            v, tau = V2[r0:r0 + L, s], tau2[k, s]
+            X[r0:r0 + L] -= np.outer(v, tau * (v.conj() @ X[r0:r0 + L]))
+    return X
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("n,b,g,ncols,cw", [(50, 8, 8, 40, 32), (200, 16, 16, 200, 64), (300, 32, 16, 77, 64),
+                                            (257, 32, 32, 257, 64), (400, 64, 32, 130, 32)])
+def test_fused_q2_slab_vs_host_reflectors(n, b, g, ncols, cw, dtype):
+    """Z <- Q2 Z through the slab kernel against one reflector at a time on the host."""
+    import makb200
+    if dtype == "c128" and (b, g) == (64, 32) and cw == 64:
+        pytest.skip("shared memory")
+    A = _band(n, b, dtype, seed=n + b)
+    d, e, V2, tau2 = makb200.sbr_chase_(makb200.to_device(A), b)
+    rng = np.random.default_rng(n)
+    Z0 = rng.standard_normal((n, ncols)) + (1j * rng.standard_normal((n, ncols)) if dtype == "c128" else 0)
+    Z0 = np.asfortranarray(Z0)
+    os.environ["MAKB200_Q2_FUSED"] = "1"
+    os.environ["MAKB200_Q2_CW"] = str(cw)
+    try:
+        Z = makb200.sbr_apply_q2_(V2, tau2, b, makb200.to_device(Z0), g=g)
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("MAKB200_Q2_FUSED", None)
+        os.environ.pop("MAKB200_Q2_CW", None)
+    Xref = _apply_q2_host(makb200.to_numpy(V2), makb200.to_numpy(tau2), n, b, Z0)
+    assert np.abs(makb200.to_numpy(Z) - Xref).max() <= 10 * n * EPS * np.abs(Xref).max()
+
+
+def test_two_stage_eigh_with_bringup_kernels():
+    """Assembled two-stage eigh_full! with the persistent chase and the fused Q2 kernel (env read per process)."""
+    import subprocess
+    import sys
+    import json
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("_twostage", os.path.join(here, "test_gpu_twostage.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    SCRIPT, ROOT = mod.SCRIPT, mod.ROOT
+    env = dict(os.environ, MAKB200_EIGH_TWOSTAGE="16", MAKB200_CHASE_PERSISTENT="1", MAKB200_Q2_FUSED="1")
+    p = subprocess.run([sys.executable, "-c", SCRIPT % ROOT], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    for r in json.loads(line[len("RESULT "):]):
+        tol = 10 * r["n"] * EPS
+        assert r["vals"] <= tol and r["resid"] <= tol * r["n"] ** 0.5 and r["orth"] <= tol * r["n"] ** 0.5 and r["gauge"], r

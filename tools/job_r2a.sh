@@ -1,0 +1,23 @@
+#!/bin/bash
+# Round-2 bring-up job (ONE gpurun call): the kernels written after the round-1 GPU budget was spent
+# (persistent chase, fused Q2 slab kernel) -- parity first, then timing against the round-1 kernels.
+#   gpurun --timeout 1500 -- 'bash tools/job_r2a.sh'
+set -u
+mkdir -p gpurun_out
+{
+echo "== bring-up parity =="
+MAKB200_BRINGUP=1 timeout 900 python -m pytest tests/test_gpu_zz_bringup.py -q -x 2>&1 | tail -15
+echo "== chase: wavefront launches vs persistent (n=8192) =="
+timeout 300 python tools/sbr_time.py 8192 64 32
+MAKB200_CHASE_PERSISTENT=1 timeout 300 python tools/sbr_time.py 8192 64 32
+for g in 8 16 32 64; do echo "-- persistent, grid cap $g"; MAKB200_CHASE_PERSISTENT=1 MAKB200_CHASE_GRID=$g timeout 120 python tools/sbr_time.py 8192 64; done
+echo "== two-stage eigh 8192 f64: round-1 kernels / +persistent chase / +fused Q2 (g = 64, 32; cw = 64, 32) =="
+for cfg in "" "MAKB200_CHASE_PERSISTENT=1" "MAKB200_CHASE_PERSISTENT=1 MAKB200_Q2_FUSED=1" \
+           "MAKB200_CHASE_PERSISTENT=1 MAKB200_Q2_FUSED=1 MAKB200_Q2_G=32" \
+           "MAKB200_CHASE_PERSISTENT=1 MAKB200_Q2_FUSED=1 MAKB200_Q2_G=32 MAKB200_Q2_CW=32" \
+           "MAKB200_EIGH_TWOSTAGE=32 MAKB200_CHASE_PERSISTENT=1 MAKB200_Q2_FUSED=1"; do
+  echo "-- $cfg"
+  env MAKB200_EIGH_TWOSTAGE=64 MAKB200_PHASES=1 $cfg timeout 300 python tools/twostage_check.py 8192 2>&1 | tail -12
+done
+} > gpurun_out/r2a.log 2>&1
+tail -60 gpurun_out/r2a.log
