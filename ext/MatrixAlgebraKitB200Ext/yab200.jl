@@ -92,12 +92,14 @@ end
 # ---- eigh: heevd!(A, W, V) (yacusolver.jl:766-810 call shape) -----------------------------------
 function heevd!(A::StridedCuMatrix{T}, W::StridedCuVector{Float64}, V::StridedCuMatrix{T}; fixgauge::Bool = false) where {T <: B200Float}
     n = checksquare(A)
+    vectors = length(V) > 0   # job 'N' when V is empty (yalapack.jl:1192-1195, 1293-1298): Sturm K-section, no vectors
     h = handle()
     lw = ccall((:makb200_eigh_worksize, libmakb200), Csize_t, (Ptr{Cvoid}, Cint, Cint), h, dtypecode(T), n)
     with_workspace(lw) do work
         rc = ccall((:makb200_eigh, libmakb200), Cint,
             (Ptr{Cvoid}, Cint, Cint, Cint, CuPtr{T}, Cint, CuPtr{Float64}, CuPtr{T}, Cint, CuPtr{UInt8}, Csize_t, CuPtr{Cint}),
-            h, dtypecode(T), fixgauge, n, A, max(1, stride(A, 2)), W, V, max(1, stride(V, 2)), work, lw, CU_NULL)
+            h, dtypecode(T), fixgauge, n, A, max(1, stride(A, 2)), W, vectors ? pointer(V) : CU_NULL,
+            vectors ? max(1, stride(V, 2)) : 0, work, lw, CU_NULL)
         chkargsok(rc, "makb200_eigh")
     end
     return W, V

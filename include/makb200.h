@@ -117,8 +117,11 @@ int makb200_qr_batched_plan_destroy(makb200_qr_batched_plan_t* plan);
  * makb200_eigh: replaces heevd!/heevr! + gaugefix!(eigh_full!) (yalapack.jl:1164-1362,
  *   yacusolver.jl:766-810, common/gauge.jl:38-45).  Only the upper triangle of A is read
  *   (uplo='U', yalapack.jl:994,1286); A is destroyed.  W: n real eigenvalues ascending;
- *   V: n x n eigenvectors (must not alias A).  info_dev: optional DEVICE int, >0 if the
- *   tridiagonal solver failed to converge.
+ *   V: n x n eigenvectors (must not alias A); V == NULL: values only (eigh_vals!, eigh.jl:157-161,
+ *   LAPACK job 'N'): after the tridiagonalisation the eigenvalues come from a Sturm-count K-section
+ *   kernel (one thread per eigenvalue) and neither the D&C eigenvector GEMMs nor the
+ *   back-transformation run.  info_dev: optional DEVICE int, >0 if the tridiagonal solver failed
+ *   to converge.
  *   Pipeline: blocked Householder tridiagonalisation (HBM-bound column-dot kernel + DMMA her2k),
  *   tridiagonal divide & conquer (makb200_stedc), compact-WY back-transformation, fused gauge. */
 int makb200_hermitian_defect(makb200_handle_t* h, int dtype, int n, const void* A, int lda,

@@ -600,11 +600,11 @@ int makb200_eigh(makb200_handle_t* h, int dtype, int fixgauge, int n, void* A, i
     if (!dtype_ok(dtype)) return -2;
     if (n < 0) return -4;
     if (lda < maxi(1, n)) return -6;
-    if (ldv < maxi(1, n)) return -9;
+    if (V && ldv < maxi(1, n)) return -9;
     if (n == 0) return 0;
     if (!A) return -5;
     if (!W) return -7;
-    if (!V || V == A) return -8;
+    if (V == A) return -8;   // V == NULL: values only (job 'N')
     if (dtype == MAKB200_F64)
         return mak::eigh_t<double>(h, n, (double*)A, lda, W, (double*)V, ldv, fixgauge, work, lwork, info_dev);
     return mak::eigh_t<cplx>(h, n, (cplx*)A, lda, W, (cplx*)V, ldv, fixgauge, work, lwork, info_dev);

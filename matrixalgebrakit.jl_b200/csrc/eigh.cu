@@ -16,6 +16,7 @@
 #include "gemm.cuh"
 #include "qr.cuh"
 #include "stedc.cuh"
+#include "sturm_core.h"
 
 namespace mak {
 
@@ -1007,6 +1008,17 @@ static int eigh_twostage_g(int b) {
     if (g < 1) g = 1;
     return g;
 }
+// ---------------------------------------------------------------------------------------
+// values-only tridiagonal solver: thread k brackets the k-th eigenvalue (sturm_core.h)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) sturm_eigvals_kernel(int n, const double* __restrict__ d,
+                                                           const double* __restrict__ e, double* __restrict__ W) {
+    const int k = blockIdx.x * 32 + threadIdx.x;
+    if (k >= n) return;
+    const sturm::Bounds b = sturm::bounds(n, d, e);
+    W[k] = sturm::kth_eigenvalue(n, d, e, b, k);
+}
+
 template <typename T>
 struct TwoStageWork {
     T* tau1;   // n
@@ -1087,6 +1099,16 @@ int eigh_t(makb200_handle* h, int n, T* A, int lda, double* W, T* V, int ldv, in
         rc = hetrd<T>(h, x);
         if (rc) return rc;
         pt.mark("hetrd");
+    }
+    if (V == nullptr) {
+        // values only (job 'N'): Sturm-count K-section on the tridiagonal, one thread per eigenvalue;
+        // no eigenvector GEMMs, no back-transformation
+        sturm_eigvals_kernel<<<(n + 31) / 32, 32, 0, s>>>(n, x.d, x.e, W);
+        count_launch();
+        MAK_LAUNCH_CHECK(h, "sturm_eigvals_kernel");
+        pt.mark("sturm");
+        pt.report("eigh_vals");
+        return 0;
     }
     double* Z;
     int ldz;

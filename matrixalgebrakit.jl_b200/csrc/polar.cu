@@ -743,10 +743,11 @@ static int svd_tall(makb200_handle* h, int m, int n, T* A, int lda, double* S, T
     int rc = polar_qdwh_t<T>(h, m, n, A, lda, w.Wp, m, w.P, n, l0, 12, w.sub, w.sub_bytes, &iters, info_dev);
     if (rc) return rc;
     pt.mark("polar");
-    rc = eigh_t<T>(h, n, w.P, n, w.wv, w.V, n, 0, w.sub, w.sub_bytes, nullptr);
+    const bool vectors = (U != nullptr && Vh != nullptr);
+    // values only (job 'N'): eigenvalues of P by Sturm K-section, no eigenvectors
+    rc = eigh_t<T>(h, n, w.P, n, w.wv, vectors ? w.V : (T*)nullptr, n, 0, w.sub, w.sub_bytes, nullptr);
     if (rc) return rc;
     pt.mark("eigh");
-    const bool vectors = (U != nullptr && Vh != nullptr);
     int nb32 = (n + 31) / 32;
     T* Vh_eff = vectors ? Vh : nullptr;
     svd_reorder_kernel<T><<<dim3(nb32, nb32), dim3(32, 8), 0, s>>>(n, n, w.wv, w.V, n, S, Vh_eff, ldvh);

@@ -64,7 +64,7 @@ def check_input(A, DV, alg=None, check=True):
     n = A.shape[0]
     if D.dim() != 1 or D.shape[0] != n or D.dtype != torch.float64:
         raise ValueError("D: real vector of length n expected")
-    if tuple(V.shape) != (n, n) or V.dtype != A.dtype or not _core.is_colmajor(V):
+    if V is not None and (tuple(V.shape) != (n, n) or V.dtype != A.dtype or not _core.is_colmajor(V)):
         raise ValueError("V: n x n column-major matrix of A's eltype expected")
 
 
@@ -75,7 +75,7 @@ def _heevd_(A, D, V, fixgauge):
     lw = h.lib.makb200_eigh_worksize(h.h, dt, n)
     work = h.workspace(lw)
     rc = h.lib.makb200_eigh(h.h, dt, int(bool(fixgauge)), n, _core.ptr(A), _core.ld(A), _core.ptr(D), _core.ptr(V),
-                            _core.ld(V), _core.ptr(work), work.numel(), C.c_void_p(0))
+                            _core.ld(V) if V is not None else 0, _core.ptr(work), work.numel(), C.c_void_p(0))
     h.check(rc, "makb200_eigh")
 
 
@@ -116,9 +116,8 @@ def eigh_vals_(A, D=None, alg=None, **kw):
     n = A.shape[0]
     if D is None:
         D = torch.empty(n, dtype=torch.float64, device=A.device)
-    V = _core.colmajor_empty(n, n, A.dtype, A.device)
-    check_input(A, (D, V), alg)
-    _heevd_(A, D, V, False)
+    check_input(A, (D, None), alg)
+    _heevd_(A, D, None, False)   # V = NULL: job 'N' (zero-length V of the reference, yalapack.jl:1192-1195, 1293-1298)
     return D
 
 
