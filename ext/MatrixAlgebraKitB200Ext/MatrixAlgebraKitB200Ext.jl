@@ -66,10 +66,30 @@ function MatrixAlgebraKit.svd_compact_svd_polar!(::B200, A, U, S, Vᴴ; fixgauge
     return U, S, Vᴴ
 end
 
-# check_hermitian in one device pass instead of the allocating fallback (MatrixAlgebraKitCUDAExt.jl:147-152)
+# Hermitian tests in one device pass instead of `A == A'` / the allocating fallback
+# (MatrixAlgebraKitCUDAExt.jl:147-152; common/matrixproperties.jl:86-112)
 function MatrixAlgebraKit.ishermitian_approx(A::B200Mat; atol, rtol, kwargs...)
-    defect, mx = YAB200.hermitian_defect(A)
-    return defect <= max(atol, rtol > 0 ? rtol * norm(A) : zero(atol))
+    defect, _, fro, _ = YAB200.hermitian_props(A, false)
+    return defect <= max(atol, rtol * fro)
+end
+function MatrixAlgebraKit.isantihermitian_approx(A::B200Mat; atol, rtol, kwargs...)
+    defect, _, fro, _ = YAB200.hermitian_props(A, true)
+    return defect <= max(atol, rtol * fro)
+end
+MatrixAlgebraKit.ishermitian_exact(A::B200Mat; kwargs...) = YAB200.hermitian_props(A, false)[4] == 0
+MatrixAlgebraKit.isantihermitian_exact(A::B200Mat; kwargs...) = YAB200.hermitian_props(A, true)[4] == 0
+
+# project_hermitian! / project_antihermitian!: the whole NativeBlocked walk (projections.jl:86-107, per-tile
+# @cuda launches in MatrixAlgebraKitCUDAExt.jl:130-143) as ONE launch; B === A is the default output
+MatrixAlgebraKit.project_hermitian_native!(A::B200Mat, B::B200Mat, ::Val{anti}; kwargs...) where {anti} =
+    YAB200.project_hermitian!(A, B, anti)
+
+# is_left_isometric (matrixproperties.jl:53-58): Gram matrix on the DMMA GEMM, both norms from one reduction
+function MatrixAlgebraKit.is_left_isometric(A::B200Mat; atol::Real = 0, rtol::Real = MatrixAlgebraKit.defaulttol(A), kwargs...)
+    P = similar(A, (size(A, 2), size(A, 2)))
+    YAB200.gemm!('C', 'N', one(eltype(A)), A, A, zero(eltype(A)), P)
+    nP, dP = YAB200.gram_defect(P)
+    return dP <= max(atol, rtol * nP)
 end
 
 # ---- left_polar!(A, (W,P), ::B200_QDWH) ------------------------------------------------------------

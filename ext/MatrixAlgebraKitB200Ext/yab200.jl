@@ -116,6 +116,52 @@ function hermitian_defect(A::StridedCuMatrix{T}) where {T <: B200Float}
     return sqrt(d2), mx
 end
 
+# ---- gemm!: C = α op(A) op(B) + β C on the DMMA kernel (the `mul!` of polar.jl:63,88) ----------
+opcode(c::AbstractChar) = c == 'N' ? Cint(0) : c == 'T' ? Cint(1) : c == 'C' ? Cint(2) : throw(ArgumentError("op $c"))
+function gemm!(opa::AbstractChar, opb::AbstractChar, α::T, A::StridedCuMatrix{T}, B::StridedCuMatrix{T}, β::T,
+        C::StridedCuMatrix{T}) where {T <: B200Float}
+    m, n = size(C)
+    k = opa == 'N' ? size(A, 2) : size(A, 1)
+    rc = ccall((:makb200_gemm, libmakb200), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, Cint, Ref{T}, CuPtr{T}, Cint, CuPtr{T}, Cint, Ref{T}, CuPtr{T}, Cint),
+        handle(), dtypecode(T), opcode(opa), opcode(opb), m, n, k, Ref(α), A, max(1, stride(A, 2)), B, max(1, stride(B, 2)),
+        Ref(β), C, max(1, stride(C, 2)))
+    chkargsok(rc, "makb200_gemm")
+    return C
+end
+
+# B = (A ± Aᴴ)/2 in one launch; B may be A (in place)
+function project_hermitian!(A::StridedCuMatrix{T}, B::StridedCuMatrix{T}, anti::Bool) where {T <: B200Float}
+    n = checksquare(A)
+    size(B) == (n, n) || throw(DimensionMismatch("B must be $n x $n"))
+    rc = ccall((:makb200_project_hermitian, libmakb200), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, CuPtr{T}, Cint, CuPtr{T}, Cint),
+        handle(), dtypecode(T), anti, n, A, max(1, stride(A, 2)), B, max(1, stride(B, 2)))
+    chkargsok(rc, "makb200_project_hermitian")
+    return B
+end
+
+# (‖part that must vanish‖_F, max|A_ij|, ‖A‖_F, #exact mismatches): every ingredient of ishermitian / isantihermitian
+function hermitian_props(A::StridedCuMatrix{T}, anti::Bool) where {T <: B200Float}
+    n = checksquare(A)
+    out = CUDA.zeros(Float64, 4)
+    rc = ccall((:makb200_hermitian_props, libmakb200), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, CuPtr{T}, Cint, CuPtr{Float64}),
+        handle(), dtypecode(T), anti, n, A, max(1, stride(A, 2)), out)
+    chkargsok(rc, "makb200_hermitian_props")
+    d2, mx, f2, bad = Array(out)
+    return sqrt(d2), mx, sqrt(f2), Int(bad)
+end
+
+# (‖P‖_F, ‖P − I‖_F) of a Gram matrix
+function gram_defect(P::StridedCuMatrix{T}) where {T <: B200Float}
+    n = checksquare(P)
+    out = CUDA.zeros(Float64, 2)
+    rc = ccall((:makb200_gram_defect, libmakb200), Cint, (Ptr{Cvoid}, Cint, Cint, CuPtr{T}, Cint, CuPtr{Float64}),
+        handle(), dtypecode(T), n, P, max(1, stride(P, 2)), out)
+    chkargsok(rc, "makb200_gram_defect")
+    p2, d2 = Array(out)
+    return sqrt(p2), sqrt(d2)
+end
+
 # ---- svd: gesvdp!(A, S, U, Vᴴ) (QDWH + eigh; yacusolver.jl:101-181 call shape) ------------------
 function gesvdp!(A::StridedCuMatrix{T}, S::StridedCuVector{Float64}, U::StridedCuMatrix{T}, Vᴴ::StridedCuMatrix{T};
         fixgauge::Bool = false, l0::Float64 = 0.0) where {T <: B200Float}

@@ -126,6 +126,20 @@ int makb200_qr_batched_plan_destroy(makb200_qr_batched_plan_t* plan);
  *   tridiagonal divide & conquer (makb200_stedc), compact-WY back-transformation, fused gauge. */
 int makb200_hermitian_defect(makb200_handle_t* h, int dtype, int n, const void* A, int lda,
                              double* out2_dev);
+/* project_hermitian! / project_antihermitian! (implementations/projections.jl:60-139; on a CuArray the
+ * reference's NativeBlocked loop is O((n/32)^2) broadcasts): B = (A + A^H)/2 (anti = 0) or
+ * (A - A^H)/2 (anti != 0) in ONE launch, entry for entry the reference's arithmetic.  B may be A
+ * (in place, the reference's default output, projections.jl:38-43) or a distinct n x n matrix. */
+int makb200_project_hermitian(makb200_handle_t* h, int dtype, int anti, int n, const void* A, int lda,
+                              void* B, int ldb);
+/* ishermitian / isantihermitian (common/matrixproperties.jl:77-195), every ingredient in one pass:
+ * out4_dev (DEVICE double[4]) = { ||part that must vanish||_F^2  (anti = 0: (A - A^H)/2),
+ * max |A_ij|, ||A||_F^2, number of entries i <= j with A_ij != +-conj(A_ji) (the exact test) }. */
+int makb200_hermitian_props(makb200_handle_t* h, int dtype, int anti, int n, const void* A, int lda,
+                            double* out4_dev);
+/* is_left_isometric (common/matrixproperties.jl:53-58) on the Gram matrix P = A^H A (makb200_gemm):
+ * out2_dev (DEVICE double[2]) = { ||P||_F^2, ||P - I||_F^2 }. */
+int makb200_gram_defect(makb200_handle_t* h, int dtype, int n, const void* P, int ldp, double* out2_dev);
 size_t makb200_eigh_worksize(makb200_handle_t* h, int dtype, int n);
 int makb200_eigh(makb200_handle_t* h, int dtype, int fixgauge, int n, void* A, int lda, double* W,
                  void* V, int ldv, void* work, size_t lwork, int* info_dev);

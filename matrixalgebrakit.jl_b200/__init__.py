@@ -28,3 +28,6 @@ from .orthnull import (adjoint_, left_null, left_null_, left_orth, left_orth_, l
 from . import partition  # noqa: E402,F401
 from .partition import gather_block_info, lpt_partition, my_blocks  # noqa: E402,F401
 from .sbr import sbr_apply_q2_, sbr_chase_, sy2sb_  # noqa: E402,F401  (experimental)
+from .projections import (defaulttol, is_left_isometric, is_right_isometric, isantihermitian, ishermitian,  # noqa: E402,F401
+                          isisometric, isunitary, project_antihermitian, project_antihermitian_, project_hermitian,
+                          project_hermitian_, project_isometric, project_isometric_)

@@ -589,6 +589,44 @@ int makb200_hermitian_defect(makb200_handle_t* h, int dtype, int n, const void* 
     return mak::herm_defect_t<cplx>(h, n, (const cplx*)A, lda, out2_dev);
 }
 
+int makb200_project_hermitian(makb200_handle_t* h, int dtype, int anti, int n, const void* A, int lda, void* B,
+                              int ldb) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (n < 0) return -4;
+    if (lda < maxi(1, n)) return -6;
+    if (ldb < maxi(1, n)) return -8;
+    if (n == 0) return 0;
+    if (!A) return -5;
+    if (!B) return -7;
+    if (B == A && ldb != lda) return -8;   // in place means the same matrix, not an overlapping one
+    if (dtype == MAKB200_F64) return mak::project_herm_t<double>(h, anti != 0, n, (const double*)A, lda, (double*)B, ldb);
+    return mak::project_herm_t<cplx>(h, anti != 0, n, (const cplx*)A, lda, (cplx*)B, ldb);
+}
+
+int makb200_hermitian_props(makb200_handle_t* h, int dtype, int anti, int n, const void* A, int lda,
+                            double* out4_dev) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (n < 0) return -4;
+    if (lda < maxi(1, n)) return -6;
+    if (!out4_dev) return -7;
+    if (n > 0 && !A) return -5;
+    if (dtype == MAKB200_F64) return mak::herm_props_t<double>(h, anti != 0, n, (const double*)A, lda, out4_dev);
+    return mak::herm_props_t<cplx>(h, anti != 0, n, (const cplx*)A, lda, out4_dev);
+}
+
+int makb200_gram_defect(makb200_handle_t* h, int dtype, int n, const void* P, int ldp, double* out2_dev) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (n < 0) return -3;
+    if (ldp < maxi(1, n)) return -5;
+    if (!out2_dev) return -6;
+    if (n > 0 && !P) return -4;
+    if (dtype == MAKB200_F64) return mak::gram_defect_t<double>(h, n, (const double*)P, ldp, out2_dev);
+    return mak::gram_defect_t<cplx>(h, n, (const cplx*)P, ldp, out2_dev);
+}
+
 size_t makb200_eigh_worksize(makb200_handle_t* h, int dtype, int n) {
     if (!h || !dtype_ok(dtype) || n < 0) return 0;
     return dtype == MAKB200_F64 ? mak::eigh_worksize_t<double>(h, n) : mak::eigh_worksize_t<cplx>(h, n);

@@ -17,6 +17,7 @@
 #include "qr.cuh"
 #include "stedc.cuh"
 #include "sturm_core.h"
+#include "projections.cuh"
 
 namespace mak {
 
@@ -983,6 +984,47 @@ int herm_defect_t(makb200_handle* h, int n, const T* A, int lda, double* out2) {
 }
 template int herm_defect_t<double>(makb200_handle*, int, const double*, int, double*);
 template int herm_defect_t<cplx>(makb200_handle*, int, const cplx*, int, double*);
+
+// project_hermitian! / project_antihermitian! (B may be A), the Hermitian property pass and the isometry
+// defect of a Gram matrix: one launch each (projections.cuh)
+template <typename T>
+int project_herm_t(makb200_handle* h, int anti, int n, const T* A, int lda, T* B, int ldb) {
+    if (n <= 0) return 0;
+    const int nb = (n + 31) / 32;
+    if (anti) project_herm_kernel<T, true><<<dim3(nb, nb), dim3(32, 8), 0, h->stream>>>(n, A, lda, B, ldb);
+    else project_herm_kernel<T, false><<<dim3(nb, nb), dim3(32, 8), 0, h->stream>>>(n, A, lda, B, ldb);
+    count_launch();
+    MAK_LAUNCH_CHECK(h, "project_herm_kernel");
+    return 0;
+}
+template <typename T>
+int herm_props_t(makb200_handle* h, int anti, int n, const T* A, int lda, double* out4) {
+    MAK_CUDA(h, cudaMemsetAsync(out4, 0, 4 * sizeof(double), h->stream));
+    if (n <= 0) return 0;
+    const int nb = (n + 31) / 32;
+    if (anti) herm_props_kernel<T, true><<<dim3(nb, nb), dim3(32, 8), 0, h->stream>>>(n, A, lda, out4);
+    else herm_props_kernel<T, false><<<dim3(nb, nb), dim3(32, 8), 0, h->stream>>>(n, A, lda, out4);
+    count_launch();
+    MAK_LAUNCH_CHECK(h, "herm_props_kernel");
+    return 0;
+}
+template <typename T>
+int gram_defect_t(makb200_handle* h, int n, const T* P, int ldp, double* out2) {
+    MAK_CUDA(h, cudaMemsetAsync(out2, 0, 2 * sizeof(double), h->stream));
+    if (n <= 0) return 0;
+    const size_t total = (size_t)n * n;
+    const size_t want = (total + 255) / 256, cap = (size_t)h->num_sms * 8;
+    gram_defect_kernel<T><<<(unsigned)(want < cap ? want : cap), 256, 0, h->stream>>>(n, P, ldp, out2);
+    count_launch();
+    MAK_LAUNCH_CHECK(h, "gram_defect_kernel");
+    return 0;
+}
+#define INST_PROJ(T)                                                                          \
+    template int project_herm_t<T>(makb200_handle*, int, int, const T*, int, T*, int);        \
+    template int herm_props_t<T>(makb200_handle*, int, int, const T*, int, double*);          \
+    template int gram_defect_t<T>(makb200_handle*, int, const T*, int, double*);
+INST_PROJ(double)
+INST_PROJ(cplx)
 
 // EXPERIMENTAL two-stage path (MAKB200_EIGH_TWOSTAGE=<bandwidth 8..64>, "1" = 64; default off):
 // dense -> band (sy2sb, qr.cu) -> tridiagonal (bulge chasing, sbr.cu) -> D&C -> Q2 (diamond blocks)

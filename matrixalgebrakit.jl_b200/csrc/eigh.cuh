@@ -2,6 +2,11 @@
 #include "common.cuh"
 namespace mak {
 template <typename T> int herm_defect_t(makb200_handle* h, int n, const T* A, int lda, double* out2);
+// B = (A +- A^H)/2 (B may be A); out4 = {||vanishing part||_F^2, max|A_ij|, ||A||_F^2, #exact mismatches};
+// out2 = {||P||_F^2, ||P - I||_F^2}
+template <typename T> int project_herm_t(makb200_handle* h, int anti, int n, const T* A, int lda, T* B, int ldb);
+template <typename T> int herm_props_t(makb200_handle* h, int anti, int n, const T* A, int lda, double* out4);
+template <typename T> int gram_defect_t(makb200_handle* h, int n, const T* P, int ldp, double* out2);
 template <typename T> size_t eigh_worksize_t(makb200_handle* h, int n);
 template <typename T>
 int eigh_t(makb200_handle* h, int n, T* A, int lda, double* W, T* V, int ldv, int fixgauge, void* work, size_t lwork,

@@ -5,6 +5,7 @@
 #include "../../matrixalgebrakit.jl_b200/csrc/batched_qr_warp.cuh"
 #include "../../matrixalgebrakit.jl_b200/csrc/sbr_chase_persistent.cuh"
 #include "../../matrixalgebrakit.jl_b200/csrc/sbr_q2_slab.cuh"
+#include "../../matrixalgebrakit.jl_b200/csrc/projections.cuh"
 
 using mak::cplx;
 
@@ -121,4 +122,38 @@ extern "C" int emu_q2_slab(int dt, int n, int b, int g, int cw, const void* V2, 
     emu::set_order(order, seed);
     return dt == 0 ? run_q2_slab<double>(n, b, g, cw, (const double*)V2, ldv, (const double*)tau2, ldt, (double*)Z, ldz, ncols)
                    : run_q2_slab<cplx>(n, b, g, cw, (const cplx*)V2, ldv, (const cplx*)tau2, ldt, (cplx*)Z, ldz, ncols);
+}
+
+// projections.cuh: the launch shapes are those of project_herm_t / herm_props_t / gram_defect_t (eigh.cu)
+template <typename T>
+static void run_project(int anti, int n, const T* A, int lda, T* B, int ldb) {
+    const int nb = (n + 31) / 32;
+    if (anti) emu::launch(mak::project_herm_kernel<T, true>, dim3(nb, nb), dim3(32, 8), 0, n, A, lda, B, ldb);
+    else emu::launch(mak::project_herm_kernel<T, false>, dim3(nb, nb), dim3(32, 8), 0, n, A, lda, B, ldb);
+}
+extern "C" int emu_project_herm(int dt, int anti, int n, const void* A, int lda, void* B, int ldb, int order, uint64_t seed) {
+    emu::set_order(order, seed);
+    if (dt == 0) run_project<double>(anti, n, (const double*)A, lda, (double*)B, ldb);
+    else run_project<cplx>(anti, n, (const cplx*)A, lda, (cplx*)B, ldb);
+    return 0;
+}
+template <typename T>
+static void run_props(int anti, int n, const T* A, int lda, double* out4) {
+    const int nb = (n + 31) / 32;
+    for (int i = 0; i < 4; ++i) out4[i] = 0.0;
+    if (anti) emu::launch(mak::herm_props_kernel<T, true>, dim3(nb, nb), dim3(32, 8), 0, n, A, lda, out4);
+    else emu::launch(mak::herm_props_kernel<T, false>, dim3(nb, nb), dim3(32, 8), 0, n, A, lda, out4);
+}
+extern "C" int emu_herm_props(int dt, int anti, int n, const void* A, int lda, double* out4, int order, uint64_t seed) {
+    emu::set_order(order, seed);
+    if (dt == 0) run_props<double>(anti, n, (const double*)A, lda, out4);
+    else run_props<cplx>(anti, n, (const cplx*)A, lda, out4);
+    return 0;
+}
+extern "C" int emu_gram_defect(int dt, int n, const void* P, int ldp, double* out2, int grid, int order, uint64_t seed) {
+    emu::set_order(order, seed);
+    out2[0] = out2[1] = 0.0;
+    if (dt == 0) emu::launch(mak::gram_defect_kernel<double>, dim3(grid), dim3(256), 0, n, (const double*)P, ldp, out2);
+    else emu::launch(mak::gram_defect_kernel<cplx>, dim3(grid), dim3(256), 0, n, (const cplx*)P, ldp, out2);
+    return 0;
 }

@@ -191,3 +191,78 @@ def test_emu_q2_slab(lib, sbr_lib, dtype, n, b, g, cw, ncols):
         assert np.abs(X - Xref).max() <= 200 * n * EPS * max(np.abs(Xref).max(), 1.0)
     # Q2 is unitary: the fused result keeps column norms
     assert np.allclose(np.linalg.norm(X, axis=0), np.linalg.norm(Z0, axis=0), rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------
+# projections.cuh: project_hermitian! / ishermitian / isisometric kernels
+# ---------------------------------------------------------------------------------------------------
+def _ref_project(A, anti):
+    """Entry for entry the reference's arithmetic (implementations/projections.jl:109-139)."""
+    return (A - A.conj().T) / 2 if anti else (A + A.conj().T) / 2
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("anti", [0, 1])
+@pytest.mark.parametrize("n,pad", [(1, 0), (5, 3), (32, 0), (33, 1), (70, 0), (97, 5)])
+def test_emu_project_hermitian(lib, n, pad, anti, dtype):
+    A0 = O.randn_matrix(n, n, dtype, seed=n + anti)
+    ref = _ref_project(A0, anti)
+    dt = 0 if dtype == "f64" else 1
+    for order, seed in ORDERS:
+        # out of place, strided input
+        Abuf = np.zeros((n + pad, n), dtype=A0.dtype, order="F")
+        Abuf[:n] = A0
+        B = np.full((n, n), np.nan, dtype=A0.dtype, order="F")
+        lib.emu_project_herm(dt, anti, n, _vp(Abuf), n + pad, _vp(B), n, order, ctypes.c_uint64(seed))
+        assert np.array_equal(B, ref)                      # bit for bit
+        assert np.array_equal(Abuf[:n], A0) and not Abuf[n:].any()
+        # in place (B === A, the reference's default output)
+        lib.emu_project_herm(dt, anti, n, _vp(Abuf), n + pad, _vp(Abuf), n + pad, order, ctypes.c_uint64(seed))
+        assert np.array_equal(Abuf[:n], ref) and not Abuf[n:].any()
+    d = np.diag(ref)
+    assert np.all(d.real == 0) if anti else np.all(d.imag == 0)
+    assert np.array_equal(ref, -ref.conj().T if anti else ref.conj().T)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("anti", [0, 1])
+@pytest.mark.parametrize("n", [1, 7, 32, 45, 100])
+def test_emu_herm_props(lib, n, anti, dtype):
+    dt = 0 if dtype == "f64" else 1
+    G = O.randn_matrix(n, n, dtype, seed=3 * n + anti)
+    H = _ref_project(G, anti)                              # exactly (anti-)Hermitian
+    out = np.zeros(4)
+    for order, seed in ORDERS:
+        lib.emu_herm_props(dt, anti, n, _vp(np.asfortranarray(H)), n, _vp(out), order, ctypes.c_uint64(seed))
+        assert out[0] == 0 and out[3] == 0
+        assert np.isclose(out[1], np.abs(H).max(), rtol=1e-15) and np.isclose(out[2], np.linalg.norm(H) ** 2, rtol=1e-13)
+        lib.emu_herm_props(dt, anti, n, _vp(G), n, _vp(out), order, ctypes.c_uint64(seed))
+        van = _ref_project(G, 1 - anti)                    # the part that must vanish
+        assert np.isclose(out[0], np.linalg.norm(van) ** 2, rtol=1e-13)
+        assert np.isclose(out[1], np.abs(G).max(), rtol=1e-15) and np.isclose(out[2], np.linalg.norm(G) ** 2, rtol=1e-13)
+        want = -G.conj().T if anti else G.conj().T
+        assert out[3] == np.count_nonzero(np.triu(G != want))
+    # one perturbed entry below the diagonal is seen by the exact test, and a strided view is read correctly
+    if n > 1:
+        Hp = np.zeros((n + 3, n), dtype=H.dtype, order="F")
+        Hp[:n] = H
+        Hp[n - 1, 0] += 1e-9
+        lib.emu_herm_props(dt, anti, n, _vp(Hp), n + 3, _vp(out), 0, ctypes.c_uint64(0))
+        assert out[3] == 1 and np.isclose(out[0], 2 * (0.5e-9) ** 2, rtol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("n,grid", [(1, 1), (20, 1), (65, 3), (130, 8)])
+def test_emu_gram_defect(lib, n, grid, dtype):
+    dt = 0 if dtype == "f64" else 1
+    A = O.randn_matrix(n + 5, n, dtype, seed=n)
+    P = np.asfortranarray(A.conj().T @ A)
+    out = np.zeros(2)
+    for order, seed in ORDERS:
+        lib.emu_gram_defect(dt, n, _vp(P), n, _vp(out), grid, order, ctypes.c_uint64(seed))
+        assert np.isclose(out[0], np.linalg.norm(P) ** 2, rtol=1e-13)
+        assert np.isclose(out[1], np.linalg.norm(P - np.eye(n)) ** 2, rtol=1e-13)
+    Q, _ = np.linalg.qr(A)
+    P = np.asfortranarray(Q.conj().T @ Q)
+    lib.emu_gram_defect(dt, n, _vp(P), n, _vp(out), grid, 0, ctypes.c_uint64(0))
+    assert np.sqrt(out[1]) <= 1e-13 * np.sqrt(out[0]) * n
