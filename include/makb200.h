@@ -169,6 +169,16 @@ int makb200_svd(makb200_handle_t* h, int dtype, int fixgauge, int m, int n, void
                 void* U, int ldu, void* Vh, int ldvh, double l0, void* work, size_t lwork,
                 int* info_dev);
 
+/* svd_trunc! with the rank known before the decomposition (truncrank(r): svd.jl:226-237,
+ * truncation.jl:54-58; BASELINE config 5 keeps 1024 of 16384 triplets).  The reference computes the
+ * full compact SVD and slices; here S still receives ALL k = min(m,n) singular values (the truncation
+ * error needs the discarded ones) but only the r leading triplets' vectors are formed: the
+ * back-transformation runs on r columns and U is an m x r x n product.  U: m x r, Vh: r x n
+ * (ldvh >= r), 1 <= r <= k; same workspace as makb200_svd; gauge as in makb200_svd. */
+int makb200_svd_leading(makb200_handle_t* h, int dtype, int fixgauge, int m, int n, int r, void* A, int lda,
+                        double* S, void* U, int ldu, void* Vh, int ldvh, double l0, void* work,
+                        size_t lwork, int* info_dev);
+
 /* -- TSQR building block: local tall-skinny QR of one row shard ------------------------------
  * New capability: qr_compact! of a row-sharded m x n matrix (m >> n) =
  * local factorization per rank + binary-tree reduction of the n x n R factors over NCCL (host

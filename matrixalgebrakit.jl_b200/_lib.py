@@ -53,6 +53,7 @@ SIGNATURES = {
     "makb200_polar_qdwh": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, C.c_double, _i, _vp, _sz, _ip, _vp]),
     "makb200_svd_worksize": (_sz, [_vp, _i, _i, _i]),
     "makb200_svd": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, C.c_double, _vp, _sz, _vp]),
+    "makb200_svd_leading": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, C.c_double, _vp, _sz, _vp]),
     "makb200_tsqr_local_worksize": (_sz, [_vp, _i, _i, _i]),
     "makb200_tsqr_local": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _sz, _vp]),
     "makb200_sbr_chase_worksize": (_sz, [_vp, _i, _i, _i]),

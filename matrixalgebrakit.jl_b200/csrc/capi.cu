@@ -722,6 +722,29 @@ int makb200_svd(makb200_handle_t* h, int dtype, int fixgauge, int m, int n, void
                             lwork, info_dev);
 }
 
+int makb200_svd_leading(makb200_handle_t* h, int dtype, int fixgauge, int m, int n, int r, void* A, int lda, double* S,
+                        void* U, int ldu, void* Vh, int ldvh, double l0, void* work, size_t lwork, int* info_dev) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (m < 0) return -4;
+    if (n < 0) return -5;
+    const int k = m < n ? m : n;
+    if (r < 0 || r > k) return -6;
+    if (lda < maxi(1, m)) return -8;
+    if (ldu < maxi(1, m)) return -11;
+    if (ldvh < maxi(1, r)) return -13;
+    if (m == 0 || n == 0 || r == 0) return r == 0 && m > 0 && n > 0 ? -6 : 0;   // r = 0: use makb200_svd with U = Vh = NULL
+    if (!A) return -7;
+    if (!S) return -9;
+    if (!U || U == A) return -10;
+    if (!Vh || Vh == A) return -12;
+    if (dtype == MAKB200_F64)
+        return mak::svd_t<double>(h, m, n, (double*)A, lda, S, (double*)U, ldu, (double*)Vh, ldvh, fixgauge,
+                                  qdwh_l0(l0), work, lwork, info_dev, r);
+    return mak::svd_t<cplx>(h, m, n, (cplx*)A, lda, S, (cplx*)U, ldu, (cplx*)Vh, ldvh, fixgauge, qdwh_l0(l0), work,
+                            lwork, info_dev, r);
+}
+
 
 // ---- tall-skinny local QR for TSQR ------------------------------------------------------
 size_t makb200_tsqr_local_worksize(makb200_handle_t* h, int dtype, int m, int n) {

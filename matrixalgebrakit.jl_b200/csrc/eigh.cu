@@ -1109,8 +1109,12 @@ size_t eigh_worksize_t(makb200_handle* h, int n) {
 
 template <typename T>
 int eigh_t(makb200_handle* h, int n, T* A, int lda, double* W, T* V, int ldv, int fixgauge, void* work, size_t lwork,
-           int* info_dev) {
+           int* info_dev, int top) {
     if (n <= 0) return 0;
+    // top in (0, n): only the eigenvectors of the `top` largest eigenvalues (the last columns of V) are
+    // back-transformed and gauged; the leading n - top columns of V are left holding scratch
+    const int c0 = (top > 0 && top < n) ? n - top : 0;
+    const int nc = n - c0;
     cudaStream_t s = h->stream;
     Arena ar(work, lwork);
     TrdCtx<T> x;
@@ -1168,20 +1172,20 @@ int eigh_t(makb200_handle* h, int n, T* A, int lda, double* W, T* V, int ldv, in
     if (two_stage) {
         // X = Q1 Q2 Z: chase reflectors in diamond blocks, then the stage-1 block reflectors
         // (QR-type columns of A[b:, 0:n-b])
-        rc = sbr_apply_q2_t<T>(h, n, b2, eigh_twostage_g(b2), ts.V2, n, ts.tau2, ts.ldt, V, ldv, n, sub, sb);
+        rc = sbr_apply_q2_t<T>(h, n, b2, eigh_twostage_g(b2), ts.V2, n, ts.tau2, ts.ldt, V + (size_t)c0 * ldv, ldv, nc, sub, sb);
         if (rc) return rc;
         pt.mark("q2");
-        rc = ormqr_left_t<T>(h, n - b2, n - b2, A + b2, lda, ts.tau1, V + b2, ldv, n, sub, sb);
+        rc = ormqr_left_t<T>(h, n - b2, n - b2, A + b2, lda, ts.tau1, V + (size_t)c0 * ldv + b2, ldv, nc, sub, sb);
         if (rc) return rc;
         pt.mark("q1");
     } else if (n > 1) {
         // V[1:, :] <- H_0 ... H_{n-2} V[1:, :]; reflectors = QR-type columns of B = A[1:, 0:n-1]
-        rc = ormqr_left_t<T>(h, n - 1, n - 1, A + 1, lda, x.tau, V + 1, ldv, n, sub, sb);
+        rc = ormqr_left_t<T>(h, n - 1, n - 1, A + 1, lda, x.tau, V + (size_t)c0 * ldv + 1, ldv, nc, sub, sb);
         if (rc) return rc;
     }
     pt.mark("backtransform");
     count_launch(3);  // mirror, last_d, gauge
-    if (fixgauge) rc = gauge_columns<T>(h, n, n, V, ldv, (T*)nullptr, 0, 0);
+    if (fixgauge) rc = gauge_columns<T>(h, n, nc, V + (size_t)c0 * ldv, ldv, (T*)nullptr, 0, 0);
     pt.mark("gauge");
     pt.report("eigh");
     return rc;
@@ -1189,7 +1193,7 @@ int eigh_t(makb200_handle* h, int n, T* A, int lda, double* W, T* V, int ldv, in
 
 template size_t eigh_worksize_t<double>(makb200_handle*, int);
 template size_t eigh_worksize_t<cplx>(makb200_handle*, int);
-template int eigh_t<double>(makb200_handle*, int, double*, int, double*, double*, int, int, void*, size_t, int*);
-template int eigh_t<cplx>(makb200_handle*, int, cplx*, int, double*, cplx*, int, int, void*, size_t, int*);
+template int eigh_t<double>(makb200_handle*, int, double*, int, double*, double*, int, int, void*, size_t, int*, int);
+template int eigh_t<cplx>(makb200_handle*, int, cplx*, int, double*, cplx*, int, int, void*, size_t, int*, int);
 
 }  // namespace mak

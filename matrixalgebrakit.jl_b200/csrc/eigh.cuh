@@ -10,7 +10,7 @@ template <typename T> int gram_defect_t(makb200_handle* h, int n, const T* P, in
 template <typename T> size_t eigh_worksize_t(makb200_handle* h, int n);
 template <typename T>
 int eigh_t(makb200_handle* h, int n, T* A, int lda, double* W, T* V, int ldv, int fixgauge, void* work, size_t lwork,
-           int* info_dev);
+           int* info_dev, int top = 0);   // V == nullptr: values only; 0 < top < n: only the last `top` eigenvectors
 // V[:, j] *= conj(sign(pivot_j)); optional `other` (k x other_n, row j scaled by sign(pivot_j))
 template <typename T>
 int gauge_columns(makb200_handle* h, int m, int ncols, T* V, int ldv, T* other, int ldo, int other_n);

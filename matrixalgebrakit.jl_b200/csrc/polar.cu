@@ -676,7 +676,7 @@ int polar_qdwh_t(makb200_handle* h, int m, int n, T* A, int lda, T* W, int ldw, 
 // ---------------------------------------------------------------------------------------
 // SVD via polar + eigh
 // ---------------------------------------------------------------------------------------
-// S[j] = max(w[n-1-j], 0);  Vh[j, :] = conj(V[:, n-1-j])   (descending order)
+// S[j] = max(w[n-1-j], 0) for j < n;  Vh[j, :] = conj(V[:, n-1-j]) for j < k   (descending order)
 template <typename T>
 __global__ void svd_reorder_kernel(int n, int k, const double* __restrict__ w, const T* __restrict__ V, int ldv,
                                    double* __restrict__ S, T* __restrict__ Vh, int ldvh) {
@@ -694,7 +694,7 @@ __global__ void svd_reorder_kernel(int n, int k, const double* __restrict__ w, c
     }
     if (bi == 0 && ty == 0) {
         int j = bj * 32 + tx;
-        if (j < k) { double v = w[n - 1 - j]; S[j] = v > 0.0 ? v : 0.0; }
+        if (j < n) { double v = w[n - 1 - j]; S[j] = v > 0.0 ? v : 0.0; }
     }
 }
 
@@ -732,9 +732,11 @@ size_t svd_worksize_t(makb200_handle* h, int m, int n) {
     return ar.off + 256;
 }
 
-// tall/square core: A (m x n, m >= n) -> U (m x n), S (n), Vh (n x n); U/Vh may be null (values)
+// tall/square core: A (m x n, m >= n) -> U (m x r), S (n, always all values), Vh (r x n); U/Vh may be null
+// (values).  r = n is the compact SVD; r < n (svd_trunc! with a rank known up front) back-transforms
+// only the r leading eigenvectors of P and forms U with an m x r x n product.
 template <typename T>
-static int svd_tall(makb200_handle* h, int m, int n, T* A, int lda, double* S, T* U, int ldu, T* Vh, int ldvh,
+static int svd_tall(makb200_handle* h, int m, int n, int r, T* A, int lda, double* S, T* U, int ldu, T* Vh, int ldvh,
                     int fixgauge, double l0, SvdWork<T>& w, int* info_dev) {
     cudaStream_t s = h->stream;
     int iters = 0;
@@ -745,20 +747,20 @@ static int svd_tall(makb200_handle* h, int m, int n, T* A, int lda, double* S, T
     pt.mark("polar");
     const bool vectors = (U != nullptr && Vh != nullptr);
     // values only (job 'N'): eigenvalues of P by Sturm K-section, no eigenvectors
-    rc = eigh_t<T>(h, n, w.P, n, w.wv, vectors ? w.V : (T*)nullptr, n, 0, w.sub, w.sub_bytes, nullptr);
+    rc = eigh_t<T>(h, n, w.P, n, w.wv, vectors ? w.V : (T*)nullptr, n, 0, w.sub, w.sub_bytes, nullptr, r);
     if (rc) return rc;
     pt.mark("eigh");
     int nb32 = (n + 31) / 32;
     T* Vh_eff = vectors ? Vh : nullptr;
-    svd_reorder_kernel<T><<<dim3(nb32, nb32), dim3(32, 8), 0, s>>>(n, n, w.wv, w.V, n, S, Vh_eff, ldvh);
+    svd_reorder_kernel<T><<<dim3(nb32, nb32), dim3(32, 8), 0, s>>>(n, r, w.wv, w.V, n, S, Vh_eff, ldvh);
     count_launch();
     MAK_LAUNCH_CHECK(h, "svd_reorder_kernel");
     if (vectors) {
         // U = W * V_desc = W * Vh^H
-        MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, m, n, n, one<T>(), w.Wp, m, Vh, ldvh, zero<T>(), U, ldu,
+        MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, m, r, n, one<T>(), w.Wp, m, Vh, ldvh, zero<T>(), U, ldu,
                   nullptr, 0);
         if (fixgauge) {
-            rc = gauge_columns<T>(h, m, n, U, ldu, Vh, ldvh, n);
+            rc = gauge_columns<T>(h, m, r, U, ldu, Vh, ldvh, n);
             if (rc) return rc;
         }
     }
@@ -769,31 +771,34 @@ static int svd_tall(makb200_handle* h, int m, int n, T* A, int lda, double* S, T
 
 template <typename T>
 int svd_t(makb200_handle* h, int m, int n, T* A, int lda, double* S, T* U, int ldu, T* Vh, int ldvh, int fixgauge,
-          double l0, void* work, size_t lwork, int* info_dev) {
+          double l0, void* work, size_t lwork, int* info_dev, int r) {
     if (m <= 0 || n <= 0) return 0;
+    const int kk = m < n ? m : n;
+    if (r <= 0 || r > kk) r = kk;   // leading triplets wanted (all singular values are always returned)
     cudaStream_t s = h->stream;
     Arena ar(work, lwork);
     SvdWork<T> w;
     svd_carve<T>(h, ar, m, n, &w);
     if (!ar.ok) return MAKB200_ERR_WORKSPACE;
-    if (m >= n) return svd_tall<T>(h, m, n, A, lda, S, U, ldu, Vh, ldvh, fixgauge, l0, w, info_dev);
+    if (m >= n) return svd_tall<T>(h, m, n, r, A, lda, S, U, ldu, Vh, ldvh, fixgauge, l0, w, info_dev);
     // wide: SVD of A^H (svd_via_adjoint!, implementations/svd.jl:134-142): A^H = U' S V'^H
     //   => A = V' S U'^H : U = (Vh')^H (m x m), Vh = (U')^H (m x n)
     const bool vectors = (U != nullptr && Vh != nullptr);
     dim3 g((m + 31) / 32, (n + 31) / 32);
     adjoint_kernel<T><<<g, dim3(32, 8), 0, s>>>(m, n, A, lda, w.At, n);
     count_launch();
-    int rc = svd_tall<T>(h, n, m, w.At, n, S, vectors ? w.Ut : nullptr, n, vectors ? w.Vht : nullptr, m, 0, l0, w,
+    int rc = svd_tall<T>(h, n, m, r, w.At, n, S, vectors ? w.Ut : nullptr, n, vectors ? w.Vht : nullptr, m, 0, l0, w,
                          info_dev);
     if (rc) return rc;
     if (vectors) {
-        dim3 g1((m + 31) / 32, (m + 31) / 32);
-        adjoint_kernel<T><<<g1, dim3(32, 8), 0, s>>>(m, m, w.Vht, m, U, ldu);
-        dim3 g2((n + 31) / 32, (m + 31) / 32);
-        adjoint_kernel<T><<<g2, dim3(32, 8), 0, s>>>(n, m, w.Ut, n, Vh, ldvh);
+        // Vht (r x m, ld m) -> U (m x r);  Ut (n x r, ld n) -> Vh (r x n)
+        dim3 g1((r + 31) / 32, (m + 31) / 32);
+        adjoint_kernel<T><<<g1, dim3(32, 8), 0, s>>>(r, m, w.Vht, m, U, ldu);
+        dim3 g2((n + 31) / 32, (r + 31) / 32);
+        adjoint_kernel<T><<<g2, dim3(32, 8), 0, s>>>(n, r, w.Ut, n, Vh, ldvh);
         count_launch(2);
         MAK_LAUNCH_CHECK(h, "adjoint_kernel");
-        if (fixgauge) return gauge_columns<T>(h, m, m, U, ldu, Vh, ldvh, n);
+        if (fixgauge) return gauge_columns<T>(h, m, r, U, ldu, Vh, ldvh, n);
     }
     return 0;
 }
@@ -1016,7 +1021,7 @@ template int adjoint_t<cplx>(makb200_handle*, int, int, const cplx*, int, cplx*,
                                  size_t, int*, int*);                                                        \
     template size_t svd_worksize_t<T>(makb200_handle*, int, int);                                            \
     template int svd_t<T>(makb200_handle*, int, int, T*, int, double*, T*, int, T*, int, int, double, void*, \
-                          size_t, int*);                                                                     \
+                          size_t, int*, int);                                                                     \
     template size_t cholqr2_worksize_t<T>(makb200_handle*, int, int);                                        \
     template int cholqr2_t<T>(makb200_handle*, int, int, T*, int, T*, int, T*, int, void*, size_t, int*, int);
 INSTP(double)

@@ -10,7 +10,7 @@ int polar_qdwh_t(makb200_handle* h, int m, int n, T* A, int lda, T* W, int ldw, 
 template <typename T> size_t svd_worksize_t(makb200_handle* h, int m, int n);
 template <typename T>
 int svd_t(makb200_handle* h, int m, int n, T* A, int lda, double* S, T* U, int ldu, T* Vh, int ldvh, int fixgauge,
-          double l0, void* work, size_t lwork, int* info_dev);
+          double l0, void* work, size_t lwork, int* info_dev, int r = 0);   // 0 < r < min(m,n): U m x r, Vh r x n
 // tall-skinny local QR (CholeskyQR2; nshift > 0: shifted CholeskyQR with that many preconditioning
 // passes) used by TSQR; A is overwritten, diag(R) > 0
 template <typename T> size_t cholqr2_worksize_t(makb200_handle* h, int m, int n);

@@ -8,7 +8,7 @@ import torch
 
 from . import _core
 from .algorithms import Algorithm, TruncatedAlgorithm, resolve_driver, select_algorithm
-from .truncation import findtruncated_svd, select_truncation, truncation_error_
+from .truncation import TruncationByOrder, findtruncated_svd, select_truncation, truncation_error_
 
 
 def initialize_output(A):
@@ -117,9 +117,44 @@ def _truncate(U, S, Vh, strategy):
     return (Ut, S[ind].clone(), Vt), ind
 
 
+def _leading_rank(A, USVh, talg):
+    """Rank r when the kept set is known before the decomposition — ``truncrank(r)`` keeps the r leading
+    triplets of the sorted spectrum (truncation.jl:54-58) — and the caller did not hand in full-size
+    outputs; else None (values-dependent strategies need the full decomposition first)."""
+    s = talg.trunc
+    k = min(A.shape)
+    if USVh is not None or not isinstance(s, TruncationByOrder) or not s.rev or A.numel() == 0:
+        return None
+    return s.howmany if 0 < s.howmany < k else None
+
+
+def _svd_leading_(A, r, alg):
+    """Leading-r SVD in one C call (``makb200_svd_leading``): all k singular values, vectors of the r
+    leading triplets only (partial back-transformation, m x r x n product for U)."""
+    _alg_ok(alg)
+    if not _core.is_colmajor(A):
+        raise ValueError("A: column-major matrix expected")
+    h = _core.Handle.get(A.device)
+    m, n = A.shape
+    dt = _core.dtype_code(A)
+    S = torch.empty(min(m, n), dtype=torch.float64, device=A.device)
+    U = _core.colmajor_empty(m, r, A.dtype, A.device)
+    Vh = _core.colmajor_empty(r, n, A.dtype, A.device)
+    work = h.workspace(h.lib.makb200_svd_worksize(h.h, dt, m, n))
+    rc = h.lib.makb200_svd_leading(h.h, dt, int(bool(alg.get("fixgauge", True))), m, n, r, _core.ptr(A), _core.ld(A),
+                                   _core.ptr(S), _core.ptr(U), _core.ld(U), _core.ptr(Vh), _core.ld(Vh), 0.0,
+                                   _core.ptr(work), work.numel(), C.c_void_p(0))
+    h.check(rc, "makb200_svd_leading")
+    return U, S, Vh
+
+
 def svd_trunc_no_error_(A, USVh=None, alg=None, trunc=None, **kw):
     """``svd_trunc_no_error!`` (svd.jl:226-230): no device->host read of the error."""
     talg = _select_trunc_alg(A, alg, trunc, kw)
+    r = _leading_rank(A, USVh, talg)
+    if r is not None:
+        U, S, Vh = _svd_leading_(A, r, talg.alg)
+        return U, S[:r].clone(), Vh
     U, S, Vh = svd_compact_(A, USVh, talg.alg)
     out, _ = _truncate(U, S, Vh, talg.trunc)
     return out
@@ -127,8 +162,15 @@ def svd_trunc_no_error_(A, USVh=None, alg=None, trunc=None, **kw):
 
 def svd_trunc_(A, USVh=None, alg=None, trunc=None, **kw):
     """``svd_trunc!`` (svd.jl:232-237): full compact SVD, slice, eps = norm of the discarded
-    values; clobbers the untruncated S (truncation.jl:171-174)."""
+    values; clobbers the untruncated S (truncation.jl:171-174).  With ``truncrank(r)`` and no
+    caller-provided outputs only the r leading triplets' vectors are formed (same values and error)."""
     talg = _select_trunc_alg(A, alg, trunc, kw)
+    r = _leading_rank(A, USVh, talg)
+    if r is not None:
+        U, S, Vh = _svd_leading_(A, r, talg.alg)
+        St = S[:r].clone()
+        eps_ = truncation_error_(S, torch.arange(r, device=S.device))
+        return U, St, Vh, eps_
     U, S, Vh = svd_compact_(A, USVh, talg.alg)
     out, ind = _truncate(U, S, Vh, talg.trunc)
     eps_ = truncation_error_(S, ind)

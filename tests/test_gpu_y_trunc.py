@@ -1,0 +1,66 @@
+"""svd_trunc! with a rank known up front (truncrank(r); svd.jl:226-237, truncation.jl:54-58): the
+leading-r path (makb200_svd_leading: partial back-transformation, m x r x n product for U) must give
+what the reference's "full compact SVD, then slice" gives.  Sorted after the GPU-verified suites
+(see test_gpu_y_projections.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mak_oracle as O
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(float).eps
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("m,n,r", [(54, 37, 17), (37, 54, 17), (54, 54, 1), (54, 54, 53), (200, 200, 64),
+                                   (300, 130, 33), (130, 300, 100), (5, 3, 2), (600, 600, 100)])
+def test_svd_trunc_rank_matches_full_then_slice(m, n, r, dtype):
+    import makb200
+    A0 = O.randn_matrix(m, n, dtype, seed=m + 3 * n + r)
+    U, S, Vh, eps = makb200.svd_trunc(makb200.to_device(A0), trunc=makb200.truncrank(r))
+    Un, Sn, Vn = makb200.to_numpy(U), S.cpu().numpy(), makb200.to_numpy(Vh)
+    assert Un.shape == (m, r) and Sn.shape == (r,) and Vn.shape == (r, n)
+    tol = O.tol_for(m, n)
+    # the reference's recipe on the LAPACK oracle
+    Uo, So, Vho, epso = O.svd_trunc(A0, O.truncrank(r))
+    assert np.max(np.abs(Sn - So)) / So[0] <= tol
+    assert abs(eps - epso) <= tol * So[0] * np.sqrt(min(m, n))
+    assert O.orth_err(Un) <= tol and O.orth_err(Vn, "right") <= tol
+    # best rank-r approximation: ||A - U S Vh||_F = eps
+    assert abs(np.linalg.norm(A0 - (Un * Sn) @ Vn) - epso) <= tol * np.linalg.norm(A0)
+    # gauge (common/gauge.jl:69-77): the entry of largest modulus of every column of U is real positive
+    piv = Un[np.argmax(np.abs(Un), axis=0), np.arange(r)]
+    assert np.all(np.abs(piv.imag) <= 1e-14) and np.all(piv.real > 0)
+    # the same triplets as the full decomposition sliced (vectors up to rounding: same algorithm, fewer columns)
+    Uf, Sf, Vf = makb200.svd_compact(makb200.to_device(A0))
+    Sf = Sf.cpu().numpy()
+    assert np.max(np.abs(Sn - Sf[:r])) <= 4 * EPS * Sf[0]
+    gap = np.min(np.abs(np.diff(Sf[: r + 1]))) / Sf[0] if r < min(m, n) else np.min(np.abs(np.diff(Sf))) / Sf[0]
+    vtol = 100 * tol / max(gap, 1e-8)
+    assert np.linalg.norm(Un - makb200.to_numpy(Uf)[:, :r]) <= vtol
+    assert np.linalg.norm(Vn - makb200.to_numpy(Vf)[:r, :]) <= vtol
+
+
+def test_svd_trunc_rank_no_error_kwargs_and_preallocated():
+    import makb200
+    A0 = O.randn_matrix(80, 60, "f64", seed=5)
+    U, S, Vh = makb200.svd_trunc_no_error(makb200.to_device(A0), trunc=makb200.truncrank(10))
+    assert tuple(U.shape) == (80, 10) and tuple(S.shape) == (10,) and tuple(Vh.shape) == (10, 60)
+    So = O.svd_vals(A0)
+    np.testing.assert_allclose(S.cpu().numpy(), So[:10], rtol=1e-12)
+    # keyword form (TruncationStrategy(; maxrank), interface/truncation.jl:37-66) takes the same path
+    U2, S2, Vh2, eps2 = makb200.svd_trunc(makb200.to_device(A0), trunc={"maxrank": 10})
+    assert tuple(U2.shape) == (80, 10) and abs(eps2 - np.linalg.norm(So[10:])) <= 1e-12 * So[0]
+    # rank >= k: nothing to truncate, full path
+    U3, S3, Vh3, eps3 = makb200.svd_trunc(makb200.to_device(A0), trunc=makb200.truncrank(100))
+    assert tuple(U3.shape) == (80, 60) and eps3 == 0.0
+    # caller-provided full-size outputs: the reference's full decomposition into them, then the slice
+    out = makb200.svd.initialize_output(makb200.to_device(A0))
+    U4, S4, Vh4, eps4 = makb200.svd_trunc_(makb200.to_device(A0), out, trunc=makb200.truncrank(10))
+    assert tuple(U4.shape) == (80, 10) and abs(eps4 - eps2) <= 1e-12 * So[0]
+    assert O.orth_err(makb200.to_numpy(out[0])) <= O.tol_for(80, 60)       # the full U was computed
+    # fixgauge=False is honoured
+    U5, S5, Vh5, _ = makb200.svd_trunc(makb200.to_device(A0), trunc=makb200.truncrank(10), fixgauge=False)
+    assert O.rel_resid(makb200.to_numpy(U2) * S2.cpu().numpy(), makb200.to_numpy(U5) * S5.cpu().numpy(),
+                       makb200.to_numpy(Vh5) @ makb200.to_numpy(Vh2).conj().T) <= 1e-10
