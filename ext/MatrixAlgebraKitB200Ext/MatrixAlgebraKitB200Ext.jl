@@ -102,6 +102,25 @@ function left_polar!(A::AbstractMatrix, WP, alg::B200_QDWH)
     return W, P
 end
 
+# svd_trunc!(A, alg) with truncrank(r) and no caller-provided outputs: only the r leading triplets' vectors are
+# formed (implementations/svd.jl:226-237 computes the full compact SVD and slices).  Same values, same ϵ.
+function _leading(A::B200Mat, alg::MatrixAlgebraKit.TruncatedAlgorithm{<:SVDViaPolar, <:MatrixAlgebraKit.TruncationByOrder})
+    t = alg.trunc
+    r, k = t.howmany, min(size(A)...)
+    (t.by === abs && t.rev && 0 < r < k) || return nothing
+    S = CUDA.zeros(Float64, k)
+    U, Vᴴ = similar(A, (size(A, 1), r)), similar(A, (r, size(A, 2)))
+    YAB200.svd_leading!(A, r, S, U, Vᴴ; fixgauge = get(alg.alg.kwargs, :fixgauge, true))
+    return U, S, Vᴴ, r
+end
+function MatrixAlgebraKit.svd_trunc!(A::B200Mat, alg::MatrixAlgebraKit.TruncatedAlgorithm{<:SVDViaPolar, <:MatrixAlgebraKit.TruncationByOrder})
+    res = _leading(A, alg)
+    res === nothing && return MatrixAlgebraKit.svd_trunc!(A, MatrixAlgebraKit.initialize_output(svd_trunc!, A, alg), alg)
+    U, S, Vᴴ, r = res
+    ϵ = norm(view(S, (r + 1):length(S)))
+    return U, Diagonal(S[1:r]), Vᴴ, ϵ
+end
+
 # sorted-values truncation search on the device vector (same as MatrixAlgebraKitCUDAExt.jl:64-66)
 MatrixAlgebraKit.findtruncated_svd(values::StridedCuVector, strategy::TruncationByValue) =
     MatrixAlgebraKit.findtruncated(values, strategy)

@@ -180,6 +180,23 @@ function gesvdp!(A::StridedCuMatrix{T}, S::StridedCuVector{Float64}, U::StridedC
     return S, U, Vᴴ
 end
 
+# leading-r SVD (svd_trunc! with truncrank(r)): S gets all k values, U is m×r, Vᴴ is r×n
+function svd_leading!(A::StridedCuMatrix{T}, r::Int, S::StridedCuVector{Float64}, U::StridedCuMatrix{T}, Vᴴ::StridedCuMatrix{T};
+        fixgauge::Bool = true, l0::Float64 = 0.0) where {T <: B200Float}
+    m, n = size(A)
+    size(U) == (m, r) && size(Vᴴ) == (r, n) && length(S) == min(m, n) || throw(DimensionMismatch("svd_leading!: U m×r, S min(m,n), Vᴴ r×n"))
+    h = handle()
+    lw = ccall((:makb200_svd_worksize, libmakb200), Csize_t, (Ptr{Cvoid}, Cint, Cint, Cint), h, dtypecode(T), m, n)
+    with_workspace(lw) do work
+        rc = ccall((:makb200_svd_leading, libmakb200), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, CuPtr{T}, Cint, CuPtr{Float64}, CuPtr{T}, Cint, CuPtr{T}, Cint, Cdouble, CuPtr{UInt8}, Csize_t, CuPtr{Cint}),
+            h, dtypecode(T), fixgauge, m, n, r, A, max(1, stride(A, 2)), S, U, max(1, stride(U, 2)), Vᴴ, max(1, stride(Vᴴ, 2)),
+            l0, work, lw, CU_NULL)
+        chkargsok(rc, "makb200_svd_leading")
+    end
+    return U, S, Vᴴ
+end
+
 # ---- polar: QDWH ----------------------------------------------------------------------------------
 function polar_qdwh!(A::StridedCuMatrix{T}, W::StridedCuMatrix{T}, P::StridedCuMatrix{T}; l0::Float64 = 0.0, maxiter::Int = 12) where {T <: B200Float}
     m, n = size(A)
