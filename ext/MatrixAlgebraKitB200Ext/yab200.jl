@@ -197,6 +197,29 @@ function svd_leading!(A::StridedCuMatrix{T}, r::Int, S::StridedCuVector{Float64}
     return U, S, Vᴴ
 end
 
+# rank and truncation error of every block of a batch from one launch (findtruncated_svd + truncation_error!,
+# implementations/truncation.jl:54-102,168-174); spec mirrors `makb200_trunc_spec`
+struct TruncSpec
+    maxrank::Cint; minrank::Cint; by_value::Cint; by_error::Cint
+    vatol::Cdouble; vrtol::Cdouble; vp::Cdouble
+    eatol::Cdouble; ertol::Cdouble; ep::Cdouble
+end
+function trunc_select_batched(Ss::Vector{<:StridedCuVector{Float64}}, spec::TruncSpec)
+    b = length(Ss)
+    ks = Cint[length(S) for S in Ss]
+    ptrs = [reinterpret(Ptr{Cvoid}, pointer(S)) for S in Ss]
+    rank, eps = CUDA.zeros(Cint, b), CUDA.zeros(Float64, b)
+    h = handle()
+    lw = ccall((:makb200_trunc_select_batched_worksize, libmakb200), Csize_t, (Ptr{Cvoid}, Cint), h, b)
+    with_workspace(lw) do work
+        rc = ccall((:makb200_trunc_select_batched, libmakb200), Cint,
+            (Ptr{Cvoid}, Cint, Ptr{Cint}, Ptr{Ptr{Cvoid}}, Ref{TruncSpec}, CuPtr{Cint}, CuPtr{Float64}, CuPtr{UInt8}, Csize_t),
+            h, b, ks, ptrs, Ref(spec), rank, eps, work, lw)
+        chkargsok(rc, "makb200_trunc_select_batched")
+    end
+    return Array(rank), Array(eps)
+end
+
 # ---- polar: QDWH ----------------------------------------------------------------------------------
 function polar_qdwh!(A::StridedCuMatrix{T}, W::StridedCuMatrix{T}, P::StridedCuMatrix{T}; l0::Float64 = 0.0, maxiter::Int = 12) where {T <: B200Float}
     m, n = size(A)

@@ -214,12 +214,31 @@ int makb200_svd_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch,
  * semantics = eigh_full!(A_i,(D_i,V_i)) incl. the eigh gauge, implementations/eigh.jl:123-156).
  * One CTA per block, two-sided Jacobi in shared memory (uplo='U' is read, A is NOT destroyed);
  * blocks that do not fit are routed through makb200_eigh (those ARE destroyed).
- * n,lda,ldv: HOST int arrays; A,W,V: HOST arrays of DEVICE pointers (V == NULL: values only, then
- * every block must fit the shared-memory kernel).  info: DEVICE int[batch] or NULL. */
+ * n,lda,ldv: HOST int arrays; A,W,V: HOST arrays of DEVICE pointers (V == NULL: values only).  info: DEVICE int[batch] or NULL. */
 size_t makb200_eigh_batched_worksize(makb200_handle_t* h, int dtype, int batch, const int* n);
 int makb200_eigh_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch, const int* n,
                          void* const* A, const int* lda, void* const* W, void* const* V,
                          const int* ldv, int* info, void* work, size_t lwork);
+
+/* -- truncation search for svd_trunc! over a batch of sorted spectra -----------------------------
+ * findtruncated_svd + truncation_error! (implementations/truncation.jl:54-102,168-174) for the strategy
+ * TruncationStrategy(; atol, rtol, maxrank, maxerror, minrank) builds (interface/truncation.jl:37-66):
+ *   ( truncrank(maxrank) & trunctol(vatol, vrtol, vp) & truncerror(eatol, ertol, ep) ) | truncrank(minrank)
+ * with every absent component switched off (maxrank / minrank < 0, by_value / by_error = 0).  On sorted
+ * singular values each component keeps a prefix, so the result is a rank.  The reference's GPU path
+ * copies every values vector to the host (MatrixAlgebraKitCUDAExt.jl:64-66); here rank_dev[i] and
+ * eps_dev[i] = ||S_i[rank_i:]||_2 for ALL blocks come from one launch (one thread per block).
+ * k: HOST int[batch]; S: HOST array of DEVICE pointers (descending values); rank_dev / eps_dev: DEVICE. */
+typedef struct makb200_trunc_spec {
+    int maxrank, minrank;      /* < 0: not set */
+    int by_value, by_error;    /* 0: not set */
+    double vatol, vrtol, vp;   /* trunctol:   keep |s| >= max(vatol, vrtol ||S||_vp) */
+    double eatol, ertol, ep;   /* truncerror: discarded ||.||_ep < max(eatol, ertol ||S||_ep) */
+} makb200_trunc_spec;
+size_t makb200_trunc_select_batched_worksize(makb200_handle_t* h, int batch);
+int makb200_trunc_select_batched(makb200_handle_t* h, int batch, const int* k, double* const* S,
+                                 const makb200_trunc_spec* spec, int* rank_dev, double* eps_dev,
+                                 void* work, size_t lwork);
 
 /* -- adjoint: B (n x m) = A^H.  Used by the LQ family, which every GPU driver of the reference
  * routes through QR of the adjoint (lq_via_qr!, implementations/lq.jl:130-131,303-327), and by

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmakb200.so")
-SOURCES = ["gemm.cu", "qr.cu", "batched.cu", "batched_blocked.cu", "stedc.cu", "sbr.cu", "eigh.cu", "polar.cu", "capi.cu"]
+SOURCES = ["gemm.cu", "qr.cu", "batched.cu", "batched_blocked.cu", "stedc.cu", "sbr.cu", "eigh.cu", "polar.cu", "truncation.cu", "capi.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC"]
 

@@ -900,11 +900,11 @@ static int eigh_batched_t(makb200_handle_t* h, int fixgauge, int batch, const in
         rc = mak::batched_eigh_smem<T>(h, (int)small2.size(), max_b2, ddev + small.size(), nullptr);
         if (rc) return rc;
     }
-    if (!big.empty() && !V) return -9;   // the single-matrix path always forms vectors
     char* wbig = (char*)work + ar.off;
     size_t lbig = lwork > ar.off ? lwork - ar.off : 0;
     return run_pooled(h, big, wbig, lbig, [&](makb200_handle_t* hh, char* w, size_t lw, int i) {
-        return mak::eigh_t<T>(hh, n[i], (T*)A[i], lda[i], (double*)W[i], (T*)V[i], ldv[i], fixgauge, w, lw, nullptr);
+        return mak::eigh_t<T>(hh, n[i], (T*)A[i], lda[i], (double*)W[i], V ? (T*)V[i] : (T*)nullptr, V ? ldv[i] : n[i],
+                              fixgauge, w, lw, nullptr);   // V == NULL: values only (Sturm K-section)
     });
 }
 

@@ -1,6 +1,8 @@
-"""Truncation strategies — host side, as in the reference (src/interface/truncation.jl:37-275,
-src/implementations/truncation.jl:45-174).  The values vector is short (k reals): the index
-search runs on a host copy, like the reference's GPU path (MatrixAlgebraKitCUDAExt.jl:64-66)."""
+"""Truncation strategies (src/interface/truncation.jl:37-275, src/implementations/truncation.jl:45-174).
+Single matrix: the values vector is short (k reals) and the index search runs on a host copy, like the
+reference's GPU path (MatrixAlgebraKitCUDAExt.jl:64-66).  Batches (``trunc_select_batched_``): rank and
+truncation error of every block from one kernel launch and one device->host read."""
+import ctypes as C
 from dataclasses import dataclass
 
 import numpy as np
@@ -171,3 +173,77 @@ def truncation_error_(values, ind):
     in place, return the 2-norm of the rest (a device scalar read)."""
     values[ind] = 0.0
     return float(torch.linalg.vector_norm(values).item())
+
+
+# ---------------------------------------------------------------------------------------------------
+# batched, device side (makb200_trunc_select_batched)
+# ---------------------------------------------------------------------------------------------------
+class TruncSpec(C.Structure):
+    """``makb200_trunc_spec`` (include/makb200.h)."""
+    _fields_ = [("maxrank", C.c_int), ("minrank", C.c_int), ("by_value", C.c_int), ("by_error", C.c_int),
+                ("vatol", C.c_double), ("vrtol", C.c_double), ("vp", C.c_double),
+                ("eatol", C.c_double), ("ertol", C.c_double), ("ep", C.c_double)]
+
+
+def _spec_and(spec, s):
+    """Fold one prefix-keeping component into ``spec``; False if it cannot be encoded."""
+    if isinstance(s, NoTruncation):
+        return True
+    if isinstance(s, TruncationByOrder) and s.rev:
+        spec.maxrank = s.howmany if spec.maxrank < 0 else min(spec.maxrank, s.howmany)
+        return True
+    if isinstance(s, TruncationByValue) and not s.keep_below and not spec.by_value and np.isfinite(s.p) and s.p > 0:
+        spec.by_value, spec.vatol, spec.vrtol, spec.vp = 1, s.atol, s.rtol, float(s.p)
+        return True
+    if isinstance(s, TruncationByError) and not spec.by_error and np.isfinite(s.p) and s.p > 0:
+        spec.by_error, spec.eatol, spec.ertol, spec.ep = 1, s.atol, s.rtol, float(s.p)
+        return True
+    if isinstance(s, TruncationIntersection):
+        return all(_spec_and(spec, c) for c in s.components)
+    return False
+
+
+def device_spec(strategy):
+    """``makb200_trunc_spec`` of a strategy of the shape ``TruncationStrategy(; atol, rtol, maxrank,
+    maxerror, minrank)`` builds — (rank & tol & error) | minrank — or None when the strategy keeps
+    something other than a prefix of the sorted values (``rev=false``, ``keep_below``) or nests deeper."""
+    spec = TruncSpec(-1, -1, 0, 0, 0.0, 0.0, 2.0, 0.0, 0.0, 2.0)
+    s = strategy
+    if isinstance(s, TruncationUnion):
+        mins = [c for c in s.components if isinstance(c, TruncationByOrder) and c.rev]
+        rest = [c for c in s.components if not (isinstance(c, TruncationByOrder) and c.rev)]
+        if len(rest) != 1 or not mins:
+            return None
+        spec.minrank = max(c.howmany for c in mins)
+        s = rest[0]
+        if isinstance(s, NoTruncation):
+            return None
+        before = (spec.maxrank, spec.by_value, spec.by_error)
+        if not _spec_and(spec, s) or (spec.maxrank, spec.by_value, spec.by_error) == before:
+            return None
+        return spec
+    return spec if _spec_and(spec, s) else None
+
+
+def trunc_select_batched_(Ss, spec):
+    """(ranks, eps) as host lists for the sorted spectra ``Ss`` (device vectors): one launch, one read."""
+    from . import _core
+    b = len(Ss)
+    if b == 0:
+        return [], []
+    dev = Ss[0].device
+    h = _core.Handle.get(dev)
+    for S in Ss:
+        if S.dtype != torch.float64 or S.dim() != 1 or (S.numel() > 1 and S.stride(0) != 1):
+            raise ValueError("trunc_select_batched_: contiguous real vectors expected")
+    k = (C.c_int * b)(*[S.numel() for S in Ss])
+    Sp = (C.c_void_p * b)(*[S.data_ptr() for S in Ss])
+    out = torch.empty(2 * b, dtype=torch.float64, device=dev)
+    rank = out[:b].view(torch.int32)[:b]          # int32[b] carved from the same allocation
+    eps = out[b:]
+    work = h.workspace(h.lib.makb200_trunc_select_batched_worksize(h.h, b))
+    rc = h.lib.makb200_trunc_select_batched(h.h, b, k, Sp, C.byref(spec), _core.ptr(rank), _core.ptr(eps),
+                                            _core.ptr(work), work.numel())
+    h.check(rc, "makb200_trunc_select_batched")
+    host = out.cpu()                               # the one device->host read
+    return host[:b].view(torch.int32)[:b].tolist(), host[b:].tolist()

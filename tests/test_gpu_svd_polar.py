@@ -172,7 +172,7 @@ def test_svd_batched_vs_oracle(dtype):
     for a, (U, S, Vh) in zip(As0, outs):
         _check_svd(a, makb200.to_numpy(U), S.cpu().numpy(), makb200.to_numpy(Vh))
     tr = makb200.svd_trunc_batched_([makb200.to_device(a) for a in As0[:6]], makb200.truncrank(5))
-    for a, (U, S, Vh, ind) in zip(As0[:6], tr):
+    for a, (U, S, Vh, eps) in zip(As0[:6], tr):
         So = O.svd_vals(a)
         k = min(5, len(So))
         np.testing.assert_allclose(S.cpu().numpy(), So[:k], rtol=1e-11)

@@ -64,3 +64,69 @@ def test_svd_trunc_rank_no_error_kwargs_and_preallocated():
     U5, S5, Vh5, _ = makb200.svd_trunc(makb200.to_device(A0), trunc=makb200.truncrank(10), fixgauge=False)
     assert O.rel_resid(makb200.to_numpy(U2) * S2.cpu().numpy(), makb200.to_numpy(U5) * S5.cpu().numpy(),
                        makb200.to_numpy(Vh5) @ makb200.to_numpy(Vh2).conj().T) <= 1e-10
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_svd_trunc_batched_device_select(dtype):
+    """Batched svd_trunc!: rank and error of every block from makb200_trunc_select_batched (one launch, one
+    read) must equal the per-block host search of the reference recipe on the oracle's values."""
+    import makb200
+    from makb200 import truncation as T
+    rng = np.random.default_rng(3)
+    sizes = [(16, 16), (17, 9), (9, 17), (32, 32), (54, 37), (64, 64), (1, 1), (70, 70)]
+    sizes += [(int(s), int(s)) for s in rng.integers(16, 64, size=12)]
+    As0 = [O.randn_matrix(m, n, dtype, seed=900 + i) for i, (m, n) in enumerate(sizes)]
+    for trunc in (makb200.truncrank(5), makb200.trunctol(rtol=0.21), makb200.truncerror(rtol=0.33),
+                  {"atol": 1.7, "maxrank": 12, "minrank": 2}, {"maxerror": 2.9, "maxrank": 30}):
+        strategy = T.select_truncation(trunc)
+        assert T.device_spec(strategy) is not None
+        res = makb200.svd_trunc_batched_([makb200.to_device(a) for a in As0], trunc)
+        assert len(res) == len(As0)
+        for a, (U, S, Vh, eps) in zip(As0, res):
+            So = O.svd_vals(a)
+            ind = T._find(So, strategy, svd=True)
+            r = len(ind)
+            assert tuple(U.shape) == (a.shape[0], r) and tuple(S.shape) == (r,) and tuple(Vh.shape) == (r, a.shape[1]), \
+                (trunc, a.shape, r, tuple(S.shape))
+            np.testing.assert_allclose(S.cpu().numpy(), So[:r], rtol=1e-11, atol=1e-13)
+            assert abs(eps - np.linalg.norm(So[r:])) <= 1e-11 * So[0]
+            Un, Vn = U.cpu().numpy(), Vh.cpu().numpy()
+            if r:
+                assert O.orth_err(Un) <= O.tol_for(*a.shape) and O.orth_err(Vn, "right") <= O.tol_for(*a.shape)
+                assert abs(np.linalg.norm(a - (Un * S.cpu().numpy()) @ Vn) - np.linalg.norm(So[r:])) <= 1e-11 * So[0]
+    # a strategy outside the prefix family takes the per-block host path, same return shape
+    res = makb200.svd_trunc_batched_([makb200.to_device(a) for a in As0[:4]], makb200.trunctol(atol=1.0, keep_below=True))
+    for a, (U, S, Vh, eps) in zip(As0[:4], res):
+        So = O.svd_vals(a)
+        keep = So <= 1.0
+        np.testing.assert_allclose(S.cpu().numpy(), So[keep], rtol=1e-11, atol=1e-13)
+        assert abs(eps - np.linalg.norm(So[~keep])) <= 1e-11 * So[0]
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_eigh_batched_values_only_including_large_blocks(dtype):
+    """makb200_eigh_batched with V == NULL: small blocks through the one-CTA kernel, blocks beyond its
+    shared-memory limit through makb200_eigh's values-only (Sturm) path."""
+    import ctypes as C
+    import makb200
+    from makb200 import _core
+    ns = [8, 24, 40, 64, 90, 150, 260]
+    As0 = [O.rand_hermitian(n, dtype, seed=40 + n) for n in ns]
+    As = [makb200.to_device(a) for a in As0]
+    Ws = [torch.empty(n, dtype=torch.float64, device="cuda:0") for n in ns]
+    h = _core.Handle.get(As[0].device)
+    b = len(ns)
+    IA, VP = C.c_int * b, C.c_void_p * b
+    n_ = IA(*ns)
+    lda = IA(*[_core.ld(A) for A in As])
+    dt = _core.dtype_code(As[0])
+    lw = h.lib.makb200_eigh_batched_worksize(h.h, dt, b, n_)
+    work = h.workspace(lw)
+    rc = h.lib.makb200_eigh_batched(h.h, dt, 0, b, n_, VP(*[A.data_ptr() for A in As]), lda,
+                                    VP(*[W.data_ptr() for W in Ws]), None, None, C.c_void_p(0), _core.ptr(work),
+                                    work.numel())
+    h.check(rc, "makb200_eigh_batched")
+    torch.cuda.synchronize()
+    for a, W, n in zip(As0, Ws, ns):
+        wref = O.eigh_vals(a)
+        assert np.max(np.abs(W.cpu().numpy() - wref)) / np.abs(wref).max() <= 10 * n * EPS
