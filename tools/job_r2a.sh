@@ -5,6 +5,10 @@
 set -u
 mkdir -p gpurun_out
 {
+echo "== kernels written after the round-1 GPU budget (ungated): values-only, leading-rank, batched truncation, projections =="
+timeout 900 python -m pytest tests/test_gpu_y_vals.py tests/test_gpu_y_trunc.py tests/test_gpu_y_projections.py -q 2>&1 | tail -15
+echo "== timings: eigh_vals vs eigh_full (8192 f64), svd_vals vs svd_compact, svd_trunc r=1024 vs full (8192) =="
+timeout 600 python tools/vals_time.py 8192 1024
 echo "== bring-up parity =="
 MAKB200_BRINGUP=1 timeout 900 python -m pytest tests/test_gpu_zz_bringup.py -q -x 2>&1 | tail -15
 echo "== chase: wavefront launches vs persistent (n=8192) =="
