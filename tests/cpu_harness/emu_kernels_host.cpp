@@ -6,6 +6,7 @@
 #include "../../matrixalgebrakit.jl_b200/csrc/sbr_chase_persistent.cuh"
 #include "../../matrixalgebrakit.jl_b200/csrc/sbr_q2_slab.cuh"
 #include "../../matrixalgebrakit.jl_b200/csrc/projections.cuh"
+#include "../../matrixalgebrakit.jl_b200/csrc/bhetrd.cuh"
 
 using mak::cplx;
 
@@ -156,4 +157,23 @@ extern "C" int emu_gram_defect(int dt, int n, const void* P, int ldp, double* ou
     if (dt == 0) emu::launch(mak::gram_defect_kernel<double>, dim3(grid), dim3(256), 0, n, (const double*)P, ldp, out2);
     else emu::launch(mak::gram_defect_kernel<cplx>, dim3(grid), dim3(256), 0, n, (const cplx*)P, ldp, out2);
     return 0;
+}
+
+// bhetrd.cuh: one CTA per block, launch shape of bhetrd_batched_t (eigh.cu)
+template <typename T>
+static int run_bhetrd(int batch, const int* n, void** A, const int* lda, void** d, void** e, void** tau, int mirror) {
+    std::vector<mak::BhetrdDesc<T>> descs(batch);
+    int nmax = 1;
+    for (int i = 0; i < batch; ++i) {
+        descs[i] = mak::BhetrdDesc<T>{n[i], (T*)A[i], lda[i], (double*)d[i], (double*)e[i], (T*)tau[i]};
+        if (n[i] > nmax) nmax = n[i];
+    }
+    emu::launch(mak::bhetrd_kernel<T>, dim3(batch), dim3(mak::BHETRD_THREADS), mak::bhetrd_smem_elems(nmax) * sizeof(T),
+                (const mak::BhetrdDesc<T>*)descs.data(), nmax, mirror);
+    return 0;
+}
+extern "C" int emu_bhetrd(int dt, int batch, const int* n, void** A, const int* lda, void** d, void** e, void** tau,
+                          int mirror, int order, uint64_t seed) {
+    emu::set_order(order, seed);
+    return dt == 0 ? run_bhetrd<double>(batch, n, A, lda, d, e, tau, mirror) : run_bhetrd<cplx>(batch, n, A, lda, d, e, tau, mirror);
 }

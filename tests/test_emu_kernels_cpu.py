@@ -266,3 +266,58 @@ def test_emu_gram_defect(lib, n, grid, dtype):
     P = np.asfortranarray(Q.conj().T @ Q)
     lib.emu_gram_defect(dt, n, _vp(P), n, _vp(out), grid, 0, ctypes.c_uint64(0))
     assert np.sqrt(out[1]) <= 1e-13 * np.sqrt(out[0]) * n
+
+
+# ---------------------------------------------------------------------------------------------------
+# bhetrd.cuh: one-CTA-per-block Hermitian tridiagonalisation (round-2 bring-up kernel)
+# ---------------------------------------------------------------------------------------------------
+def _q_from_reflectors(Aout, tau):
+    """Q = H_0 ... H_{n-2}, H_j = I - tau_j v_j v_j^H, v_j = [0_{j+1}; 1; Aout[j+2:, j]]."""
+    n = Aout.shape[0]
+    Q = np.eye(n, dtype=Aout.dtype)
+    for j in range(n - 2, -1, -1):
+        v = np.zeros(n, dtype=Aout.dtype)
+        v[j + 1] = 1.0
+        v[j + 2:] = Aout[j + 2:, j]
+        Q -= tau[j] * np.outer(v, v.conj() @ Q)
+    return Q
+
+
+@pytest.mark.parametrize("mirror", [0, 1])
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_emu_bhetrd_batch(lib, dtype, mirror):
+    dt = 0 if dtype == "f64" else 1
+    ns = [1, 2, 3, 17, 33, 64, 70]
+    for order, seed in ORDERS[mirror:mirror + 2]:
+        As0 = [O.rand_hermitian(n, dtype, seed=50 + n) for n in ns]
+        As0[3] = np.asfortranarray(np.diag(np.arange(1.0, 18.0)).astype(As0[3].dtype))   # already tridiagonal: tau = 0 steps
+        pads = [0, 1, 0, 3, 0, 5, 0]
+        bufs = []
+        for a, p in zip(As0, pads):
+            b = np.zeros((a.shape[0] + p, a.shape[0]), dtype=a.dtype, order="F")
+            b[:a.shape[0]] = a
+            if mirror:
+                b[np.tril_indices(a.shape[0], -1)] = 777.0     # uplo = 'U': the lower triangle is garbage on entry
+            else:
+                b[np.triu_indices(a.shape[0], 1)] = 777.0      # the upper triangle must never be read
+            bufs.append(b)
+        ds = [np.zeros(n) for n in ns]
+        es = [np.zeros(max(n - 1, 1)) for n in ns]
+        taus = [np.zeros(max(n - 1, 1), dtype=As0[0].dtype) for n in ns]
+        rc = lib.emu_bhetrd(dt, len(ns), _ints(ns), _ptrs(bufs), _ints([b.shape[0] for b in bufs]), _ptrs(ds), _ptrs(es),
+                            _ptrs(taus), mirror, order, ctypes.c_uint64(seed))
+        assert rc == 0
+        for a, b, d, e, tau, n in zip(As0, bufs, ds, es, taus, ns):
+            assert not b[n:].any()
+            if mirror:
+                assert np.array_equal(b[:n][np.triu_indices(n, 1)], a[np.triu_indices(n, 1)])   # upper untouched
+            else:
+                assert np.all(b[np.triu_indices(n, 1)] == 777.0)
+            T = np.diag(d) + np.diag(e[:n - 1], 1) + np.diag(e[:n - 1], -1)
+            assert np.all(e[:n - 1] >= 0)                               # non-negative-beta reflectors
+            wref = np.linalg.eigvalsh(a)
+            scale = max(np.abs(wref).max(), 1.0)
+            assert np.max(np.abs(np.linalg.eigvalsh(T) - wref)) <= 10 * n * EPS * scale
+            Q = _q_from_reflectors(b[:n], tau)
+            assert np.linalg.norm(Q.conj().T @ Q - np.eye(n)) <= 10 * n * EPS
+            assert np.linalg.norm(Q.conj().T @ a @ Q - T) <= 10 * n * EPS * np.linalg.norm(a)
