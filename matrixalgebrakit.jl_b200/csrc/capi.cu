@@ -8,6 +8,7 @@
 #include "stedc.cuh"
 #include "polar.cuh"
 #include "sbr.cuh"
+#include "bhetrd.cuh"
 #include <vector>
 #include <algorithm>
 #include <atomic>
@@ -866,6 +867,10 @@ int makb200_svd_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch,
 }  // extern "C"
 
 // ---- batched eigh -------------------------------------------------------------------------
+static bool bhetrd_enabled() {
+    const char* e = getenv("MAKB200_BHETRD");   // read per call: the bring-up tests toggle it
+    return e && e[0] == '1';
+}
 template <typename T>
 static int eigh_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int* n, void* const* A, const int* lda,
                           void* const* W, void* const* V, const int* ldv, int* info, void* work, size_t lwork) {
@@ -900,11 +905,39 @@ static int eigh_batched_t(makb200_handle_t* h, int fixgauge, int batch, const in
         rc = mak::batched_eigh_smem<T>(h, (int)small2.size(), max_b2, ddev + small.size(), nullptr);
         if (rc) return rc;
     }
+    // EXPERIMENTAL (MAKB200_BHETRD=1, round-2 bring-up): tridiagonalise every big block with n <= BHETRD_MAX_N in
+    // ONE launch (one CTA per block, csrc/bhetrd.cuh) instead of two launches per column per block; the pooled
+    // per-block path then starts at the tridiagonal solver.
+    std::vector<mak::TrdPre<T>> pre(batch, mak::TrdPre<T>{nullptr, nullptr, nullptr});
+    if (bhetrd_enabled() && !big.empty()) {
+        std::vector<mak::BhetrdDesc<T>> bd;
+        int nmax = 0;
+        for (int i : big) {
+            if (n[i] > mak::BHETRD_MAX_N) continue;
+            const size_t nn = (size_t)n[i];
+            pre[i].d = ar.get<double>(nn);
+            pre[i].e = ar.get<double>(nn);
+            pre[i].tau = ar.get<T>(nn);
+            bd.push_back(mak::BhetrdDesc<T>{n[i], (T*)A[i], lda[i], pre[i].d, pre[i].e, pre[i].tau});
+            if (n[i] > nmax) nmax = n[i];
+        }
+        mak::BhetrdDesc<T>* bdev = ar.get<mak::BhetrdDesc<T>>(bd.size() > 0 ? bd.size() : 1);
+        if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+        if (!bd.empty()) {
+            {
+                mak::Stager st(h, bd.size() * sizeof(mak::BhetrdDesc<T>) + 1024);
+                MAK_CUDA(h, st.put(bdev, bd.data(), bd.size() * sizeof(mak::BhetrdDesc<T>), h->stream));
+            }
+            int rc = mak::bhetrd_batched_t<T>(h, (int)bd.size(), bdev, nmax);
+            if (rc) return rc;
+        }
+    }
     char* wbig = (char*)work + ar.off;
     size_t lbig = lwork > ar.off ? lwork - ar.off : 0;
     return run_pooled(h, big, wbig, lbig, [&](makb200_handle_t* hh, char* w, size_t lw, int i) {
         return mak::eigh_t<T>(hh, n[i], (T*)A[i], lda[i], (double*)W[i], V ? (T*)V[i] : (T*)nullptr, V ? ldv[i] : n[i],
-                              fixgauge, w, lw, nullptr);   // V == NULL: values only (Sturm K-section)
+                              fixgauge, w, lw, nullptr, 0,
+                              pre[i].d ? &pre[i] : nullptr);   // V == NULL: values only (Sturm K-section)
     });
 }
 
@@ -922,9 +955,12 @@ size_t makb200_eigh_batched_worksize(makb200_handle_t* h, int dtype, int batch, 
             if (w > big) big = w;
             any = true;
             ++nbig;
+            // d, e, tau of the one-launch tridiagonalisation (MAKB200_BHETRD) + its descriptor
+            bytes += 2 * mak::align_up(sizeof(double) * (size_t)n[i], 256) + mak::align_up(sizeof(cplx) * (size_t)n[i], 256) +
+                     sizeof(mak::BhetrdDesc<cplx>);
         }
     }
-    return bytes + (any ? pooled_worksize(big, nbig) : 0) + 256;
+    return bytes + (any ? pooled_worksize(big, nbig) : 0) + 512;
 }
 
 int makb200_eigh_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch, const int* n, void* const* A,

@@ -18,6 +18,7 @@
 #include "stedc.cuh"
 #include "sturm_core.h"
 #include "projections.cuh"
+#include "bhetrd.cuh"
 
 namespace mak {
 
@@ -1109,7 +1110,7 @@ size_t eigh_worksize_t(makb200_handle* h, int n) {
 
 template <typename T>
 int eigh_t(makb200_handle* h, int n, T* A, int lda, double* W, T* V, int ldv, int fixgauge, void* work, size_t lwork,
-           int* info_dev, int top) {
+           int* info_dev, int top, const TrdPre<T>* pre) {
     if (n <= 0) return 0;
     // top in (0, n): only the eigenvectors of the `top` largest eigenvalues (the last columns of V) are
     // back-transformed and gauged; the leading n - top columns of V are left holding scratch
@@ -1129,12 +1130,19 @@ int eigh_t(makb200_handle* h, int n, T* A, int lda, double* W, T* V, int ldv, in
     int nb32 = (n + 31) / 32;
     PhaseTimer pt(s);
     pt.mark("start");
-    mirror_upper_kernel<T><<<dim3(nb32, nb32), dim3(32, 8), 0, s>>>(n, A, lda);
-    MAK_LAUNCH_CHECK(h, "mirror_upper_kernel");
+    if (!pre) {
+        mirror_upper_kernel<T><<<dim3(nb32, nb32), dim3(32, 8), 0, s>>>(n, A, lda);
+        MAK_LAUNCH_CHECK(h, "mirror_upper_kernel");
+    }
     const int b2 = eigh_twostage_b();
-    const bool two_stage = b2 > 0 && n > 2 * b2;
-    int rc;
-    if (two_stage) {
+    const bool two_stage = !pre && b2 > 0 && n > 2 * b2;
+    int rc = 0;
+    if (pre) {
+        // tridiagonalised in place by bhetrd_batched_t: d, e, tau and the reflectors below the sub-diagonal of A
+        x.d = pre->d;
+        x.e = pre->e;
+        x.tau = pre->tau;
+    } else if (two_stage) {
         rc = sy2sb_t<T>(h, n, b2, A, lda, ts.tau1, sub, sb);
         if (rc) return rc;
         pt.mark("sy2sb");
@@ -1193,7 +1201,28 @@ int eigh_t(makb200_handle* h, int n, T* A, int lda, double* W, T* V, int ldv, in
 
 template size_t eigh_worksize_t<double>(makb200_handle*, int);
 template size_t eigh_worksize_t<cplx>(makb200_handle*, int);
-template int eigh_t<double>(makb200_handle*, int, double*, int, double*, double*, int, int, void*, size_t, int*, int);
-template int eigh_t<cplx>(makb200_handle*, int, cplx*, int, double*, cplx*, int, int, void*, size_t, int*, int);
+template int eigh_t<double>(makb200_handle*, int, double*, int, double*, double*, int, int, void*, size_t, int*, int,
+                            const TrdPre<double>*);
+template int eigh_t<cplx>(makb200_handle*, int, cplx*, int, double*, cplx*, int, int, void*, size_t, int*, int,
+                          const TrdPre<cplx>*);
+
+template <typename T>
+int bhetrd_batched_t(makb200_handle* h, int nblk, const void* descs_dev, int nmax) {
+    if (nblk <= 0) return 0;
+    if (nmax > BHETRD_MAX_N) return -1;
+    const size_t smem = bhetrd_smem_elems(nmax) * sizeof(T);
+    static size_t configured = 0;   // grows monotonically; the attribute is per kernel instantiation
+    if (smem > 48 * 1024 && smem > configured) {
+        MAK_CUDA(h, cudaFuncSetAttribute(bhetrd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(bhetrd_smem_elems(BHETRD_MAX_N) * sizeof(T))));
+        configured = bhetrd_smem_elems(BHETRD_MAX_N) * sizeof(T);
+    }
+    bhetrd_kernel<T><<<nblk, BHETRD_THREADS, smem, h->stream>>>((const BhetrdDesc<T>*)descs_dev, nmax, 1);
+    count_launch();
+    MAK_LAUNCH_CHECK(h, "bhetrd_kernel");
+    return 0;
+}
+template int bhetrd_batched_t<double>(makb200_handle*, int, const void*, int);
+template int bhetrd_batched_t<cplx>(makb200_handle*, int, const void*, int);
 
 }  // namespace mak

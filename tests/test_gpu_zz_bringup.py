@@ -109,3 +109,34 @@ def test_two_stage_eigh_with_bringup_kernels():
     for r in json.loads(line[len("RESULT "):]):
         tol = 10 * r["n"] * EPS
         assert r["vals"] <= tol and r["resid"] <= tol * r["n"] ** 0.5 and r["orth"] <= tol * r["n"] ** 0.5 and r["gauge"], r
+
+
+@pytest.fixture
+def bhetrd():
+    os.environ["MAKB200_BHETRD"] = "1"
+    yield
+    os.environ.pop("MAKB200_BHETRD", None)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_batched_eigh_with_one_launch_tridiagonalisation(bhetrd, dtype):
+    """eigh_full! of mid-size blocks (beyond the one-CTA Jacobi kernel) with MAKB200_BHETRD=1: every such block
+    is tridiagonalised by csrc/bhetrd.cuh in ONE launch, then stedc + back-transformation per block."""
+    import makb200
+    from oracle import mak_oracle as O
+    ns = [20, 70, 90, 129, 200, 257, 300, 33, 512]
+    As0 = [O.rand_hermitian(n, dtype, seed=600 + n) for n in ns]
+    # only the upper triangle may be read (uplo = 'U'): poison the strict lower part of one block
+    As0p = [a.copy() for a in As0]
+    As0p[3][np.tril_indices(ns[3], -1)] = 1e3
+    outs = makb200.eigh_full_batched_([makb200.to_device(a) for a in As0p], check=False)
+    torch.cuda.synchronize()
+    for a, (D, V), n in zip(As0, outs, ns):
+        w, Vn = D.cpu().numpy(), makb200.to_numpy(V)
+        wref = O.eigh_vals(a)
+        tol = 10 * n * EPS
+        assert np.max(np.abs(w - wref)) / np.abs(wref).max() <= tol
+        assert np.linalg.norm(a @ Vn - Vn * w) / np.linalg.norm(a) <= tol
+        assert np.linalg.norm(Vn.conj().T @ Vn - np.eye(n)) <= tol
+        piv = Vn[np.argmax(np.abs(Vn), axis=0), np.arange(n)]
+        assert np.all(np.abs(piv.imag) <= 1e-13) and np.all(piv.real > 0)       # gauge (common/gauge.jl:38-45)
