@@ -40,14 +40,11 @@ struct BhetrdDesc {
 inline size_t bhetrd_smem_elems(int nmax) { return (size_t)(2 + BHETRD_NW) * (size_t)nmax + 64; }
 
 template <typename T>
-__global__ void __launch_bounds__(BHETRD_THREADS) bhetrd_kernel(const BhetrdDesc<T>* __restrict__ descs, int nmax,
-                                                                int mirror_upper) {
-    MAK_DYN_SMEM(smem_raw);
+__device__ __forceinline__ void bhetrd_body(const BhetrdDesc<T>& D, int nmax, int mirror_upper, unsigned char* smem_raw) {
     T* v = reinterpret_cast<T*>(smem_raw);
     T* w = v + nmax;
     T* yp = w + nmax;                          // [NW][nmax]
     T* scratch = yp + (size_t)BHETRD_NW * nmax;  // 64
-    const BhetrdDesc<T> D = descs[blockIdx.x];
     const int n = D.n, lda = D.lda;
     T* A = D.A;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -131,6 +128,21 @@ __global__ void __launch_bounds__(BHETRD_THREADS) bhetrd_kernel(const BhetrdDesc
         __syncthreads();
     }
     if (tid == 0) D.d[n - 1] = real_(A[(size_t)(n - 1) * lda + (n - 1)]);
+}
+
+// one CTA per block of a batch (descriptors in device memory)
+template <typename T>
+__global__ void __launch_bounds__(BHETRD_THREADS) bhetrd_kernel(const BhetrdDesc<T>* __restrict__ descs, int nmax,
+                                                                int mirror_upper) {
+    MAK_DYN_SMEM(smem_raw);
+    const BhetrdDesc<T> D = descs[blockIdx.x];
+    bhetrd_body<T>(D, nmax, mirror_upper, smem_raw);
+}
+// a single block, descriptor by value (per-block path: one launch instead of two per column)
+template <typename T>
+__global__ void __launch_bounds__(BHETRD_THREADS) bhetrd_one_kernel(BhetrdDesc<T> D, int mirror_upper) {
+    MAK_DYN_SMEM(smem_raw);
+    bhetrd_body<T>(D, D.n, mirror_upper, smem_raw);
 }
 
 }  // namespace mak

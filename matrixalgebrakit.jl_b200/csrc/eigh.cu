@@ -1097,6 +1097,23 @@ static void eigh_carve(makb200_handle* h, AR& ar, int n, TrdCtx<T>* x, double** 
     *sub = ar.template get<char>(*sub_bytes);
 }
 
+// opt-in dynamic shared memory of the one-CTA tridiagonalisation kernels (both entry points, once per type)
+template <typename T>
+static int bhetrd_configure(makb200_handle* h, size_t smem) {
+    static bool done = false;   // benign race: the attribute call is idempotent
+    if (smem > 48 * 1024 && !done) {
+        const int mx = (int)(bhetrd_smem_elems(BHETRD_MAX_N) * sizeof(T));
+        MAK_CUDA(h, cudaFuncSetAttribute(bhetrd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        MAK_CUDA(h, cudaFuncSetAttribute(bhetrd_one_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        done = true;
+    }
+    return 0;
+}
+static bool bhetrd_single() {
+    const char* e = getenv("MAKB200_BHETRD");   // read per call: the bring-up tests toggle it
+    return e && e[0] == '2';
+}
+
 template <typename T>
 size_t eigh_worksize_t(makb200_handle* h, int n) {
     ArenaSize ar;
@@ -1149,6 +1166,16 @@ int eigh_t(makb200_handle* h, int n, T* A, int lda, double* W, T* V, int ldv, in
         rc = sbr_chase_t<T>(h, n, b2, A, lda, x.d, x.e, ts.V2, n, ts.tau2, ts.ldt, sub, sb);
         if (rc) return rc;
         pt.mark("chase");
+    } else if (bhetrd_single() && n <= BHETRD_MAX_N && n >= 3) {
+        // EXPERIMENTAL (MAKB200_BHETRD=2): the whole tridiagonalisation in ONE single-CTA launch; meant for the
+        // pooled per-block paths (batched svd / eigh of mid-size blocks), where 2n launches per block bound the rate
+        const size_t smem = bhetrd_smem_elems(n) * sizeof(T);
+        rc = bhetrd_configure<T>(h, smem);
+        if (rc) return rc;
+        bhetrd_one_kernel<T><<<1, BHETRD_THREADS, smem, s>>>(BhetrdDesc<T>{n, A, lda, x.d, x.e, x.tau}, 0);
+        count_launch();
+        MAK_LAUNCH_CHECK(h, "bhetrd_one_kernel");
+        pt.mark("bhetrd");
     } else {
         rc = hetrd<T>(h, x);
         if (rc) return rc;
@@ -1211,12 +1238,8 @@ int bhetrd_batched_t(makb200_handle* h, int nblk, const void* descs_dev, int nma
     if (nblk <= 0) return 0;
     if (nmax > BHETRD_MAX_N) return -1;
     const size_t smem = bhetrd_smem_elems(nmax) * sizeof(T);
-    static size_t configured = 0;   // grows monotonically; the attribute is per kernel instantiation
-    if (smem > 48 * 1024 && smem > configured) {
-        MAK_CUDA(h, cudaFuncSetAttribute(bhetrd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(bhetrd_smem_elems(BHETRD_MAX_N) * sizeof(T))));
-        configured = bhetrd_smem_elems(BHETRD_MAX_N) * sizeof(T);
-    }
+    int rc = bhetrd_configure<T>(h, smem);
+    if (rc) return rc;
     bhetrd_kernel<T><<<nblk, BHETRD_THREADS, smem, h->stream>>>((const BhetrdDesc<T>*)descs_dev, nmax, 1);
     count_launch();
     MAK_LAUNCH_CHECK(h, "bhetrd_kernel");

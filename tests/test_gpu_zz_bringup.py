@@ -140,3 +140,35 @@ def test_batched_eigh_with_one_launch_tridiagonalisation(bhetrd, dtype):
         assert np.linalg.norm(Vn.conj().T @ Vn - np.eye(n)) <= tol
         piv = Vn[np.argmax(np.abs(Vn), axis=0), np.arange(n)]
         assert np.all(np.abs(piv.imag) <= 1e-13) and np.all(piv.real > 0)       # gauge (common/gauge.jl:38-45)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_single_launch_tridiagonalisation_inside_eigh_and_pooled_svd(dtype):
+    """MAKB200_BHETRD=2: eigh_t replaces its 2n launches by ONE single-CTA launch (n <= 512), which is what the
+    pooled per-block paths of the batched svd / eigh run for mid-size blocks."""
+    import makb200
+    from oracle import mak_oracle as O
+    os.environ["MAKB200_BHETRD"] = "2"
+    try:
+        for n in (3, 54, 130, 300, 512):
+            A0 = O.rand_hermitian(n, dtype, seed=70 + n)
+            D, V = makb200.eigh_full(makb200.to_device(A0))
+            w, Vn = D.cpu().numpy(), makb200.to_numpy(V)
+            wref = O.eigh_vals(A0)
+            tol = 10 * n * EPS
+            assert np.max(np.abs(w - wref)) / np.abs(wref).max() <= tol
+            assert np.linalg.norm(A0 @ Vn - Vn * w) / np.linalg.norm(A0) <= tol
+            assert np.linalg.norm(Vn.conj().T @ Vn - np.eye(n)) <= tol
+            wv = makb200.eigh_vals(makb200.to_device(A0)).cpu().numpy()
+            assert np.max(np.abs(wv - wref)) / np.abs(wref).max() <= tol
+        sizes = [(100, 100), (180, 120), (120, 180), (260, 260), (40, 40)]
+        As0 = [O.randn_matrix(m, k, dtype, seed=80 + i) for i, (m, k) in enumerate(sizes)]
+        outs = makb200.svd_compact_batched_([makb200.to_device(a) for a in As0])
+        torch.cuda.synchronize()
+        for a, (U, S, Vh) in zip(As0, outs):
+            Un, Sn, Vn = makb200.to_numpy(U), S.cpu().numpy(), makb200.to_numpy(Vh)
+            tol = O.tol_for(*a.shape)
+            assert np.max(np.abs(Sn - O.svd_vals(a))) / Sn[0] <= tol
+            assert O.rel_resid(a, Un * Sn, Vn) <= tol and O.orth_err(Un) <= tol and O.orth_err(Vn, "right") <= tol
+    finally:
+        os.environ.pop("MAKB200_BHETRD", None)

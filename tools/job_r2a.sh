@@ -14,6 +14,10 @@ MAKB200_BRINGUP=1 timeout 900 python -m pytest tests/test_gpu_zz_bringup.py -q -
 echo "== batched eigh 65-512 c128 (sample of 64 blocks per bucket): pooled per-block hetrd vs one-launch tridiagonalisation =="
 timeout 600 python tools/batched_bench.py 20000 512 eigh 2>&1 | grep -E "eigh_(65|129|257)|blocks_per_s" | head -12
 MAKB200_BHETRD=1 timeout 600 python tools/batched_bench.py 20000 512 eigh 2>&1 | grep -E "eigh_(65|129|257)|blocks_per_s" | head -12
+echo "== batched svd 65-512 c128 (64 blocks per bucket): 2n launches per block vs single-CTA tridiagonalisation inside eigh_t; then with a wider pool =="
+timeout 900 python tools/batched_bench.py 20000 512 svd 2>&1 | grep -E "svd_(65|129|257)|blocks_per_s" | head -12
+MAKB200_BHETRD=2 timeout 900 python tools/batched_bench.py 20000 512 svd 2>&1 | grep -E "svd_(65|129|257)|blocks_per_s" | head -12
+MAKB200_BHETRD=2 MAKB200_POOL_STREAMS=32 MAKB200_POOL_THREADS=8 timeout 900 python tools/batched_bench.py 20000 512 svd 2>&1 | grep -E "svd_(65|129|257)|blocks_per_s" | head -12
 echo "== chase: wavefront launches vs persistent (n=8192) =="
 timeout 300 python tools/sbr_time.py 8192 64 32
 MAKB200_CHASE_PERSISTENT=1 timeout 300 python tools/sbr_time.py 8192 64 32
