@@ -135,9 +135,23 @@ static bool bqr_warp_reg() {
     return v;
 }
 
+static bool bqr_warp_blk() {
+    const char* e = getenv("MAKB200_BQR_WARP_BLK");   // read per call: the bring-up tests toggle it
+    return e && e[0] == '1';
+}
+
 template <typename T>
 int batched_qr_warp(makb200_handle* h, int batch, int cap_elems, const QrBlockDesc<T>* descs, int rmax) {
     if (batch <= 0) return 0;
+    if (bqr_warp_blk()) {
+        // panel-blocked variant (round-2 bring-up): 5 instead of 14 shared-memory wavefronts per (row, step)
+        const int grid = (batch + 3) / 4;
+        const size_t smem = 4 * (size_t)(cap_elems + BQW_TF_ELEMS) * sizeof(T);
+        batched_qr_warp_blk_kernel<T><<<grid, 128, smem, h->stream>>>(descs, batch, cap_elems);
+        count_launch();
+        MAK_LAUNCH_CHECK(h, "batched_qr_warp_blk_kernel");
+        return 0;
+    }
     if (bqr_warp_reg()) {
         const int grid = (batch + 3) / 4;
         if (rmax <= 16) batched_qr_warp_reg_kernel<T, 16><<<grid, 128, 0, h->stream>>>(descs, batch);
@@ -546,6 +560,8 @@ template int batched_eigh_smem<cplx>(makb200_handle*, int, size_t, const EighBlo
 int batched_init(makb200_handle* h) {
     MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_warp_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_warp_kernel<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_warp_blk_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_warp_blk_kernel<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_kernel<double, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)BQ_SMEM_BYTES));
     MAK_CUDA(h, cudaFuncSetAttribute(batched_qr_kernel<double, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -206,4 +206,257 @@ batched_qr_warp_reg_kernel(const QrBlockDesc<T>* __restrict__ descs, int batch) 
     }
 }
 
+// Panel-blocked variant (opt-in, MAKB200_BQR_WARP_BLK=1, round-2 bring-up): the shared-memory kernel above
+// moves 14 LSU wavefronts per (row, step) - two passes over the lane's column per reflector - against 5 clk
+// of DFMA.  Here reflectors are generated four at a time with lane = ROW (the 4-column panel lives in
+// registers, norms and dots are warp reductions, the 4x4 compact-WY factor Tf is built on the fly), and the
+// trailing columns (lane = COLUMN) take the whole block reflector in TWO passes:
+//   s = V^H c (4 dots in one sweep),  w = Tf^H s,  c -= V w
+// i.e. (8 + 12)/4 = 5 wavefronts per (row, step).  Q is accumulated backwards panel by panel the same way
+// (c -= V (Tf (V^H c))), the panel's own columns are E - V (Tf V_top^H) with lane = row.
+// Layout: per warp the padded block S (lds = m|1) followed by 8 x 16 entries for the Tf of every panel.
+constexpr int BQW_NB = 4;
+constexpr int BQW_TF_ELEMS = 8 * BQW_NB * BQW_NB;   // 32 / NB panels at most
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+batched_qr_warp_blk_kernel(const QrBlockDesc<T>* __restrict__ descs, int batch, int cap_elems) {
+    MAK_DYN_SMEM(smem_raw);
+    constexpr int NB = BQW_NB;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int blk = blockIdx.x * 4 + warp;
+    if (blk >= batch) return;
+    const QrBlockDesc<T> d = descs[blk];
+    const int m = d.m, n = d.n, k = m < n ? m : n;
+    const int lds = m | 1;
+    T* S = reinterpret_cast<T*>(smem_raw) + (size_t)warp * (cap_elems + BQW_TF_ELEMS);
+    T* Tst = S + cap_elems;
+    for (int c = 0; c < n; ++c)
+        if (lane < m) S[c * lds + lane] = d.A[(size_t)c * d.lda + lane];
+    __syncwarp();
+    T* mycol = S + (lane < n ? lane : 0) * lds;
+    const int npanels = (k + NB - 1) / NB;
+
+    // ---------------- factorization ----------------
+    for (int p = 0; p < npanels; ++p) {
+        const int j0 = p * NB, pb = (k - j0 < NB) ? (k - j0) : NB;
+        // ---- panel (lane = row): generate pb reflectors and Tf ----
+        T a[NB], Tf[NB][NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            a[i] = (i < pb && lane >= j0 && lane < m) ? S[(j0 + i) * lds + lane] : zero<T>();
+#pragma unroll
+            for (int q = 0; q < NB; ++q) Tf[q][i] = zero<T>();
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            if (i < pb) {                                   // uniform across the warp
+                const int jc = j0 + i;
+                const double sigma = warp_sum((lane > jc && lane < m) ? abs2_(a[i]) : 0.0);
+                const T alpha = shfl_(a[i], jc);
+                double beta; T tau, scale;
+                larfgp_scalars<T>(alpha, sigma, beta, tau, scale);
+                if (lane > jc && lane < m) a[i] = mul_(a[i], scale);
+                if (lane == jc) a[i] = mk<T>(beta);
+                // v_i as seen by this lane: 0 above the pivot row, 1 on it, the scaled entry below
+                const T vi = (lane < jc || lane >= m) ? zero<T>() : (lane == jc ? one<T>() : a[i]);
+                // apply H_i^H to the rest of the panel
+#pragma unroll
+                for (int l = 0; l < NB; ++l) {
+                    if (l > i && l < pb) {
+                        T sl = zero<T>();
+                        fmac_(sl, vi, a[l]);
+                        sl = warp_sum(sl);
+                        const T f = mul_(conj_(tau), sl);
+                        a[l] = sub_(a[l], mul_(f, vi));
+                    }
+                }
+                // Tf(0:i, i) = -tau Tf(0:i, 0:i) (V(:, 0:i)^H v_i),  Tf(i, i) = tau
+                T z[NB];
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    z[q] = zero<T>();
+                    if (q < i) {
+                        // V(:, q) at this lane: rows above j0+q are R entries (not V): only rows >= jc matter, all below j0+q
+                        const T vq = (lane < jc || lane >= m) ? zero<T>() : a[q];
+                        T zz = zero<T>();
+                        fmac_(zz, vq, vi);
+                        z[q] = warp_sum(zz);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    if (q < i) {
+                        T acc = zero<T>();
+#pragma unroll
+                        for (int l = 0; l < NB; ++l)
+                            if (l >= q && l < i) fma_(acc, Tf[q][l], z[l]);
+                        Tf[q][i] = neg_(mul_(tau, acc));
+                    }
+                }
+                Tf[i][i] = tau;
+            }
+        }
+        // write the panel back (rows >= j0: R entries of the panel's upper triangle, beta, v) and Tf
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+            if (i < pb && lane >= j0 && lane < m) S[(j0 + i) * lds + lane] = a[i];
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < NB; ++q)
+#pragma unroll
+                for (int i = 0; i < NB; ++i) Tst[p * NB * NB + q * NB + i] = Tf[q][i];
+        }
+        __syncwarp();
+        // ---- trailing columns (lane = column): c <- (I - V Tf^H V^H) c ----
+        const int c0 = j0 + pb;
+        if (lane >= c0 && lane < n) {
+            T sdot[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) sdot[i] = zero<T>();
+#pragma unroll
+            for (int tt = 0; tt < NB; ++tt) {               // triangle rows j0 .. j0+pb-1 (unit lower part of V)
+                if (tt < pb) {
+                    const T x = mycol[j0 + tt];
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) {
+                        if (i == tt) sdot[i] = add_(sdot[i], x);
+                        else if (i < tt) fmac_(sdot[i], S[(j0 + i) * lds + j0 + tt], x);
+                    }
+                }
+            }
+            for (int r = c0; r < m; ++r) {
+                const T x = mycol[r];
+#pragma unroll
+                for (int i = 0; i < NB; ++i)
+                    if (i < pb) fmac_(sdot[i], S[(j0 + i) * lds + r], x);
+            }
+            T w[NB];                                        // w = Tf^H s
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                w[i] = zero<T>();
+#pragma unroll
+                for (int q = 0; q < NB; ++q)
+                    if (q <= i && i < pb) fmac_(w[i], Tst[p * NB * NB + q * NB + i], sdot[q]);
+            }
+#pragma unroll
+            for (int tt = 0; tt < NB; ++tt) {
+                if (tt < pb) {
+                    T x = mycol[j0 + tt];
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) {
+                        if (i == tt) x = sub_(x, w[i]);
+                        else if (i < tt) x = sub_(x, mul_(S[(j0 + i) * lds + j0 + tt], w[i]));
+                    }
+                    mycol[j0 + tt] = x;
+                }
+            }
+            for (int r = c0; r < m; ++r) {
+                T x = mycol[r];
+#pragma unroll
+                for (int i = 0; i < NB; ++i)
+                    if (i < pb) x = sub_(x, mul_(S[(j0 + i) * lds + r], w[i]));
+                mycol[r] = x;
+            }
+        }
+        __syncwarp();
+    }
+    // ---------------- R out (lane = row) ----------------
+    if (d.R) {
+        for (int c = 0; c < n; ++c)
+            if (lane < k) d.R[(size_t)c * d.ldr + lane] = (lane <= c) ? S[c * lds + lane] : zero<T>();
+    }
+    __syncwarp();
+    // ---------------- Q in place (columns 0..k-1), backward over the panels ----------------
+    for (int p = npanels - 1; p >= 0; --p) {
+        const int j0 = p * NB, pb = (k - j0 < NB) ? (k - j0) : NB;
+        const int c0 = j0 + pb;
+        // ---- already formed columns (lane = column): c <- (I - V Tf V^H) c; their rows < c0 are zero ----
+        if (lane >= c0 && lane < k) {
+            T sdot[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) sdot[i] = zero<T>();
+            for (int r = c0; r < m; ++r) {
+                const T x = mycol[r];
+#pragma unroll
+                for (int i = 0; i < NB; ++i)
+                    if (i < pb) fmac_(sdot[i], S[(j0 + i) * lds + r], x);
+            }
+            T w[NB];                                        // w = Tf s
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                w[i] = zero<T>();
+#pragma unroll
+                for (int q = 0; q < NB; ++q)
+                    if (q >= i && q < pb) fma_(w[i], Tst[p * NB * NB + i * NB + q], sdot[q]);
+            }
+#pragma unroll
+            for (int tt = 0; tt < NB; ++tt) {
+                if (tt < pb) {
+                    T x = zero<T>();                        // rows j0..c0-1 of a formed column are zero on entry
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) {
+                        if (i == tt) x = sub_(x, w[i]);
+                        else if (i < tt) x = sub_(x, mul_(S[(j0 + i) * lds + j0 + tt], w[i]));
+                    }
+                    mycol[j0 + tt] = x;
+                }
+            }
+            for (int r = c0; r < m; ++r) {
+                T x = mycol[r];
+#pragma unroll
+                for (int i = 0; i < NB; ++i)
+                    if (i < pb) x = sub_(x, mul_(S[(j0 + i) * lds + r], w[i]));
+                mycol[r] = x;
+            }
+        }
+        __syncwarp();
+        // ---- the panel's own columns (lane = row): Q(:, j0+c) = e_{j0+c} - V (Tf V_top^H)(:, c) ----
+        T vrow[NB], Mx[NB][NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            T x = zero<T>();
+            if (i < pb && lane < m) {
+                if (lane == j0 + i) x = one<T>();
+                else if (lane > j0 + i) x = S[(j0 + i) * lds + lane];
+            }
+            vrow[i] = x;
+        }
+        // u_c = V_top^H e_c = conj(row c of the unit lower triangle);  Mx(:, c) = Tf u_c
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            T u[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                u[i] = zero<T>();
+                if (c < pb) {
+                    if (i == c) u[i] = one<T>();
+                    else if (i < c) u[i] = conj_(S[(j0 + i) * lds + j0 + c]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                T acc = zero<T>();
+#pragma unroll
+                for (int i = 0; i < NB; ++i)
+                    if (i >= q && i <= c && c < pb) fma_(acc, Tst[p * NB * NB + q * NB + i], u[i]);
+                Mx[q][c] = acc;
+            }
+        }
+        __syncwarp();                                       // every lane has read V and V_top before the overwrite
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            if (c < pb && lane < m) {
+                T x = (lane == j0 + c) ? one<T>() : zero<T>();
+#pragma unroll
+                for (int i = 0; i < NB; ++i) x = sub_(x, mul_(vrow[i], Mx[i][c]));
+                S[(j0 + c) * lds + lane] = x;
+            }
+        }
+        __syncwarp();
+    }
+    for (int c = 0; c < k; ++c)
+        if (lane < m) d.Q[(size_t)c * d.ldq + lane] = S[c * lds + lane];
+}
+
 }  // namespace mak

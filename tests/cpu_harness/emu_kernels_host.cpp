@@ -30,6 +30,9 @@ static int run_bqr_warp(int variant, int batch, const int* m, const int* n, void
         if (rmax <= 16) emu::launch(mak::batched_qr_warp_reg_kernel<T, 16>, dim3(grid), dim3(128), 0, (const mak::QrBlockDesc<T>*)d.data(), batch);
         else if (rmax <= 24) emu::launch(mak::batched_qr_warp_reg_kernel<T, 24>, dim3(grid), dim3(128), 0, (const mak::QrBlockDesc<T>*)d.data(), batch);
         else emu::launch(mak::batched_qr_warp_reg_kernel<T, 32>, dim3(grid), dim3(128), 0, (const mak::QrBlockDesc<T>*)d.data(), batch);
+    } else if (variant == 2) {
+        emu::launch(mak::batched_qr_warp_blk_kernel<T>, dim3(grid), dim3(128), 4 * (size_t)(cap + mak::BQW_TF_ELEMS) * sizeof(T),
+                    (const mak::QrBlockDesc<T>*)d.data(), batch, cap);
     } else {
         return -1;
     }

@@ -172,3 +172,32 @@ def test_single_launch_tridiagonalisation_inside_eigh_and_pooled_svd(dtype):
             assert O.rel_resid(a, Un * Sn, Vn) <= tol and O.orth_err(Un) <= tol and O.orth_err(Vn, "right") <= tol
     finally:
         os.environ.pop("MAKB200_BHETRD", None)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_panel_blocked_warp_qr(dtype):
+    """MAKB200_BQR_WARP_BLK=1: tiny blocks (m, n <= 32) through batched_qr_warp_blk_kernel; same gauge-fixed
+    factors as the oracle and as the default warp kernel."""
+    import makb200
+    from oracle import mak_oracle as O
+    rng = np.random.default_rng(5)
+    shapes = [(16, 16), (32, 32), (23, 23), (32, 17), (17, 32), (5, 3), (1, 1), (31, 32), (24, 24), (2, 7), (32, 4), (4, 32),
+              (9, 9), (28, 27)] + [(int(a), int(b)) for a, b in rng.integers(1, 33, size=(60, 2))]
+    As0 = [O.randn_matrix(m, n, dtype, seed=400 + i) for i, (m, n) in enumerate(shapes)]
+    os.environ["MAKB200_BQR_WARP_BLK"] = "1"
+    try:
+        outs = makb200.qr_compact_batched_([makb200.to_device(a) for a in As0])
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("MAKB200_BQR_WARP_BLK", None)
+    ref = makb200.qr_compact_batched_([makb200.to_device(a) for a in As0])
+    torch.cuda.synchronize()
+    for a, (Q, R), (Q0, R0) in zip(As0, outs, ref):
+        m, n = a.shape
+        tol = O.tol_for(m, n)
+        Qn, Rn = makb200.to_numpy(Q), makb200.to_numpy(R)
+        Qo, Ro = O.qr_compact(a.copy())
+        assert O.rel_resid(a, Qn, Rn) <= tol and O.orth_err(Qn) <= tol
+        assert np.all(np.tril(Rn, -1) == 0) and np.all(np.real(np.diag(Rn)) >= 0)
+        assert np.linalg.norm(Rn - Ro) <= 200 * tol * np.linalg.norm(Ro) and np.linalg.norm(Qn - Qo) <= 200 * tol * np.sqrt(min(m, n))
+        assert np.linalg.norm(Qn - makb200.to_numpy(Q0)) <= 200 * tol * np.sqrt(min(m, n))

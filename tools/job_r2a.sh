@@ -11,6 +11,9 @@ echo "== timings: eigh_vals vs eigh_full (8192 f64), svd_vals vs svd_compact, sv
 timeout 600 python tools/vals_time.py 8192 1024
 echo "== bring-up parity =="
 MAKB200_BRINGUP=1 timeout 900 python -m pytest tests/test_gpu_zz_bringup.py -q -x 2>&1 | tail -15
+echo "== tiny-block QR (16-32 c128, x16 replicas): warp kernel vs panel-blocked warp kernel =="
+timeout 300 python tools/batched_bench.py 20000 32 qr 2>&1 | grep -E "qr_16|blocks_per_s|hbm_frac" | head -6
+MAKB200_BQR_WARP_BLK=1 timeout 300 python tools/batched_bench.py 20000 32 qr 2>&1 | grep -E "qr_16|blocks_per_s|hbm_frac" | head -6
 echo "== batched eigh 65-512 c128 (sample of 64 blocks per bucket): pooled per-block hetrd vs one-launch tridiagonalisation =="
 timeout 600 python tools/batched_bench.py 20000 512 eigh 2>&1 | grep -E "eigh_(65|129|257)|blocks_per_s" | head -12
 MAKB200_BHETRD=1 timeout 600 python tools/batched_bench.py 20000 512 eigh 2>&1 | grep -E "eigh_(65|129|257)|blocks_per_s" | head -12
