@@ -698,9 +698,28 @@ __global__ void svd_reorder_kernel(int n, int k, const double* __restrict__ w, c
     }
 }
 
+// out[0] = max_j | ||U(:, j)||^2 - 1 |  (one warp per column; non-negative doubles order like their bit patterns).
+// For a full-rank A the left factor U = W V is isometric to rounding; for a rank-deficient A the QDWH polar
+// factor W is only a partial isometry and the columns of U that belong to zero singular values collapse.
+template <typename T>
+__global__ void col_norm_defect_kernel(int m, int ncols, const T* __restrict__ U, int ldu, double* out) {
+    const int lane = threadIdx.x & 31, j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= ncols) return;
+    const T* u = U + (size_t)j * ldu;
+    double s = 0.0;
+    for (int r = lane; r < m; r += 32) s += abs2_(u[r]);
+    s = warp_sum(s);
+    if (lane == 0) {
+        double dft = fabs(s - 1.0);
+        if (!(dft == dft)) dft = 1e300;   // NaN counts as a defect
+        atomicMax((unsigned long long*)out, (unsigned long long)__double_as_longlong(dft));
+    }
+}
+
 template <typename T>
 struct SvdWork {
     T *Wp, *P, *V, *At, *Ut, *Vht;
+    double* flag;
     double* wv;
     void* sub;
     size_t sub_bytes;
@@ -715,12 +734,15 @@ static void svd_carve(makb200_handle* h, AR& ar, int m, int n, SvdWork<T>* w) {
     w->P = ar.template get<T>(N * N);
     w->V = ar.template get<T>(N * N);
     w->wv = ar.template get<double>(N);
+    w->flag = ar.template get<double>(2);
     w->At = wide ? ar.template get<T>(M * N) : nullptr;
     w->Ut = wide ? ar.template get<T>(M * N) : nullptr;
     w->Vht = wide ? ar.template get<T>(N * N) : nullptr;
     size_t a = polar_worksize_t<T>(h, mm, nn);
     size_t b = eigh_worksize_t<T>(h, nn);
+    size_t c = qr_worksize_t<T>(h, mm, nn, nn);   // re-orthonormalisation of U for rank-deficient input
     w->sub_bytes = a > b ? a : b;
+    if (c > w->sub_bytes) w->sub_bytes = c;
     w->sub = ar.template get<char>(w->sub_bytes);
 }
 
@@ -759,6 +781,26 @@ static int svd_tall(makb200_handle* h, int m, int n, int r, T* A, int lda, doubl
         // U = W * V_desc = W * Vh^H
         MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, m, r, n, one<T>(), w.Wp, m, Vh, ldvh, zero<T>(), U, ldu,
                   nullptr, 0);
+        // Rank-deficient A: W is a partial isometry, so the columns of U that belong to (numerically) zero
+        // singular values are not unit vectors.  LAPACK returns an isometric U for any input, so detect the
+        // case (one 8-byte read, like the reference's info read per call) and replace U by the Q of its
+        // positive-diagonal Householder QR: the leading isometric columns are reproduced, the collapsed
+        // ones become an orthonormal completion.
+        MAK_CUDA(h, cudaMemsetAsync(w.flag, 0, sizeof(double), s));
+        col_norm_defect_kernel<T><<<(r + 7) / 8, 256, 0, s>>>(m, r, U, ldu, w.flag);
+        count_launch();
+        MAK_LAUNCH_CHECK(h, "col_norm_defect_kernel");
+        double defect = 0.0;
+        MAK_CUDA(h, cudaMemcpyAsync(&defect, w.flag, sizeof(double), cudaMemcpyDeviceToHost, s));
+        MAK_CUDA(h, cudaStreamSynchronize(s));
+        if (defect > 1e-6) {
+            rc = qr_fused_t<T>(h, MAKB200_QR_COMPACT, m, r, U, ldu, w.Wp, m, (T*)nullptr, 0, w.sub, w.sub_bytes);
+            if (rc) return rc;
+            copy2d_kernel<T><<<grid_for2((size_t)m * r, h->num_sms), 256, 0, s>>>(m, r, w.Wp, m, U, ldu);
+            count_launch();
+            MAK_LAUNCH_CHECK(h, "copy2d_kernel");
+            pt.mark("U_repair");
+        }
         if (fixgauge) {
             rc = gauge_columns<T>(h, m, r, U, ldu, Vh, ldvh, n);
             if (rc) return rc;

@@ -1,0 +1,53 @@
+"""Rank-deficient input to svd_compact!/svd_trunc! on the single-matrix path (QDWH polar + eigh): the polar
+factor of a singular matrix is only a partial isometry, so U is re-orthonormalised when its column norms
+show it (polar.cu: col_norm_defect_kernel + Householder QR of U).  LAPACK (the reference path) returns
+isometric factors for any input; so must we.  Sorted after the GPU-verified suites (see
+test_gpu_y_projections.py)."""
+import numpy as np
+import pytest
+
+from oracle import mak_oracle as O
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(float).eps
+
+
+def _lowrank(m, n, r, dtype, seed):
+    return np.asfortranarray(O.randn_matrix(m, r, dtype, seed) @ O.randn_matrix(r, n, dtype, seed + 1))
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("m,n,r", [(120, 90, 40), (90, 120, 40), (200, 200, 199), (150, 150, 1), (300, 100, 60)])
+def test_svd_compact_rank_deficient(m, n, r, dtype):
+    import makb200
+    A0 = _lowrank(m, n, r, dtype, seed=m + n + r)
+    U, S, Vh = makb200.svd_compact(makb200.to_device(A0))
+    Un, Sn, Vn = makb200.to_numpy(U), S.cpu().numpy(), makb200.to_numpy(Vh)
+    tol = O.tol_for(m, n)
+    So = O.svd_vals(A0)
+    assert np.max(np.abs(Sn - So)) / So[0] <= tol
+    assert np.all(Sn[r:] <= 100 * tol * So[0])                        # numerically zero beyond the rank
+    assert O.rel_resid(A0, Un * Sn, Vn) <= tol
+    assert O.orth_err(Un) <= tol and O.orth_err(Vn, "right") <= tol    # isometric factors, as LAPACK returns
+    # the leading r triplets are those of the oracle (gauge-fixed; scaled by the gap to the next value)
+    Uo, _, Vho = O.svd_compact(A0)
+    gaps = np.abs(np.diff(np.append(So[:r], 0.0))) / So[0]
+    ok = gaps > 1e-3
+    assert np.max(np.abs(np.abs(np.sum(Un[:, :r].conj() * Uo[:, :r], axis=0))[ok] - 1)) <= 1e-8
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_svd_of_zero_and_trunc_of_rank_deficient(dtype):
+    import makb200
+    Z = np.zeros((100, 80), dtype=np.float64 if dtype == "f64" else np.complex128, order="F")
+    U, S, Vh = makb200.svd_compact(makb200.to_device(Z))
+    Un, Vn = makb200.to_numpy(U), makb200.to_numpy(Vh)
+    assert np.all(S.cpu().numpy() == 0)
+    assert O.orth_err(Un) <= O.tol_for(100, 80) and O.orth_err(Vn, "right") <= O.tol_for(100, 80)
+    A0 = _lowrank(140, 110, 30, dtype, seed=3)
+    U, S, Vh, eps = makb200.svd_trunc(makb200.to_device(A0), trunc=makb200.trunctol(rtol=1e-10))
+    assert tuple(S.shape) == (30,) and eps <= 1e-10 * float(S[0])
+    assert O.rel_resid(A0, makb200.to_numpy(U) * S.cpu().numpy(), makb200.to_numpy(Vh)) <= O.tol_for(140, 110)
+    U, S, Vh, eps = makb200.svd_trunc(makb200.to_device(A0), trunc=makb200.truncrank(50))   # leading-r path, r > rank
+    assert tuple(U.shape) == (140, 50) and O.orth_err(makb200.to_numpy(U)) <= O.tol_for(140, 110)
+    assert O.rel_resid(A0, makb200.to_numpy(U) * S.cpu().numpy(), makb200.to_numpy(Vh)) <= O.tol_for(140, 110)
