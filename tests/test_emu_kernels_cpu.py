@@ -320,6 +320,10 @@ def test_emu_bhetrd_batch(lib, dtype, mirror):
     for order, seed in ORDERS[mirror:mirror + 2]:
         As0 = [O.rand_hermitian(n, dtype, seed=50 + n) for n in ns]
         As0[3] = np.asfortranarray(np.diag(np.arange(1.0, 18.0)).astype(As0[3].dtype))   # already tridiagonal: tau = 0 steps
+        bd = np.diag(np.arange(1.0, 34.0)).astype(As0[4].dtype)                           # dense 10x10 block + diagonal rest:
+        bd[:10, :10] = O.rand_hermitian(10, dtype, seed=9)                                # a tau = 0 step with an update pending
+        bd[20:28, 20:28] = O.rand_hermitian(8, dtype, seed=10)                            # and reflectors starting again after it
+        As0[4] = np.asfortranarray(bd)
         pads = [0, 1, 0, 3, 0, 5, 0]
         bufs = []
         for a, p in zip(As0, pads):
