@@ -31,3 +31,5 @@ from .sbr import sbr_apply_q2_, sbr_chase_, sy2sb_  # noqa: E402,F401  (experime
 from .projections import (defaulttol, is_left_isometric, is_right_isometric, isantihermitian, ishermitian,  # noqa: E402,F401
                           isisometric, isunitary, project_antihermitian, project_antihermitian_, project_hermitian,
                           project_hermitian_, project_isometric, project_isometric_)
+from .eigh import eigh_vals_batched_  # noqa: E402,F401
+from .svd import svd_vals_batched_  # noqa: E402,F401

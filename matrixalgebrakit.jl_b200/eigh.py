@@ -183,3 +183,26 @@ def eigh_full_batched_(As, DVs=None, fixgauge=True, check=True):
     if len(As) == 0:
         return []
     return BatchedEighPlan(As, DVs, fixgauge, check).run()
+
+
+def eigh_vals_batched_(As, Ds=None, check=True):
+    """Batched ``eigh_vals!`` (eigh.jl:157-161 per block, job 'N'): one C-ABI call with V = NULL; blocks
+    beyond the one-CTA kernel take the tridiagonalisation + Sturm K-section path."""
+    if len(As) == 0:
+        return []
+    h = _core.Handle.get(As[0].device)
+    dt = _core.dtype_code(As[0])
+    b = len(As)
+    if Ds is None:
+        Ds = [torch.empty(A.shape[0], dtype=torch.float64, device=A.device) for A in As]
+    for A, D in zip(As, Ds):
+        check_input(A, (D, None), None, check=check)
+    IA, VP = C.c_int * b, C.c_void_p * b
+    n = IA(*[A.shape[0] for A in As])
+    lda = IA(*[_core.ld(A) for A in As])
+    Ap, Wp = VP(*[A.data_ptr() for A in As]), VP(*[D.data_ptr() for D in Ds])
+    work = h.workspace(h.lib.makb200_eigh_batched_worksize(h.h, dt, b, n))
+    rc = h.lib.makb200_eigh_batched(h.h, dt, 0, b, n, Ap, lda, Wp, None, None, C.c_void_p(0), _core.ptr(work),
+                                    work.numel())
+    h.check(rc, "makb200_eigh_batched")
+    return Ds

@@ -226,6 +226,32 @@ def svd_compact_batched_(As, USVhs=None, fixgauge=True):
     return BatchedSVDPlan(As, USVhs, fixgauge).run()
 
 
+def svd_vals_batched_(As, Ss=None):
+    """Batched ``svd_vals!`` (svd.jl:214-219 per block, job 'N'): one C-ABI call, U = Vh = NULL."""
+    if len(As) == 0:
+        return []
+    h = _core.Handle.get(As[0].device)
+    dt = _core.dtype_code(As[0])
+    b = len(As)
+    for A in As:
+        if not _core.is_colmajor(A) or _core.dtype_code(A) != dt:
+            raise ValueError("svd_vals_batched_: column-major blocks of one eltype expected")
+    if Ss is None:
+        Ss = [torch.empty(min(A.shape), dtype=torch.float64, device=A.device) for A in As]
+    for A, S in zip(As, Ss):
+        if S.dim() != 1 or S.shape[0] != min(A.shape) or S.dtype != torch.float64:
+            raise ValueError("S: real vector of length min(m,n) expected")
+    IA, VP = C.c_int * b, C.c_void_p * b
+    m, n = IA(*[A.shape[0] for A in As]), IA(*[A.shape[1] for A in As])
+    lda = IA(*[_core.ld(A) for A in As])
+    Ap, Sp = VP(*[A.data_ptr() for A in As]), VP(*[S.data_ptr() for S in Ss])
+    work = h.workspace(h.lib.makb200_svd_batched_worksize(h.h, dt, b, m, n))
+    rc = h.lib.makb200_svd_batched(h.h, dt, 0, b, m, n, Ap, lda, Sp, None, None, None, None, C.c_void_p(0),
+                                   _core.ptr(work), work.numel())
+    h.check(rc, "makb200_svd_batched")
+    return Ss
+
+
 def svd_trunc_batched_(As, trunc, USVhs=None):
     """Batched ``svd_trunc!``: batched compact SVD, then per block the reference's slice and error
     (svd.jl:232-237) -> list of ``(U, S, Vh, eps)``.  Strategies that keep a prefix of the sorted values

@@ -88,3 +88,28 @@ def test_vals_empty():
     import makb200
     assert makb200.eigh_vals(makb200.colmajor_zeros(0, 0, torch.float64, "cuda:0")).numel() == 0
     assert makb200.svd_vals(makb200.colmajor_zeros(0, 5, torch.float64, "cuda:0")).numel() == 0
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_vals_batched(dtype):
+    """Batched eigh_vals! / svd_vals! (V = NULL, U = Vh = NULL through the batched C entry points): small blocks in
+    the one-CTA Jacobi kernels, larger ones through the single-matrix values-only path."""
+    import makb200
+    ns = [1, 8, 24, 40, 64, 90, 150, 260]
+    Hs0 = [O.rand_hermitian(n, dtype, seed=40 + n) for n in ns]
+    Ds = makb200.eigh_vals_batched_([makb200.to_device(a) for a in Hs0])
+    torch.cuda.synchronize()
+    for a, D, n in zip(Hs0, Ds, ns):
+        wref = O.eigh_vals(a)
+        assert np.max(np.abs(D.cpu().numpy() - wref)) / np.abs(wref).max() <= 10 * n * EPS
+    with pytest.raises(makb200.DomainError):
+        makb200.eigh_vals_batched_([makb200.to_device(O.randn_matrix(20, 20, dtype, 1))])
+    shapes = [(1, 1), (16, 16), (17, 9), (9, 17), (54, 37), (64, 64), (100, 100), (180, 120), (120, 180)]
+    As0 = [O.randn_matrix(m, k, dtype, seed=60 + i) for i, (m, k) in enumerate(shapes)]
+    Ss = makb200.svd_vals_batched_([makb200.to_device(a) for a in As0])
+    torch.cuda.synchronize()
+    for a, S in zip(As0, Ss):
+        sref = O.svd_vals(a)
+        s = S.cpu().numpy()
+        assert s.shape == sref.shape and np.all(np.diff(s) <= 0)
+        assert np.max(np.abs(s - sref)) / sref[0] <= 10 * max(a.shape) * EPS
