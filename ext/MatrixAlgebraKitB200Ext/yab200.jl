@@ -204,17 +204,18 @@ struct TruncSpec
     vatol::Cdouble; vrtol::Cdouble; vp::Cdouble
     eatol::Cdouble; ertol::Cdouble; ep::Cdouble
 end
-function trunc_select_batched(Ss::Vector{<:StridedCuVector{Float64}}, spec::TruncSpec)
+function trunc_select_batched(Ss::Vector{<:StridedCuVector{Float64}}, spec::TruncSpec; maxranks::Union{Nothing, Vector{<:Integer}} = nothing)
     b = length(Ss)
     ks = Cint[length(S) for S in Ss]
+    caps = maxranks === nothing ? Ptr{Cint}(C_NULL) : Cint.(maxranks)   # per-block rank caps (config 3: n_i ÷ 2)
     ptrs = [reinterpret(Ptr{Cvoid}, pointer(S)) for S in Ss]
     rank, eps = CUDA.zeros(Cint, b), CUDA.zeros(Float64, b)
     h = handle()
     lw = ccall((:makb200_trunc_select_batched_worksize, libmakb200), Csize_t, (Ptr{Cvoid}, Cint), h, b)
     with_workspace(lw) do work
         rc = ccall((:makb200_trunc_select_batched, libmakb200), Cint,
-            (Ptr{Cvoid}, Cint, Ptr{Cint}, Ptr{Ptr{Cvoid}}, Ref{TruncSpec}, CuPtr{Cint}, CuPtr{Float64}, CuPtr{UInt8}, Csize_t),
-            h, b, ks, ptrs, Ref(spec), rank, eps, work, lw)
+            (Ptr{Cvoid}, Cint, Ptr{Cint}, Ptr{Ptr{Cvoid}}, Ref{TruncSpec}, Ptr{Cint}, CuPtr{Cint}, CuPtr{Float64}, CuPtr{UInt8}, Csize_t),
+            h, b, ks, ptrs, Ref(spec), caps, rank, eps, work, lw)
         chkargsok(rc, "makb200_trunc_select_batched")
     end
     return Array(rank), Array(eps)

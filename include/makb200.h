@@ -236,9 +236,11 @@ typedef struct makb200_trunc_spec {
     double eatol, ertol, ep;   /* truncerror: discarded ||.||_ep < max(eatol, ertol ||S||_ep) */
 } makb200_trunc_spec;
 size_t makb200_trunc_select_batched_worksize(makb200_handle_t* h, int batch);
+/* maxrank_blk: optional HOST int[batch] of per-block rank caps (BASELINE config 3 truncates block i at
+ * truncrank(n_i / 2)); entry < 0 or NULL: no per-block cap.  It intersects with spec->maxrank. */
 int makb200_trunc_select_batched(makb200_handle_t* h, int batch, const int* k, double* const* S,
-                                 const makb200_trunc_spec* spec, int* rank_dev, double* eps_dev,
-                                 void* work, size_t lwork);
+                                 const makb200_trunc_spec* spec, const int* maxrank_blk, int* rank_dev,
+                                 double* eps_dev, void* work, size_t lwork);
 
 /* -- adjoint: B (n x m) = A^H.  Used by the LQ family, which every GPU driver of the reference
  * routes through QR of the adjoint (lq_via_qr!, implementations/lq.jl:130-131,303-327), and by

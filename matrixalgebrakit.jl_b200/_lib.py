@@ -68,7 +68,7 @@ SIGNATURES = {
     "makb200_svd_batched_worksize": (_sz, [_vp, _i, _i, _ip, _ip]),
     "makb200_svd_batched": (_i, [_vp, _i, _i, _i, _ip, _ip, _vpp, _ip, _vpp, _vpp, _ip, _vpp, _ip, _vp, _vp, _sz]),
     "makb200_trunc_select_batched_worksize": (_sz, [_vp, _i]),
-    "makb200_trunc_select_batched": (_i, [_vp, _i, _ip, _vpp, _vp, _vp, _vp, _vp, _sz]),
+    "makb200_trunc_select_batched": (_i, [_vp, _i, _ip, _vpp, _vp, _ip, _vp, _vp, _vp, _sz]),
     "makb200_adjoint": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i]),
 }
 

@@ -10,6 +10,7 @@ namespace mak {
 struct TruncDesc {
     const double* S;
     int k;
+    int maxrank;   // per-block cap, < 0: none
 };
 
 __global__ void trunc_select_kernel(int batch, const TruncDesc* __restrict__ descs, makb200_trunc_spec sp,
@@ -18,6 +19,8 @@ __global__ void trunc_select_kernel(int batch, const TruncDesc* __restrict__ des
     if (i >= batch) return;
     int r;
     double e;
+    const int cap = descs[i].maxrank;
+    if (cap >= 0) sp.maxrank = (sp.maxrank >= 0 && sp.maxrank < cap) ? sp.maxrank : cap;   // sp is this thread's copy
     trunc::select(descs[i].k, descs[i].S, sp, &r, &e);
     rank[i] = r;
     eps[i] = e;
@@ -33,16 +36,16 @@ size_t makb200_trunc_select_batched_worksize(makb200_handle_t* h, int batch) {
 }
 
 int makb200_trunc_select_batched(makb200_handle_t* h, int batch, const int* k, double* const* S,
-                                 const makb200_trunc_spec* spec, int* rank_dev, double* eps_dev, void* work,
-                                 size_t lwork) {
+                                 const makb200_trunc_spec* spec, const int* maxrank_blk, int* rank_dev,
+                                 double* eps_dev, void* work, size_t lwork) {
     if (!h) return -1;
     if (batch < 0) return -2;
     if (batch == 0) return 0;
     if (!k) return -3;
     if (!S) return -4;
     if (!spec) return -5;
-    if (!rank_dev) return -6;
-    if (!eps_dev) return -7;
+    if (!rank_dev) return -7;
+    if (!eps_dev) return -8;
     if (spec->by_value && !(spec->vp > 0.0 && spec->vp < 1e300)) return -5;   // finite p only
     if (spec->by_error && !(spec->ep > 0.0 && spec->ep < 1e300)) return -5;
     std::vector<mak::TruncDesc> d((size_t)batch);
@@ -51,6 +54,7 @@ int makb200_trunc_select_batched(makb200_handle_t* h, int batch, const int* k, d
         if (k[i] > 0 && !S[i]) return -4;
         d[i].S = S[i];
         d[i].k = k[i];
+        d[i].maxrank = maxrank_blk ? maxrank_blk[i] : -1;
     }
     mak::Arena ar(work, lwork);
     mak::TruncDesc* ddev = ar.get<mak::TruncDesc>((size_t)batch);

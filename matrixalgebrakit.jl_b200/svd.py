@@ -252,23 +252,25 @@ def svd_vals_batched_(As, Ss=None):
     return Ss
 
 
-def svd_trunc_batched_(As, trunc, USVhs=None):
+def svd_trunc_batched_(As, trunc, USVhs=None, maxranks=None):
     """Batched ``svd_trunc!``: batched compact SVD, then per block the reference's slice and error
     (svd.jl:232-237) -> list of ``(U, S, Vh, eps)``.  Strategies that keep a prefix of the sorted values
     (everything ``TruncationStrategy(; atol, rtol, maxrank, maxerror, minrank)`` builds) are decided for
     ALL blocks by one kernel and one device->host read, and the kept factors are views ``U[:, :r]``,
-    ``S[:r]``, ``Vh[:r, :]`` of the compact ones; other strategies take the per-block host search."""
-    from .truncation import device_spec, trunc_select_batched_
+    ``S[:r]``, ``Vh[:r, :]`` of the compact ones; other strategies take the per-block host search.
+    ``maxranks``: optional per-block rank caps (BASELINE config 3 uses ``truncrank(n_i // 2)`` per block)."""
+    from .truncation import device_spec, trunc_and, trunc_select_batched_, truncrank
     strategy = select_truncation(trunc)
     outs = svd_compact_batched_(As, USVhs)
     spec = device_spec(strategy)
     res = []
     if spec is not None:
-        ranks, eps = trunc_select_batched_([S for _, S, _ in outs], spec)
+        ranks, eps = trunc_select_batched_([S for _, S, _ in outs], spec, maxranks)
         for (U, S, Vh), r, e in zip(outs, ranks, eps):
             res.append((U[:, :r], S[:r], Vh[:r, :], e))
         return res
-    for U, S, Vh in outs:
-        (Ut, St, Vt), ind = _truncate(U, S, Vh, strategy)
+    for i, (U, S, Vh) in enumerate(outs):
+        st = strategy if maxranks is None else trunc_and(strategy, truncrank(int(maxranks[i])))
+        (Ut, St, Vt), ind = _truncate(U, S, Vh, st)
         res.append((Ut, St, Vt, truncation_error_(S, ind)))
     return res

@@ -225,8 +225,9 @@ def device_spec(strategy):
     return spec if _spec_and(spec, s) else None
 
 
-def trunc_select_batched_(Ss, spec):
-    """(ranks, eps) as host lists for the sorted spectra ``Ss`` (device vectors): one launch, one read."""
+def trunc_select_batched_(Ss, spec, maxranks=None):
+    """(ranks, eps) as host lists for the sorted spectra ``Ss`` (device vectors): one launch, one read.
+    ``maxranks``: optional per-block rank caps (intersected with the strategy)."""
     from . import _core
     b = len(Ss)
     if b == 0:
@@ -242,7 +243,12 @@ def trunc_select_batched_(Ss, spec):
     rank = out[:b].view(torch.int32)[:b]          # int32[b] carved from the same allocation
     eps = out[b:]
     work = h.workspace(h.lib.makb200_trunc_select_batched_worksize(h.h, b))
-    rc = h.lib.makb200_trunc_select_batched(h.h, b, k, Sp, C.byref(spec), _core.ptr(rank), _core.ptr(eps),
+    caps = None
+    if maxranks is not None:
+        if len(maxranks) != b:
+            raise ValueError("maxranks: one entry per block expected")
+        caps = (C.c_int * b)(*[int(r) for r in maxranks])
+    rc = h.lib.makb200_trunc_select_batched(h.h, b, k, Sp, C.byref(spec), caps, _core.ptr(rank), _core.ptr(eps),
                                             _core.ptr(work), work.numel())
     h.check(rc, "makb200_trunc_select_batched")
     host = out.cpu()                               # the one device->host read

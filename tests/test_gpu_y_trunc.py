@@ -94,6 +94,17 @@ def test_svd_trunc_batched_device_select(dtype):
             if r:
                 assert O.orth_err(Un) <= O.tol_for(*a.shape) and O.orth_err(Vn, "right") <= O.tol_for(*a.shape)
                 assert abs(np.linalg.norm(a - (Un * S.cpu().numpy()) @ Vn) - np.linalg.norm(So[r:])) <= 1e-11 * So[0]
+    # per-block rank caps (BASELINE config 3: truncrank(n_i // 2) per block), alone and on top of a tolerance
+    caps = [min(a.shape) // 2 for a in As0]
+    for trunc in (None, makb200.trunctol(rtol=0.21)):
+        res = makb200.svd_trunc_batched_([makb200.to_device(a) for a in As0], trunc, maxranks=caps)
+        for a, cap, (U, S, Vh, eps) in zip(As0, caps, res):
+            So = O.svd_vals(a)
+            st = T.truncrank(cap) if trunc is None else T.trunc_and(trunc, T.truncrank(cap))
+            r = len(T._find(So, st, svd=True))
+            assert tuple(U.shape) == (a.shape[0], r) and tuple(Vh.shape) == (r, a.shape[1])
+            np.testing.assert_allclose(S.cpu().numpy(), So[:r], rtol=1e-11, atol=1e-13)
+            assert abs(eps - np.linalg.norm(So[r:])) <= 1e-11 * So[0]
     # a strategy outside the prefix family takes the per-block host path, same return shape
     res = makb200.svd_trunc_batched_([makb200.to_device(a) for a in As0[:4]], makb200.trunctol(atol=1.0, keep_below=True))
     for a, (U, S, Vh, eps) in zip(As0[:4], res):

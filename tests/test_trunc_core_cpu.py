@@ -23,13 +23,14 @@ def lib():
     return ctypes.CDLL(out)
 
 
-def _run(lib, spectra, spec):
+def _run(lib, spectra, spec, caps=None):
     b = len(spectra)
     k = (ctypes.c_int * b)(*[len(s) for s in spectra])
     ptrs = (ctypes.c_void_p * b)(*[s.ctypes.data for s in spectra])
     rank = (ctypes.c_int * b)()
     eps = (ctypes.c_double * b)()
-    assert lib.trunc_select_host(b, k, ptrs, ctypes.byref(spec), rank, eps) == 0
+    capv = (ctypes.c_int * b)(*caps) if caps is not None else None
+    assert lib.trunc_select_host(b, k, ptrs, ctypes.byref(spec), capv, rank, eps) == 0
     return list(rank), list(eps)
 
 
@@ -80,3 +81,20 @@ def test_strategies_outside_the_prefix_family_fall_back():
     spec = T.device_spec(T.select_truncation({"atol": 0.2, "maxrank": 7, "minrank": 2, "maxerror": 0.3}))
     assert (spec.maxrank, spec.minrank, spec.by_value, spec.by_error) == (7, 2, 1, 1)
     assert (spec.vatol, spec.eatol) == (0.2, 0.3)
+
+
+def test_per_block_rank_caps(lib):
+    """BASELINE config 3: block i is truncated at truncrank(n_i // 2), optionally on top of a shared tolerance."""
+    spectra = [s for s in _spectra() if len(s) > 0]
+    caps = [len(s) // 2 for s in spectra]
+    for base in (T.notrunc(), T.trunctol(rtol=0.05), T.select_truncation({"atol": 0.2, "maxrank": 7, "minrank": 2})):
+        ranks, eps = _run(lib, spectra, T.device_spec(base), caps)
+        for v, r, e, cap in zip(spectra, ranks, eps, caps):
+            if isinstance(base, T.TruncationUnion):       # (tol & rank & cap) | minrank
+                inner = T.trunc_and(base.components[0], T.truncrank(cap))
+                st = T.trunc_or(inner, *[c for c in base.components[1:]])
+            else:
+                st = T.trunc_and(base, T.truncrank(cap))
+            ind = T._find(v, st, svd=True)
+            assert np.array_equal(ind, np.arange(r)), (base, cap, r, ind)
+            assert np.isclose(e, np.linalg.norm(v[r:]), rtol=1e-14, atol=0)

@@ -46,6 +46,15 @@ def run(op, idx, rep=1):
     else:
         plan = makb200.BatchedSVDPlan(As)
     fn = plan.run
+    if op == "svdtrunc":
+        # config 3 as stated: svd_trunc!(trunc = truncrank(n_i // 2)) per block = batched compact SVD + ONE
+        # truncation launch + one read; the kept factors are views
+        spec = makb200.truncation.device_spec(makb200.notrunc())
+        caps = [a.shape[0] // 2 for a in As]
+
+        def fn():
+            outs = plan.run()
+            makb200.truncation.trunc_select_batched_([S for _, S, _ in outs], spec, caps)
     ts = []
     for it in range(3):
         for a, b in zip(As, blocks):
@@ -63,7 +72,7 @@ for op in ops:
         idx = [i for i, n in enumerate(mine) if lo <= n <= hi]
         if not idx:
             continue
-        if op in ("svd", "eigh") and lo > 64 and len(idx) > 64:
+        if op in ("svd", "svdtrunc", "eigh") and lo > 64 and len(idx) > 64:
             idx = idx[:64]          # large-block SVD/eigh go through the single-matrix path: bounded sample
         # the smallest bucket is replicated so that the launch carries enough bytes to show the
         # steady-state HBM fraction (4151 blocks are only ~0.1 GB = 17 us at HBM speed)
@@ -73,7 +82,7 @@ for op in ops:
         if op == "qr":
             byt = 16 * 3 * (ns ** 2).sum()
             fl = 4 * (8.0 / 3) * (ns ** 3).sum()
-        elif op == "svd":
+        elif op in ("svd", "svdtrunc"):
             byt = 16 * 3 * (ns ** 2).sum() + 8 * ns.sum()
             fl = 4 * (20.0 / 3) * (ns ** 3).sum()
         else:
