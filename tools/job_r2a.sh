@@ -18,6 +18,8 @@ MAKB200_BRINGUP=1 timeout 600 python -m pytest tests/test_gpu_zz_bringup.py -q -
 echo "== tiny-block QR (16-32 c128, x16 replicas): warp kernel vs panel-blocked warp kernel =="
 timeout 300 python tools/batched_bench.py 20000 32 qr 2>&1 | grep -E "qr_16|blocks_per_s|hbm_frac" | head -6
 MAKB200_BQR_WARP_BLK=1 timeout 300 python tools/batched_bench.py 20000 32 qr 2>&1 | grep -E "qr_16|blocks_per_s|hbm_frac" | head -6
+echo "== batched svd_trunc!(truncrank(n_i/2)) of the 16-64 blocks: compact SVD + one truncation launch =="
+timeout 300 python tools/batched_bench.py 20000 64 svd,svdtrunc 2>&1 | grep -E "svd(trunc)?_(16|33)|blocks_per_s" | head -12
 echo "== batched eigh 65-512 c128 (64 blocks per bucket): pooled per-block hetrd vs one-launch tridiagonalisation =="
 timeout 600 python tools/batched_bench.py 4000 512 eigh 2>&1 | grep -E "eigh_(65|129|257)|blocks_per_s" | head -12
 MAKB200_BHETRD=1 timeout 600 python tools/batched_bench.py 4000 512 eigh 2>&1 | grep -E "eigh_(65|129|257)|blocks_per_s" | head -12
