@@ -116,8 +116,24 @@ def test_julia_ccalls_match_the_header_and_ctypes():
         assert len(sig[1]) == protos[name], f"ctypes signature of {name} has {len(sig[1])} arguments, the header {protos[name]}"
 
 
-def test_every_ctypes_signature_matches_the_header_arity():
+def _ctypes_class(t):
+    import ctypes as C
+    if t in (C.c_int, C.c_uint):
+        return "int"
+    if t is C.c_size_t:
+        return "size"
+    if t is C.c_double:
+        return "double"
+    if t is C.c_void_p or t is C.c_char_p or hasattr(t, "_type_") and not isinstance(t._type_, str):
+        return "ptr"
+    return "?"
+
+
+def test_every_ctypes_signature_matches_the_header():
     protos = _c_prototypes()
+    classes = _c_param_classes()
     for name, (_, args) in makb200._lib.SIGNATURES.items():
         assert name in protos, name
         assert len(args) == protos[name], (name, len(args), protos[name])
+        got = [_ctypes_class(t) for t in args]
+        assert got == classes[name], f"ctypes signature of {name}: {got} vs C parameters {classes[name]}"
