@@ -84,6 +84,11 @@ MatrixAlgebraKit.isantihermitian_exact(A::B200Mat; kwargs...) = YAB200.hermitian
 MatrixAlgebraKit.project_hermitian_native!(A::B200Mat, B::B200Mat, ::Val{anti}; kwargs...) where {anti} =
     YAB200.project_hermitian!(A, B, anti)
 
+# one! / uppertriangular! / lowertriangular! (common/initialization.jl:11-36; n `zero!` launches on a CuArray): one launch
+MatrixAlgebraKit.one!(A::B200Mat) = (isempty(A) ? A : YAB200.tri_init!(A, 0))
+MatrixAlgebraKit.uppertriangular!(A::B200Mat) = YAB200.tri_init!(A, 1)
+MatrixAlgebraKit.lowertriangular!(A::B200Mat) = YAB200.tri_init!(A, 2)
+
 # is_left_isometric (matrixproperties.jl:53-58): Gram matrix on the DMMA GEMM, both norms from one reduction
 function MatrixAlgebraKit.is_left_isometric(A::B200Mat; atol::Real = 0, rtol::Real = MatrixAlgebraKit.defaulttol(A), kwargs...)
     P = similar(A, (size(A, 2), size(A, 2)))

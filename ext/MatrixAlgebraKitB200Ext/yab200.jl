@@ -140,6 +140,15 @@ function project_hermitian!(A::StridedCuMatrix{T}, B::StridedCuMatrix{T}, anti::
     return B
 end
 
+# one! (mode 0), uppertriangular! (1), lowertriangular! (2) in one launch
+function tri_init!(A::StridedCuMatrix{T}, mode::Integer) where {T <: B200Float}
+    m, n = size(A)
+    rc = ccall((:makb200_tri_init, libmakb200), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cint, CuPtr{T}, Cint),
+        handle(), dtypecode(T), mode, m, n, A, max(1, stride(A, 2)))
+    chkargsok(rc, "makb200_tri_init")
+    return A
+end
+
 # (‖part that must vanish‖_F, max|A_ij|, ‖A‖_F, #exact mismatches): every ingredient of ishermitian / isantihermitian
 function hermitian_props(A::StridedCuMatrix{T}, anti::Bool) where {T <: B200Float}
     n = checksquare(A)

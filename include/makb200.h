@@ -140,6 +140,10 @@ int makb200_hermitian_props(makb200_handle_t* h, int dtype, int anti, int n, con
 /* is_left_isometric (common/matrixproperties.jl:53-58) on the Gram matrix P = A^H A (makb200_gemm):
  * out2_dev (DEVICE double[2]) = { ||P||_F^2, ||P - I||_F^2 }. */
 int makb200_gram_defect(makb200_handle_t* h, int dtype, int n, const void* P, int ldp, double* out2_dev);
+/* one! / uppertriangular! / lowertriangular! (src/common/initialization.jl:11-36; on a CuArray the
+ * reference's uppertriangular! is one zero! launch per column): one launch.
+ * mode 0: A = I (rectangular identity), 1: zero strictly below the diagonal, 2: zero strictly above it. */
+int makb200_tri_init(makb200_handle_t* h, int dtype, int mode, int m, int n, void* A, int lda);
 size_t makb200_eigh_worksize(makb200_handle_t* h, int dtype, int n);
 int makb200_eigh(makb200_handle_t* h, int dtype, int fixgauge, int n, void* A, int lda, double* W,
                  void* V, int ldv, void* work, size_t lwork, int* info_dev);

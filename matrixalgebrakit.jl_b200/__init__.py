@@ -33,3 +33,4 @@ from .projections import (defaulttol, is_left_isometric, is_right_isometric, isa
                           project_hermitian_, project_isometric, project_isometric_)
 from .eigh import eigh_vals_batched_  # noqa: E402,F401
 from .svd import svd_vals_batched_  # noqa: E402,F401
+from .projections import lowertriangular_, one_, uppertriangular_  # noqa: E402,F401

@@ -617,6 +617,19 @@ int makb200_hermitian_props(makb200_handle_t* h, int dtype, int anti, int n, con
     return mak::herm_props_t<cplx>(h, anti != 0, n, (const cplx*)A, lda, out4_dev);
 }
 
+int makb200_tri_init(makb200_handle_t* h, int dtype, int mode, int m, int n, void* A, int lda) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (mode < 0 || mode > 2) return -3;
+    if (m < 0) return -4;
+    if (n < 0) return -5;
+    if (lda < maxi(1, m)) return -7;
+    if (m == 0 || n == 0) return 0;
+    if (!A) return -6;
+    if (dtype == MAKB200_F64) return mak::tri_init_t<double>(h, mode, m, n, (double*)A, lda);
+    return mak::tri_init_t<cplx>(h, mode, m, n, (cplx*)A, lda);
+}
+
 int makb200_gram_defect(makb200_handle_t* h, int dtype, int n, const void* P, int ldp, double* out2_dev) {
     if (!h) return -1;
     if (!dtype_ok(dtype)) return -2;

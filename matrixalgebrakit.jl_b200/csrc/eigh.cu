@@ -1020,10 +1020,21 @@ int gram_defect_t(makb200_handle* h, int n, const T* P, int ldp, double* out2) {
     MAK_LAUNCH_CHECK(h, "gram_defect_kernel");
     return 0;
 }
+template <typename T>
+int tri_init_t(makb200_handle* h, int mode, int m, int n, T* A, int lda) {
+    if (m <= 0 || n <= 0) return 0;
+    const size_t total = (size_t)m * n;
+    const size_t want = (total + 255) / 256, cap = (size_t)h->num_sms * 16;
+    tri_init_kernel<T><<<(unsigned)(want < cap ? want : cap), 256, 0, h->stream>>>(mode, m, n, A, lda);
+    count_launch();
+    MAK_LAUNCH_CHECK(h, "tri_init_kernel");
+    return 0;
+}
 #define INST_PROJ(T)                                                                          \
     template int project_herm_t<T>(makb200_handle*, int, int, const T*, int, T*, int);        \
     template int herm_props_t<T>(makb200_handle*, int, int, const T*, int, double*);          \
-    template int gram_defect_t<T>(makb200_handle*, int, const T*, int, double*);
+    template int gram_defect_t<T>(makb200_handle*, int, const T*, int, double*);             \
+    template int tri_init_t<T>(makb200_handle*, int, int, int, T*, int);
 INST_PROJ(double)
 INST_PROJ(cplx)
 

@@ -144,4 +144,19 @@ __global__ void gram_defect_kernel(int n, const T* __restrict__ P, int ldp, doub
     }
 }
 
+// one! / uppertriangular! / lowertriangular! (src/common/initialization.jl:11-36; on a CuArray the reference's
+// uppertriangular! is one `zero!` launch PER COLUMN): one grid-stride launch over the m x n entries.
+//   mode 0: A = I (rectangular identity)   1: zero below the diagonal   2: zero above the diagonal
+template <typename T>
+__global__ void tri_init_kernel(int mode, int m, int n, T* __restrict__ A, int lda) {
+    const size_t total = (size_t)m * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(idx % m), c = (int)(idx / m);
+        T* p = A + (size_t)c * lda + r;
+        if (mode == 0) *p = (r == c) ? one<T>() : zero<T>();
+        else if (mode == 1) { if (r > c) *p = zero<T>(); }
+        else { if (r < c) *p = zero<T>(); }
+    }
+}
+
 }  // namespace mak

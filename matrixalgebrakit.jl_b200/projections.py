@@ -184,3 +184,30 @@ def isunitary(A, atol=0, rtol=None):
     if A.shape[0] != A.shape[1]:
         return False
     return is_left_isometric(A, atol, rtol)
+
+
+def _tri_init_(A, mode):
+    if A.dim() != 2 or not _core.is_colmajor(A):
+        raise ValueError("A: column-major matrix expected")
+    m, n = A.shape
+    if m == 0 or n == 0:
+        return A
+    h = _core.Handle.get(A.device)
+    rc = h.lib.makb200_tri_init(h.h, _core.dtype_code(A), mode, m, n, _core.ptr(A), _core.ld(A))
+    h.check(rc, "makb200_tri_init")
+    return A
+
+
+def one_(A):
+    """``one!(A)`` (src/common/initialization.jl:11-16): rectangular identity, one launch."""
+    return _tri_init_(A, 0)
+
+
+def uppertriangular_(A):
+    """``uppertriangular!(A)`` (initialization.jl:18-26): zero strictly below the diagonal, one launch."""
+    return _tri_init_(A, 1)
+
+
+def lowertriangular_(A):
+    """``lowertriangular!(A)`` (initialization.jl:28-36): zero strictly above the diagonal, one launch."""
+    return _tri_init_(A, 2)

@@ -180,3 +180,10 @@ extern "C" int emu_bhetrd(int dt, int batch, const int* n, void** A, const int* 
     emu::set_order(order, seed);
     return dt == 0 ? run_bhetrd<double>(batch, n, A, lda, d, e, tau, mirror) : run_bhetrd<cplx>(batch, n, A, lda, d, e, tau, mirror);
 }
+
+extern "C" int emu_tri_init(int dt, int mode, int m, int n, void* A, int lda, int grid, int order, uint64_t seed) {
+    emu::set_order(order, seed);
+    if (dt == 0) emu::launch(mak::tri_init_kernel<double>, dim3(grid), dim3(256), 0, mode, m, n, (double*)A, lda);
+    else emu::launch(mak::tri_init_kernel<cplx>, dim3(grid), dim3(256), 0, mode, m, n, (cplx*)A, lda);
+    return 0;
+}

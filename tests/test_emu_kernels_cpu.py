@@ -354,3 +354,16 @@ def test_emu_bhetrd_batch(lib, dtype, mirror):
             Q = _q_from_reflectors(b[:n], tau)
             assert np.linalg.norm(Q.conj().T @ Q - np.eye(n)) <= 10 * n * EPS
             assert np.linalg.norm(Q.conj().T @ a @ Q - T) <= 10 * n * EPS * np.linalg.norm(a)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("m,n,pad,grid", [(1, 1, 0, 1), (7, 5, 2, 1), (5, 7, 0, 2), (40, 40, 3, 3)])
+def test_emu_tri_init(lib, m, n, pad, grid, dtype):
+    dt = 0 if dtype == "f64" else 1
+    A0 = O.randn_matrix(m, n, dtype, seed=m + n)
+    want = [np.eye(m, n, dtype=A0.dtype), np.triu(A0), np.tril(A0)]
+    for mode in range(3):
+        buf = np.full((m + pad, n), 5.0, dtype=A0.dtype, order="F")
+        buf[:m] = A0
+        lib.emu_tri_init(dt, mode, m, n, _vp(buf), m + pad, grid, 0, ctypes.c_uint64(0))
+        assert np.array_equal(buf[:m], want[mode]) and np.all(buf[m:] == 5.0)

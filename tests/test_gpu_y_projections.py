@@ -104,3 +104,23 @@ def test_project_isometric_and_isisometric(m, n, dtype):
         makb200.isisometric(W, side="up")
     with pytest.raises(ValueError):                                      # m < n (projections.jl:27-28)
         makb200.project_isometric(makb200.to_device(O.randn_matrix(n, m + 1, dtype, 2)))
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("m,n", [(1, 1), (54, 37), (37, 54), (200, 200)])
+def test_one_uppertriangular_lowertriangular(m, n, dtype):
+    """one! / uppertriangular! / lowertriangular! (src/common/initialization.jl:11-36), one launch each, in place,
+    strided views included."""
+    import makb200
+    A0 = O.randn_matrix(m, n, dtype, seed=m * n)
+    want = {makb200.one_: np.eye(m, n), makb200.uppertriangular_: np.triu(A0), makb200.lowertriangular_: np.tril(A0)}
+    for f, ref in want.items():
+        big = makb200.colmajor_zeros(m + 5, n, makb200.to_device(A0).dtype, "cuda:0")
+        big[:m, :] = makb200.to_device(A0)
+        big[m:, :] = 7.0
+        view = big[:m, :]
+        assert f(view) is view
+        out = makb200.to_numpy(big)
+        assert np.array_equal(out[:m], ref.astype(A0.dtype)) and np.all(out[m:] == 7.0)
+    E = makb200.colmajor_zeros(0, 4, torch.float64, "cuda:0")
+    assert makb200.one_(E) is E
