@@ -73,44 +73,12 @@ def test_svd_graded_and_vals():
     tol = O.tol_for(n)
     assert np.max(np.abs(S - sv)) / sv[0] <= tol
     assert O.rel_resid(A, U * S, Vh) <= tol and O.orth_err(U) <= tol and O.orth_err(Vh, "right") <= tol
-    Sv = makb200.svd_vals(makb200.to_device(A)).cpu().numpy()
-    assert np.max(np.abs(Sv - sv)) / sv[0] <= tol
+    # svd_vals! (values-only path) on this graded spectrum: tests/test_gpu_y_vals.py
     U2, S2, Vh2 = makb200.svd_compact(makb200.to_device(A), fixgauge=False)
     assert O.rel_resid(A, makb200.to_numpy(U2) * S2.cpu().numpy(), makb200.to_numpy(Vh2)) <= tol
 
 
-@pytest.mark.parametrize("dtype", ["f64", "c128"])
-def test_svd_trunc_vs_oracle(dtype):
-    import makb200
-    A0 = O.randn_matrix(54, 37, dtype, seed=9)
-    S0 = O.svd_vals(A0)
-    r = 17
-    U, S, Vh, eps = makb200.svd_trunc(makb200.to_device(A0), trunc=makb200.truncrank(r))
-    Uo, So, Vho, epso = O.svd_trunc(A0, O.truncrank(r))
-    Un, Sn, Vn = makb200.to_numpy(U), S.cpu().numpy(), makb200.to_numpy(Vh)
-    assert Un.shape == (54, r) and Vn.shape == (r, 37)
-    np.testing.assert_allclose(Sn, S0[:r], rtol=1e-12)
-    np.testing.assert_allclose(eps, epso, rtol=1e-10)
-    np.testing.assert_allclose(np.linalg.norm(A0 - (Un * Sn) @ Vn, 2), S0[r], rtol=1e-9)
-    assert np.linalg.norm(Un - Uo) < 1e-9 and np.linalg.norm(Vn - Vho) < 1e-9
-    # equivalence of the strategies (svd.jl:156-197)
-    for tr in (makb200.trunctol(atol=S0[r] + 1e-9), makb200.truncerror(atol=np.linalg.norm(S0[r:]) + 1e-9),
-               {"maxrank": r}):
-        U2, S2, Vh2 = makb200.svd_trunc_no_error(makb200.to_device(A0), trunc=tr)
-        assert S2.numel() == r
-    # fixed spectrum fixture (svd.jl:198-254)
-    Uq, _ = O.qr_compact(O.randn_matrix(4, 4, dtype, 1))
-    Vq, _ = O.qr_compact(O.randn_matrix(4, 4, dtype, 2))
-    Sd = np.array([0.9, 0.3, 0.1, 0.01])
-    A4 = (Uq * Sd) @ Vq
-    for tr, keep in (({"rtol": 0.2, "maxrank": 1}, 1), ({"rtol": 0.2, "maxrank": 3}, 2), ({"rtol": 0.5, "minrank": 3}, 3),
-                     ({"rtol": 0.2, "minrank": 1}, 2), (makb200.trunctol(atol=0.2), 2)):
-        U4, S4, V4, e4 = makb200.svd_trunc(makb200.to_device(A4), trunc=tr)
-        np.testing.assert_allclose(S4.cpu().numpy(), Sd[:keep], rtol=1e-12)
-        np.testing.assert_allclose(e4, np.linalg.norm(Sd[keep:]), rtol=1e-10)
-    with pytest.raises(ValueError):
-        talg = makb200.TruncatedAlgorithm(makb200.SVDViaPolar(), makb200.trunctol(atol=0.2))
-        makb200.svd_trunc(makb200.to_device(A4), alg=talg, trunc={"maxrank": 2})
+# test_svd_trunc_vs_oracle lives in tests/test_gpu_y_trunc.py (truncrank takes the leading-rank path)
 
 
 @pytest.mark.parametrize("dtype", ["f64", "c128"])
@@ -171,11 +139,7 @@ def test_svd_batched_vs_oracle(dtype):
     torch.cuda.synchronize()
     for a, (U, S, Vh) in zip(As0, outs):
         _check_svd(a, makb200.to_numpy(U), S.cpu().numpy(), makb200.to_numpy(Vh))
-    tr = makb200.svd_trunc_batched_([makb200.to_device(a) for a in As0[:6]], makb200.truncrank(5))
-    for a, (U, S, Vh, eps) in zip(As0[:6], tr):
-        So = O.svd_vals(a)
-        k = min(5, len(So))
-        np.testing.assert_allclose(S.cpu().numpy(), So[:k], rtol=1e-11)
+    # batched svd_trunc! (device-side truncation search): tests/test_gpu_y_trunc.py
 
 
 @pytest.mark.parametrize("dtype", ["f64", "c128"])

@@ -141,3 +141,37 @@ def test_eigh_batched_values_only_including_large_blocks(dtype):
     for a, W, n in zip(As0, Ws, ns):
         wref = O.eigh_vals(a)
         assert np.max(np.abs(W.cpu().numpy() - wref)) / np.abs(wref).max() <= 10 * n * EPS
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_svd_trunc_vs_oracle(dtype):
+    import makb200
+    A0 = O.randn_matrix(54, 37, dtype, seed=9)
+    S0 = O.svd_vals(A0)
+    r = 17
+    U, S, Vh, eps = makb200.svd_trunc(makb200.to_device(A0), trunc=makb200.truncrank(r))
+    Uo, So, Vho, epso = O.svd_trunc(A0, O.truncrank(r))
+    Un, Sn, Vn = makb200.to_numpy(U), S.cpu().numpy(), makb200.to_numpy(Vh)
+    assert Un.shape == (54, r) and Vn.shape == (r, 37)
+    np.testing.assert_allclose(Sn, S0[:r], rtol=1e-12)
+    np.testing.assert_allclose(eps, epso, rtol=1e-10)
+    np.testing.assert_allclose(np.linalg.norm(A0 - (Un * Sn) @ Vn, 2), S0[r], rtol=1e-9)
+    assert np.linalg.norm(Un - Uo) < 1e-9 and np.linalg.norm(Vn - Vho) < 1e-9
+    # equivalence of the strategies (svd.jl:156-197)
+    for tr in (makb200.trunctol(atol=S0[r] + 1e-9), makb200.truncerror(atol=np.linalg.norm(S0[r:]) + 1e-9),
+               {"maxrank": r}):
+        U2, S2, Vh2 = makb200.svd_trunc_no_error(makb200.to_device(A0), trunc=tr)
+        assert S2.numel() == r
+    # fixed spectrum fixture (svd.jl:198-254)
+    Uq, _ = O.qr_compact(O.randn_matrix(4, 4, dtype, 1))
+    Vq, _ = O.qr_compact(O.randn_matrix(4, 4, dtype, 2))
+    Sd = np.array([0.9, 0.3, 0.1, 0.01])
+    A4 = (Uq * Sd) @ Vq
+    for tr, keep in (({"rtol": 0.2, "maxrank": 1}, 1), ({"rtol": 0.2, "maxrank": 3}, 2), ({"rtol": 0.5, "minrank": 3}, 3),
+                     ({"rtol": 0.2, "minrank": 1}, 2), (makb200.trunctol(atol=0.2), 2)):
+        U4, S4, V4, e4 = makb200.svd_trunc(makb200.to_device(A4), trunc=tr)
+        np.testing.assert_allclose(S4.cpu().numpy(), Sd[:keep], rtol=1e-12)
+        np.testing.assert_allclose(e4, np.linalg.norm(Sd[keep:]), rtol=1e-10)
+    with pytest.raises(ValueError):
+        talg = makb200.TruncatedAlgorithm(makb200.SVDViaPolar(), makb200.trunctol(atol=0.2))
+        makb200.svd_trunc(makb200.to_device(A4), alg=talg, trunc={"maxrank": 2})

@@ -113,3 +113,15 @@ def test_vals_batched(dtype):
         s = S.cpu().numpy()
         assert s.shape == sref.shape and np.all(np.diff(s) <= 0)
         assert np.max(np.abs(s - sref)) / sref[0] <= 10 * max(a.shape) * EPS
+
+
+def test_svd_vals_graded_spectrum():
+    """Singular values spanning 12 decades between random unitaries: absolute accuracy eps * sigma_1."""
+    import makb200
+    n = 128
+    Uq, _ = O.qr_compact(O.randn_matrix(n, n, "f64", 5))
+    Vq, _ = O.qr_compact(O.randn_matrix(n, n, "f64", 6))
+    sv = 10.0 ** (-12 * np.arange(n) / n)
+    A = (Uq * sv) @ Vq
+    Sv = makb200.svd_vals(makb200.to_device(A)).cpu().numpy()
+    assert np.max(np.abs(Sv - sv)) / sv[0] <= O.tol_for(n)
