@@ -140,6 +140,16 @@ function project_hermitian!(A::StridedCuMatrix{T}, B::StridedCuMatrix{T}, anti::
     return B
 end
 
+# ‖A‖_F² in one launch (‖W‖_F² = n for an isometric polar factor, = rank for QDWH's partial isometry)
+function fro2(A::StridedCuMatrix{T}) where {T <: B200Float}
+    m, n = size(A)
+    out = CUDA.zeros(Float64, 1)
+    rc = ccall((:makb200_fro2, libmakb200), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, CuPtr{T}, Cint, CuPtr{Float64}),
+        handle(), dtypecode(T), m, n, A, max(1, stride(A, 2)), out)
+    chkargsok(rc, "makb200_fro2")
+    return Array(out)[1]
+end
+
 # one! (mode 0), uppertriangular! (1), lowertriangular! (2) in one launch
 function tri_init!(A::StridedCuMatrix{T}, mode::Integer) where {T <: B200Float}
     m, n = size(A)

@@ -140,6 +140,10 @@ int makb200_hermitian_props(makb200_handle_t* h, int dtype, int anti, int n, con
 /* is_left_isometric (common/matrixproperties.jl:53-58) on the Gram matrix P = A^H A (makb200_gemm):
  * out2_dev (DEVICE double[2]) = { ||P||_F^2, ||P - I||_F^2 }. */
 int makb200_gram_defect(makb200_handle_t* h, int dtype, int n, const void* P, int ldp, double* out2_dev);
+/* out1_dev[0] = ||A||_F^2 (DEVICE double).  Used after makb200_polar_qdwh: ||W||_F^2 = n for an isometric polar
+ * factor, = rank(A) for the partial isometry QDWH converges to on singular input (the host layer then
+ * takes the PolarViaSVD recipe, implementations/polar.jl:59-70, so that W is isometric as with LAPACK). */
+int makb200_fro2(makb200_handle_t* h, int dtype, int m, int n, const void* A, int lda, double* out1_dev);
 /* one! / uppertriangular! / lowertriangular! (src/common/initialization.jl:11-36; on a CuArray the
  * reference's uppertriangular! is one zero! launch per column): one launch.
  * mode 0: A = I (rectangular identity), 1: zero strictly below the diagonal, 2: zero strictly above it. */

@@ -45,6 +45,7 @@ SIGNATURES = {
     "makb200_project_hermitian": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i]),
     "makb200_hermitian_props": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
     "makb200_tri_init": (_i, [_vp, _i, _i, _i, _i, _vp, _i]),
+    "makb200_fro2": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
     "makb200_gram_defect": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "makb200_eigh_worksize": (_sz, [_vp, _i, _i]),
     "makb200_eigh": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _sz, _vp]),

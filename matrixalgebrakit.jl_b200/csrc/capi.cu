@@ -630,6 +630,18 @@ int makb200_tri_init(makb200_handle_t* h, int dtype, int mode, int m, int n, voi
     return mak::tri_init_t<cplx>(h, mode, m, n, (cplx*)A, lda);
 }
 
+int makb200_fro2(makb200_handle_t* h, int dtype, int m, int n, const void* A, int lda, double* out1_dev) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (m < 0) return -3;
+    if (n < 0) return -4;
+    if (lda < maxi(1, m)) return -6;
+    if (!out1_dev) return -7;
+    if (m > 0 && n > 0 && !A) return -5;
+    if (dtype == MAKB200_F64) return mak::fro2_t<double>(h, m, n, (const double*)A, lda, out1_dev);
+    return mak::fro2_t<cplx>(h, m, n, (const cplx*)A, lda, out1_dev);
+}
+
 int makb200_gram_defect(makb200_handle_t* h, int dtype, int n, const void* P, int ldp, double* out2_dev) {
     if (!h) return -1;
     if (!dtype_ok(dtype)) return -2;

@@ -1030,11 +1030,23 @@ int tri_init_t(makb200_handle* h, int mode, int m, int n, T* A, int lda) {
     MAK_LAUNCH_CHECK(h, "tri_init_kernel");
     return 0;
 }
+template <typename T>
+int fro2_t(makb200_handle* h, int m, int n, const T* A, int lda, double* out1) {
+    MAK_CUDA(h, cudaMemsetAsync(out1, 0, sizeof(double), h->stream));
+    if (m <= 0 || n <= 0) return 0;
+    const size_t total = (size_t)m * n;
+    const size_t want = (total + 255) / 256, cap = (size_t)h->num_sms * 8;
+    fro2_atomic_kernel<T><<<(unsigned)(want < cap ? want : cap), 256, 0, h->stream>>>(m, n, A, lda, out1);
+    count_launch();
+    MAK_LAUNCH_CHECK(h, "fro2_atomic_kernel");
+    return 0;
+}
 #define INST_PROJ(T)                                                                          \
     template int project_herm_t<T>(makb200_handle*, int, int, const T*, int, T*, int);        \
     template int herm_props_t<T>(makb200_handle*, int, int, const T*, int, double*);          \
     template int gram_defect_t<T>(makb200_handle*, int, const T*, int, double*);             \
-    template int tri_init_t<T>(makb200_handle*, int, int, int, T*, int);
+    template int tri_init_t<T>(makb200_handle*, int, int, int, T*, int);                    \
+    template int fro2_t<T>(makb200_handle*, int, int, const T*, int, double*);
 INST_PROJ(double)
 INST_PROJ(cplx)
 

@@ -9,6 +9,8 @@ template <typename T> int herm_props_t(makb200_handle* h, int anti, int n, const
 template <typename T> int gram_defect_t(makb200_handle* h, int n, const T* P, int ldp, double* out2);
 // mode 0: A = I, 1: zero below the diagonal (uppertriangular!), 2: zero above it (lowertriangular!)
 template <typename T> int tri_init_t(makb200_handle* h, int mode, int m, int n, T* A, int lda);
+// out1[0] = ||A||_F^2
+template <typename T> int fro2_t(makb200_handle* h, int m, int n, const T* A, int lda, double* out1);
 template <typename T> size_t eigh_worksize_t(makb200_handle* h, int n);
 template <typename T>
 struct TrdPre { double* d; double* e; T* tau; };   // a block already tridiagonalised in place (bhetrd_batched_t)

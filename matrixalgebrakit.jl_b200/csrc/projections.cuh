@@ -159,4 +159,26 @@ __global__ void tri_init_kernel(int mode, int m, int n, T* __restrict__ A, int l
     }
 }
 
+// out[0] += ||A||_F^2 of an m x n matrix (grid-stride, one atomic per CTA; feeds threshold tests only, e.g.
+// ||W||_F^2 = n for an isometric polar factor, = rank for the partial isometry QDWH returns on singular input)
+template <typename T>
+__global__ void fro2_atomic_kernel(int m, int n, const T* __restrict__ A, int lda, double* out) {
+    __shared__ double red[8];
+    double a = 0.0;
+    const size_t total = (size_t)m * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(idx % m), c = (int)(idx / m);
+        a += abs2_(A[(size_t)c * lda + r]);
+    }
+    a = warp_sum(a);
+    const int t = threadIdx.x;
+    if ((t & 31) == 0) red[t >> 5] = a;
+    __syncthreads();
+    if (t == 0) {
+        double s0 = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s0 += red[i];
+        atomicAdd(out, s0);
+    }
+}
+
 }  // namespace mak

@@ -46,6 +46,11 @@ def left_polar_(A, WP=None, alg=None, **kw):
     h = _core.Handle.get(A.device)
     dt = _core.dtype_code(A)
     want_p = P is not None and P.numel() > 0
+    # QDWH converges to a PARTIAL isometry when A is singular (zero singular values stay zero); the reference's
+    # PolarViaSVD returns an isometric W for any input.  Keep a copy of A (the C call destroys it) so that the
+    # rare singular case can take the PolarViaSVD recipe on the rank-robust B200 SVD.
+    A_keep = _core.colmajor_empty(m, n, A.dtype, A.device)
+    A_keep.copy_(A)
     lw = h.lib.makb200_polar_worksize(h.h, dt, m, n)
     work = h.workspace(lw)
     iters = C.c_int(0)
@@ -55,6 +60,13 @@ def left_polar_(A, WP=None, alg=None, **kw):
                                   int(alg.get("maxiter") or 0), _core.ptr(work), work.numel(), C.byref(iters),
                                   C.c_void_p(0))
     h.check(rc, "makb200_polar_qdwh")
+    fro2 = torch.empty(1, dtype=torch.float64, device=A.device)
+    rc = h.lib.makb200_fro2(h.h, dt, m, n, _core.ptr(W), _core.ld(W), _core.ptr(fro2))
+    h.check(rc, "makb200_fro2")
+    w2 = float(fro2.item())            # ||W||_F^2 = n for an isometry, = rank(A) for a partial isometry
+    if not (w2 > n - 0.5):
+        from .algorithms import SVDViaPolar
+        return _left_polar_via_svd_(A_keep, W, P, Algorithm("PolarViaSVD", {"svd_alg": SVDViaPolar()}))
     return W, P
 
 

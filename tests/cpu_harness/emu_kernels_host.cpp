@@ -187,3 +187,11 @@ extern "C" int emu_tri_init(int dt, int mode, int m, int n, void* A, int lda, in
     else emu::launch(mak::tri_init_kernel<cplx>, dim3(grid), dim3(256), 0, mode, m, n, (cplx*)A, lda);
     return 0;
 }
+
+extern "C" int emu_fro2(int dt, int m, int n, const void* A, int lda, double* out1, int grid, int order, uint64_t seed) {
+    emu::set_order(order, seed);
+    out1[0] = 0.0;
+    if (dt == 0) emu::launch(mak::fro2_atomic_kernel<double>, dim3(grid), dim3(256), 0, m, n, (const double*)A, lda, out1);
+    else emu::launch(mak::fro2_atomic_kernel<cplx>, dim3(grid), dim3(256), 0, m, n, (const cplx*)A, lda, out1);
+    return 0;
+}

@@ -367,3 +367,15 @@ def test_emu_tri_init(lib, m, n, pad, grid, dtype):
         buf[:m] = A0
         lib.emu_tri_init(dt, mode, m, n, _vp(buf), m + pad, grid, 0, ctypes.c_uint64(0))
         assert np.array_equal(buf[:m], want[mode]) and np.all(buf[m:] == 5.0)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("m,n,pad,grid", [(1, 1, 0, 1), (70, 33, 3, 2), (33, 70, 0, 5)])
+def test_emu_fro2(lib, m, n, pad, grid, dtype):
+    dt = 0 if dtype == "f64" else 1
+    A0 = O.randn_matrix(m, n, dtype, seed=m + n)
+    buf = np.full((m + pad, n), 9.0, dtype=A0.dtype, order="F")
+    buf[:m] = A0
+    out = np.zeros(1)
+    lib.emu_fro2(dt, m, n, _vp(buf), m + pad, _vp(out), grid, 2, ctypes.c_uint64(3))
+    assert np.isclose(out[0], np.linalg.norm(A0) ** 2, rtol=1e-13)

@@ -51,3 +51,29 @@ def test_svd_of_zero_and_trunc_of_rank_deficient(dtype):
     U, S, Vh, eps = makb200.svd_trunc(makb200.to_device(A0), trunc=makb200.truncrank(50))   # leading-r path, r > rank
     assert tuple(U.shape) == (140, 50) and O.orth_err(makb200.to_numpy(U)) <= O.tol_for(140, 110)
     assert O.rel_resid(A0, makb200.to_numpy(U) * S.cpu().numpy(), makb200.to_numpy(Vh)) <= O.tol_for(140, 110)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("m,n,r", [(120, 90, 40), (150, 150, 149), (100, 80, 0)])
+def test_left_polar_and_project_isometric_rank_deficient(m, n, r, dtype):
+    """left_polar! / project_isometric! on a singular matrix: QDWH alone gives a partial isometry (||W||_F^2 = rank);
+    the host layer detects it (makb200_fro2) and takes the PolarViaSVD recipe (polar.jl:59-70), so W is isometric,
+    P Hermitian PSD and A = W P, as with the reference's LAPACK path."""
+    import makb200
+    A0 = _lowrank(m, n, r, dtype, seed=m + r) if r > 0 else np.zeros((m, n), dtype=O.randn_matrix(1, 1, dtype).dtype, order="F")
+    W, P = makb200.left_polar(makb200.to_device(A0))
+    Wn, Pn = makb200.to_numpy(W), makb200.to_numpy(P)
+    tol = O.tol_for(m, n)
+    assert O.orth_err(Wn) <= tol
+    assert np.linalg.norm(Wn @ Pn - A0) <= tol * max(np.linalg.norm(A0), 1e-300) or (r == 0 and np.linalg.norm(Wn @ Pn) == 0)
+    assert np.linalg.norm(Pn - Pn.conj().T) <= tol * max(np.linalg.norm(Pn), 1e-300) or r == 0
+    ev = np.linalg.eigvalsh((Pn + Pn.conj().T) / 2)
+    assert ev.min() >= -tol * max(ev.max(), 1e-300) - 1e-300
+    Wi = makb200.project_isometric(makb200.to_device(A0))
+    assert makb200.isisometric(Wi) and O.orth_err(makb200.to_numpy(Wi)) <= tol
+    # a full-rank input keeps taking the pure QDWH path and returns the caller's objects
+    A1 = O.randn_matrix(m, n, dtype, seed=1)
+    W2 = makb200.colmajor_empty(m, n, W.dtype, "cuda:0")
+    P2 = makb200.colmajor_empty(n, n, W.dtype, "cuda:0")
+    Wr, Pr = makb200.left_polar_(makb200.to_device(A1), (W2, P2))
+    assert Wr is W2 and Pr is P2 and O.orth_err(makb200.to_numpy(W2)) <= tol
