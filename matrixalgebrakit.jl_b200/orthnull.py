@@ -7,10 +7,6 @@
 * ``left_orth_/right_orth_/left_null_/right_null_`` — thin routers
   (src/implementations/orthnull.jl:79-117) with ``kind`` in {"qr"/"lq", "polar", "svd"}.
 All numerical work stays in libmakb200 (QR, adjoint, SVD, polar, GEMM)."""
-import ctypes as C
-
-import torch
-
 from . import _core
 from .qr import copy_input, qr_compact_, qr_full_
 from .svd import svd_compact_, svd_trunc_no_error_

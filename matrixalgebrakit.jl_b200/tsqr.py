@@ -11,7 +11,6 @@ the data path); it is latency-bound (~10-20 us per round) next to >= 15 ms of lo
 The numerical kernels are injected through ``ops`` so the tree logic can be tested with gloo on
 CPU (tests/test_tsqr_gloo.py supplies a numpy stand-in); the default ``ops`` is the CUDA library
 and fails loudly without a GPU."""
-import ctypes as C
 
 import torch
 import torch.distributed as dist
