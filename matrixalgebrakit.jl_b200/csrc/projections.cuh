@@ -181,4 +181,29 @@ __global__ void fro2_atomic_kernel(int m, int n, const T* __restrict__ A, int ld
     }
 }
 
+// upper <- conj(lower) of an n x n matrix, in place, tiled so both sides are coalesced; the diagonal is made
+// real.  One CTA per tile pair (bi >= bj) reads the lower tile into shared memory and writes its adjoint into
+// the mirror tile.  Used by the lower-triangle variant of the dense -> band reduction (sy2sb_t, qr.cu), whose
+// rank-2b update only computes the tiles on and below the diagonal.
+template <typename T>
+__global__ void mirror_lower_kernel(int n, T* __restrict__ A, int lda) {
+    __shared__ T tile[32][33];
+    const int bi = blockIdx.x, bj = blockIdx.y;   // tile rows bi*32.., columns bj*32..
+    if (bi < bj) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int k = ty; k < 32; k += 8) {
+        const int r = bi * 32 + tx, c = bj * 32 + k;
+        tile[k][tx] = (r < n && c < n) ? A[(size_t)c * lda + r] : zero<T>();
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        // target (r2, c2) in tile (bj, bi): r2 = bj*32 + tx, c2 = bi*32 + k;  source (c2, r2) = tile[tx][k]
+        const int r2 = bj * 32 + tx, c2 = bi * 32 + k;
+        if (r2 < n && c2 < n) {
+            if (r2 < c2) A[(size_t)c2 * lda + r2] = conj_(tile[tx][k]);
+            else if (r2 == c2) A[(size_t)c2 * lda + r2] = mk<T>(real_(tile[tx][k]));
+        }
+    }
+}
+
 }  // namespace mak

@@ -11,6 +11,7 @@
 #include <cooperative_groups.h>
 #include <type_traits>
 #include "qr.cuh"
+#include "projections.cuh"
 #include "gemm.cuh"
 
 namespace cg = cooperative_groups;
@@ -720,6 +721,11 @@ size_t sy2sb_worksize_t(makb200_handle* h, int n, int b) {
     sy2sb_carve<T>(h, ar, n, b, &w);
     return ar.off + 256;
 }
+static bool sy2sb_lower() {
+    const char* e = getenv("MAKB200_SY2SB_LOWER");   // read per call: the bring-up runs toggle it
+    return e && e[0] == '1';
+}
+
 template <typename T>
 int sy2sb_t(makb200_handle* h, int n, int b, T* A, int lda, T* tau1, void* work, size_t lwork) {
     if (n <= 0) return 0;
@@ -757,8 +763,23 @@ int sy2sb_t(makb200_handle* h, int n, int b, T* A, int lda, T* tau1, void* work,
         MAK_GEMM(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_N, mp, kb, kb, mk<T>(-0.5), V, mp, w.M2, b, one_, PB1, mp,
                  nullptr, 0);
         // A22 -= [V W] [W V]^H
-        MAK_GEMM(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, mp, mp, 2 * kb, mone, PB0, mp, PB1, mp, one_, A22, lda,
-                 nullptr, 0);
+        if (sy2sb_lower()) {
+            // opt-in (MAKB200_SY2SB_LOWER=1, round-2 bring-up): only the tiles on and below the diagonal (half the
+            // flops of the rank-2b update), then upper <- conj(lower) so that the next Y = A22 V still sees the
+            // full Hermitian matrix (one n^2 pass per panel: ~3 % of the update's time at n = 8192)
+            {
+                cudaError_t e_ = gemm<T>(s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, mp, mp, 2 * kb, mone, PB0, mp, PB1, mp,
+                                         one_, A22, lda, nullptr, 0, true);
+                if (e_ != cudaSuccess) return cuda_fail(h, e_, "gemm");
+            }
+            const int nbt = (mp + 31) / 32;
+            mirror_lower_kernel<T><<<dim3(nbt, nbt), dim3(32, 8), 0, s>>>(mp, A22, lda);
+            count_launch();
+            MAK_LAUNCH_CHECK(h, "mirror_lower_kernel");
+        } else {
+            MAK_GEMM(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, mp, mp, 2 * kb, mone, PB0, mp, PB1, mp, one_, A22, lda,
+                     nullptr, 0);
+        }
     }
     return 0;
 }

@@ -195,3 +195,11 @@ extern "C" int emu_fro2(int dt, int m, int n, const void* A, int lda, double* ou
     else emu::launch(mak::fro2_atomic_kernel<cplx>, dim3(grid), dim3(256), 0, m, n, (const cplx*)A, lda, out1);
     return 0;
 }
+
+extern "C" int emu_mirror_lower(int dt, int n, void* A, int lda, int order, uint64_t seed) {
+    emu::set_order(order, seed);
+    const int nb = (n + 31) / 32;
+    if (dt == 0) emu::launch(mak::mirror_lower_kernel<double>, dim3(nb, nb), dim3(32, 8), 0, n, (double*)A, lda);
+    else emu::launch(mak::mirror_lower_kernel<cplx>, dim3(nb, nb), dim3(32, 8), 0, n, (cplx*)A, lda);
+    return 0;
+}

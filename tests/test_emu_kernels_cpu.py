@@ -379,3 +379,17 @@ def test_emu_fro2(lib, m, n, pad, grid, dtype):
     out = np.zeros(1)
     lib.emu_fro2(dt, m, n, _vp(buf), m + pad, _vp(out), grid, 2, ctypes.c_uint64(3))
     assert np.isclose(out[0], np.linalg.norm(A0) ** 2, rtol=1e-13)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("n,pad", [(1, 0), (31, 2), (32, 0), (33, 1), (100, 0)])
+def test_emu_mirror_lower(lib, n, pad, dtype):
+    dt = 0 if dtype == "f64" else 1
+    G = O.randn_matrix(n, n, dtype, seed=n)
+    L = np.tril(G, -1)
+    want = L + L.conj().T + np.diag(np.diag(G).real)
+    for order, seed in ORDERS:
+        buf = np.full((n + pad, n), 3.0, dtype=G.dtype, order="F")
+        buf[:n] = G
+        lib.emu_mirror_lower(dt, n, _vp(buf), n + pad, order, ctypes.c_uint64(seed))
+        assert np.array_equal(buf[:n], want) and np.all(buf[n:] == 3.0)

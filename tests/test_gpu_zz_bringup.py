@@ -201,3 +201,23 @@ def test_panel_blocked_warp_qr(dtype):
         assert np.all(np.tril(Rn, -1) == 0) and np.all(np.real(np.diag(Rn)) >= 0)
         assert np.linalg.norm(Rn - Ro) <= 200 * tol * np.linalg.norm(Ro) and np.linalg.norm(Qn - Qo) <= 200 * tol * np.sqrt(min(m, n))
         assert np.linalg.norm(Qn - makb200.to_numpy(Q0)) <= 200 * tol * np.sqrt(min(m, n))
+
+
+def test_two_stage_eigh_with_lower_triangle_stage1():
+    """MAKB200_SY2SB_LOWER=1: the dense -> band reduction updates only the tiles on/below the diagonal and mirrors
+    them (csrc/projections.cuh: mirror_lower_kernel); band eigenvalues and the assembled two-stage eigh_full!."""
+    import subprocess
+    import sys
+    import json
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("_twostage", os.path.join(here, "test_gpu_twostage.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    env = dict(os.environ, MAKB200_EIGH_TWOSTAGE="16", MAKB200_SY2SB_LOWER="1")
+    p = subprocess.run([sys.executable, "-c", mod.SCRIPT % mod.ROOT], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    for r in json.loads(line[len("RESULT "):]):
+        tol = 10 * r["n"] * EPS
+        assert r["band"] <= tol and r["vals"] <= tol and r["resid"] <= tol * r["n"] ** 0.5 and r["orth"] <= tol * r["n"] ** 0.5, r
