@@ -721,6 +721,10 @@ size_t sy2sb_worksize_t(makb200_handle* h, int n, int b) {
     sy2sb_carve<T>(h, ar, n, b, &w);
     return ar.off + 256;
 }
+static bool sy2sb_lookahead() {
+    const char* e = getenv("MAKB200_SY2SB_LOOKAHEAD");   // read per call: the bring-up runs toggle it
+    return e && e[0] == '1';
+}
 static bool sy2sb_lower() {
     const char* e = getenv("MAKB200_SY2SB_LOWER");   // read per call: the bring-up runs toggle it
     return e && e[0] == '1';
@@ -741,11 +745,24 @@ int sy2sb_t(makb200_handle* h, int n, int b, T* A, int lda, T* tau1, void* work,
     const bool la_save = h->no_lookahead;
     h->no_lookahead = true;   // single-block panels: keep everything on the caller's stream
     struct Restore { makb200_handle* h; bool v; ~Restore() { h->no_lookahead = v; } } restore{h, la_save};
+    // opt-in (MAKB200_SY2SB_LOOKAHEAD=1, round-2 bring-up): the next panel's columns are updated first and its QR
+    // runs on the high-priority auxiliary stream while the bulk of the rank-2b update drains on the caller's stream
+    // (the panel chain is ~25 % of the stage at n = 8192: 128 panels x 64 columns of cluster-barrier latency)
+    const bool lookahead = sy2sb_lookahead() && !la_save;   // the auxiliary stream is shared: not inside a pooled call
+    const bool lower = sy2sb_lower();
+    cudaStream_t sMain = s, sAux = h->aux_stream;
+    bool panel_ready = false;   // the QR of the current panel was already done (on sAux) by the previous iteration
     for (int j0 = 0; j0 + b < n; j0 += b) {
         const int mp = n - j0 - b, kb = mp < b ? mp : b;
         T* P = A + (size_t)j0 * lda + (j0 + b);
-        int rc = geqrf_blocked<T>(h, mp, b, P, lda, w.qr);       // V -> qr.Vw (mp x kb, ld mp), T -> qr.Tall (ld nb)
-        if (rc) return rc;
+        int rc = 0;
+        if (!panel_ready) {
+            rc = geqrf_blocked<T>(h, mp, b, P, lda, w.qr);       // V -> qr.Vw (mp x kb, ld mp), T -> qr.Tall (ld nb)
+            if (rc) return rc;
+        } else {
+            MAK_CUDA(h, cudaStreamWaitEvent(sMain, h->ev[7], 0));   // join the look-ahead panel
+        }
+        panel_ready = false;
         MAK_CUDA(h, cudaMemcpyAsync(tau1 + j0, w.qr.tau, sizeof(T) * kb, cudaMemcpyDeviceToDevice, s));
         const T* V = w.qr.Vw;
         const T* Tm = w.qr.Tall;
@@ -763,24 +780,46 @@ int sy2sb_t(makb200_handle* h, int n, int b, T* A, int lda, T* tau1, void* work,
         MAK_GEMM(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_N, mp, kb, kb, mk<T>(-0.5), V, mp, w.M2, b, one_, PB1, mp,
                  nullptr, 0);
         // A22 -= [V W] [W V]^H
-        if (sy2sb_lower()) {
-            // opt-in (MAKB200_SY2SB_LOWER=1, round-2 bring-up): only the tiles on and below the diagonal (half the
-            // flops of the rank-2b update), then upper <- conj(lower) so that the next Y = A22 V still sees the
-            // full Hermitian matrix (one n^2 pass per panel: ~3 % of the update's time at n = 8192)
-            {
-                cudaError_t e_ = gemm<T>(s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, mp, mp, 2 * kb, mone, PB0, mp, PB1, mp,
-                                         one_, A22, lda, nullptr, 0, true);
-                if (e_ != cudaSuccess) return cuda_fail(h, e_, "gemm");
-            }
-            const int nbt = (mp + 31) / 32;
-            mirror_lower_kernel<T><<<dim3(nbt, nbt), dim3(32, 8), 0, s>>>(mp, A22, lda);
+        const int j1 = j0 + b;
+        const bool next = lookahead && (j1 + b < n) && mp > b;
+        // columns [c_lo, mp) of A22 are updated by the bulk product below; with look-ahead the first b columns
+        // (the next panel and its band block) go first, on their own
+        int c_lo = 0;
+        if (next) {
+            MAK_GEMM(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, mp, b, 2 * kb, mone, PB0, mp, PB1, mp, one_, A22, lda,
+                     nullptr, 0);
+            MAK_CUDA(h, cudaEventRecord(h->ev[6], sMain));
+            MAK_CUDA(h, cudaStreamWaitEvent(sAux, h->ev[6], 0));
+            h->stream = sAux;
+            rc = geqrf_blocked<T>(h, n - j1 - b, b, A + (size_t)j1 * lda + (j1 + b), lda, w.qr);
+            h->stream = sMain;
+            if (rc) return rc;
+            MAK_CUDA(h, cudaEventRecord(h->ev[7], sAux));
+            panel_ready = true;
+            c_lo = b;
+        }
+        const int nc = mp - c_lo;
+        if (nc <= 0) continue;
+        if (lower) {
+            // opt-in (MAKB200_SY2SB_LOWER=1): only the tiles on and below the diagonal of the square block
+            // A22[c_lo:, c_lo:] (half the flops of the rank-2b update), then upper <- conj(lower) so that the next
+            // Y = A22 V still sees the full Hermitian matrix (one pass per panel: ~3 % of the update at n = 8192).
+            // Without look-ahead c_lo = 0 and the block is all of A22; with it the strip A22[0:b, b:] above the
+            // block is the mirror of the next panel's columns, which nothing reads again.
+            T* C = A22 + (size_t)c_lo * lda + c_lo;
+            cudaError_t e_ = gemm<T>(s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, nc, nc, 2 * kb, mone, PB0 + c_lo, mp,
+                                     PB1 + c_lo, mp, one_, C, lda, nullptr, 0, true);
+            if (e_ != cudaSuccess) return cuda_fail(h, e_, "gemm");
+            const int nbt = (nc + 31) / 32;
+            mirror_lower_kernel<T><<<dim3(nbt, nbt), dim3(32, 8), 0, s>>>(nc, C, lda);
             count_launch();
             MAK_LAUNCH_CHECK(h, "mirror_lower_kernel");
         } else {
-            MAK_GEMM(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, mp, mp, 2 * kb, mone, PB0, mp, PB1, mp, one_, A22, lda,
-                     nullptr, 0);
+            MAK_GEMM(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, mp, nc, 2 * kb, mone, PB0, mp, PB1 + c_lo, mp, one_,
+                     A22 + (size_t)c_lo * lda, lda, nullptr, 0);
         }
     }
+    if (panel_ready) MAK_CUDA(h, cudaStreamWaitEvent(sMain, h->ev[7], 0));
     return 0;
 }
 

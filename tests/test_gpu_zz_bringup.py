@@ -221,3 +221,24 @@ def test_two_stage_eigh_with_lower_triangle_stage1():
     for r in json.loads(line[len("RESULT "):]):
         tol = 10 * r["n"] * EPS
         assert r["band"] <= tol and r["vals"] <= tol and r["resid"] <= tol * r["n"] ** 0.5 and r["orth"] <= tol * r["n"] ** 0.5, r
+
+
+@pytest.mark.parametrize("extra", [{"MAKB200_SY2SB_LOOKAHEAD": "1"}, {"MAKB200_SY2SB_LOOKAHEAD": "1", "MAKB200_SY2SB_LOWER": "1"}])
+def test_two_stage_eigh_with_stage1_lookahead(extra):
+    """MAKB200_SY2SB_LOOKAHEAD=1: the next panel's QR runs on the auxiliary stream while the bulk rank-2b update
+    drains (alone and together with the lower-triangle update)."""
+    import subprocess
+    import sys
+    import json
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("_twostage", os.path.join(here, "test_gpu_twostage.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    env = dict(os.environ, MAKB200_EIGH_TWOSTAGE="16", **extra)
+    p = subprocess.run([sys.executable, "-c", mod.SCRIPT % mod.ROOT], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    for r in json.loads(line[len("RESULT "):]):
+        tol = 10 * r["n"] * EPS
+        assert r["band"] <= tol and r["vals"] <= tol and r["resid"] <= tol * r["n"] ** 0.5 and r["orth"] <= tol * r["n"] ** 0.5, r

@@ -12,7 +12,7 @@ timeout 900 python -m pytest tests/test_gpu_y_vals.py tests/test_gpu_y_trunc.py 
 echo "== timings: eigh_vals vs eigh_full, svd_vals vs svd_compact, svd_trunc r=1024 (8192 f64) =="
 timeout 600 python tools/vals_time.py 8192 1024
 echo "== (2) gated, no inter-CTA waits: panel-blocked warp QR, one-launch / single-CTA tridiagonalisation, lower-triangle stage 1 =="
-MAKB200_BRINGUP=1 timeout 900 python -m pytest tests/test_gpu_zz_bringup.py -q -k "panel_blocked or one_launch or single_launch or lower_triangle" 2>&1 | tail -8
+MAKB200_BRINGUP=1 timeout 900 python -m pytest tests/test_gpu_zz_bringup.py -q -k "panel_blocked or one_launch or single_launch or lower_triangle or stage1_lookahead" 2>&1 | tail -8
 echo "== (3) gated: fused Q2 slab kernel =="
 MAKB200_BRINGUP=1 timeout 600 python -m pytest tests/test_gpu_zz_bringup.py -q -k "fused_q2" 2>&1 | tail -8
 echo "== tiny-block QR (16-32 c128, x16 replicas): warp kernel vs panel-blocked warp kernel =="
@@ -34,11 +34,11 @@ timeout 300 python tools/sbr_time.py 8192 64 32
 MAKB200_CHASE_PERSISTENT=1 timeout 120 python tools/sbr_time.py 8192 64 32
 for g in 8 16 32 64; do echo "-- persistent, grid cap $g"; MAKB200_CHASE_PERSISTENT=1 MAKB200_CHASE_GRID=$g timeout 120 python tools/sbr_time.py 8192 64; done
 echo "== two-stage eigh 8192 f64: round-1 kernels / +persistent chase / +fused Q2 (g = 64, 32; cw = 64, 32) =="
-for cfg in "" "MAKB200_SY2SB_LOWER=1" "MAKB200_Q2_FUSED=1" "MAKB200_SY2SB_LOWER=1 MAKB200_Q2_FUSED=1" "MAKB200_CHASE_PERSISTENT=1" "MAKB200_CHASE_PERSISTENT=1 MAKB200_Q2_FUSED=1" \
+for cfg in "" "MAKB200_SY2SB_LOWER=1" "MAKB200_SY2SB_LOOKAHEAD=1" "MAKB200_SY2SB_LOWER=1 MAKB200_SY2SB_LOOKAHEAD=1" "MAKB200_Q2_FUSED=1" "MAKB200_SY2SB_LOWER=1 MAKB200_Q2_FUSED=1" "MAKB200_CHASE_PERSISTENT=1" "MAKB200_CHASE_PERSISTENT=1 MAKB200_Q2_FUSED=1" \
            "MAKB200_CHASE_PERSISTENT=1 MAKB200_Q2_FUSED=1 MAKB200_Q2_G=32" \
            "MAKB200_CHASE_PERSISTENT=1 MAKB200_Q2_FUSED=1 MAKB200_Q2_G=32 MAKB200_Q2_CW=32" \
-           "MAKB200_SY2SB_LOWER=1 MAKB200_CHASE_PERSISTENT=1 MAKB200_Q2_FUSED=1" \
-           "MAKB200_EIGH_TWOSTAGE=32 MAKB200_SY2SB_LOWER=1 MAKB200_CHASE_PERSISTENT=1 MAKB200_Q2_FUSED=1"; do
+           "MAKB200_SY2SB_LOWER=1 MAKB200_SY2SB_LOOKAHEAD=1 MAKB200_CHASE_PERSISTENT=1 MAKB200_Q2_FUSED=1" \
+           "MAKB200_EIGH_TWOSTAGE=32 MAKB200_SY2SB_LOWER=1 MAKB200_SY2SB_LOOKAHEAD=1 MAKB200_CHASE_PERSISTENT=1 MAKB200_Q2_FUSED=1"; do
   echo "-- $cfg"
   env MAKB200_EIGH_TWOSTAGE=64 MAKB200_PHASES=1 $cfg timeout 300 python tools/twostage_check.py 8192 2>&1 | tail -12
 done
