@@ -107,7 +107,7 @@ function left_polar!(A::AbstractMatrix, WP, alg::B200_QDWH)
     YAB200.polar_qdwh!(A, W, P; l0 = get(alg.kwargs, :l0, 0.0), maxiter = get(alg.kwargs, :maxiter, 12))
     # singular A: QDWH converges to a partial isometry (‖W‖_F² = rank); take the PolarViaSVD recipe (polar.jl:59-70)
     # on the rank-robust B200 SVD so that W is isometric for any input, as with LAPACK
-    YAB200.fro2(W) > size(A, 2) - 0.5 || return left_polar!(Ac, WP, MatrixAlgebraKit.PolarViaSVD(SVDViaPolar()))
+    abs(YAB200.fro2(W) - size(A, 2)) <= 1.0e-9 * size(A, 2) || return left_polar!(Ac, WP, MatrixAlgebraKit.PolarViaSVD(SVDViaPolar()))
     return W, P
 end
 

@@ -64,7 +64,7 @@ def left_polar_(A, WP=None, alg=None, **kw):
     rc = h.lib.makb200_fro2(h.h, dt, m, n, _core.ptr(W), _core.ld(W), _core.ptr(fro2))
     h.check(rc, "makb200_fro2")
     w2 = float(fro2.item())            # ||W||_F^2 = n for an isometry, = rank(A) for a partial isometry
-    if not (w2 > n - 0.5):
+    if not (abs(w2 - n) <= 1e-9 * n):  # also catches directions QDWH has not fully converged on (and NaN)
         from .algorithms import SVDViaPolar
         return _left_polar_via_svd_(A_keep, W, P, Algorithm("PolarViaSVD", {"svd_alg": SVDViaPolar()}))
     return W, P
