@@ -12,6 +12,7 @@
 #include "eigh.cuh"
 #include "gemm.cuh"
 #include "qr.cuh"
+#include "projections.cuh"
 #include <vector>
 #include <cmath>
 
@@ -695,24 +696,6 @@ __global__ void svd_reorder_kernel(int n, int k, const double* __restrict__ w, c
     if (bi == 0 && ty == 0) {
         int j = bj * 32 + tx;
         if (j < n) { double v = w[n - 1 - j]; S[j] = v > 0.0 ? v : 0.0; }
-    }
-}
-
-// out[0] = max_j | ||U(:, j)||^2 - 1 |  (one warp per column; non-negative doubles order like their bit patterns).
-// For a full-rank A the left factor U = W V is isometric to rounding; for a rank-deficient A the QDWH polar
-// factor W is only a partial isometry and the columns of U that belong to zero singular values collapse.
-template <typename T>
-__global__ void col_norm_defect_kernel(int m, int ncols, const T* __restrict__ U, int ldu, double* out) {
-    const int lane = threadIdx.x & 31, j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (j >= ncols) return;
-    const T* u = U + (size_t)j * ldu;
-    double s = 0.0;
-    for (int r = lane; r < m; r += 32) s += abs2_(u[r]);
-    s = warp_sum(s);
-    if (lane == 0) {
-        double dft = fabs(s - 1.0);
-        if (!(dft == dft)) dft = 1e300;   // NaN counts as a defect
-        atomicMax((unsigned long long*)out, (unsigned long long)__double_as_longlong(dft));
     }
 }
 

@@ -203,3 +203,11 @@ extern "C" int emu_mirror_lower(int dt, int n, void* A, int lda, int order, uint
     else emu::launch(mak::mirror_lower_kernel<cplx>, dim3(nb, nb), dim3(32, 8), 0, n, (cplx*)A, lda);
     return 0;
 }
+
+extern "C" int emu_col_norm_defect(int dt, int m, int ncols, const void* U, int ldu, double* out, int order, uint64_t seed) {
+    emu::set_order(order, seed);
+    out[0] = 0.0;
+    if (dt == 0) emu::launch(mak::col_norm_defect_kernel<double>, dim3((ncols + 7) / 8), dim3(256), 0, m, ncols, (const double*)U, ldu, out);
+    else emu::launch(mak::col_norm_defect_kernel<cplx>, dim3((ncols + 7) / 8), dim3(256), 0, m, ncols, (const cplx*)U, ldu, out);
+    return 0;
+}

@@ -393,3 +393,25 @@ def test_emu_mirror_lower(lib, n, pad, dtype):
         buf[:n] = G
         lib.emu_mirror_lower(dt, n, _vp(buf), n + pad, order, ctypes.c_uint64(seed))
         assert np.array_equal(buf[:n], want) and np.all(buf[n:] == 3.0)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_emu_col_norm_defect(lib, dtype):
+    """The check that triggers the re-orthonormalisation of U for rank-deficient input (polar.cu: svd_tall)."""
+    dt = 0 if dtype == "f64" else 1
+    Q, _ = np.linalg.qr(O.randn_matrix(70, 19, dtype, seed=1))
+    out = np.zeros(1)
+    for order, seed in ORDERS:
+        U = np.asfortranarray(Q)
+        lib.emu_col_norm_defect(dt, 70, 19, _vp(U), 70, _vp(out), order, ctypes.c_uint64(seed))
+        assert out[0] <= 1e-14
+        U = np.asfortranarray(Q.copy())
+        U[:, 11] *= 0.5                                   # a collapsed column: ||u||^2 = 0.25
+        lib.emu_col_norm_defect(dt, 70, 19, _vp(U), 70, _vp(out), order, ctypes.c_uint64(seed))
+        assert abs(out[0] - 0.75) <= 1e-14
+        U[:, 3] = 0.0
+        lib.emu_col_norm_defect(dt, 70, 19, _vp(U), 70, _vp(out), order, ctypes.c_uint64(seed))
+        assert out[0] == 1.0
+        U[5, 7] = np.nan
+        lib.emu_col_norm_defect(dt, 70, 19, _vp(U), 70, _vp(out), order, ctypes.c_uint64(seed))
+        assert out[0] == 1e300
