@@ -1162,7 +1162,7 @@ int eigh_t(makb200_handle* h, int n, T* A, int lda, double* W, T* V, int ldv, in
     double* Zreal;
     void* sub;
     size_t sb;
-    TwoStageWork<T> ts;
+    TwoStageWork<T> ts{};
     eigh_carve<T>(h, ar, n, &x, &Zreal, &sub, &sb, &ts);
     if (!ar.ok) return MAKB200_ERR_WORKSPACE;
     x.A = A;
