@@ -10,8 +10,14 @@ it) on an 8192 x 8192 Float64 matrix.  A "step" is one pass of the hot path over
 matrix (i.i.d. N(0,1), Hermitian part for eigh).  `value` = algorithmic GFLOP/s
 (F_eigh_full = 10 n^3/3, F_svd_compact = 20 n^3/3) with the input resident in HBM; `e2e` = the
 same through the public operator with HOST buffers (pinned H2D of A and D2H of all outputs inside
-the timed region).  N>1: the configuration does not shard (SURVEY §8e "replicas only"), every rank
-factorizes its own matrix; value = aggregate.
+the timed region).  After the timed region the LAST step's outputs are checked on the device (residual,
+orthogonality, trace identities) and the figures go into the JSON line (`parity`).
+
+N>1 (`--workload auto`): configs[1] does not shard (SURVEY 8e "replicas only"), so the multi-GPU line measures the
+config that does: BASELINE configs[3], TSQR `qr_compact!` of a 16 777 216 x 256 Float64 matrix row-sharded over
+the N ranks (STRONG scaling; one C-ABI call `makb200_tsqr(h, ncclComm_t, ...)` per step: local CholeskyQR2, binary
+tree over NCCL on the R factors, tree factors folded into the last solve).  `--workload tsqr --gpus 1` runs the
+same matrix on one GPU (the strong-scaling base); `--workload c2` forces per-rank replicas of configs[1].
 """
 import argparse
 import json
@@ -112,9 +118,19 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------
 # reference arm: the oracle (LAPACK replay of the reference's call sequence) on host cores
 # --------------------------------------------------------------------------------------
+def blas_all_cores():
+    """torchrun exports OMP_NUM_THREADS=1: give the BLAS behind scipy every host core explicitly."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+
+
 def cpu_sample(ops, n_cpu, reps=1):
     """time the oracle on a bounded sample; returns (GFLOP/s, seconds, description)."""
     from oracle import mak_oracle as O
+    blas_all_cores()
     tot_f, tot_t = 0.0, 0.0
     for op in ops:
         if op == "eigh":
@@ -134,6 +150,23 @@ def cpu_sample(ops, n_cpu, reps=1):
     return tot_f / tot_t / 1e9, tot_t, f"{'+'.join(ops)} {n_cpu}x{n_cpu} f64 x{reps} (LAPACK via scipy/OpenBLAS)"
 
 
+def tsqr_flops(m, n):
+    return 4.0 * m * n * n - 4.0 * n ** 3 / 3.0
+
+
+def cpu_sample_tsqr(m_cpu, n, m_full):
+    """oracle qr_compact (geqrt(36) + gemqrt on I) of an m_cpu x n row sample; GFLOP/s is per-row work, so the
+    figure transfers linearly in m (the full 16.7M x 256 needs 69 GB and > 2^31 elements under LP64)."""
+    from oracle import mak_oracle as O
+    blas_all_cores()
+    A = O.randn_matrix(m_cpu, n, "f64", seed=5)
+    t0 = time.perf_counter()
+    O.qr_compact(A)
+    t = time.perf_counter() - t0
+    return tsqr_flops(m_cpu, n) / t / 1e9, t, (f"qr_compact {m_cpu}x{n} f64 x1 (LAPACK geqrt+gemqrt via scipy/OpenBLAS); "
+                                               f"extrapolated linearly in m to {m_full} rows")
+
+
 def threads_info():
     try:
         from threadpoolctl import threadpool_info
@@ -145,26 +178,46 @@ def threads_info():
     return os.cpu_count() or 1
 
 
+def pick_workload(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload != "auto":
+        return args.workload
+    return "c2" if max(world, args.gpus) == 1 else "tsqr"
+
+
 def run_reference(args):
+    """The reference's CPU path (LAPACK replay = oracle, kind "port": Julia cannot run here) on ALL host cores.
+    c2: ONE repetition at the bench's own n (8192: about 1.5 min) whatever --steps says - a smaller n would not be
+    the same config; tsqr: a 2 097 152-row sample, linear in m."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ops = args.ops.split(",")
-    n_cpu = args.cpu_n
-    for _ in range(args.warmup if args.warmup < 2 else 1):
+    wl = pick_workload(args)
+    blas_all_cores()
+    if wl == "tsqr":
+        m_cpu = min(args.tsqr_rows, 1 << 21)
+        cpu_sample_tsqr(1 << 16, args.tsqr_cols, args.tsqr_rows)
+        v, secs, desc = cpu_sample_tsqr(m_cpu, args.tsqr_cols, args.tsqr_rows)
+        ms_step = secs * 1e3 * args.tsqr_rows / m_cpu
+        workload = (f"tsqr qr_compact! {args.tsqr_rows}x{args.tsqr_cols} Float64 (BASELINE configs[3]); reference step = "
+                    f"{m_cpu}-row sample, ms_per_step extrapolated linearly in m")
+        steps_done, scaling = 1, "strong"
+    else:
+        ops = args.ops.split(",")
+        n_cpu = args.cpu_n if args.cpu_n > 0 else args.n
         cpu_sample(ops, min(n_cpu, 1024))
-    vals, secs = [], []
-    for _ in range(args.steps):
-        g, s, desc = cpu_sample(ops, n_cpu)
-        vals.append(g); secs.append(s)
-    v = float(np.sum([flops(o, n_cpu) for o in ops]) * len(vals) / np.sum(secs) / 1e9)
+        v, secs, desc = cpu_sample(ops, n_cpu)
+        ms_step = secs * 1e3
+        extra = "" if n_cpu == args.n else f"; bounded sample n={n_cpu}, GFLOP/s extrapolated (flops ~ n^3)"
+        workload = (f"{'+'.join(o + ('_full!' if o == 'eigh' else '_compact!') for o in ops)} {args.n}x{args.n} Float64 "
+                    f"(BASELINE configs[1]); ONE repetition at n={n_cpu} independent of --steps{extra}")
+        steps_done, scaling = 1, "weak"
     cores = threads_info()
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "GFLOP/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs) * 1e3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{'+'.join(ops)}_full n={args.n} f64 (BASELINE configs[1]); reference step = bounded "
-                               f"sample n={n_cpu}, GFLOP/s is size-normalised"},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms_step),
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "repetitions_timed": steps_done, "host_cores": os.cpu_count()},
         "cpu_baseline": {"value": v, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": v, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -176,6 +229,12 @@ def run_reference(args):
 # our arm
 # --------------------------------------------------------------------------------------
 def run_ours(args):
+    if pick_workload(args) == "tsqr":
+        return run_tsqr(args)
+    return run_c2(args)
+
+
+def run_c2(args):
     import ctypes
     import torch
     import torch.distributed as dist
@@ -281,7 +340,7 @@ def run_ours(args):
     def e2e_fn():
         a, b = step_e2e()
         bytes_io[0], bytes_io[1] = a, b
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, args.steps)
     ms_e2e = timed(e2e_fn, e2e_steps)
     e2e_value = world * step_flops * e2e_steps / (ms_e2e * 1e-3) / 1e9
 
@@ -341,6 +400,41 @@ def run_ours(args):
     if roofline and len(cands) > 1:
         roofline["second_kernel"] = cands[1]
 
+    # ---- output check of the LAST step, on the device (torch ops are the checker here, not the product) ----
+    parity = {"tolerance_10_n_eps": 10 * n * 2.220446049250313e-16}
+    with torch.no_grad():
+        eye = torch.eye(n, dtype=torch.float64, device=dev)
+        if "eigh" in ops:
+            D, V = outs["eigh"]
+            w = D if D.dim() == 1 else torch.diagonal(D)
+            H = dev_in["eigh"]
+            nh = float(torch.linalg.matrix_norm(H))
+            parity["eigh"] = {
+                "resid_AV_VD_over_A": float(torch.linalg.matrix_norm(H @ V - V * w)) / nh,
+                "orth_VhV_I": float(torch.linalg.matrix_norm(V.t() @ V - eye)),
+                "trace_err": abs(float(w.sum() - torch.diagonal(H).sum())) / nh,
+                "sum_lambda2_vs_fro2": abs(float((w * w).sum()) - nh * nh) / (nh * nh),
+                "ascending": bool((w[1:] >= w[:-1]).all()),
+            }
+        if "svd" in ops:
+            U, S, Vh = outs["svd"]
+            G = dev_in["svd"]
+            ng = float(torch.linalg.matrix_norm(G))
+            res = float(torch.linalg.matrix_norm(G - (U * S) @ Vh)) / ng
+            ou = float(torch.linalg.matrix_norm(U.t() @ U - eye))
+            ov = float(torch.linalg.matrix_norm(Vh @ Vh.t() - eye))
+            parity["svd"] = {
+                "resid_A_USVh_over_A": res, "orth_UhU_I": ou, "orth_VhVhh_I": ov,
+                "sum_sigma2_vs_fro2": abs(float((S * S).sum()) - ng * ng) / (ng * ng),
+                "descending_nonneg": bool((S[1:] <= S[:-1]).all() and (S >= 0).all()),
+                # Weyl: a factorization with this residual and orthogonality has |sigma - sigma_exact| <= bound * sigma_1
+                "sigma_err_bound_over_sigma1": res * ng / float(S[0]) + ou + ov,
+            }
+        del eye
+    parity["ok"] = all(v2 <= parity["tolerance_10_n_eps"] for k in ("eigh", "svd") if k in parity
+                       for k2, v2 in parity[k].items() if k2.startswith(("resid", "orth")))
+    parity["oracle_comparison"] = "tests/test_gpu_x_config_size.py compares sigma/lambda with the LAPACK oracle at n = 2048/4096"
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -348,7 +442,10 @@ def run_ours(args):
     # CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
     if world == 1 and not args.no_cpu:
-        g, s, desc = cpu_sample(ops, args.cpu_n)
+        n_cpu = args.cpu_n if args.cpu_n > 0 else min(n, 4096)
+        g, s, desc = cpu_sample(ops, n_cpu)
+        if n_cpu != n:
+            desc += f"; GFLOP/s extrapolated to n={n} (flops ~ n^3)"
         cpu = {"value": g, "unit": "GFLOP/s", "cores": threads_info(), "kind": "port", "sample": desc, "seconds": s}
     line = {
         "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
@@ -360,7 +457,191 @@ def run_ours(args):
                    "factorizations_per_s": world * len(ops) * args.steps / (ms * 1e-3)},
         "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": bytes_io[0],
                 "d2h_bytes_per_step": bytes_io[1], "ms_per_step": ms_e2e / e2e_steps},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_tsqr(args):
+    """BASELINE configs[3]: qr_compact! of a 16 777 216 x 256 Float64 matrix row-sharded over the ranks (strong scaling)."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    import makb200
+    from makb200 import tsqr as T
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = makb200._lib.load()
+    M, n = args.tsqr_rows, args.tsqr_cols
+    rows = [M // world + (1 if r < M % world else 0) for r in range(world)]
+    m_loc = rows[rank]
+    # synthetic shard, generated on the device with Philox, seed 5 + rank (SURVEY 8d)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5 + rank)
+    A_src = torch.randn((n, m_loc), dtype=torch.float64, device=dev, generator=g).t()
+    A = makb200.colmajor_empty(m_loc, n, torch.float64, dev)
+    Q = makb200.colmajor_empty(m_loc, n, torch.float64, dev)
+    R = makb200.colmajor_empty(n, n, torch.float64, dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    h = makb200.Handle.get(dev)
+    comm = T.nccl_comm(None, dev) if world > 1 else ctypes.c_void_p(0)
+    lw = lib.makb200_tsqr_worksize(h.h, 0, m_loc, n, world)
+    work = torch.empty(max(int(lw), 1), dtype=torch.uint8, device=dev)
+
+    def call():
+        h2 = makb200.Handle.get(dev)
+        rc = lib.makb200_tsqr(h2.h, comm, 0, m_loc, n, A.data_ptr(), m_loc, Q.data_ptr(), m_loc, R.data_ptr(), n,
+                              work.data_ptr(), work.numel(), info.data_ptr())
+        h2.check(rc, "makb200_tsqr")
+
+    def step_dev():
+        A.copy_(A_src)   # the factorization overwrites A: refresh from the resident copy (counted)
+        call()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    nwarm = max(args.warmup, 3)
+    for _ in range(nwarm):
+        step_dev()
+    torch.cuda.synchronize()
+    if int(info.item()) != 0:
+        raise RuntimeError("makb200_tsqr reported a Cholesky breakdown on the synthetic shard")
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.makb200_launch_count()
+    ms = timed(step_dev, args.steps)
+    launches = int(lib.makb200_launch_count() - l0)
+    clocks = sampler.stop() if rank == 0 else None
+    fl = tsqr_flops(M, n)
+    value = fl * args.steps / (ms * 1e-3) / 1e9
+    ms_copy = timed(lambda: A.copy_(A_src), args.steps) / args.steps
+
+    # ---- roofline of the dominant kernel: the DMMA GEMM (Gram products and triangular solves), one instrumented step
+    lib.makb200_kernel_timing(1)
+    step_dev()
+    torch.cuda.synchronize()
+    gms, gl = ctypes.c_double(), ctypes.c_int()
+    lib.makb200_kernel_time(1, ctypes.byref(gms), ctypes.byref(gl))
+    gflops = float(lib.makb200_gemm_flops())
+    lib.makb200_kernel_timing(0)
+    step_ms = ms / args.steps
+    pk = fp64_peak()
+    ach = gflops / (gms.value * 1e-3) / 1e12 if gms.value > 0 else 0.0
+    roofline = {"kernel": "gemm_kernel<double> (DMMA m8n8k4)", "bound": "tensor", "achieved": ach, "peak": pk[0],
+                "unit": "TFLOP/s", "frac": ach / pk[0], "traffic": None, "launches_per_step": gl.value,
+                "avg_launch_ms": gms.value / max(gl.value, 1), "alg_flops_per_launch": gflops / max(gl.value, 1),
+                "kernel_share_of_step": gms.value / step_ms, "peak_source": pk[1],
+                "note": "flops = executed DMMA tiles of this rank's launches (lower-mode launches count executed tiles only)"}
+
+    # ---- parity of the last step on the device: residual on a row sample, global orthogonality, R^H R = A^H A ----
+    with torch.no_grad():
+        idx = torch.randint(0, m_loc, (min(m_loc, 65536),), device=dev)
+        num = torch.linalg.matrix_norm(A_src[idx] - Q[idx] @ R) ** 2
+        den = torch.linalg.matrix_norm(A_src[idx]) ** 2
+        Gq = torch.zeros((n, n), dtype=torch.float64, device=dev)
+        Ga = torch.zeros((n, n), dtype=torch.float64, device=dev)
+        for r0 in range(0, m_loc, 1 << 20):
+            qs, as_ = Q[r0:r0 + (1 << 20)], A_src[r0:r0 + (1 << 20)]
+            Gq += qs.t() @ qs
+            Ga += as_.t() @ as_
+        red = torch.stack([num, den])
+        if world > 1:
+            dist.all_reduce(red)
+            dist.all_reduce(Gq)
+            dist.all_reduce(Ga)
+        tolp = 10 * M * 2.220446049250313e-16
+        parity = {
+            "tolerance_10_n_eps": tolp,
+            "resid_A_QR_over_A_row_sample": float(torch.sqrt(red[0] / red[1])),
+            "orth_QhQ_I_global": float(torch.linalg.matrix_norm(Gq - torch.eye(n, dtype=torch.float64, device=dev))),
+            "gram_identity_RhR_vs_AhA": float(torch.linalg.matrix_norm(R.t() @ R - Ga) / torch.linalg.matrix_norm(Ga)),
+            "diagR_positive_upper": bool((torch.diagonal(R) > 0).all() and float(torch.tril(R, -1).abs().max()) == 0.0),
+            "oracle_comparison": "tests/test_gpu_tsqr_multi.py (torchrun) compares Q_p and R with the LAPACK oracle of the concatenated matrix",
+        }
+        parity["ok"] = (parity["resid_A_QR_over_A_row_sample"] <= tolp and parity["orth_QhQ_I_global"] <= tolp
+                        and parity["diagR_positive_upper"])
+        del Gq, Ga
+
+    # ---- e2e: HOST shards in, HOST Q and R out, through the same C-ABI call.  Pinned staging of `chunk` rows is
+    # reused for every slab of the shard (bounded host memory), so the device sees a shard of repeated row slabs.
+    chunk = min(m_loc, 1 << 19)
+    hin = torch.empty((n, chunk), dtype=torch.float64).pin_memory()
+    hin.copy_(A_src[:chunk].t())
+    hq = torch.empty((n, chunk), dtype=torch.float64).pin_memory()
+    hr = torch.empty((n, n), dtype=torch.float64).pin_memory()
+    bytes_io = [0, 0]
+
+    def step_e2e():
+        h2d = d2h = 0
+        for r0 in range(0, m_loc, chunk):
+            c = min(chunk, m_loc - r0)
+            A[r0:r0 + c].t().copy_(hin[:, :c], non_blocking=True)
+            h2d += c * n * 8
+        call()
+        for r0 in range(0, m_loc, chunk):
+            c = min(chunk, m_loc - r0)
+            hq[:, :c].copy_(Q[r0:r0 + c].t(), non_blocking=True)
+            d2h += c * n * 8
+        hr.copy_(R.t(), non_blocking=True)
+        d2h += n * n * 8
+        bytes_io[0], bytes_io[1] = h2d, d2h
+    step_e2e()
+    e2e_steps = max(1, min(args.steps, 3))
+    ms_e2e = timed(step_e2e, e2e_steps)
+    e2e_value = fl * e2e_steps / (ms_e2e * 1e-3) / 1e9
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        gcpu, scpu, desc = cpu_sample_tsqr(min(M, 1 << 20), n, M)
+        cpu = {"value": gcpu, "unit": "GFLOP/s", "cores": threads_info(), "kind": "port", "sample": desc, "seconds": scpu}
+    api_from = None
+    line = {
+        "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": nwarm, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"tsqr qr_compact! {M}x{n} Float64 row-sharded over {world} rank(s) (BASELINE configs[3])",
+                   "rows_per_rank": rows[0], "flops_per_step": fl,
+                   "l2": f"inputs ({m_loc * n * 8 / 2**30:.1f} GiB per rank) larger than L2; A refreshed from a resident copy each step "
+                         f"({ms_copy:.2f} ms of the step)",
+                   "collective": ("binary tree over ranks: ncclSend/ncclRecv of one n x n R factor per round on the compute stream, "
+                                  "ncclBroadcast of R; own communicator from makb200_comm_create") if world > 1 else "none (1 rank)",
+                   "factorizations_per_s": args.steps / (ms * 1e-3),
+                   "hbm_floor_ms_per_rank": 16.0 * m_loc * n / (peaks()[0] * 1e9) * 1e3},
+        "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": bytes_io[0] * world,
+                "d2h_bytes_per_step": bytes_io[1] * world, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                "host_buffer": f"pinned staging of {chunk} rows reused per slab"},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
     }
     print(json.dumps(line))
     if world > 1:
@@ -375,7 +656,11 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--n", type=int, default=8192)
     ap.add_argument("--ops", default="eigh,svd")
-    ap.add_argument("--cpu-n", type=int, default=4096, help="size of the bounded CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=0, help="n of the CPU sample (0: reference arm = --n, cpu_baseline = min(n, 4096))")
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "tsqr"],
+                    help="auto: configs[1] (eigh+svd 8192^2) at 1 GPU, configs[3] (TSQR 16.7M x 256, strong scaling) at N > 1")
+    ap.add_argument("--tsqr-rows", type=int, default=16777216)
+    ap.add_argument("--tsqr-cols", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -32,7 +32,7 @@ typedef struct makb200_handle makb200_handle_t;
 enum { MAKB200_F64 = 0, MAKB200_C128 = 1 };
 enum { MAKB200_QR_COMPACT = 0, MAKB200_QR_FULL = 1 };
 enum { MAKB200_OP_N = 0, MAKB200_OP_T = 1, MAKB200_OP_C = 2 };
-enum { MAKB200_ERR_CUDA = 1000, MAKB200_ERR_WORKSPACE = 1001, MAKB200_ERR_NOCONV = 1002 };
+enum { MAKB200_ERR_CUDA = 1000, MAKB200_ERR_WORKSPACE = 1001, MAKB200_ERR_NOCONV = 1002, MAKB200_ERR_NCCL = 1003 };
 
 /* -- handle: plays the role of cuSOLVER.dense_handle() (yacusolver.jl:76) ------------ */
 int makb200_create(makb200_handle_t** h, int device);
@@ -203,6 +203,29 @@ int makb200_tsqr_local(makb200_handle_t* h, int dtype, int m, int n, void* A, in
 int makb200_tsqr_local_ex(makb200_handle_t* h, int dtype, int m, int n, void* A, int lda, void* Q,
                           int ldq, void* R, int ldr, int nshift, void* work, size_t lwork,
                           int* info_dev);
+
+/* -- multi-GPU TSQR: qr_compact! of a row-sharded tall-skinny matrix (BASELINE config 4) -------------
+ * New capability (SURVEY.md 8b "multi-GPU: tsqr(h, ncclComm_t, ...)", 8e).  One process per GPU; rank p
+ * passes its m_local x n shard (m_local may differ per rank, n <= sum of the m_local).  Result = the
+ * single-GPU qr_compact!(vcat(A_0, ..., A_{P-1})): Q_p (m_local x n) on rank p, the same R (n x n upper,
+ * diag(R) > 0: common/gauge.jl:16-25 is satisfied) on every rank.
+ *   local step     CholeskyQR2 on the DMMA GEMM (as makb200_tsqr_local; kappa(A) <~ 1e7, breakdown -> info_dev)
+ *   exchange step  binary tree over ranks on the n x n R factors: ncclSend/ncclRecv issued on the handle's
+ *                  stream (no host synchronisation), Householder QR of each stacked pair, the path product of
+ *                  the tree factors sent back down and folded into the last local triangular solve
+ *                  (Q_p = Q1_p (L2^-H T_p): no tall-matrix work beyond the single-GPU algorithm), ncclBroadcast of R.
+ * `nccl_comm` is an ncclComm_t (NCCL.jl: `comm.handle`; Python: makb200_comm_create below) whose rank
+ * order is the row order of the shards; NULL = single rank.  A is overwritten.  NCCL is resolved with
+ * dlopen("libnccl.so.2") at first use (the copy already mapped by the process wins; env MAKB200_NCCL_LIB
+ * overrides), so the single-GPU entry points have no NCCL dependency.
+ * makb200_nccl_unique_id / makb200_comm_create / _destroy: thin wrappers of ncclGetUniqueId /
+ * ncclCommInitRank / ncclCommDestroy for hosts without their own NCCL binding; id128: HOST, 128 bytes. */
+int makb200_nccl_unique_id(void* id128);
+int makb200_comm_create(void** nccl_comm, int nranks, int rank, const void* id128);
+int makb200_comm_destroy(void* nccl_comm);
+size_t makb200_tsqr_worksize(makb200_handle_t* h, int dtype, int m_local, int n, int nranks);
+int makb200_tsqr(makb200_handle_t* h, void* nccl_comm, int dtype, int m_local, int n, void* A, int lda,
+                 void* Q, int ldq, void* R, int ldr, void* work, size_t lwork, int* info_dev);
 
 /* -- batched svd_compact! of many small blocks -------------------------------------------------
  * New capability (reference: commented-out gesvdjBatched stubs yacusolver.jl:506-569).

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libmakb200.so")
 F64, C128 = 0, 1
 QR_COMPACT, QR_FULL = 0, 1
 OP_N, OP_T, OP_C = 0, 1, 2
-ERR_CUDA, ERR_WORKSPACE, ERR_NOCONV = 1000, 1001, 1002
+ERR_CUDA, ERR_WORKSPACE, ERR_NOCONV, ERR_NCCL = 1000, 1001, 1002, 1003
 
 _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
 _ip = C.POINTER(C.c_int)
@@ -72,6 +72,11 @@ SIGNATURES = {
     "makb200_trunc_select_batched_worksize": (_sz, [_vp, _i]),
     "makb200_trunc_select_batched": (_i, [_vp, _i, _ip, _vpp, _vp, _ip, _vp, _vp, _vp, _sz]),
     "makb200_adjoint": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i]),
+    "makb200_nccl_unique_id": (_i, [_vp]),
+    "makb200_comm_create": (_i, [C.POINTER(_vp), _i, _i, _vp]),
+    "makb200_comm_destroy": (_i, [_vp]),
+    "makb200_tsqr_worksize": (_sz, [_vp, _i, _i, _i, _i]),
+    "makb200_tsqr": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _sz, _vp]),
 }
 
 _lib = None

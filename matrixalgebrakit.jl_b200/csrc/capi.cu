@@ -9,6 +9,8 @@
 #include "polar.cuh"
 #include "sbr.cuh"
 #include "bhetrd.cuh"
+#include "nccl_dl.h"
+#include <dlfcn.h>
 #include <vector>
 #include <algorithm>
 #include <atomic>
@@ -803,6 +805,73 @@ int makb200_tsqr_local(makb200_handle_t* h, int dtype, int m, int n, void* A, in
     return rc == -11 ? -1 : (rc <= -12 ? rc + 1 : rc);
 }
 
+// ---- multi-GPU TSQR (NCCL resolved at run time) --------------------------------------------
+size_t makb200_tsqr_worksize(makb200_handle_t* h, int dtype, int m, int n, int nranks) {
+    if (!h || !dtype_ok(dtype) || m < 0 || n < 0 || nranks < 1) return 0;
+    return dtype == MAKB200_F64 ? mak::tsqr_worksize_t<double>(h, m, n, nranks) : mak::tsqr_worksize_t<cplx>(h, m, n, nranks);
+}
+
+int makb200_nccl_unique_id(void* id128) {
+    if (!id128) return -1;
+    const mak::NcclApi* api = mak::nccl_api();
+    if (!api) return MAKB200_ERR_NCCL;
+    ncclUniqueId id;
+    if (api->GetUniqueId(&id) != ncclSuccess) return MAKB200_ERR_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    return 0;
+}
+
+int makb200_comm_create(void** comm, int nranks, int rank, const void* id128) {
+    if (!comm) return -1;
+    if (nranks < 1) return -2;
+    if (rank < 0 || rank >= nranks) return -3;
+    if (!id128) return -4;
+    const mak::NcclApi* api = mak::nccl_api();
+    if (!api) return MAKB200_ERR_NCCL;
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclComm_t c = nullptr;
+    if (api->CommInitRank(&c, nranks, id, rank) != ncclSuccess) return MAKB200_ERR_NCCL;
+    *comm = (void*)c;
+    return 0;
+}
+
+int makb200_comm_destroy(void* comm) {
+    if (!comm) return -1;
+    const mak::NcclApi* api = mak::nccl_api();
+    if (!api) return MAKB200_ERR_NCCL;
+    return api->CommDestroy((ncclComm_t)comm) == ncclSuccess ? 0 : MAKB200_ERR_NCCL;
+}
+
+int makb200_tsqr(makb200_handle_t* h, void* comm, int dtype, int m, int n, void* A, int lda, void* Q, int ldq, void* R,
+                 int ldr, void* work, size_t lwork, int* info_dev) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -3;
+    if (m < 0) return -4;
+    if (n < 0) return -5;
+    if (lda < maxi(1, m)) return -7;
+    if (ldq < maxi(1, m)) return -9;
+    if (R && ldr > 0 && ldr < maxi(1, n)) return -11;
+    if (m > 0 && n > 0 && !A) return -6;
+    if (m > 0 && n > 0 && (!Q || Q == A)) return -8;
+    if (!comm && n > m) return -5;
+    const mak::NcclApi* api = nullptr;
+    if (comm) {
+        const char* why = nullptr;
+        api = mak::nccl_api(&why);
+        if (!api) {
+            snprintf(h->err, sizeof(h->err), "libnccl.so.2 not loadable: %s", why ? why : "?");
+            return MAKB200_ERR_NCCL;
+        }
+    }
+    if (dtype == MAKB200_F64)
+        return mak::tsqr_t<double>(h, api, (ncclComm_t)comm, m, n, (double*)A, lda, (double*)Q, ldq, (double*)R, ldr, work,
+                                   lwork, info_dev);
+    return mak::tsqr_t<cplx>(h, api, (ncclComm_t)comm, m, n, (cplx*)A, lda, (cplx*)Q, ldq, (cplx*)R, ldr, work, lwork,
+                             info_dev);
+}
+
 }  // extern "C"
 
 // ---- batched svd --------------------------------------------------------------------------
@@ -1099,3 +1168,44 @@ int makb200_sbr_apply_q2(makb200_handle_t* h, int dtype, int n, int b, int g, co
 }
 
 }  // extern "C"
+
+// ---- NCCL loader ---------------------------------------------------------------------------
+namespace mak {
+const NcclApi* nccl_api(const char** why) {
+    static NcclApi api;
+    static int state = 0;   // 0 untried, 1 ok, -1 failed
+    static char msg[256];
+    if (state == 0) {
+        void* lib = nullptr;
+        const char* from = nullptr;
+        const char* env = getenv("MAKB200_NCCL_LIB");
+        if (env && env[0]) { lib = dlopen(env, RTLD_NOW | RTLD_GLOBAL); from = env; }
+        if (!lib) { lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD); from = "libnccl.so.2 (already mapped by the process)"; }
+        if (!lib) { lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL); from = "libnccl.so.2 (library search path)"; }
+        bool ok = lib != nullptr;
+        if (!ok) { const char* e = dlerror(); snprintf(msg, sizeof(msg), "%s", e ? e : "dlopen failed"); }
+#define MAK_SYM(field, name)                                                             \
+        if (ok) {                                                                            \
+            *(void**)(&api.field) = dlsym(lib, name);                                        \
+            if (!api.field) { ok = false; snprintf(msg, sizeof(msg), "missing symbol %s", name); } \
+        }
+        MAK_SYM(GetUniqueId, "ncclGetUniqueId")
+        MAK_SYM(CommInitRank, "ncclCommInitRank")
+        MAK_SYM(CommDestroy, "ncclCommDestroy")
+        MAK_SYM(CommCount, "ncclCommCount")
+        MAK_SYM(CommUserRank, "ncclCommUserRank")
+        MAK_SYM(Send, "ncclSend")
+        MAK_SYM(Recv, "ncclRecv")
+        MAK_SYM(Broadcast, "ncclBroadcast")
+        MAK_SYM(AllGather, "ncclAllGather")
+        MAK_SYM(GroupStart, "ncclGroupStart")
+        MAK_SYM(GroupEnd, "ncclGroupEnd")
+        MAK_SYM(GetErrorString, "ncclGetErrorString")
+#undef MAK_SYM
+        api.loaded_from = from;
+        state = ok ? 1 : -1;
+    }
+    if (state < 0 && why) *why = msg;
+    return state > 0 ? &api : nullptr;
+}
+}  // namespace mak

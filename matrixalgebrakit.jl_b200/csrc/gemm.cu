@@ -366,7 +366,19 @@ cudaError_t gemm(cudaStream_t stream, int num_sms, int opa, int opb, int m, int 
         if (splitk < 2) splitk = 1;
     }
     grid.z = splitk;
-    if (g_clock_gemm.on) g_gemm_flops += 2.0 * (double)m * (double)n * (double)k * (is_cplx<T>::value ? 4.0 : 1.0);
+    if (g_clock_gemm.on) {
+        // flops of the tiles that actually run: a `lower` launch skips every tile entirely above the diagonal
+        double mn = (double)m * (double)n;
+        if (lower) {
+            mn = 0.0;
+            for (int bx = 0; bx < (int)grid.x; ++bx) {
+                int rows = min(C::BM, m - bx * C::BM);
+                int ncols = min(n, ((bx * C::BM + C::BM + C::BN - 1) / C::BN) * C::BN);
+                mn += (double)rows * (double)ncols;
+            }
+        }
+        g_gemm_flops += 2.0 * mn * (double)k * (is_cplx<T>::value ? 4.0 : 1.0);
+    }
     cudaError_t e = dispatch<T>(stream, opa != MAKB200_OP_N, opb != MAKB200_OP_N, grid, p, nullptr, splitk, (T*)ws);
     if (e != cudaSuccess) return e;
     if (splitk > 1) {

@@ -13,6 +13,7 @@
 #include "gemm.cuh"
 #include "qr.cuh"
 #include "projections.cuh"
+#include "nccl_dl.h"
 #include <vector>
 #include <cmath>
 
@@ -1027,6 +1028,209 @@ int cholqr2_t(makb200_handle* h, int m, int n, T* A, int lda, T* Q, int ldq, T* 
     if (info_dev) MAK_CUDA(h, cudaMemcpyAsync(info_dev, w.info, sizeof(int), cudaMemcpyDeviceToDevice, s));
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------
+// multi-GPU TSQR (BASELINE config 4): qr_compact! of a row-sharded tall-skinny matrix
+// ---------------------------------------------------------------------------------------
+// Rank p holds A_p (m_loc x n).  Local: CholeskyQR2 up to - but not including - the last triangular solve:
+//   A_p = Q1_p L1^H,  Q1_p^H Q1_p = L2 L2^H,  R_p = L2^H L1^H   (Q_p^loc = Q1_p L2^-H is never formed)
+// Across ranks: binary tree over R_p.  Each round one n x n block travels (ncclSend/ncclRecv on the handle's
+// stream, 512 KiB for n = 256 f64), the receiver takes the Householder QR of the stacked pair [R; R_b] and
+// keeps the 2n x n orthogonal factor.  Down-sweep: the path product T_p (n x n) of those factors reaches
+// every rank, and the ONE remaining tall GEMM applies the local solve and the tree together:
+//   Q_p = Q1_p (L2^-H T_p)
+// so a multi-GPU run does no tall-matrix work beyond the single-GPU algorithm (round 1 paid an extra
+// m_loc x n x n product).  R (positive diagonal by construction of the tree QRs) is broadcast from rank 0.
+constexpr int TSQR_MAX_LEVELS = 16;
+
+template <typename T>
+struct TsqrWork {
+    CqrWork<T> c;
+    T *Rcur, *Rb, *S, *Tcur, *Tb, *Tn, *Minv, *M, *Eye;
+    T* Qs[TSQR_MAX_LEVELS];
+    void* sub;
+    size_t sub_bytes;
+};
+
+template <typename T, typename AR>
+static void tsqr_carve(makb200_handle* h, AR& ar, int m, int n, int nranks, TsqrWork<T>* w) {
+    cqr_carve<T>(h, ar, m, n, &w->c);
+    size_t nn = (size_t)(n > 0 ? n : 1) * (size_t)(n > 0 ? n : 1);
+    w->Rcur = ar.template get<T>(nn);
+    w->Rb = ar.template get<T>(nn);
+    w->S = ar.template get<T>(2 * nn);
+    w->Tcur = ar.template get<T>(nn);
+    w->Tb = ar.template get<T>(nn);
+    w->Tn = ar.template get<T>(nn);
+    w->Minv = ar.template get<T>(nn);
+    w->M = ar.template get<T>(nn);
+    w->Eye = ar.template get<T>(nn);
+    int levels = 0;
+    for (int s = 1; s < nranks; s *= 2) ++levels;
+    for (int l = 0; l < TSQR_MAX_LEVELS; ++l) w->Qs[l] = l < levels ? ar.template get<T>(2 * nn) : nullptr;
+    w->sub_bytes = nranks > 1 ? qr_worksize_t<T>(h, 2 * n, n, n) : 0;
+    w->sub = ar.template get<char>(w->sub_bytes);
+}
+
+template <typename T>
+size_t tsqr_worksize_t(makb200_handle* h, int m, int n, int nranks) {
+    ArenaSize ar;
+    TsqrWork<T> w;
+    tsqr_carve<T>(h, ar, m, n, nranks, &w);
+    return ar.off + 256;
+}
+
+// S (2n x n) = [Ra; Rb]
+template <typename T>
+__global__ void stack2_kernel(int n, const T* __restrict__ Ra, const T* __restrict__ Rb, T* __restrict__ S) {
+    size_t total = (size_t)2 * n * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(idx % (2 * n)), c = (int)(idx / (2 * n));
+        S[idx] = r < n ? Ra[(size_t)c * n + r] : Rb[(size_t)c * n + (r - n)];
+    }
+}
+
+#define MAK_NCCL(h, api, call)                                                               \
+    do {                                                                                     \
+        ncclResult_t _r = (call);                                                            \
+        if (_r != ncclSuccess) {                                                             \
+            snprintf(h->err, sizeof(h->err), "%s: %s", #call, api->GetErrorString(_r));      \
+            return MAKB200_ERR_NCCL;                                                         \
+        }                                                                                    \
+    } while (0)
+
+template <typename T>
+int tsqr_t(makb200_handle* h, const NcclApi* api, ncclComm_t comm, int m, int n, T* A, int lda, T* Q, int ldq, T* R,
+           int ldr, void* work, size_t lwork, int* info_dev) {
+    int nranks = 1, rank = 0;
+    if (comm) {
+        MAK_NCCL(h, api, api->CommCount(comm, &nranks));
+        MAK_NCCL(h, api, api->CommUserRank(comm, &rank));
+    }
+    if (n <= 0) return 0;
+    cudaStream_t s = h->stream;
+    Arena ar(work, lwork);
+    TsqrWork<T> w;
+    tsqr_carve<T>(h, ar, m, n, nranks, &w);
+    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    MAK_CUDA(h, cudaMemsetAsync(w.c.info, 0, sizeof(int) * 4, s));
+    PhaseTimer pt(s);
+    pt.mark("start");
+    const size_t nn = (size_t)n * n;
+    const size_t cnt = nn * (is_cplx<T>::value ? 2 : 1);   // doubles per n x n block on the wire
+    const dim3 g((n + 127) / 128, n);
+    const int gnn = grid_for2(nn, h->num_sms);
+    int rc;
+    // ---- local: two Gram/Cholesky passes; the second solve is deferred ----
+    if (m > 0) {
+        rc = cholqr_pass<T>(h, m, n, A, lda, A, lda, w.c.L1, w.c);     // Q1 over A (block order makes it safe in place)
+        if (rc) return rc;
+        pt.mark("pass1");
+        MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, n, n, m, one<T>(), A, lda, A, lda, zero<T>(), w.c.G, n,
+                  w.c.ws, w.c.ws_bytes);
+        rc = potrf_blocked<T>(h, n, w.c.G, n, w.c.L2, n, w.c.Linv, w.c.info);
+        if (rc) return rc;
+        lower_clean_kernel<T><<<g, 128, 0, s>>>(n, w.c.L1);
+        lower_clean_kernel<T><<<g, 128, 0, s>>>(n, w.c.L2);
+        rmul_upper_kernel<T><<<g, 128, 0, s>>>(n, w.c.L2, w.c.L1, w.Rcur, n);
+        count_launch(3);
+        pt.mark("gram2");
+    } else {
+        MAK_CUDA(h, cudaMemsetAsync(w.Rcur, 0, nn * sizeof(T), s));   // a rank without rows contributes R = 0
+    }
+    if (nranks == 1) {
+        for (int r0 = 0; r0 < m; r0 += CQR_SLAB) {
+            int mr = (m - r0 < CQR_SLAB) ? (m - r0) : CQR_SLAB;
+            rc = trsm_right<T>(h, true, mr, n, A + r0, lda, w.c.L2, n, w.c.Linv, Q + r0, ldq, w.c.Tmp);
+            if (rc) return rc;
+        }
+        if (R && ldr > 0) {
+            copy2d_kernel<T><<<gnn, 256, 0, s>>>(n, n, w.Rcur, n, R, ldr);
+            count_launch();
+        }
+        MAK_LAUNCH_CHECK(h, "tsqr (1 rank)");
+        pt.mark("solve");
+        pt.report("tsqr");
+        if (info_dev) MAK_CUDA(h, cudaMemcpyAsync(info_dev, w.c.info, sizeof(int), cudaMemcpyDeviceToDevice, s));
+        return 0;
+    }
+    // ---- up-sweep ----
+    int nfac = 0, fac_partner[TSQR_MAX_LEVELS];
+    int sent_to = -1;
+    bool active = true;
+    for (int stride = 1; stride < nranks; stride *= 2) {
+        if (!active) continue;
+        if (rank % (2 * stride) == 0) {
+            int partner = rank + stride;
+            if (partner < nranks) {
+                MAK_NCCL(h, api, api->Recv(w.Rb, cnt, ncclDouble, partner, comm, s));
+                stack2_kernel<T><<<grid_for2(2 * nn, h->num_sms), 256, 0, s>>>(n, w.Rcur, w.Rb, w.S);
+                count_launch();
+                rc = qr_fused_t<T>(h, MAKB200_QR_COMPACT, 2 * n, n, w.S, 2 * n, w.Qs[nfac], 2 * n, w.Rcur, n, w.sub,
+                                   w.sub_bytes);
+                if (rc) return rc;
+                fac_partner[nfac++] = partner;
+            }
+        } else {
+            sent_to = rank - stride;
+            MAK_NCCL(h, api, api->Send(w.Rcur, cnt, ncclDouble, sent_to, comm, s));
+            active = false;
+        }
+    }
+    pt.mark("up");
+    // ---- down-sweep: T_p = product of the tree factors on the path root -> p ----
+    T* Tc = w.Tcur;
+    T* Tn = w.Tn;
+    if (rank == 0) {
+        eye_kernel<T><<<gnn, 256, 0, s>>>(n, Tc, n);
+        count_launch();
+    } else {
+        MAK_NCCL(h, api, api->Recv(Tc, cnt, ncclDouble, sent_to, comm, s));
+    }
+    for (int f = nfac - 1; f >= 0; --f) {
+        const T* Qs = w.Qs[f];
+        MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_N, n, n, n, one<T>(), Qs + n, 2 * n, Tc, n, zero<T>(), w.Tb, n,
+                  nullptr, 0);
+        MAK_NCCL(h, api, api->Send(w.Tb, cnt, ncclDouble, fac_partner[f], comm, s));
+        MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_N, n, n, n, one<T>(), Qs, 2 * n, Tc, n, zero<T>(), Tn, n,
+                  nullptr, 0);
+        T* t = Tc; Tc = Tn; Tn = t;
+    }
+    pt.mark("down");
+    // ---- Q_p = Q1_p (L2^-H T_p): explicit L2^-H from the blocked solver applied to I, then two products ----
+    if (m > 0) {
+        eye_kernel<T><<<gnn, 256, 0, s>>>(n, w.Eye, n);
+        count_launch();
+        rc = trsm_right<T>(h, true, n, n, w.Eye, n, w.c.L2, n, w.c.Linv, w.Minv, n, w.c.Tmp);
+        if (rc) return rc;
+        MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_N, n, n, n, one<T>(), w.Minv, n, Tc, n, zero<T>(), w.M, n,
+                  nullptr, 0);
+        for (int r0 = 0; r0 < m; r0 += CQR_SLAB) {
+            int mr = (m - r0 < CQR_SLAB) ? (m - r0) : CQR_SLAB;
+            MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_N, mr, n, n, one<T>(), A + r0, lda, w.M, n, zero<T>(),
+                      Q + r0, ldq, nullptr, 0);
+        }
+    }
+    pt.mark("apply");
+    // ---- R to everybody ----
+    MAK_NCCL(h, api, api->Broadcast(w.Rcur, w.Rcur, cnt, ncclDouble, 0, comm, s));
+    if (R && ldr > 0) {
+        copy2d_kernel<T><<<gnn, 256, 0, s>>>(n, n, w.Rcur, n, R, ldr);
+        count_launch();
+    }
+    MAK_LAUNCH_CHECK(h, "tsqr tail");
+    pt.mark("bcast");
+    pt.report("tsqr");
+    if (info_dev) MAK_CUDA(h, cudaMemcpyAsync(info_dev, w.c.info, sizeof(int), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+template size_t tsqr_worksize_t<double>(makb200_handle*, int, int, int);
+template size_t tsqr_worksize_t<cplx>(makb200_handle*, int, int, int);
+template int tsqr_t<double>(makb200_handle*, const NcclApi*, ncclComm_t, int, int, double*, int, double*, int, double*, int,
+                            void*, size_t, int*);
+template int tsqr_t<cplx>(makb200_handle*, const NcclApi*, ncclComm_t, int, int, cplx*, int, cplx*, int, cplx*, int, void*,
+                          size_t, int*);
 
 template <typename T>
 int adjoint_t(makb200_handle* h, int m, int n, const T* A, int lda, T* B, int ldb) {

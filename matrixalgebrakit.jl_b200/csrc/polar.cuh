@@ -1,5 +1,6 @@
 #pragma once
 #include "common.cuh"
+#include "nccl_dl.h"
 namespace mak {
 int polar_init(makb200_handle* h);
 template <typename T> size_t polar_worksize_t(makb200_handle* h, int m, int n);
@@ -17,6 +18,11 @@ template <typename T> size_t cholqr2_worksize_t(makb200_handle* h, int m, int n)
 template <typename T>
 int cholqr2_t(makb200_handle* h, int m, int n, T* A, int lda, T* Q, int ldq, T* R, int ldr, void* work, size_t lwork,
               int* info_dev, int nshift = 0);
+// multi-GPU TSQR: local CholeskyQR2 + binary-tree reduction of R over NCCL, tree factors folded into the last solve
+template <typename T> size_t tsqr_worksize_t(makb200_handle* h, int m, int n, int nranks);
+template <typename T>
+int tsqr_t(makb200_handle* h, const NcclApi* api, ncclComm_t comm, int m, int n, T* A, int lda, T* Q, int ldq, T* R,
+           int ldr, void* work, size_t lwork, int* info_dev);
 // B (n x m) = A^H for A (m x n); tiled, coalesced on both sides
 template <typename T> int adjoint_t(makb200_handle* h, int m, int n, const T* A, int lda, T* B, int ldb);
 }  // namespace mak

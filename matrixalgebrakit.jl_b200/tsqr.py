@@ -1,16 +1,20 @@
 """TSQR: qr_compact! of a tall-skinny matrix row-sharded over ranks (BASELINE configs[3]).
 
-New capability (SURVEY.md §8e): the result must equal the single-GPU ``qr_compact!`` of the
-row-concatenated matrix.  Per rank: local factorization (``makb200_tsqr_local``, CholeskyQR2 on
-the DMMA GEMM).  Across ranks: binary-tree reduction of the n x n R factors — each round one
-``send/recv`` of a 256x256 block (512 KiB) over NCCL/NVLink, a Householder QR of the stacked
-2n x n pair on the receiver, the tree factors pushed back down and one local GEMM
-``Q_p <- Q_p T_p``.  The exchange is issued from the stream that produced R (no host sync in
-the data path); it is latency-bound (~10-20 us per round) next to >= 15 ms of local work.
+New capability (SURVEY.md 8e): the result must equal the single-GPU ``qr_compact!`` of the
+row-concatenated matrix.  The product path is ONE C-ABI call, ``makb200_tsqr(h, ncclComm_t, ...)``
+(csrc/polar.cu: tsqr_t): local CholeskyQR2 on the DMMA GEMM, binary-tree reduction of the n x n R
+factors with ncclSend/ncclRecv issued from the producing stream, Householder QR of each stacked pair,
+the tree's path product folded into the last local solve (``Q_p = Q1_p (L2^-H T_p)``) and an
+ncclBroadcast of R.  This module only builds the communicator (``makb200_comm_create``; the
+ncclUniqueId travels through torch.distributed) and marshals pointers.
 
-The numerical kernels are injected through ``ops`` so the tree logic can be tested with gloo on
-CPU (tests/test_tsqr_gloo.py supplies a numpy stand-in); the default ``ops`` is the CUDA library
-and fails loudly without a GPU."""
+``ops`` injects the numerical steps into a Python model of the same tree so that the topology
+(send/recv pairing, uneven world sizes, down-sweep order) is tested with gloo on CPU
+(tests/test_tsqr_gloo.py supplies a numpy stand-in).  ``robust=True`` (shifted CholeskyQR local step for
+ill-conditioned shards) also takes that tree with the CUDA library as ``ops``.  Nothing here falls back to
+the CPU: the default path fails loudly without a GPU."""
+
+import ctypes as C
 
 import torch
 import torch.distributed as dist
@@ -84,6 +88,59 @@ def _recv(buf, src, group):
     return buf
 
 
+_COMMS = {}
+
+
+def nccl_comm(group=None, device=None):
+    """ncclComm_t (as a ctypes void pointer) spanning ``group`` in rank order, created once per (group, device)
+    by ``makb200_comm_create``; the 128-byte ncclUniqueId is broadcast through torch.distributed."""
+    from . import _lib
+    lib = _lib.load()
+    dev = torch.device(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    key = (id(group) if group is not None else 0, dev.index)
+    if key in _COMMS:
+        return _COMMS[key]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    buf = (C.c_char * 128)()
+    if rank == 0:
+        rc = lib.makb200_nccl_unique_id(buf)
+        if rc != 0:
+            raise _core.MakError(f"makb200_nccl_unique_id failed ({rc}): libnccl.so.2 not loadable")
+    box = [bytes(buf) if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    idbytes = (C.c_char * 128).from_buffer_copy(box[0])
+    comm = C.c_void_p()
+    with torch.cuda.device(dev):
+        rc = lib.makb200_comm_create(C.byref(comm), world, rank, idbytes)
+    if rc != 0:
+        raise _core.MakError(f"makb200_comm_create failed ({rc})")
+    _COMMS[key] = comm
+    return comm
+
+
+def _tsqr_cabi(A_local, group, check):
+    m, n = A_local.shape
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    h = _core.Handle.get(A_local.device)
+    dt = _core.dtype_code(A_local)
+    if not _core.is_colmajor(A_local):
+        raise ValueError("tsqr_: column-major shard expected")
+    comm = nccl_comm(group, A_local.device) if world > 1 else C.c_void_p(0)
+    Q = _core.colmajor_empty(m, n, A_local.dtype, A_local.device)
+    R = _core.colmajor_empty(n, n, A_local.dtype, A_local.device)
+    info = torch.zeros(1, dtype=torch.int32, device=A_local.device)
+    lw = h.lib.makb200_tsqr_worksize(h.h, dt, m, n, world)
+    work = h.workspace(lw)
+    rc = h.lib.makb200_tsqr(h.h, comm, dt, m, n, _core.ptr(A_local), _core.ld(A_local), _core.ptr(Q), _core.ld(Q),
+                            _core.ptr(R), _core.ld(R), _core.ptr(work), work.numel(), _core.ptr(info))
+    h.check(rc, "makb200_tsqr")
+    if check and int(info.item()) != 0:
+        raise _core.MakError("tsqr: Cholesky breakdown in the local factorization (matrix too ill-conditioned "
+                             "for CholeskyQR2, kappa >~ 1e7): call tsqr_(A, robust=True) on a fresh copy "
+                             "(the input was destroyed)")
+    return Q, R
+
+
 def tsqr_(A_local, group=None, ops=None, check=True, robust=False):
     """Row-sharded ``qr_compact!``: every rank passes its (m_loc x n) shard (destroyed) and gets
     back (Q_local, R) with R identical on all ranks, diag(R) >= 0.
@@ -91,6 +148,8 @@ def tsqr_(A_local, group=None, ops=None, check=True, robust=False):
     ``robust=True`` (or an int 1..3 = number of preconditioning passes) runs the local step as
     shifted CholeskyQR (2 extra passes by default): any numerically full-rank shard, at twice the
     cost of the default CholeskyQR2 (kappa <~ 1e7)."""
+    if ops is None and not robust:
+        return _tsqr_cabi(A_local, group, check)
     if ops is None:
         ops = _CudaOps(nshift=(2 if robust is True else int(robust)))
     n = A_local.shape[1]

@@ -7,6 +7,8 @@
 set -u
 mkdir -p gpurun_out
 {
+echo "== (0) cuSOLVER / cuBLAS bar (library calls, same box) =="
+timeout 600 python tools/cusolver_bar.py gpurun_out/r2_cusolver_bar.json 2>&1 | tail -40
 echo "== (1) ungated: values-only, leading-rank, batched truncation, projections, rank-deficient SVD =="
 timeout 900 python -m pytest tests/test_gpu_y_vals.py tests/test_gpu_y_trunc.py tests/test_gpu_y_projections.py tests/test_gpu_y_rankdef.py -q 2>&1 | tail -15
 echo "== timings: eigh_vals vs eigh_full, svd_vals vs svd_compact, svd_trunc r=1024 (8192 f64) =="
@@ -40,9 +42,9 @@ for cfg in "" "MAKB200_SY2SB_LOWER=1" "MAKB200_SY2SB_LOOKAHEAD=1" "MAKB200_SY2SB
            "MAKB200_SY2SB_LOWER=1 MAKB200_SY2SB_LOOKAHEAD=1 MAKB200_CHASE_PERSISTENT=1 MAKB200_Q2_FUSED=1" \
            "MAKB200_EIGH_TWOSTAGE=32 MAKB200_SY2SB_LOWER=1 MAKB200_SY2SB_LOOKAHEAD=1 MAKB200_CHASE_PERSISTENT=1 MAKB200_Q2_FUSED=1"; do
   echo "-- $cfg"
-  env MAKB200_EIGH_TWOSTAGE=64 MAKB200_PHASES=1 $cfg timeout 300 python tools/twostage_check.py 8192 2>&1 | tail -12
+  env SKIP_SMALL=1 MAKB200_EIGH_TWOSTAGE=64 MAKB200_PHASES=1 $cfg timeout 300 python tools/twostage_check.py 8192 2>&1 | tail -12
 done
 echo "== (5) the assembled two-stage path with both bring-up kernels through the test =="
 MAKB200_BRINGUP=1 timeout 600 python -m pytest tests/test_gpu_zz_bringup.py -q -k "two_stage" 2>&1 | tail -6
 } > gpurun_out/r2a.log 2>&1
-tail -80 gpurun_out/r2a.log
+tail -150 gpurun_out/r2a.log
