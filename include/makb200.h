@@ -75,6 +75,15 @@ size_t makb200_orgqr_worksize(makb200_handle_t* h, int dtype, int m, int ncols, 
 int makb200_orgqr(makb200_handle_t* h, int dtype, int m, int ncols, int k, const void* A,
                   int lda, const void* tau, void* Q, int ldq, void* work, size_t lwork);
 
+/* makb200_ormqr  replaces unmqr!/ormqr (yalapack.jl:688-735; yacusolver.jl:14; MatrixAlgebraKitCUDAExt.jl:32-34),
+ *   the consumer being qr_null_householder! (implementations/qr.jl:236-262: unmqr!(driver,'L','N',A,tau,N)):
+ *   C (m x n) <- Q C (trans = MAKB200_OP_N) or Q^H C (MAKB200_OP_C; MAKB200_OP_T for Float64), Q = H_1...H_k from
+ *   makb200_geqrf (A m x k below the diagonal, tau).  side: 0 = left; the right side is not provided (-3).
+ *   Compact-WY blocks of 128 reflectors, three DMMA GEMMs per block. */
+size_t makb200_ormqr_worksize(makb200_handle_t* h, int dtype, int m, int n, int k);
+int makb200_ormqr(makb200_handle_t* h, int dtype, int side, int trans, int m, int n, int k, const void* A,
+                  int lda, const void* tau, void* C, int ldc, void* work, size_t lwork);
+
 /* -- L2 fused QR: qr_householder!(driver, A, Q, R; positive) (implementations/qr.jl:132-188)
  *   mode COMPACT: Q m x k, R k x n; FULL: Q m x m, R m x n (k = min(m,n)).
  *   R == NULL or ldr == 0  => "R not requested" (zero-length R, qr.jl:149).
@@ -272,6 +281,11 @@ size_t makb200_trunc_select_batched_worksize(makb200_handle_t* h, int batch);
 int makb200_trunc_select_batched(makb200_handle_t* h, int batch, const int* k, double* const* S,
                                  const makb200_trunc_spec* spec, const int* maxrank_blk, int* rank_dev,
                                  double* eps_dev, void* work, size_t lwork);
+
+/* -- gaugefix!(eigh_full!, V) on its own (common/gauge.jl:38-45; also the per-column rule of the svd_full! gauge,
+ * gauge.jl:47-67, for the columns / rows beyond min(m,n)): every column of V (m x ncols) is multiplied by
+ * conj(sign(first entry of maximal modulus)).  One launch (the reference loops over columns with a host scalar). */
+int makb200_gauge_columns(makb200_handle_t* h, int dtype, int m, int ncols, void* V, int ldv);
 
 /* -- adjoint: B (n x m) = A^H.  Used by the LQ family, which every GPU driver of the reference
  * routes through QR of the adjoint (lq_via_qr!, implementations/lq.jl:130-131,303-327), and by

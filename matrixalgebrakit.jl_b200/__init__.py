@@ -9,13 +9,14 @@ from ._core import (Handle, MakError, as_colmajor, colmajor_empty, colmajor_zero
 from .algorithms import *  # noqa: F401,F403
 from .algorithms import (Algorithm, TruncatedAlgorithm, default_algorithm, select_algorithm)
 from .gemm import gemm_
-from .qr import (qr_compact, qr_compact_, qr_compact_batched_, qr_full, qr_full_, qr_householder_)
+from .qr import (geqrf_, qr_compact, qr_compact_, qr_compact_batched_, qr_full, qr_full_, qr_householder_, qr_null_householder_,
+                 ungqr_, unmqr_)
 from .eigh import (DomainError, check_hermitian, eigh_full, eigh_full_, eigh_trunc, eigh_trunc_, eigh_vals,
                    eigh_vals_)
 from .truncation import (findtruncated, findtruncated_svd, notrunc, select_truncation, trunc_and, trunc_or,
                          truncerror, truncrank, trunctol)
 from .polar import left_polar, left_polar_
-from .svd import (svd_compact, svd_compact_, svd_trunc, svd_trunc_, svd_trunc_no_error, svd_trunc_no_error_,
+from .svd import (svd_compact, svd_compact_, svd_full, svd_full_, svd_trunc, svd_trunc_, svd_trunc_no_error, svd_trunc_no_error_,
                   svd_vals, svd_vals_)
 from . import eigh, polar, qr, svd, truncation  # noqa: E402,F401
 from .tsqr import tsqr_

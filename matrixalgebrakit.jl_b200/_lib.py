@@ -33,6 +33,8 @@ SIGNATURES = {
     "makb200_geqrf": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _sz]),
     "makb200_orgqr_worksize": (_sz, [_vp, _i, _i, _i, _i]),
     "makb200_orgqr": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _sz]),
+    "makb200_ormqr_worksize": (_sz, [_vp, _i, _i, _i, _i]),
+    "makb200_ormqr": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _sz]),
     "makb200_qr_worksize": (_sz, [_vp, _i, _i, _i, _i]),
     "makb200_qr": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _sz]),
     "makb200_qr_batched_worksize": (_sz, [_vp, _i, _i, _ip, _ip]),
@@ -72,6 +74,7 @@ SIGNATURES = {
     "makb200_trunc_select_batched_worksize": (_sz, [_vp, _i]),
     "makb200_trunc_select_batched": (_i, [_vp, _i, _ip, _vpp, _vp, _ip, _vp, _vp, _vp, _sz]),
     "makb200_adjoint": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i]),
+    "makb200_gauge_columns": (_i, [_vp, _i, _i, _i, _vp, _i]),
     "makb200_nccl_unique_id": (_i, [_vp]),
     "makb200_comm_create": (_i, [C.POINTER(_vp), _i, _i, _vp]),
     "makb200_comm_destroy": (_i, [_vp]),

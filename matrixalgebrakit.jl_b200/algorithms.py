@@ -141,7 +141,7 @@ def default_polar_algorithm(A, **kw):
 
 
 _DEFAULTS = {
-    "qr_compact": default_qr_algorithm, "qr_full": default_qr_algorithm,
+    "qr_compact": default_qr_algorithm, "qr_full": default_qr_algorithm, "qr_null": default_qr_algorithm,
     "svd_compact": default_svd_algorithm, "svd_full": default_svd_algorithm,
     "svd_vals": default_svd_algorithm,
     "eigh_full": default_eigh_algorithm, "eigh_vals": default_eigh_algorithm,

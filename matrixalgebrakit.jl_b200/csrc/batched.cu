@@ -269,12 +269,79 @@ batched_svd_kernel(const SvdBlockDesc<T>* __restrict__ descs, int* __restrict__ 
         perm[rank] = j;
     }
     __syncthreads();
+    // normalise the columns of G in place (left vectors of the tall problem); exactly-zero columns stay zero
+    for (int j = warp; j < nn; j += NW) {
+        const double sj = sig[j], invj = sj > 0.0 ? 1.0 / sj : 0.0;
+        for (int r = lane; r < mm; r += 32) G[(size_t)j * ldg + r] = scale_(G[(size_t)j * ldg + r], invj);
+    }
+    __syncthreads();
+    // Collapsed columns (sigma == 0: a zero block, a zero column, or a zero row of a wide block) would leave U
+    // (tall) / Vh (wide) non-isometric, while the reference contract (LAPACK gesdd) is an isometry for ANY input.
+    // Complete them: the unit vector e_k with the least mass in the span so far, projected off that span
+    // (w = e_k - sum_c u_c conj(u_c[k]) needs no dot products) and normalised; ||w||^2 >= 1 - rank/mm.
+    {
+        int nz = 0;
+        while (nz < nn && sig[perm[nn - 1 - nz]] == 0.0) ++nz;    // sorted: the zeros are last
+        double* mass = reinterpret_cast<double*>(perm + nn + (nn & 1));   // mm doubles behind perm
+        __shared__ double s_best[NT / 32];
+        __shared__ int s_bidx[NT / 32];
+        __shared__ double s_red[NT / 32];
+        if (nz > 0) {
+            for (int r = tid; r < mm; r += NT) {
+                double a = 0.0;
+                for (int cc = 0; cc < nn; ++cc) a += abs2_(G[(size_t)cc * ldg + r]);
+                mass[r] = a;
+            }
+            __syncthreads();
+            for (int t = 0; t < nz; ++t) {
+                const int z = perm[nn - nz + t];
+                // k = first row of least mass
+                double best = 1e300; int bi = 0x7fffffff;
+                for (int r = tid; r < mm; r += NT)
+                    if (mass[r] < best) { best = mass[r]; bi = r; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                if (lane == 0) { s_best[warp] = best; s_bidx[warp] = bi; }
+                __syncthreads();
+                for (int w = 0; w < NW; ++w)
+                    if (s_best[w] < best || (s_best[w] == best && s_bidx[w] < bi)) { best = s_best[w]; bi = s_bidx[w]; }
+                const int k = bi;
+                double nrm = 0.0;
+                for (int r = tid; r < mm; r += NT) {
+                    T wv = (r == k) ? one<T>() : zero<T>();
+                    for (int cc = 0; cc < nn; ++cc) {
+                        if (cc == z) continue;
+                        const T uk = G[(size_t)cc * ldg + k];
+                        wv = sub_(wv, mul_(G[(size_t)cc * ldg + r], conj_(uk)));
+                    }
+                    G[(size_t)z * ldg + r] = wv;     // column z is read by nobody in this loop (cc != z)
+                    nrm += abs2_(wv);
+                }
+                nrm = warp_sum(nrm);
+                if (lane == 0) s_red[warp] = nrm;
+                __syncthreads();
+                double tot = 0.0;
+                for (int w = 0; w < NW; ++w) tot += s_red[w];
+                const double invn = tot > 0.0 ? 1.0 / sqrt(tot) : 0.0;
+                for (int r = tid; r < mm; r += NT) {
+                    const T u = scale_(G[(size_t)z * ldg + r], invn);
+                    G[(size_t)z * ldg + r] = u;
+                    mass[r] += abs2_(u);
+                }
+                __syncthreads();
+            }
+        }
+    }
     // outputs: one warp per singular triplet
     for (int j = warp; j < nn; j += NW) {
         const int src = perm[j];
         const double sj = sig[src];
-        const double inv = sj > 0.0 ? 1.0 / sj : 0.0;
-        const T* g = G + (size_t)src * ldg;   // sigma * (left vector of the tall problem)
+        const double inv = 1.0;               // G is normalised in place above
+        const T* g = G + (size_t)src * ldg;   // left vector of the tall problem
         const T* v = V + (size_t)src * ldv;   // right vector of the tall problem
         // U column of the ORIGINAL problem: tall -> g/sigma (length m); wide -> v (length m)
         const int ulen = d.m;
@@ -315,7 +382,8 @@ batched_svd_kernel(const SvdBlockDesc<T>* __restrict__ descs, int* __restrict__ 
 
 size_t batched_svd_smem_bytes(int m, int n, size_t elem) {
     int mm = m < n ? n : m, nn = m < n ? m : n;
-    return ((size_t)(mm | 1) * nn + (size_t)(nn | 1) * nn) * elem + (size_t)nn * 12 + 64;
+    // G, V, sig[nn], perm[nn] (+ pad), mass[mm] (completion of collapsed columns)
+    return ((size_t)(mm | 1) * nn + (size_t)(nn | 1) * nn) * elem + (size_t)nn * 12 + (size_t)mm * 8 + 64;
 }
 size_t batched_svd_max_smem_bytes() { return BQ_SMEM_BYTES; }
 

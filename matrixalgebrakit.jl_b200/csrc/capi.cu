@@ -805,6 +805,47 @@ int makb200_tsqr_local(makb200_handle_t* h, int dtype, int m, int n, void* A, in
     return rc == -11 ? -1 : (rc <= -12 ? rc + 1 : rc);
 }
 
+int makb200_gauge_columns(makb200_handle_t* h, int dtype, int m, int ncols, void* V, int ldv) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (m < 0) return -3;
+    if (ncols < 0) return -4;
+    if (ldv < maxi(1, m)) return -6;
+    if (m == 0 || ncols == 0) return 0;
+    if (!V) return -5;
+    mak::count_launch();
+    if (dtype == MAKB200_F64) return mak::gauge_columns<double>(h, m, ncols, (double*)V, ldv, (double*)nullptr, 0, 0);
+    return mak::gauge_columns<cplx>(h, m, ncols, (cplx*)V, ldv, (cplx*)nullptr, 0, 0);
+}
+
+// ---- L1 shim: ormqr / unmqr (left side) -----------------------------------------------------
+size_t makb200_ormqr_worksize(makb200_handle_t* h, int dtype, int m, int n, int k) {
+    if (!h || !dtype_ok(dtype) || m < 0 || n < 0 || k < 0) return 0;
+    return dtype == MAKB200_F64 ? mak::ormqr_worksize_t<double>(h, m, k, n) : mak::ormqr_worksize_t<cplx>(h, m, k, n);
+}
+
+int makb200_ormqr(makb200_handle_t* h, int dtype, int side, int trans, int m, int n, int k, const void* A, int lda,
+                  const void* tau, void* C, int ldc, void* work, size_t lwork) {
+    if (!h) return -1;
+    if (!dtype_ok(dtype)) return -2;
+    if (side != 0) return -3;                               // left side only
+    if (!op_ok(trans)) return -4;
+    if (trans == MAKB200_OP_T && dtype == MAKB200_C128) return -4;   // LAPACK zunmqr: 'N' or 'C'
+    if (m < 0) return -5;
+    if (n < 0) return -6;
+    if (k < 0 || k > m) return -7;
+    if (lda < maxi(1, m)) return -9;
+    if (ldc < maxi(1, m)) return -12;
+    if (m == 0 || n == 0 || k == 0) return 0;
+    if (!A) return -8;
+    if (!tau) return -10;
+    if (!C || C == A) return -11;
+    const bool adj = trans != MAKB200_OP_N;
+    if (dtype == MAKB200_F64)
+        return mak::ormqr_left_t<double>(h, m, k, (const double*)A, lda, (const double*)tau, (double*)C, ldc, n, work, lwork, adj);
+    return mak::ormqr_left_t<cplx>(h, m, k, (const cplx*)A, lda, (const cplx*)tau, (cplx*)C, ldc, n, work, lwork, adj);
+}
+
 // ---- multi-GPU TSQR (NCCL resolved at run time) --------------------------------------------
 size_t makb200_tsqr_worksize(makb200_handle_t* h, int dtype, int m, int n, int nranks) {
     if (!h || !dtype_ok(dtype) || m < 0 || n < 0 || nranks < 1) return 0;

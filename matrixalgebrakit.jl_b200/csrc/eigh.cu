@@ -113,6 +113,9 @@ struct TrdCtx {
     double* pn;      // partial tail norms of the current column
     T* pyv;          // partial y^H v
     T* tau; double* d; double* e;
+    // persistent TMA column kernel (trd2.cuh): fixed-slot partial buffers, panel-dot partials, step scalars, ticket
+    T* yrowp; T* ycolp; T* tpart; int tpld;
+    int v2;          // 1: trd_symv2_kernel / trd_w2_kernel
 };
 
 constexpr int TRD_K1_THREADS = 256;   // 8 warps x 4 columns
@@ -657,7 +660,7 @@ trd_symv_tma_kernel(const __grid_constant__ CUtensorMap tmap, TrdCtx<T> x, int c
 
 // host: 2-D tiled tensor map over A viewed as doubles (rows = n * sizeof(T)/8 contiguous, n columns)
 template <typename T>
-static bool make_symv_tmap(CUtensorMap* tm, const T* A, int n, int lda) {
+static bool make_symv_tmap(CUtensorMap* tm, const T* A, int n, int lda, bool force = false) {
     static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
     static bool tried = false;
     if (!tried) {
@@ -671,7 +674,7 @@ static bool make_symv_tmap(CUtensorMap* tm, const T* A, int n, int lda) {
     // measured on B200 (round 1): the register-landing kernel is ~8 % faster than the TMA ring for this
     // access pattern, so TMA is opt-in (MAKB200_SYMV_TMA=1)
     const char* e = getenv("MAKB200_SYMV_TMA");
-    if (!(e && e[0] == '1')) return false;
+    if (!force && !(e && e[0] == '1')) return false;
     if (!enc) return false;
     if ((reinterpret_cast<uintptr_t>(A) & 15) != 0) return false;
     if (((size_t)lda * sizeof(T)) % 16 != 0) return false;
@@ -695,6 +698,10 @@ __device__ __forceinline__ T trd_ycol(const TrdCtx<T>& x, int row0, int mt, int 
     for (int sg = 0; sg < nseg; ++sg) s = add_(s, x.y[((size_t)b * x.maxseg + sg) * CW + k]);
     return s;
 }
+
+}  // namespace mak
+#include "trd2.cuh"
+namespace mak {
 
 // 288 threads: warps 0..7 make ONE pass over the panel rows (V[r,p], W[r,p] feed both the w update
 // and the left-looking update of the next column) and sum the row parts of y; warp 8 computes the
@@ -815,10 +822,27 @@ __global__ void trd_last_d_kernel(TrdCtx<T> x) {
     x.d[x.n - 1] = real_(x.A[(size_t)(x.n - 1) * x.lda + (x.n - 1)]);
 }
 
+// grid of the persistent column kernel: one wave of two CTAs per SM
+static int trd2_grid(makb200_handle* h) { return 2 * h->num_sms; }
+static bool trd2_enabled() {
+    static const bool v = []() { const char* e = getenv("MAKB200_SYMV_V2"); return !(e && e[0] == '0'); }();
+    return v;
+}
+
 template <typename T, typename AR>
-static void trd_carve(AR& ar, int n, TrdCtx<T>* x) {
+static void trd_carve(AR& ar, int n, TrdCtx<T>* x, int G = 0) {
     size_t nn = (size_t)(n > 0 ? n : 1);
     x->n = n;
+    x->v2 = 0;
+    x->yrowp = x->ycolp = x->tpart = nullptr;
+    x->tpld = 0;
+    if (G >= 2 * TRD_NB && trd2_enabled() && n >= 2 && n <= 64 * G) {
+        x->v2 = 1;
+        x->yrowp = ar.template get<T>((size_t)G * nn);
+        x->ycolp = ar.template get<T>((size_t)((nn + TRD2_BH - 1) / TRD2_BH) * nn);
+        x->tpld = (int)(nn / TRD_K2_ROWS + 2);
+        x->tpart = ar.template get<T>((size_t)x->tpld * 2 * TRD_NB);
+    }
     x->P = ar.template get<T>(nn * 3 * TRD_NB);
     x->ldp = n > 0 ? n : 1;
     x->maxseg = (int)((nn + TRD_SEG_MIN - 1) / TRD_SEG_MIN);
@@ -832,7 +856,11 @@ static void trd_carve(AR& ar, int n, TrdCtx<T>* x) {
     x->ypart = ar.template get<T>(nn * ((nn + SymvCW<T>::value - 1) / SymvCW<T>::value));
     x->t = ar.template get<T>(2 * TRD_NB);
     x->pn = ar.template get<double>(nn / TRD_K2_ROWS + 2);
-    x->pyv = ar.template get<T>((nn / SymvCW<T>::value + 2 * TRD_NB / 32 + 8) * (size_t)(x->maxseg + 1));
+    {
+        size_t npyv = (nn / SymvCW<T>::value + 2 * TRD_NB / 32 + 8) * (size_t)(x->maxseg + 1);
+        if (npyv < (size_t)G) npyv = (size_t)G;     // the persistent kernel writes one slot per CTA
+        x->pyv = ar.template get<T>(npyv);
+    }
     x->tau = ar.template get<T>(nn);
     x->d = ar.template get<double>(nn);
     x->e = ar.template get<double>(nn);
@@ -855,6 +883,18 @@ static int hetrd(makb200_handle* h, TrdCtx<T>& x) {
         trd_last_d_kernel<T><<<1, 1, 0, s>>>(x);
         return 0;
     }
+    // persistent TMA column kernels (trd2.cuh): need a 16-byte aligned A / leading dimension for the tensor map
+    CUtensorMap tmap2;
+    const bool v2 = x.v2 && !use_tma && make_symv_tmap<T>(&tmap2, x.A, n, x.lda, true);
+    constexpr size_t v2_smem = (size_t)TRD2_NST * TRD2_BH * SymvCW<T>::value * sizeof(T) + 128;
+    const int G2 = trd2_grid(h);
+    if (v2) {
+        static bool v2_configured = false;
+        if (!v2_configured) {
+            MAK_CUDA(h, cudaFuncSetAttribute(trd_symv2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2_smem));
+            v2_configured = true;
+        }
+    }
     for (int j0 = 0; j0 < n - 1; j0 += TRD_NB) {
         const int ncols = (n - 1 - j0 < TRD_NB) ? (n - 1 - j0) : TRD_NB;
         x.pw = ncols;
@@ -871,6 +911,25 @@ static int hetrd(makb200_handle* h, TrdCtx<T>& x) {
             const int nstrips = (mt + SymvCW<T>::value - 1) / SymvCW<T>::value;
             const int gx = nstrips + (2 * i + 31) / 32, gy = (mt + x.seg - 1) / x.seg;
             const int g1 = gx * gy;  // pyv slots written by this launch
+            if (v2) {
+                const int do_next2 = (i + 1 < ncols) ? 1 : 0;
+                const bool pdl2 = trd_pdl() && !g_clock_dots.on;
+                g_clock_dots.begin(s);
+                if (pdl2) {
+                    cudaError_t e = launch_pdl(trd_symv2_kernel<T>, dim3(G2), dim3(288), v2_smem, s, tmap2, x, c, i, npn);
+                    if (e != cudaSuccess) return cuda_fail(h, e, "trd_symv2_kernel (PDL)");
+                } else trd_symv2_kernel<T><<<G2, 288, v2_smem, s>>>(tmap2, x, c, i, npn);
+                g_clock_dots.end(s);
+                g_clock_w.begin(s);
+                if (pdl2) {
+                    cudaError_t e = launch_pdl(trd_w2_kernel<T>, dim3(g2), dim3(288), 0, s, x, c, i, G2, do_next2);
+                    if (e != cudaSuccess) return cuda_fail(h, e, "trd_w2_kernel (PDL)");
+                } else trd_w2_kernel<T><<<g2, 288, 0, s>>>(x, c, i, G2, do_next2);
+                g_clock_w.end(s);
+                count_launch(2);
+                npn = g2;
+                continue;
+            }
             g_clock_dots.begin(s);
             const bool pdl = trd_pdl() && !use_tma && !g_clock_dots.on;
             if (use_tma) trd_symv_tma_kernel<T><<<dim3(gx, gy), 288, tma_smem_bytes, s>>>(tmap, x, c, i, npn, nstrips);
@@ -1096,7 +1155,7 @@ struct TwoStageWork {
 template <typename T, typename AR>
 static void eigh_carve(makb200_handle* h, AR& ar, int n, TrdCtx<T>* x, double** Zreal, void** sub, size_t* sub_bytes,
                        TwoStageWork<T>* ts = nullptr) {
-    trd_carve<T>(ar, n, x);
+    trd_carve<T>(ar, n, x, trd2_grid(h));
     size_t nn = (size_t)(n > 0 ? n : 1);
     *Zreal = is_cplx<T>::value ? ar.template get<double>(nn * nn) : nullptr;
     size_t a = stedc_worksize(n);

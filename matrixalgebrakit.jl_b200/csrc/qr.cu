@@ -656,7 +656,7 @@ size_t ormqr_worksize_t(makb200_handle* h, int m, int k, int nc) {
 
 template <typename T>
 int ormqr_left_t(makb200_handle* h, int m, int k, const T* A, int lda, const T* tau, T* C, int ldc, int nc,
-                 void* work, size_t lwork) {
+                 void* work, size_t lwork, bool adjoint) {
     if (m <= 0 || nc <= 0 || k <= 0) return 0;
     Arena ar(work, lwork);
     QrWork<T> w;
@@ -666,7 +666,9 @@ int ormqr_left_t(makb200_handle* h, int m, int k, const T* A, int lda, const T* 
     const int nb = w.nb;
     const int nblk = (k + nb - 1) / nb;
     T* Tb = w.Tall;  // one block at a time
-    for (int b = nblk - 1; b >= 0; --b) {
+    // Q C = H_0 (H_1 (... C)): last block first;  Q^H C = H_{k-1}^H (... (H_0^H C)): first block first, T^H
+    for (int bb = 0; bb < nblk; ++bb) {
+        const int b = adjoint ? bb : nblk - 1 - bb;
         const int j0 = b * nb;
         const int jb = (k - j0 < nb) ? (k - j0) : nb;
         const int mp = m - j0;
@@ -682,7 +684,7 @@ int ormqr_left_t(makb200_handle* h, int m, int k, const T* A, int lda, const T* 
             if (e != cudaSuccess) return cuda_fail(h, e, "larft_diag_kernel");
         }
         count_launch();
-        int rc = apply_block_reflector<T>(h, false, mp, nc, jb, w.Vw, mp, Tb, nb, C + j0, ldc, w);
+        int rc = apply_block_reflector<T>(h, adjoint, mp, nc, jb, w.Vw, mp, Tb, nb, C + j0, ldc, w);
         if (rc) return rc;
     }
     return 0;
@@ -831,7 +833,7 @@ int sy2sb_t(makb200_handle* h, int n, int b, T* A, int lda, T* tau1, void* work,
     template int geqrf_t<T>(makb200_handle*, int, int, T*, int, T*, void*, size_t);                        \
     template int orgqr_t<T>(makb200_handle*, int, int, int, const T*, int, const T*, T*, int, void*, size_t); \
     template size_t ormqr_worksize_t<T>(makb200_handle*, int, int, int);                                   \
-    template int ormqr_left_t<T>(makb200_handle*, int, int, const T*, int, const T*, T*, int, int, void*, size_t);
+    template int ormqr_left_t<T>(makb200_handle*, int, int, const T*, int, const T*, T*, int, int, void*, size_t, bool);
 INST(double)
 INST(cplx)
 

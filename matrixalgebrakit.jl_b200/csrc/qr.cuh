@@ -13,7 +13,7 @@ int orgqr_t(makb200_handle* h, int m, int ncols, int k, const T* A, int lda, con
 template <typename T> size_t ormqr_worksize_t(makb200_handle* h, int m, int k, int nc);
 template <typename T>
 int ormqr_left_t(makb200_handle* h, int m, int k, const T* A, int lda, const T* tau, T* C, int ldc, int nc, void* work,
-                 size_t lwork);
+                 size_t lwork, bool adjoint = false);   // adjoint: C <- Q^H C
 // EXPERIMENTAL: dense -> band (first stage of the two-stage tridiagonalisation); A full Hermitian, in place
 template <typename T> size_t sy2sb_worksize_t(makb200_handle* h, int n, int b);
 template <typename T> int sy2sb_t(makb200_handle* h, int n, int b, T* A, int lda, T* tau1, void* work, size_t lwork);

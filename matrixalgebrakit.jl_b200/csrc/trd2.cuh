@@ -1,0 +1,420 @@
+// Persistent, TMA-fed column kernels of the Hermitian tridiagonalisation (included by eigh.cu).
+//
+// Round 1 streamed the trailing matrix with ~2700 short-lived CTAs per column (128 KB each between a
+// reflector prologue and a reduction epilogue): 0.36 of the measured HBM rate, 24 % warps active (ncu,
+// profiles/r1_ncu_summaries.txt).  Here ONE wave of 2 CTAs per SM runs per column.  Every CTA owns a
+// contiguous chunk of the band-major tile list (trd_tiles.h) and keeps a 3-stage shared-memory ring full
+// for the whole launch: a producer lane issues cp.async.bulk.tensor (one 256-row x CW-column tile = 32 KB
+// per stage, no register cost, ~190 KB of loads in flight per SM), eight consumer warps do the two FMAs
+// per element out of shared memory (lane = row).  The ring is filled before the reflector scalars are
+// known (the loads do not depend on them), so the prologue latency is hidden.
+//
+//   per tile    column parts  ycol[J][k] = sum_{r in band J} conj(A[r,k]) v[r]   (butterfly reduction, one
+//               named barrier per tile), row part accumulated in one register per thread
+//   per band    row parts     yrow[g][r] = sum_{k in chunk g} A[r,k] v[k]  (+ the real diagonal term)
+//   per CTA     v^H A22 v partial; V(:, i) over its row slice; CTA g < 2i finishes panel dot product g
+//               (t1 = W^H v, t2 = V^H v) from the per-CTA partials the previous w kernel left behind
+//
+// trd_w2_kernel then forms w, writes the reflector back, updates the next column and its partial norms; per row
+// it sums <= (chunks per band) + (bands) partials instead of the n/16 strips of round 1.  The panel rows it has
+// in hand anyway (V[r,p], W[r,p]) also give the NEXT column's panel dot products up to the reflector scale,
+// which is not known yet:  W^H v' = conj(W[row0',:]) + scale' * W^H a'[row0'+1:]  - so they cost no extra pass
+// over the panel and no extra launch; no atomics anywhere (bit-reproducible).
+#pragma once
+#include "trd_tiles.h"
+
+namespace mak {
+
+constexpr int TRD2_BH = 256;
+constexpr int TRD2_NST = 3;
+template <typename T> struct Trd2SV { static constexpr int value = 1024; };     // entries of v staged per run
+template <> struct Trd2SV<cplx> { static constexpr int value = 512; };
+
+__device__ __forceinline__ double shfl_xor_(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+__device__ __forceinline__ cplx shfl_xor_(cplx v, int o) {
+    return cplx{__shfl_xor_sync(0xffffffffu, v.re, o), __shfl_xor_sync(0xffffffffu, v.im, o)};
+}
+
+// Sum c[0..CNT) over the 32 lanes with 2*(CNT-1)+... shuffles instead of 5*CNT: after the call lane l holds in c[0]
+// the total of entry trd2_owned<CNT>(l) (pairs/quads of lanes hold the same entry).
+template <typename T, int CNT, int O>
+struct MultiReduce {
+    static __device__ __forceinline__ void run(T* c, int lane) {
+        if constexpr (CNT > 1) {
+            constexpr int H = CNT / 2;
+            const bool up = (lane & O) != 0;
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                const T send = up ? c[k] : c[k + H];
+                const T keep = up ? c[k + H] : c[k];
+                c[k] = add_(keep, shfl_xor_(send, O));
+            }
+            MultiReduce<T, H, O / 2>::run(c, lane);
+        } else if constexpr (O >= 1) {
+            c[0] = add_(c[0], shfl_xor_(c[0], O));
+            MultiReduce<T, 1, O / 2>::run(c, lane);
+        }
+    }
+};
+template <int CNT>
+__device__ __forceinline__ int trd2_owned(int lane) {
+    int k = 0, o = 16;
+#pragma unroll
+    for (int h = CNT / 2; h >= 1; h >>= 1, o >>= 1)
+        if (lane & o) k += h;
+    return k;
+}
+// first lane of the group that holds entry k: the bits used by trd2_owned, the rest zero
+template <int CNT>
+__device__ __forceinline__ bool trd2_owner_lane(int lane) {
+    int used = 0, o = 16;
+#pragma unroll
+    for (int h = CNT / 2; h >= 1; h >>= 1, o >>= 1) used |= o;
+    return (lane & ~used) == 0;
+}
+
+__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// v[g] of the current reflector (global row g): 1 at row0, scaled column below, 0 outside the trailing block
+template <typename T>
+__device__ __forceinline__ T trd2_v(const T* __restrict__ Acol, int g, int row0, int n, T scale) {
+    if (g < row0 || g >= n) return zero<T>();
+    if (g == row0) return one<T>();
+    return mul_(Acol[g], scale);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(288, 2)
+trd_symv2_kernel(const __grid_constant__ CUtensorMap tmap, TrdCtx<T> x, int c, int i, int npn) {
+    constexpr int CW = SymvCW<T>::value;
+    constexpr int BH = TRD2_BH;
+    constexpr int NBOX = sizeof(T) / 8;
+    constexpr int RB = BH / NBOX;                  // matrix rows per TMA box
+    constexpr unsigned STAGE_BYTES = BH * CW * sizeof(T);
+    constexpr int SV = Trd2SV<T>::value;
+    constexpr int SVT = SV / CW;                   // tiles per staged run of v
+    pdl_wait_then_trigger();
+    extern __shared__ __align__(128) unsigned char trd2_smem_raw[];
+    unsigned char* ring = trd2_smem_raw + ((128u - (smem_u32(trd2_smem_raw) & 127u)) & 127u);
+    __shared__ T s_v[SV];
+    __shared__ T s_col[2][8][CW];
+    __shared__ double s_q[8];
+    __shared__ __align__(8) uint64_t full_bar[TRD2_NST], empty_bar[TRD2_NST];
+
+    const int n = x.n, row0 = c + 1, mt = n - row0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = blockIdx.x, G = gridDim.x;
+    const TrdTiling tl = trd_tiling(n, row0, BH, CW, G);
+    const int t_beg = min(tl.NT, g * tl.q), t_end = min(tl.NT, t_beg + tl.q);
+
+    if (tid == 0) {
+        for (int st = 0; st < TRD2_NST; ++st) { mbar_init(&full_bar[st], 1); mbar_init(&empty_bar[st], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 8) {
+        // ---- producer: keep the ring full with this chunk's tiles ----
+        if (lane == 0 && t_beg < t_end) {
+            int J = trd_tile_band(tl, t_beg);
+            int S = tl.S0 + (t_beg - trd_band_first_tile(tl, J));
+            int Slast = trd_band_last_strip(tl, J);
+            for (int t = t_beg, it = 0; t < t_end; ++t, ++it) {
+                const int st = it % TRD2_NST, use = it / TRD2_NST;
+                if (use > 0) mbar_wait(&empty_bar[st], (unsigned)((use - 1) & 1));
+                mbar_expect_tx(&full_bar[st], STAGE_BYTES);
+                unsigned char* dst = ring + (size_t)st * STAGE_BYTES;
+#pragma unroll
+                for (int bx = 0; bx < NBOX; ++bx)
+                    tma_load_2d(dst + (size_t)bx * (STAGE_BYTES / NBOX), &tmap, &full_bar[st], (BH * J) * NBOX + bx * 256,
+                                CW * S);
+                if (++S > Slast) { ++J; S = tl.S0; Slast = (J < tl.JB) ? trd_band_last_strip(tl, J) : 0; }
+            }
+        }
+        return;   // the producer warp takes no part in the consumer barriers (bar 1) below
+    }
+
+    // ---- consumers ----
+    // reflector scalars: every warp sums the partial norms itself in the same fixed order
+    double sigma = 0.0;
+    for (int q = lane; q < npn; q += 32) sigma += x.pn[q];
+    sigma = warp_sum(sigma);
+    const T* Acol = x.A + (size_t)c * x.lda;
+    const T alpha = Acol[row0];
+    double beta; T tau, scale;
+    larfgp_scalars<T>(alpha, sigma, beta, tau, scale);
+
+    // V(:, i) over this CTA's row slice (two copies in the panel buffer)
+    {
+        int r_lo, r_hi;
+        trd_slice(tl, g, r_lo, r_hi);
+        const int len = r_hi - r_lo;               // <= 64 (G >= mt / 64 is checked on the host)
+        if (tid < len) {
+            const int gr = row0 + r_lo + tid;
+            const T vq = trd2_v<T>(Acol, gr, row0, n, scale);
+            x.P[(size_t)i * x.ldp + gr] = vq;
+            x.P[(size_t)(2 * x.pw + i) * x.ldp + gr] = vq;
+        }
+    }
+    // panel dot product number g: sum of the partials of the previous w kernel's CTAs (rows >= row0 + 1 of the
+    // unscaled column), times scale, plus the row-row0 term (v[row0] = 1)
+    if (g < 2 * i) {
+        const bool isw = g < i;
+        const int p = isw ? g : g - i;
+        const T* src = x.tpart + (size_t)(isw ? p : TRD_NB + p) * x.tpld;
+        T acc = zero<T>();
+        for (int b = tid; b < npn; b += 256) acc = add_(acc, src[b]);
+        acc = warp_sum(acc);
+        if (lane == 0) s_col[0][warp][0] = acc;
+        bar_consumers();
+        if (tid == 0) {
+            T tot = s_col[0][0][0];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) tot = add_(tot, s_col[0][w][0]);
+            const T first = conj_(x.P[(size_t)(isw ? x.pw + p : p) * x.ldp + row0]);
+            x.t[isw ? p : TRD_NB + p] = add_(first, mul_(scale, tot));
+        }
+        bar_consumers();                           // s_col is reused by the tile loop
+    }
+
+    double qacc = 0.0;
+    if (t_beg < t_end) {
+        int J = trd_tile_band(tl, t_beg);
+        int S = tl.S0 + (t_beg - trd_band_first_tile(tl, J));
+        int Slast = trd_band_last_strip(tl, J);
+        const int rr = tid;                          // row inside the tile (warp w owns rows 32w..32w+31)
+        T vr = zero<T>(), rowacc = zero<T>();
+        double adiag = 0.0;
+        bool band_open = false;
+        int run_left = 0, sv_base = 0;               // staged strips of v: global columns [sv_base, sv_base + CW*run)
+        for (int t = t_beg, it = 0; t < t_end; ++t, ++it) {
+            const int gr = BH * J + rr;
+            if (!band_open) {
+                vr = trd2_v<T>(Acol, gr, row0, n, scale);
+                rowacc = zero<T>();
+                adiag = 0.0;
+                band_open = true;
+                run_left = 0;
+            }
+            if (run_left == 0) {
+                // stage v for the next strips of this band inside the chunk
+                int cnt = min(min(Slast - S + 1, t_end - t), SVT);
+                bar_consumers();                     // everybody is done with the previous contents of s_v
+                sv_base = CW * S;
+                for (int e = tid; e < cnt * CW; e += 256) s_v[e] = trd2_v<T>(Acol, sv_base + e, row0, n, scale);
+                bar_consumers();
+                run_left = cnt;
+            }
+            const int st = it % TRD2_NST, use = it / TRD2_NST;
+            mbar_wait(&full_bar[st], (unsigned)(use & 1));
+            const T* tile = reinterpret_cast<const T*>(ring + (size_t)st * STAGE_BYTES);
+            const T* src = tile + (size_t)(rr / RB) * (CW * RB) + (rr % RB);
+            const T* sv = s_v + (CW * S - sv_base);
+            const int gc0 = CW * S;
+            T colacc[CW];
+            if (gc0 + CW - 1 < BH * J) {
+                // every column of the strip is left of every row of the band: no triangle mask
+#pragma unroll
+                for (int k = 0; k < CW; ++k) {
+                    const T a = src[k * RB];
+                    fma_(rowacc, a, sv[k]);
+                    colacc[k] = zero<T>();
+                    fmac_(colacc[k], a, vr);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < CW; ++k) {
+                    const int gc = gc0 + k;
+                    colacc[k] = zero<T>();
+                    if (gr > gc) {
+                        const T a = src[k * RB];
+                        fma_(rowacc, a, sv[k]);
+                        fmac_(colacc[k], a, vr);
+                    } else if (gr == gc) {
+                        adiag = real_(src[k * RB]);   // Hermitian: real diagonal
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[st]);
+            // column parts of this tile: lanes -> warps -> ycol[J][gc0 .. gc0+CW)
+            MultiReduce<T, CW, 16>::run(colacc, lane);
+            const int par = it & 1;
+            if (trd2_owner_lane<CW>(lane)) s_col[par][warp][trd2_owned<CW>(lane)] = colacc[0];
+            bar_consumers();
+            if (tid < CW) {
+                T v = s_col[par][0][tid];
+#pragma unroll
+                for (int w = 1; w < 8; ++w) v = add_(v, s_col[par][w][tid]);
+                if (gc0 + tid < n) x.ycolp[(size_t)J * x.ldy + gc0 + tid] = v;
+            }
+            --run_left;
+            const bool band_end = (S == Slast) || (t + 1 == t_end);
+            if (band_end) {
+                // row part of this band from this chunk (+ the diagonal term, which lives in exactly one chunk)
+                const T yr = add_(rowacc, scale_(vr, adiag));
+                if (gr < n) x.yrowp[(size_t)g * x.ldy + gr] = yr;
+                T cv = zero<T>();
+                fmac_(cv, vr, rowacc);               // conj(v_r) * (strictly-lower row part)
+                qacc += 2.0 * real_(cv) + adiag * abs2_(vr);
+                band_open = false;
+            }
+            if (S == Slast) { ++J; S = tl.S0; Slast = (J < tl.JB) ? trd_band_last_strip(tl, J) : 0; }
+            else ++S;
+        }
+    }
+    qacc = warp_sum(qacc);
+    if (lane == 0) s_q[warp] = qacc;
+    bar_consumers();
+    if (tid == 0) {
+        double qs = 0.0;
+        for (int w = 0; w < 8; ++w) qs += s_q[w];
+        x.pyv[g] = mk<T>(qs);                        // v^H A22 v is real
+        if (g == 0) {
+            x.tau[c] = tau;
+            x.e[c] = beta;
+            x.d[c] = real_(x.A[(size_t)c * x.lda + c]);
+        }
+    }
+}
+
+// y[r] for global row r: row parts of band(r) from its chunks + column parts from bands >= band(r)
+template <typename T>
+__device__ __forceinline__ T trd2_ysum(const TrdCtx<T>& x, const TrdTiling& tl, int r, int part, int nparts) {
+    const int J = r / tl.BH;
+    int g_lo, g_hi;
+    trd_band_chunks(tl, J, g_lo, g_hi);
+    T s0 = zero<T>(), s1 = zero<T>();
+    for (int gg = g_lo + part; gg <= g_hi; gg += nparts) s0 = add_(s0, x.yrowp[(size_t)gg * x.ldy + r]);
+    for (int JJ = J + part; JJ < tl.JB; JJ += nparts) s1 = add_(s1, x.ycolp[(size_t)JJ * x.ldy + r]);
+    return add_(s0, s1);
+}
+
+// 288 threads: warps 0..7 = 32 rows x 8 groups make ONE pass over the panel rows (V[r,p], W[r,p] feed the w update,
+// the left-looking update of the next column and - second use of the same rows - the next column's panel dot
+// partials) and share the partial sums of y; warp 8 computes the step's scalars concurrently.
+template <typename T>
+__global__ void __launch_bounds__(288)
+trd_w2_kernel(TrdCtx<T> x, int c, int i, int G, int do_next) {
+    pdl_wait_then_trigger();
+    __shared__ T sm[TRD_K2_NG][TRD_K2_ROWS];
+    __shared__ T sm2[TRD_K2_NG][TRD_K2_ROWS];
+    __shared__ T st[2 * TRD_NB];       // t1, t2
+    __shared__ T srow[2 * TRD_NB + 2]; // conj(W[c1,p]), conj(V[c1,p])
+    __shared__ T sa[TRD_K2_ROWS];      // updated next column over this CTA's rows (0 outside its tail)
+    __shared__ T sscal[2];
+    __shared__ double red[32];
+    const int n = x.n, row0 = c + 1, c1 = c + 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool scalar_warp = (warp == 8);
+    const int tx = tid % TRD_K2_ROWS, ty = (tid / TRD_K2_ROWS) % TRD_K2_NG;
+    const int r = row0 + blockIdx.x * TRD_K2_ROWS + tx;
+    const bool live = !scalar_warp && r < n;
+    const T tauc = x.tau[c];
+    const TrdTiling tl = trd_tiling(n, row0, TRD2_BH, SymvCW<T>::value, G);
+    for (int p = tid; p < i; p += blockDim.x) {
+        st[p] = x.t[p];
+        st[TRD_NB + p] = x.t[TRD_NB + p];
+        srow[p] = conj_(x.P[(size_t)(x.pw + p) * x.ldp + c1]);          // conj(W[c1,p])
+        srow[TRD_NB + 1 + p] = conj_(x.P[(size_t)p * x.ldp + c1]);      // conj(V[c1,p])
+    }
+    __syncthreads();
+    T part = zero<T>(), part2 = zero<T>();
+    if (scalar_warp) {
+        // alpha2 = -(tau/2) * w^H v,  w^H v = conj(tau) * (y^H v - t1^H t2 - t2^H t1)
+        T yhv = zero<T>();
+        for (int q = lane; q < G; q += 32) yhv = add_(yhv, x.pyv[q]);
+        T s12 = zero<T>();
+        for (int p = lane; p < i; p += 32) {
+            fmac_(s12, st[p], st[TRD_NB + p]);
+            fmac_(s12, st[TRD_NB + p], st[p]);
+        }
+        // first row of w (row c+1): y - V t1 - W t2
+        T sf = zero<T>();
+        for (int p = lane; p < i; p += 32) {
+            fma_(sf, x.P[(size_t)p * x.ldp + row0], st[p]);
+            fma_(sf, x.P[(size_t)(x.pw + p) * x.ldp + row0], st[TRD_NB + p]);
+        }
+        T y0 = trd2_ysum<T>(x, tl, row0, lane, 32);
+        yhv = warp_sum(yhv);
+        s12 = warp_sum(s12);
+        sf = warp_sum(sf);
+        y0 = warp_sum(y0);
+        if (lane == 0) {
+            const T whv = mul_(conj_(tauc), sub_(yhv, s12));
+            const T alpha2 = neg_(scale_(mul_(tauc, whv), 0.5));
+            sscal[0] = alpha2;
+            sscal[1] = add_(mul_(tauc, sub_(y0, sf)), alpha2);          // w[row0], v[row0] = 1
+        }
+    } else if (live) {
+        for (int p = ty; p < i; p += TRD_K2_NG) {
+            const T vp = x.P[(size_t)p * x.ldp + r], wp = x.P[(size_t)(x.pw + p) * x.ldp + r];
+            fma_(part, vp, st[p]);
+            fma_(part, wp, st[TRD_NB + p]);
+            fma_(part2, vp, srow[p]);
+            fma_(part2, wp, srow[TRD_NB + 1 + p]);
+        }
+        part = sub_(part, trd2_ysum<T>(x, tl, r, ty, TRD_K2_NG));       // w = tau (y - part)
+    }
+    if (!scalar_warp) { sm[ty][tx] = part; sm2[ty][tx] = part2; }
+    if (tid < TRD_K2_ROWS) sa[tid] = zero<T>();
+    __syncthreads();
+    const T alpha2 = sscal[0], wfirst = sscal[1];
+    double nrm = 0.0;
+    T vr = zero<T>(), wr = zero<T>();
+    if (live && ty == 0) {
+        T s = sm[0][tx];
+#pragma unroll
+        for (int gq = 1; gq < TRD_K2_NG; ++gq) s = add_(s, sm[gq][tx]);
+        vr = x.P[(size_t)i * x.ldp + r];
+        wr = add_(mul_(tauc, neg_(s)), mul_(alpha2, vr));
+        x.P[(size_t)(x.pw + i) * x.ldp + r] = wr;                              // W(:, i)
+        x.A[(size_t)c * x.lda + r] = (r == row0) ? mk<T>(x.e[c]) : vr;          // reflector storage
+        if (do_next) {
+            // left-looking update of column c1 = c+1: previous panel columns + the new one
+            T s2 = sm2[0][tx];
+#pragma unroll
+            for (int gq = 1; gq < TRD_K2_NG; ++gq) s2 = add_(s2, sm2[gq][tx]);
+            fma_(s2, vr, conj_(wfirst));   // V[r,i] conj(W[c1,i])
+            s2 = add_(s2, wr);             // W[r,i] conj(V[c1,i]), V[c1,i] = 1
+            T a = sub_(x.A[(size_t)c1 * x.lda + r], s2);
+            if (r == c1) a = mk<T>(real_(a));
+            x.A[(size_t)c1 * x.lda + r] = a;
+            if (r >= c1 + 2) { nrm = abs2_(a); sa[tx] = a; }
+        }
+    }
+    if (!do_next) return;
+    double tot = block_sum<double>(nrm, red);    // (contains the barriers that publish sa)
+    if (tid == 0) x.pn[blockIdx.x] = tot;
+    // panel dot partials of the next column (rows >= c1 + 2 of its unscaled tail): sum_r conj(W[r,p]) a[r],
+    // sum_r conj(V[r,p]) a[r] for p <= i; warp ty reduces over its 32 rows
+    if (scalar_warp) return;
+    const T ar = sa[tx];
+    const size_t blk = blockIdx.x;
+    for (int p = ty; p < i; p += TRD_K2_NG) {
+        T dw = zero<T>(), dv = zero<T>();
+        if (live) {
+            fmac_(dw, x.P[(size_t)(x.pw + p) * x.ldp + r], ar);
+            fmac_(dv, x.P[(size_t)p * x.ldp + r], ar);
+        }
+        dw = warp_sum(dw);
+        dv = warp_sum(dv);
+        if (lane == 0) {
+            x.tpart[(size_t)p * x.tpld + blk] = dw;
+            x.tpart[(size_t)(TRD_NB + p) * x.tpld + blk] = dv;
+        }
+    }
+    if (ty == 0) {
+        T dw = zero<T>(), dv = zero<T>();
+        fmac_(dw, wr, ar);                        // the column of W and V this launch produced (p = i)
+        fmac_(dv, vr, ar);
+        dw = warp_sum(dw);
+        dv = warp_sum(dv);
+        if (lane == 0) {
+            x.tpart[(size_t)i * x.tpld + blk] = dw;
+            x.tpart[(size_t)(TRD_NB + i) * x.tpld + blk] = dv;
+        }
+    }
+}
+
+}  // namespace mak

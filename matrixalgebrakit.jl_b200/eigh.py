@@ -80,8 +80,12 @@ def _heevd_(A, D, V, fixgauge):
 
 
 def _alg_ok(alg):
-    if not isinstance(alg, Algorithm) or alg.name not in ("DivideAndConquer",):
-        raise ValueError(f"eigh: algorithm {alg} is not provided by the B200 driver (use DivideAndConquer)")
+    # heevd!(::B200) and heevr!(::B200) are the same kernels (tridiagonalisation + tridiagonal D&C): the tag names the
+    # contract (ascending values, gauge-fixed vectors), the driver the implementation.  So the BASELINE-named alias
+    # LAPACK_MultipleRelativelyRobustRepresentations(driver = B200()) works; heev!/heevj! are not provided and throw.
+    if not isinstance(alg, Algorithm) or alg.name not in ("DivideAndConquer", "RobustRepresentations"):
+        raise ValueError(f"eigh: algorithm {alg} is not provided by the B200 driver "
+                         "(DivideAndConquer and RobustRepresentations are)")
     resolve_driver(alg.get("driver"), None)
 
 

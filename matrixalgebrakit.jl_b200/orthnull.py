@@ -28,17 +28,20 @@ def _adj(A):
 
 
 def qr_null_(A, N=None, alg=None, **kw):
-    """``qr_null!(A, N, alg)``: orthonormal basis of the cokernel of A (m x (m - min(m,n)))."""
+    """``qr_null!(A, N, alg)``: orthonormal basis of the cokernel of A (m x (m - min(m,n))), by the reference's
+    recipe ``qr_null_householder!`` (qr.jl:236-262): N = [0; I], ``geqrf!``, ``unmqr!('L','N')``.  Destroys A."""
+    from .algorithms import select_algorithm
+    from .qr import _alg_kwargs, qr_null_householder_
     m, n = A.shape
     k = min(m, n)
     if N is not None and tuple(N.shape) != (m, m - k):
         raise ValueError(f"N: size {tuple(N.shape)} != {(m, m - k)}")
-    Rnone = _core.colmajor_empty(0, 0, A.dtype, A.device)
-    Q, _ = qr_full_(A, (_core.colmajor_empty(m, m, A.dtype, A.device), Rnone), alg, **kw)
+    alg = select_algorithm("qr_null", A, alg, **kw)
+    kws = _alg_kwargs(alg)
     if N is None:
         N = _core.colmajor_empty(m, m - k, A.dtype, A.device)
-    N.copy_(Q[:, k:])
-    return N
+    return qr_null_householder_(A, N, positive=kws.get("positive", True), pivoted=kws.get("pivoted", False),
+                                blocksize=kws.get("blocksize", 0))
 
 
 def lq_compact_(A, LQ=None, alg=None, **kw):

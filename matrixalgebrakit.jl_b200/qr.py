@@ -166,3 +166,89 @@ def qr_compact_batched_(As, QRs=None):
     if len(As) == 0:
         return []
     return BatchedQRPlan(As, QRs).run()
+
+
+# ---- L1 (LAPACK-shaped) shims: geqrf! / ungqr! / unmqr!(::B200, ...) ---------------------------------------
+# Call shapes of YALAPACK / YACUSOLVER (yalapack.jl:168-200,550-583,688-735; yacusolver.jl:12-14), as
+# ext/MatrixAlgebraKitCUDAExt/MatrixAlgebraKitCUDAExt.jl:32-34 forwards them; consumers: the blocksize = 1 branch of
+# qr_householder! (qr.jl:160-175) and qr_null_householder! (qr.jl:236-262).
+def geqrf_(A, tau=None):
+    """``geqrf!(A, tau)``: A <- (V below the diagonal, R on and above it), tau[k], k = min(m, n)."""
+    _check_matrix(A)
+    m, n = A.shape
+    k = min(m, n)
+    if tau is None:
+        tau = torch.empty(k, dtype=A.dtype, device=A.device)
+    if tau.dim() != 1 or tau.shape[0] != k or tau.dtype != A.dtype:
+        raise ValueError(f"tau: vector of length {k} and eltype {A.dtype} expected")
+    h = _core.Handle.get(A.device)
+    dt = _core.dtype_code(A)
+    work = h.workspace(h.lib.makb200_geqrf_worksize(h.h, dt, m, n))
+    rc = h.lib.makb200_geqrf(h.h, dt, m, n, _core.ptr(A), _core.ld(A), _core.ptr(tau), _core.ptr(work), work.numel())
+    h.check(rc, "makb200_geqrf")
+    return A, tau
+
+
+def ungqr_(A, tau, Q=None):
+    """``ungqr!``: Q (m x ncols, k <= ncols <= m) = first ncols columns of H_1 ... H_k; A, tau from ``geqrf_``."""
+    _check_matrix(A)
+    m, k = A.shape[0], tau.shape[0]
+    if Q is None:
+        Q = _core.colmajor_empty(m, k, A.dtype, A.device)
+    _check_matrix(Q, "Q")
+    if Q.shape[0] != m or not (k <= Q.shape[1] <= m) or Q.dtype != A.dtype:
+        raise ValueError(f"Q: {m} x ncols with {k} <= ncols <= {m} expected, got {tuple(Q.shape)}")
+    if Q.data_ptr() == A.data_ptr() and Q.numel() > 0:
+        raise ValueError("ungqr_: in-place Q is not supported by the B200 driver")
+    h = _core.Handle.get(A.device)
+    dt = _core.dtype_code(A)
+    work = h.workspace(h.lib.makb200_orgqr_worksize(h.h, dt, m, Q.shape[1], k))
+    rc = h.lib.makb200_orgqr(h.h, dt, m, Q.shape[1], k, _core.ptr(A), _core.ld(A), _core.ptr(tau), _core.ptr(Q), _core.ld(Q),
+                             _core.ptr(work), work.numel())
+    h.check(rc, "makb200_orgqr")
+    return Q
+
+
+def unmqr_(side, trans, A, tau, C):
+    """``unmqr!(side, trans, A, tau, C)``: C <- Q C ('L','N') or Q^H C ('L','C'); Q = H_1 ... H_k from ``geqrf_``.
+    The right side is not provided by the B200 driver (ValueError, like the capability negatives of qr.jl:140-145)."""
+    _check_matrix(A)
+    _check_matrix(C, "C")
+    if side != "L":
+        raise ValueError("unmqr_: the B200 driver provides side = 'L' only")
+    if trans not in ("N", "C") and not (trans == "T" and A.dtype == torch.float64):
+        raise ValueError(f"unmqr_: trans = {trans!r}")
+    m, n = C.shape
+    k = tau.shape[0]
+    if A.shape[0] != m or A.shape[1] < k or C.dtype != A.dtype:
+        raise ValueError("unmqr_: A must be m x (>= k) with the rows and eltype of C")
+    h = _core.Handle.get(A.device)
+    dt = _core.dtype_code(A)
+    work = h.workspace(h.lib.makb200_ormqr_worksize(h.h, dt, m, n, k))
+    rc = h.lib.makb200_ormqr(h.h, dt, 0, _lib.OP_N if trans == "N" else _lib.OP_C, m, n, k, _core.ptr(A), _core.ld(A),
+                             _core.ptr(tau), _core.ptr(C), _core.ld(C), _core.ptr(work), work.numel())
+    h.check(rc, "makb200_ormqr")
+    return C
+
+
+def qr_null_householder_(A, N, positive=True, pivoted=False, blocksize=0):
+    """``qr_null_householder!(driver, A, N)`` (qr.jl:236-262), the reference's recipe: N = [0; I], geqrf!, then
+    unmqr!('L','N') - the m x (m-k) basis comes from k reflectors applied to m-k columns, no m x m Q is formed."""
+    if blocksize > 1:
+        raise ValueError("B200 does not provide a blocked QR decomposition")
+    if pivoted:
+        raise ValueError("B200 does not provide a pivoted QR decomposition")
+    m, n = A.shape
+    k = min(m, n)
+    if tuple(N.shape) != (m, m - k):
+        raise ValueError(f"N: size {tuple(N.shape)} != {(m, m - k)}")
+    if m - k == 0:
+        return N
+    h = _core.Handle.get(A.device)
+    # zero!(N); one!(view(N, k+1:m, 1:m-k)) in one launch: rectangular identity on the bottom block, zeros above
+    N[:k].zero_()
+    bottom = N[k:]
+    rc = h.lib.makb200_tri_init(h.h, _core.dtype_code(N), 0, m - k, m - k, _core.ptr(bottom), _core.ld(N))
+    h.check(rc, "makb200_tri_init")
+    A, tau = geqrf_(A)
+    return unmqr_("L", "N", A, tau, N)

@@ -34,8 +34,12 @@ def check_input(A, USVh):
 
 
 def _alg_ok(alg):
-    if not isinstance(alg, Algorithm) or alg.name != "SVDViaPolar":
-        raise ValueError(f"svd: algorithm {alg} is not provided by the B200 driver (use SVDViaPolar)")
+    # gesdd!/gesdvd!/gesvdp!(::B200) are one implementation (QDWH polar + Hermitian D&C): the tag names the contract
+    # (descending values, gauge-fixed vectors), the driver the implementation, so the BASELINE-named alias
+    # LAPACK_DivideAndConquer(driver = B200()) works.  gesvd!/gesvdj! (QRIteration, Jacobi) are not provided and throw.
+    if not isinstance(alg, Algorithm) or alg.name not in ("SVDViaPolar", "DivideAndConquer", "SafeDivideAndConquer"):
+        raise ValueError(f"svd: algorithm {alg} is not provided by the B200 driver "
+                         "(SVDViaPolar, DivideAndConquer and SafeDivideAndConquer are)")
     resolve_driver(alg.get("driver"), None)
 
 
@@ -89,6 +93,86 @@ def svd_vals_(A, S=None, alg=None, **kw):
 def _copy_input(A):
     from .qr import copy_input
     return copy_input(A)
+
+
+def _gauge_columns_(V):
+    """columns of V *= conj(sign(first entry of maximal modulus)) (common/gauge.jl:12-14,38-45), one launch."""
+    h = _core.Handle.get(V.device)
+    rc = h.lib.makb200_gauge_columns(h.h, _core.dtype_code(V), V.shape[0], V.shape[1], _core.ptr(V), _core.ld(V))
+    h.check(rc, "makb200_gauge_columns")
+    return V
+
+
+def initialize_output_full(A):
+    """``initialize_output(svd_full!, A, alg)`` (svd.jl:74-80): U m x m, S m x n REAL matrix, Vh n x n."""
+    m, n = A.shape
+    return (_core.colmajor_empty(m, m, A.dtype, A.device), _core.colmajor_zeros(m, n, torch.float64, A.device),
+            _core.colmajor_empty(n, n, A.dtype, A.device))
+
+
+def svd_full_(A, USVh=None, alg=None, **kw):
+    """``svd_full!(A, (U,S,Vh), alg)`` (svd.jl:173-176,202-212; LAPACK job 'A').  The leading min(m,n) triplets are
+    the compact decomposition; the extra columns of U (m > n) / rows of Vh (m < n) are an orthonormal basis of the
+    complement, taken the way ``qr_null!`` takes it (k Householder reflectors applied to [0; I], no m x m QR), each
+    with its own gauge (common/gauge.jl:47-67).  ``supports_svd_full(::B200, :svd_polar) = true``.  Destroys A."""
+    from .orthnull import adjoint_
+    from .qr import qr_null_householder_
+    alg = select_algorithm("svd_compact", A, alg, **kw)
+    _alg_ok(alg)
+    if not _core.is_colmajor(A):
+        raise ValueError("A: column-major matrix expected")
+    m, n = A.shape
+    k = min(m, n)
+    if USVh is None:
+        USVh = initialize_output_full(A)
+    U, S, Vh = USVh
+    if tuple(U.shape) != (m, m) or U.dtype != A.dtype or not _core.is_colmajor(U):
+        raise ValueError(f"U: {m} x {m} column-major matrix expected")
+    if tuple(S.shape) != (m, n) or S.dtype != torch.float64:
+        raise ValueError(f"S: real {m} x {n} matrix expected")
+    if tuple(Vh.shape) != (n, n) or Vh.dtype != A.dtype or not _core.is_colmajor(Vh):
+        raise ValueError(f"Vh: {n} x {n} column-major matrix expected")
+    fixgauge = alg.get("fixgauge", True)
+    S.zero_()
+    if A.numel() == 0:   # svd.jl:205: one!(U), zero!(S), one!(Vh)
+        for M in (U, Vh):
+            if M.numel():
+                M.zero_()
+                M.diagonal().fill_(1)
+        return U, S, Vh
+    Sd = torch.empty(k, dtype=torch.float64, device=A.device)
+    Uc = U[:, :k]                                       # leading columns of the caller's U (ld = m)
+    Vc = Vh if m >= n else _core.colmajor_empty(k, n, A.dtype, A.device)   # k x n block: rows of Vh are strided
+    _gesvdp_(A, Sd, Uc, Vc, fixgauge)
+    if m < n:
+        Vh[:k].copy_(Vc)
+    torch.diagonal(S).copy_(Sd)
+    if m > k:
+        N = qr_null_householder_(_clone_cm(Uc), U[:, k:])
+        if fixgauge:
+            _gauge_columns_(N)
+    if n > k:
+        # rows spanning the complement of the row space: (qr_null of Vc^H)^H; column gauge before the adjoint makes the
+        # entry of maximal modulus of every extra row real positive, as the reference's row rule does
+        Vct = adjoint_(_core.colmajor_empty(n, k, A.dtype, A.device), Vc)
+        Nt = qr_null_householder_(Vct, _core.colmajor_empty(n, n - k, A.dtype, A.device))
+        if fixgauge:
+            _gauge_columns_(Nt)
+        Nh = adjoint_(_core.colmajor_empty(n - k, n, A.dtype, A.device), Nt)
+        Vh[k:].copy_(Nh)
+    return U, S, Vh
+
+
+def _clone_cm(M):
+    out = _core.colmajor_empty(M.shape[0], M.shape[1], M.dtype, M.device)
+    out.copy_(M)
+    return out
+
+
+def svd_full(A, alg=None, **kw):
+    return svd_full_(_copy_input(A), None, alg, **kw)
+
+
 
 
 def svd_compact(A, alg=None, **kw):

@@ -182,6 +182,42 @@ def svd_compact(A, alg="DivideAndConquer", fixgauge=True):
     return U, S, Vh
 
 
+def gaugefix_svd_full(U, Vh):
+    """``gaugefix!(svd_full!, U, Vh)`` (src/common/gauge.jl:47-67): leading min(m,n) triplets as in the compact
+    gauge; extra columns of U and extra rows of Vh are each scaled by conj(sign(own entry of maximal modulus))."""
+    m, n = U.shape[1], Vh.shape[0]
+    k = min(m, n)
+    s = _sign(_argmaxabs_cols(U[:, :k]))
+    U[:, :k] *= np.conj(s)[None, :]
+    Vh[:k, :] *= s[:, None]
+    if m > k:
+        s2 = _sign(_argmaxabs_cols(U[:, k:]))
+        U[:, k:] *= np.conj(s2)[None, :]
+    if n > k:
+        s3 = _sign(_argmaxabs_cols(Vh[k:, :].T))
+        Vh[k:, :] *= np.conj(s3)[:, None]
+    return U, Vh
+
+
+def svd_full(A, alg="DivideAndConquer", fixgauge=True):
+    """``svd_full!`` (svd.jl:202-212): gesdd with jobz='A'; S is the m x n matrix with the values on its diagonal."""
+    A = _f(A)
+    m, n = A.shape
+    k = min(m, n)
+    if A.size == 0:
+        return (np.asfortranarray(np.eye(m, dtype=A.dtype)), np.zeros((m, n)), np.asfortranarray(np.eye(n, dtype=A.dtype)))
+    p = _pfx(A)
+    drv = "gesdd" if alg in ("DivideAndConquer", "SafeDivideAndConquer") else "gesvd"
+    U, sv, Vh, info = getattr(_lp, p + drv)(A, compute_uv=1, full_matrices=1)
+    assert info == 0, info
+    U, Vh = np.asfortranarray(U), np.asfortranarray(Vh)
+    S = np.zeros((m, n))
+    S[np.arange(k), np.arange(k)] = sv
+    if fixgauge:
+        gaugefix_svd_full(U, Vh)
+    return U, S, Vh
+
+
 def svd_vals(A):
     """``svd_vals!`` (svd.jl:214-219): gesdd with jobz='N'."""
     A = _f(A)

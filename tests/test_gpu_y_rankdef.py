@@ -5,6 +5,7 @@ isometric factors for any input; so must we.  Sorted after the GPU-verified suit
 test_gpu_y_projections.py)."""
 import numpy as np
 import pytest
+import torch
 
 from oracle import mak_oracle as O
 
@@ -77,3 +78,36 @@ def test_left_polar_and_project_isometric_rank_deficient(m, n, r, dtype):
     P2 = makb200.colmajor_empty(n, n, W.dtype, "cuda:0")
     Wr, Pr = makb200.left_polar_(makb200.to_device(A1), (W2, P2))
     assert Wr is W2 and Pr is P2 and O.orth_err(makb200.to_numpy(W2)) <= tol
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_batched_svd_collapsed_columns_are_completed(dtype):
+    """One-CTA batched SVD: blocks with exactly-zero singular values - a zero block, a zero
+    column, a wide block with a zero row, rank one - must still give an isometric U and Vh (LAPACK contract)."""
+    import makb200
+    rng = np.random.default_rng(3)
+
+    def rnd(m, n):
+        a = rng.standard_normal((m, n))
+        return a + 1j * rng.standard_normal((m, n)) if dtype == "c128" else a
+
+    blocks = []
+    blocks.append(np.zeros((20, 12)))                               # zero block, tall
+    blocks.append(np.zeros((9, 17)))                                # zero block, wide
+    a = rnd(30, 16); a[:, 5] = 0; a[:, 11] = 0; blocks.append(a)    # zero columns
+    a = rnd(14, 40); a[3, :] = 0; blocks.append(a)                  # wide block with a zero row
+    a = np.outer(rnd(24, 1)[:, 0], np.ones(24)); blocks.append(a)   # rank one, square (values exactly repeated)
+    a = rnd(32, 32); a[:, 16:] = 0; blocks.append(a)                # half of the columns zero
+    blocks.append(rnd(25, 25))                                      # a regular block in the same launch
+    blocks = [np.asfortranarray(b.astype(np.complex128 if dtype == "c128" else np.float64)) for b in blocks]
+    outs = makb200.svd_compact_batched_([makb200.to_device(b) for b in blocks])
+    torch.cuda.synchronize()
+    for b, (U, S, Vh) in zip(blocks, outs):
+        Un, Sn, Vhn = makb200.to_numpy(U), S.cpu().numpy(), makb200.to_numpy(Vh)
+        tol = O.tol_for(*b.shape)
+        so = O.svd_vals(b)
+        assert np.all(np.diff(Sn) <= 0) and np.all(Sn >= 0)
+        assert np.max(np.abs(Sn - so)) <= tol * max(so[0], 1.0)
+        assert np.linalg.norm(b - (Un * Sn) @ Vhn) <= tol * max(np.linalg.norm(b), 1.0)
+        assert O.orth_err(Un) <= tol, "U must be an isometry for rank-deficient blocks too"
+        assert O.orth_err(Vhn, "right") <= tol
