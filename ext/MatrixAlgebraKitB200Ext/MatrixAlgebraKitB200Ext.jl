@@ -12,9 +12,10 @@ module MatrixAlgebraKitB200Ext
 
 using MatrixAlgebraKit
 using MatrixAlgebraKit: @algdef, Algorithm, check_input, one!, zero!, diagview
-using MatrixAlgebraKit: B200, Householder, DivideAndConquer, SVDViaPolar, B200_QDWH, TruncationByValue
+using MatrixAlgebraKit: B200, Householder, DivideAndConquer, SafeDivideAndConquer, RobustRepresentations, SVDViaPolar, B200_QDWH, TruncationByValue
 using MatrixAlgebraKit: default_qr_algorithm, default_svd_algorithm, default_eigh_algorithm
-import MatrixAlgebraKit: geqrf!, ungqr!, gesvdp!, heevd!, qr_householder!, left_polar!
+import MatrixAlgebraKit: geqrf!, ungqr!, unmqr!, gesvdp!, gesdd!, gesdvd!, gesvd!, gesvdj!, heevd!, heevr!, heev!, heevj!
+import MatrixAlgebraKit: qr_householder!, qr_null_householder!, left_polar!
 using CUDA
 using LinearAlgebra
 using LinearAlgebra: BlasFloat
@@ -37,7 +38,84 @@ geqrf!(::B200, A::StridedCuMatrix, args...) = (_chk_eltype(A); YAB200.geqrf!(A, 
 ungqr!(::B200, A::StridedCuMatrix, tau, Q = similar(A)) = (_chk_eltype(A); YAB200.ungqr!(A, tau, Q))
 heevd!(::B200, A::StridedCuMatrix, Dd::StridedCuVector, V::StridedCuMatrix; kwargs...) = (_chk_eltype(A); YAB200.heevd!(A, Dd, V))
 gesvdp!(::B200, A::StridedCuMatrix, S::StridedCuVector, U::StridedCuMatrix, Vᴴ::StridedCuMatrix; kwargs...) = (_chk_eltype(A); YAB200.gesvdp!(A, S, U, Vᴴ))
-MatrixAlgebraKit.supports_svd_full(::B200, f::Symbol) = false
+unmqr!(::B200, side, trans, A::StridedCuMatrix, tau, C::StridedCuMatrix) = (_chk_eltype(A); YAB200.unmqr!(side, trans, A, tau, C))
+
+# The LAPACK-named tags with `driver = B200()` (what the deprecated aliases `LAPACK_DivideAndConquer(; driver = B200())`
+# and `LAPACK_MultipleRelativelyRobustRepresentations(; driver = B200())` expand to, svd.jl:352-368, eigh.jl:210-217) are
+# the same kernels: the tag names the contract (sorted values, gauge-fixed vectors), the driver the implementation.
+# Reference bodies that dispatch on these shims: implementations/svd.jl:196-201, eigh.jl:150-156.
+gesdd!(::B200, A::StridedCuMatrix, S::StridedCuVector, U::StridedCuMatrix, Vᴴ::StridedCuMatrix; kwargs...) = (_chk_eltype(A); YAB200.gesvdp!(A, S, U, Vᴴ))
+gesdvd!(::B200, A::StridedCuMatrix, S::StridedCuVector, U::StridedCuMatrix, Vᴴ::StridedCuMatrix; kwargs...) = (_chk_eltype(A); YAB200.gesvdp!(A, S, U, Vᴴ))
+heevr!(::B200, A::StridedCuMatrix, Dd::StridedCuVector, V::StridedCuMatrix; kwargs...) = (_chk_eltype(A); YAB200.heevd!(A, Dd, V))
+# ... and the ones this driver does not provide throw (no MethodError, SURVEY A8)
+for f in (:gesvd!, :gesvdj!, :heev!, :heevj!)
+    @eval $f(d::B200, args...; kwargs...) = throw(ArgumentError(LazyString("driver ", d, " does not provide `", $(QuoteNode(f)), "`")))
+end
+
+# svd_full! (job 'A', implementations/svd.jl:202-212): the compact decomposition in the leading columns / rows, the
+# complement by qr_null_householder! (k reflectors applied to [0; I]), each extra vector with its own gauge
+MatrixAlgebraKit.supports_svd_full(::B200, f::Symbol) = f in (:svd_polar, :divide_and_conquer, :safe_divide_and_conquer)
+function _svd_full_b200!(A, U, S, Vᴴ; fixgauge::Bool = true)
+    isempty(A) && return one!(U), zero!(S), one!(Vᴴ)
+    _chk_eltype(A)
+    m, n = size(A)
+    k = min(m, n)
+    zero!(S)
+    Sd = CUDA.zeros(Float64, k)
+    Uc = view(U, :, 1:k)
+    Vc = m >= n ? Vᴴ : similar(A, (k, n))
+    YAB200.gesvdp!(A, Sd, Uc, Vc; fixgauge)
+    m < n && copyto!(view(Vᴴ, 1:k, :), Vc)
+    diagview(S) .= Sd
+    if m > k
+        N = qr_null_householder!(B200(), copy(Uc), view(U, :, (k + 1):m))
+        fixgauge && YAB200.gauge_columns!(N)
+    end
+    if n > k
+        Nt = qr_null_householder!(B200(), YAB200.adjoint!(similar(A, (n, k)), Vc), similar(A, (n, n - k)))
+        fixgauge && YAB200.gauge_columns!(Nt)      # column gauge before the adjoint = the reference's row rule (gauge.jl:61-64)
+        YAB200.adjoint!(view(Vᴴ, (k + 1):n, :), Nt)
+    end
+    return U, S, Vᴴ
+end
+MatrixAlgebraKit.svd_full_svd_polar!(::B200, A, U, S, Vᴴ; kwargs...) = _svd_full_b200!(A, U, S, Vᴴ; kwargs...)
+MatrixAlgebraKit.svd_full_divide_and_conquer!(::B200, A, U, S, Vᴴ; kwargs...) = _svd_full_b200!(A, U, S, Vᴴ; kwargs...)
+MatrixAlgebraKit.svd_full_safe_divide_and_conquer!(::B200, A, U, S, Vᴴ; kwargs...) = _svd_full_b200!(A, U, S, Vᴴ; kwargs...)
+
+# qr_null! the reference's way (implementations/qr.jl:236-262: N = [0; I], geqrf!, unmqr!('L','N')); the LQ family and
+# left_orth!/right_orth!/left_null!/right_null! reach it through lq_via_qr! / lq_null_via_qr! (lq.jl:130-131,303-327)
+function qr_null_householder!(driver::B200, A::AbstractMatrix, N::AbstractMatrix;
+        positive::Bool = true, pivoted::Bool = false, blocksize::Int = 0)
+    _chk_eltype(A)
+    blocksize <= 1 || throw(ArgumentError(lazy"$driver does not provide a blocked QR decomposition"))
+    pivoted && throw(ArgumentError(lazy"$driver does not provide a pivoted QR decomposition"))
+    m, n = size(A)
+    minmn = min(m, n)
+    zero!(N)
+    one!(view(N, (minmn + 1):m, 1:(m - minmn)))
+    A, τ = geqrf!(driver, A)
+    return unmqr!(driver, 'L', 'N', A, τ, N)
+end
+
+# ---- batched public entry points (SURVEY 8f rank 4): one C call for a vector of blocks, per-block semantics -------
+function MatrixAlgebraKit.qr_compact!(As::Vector{<:B200Mat}, QRs::Vector{<:Tuple}, alg::Householder)
+    Qs, Rs = [qr[1] for qr in QRs], [qr[2] for qr in QRs]
+    foreach((A, qr) -> check_input(qr_compact!, A, qr, alg), As, QRs)
+    YAB200.qr_batched!(As, Qs, Rs)
+    return QRs
+end
+function MatrixAlgebraKit.svd_compact!(As::Vector{<:B200Mat}, USVs::Vector{<:Tuple}, alg::Union{SVDViaPolar, DivideAndConquer})
+    foreach((A, usv) -> check_input(svd_compact!, A, usv, alg), As, USVs)
+    YAB200.svd_batched!(As, [u[1] for u in USVs], [diagview(u[2]) for u in USVs], [u[3] for u in USVs];
+        fixgauge = get(alg.kwargs, :fixgauge, true))
+    return USVs
+end
+function MatrixAlgebraKit.eigh_full!(As::Vector{<:B200Mat}, DVs::Vector{<:Tuple}, alg::DivideAndConquer)
+    foreach((A, dv) -> check_input(eigh_full!, A, dv, alg), As, DVs)
+    YAB200.eigh_batched!(As, [diagview(dv[1]) for dv in DVs], [dv[2] for dv in DVs];
+        fixgauge = get(alg.kwargs, :fixgauge, MatrixAlgebraKit.default_fixgauge()))
+    return DVs
+end
 
 # ---- L2: whole-op QR (factorization + R extraction + Q formation + gauge in one C call) ---------
 function qr_householder!(driver::B200, A::AbstractMatrix, Q::AbstractMatrix, R::AbstractMatrix;
@@ -58,6 +136,18 @@ function MatrixAlgebraKit.eigh_full_divide_and_conquer!(::B200, A, DV; fixgauge:
     _chk_eltype(A)
     YAB200.heevd!(A, diagview(D), V; fixgauge)
     return DV
+end
+function MatrixAlgebraKit.eigh_full_robust_representations!(::B200, A, DV; fixgauge::Bool = MatrixAlgebraKit.default_fixgauge(), kwargs...)
+    D, V = DV
+    _chk_eltype(A)
+    YAB200.heevd!(A, diagview(D), V; fixgauge)
+    return DV
+end
+function MatrixAlgebraKit.svd_compact_divide_and_conquer!(d::B200, A, U, S, Vᴴ; kwargs...)
+    return MatrixAlgebraKit.svd_compact_svd_polar!(d, A, U, S, Vᴴ; kwargs...)
+end
+function MatrixAlgebraKit.svd_compact_safe_divide_and_conquer!(d::B200, A, U, S, Vᴴ; kwargs...)
+    return MatrixAlgebraKit.svd_compact_svd_polar!(d, A, U, S, Vᴴ; kwargs...)
 end
 function MatrixAlgebraKit.svd_compact_svd_polar!(::B200, A, U, S, Vᴴ; fixgauge::Bool = true, kwargs...)
     isempty(A) && return one!(U), zero!(S), one!(Vᴴ)

@@ -367,4 +367,63 @@ function adjoint!(B::StridedCuMatrix{T}, A::StridedCuMatrix{T}) where {T <: B200
     return B
 end
 
+# ---- L1 shim: unmqr!(side, trans, A, tau, C) (yalapack.jl:688-735; yacusolver.jl:14) ---------------------------
+function unmqr!(side::AbstractChar, trans::AbstractChar, A::StridedCuMatrix{T}, tau::StridedCuVector{T}, C::StridedCuMatrix{T}) where {T <: B200Float}
+    side == 'L' || throw(ArgumentError("the B200 driver provides unmqr! for side = 'L' only"))
+    chkstride1(A, C)
+    m, n = size(C)
+    k = length(tau)
+    size(A, 1) == m || throw(DimensionMismatch("A has $(size(A, 1)) rows, C has $m"))
+    h = handle()
+    lw = ccall((:makb200_ormqr_worksize, libmakb200), Csize_t, (Ptr{Cvoid}, Cint, Cint, Cint, Cint), h, dtypecode(T), m, n, k)
+    with_workspace(lw) do work
+        rc = ccall((:makb200_ormqr, libmakb200), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, Cint, CuPtr{T}, Cint, CuPtr{T}, CuPtr{T}, Cint, CuPtr{UInt8}, Csize_t),
+            h, dtypecode(T), 0, opcode(trans), m, n, k, A, max(1, stride(A, 2)), tau, C, max(1, stride(C, 2)), work, lw)
+        chkargsok(rc, "makb200_ormqr")
+    end
+    return C
+end
+
+# ---- gaugefix!(eigh_full!, V) as one launch (common/gauge.jl:38-45) ------------------------------------------------
+function gauge_columns!(V::StridedCuMatrix{T}) where {T <: B200Float}
+    rc = ccall((:makb200_gauge_columns, libmakb200), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, CuPtr{T}, Cint),
+        handle(), dtypecode(T), size(V, 1), size(V, 2), V, max(1, stride(V, 2)))
+    chkargsok(rc, "makb200_gauge_columns")
+    return V
+end
+
+# ---- multi-GPU TSQR: one call, NCCL communicator in rank order = row order of the shards -------------------------
+# `comm` is an `NCCL.Communicator` (NCCL.jl); its raw `ncclComm_t` is `comm.handle`.  Hosts without NCCL.jl can build
+# one with `comm_create` (the 128-byte id from `nccl_unique_id()` on rank 0, shipped by any side channel).
+function nccl_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    rc = ccall((:makb200_nccl_unique_id, libmakb200), Cint, (Ptr{UInt8},), id)
+    rc == 0 || error("makb200_nccl_unique_id failed with code $rc (libnccl.so.2 not loadable)")
+    return id
+end
+function comm_create(nranks::Integer, rank::Integer, id::Vector{UInt8})
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:makb200_comm_create, libmakb200), Cint, (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{UInt8}), ref, nranks, rank, id)
+    rc == 0 || error("makb200_comm_create failed with code $rc")
+    return ref[]
+end
+comm_destroy(comm::Ptr{Cvoid}) = ccall((:makb200_comm_destroy, libmakb200), Cint, (Ptr{Cvoid},), comm)
+
+function tsqr!(comm::Ptr{Cvoid}, nranks::Integer, A::StridedCuMatrix{T}, Q::StridedCuMatrix{T}, R::StridedCuMatrix{T}) where {T <: B200Float}
+    chkstride1(A, Q, R)
+    m, n = size(A)
+    h = handle()
+    lw = ccall((:makb200_tsqr_worksize, libmakb200), Csize_t, (Ptr{Cvoid}, Cint, Cint, Cint, Cint), h, dtypecode(T), m, n, nranks)
+    info = CUDA.zeros(Cint, 1)
+    with_workspace(lw) do work
+        rc = ccall((:makb200_tsqr, libmakb200), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, CuPtr{T}, Cint, CuPtr{T}, Cint, CuPtr{T}, Cint, CuPtr{UInt8}, Csize_t, CuPtr{Cint}),
+            h, comm, dtypecode(T), m, n, A, max(1, stride(A, 2)), Q, max(1, stride(Q, 2)), R, max(1, stride(R, 2)), work, lw, info)
+        chkargsok(rc, "makb200_tsqr")
+    end
+    Array(info)[1] == 0 || error("tsqr!: Cholesky breakdown in the local factorization (kappa(A) too large for CholeskyQR2)")
+    return Q, R
+end
+
 end # module

@@ -76,15 +76,28 @@ struct KernelClock {
         cudaEventRecord(ev[n + 1], s);
         n += 2;
     }
+    // optional per-launch tags (GEMM: m, n, k, flags) for the shape log (env MAKB200_GEMM_LOG=<file>)
+    struct Tag { int m, n, k, flags; double flops; };
+    Tag* tags = nullptr;
+    void tag(int m, int n, int k, int flags, double flops) {
+        if (!on || n_tags_ok() == false) return;
+        if (!tags) tags = (Tag*)malloc(sizeof(Tag) * (MAXEV / 2));
+        tags[this->n / 2] = Tag{m, n, k, flags, flops};
+    }
+    bool n_tags_ok() const { return n + 2 <= MAXEV; }
     // total milliseconds and launch count since the last reset (synchronises)
     void collect(double* ms, int* launches) {
         double t = 0;
+        const char* logp = tags ? getenv("MAKB200_GEMM_LOG") : nullptr;
+        FILE* lf = (logp && logp[0]) ? fopen(logp, "w") : nullptr;
         for (int i = 0; i + 1 < n; i += 2) {
             cudaEventSynchronize(ev[i + 1]);
             float f = 0;
             cudaEventElapsedTime(&f, ev[i], ev[i + 1]);
             t += f;
+            if (lf) fprintf(lf, "%d %d %d %d %.6e %.6f\n", tags[i / 2].m, tags[i / 2].n, tags[i / 2].k, tags[i / 2].flags, tags[i / 2].flops, (double)f);
         }
+        if (lf) fclose(lf);
         *ms = t;
         *launches = n / 2;
         n = 0;

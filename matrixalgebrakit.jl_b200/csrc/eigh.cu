@@ -836,7 +836,11 @@ static void trd_carve(AR& ar, int n, TrdCtx<T>* x, int G = 0) {
     x->v2 = 0;
     x->yrowp = x->ycolp = x->tpart = nullptr;
     x->tpld = 0;
-    if (G >= 2 * TRD_NB && trd2_enabled() && n >= 2 && n <= 64 * G) {
+    // below ~1.5k columns a step is a chain of latencies, not bytes, and the lighter round-1 kernels win
+    // (c128 n = 1024: 13.8 vs 16.4 ms; n = 4096: 149 vs 110 ms): MAKB200_SYMV_V2_MIN moves the switch
+    // (read per call: tests/test_gpu_eigh.py runs the small-n sweep with the switch at 2)
+    const int v2_min = []() { const char* e = getenv("MAKB200_SYMV_V2_MIN"); int v = e ? atoi(e) : 1536; return v < 2 ? 2 : v; }();
+    if (G >= 2 * TRD_NB && trd2_enabled() && n >= v2_min && n <= 64 * G) {
         x->v2 = 1;
         x->yrowp = ar.template get<T>((size_t)G * nn);
         x->ycolp = ar.template get<T>((size_t)((nn + TRD2_BH - 1) / TRD2_BH) * nn);

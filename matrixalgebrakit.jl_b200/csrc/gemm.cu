@@ -42,6 +42,15 @@ template <> struct Cfg<cplx, 2> {
     static constexpr int BM = 64, BN = 64, BK = 8, WM = 32, WN = 32, STAGES = 3, THREADS = 128, MINB = 3;
     static constexpr int SA_MN = BM + 2, SB_MN = BN + 2, S_K = BK + 4;
 };
+// V = 3: 128 x 64 tile, 256 threads, TWO resident CTAs per SM.  For the rank-k updates of the blocked factorizations
+// (K = 64..256: her2k of hetrd, compact-WY trailing updates, Cholesky panel updates) the C tile is read and written
+// once per 8..16 k-tiles, and with one resident CTA that epilogue is not overlapped with anybody's main loop: the
+// 8192 x 8192 x 128 update ran at 15 TF/s against cuBLAS's 31 (profiles/r2_gemm_shapes.txt).
+template <> struct Cfg<double, 3> {
+    static constexpr int BM = 128, BN = 64, BK = 16, WM = 32, WN = 32, STAGES = 4, THREADS = 256, MINB = 2;
+    static constexpr int SA_MN = BM + 4, SB_MN = BN + 4, S_K = BK + 4;
+};
+template <> struct Cfg<cplx, 3> : Cfg<cplx, 2> {};
 template <typename C, typename = void> struct MinBlocks { static constexpr int value = 1; };
 template <typename C> struct MinBlocks<C, decltype((void)C::MINB)> { static constexpr int value = C::MINB; };
 
@@ -239,13 +248,40 @@ gemm_kernel(const GemmProblem<T> p0, const GemmProblem<T>* __restrict__ plist, i
     }
     cp_async_wait<0>();
 
-    // epilogue: thread holds C[row = lr][cols = 2*lc, 2*lc+1] of each 8x8 tile
+    // epilogue: thread holds C[row = lr][cols = 2*lc, 2*lc+1] of each 8x8 tile.  beta != 0: the C values of one row
+    // block are all loaded before the first store - C may alias nothing the compiler can prove, so a fused
+    // load/modify/store loop serialises into NT*2 L2 round trips per row block (the rank-k updates with K = 128 ran at
+    // 15 TF/s because of it, profiles/r2_gemm_shapes.txt)
     const bool partial = (!plist && splitk > 1);
     const bool beta0 = is_zero(p.beta);
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
         int r = m0 + wm + i * 8 + lr;
         if (r >= M) continue;
+        if (partial) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    int c = n0 + wn + j * 8 + lc * 2 + e;
+                    if (c >= N) continue;
+                    T v;
+                    if constexpr (is_cplx<T>::value) v = cplx{e ? acc[i][j].r1 : acc[i][j].r0, e ? acc[i][j].i1 : acc[i][j].i0};
+                    else v = e ? acc[i][j].c1 : acc[i][j].c0;
+                    ws[(size_t)blockIdx.z * M * N + (size_t)c * M + r] = v;
+                }
+            }
+            continue;
+        }
+        T old[NT][2];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                int c = n0 + wn + j * 8 + lc * 2 + e;
+                old[j][e] = (!beta0 && c < N) ? p.C[(size_t)c * p.ldc + r] : zero<T>();
+            }
+        }
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
 #pragma unroll
@@ -255,14 +291,9 @@ gemm_kernel(const GemmProblem<T> p0, const GemmProblem<T>* __restrict__ plist, i
                 T v;
                 if constexpr (is_cplx<T>::value) v = cplx{e ? acc[i][j].r1 : acc[i][j].r0, e ? acc[i][j].i1 : acc[i][j].i0};
                 else v = e ? acc[i][j].c1 : acc[i][j].c0;
-                if (partial) {
-                    ws[(size_t)blockIdx.z * M * N + (size_t)c * M + r] = v;
-                } else {
-                    T* dst = p.C + (size_t)c * p.ldc + r;
-                    T out = mul_(p.alpha, v);
-                    if (!beta0) out = add_(out, mul_(p.beta, *dst));
-                    *dst = out;
-                }
+                T out = mul_(p.alpha, v);
+                if (!beta0) out = add_(out, mul_(p.beta, old[j][e]));
+                p.C[(size_t)c * p.ldc + r] = out;
             }
         }
     }
@@ -296,9 +327,19 @@ __global__ void scale_c_kernel(int M, int N, T beta, T* __restrict__ Cm, int ldc
     }
 }
 
+}  // namespace mak
+#include "gemm_tma.cuh"
+namespace mak {
+
 static int gemm_variant() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("MAKB200_GEMM_VARIANT"); v = e ? atoi(e) : 1; if (v != 0) v = 1; }
+    if (v < 0) { const char* e = getenv("MAKB200_GEMM_VARIANT"); v = e ? atoi(e) : 1; if (v != 0 && v != 3) v = 1; }
+    return v;
+}
+// K at or below which the two-CTA-per-SM configuration is used (0 disables)
+static int gemm_shortk() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MAKB200_GEMM_SHORTK"); v = e ? atoi(e) : 256; if (v < 0) v = 0; }
     return v;
 }
 
@@ -344,6 +385,33 @@ cudaError_t gemm(cudaStream_t stream, int num_sms, int opa, int opb, int m, int 
                  size_t ws_bytes, bool lower) {
     using C = Cfg<T, 0>;  // both variants share the CTA tile
     if (m <= 0 || n <= 0) return cudaSuccess;
+    if (k > 0 && !is_zero(alpha) && (gemm_variant() == 3 || (k <= gemm_shortk() && (size_t)m * n >= (size_t)1 << 20))) {
+        // rank-k update on a large C: two resident CTAs per SM so that one CTA's C read/write overlaps the other's
+        // main loop; no split-K (the output grid fills the machine)
+        using C3 = Cfg<T, 3>;
+        GemmProblem<T> p3;
+        p3.m = m; p3.n = n; p3.k = k;
+        p3.A = A; p3.lda = lda; p3.B = B; p3.ldb = ldb; p3.C = Cm; p3.ldc = ldc;
+        p3.alpha = alpha; p3.beta = beta;
+        p3.conja = (opa == MAKB200_OP_C); p3.conjb = (opb == MAKB200_OP_C);
+        p3.lower = lower ? 1 : 0;
+        dim3 g3((m + C3::BM - 1) / C3::BM, (n + C3::BN - 1) / C3::BN, 1);
+        if (g_clock_gemm.on) {
+            double mn = (double)m * (double)n;
+            if (lower) {
+                mn = 0.0;
+                for (int bx = 0; bx < (int)g3.x; ++bx) {
+                    int rows = min(C3::BM, m - bx * C3::BM);
+                    int ncols = min(n, ((bx * C3::BM + C3::BM + C3::BN - 1) / C3::BN) * C3::BN);
+                    mn += (double)rows * (double)ncols;
+                }
+            }
+            const double fl = 2.0 * mn * (double)k * (is_cplx<T>::value ? 4.0 : 1.0);
+            g_gemm_flops += fl;
+            g_clock_gemm.tag(m, n, k, (opa != MAKB200_OP_N ? 1 : 0) | (opb != MAKB200_OP_N ? 2 : 0) | (lower ? 4 : 0) | 8, fl);
+        }
+        return dispatch2<T, C3>(stream, opa != MAKB200_OP_N, opb != MAKB200_OP_N, g3, p3, nullptr, 1, nullptr);
+    }
     if (k <= 0 || is_zero(alpha)) {
         if (is_one(beta)) return cudaSuccess;
         scale_c_kernel<T><<<min(1024, (int)(((size_t)m * n + 255) / 256)), 256, 0, stream>>>(m, n, beta, Cm, ldc);
@@ -359,8 +427,14 @@ cudaError_t gemm(cudaStream_t stream, int num_sms, int opa, int opb, int m, int 
     // split-K when the output grid cannot fill the machine and K is long
     int splitk = 1;
     int tiles = grid.x * grid.y, ktiles = (k + C::BK - 1) / C::BK;
+    if (lower) {
+        // only the tiles that touch the lower triangle run: split K by THAT count (the Gram matrices of the tall-skinny
+        // QR are 2 x 2 tiles of which 3 run: 3 x 49 CTAs fill 147 of 148 SMs, 4 x 32 left 52 idle)
+        tiles = 0;
+        for (int bx = 0; bx < (int)grid.x; ++bx) tiles += min((int)grid.y, (bx * C::BM + C::BM + C::BN - 1) / C::BN);
+    }
     if (ws && tiles * 2 <= num_sms && ktiles >= 16) {
-        splitk = min(min(num_sms / tiles, ktiles / 8), 32);
+        splitk = min(min(num_sms / tiles, ktiles / 8), 64);
         size_t need = (size_t)splitk * m * n * sizeof(T);
         while (splitk > 1 && need > ws_bytes) { --splitk; need = (size_t)splitk * m * n * sizeof(T); }
         if (splitk < 2) splitk = 1;
@@ -377,9 +451,19 @@ cudaError_t gemm(cudaStream_t stream, int num_sms, int opa, int opb, int m, int 
                 mn += (double)rows * (double)ncols;
             }
         }
-        g_gemm_flops += 2.0 * mn * (double)k * (is_cplx<T>::value ? 4.0 : 1.0);
+        const double fl = 2.0 * mn * (double)k * (is_cplx<T>::value ? 4.0 : 1.0);
+        g_gemm_flops += fl;
+        // flags: bit0 opa != N, bit1 opb != N, bit2 lower, bits 4.. split-K factor
+        g_clock_gemm.tag(m, n, k, (opa != MAKB200_OP_N ? 1 : 0) | (opb != MAKB200_OP_N ? 2 : 0) | (lower ? 4 : 0) | (splitk << 4), fl);
     }
-    cudaError_t e = dispatch<T>(stream, opa != MAKB200_OP_N, opb != MAKB200_OP_N, grid, p, nullptr, splitk, (T*)ws);
+    cudaError_t e = cudaSuccess;
+    bool done = false;
+    if constexpr (!is_cplx<T>::value) {
+        // TMA-fed warp-specialised kernel when both operands can be described by a tensor map (16-byte aligned base
+        // and leading dimension); otherwise (odd leading dimension, e.g. a view starting at an odd row) cp.async
+        done = gemm_tma_try(stream, opa != MAKB200_OP_N, opb != MAKB200_OP_N, grid, p, splitk, (double*)ws, &e);
+    }
+    if (!done) e = dispatch<T>(stream, opa != MAKB200_OP_N, opb != MAKB200_OP_N, grid, p, nullptr, splitk, (T*)ws);
     if (e != cudaSuccess) return e;
     if (splitk > 1) {
         size_t total = (size_t)m * n;

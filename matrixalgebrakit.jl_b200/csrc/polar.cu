@@ -459,6 +459,7 @@ static void polar_carve(makb200_handle* h, AR& ar, int m, int n, bool tall, Pola
     w->sub_bytes = a > b ? a : b;
     w->sub = ar.template get<char>(w->sub_bytes);
     w->ws_bytes = (size_t)h->num_sms * 128 * 128 * sizeof(double);
+    if (nn <= 1024 && w->ws_bytes < 64 * nn * nn * sizeof(T)) w->ws_bytes = 64 * nn * nn * sizeof(T);   // split-K up to 64
     w->ws = ar.template get<char>(w->ws_bytes);
 }
 
@@ -920,6 +921,7 @@ static void cqr_carve(makb200_handle* h, AR& ar, int m, int n, CqrWork<T>* w) {
     w->Tmp = ar.template get<T>(slab * nb);
     w->info = ar.template get<int>(4);
     w->ws_bytes = (size_t)h->num_sms * 128 * 128 * sizeof(double);
+    if (nn <= 1024 && w->ws_bytes < 64 * nn * nn * sizeof(T)) w->ws_bytes = 64 * nn * nn * sizeof(T);   // split-K up to 64
     w->ws = ar.template get<char>(w->ws_bytes);
 }
 
@@ -936,8 +938,9 @@ static int cholqr_pass(makb200_handle* h, int m, int n, const T* X, int ldx, T* 
                        double shift_coef = 0.0) {
     cudaStream_t s = h->stream;
     // G = X^H X (split-K over the long dimension)
+    // (only the lower triangle of G is read by the Cholesky factorization: upper tiles are skipped)
     MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, n, n, m, one<T>(), X, ldx, X, ldx, zero<T>(), w.G, n, w.ws,
-              w.ws_bytes);
+              w.ws_bytes, true);
     if (shift_coef > 0.0) {
         add_shift_kernel<T><<<1, 256, 0, s>>>(n, w.G, shift_coef);
         count_launch();
@@ -1128,7 +1131,7 @@ int tsqr_t(makb200_handle* h, const NcclApi* api, ncclComm_t comm, int m, int n,
         if (rc) return rc;
         pt.mark("pass1");
         MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, n, n, m, one<T>(), A, lda, A, lda, zero<T>(), w.c.G, n,
-                  w.c.ws, w.c.ws_bytes);
+                  w.c.ws, w.c.ws_bytes, true);
         rc = potrf_blocked<T>(h, n, w.c.G, n, w.c.L2, n, w.c.Linv, w.c.info);
         if (rc) return rc;
         lower_clean_kernel<T><<<g, 128, 0, s>>>(n, w.c.L1);

@@ -637,9 +637,12 @@ int orgqr_t(makb200_handle* h, int m, int ncols, int k, const T* A, int lda, con
     MAK_LAUNCH_CHECK(h, "copy_v_kernel");
             MAK_GEMM(h, s, h->num_sms, MAKB200_OP_C, MAKB200_OP_N, jb, jb, mp, one<T>(), w.Vw, mp, w.Vw, mp, zero<T>(),
                      w.G, nb, w.ws, w.ws_bytes);
-            larft_diag_kernel<T><<<1, 128, larft_smem<T>(jb), s>>>(jb, tau + j0, w.Tall + (size_t)b * nb * nb, nb, w.G, nb);
+            {
+                // through larft_launch: it opts the kernel in to > 48 KB of dynamic shared memory (jb = 128 needs 66 KB)
+                cudaError_t e = larft_launch<T>(s, jb, tau + j0, w.Tall + (size_t)b * nb * nb, nb, w.G, nb);
+                if (e != cudaSuccess) return cuda_fail(h, e, "larft_diag_kernel");
+            }
             count_launch();
-        MAK_LAUNCH_CHECK(h, "larft_diag_kernel");
         }
     }
     return orgqr_blocked<T>(h, m, ncols, k, A, lda, Q, ldq, w);

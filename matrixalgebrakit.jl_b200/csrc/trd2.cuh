@@ -310,20 +310,39 @@ trd_w2_kernel(TrdCtx<T> x, int c, int i, int G, int do_next) {
     const int tx = tid % TRD_K2_ROWS, ty = (tid / TRD_K2_ROWS) % TRD_K2_NG;
     const int r = row0 + blockIdx.x * TRD_K2_ROWS + tx;
     const bool live = !scalar_warp && r < n;
-    const T tauc = x.tau[c];
     const TrdTiling tl = trd_tiling(n, row0, TRD2_BH, SymvCW<T>::value, G);
+    // every global load of this thread is issued before the first barrier (the launch is a chain of L2 latencies, not
+    // bytes): the panel rows stay in registers for all three uses
+    constexpr int PU = TRD_NB / TRD_K2_NG;            // panel columns per thread
+    T vpr[PU], wpr[PU];
+#pragma unroll
+    for (int u = 0; u < PU; ++u) {
+        const int p = ty + u * TRD_K2_NG;
+        const bool on = live && p < i;
+        vpr[u] = on ? x.P[(size_t)p * x.ldp + r] : zero<T>();
+        wpr[u] = on ? x.P[(size_t)(x.pw + p) * x.ldp + r] : zero<T>();
+    }
+    const T ysum = live ? trd2_ysum<T>(x, tl, r, ty, TRD_K2_NG) : zero<T>();
+    const bool fin = live && ty == 0;
+    const T vr = fin ? x.P[(size_t)i * x.ldp + r] : zero<T>();
+    const T anext = (fin && do_next) ? x.A[(size_t)c1 * x.lda + r] : zero<T>();
+    const T tauc = x.tau[c];
+    const double ec = x.e[c];
     for (int p = tid; p < i; p += blockDim.x) {
         st[p] = x.t[p];
         st[TRD_NB + p] = x.t[TRD_NB + p];
         srow[p] = conj_(x.P[(size_t)(x.pw + p) * x.ldp + c1]);          // conj(W[c1,p])
         srow[TRD_NB + 1 + p] = conj_(x.P[(size_t)p * x.ldp + c1]);      // conj(V[c1,p])
     }
+    T yhv = zero<T>(), y0 = zero<T>();
+    if (scalar_warp) {
+        for (int q = lane; q < G; q += 32) yhv = add_(yhv, x.pyv[q]);
+        y0 = trd2_ysum<T>(x, tl, row0, lane, 32);
+    }
     __syncthreads();
     T part = zero<T>(), part2 = zero<T>();
     if (scalar_warp) {
         // alpha2 = -(tau/2) * w^H v,  w^H v = conj(tau) * (y^H v - t1^H t2 - t2^H t1)
-        T yhv = zero<T>();
-        for (int q = lane; q < G; q += 32) yhv = add_(yhv, x.pyv[q]);
         T s12 = zero<T>();
         for (int p = lane; p < i; p += 32) {
             fmac_(s12, st[p], st[TRD_NB + p]);
@@ -335,7 +354,6 @@ trd_w2_kernel(TrdCtx<T> x, int c, int i, int G, int do_next) {
             fma_(sf, x.P[(size_t)p * x.ldp + row0], st[p]);
             fma_(sf, x.P[(size_t)(x.pw + p) * x.ldp + row0], st[TRD_NB + p]);
         }
-        T y0 = trd2_ysum<T>(x, tl, row0, lane, 32);
         yhv = warp_sum(yhv);
         s12 = warp_sum(s12);
         sf = warp_sum(sf);
@@ -347,29 +365,31 @@ trd_w2_kernel(TrdCtx<T> x, int c, int i, int G, int do_next) {
             sscal[1] = add_(mul_(tauc, sub_(y0, sf)), alpha2);          // w[row0], v[row0] = 1
         }
     } else if (live) {
-        for (int p = ty; p < i; p += TRD_K2_NG) {
-            const T vp = x.P[(size_t)p * x.ldp + r], wp = x.P[(size_t)(x.pw + p) * x.ldp + r];
-            fma_(part, vp, st[p]);
-            fma_(part, wp, st[TRD_NB + p]);
-            fma_(part2, vp, srow[p]);
-            fma_(part2, wp, srow[TRD_NB + 1 + p]);
+#pragma unroll
+        for (int u = 0; u < PU; ++u) {
+            const int p = ty + u * TRD_K2_NG;
+            if (p < i) {
+                fma_(part, vpr[u], st[p]);
+                fma_(part, wpr[u], st[TRD_NB + p]);
+                fma_(part2, vpr[u], srow[p]);
+                fma_(part2, wpr[u], srow[TRD_NB + 1 + p]);
+            }
         }
-        part = sub_(part, trd2_ysum<T>(x, tl, r, ty, TRD_K2_NG));       // w = tau (y - part)
+        part = sub_(part, ysum);                                        // w = tau (y - part)
     }
     if (!scalar_warp) { sm[ty][tx] = part; sm2[ty][tx] = part2; }
     if (tid < TRD_K2_ROWS) sa[tid] = zero<T>();
     __syncthreads();
     const T alpha2 = sscal[0], wfirst = sscal[1];
     double nrm = 0.0;
-    T vr = zero<T>(), wr = zero<T>();
-    if (live && ty == 0) {
+    T wr = zero<T>();
+    if (fin) {
         T s = sm[0][tx];
 #pragma unroll
         for (int gq = 1; gq < TRD_K2_NG; ++gq) s = add_(s, sm[gq][tx]);
-        vr = x.P[(size_t)i * x.ldp + r];
         wr = add_(mul_(tauc, neg_(s)), mul_(alpha2, vr));
         x.P[(size_t)(x.pw + i) * x.ldp + r] = wr;                              // W(:, i)
-        x.A[(size_t)c * x.lda + r] = (r == row0) ? mk<T>(x.e[c]) : vr;          // reflector storage
+        x.A[(size_t)c * x.lda + r] = (r == row0) ? mk<T>(ec) : vr;              // reflector storage
         if (do_next) {
             // left-looking update of column c1 = c+1: previous panel columns + the new one
             T s2 = sm2[0][tx];
@@ -377,7 +397,7 @@ trd_w2_kernel(TrdCtx<T> x, int c, int i, int G, int do_next) {
             for (int gq = 1; gq < TRD_K2_NG; ++gq) s2 = add_(s2, sm2[gq][tx]);
             fma_(s2, vr, conj_(wfirst));   // V[r,i] conj(W[c1,i])
             s2 = add_(s2, wr);             // W[r,i] conj(V[c1,i]), V[c1,i] = 1
-            T a = sub_(x.A[(size_t)c1 * x.lda + r], s2);
+            T a = sub_(anext, s2);
             if (r == c1) a = mk<T>(real_(a));
             x.A[(size_t)c1 * x.lda + r] = a;
             if (r >= c1 + 2) { nrm = abs2_(a); sa[tx] = a; }
@@ -391,17 +411,19 @@ trd_w2_kernel(TrdCtx<T> x, int c, int i, int G, int do_next) {
     if (scalar_warp) return;
     const T ar = sa[tx];
     const size_t blk = blockIdx.x;
-    for (int p = ty; p < i; p += TRD_K2_NG) {
-        T dw = zero<T>(), dv = zero<T>();
-        if (live) {
-            fmac_(dw, x.P[(size_t)(x.pw + p) * x.ldp + r], ar);
-            fmac_(dv, x.P[(size_t)p * x.ldp + r], ar);
-        }
-        dw = warp_sum(dw);
-        dv = warp_sum(dv);
-        if (lane == 0) {
-            x.tpart[(size_t)p * x.tpld + blk] = dw;
-            x.tpart[(size_t)(TRD_NB + p) * x.tpld + blk] = dv;
+#pragma unroll
+    for (int u = 0; u < PU; ++u) {
+        const int p = ty + u * TRD_K2_NG;
+        if (p < i) {                              // uniform per warp
+            T dw = zero<T>(), dv = zero<T>();
+            fmac_(dw, wpr[u], ar);
+            fmac_(dv, vpr[u], ar);
+            dw = warp_sum(dw);
+            dv = warp_sum(dv);
+            if (lane == 0) {
+                x.tpart[(size_t)p * x.tpld + blk] = dw;
+                x.tpart[(size_t)(TRD_NB + p) * x.tpld + blk] = dv;
+            }
         }
     }
     if (ty == 0) {

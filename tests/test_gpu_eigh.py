@@ -191,3 +191,15 @@ def test_eigh_batched_pooled_threads(dtype):
     torch.cuda.synchronize()
     for a, (D, V) in zip(As0, DVs):
         _check(a, D.cpu().numpy(), makb200.to_numpy(V), vec_cmp=False)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_eigh_persistent_column_kernels_small_n_sweep(dtype, monkeypatch):
+    """The persistent TMA column kernels (csrc/trd2.cuh) are the default from n = 1536 up; here the switch is moved to
+    n = 2 so that every tile-geometry corner (one tile, partial bands, chunks with no work, odd n -> unaligned lda ->
+    round-1 kernels) runs against the oracle.  The geometry itself is replayed on the CPU in tests/test_trd_tiles_cpu.py."""
+    monkeypatch.setenv("MAKB200_SYMV_V2_MIN", "2")
+    for n in list(range(2, 36, 3)) + [64, 66, 128, 130, 256, 258, 300, 512, 514, 600, 1024, 1026]:
+        A = O.rand_hermitian(n, dtype, seed=500 + n)
+        w, V = _eigh(A)
+        _check(A, w, V, vec_cmp=False)
