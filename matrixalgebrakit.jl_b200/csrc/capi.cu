@@ -16,6 +16,9 @@
 #include <atomic>
 #include <cstring>
 #include <thread>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 using mak::cplx;
 
@@ -49,6 +52,8 @@ int makb200_create(makb200_handle_t** out, int device) {
         }
     }
     h->no_lookahead = false;
+    h->graph_cache = nullptr;
+    h->defect_dev = nullptr;
     h->stage = nullptr;
     h->stage_bytes = 0;
     if (cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming) != cudaSuccess) { delete h; return MAKB200_ERR_CUDA; }
@@ -67,8 +72,11 @@ int makb200_create(makb200_handle_t** out, int device) {
     return 0;
 }
 
+static void graph_cache_destroy(makb200_handle_t* h);
+
 int makb200_destroy(makb200_handle_t* h) {
     if (!h) return -1;
+    graph_cache_destroy(h);
     cudaStreamDestroy(h->aux_stream);
     cudaEventDestroy(h->stage_ev);
     if (h->stage) cudaFreeHost(h->stage);
@@ -225,7 +233,7 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
 }
 // measured on B200 (round 1, 257-512 c128 blocks): 8 streams / 8 threads 229 svd/s, 561 eigh/s;
 // 32 streams / 16 threads 176 / 351 (driver lock contention) -> defaults 8 / 8
-static int pool_streams() { static int v = env_int("MAKB200_POOL_STREAMS", 8, 1, NPOOL); return v; }
+static int pool_streams() { static int v = env_int("MAKB200_POOL_STREAMS", 8, 1, 32); return v; }
 static int pool_threads() {   // host threads feeding the stream pool (1 = single-threaded round robin)
     static int v = -1;
     if (v < 0) {
@@ -241,9 +249,12 @@ static int pool_threads() {   // host threads feeding the stream pool (1 = singl
     return v;
 }
 // Workspace of a pooled call: one slice per stream.
-static size_t pooled_worksize(size_t per_block, size_t nbig) {
-    const size_t np = nbig < (size_t)pool_streams() ? nbig : (size_t)pool_streams();
-    return (per_block + 512) * np;
+static int graph_slots();
+static size_t pooled_worksize(size_t per_block, size_t nbig, size_t staging = 0) {
+    size_t np = (size_t)pool_streams();
+    if (staging > 0 && (size_t)graph_slots() > np) np = (size_t)graph_slots();   // graph-replayed path: more, cheaper slots
+    if (nbig < np) np = nbig;
+    return (per_block + staging + 1024) * np;
 }
 
 template <typename F>
@@ -311,6 +322,147 @@ static int run_pooled(makb200_handle_t* h, const std::vector<int>& big, char* wo
         MAK_CUDA(h, cudaStreamWaitEvent(main, h->pool_ev[s], 0));
     }
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Graph replay of the per-block paths.  A mid-size block (65..512) runs the single-matrix svd_t / eigh_t: a serial
+// chain of ~1000 tiny launches (n = 384 c128: 1326 launches, 22 ms), so the pooled path is bound by what host threads
+// can launch.  Blocks of one shape run the SAME launch sequence; here it is captured ONCE per (op, shape, stream slot)
+// against fixed staging buffers in that slot's workspace slice and replayed per block between a copy-in and a copy-out:
+// per block the host issues one cudaGraphLaunch and a few small copies instead of a thousand launches, the tensor maps
+// of the GEMMs are encoded once at capture, and the GPU runs the chain back to back.  Shapes are dealt to the slots
+// (longest processing time first) so every graph is reused for all blocks of its shape.
+// The rank-defect check of svd_t is a host read: captured sequences store the indicator per block instead, ONE read
+// after the batch finds deficient blocks, and those are redone through the uncaptured path (the staged copy-in leaves
+// the caller's A intact).
+// ---------------------------------------------------------------------------------------------------------------
+struct GraphEntry { cudaGraphExec_t exec; void* stage; };
+struct GraphCache {
+    std::mutex mu;
+    std::map<std::tuple<int, int, int, int, int, int>, GraphEntry> map;   // (kind, dtype, m, n, flags, slot)
+};
+static GraphCache* graph_cache(makb200_handle_t* h) {
+    if (!h->graph_cache) h->graph_cache = new GraphCache();
+    return (GraphCache*)h->graph_cache;
+}
+static void graph_cache_destroy(makb200_handle_t* h) {
+    if (!h->graph_cache) return;
+    GraphCache* c = (GraphCache*)h->graph_cache;
+    for (auto& kv : c->map) cudaGraphExecDestroy(kv.second.exec);
+    delete c;
+    h->graph_cache = nullptr;
+}
+// MEASURED (round 2, profiles/r2_batched_graphs.log): replay works and is parity-green, but the throughput does not move
+// (257-512 c128 svd: 263 vs 231 blocks/s): with 32 chains in flight the device itself dispatches only ~350 k kernels/s
+// (263 blocks/s x 1326 kernels), so the bound is the NUMBER of kernels per block, not who launches them.  Replay stays
+// opt-in (MAKB200_BATCH_GRAPHS=1); the default remains the launch-per-kernel pool, which has no first-call capture cost.
+static bool graphs_enabled() {
+    const char* e = getenv("MAKB200_BATCH_GRAPHS");   // read per call: tests run both paths
+    return e && e[0] == '1';
+}
+static int graph_slots() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MAKB200_GRAPH_SLOTS"); v = e ? atoi(e) : 32; if (v < 1) v = 1; if (v > MAK_NPOOL) v = MAK_NPOOL; }
+    return v;
+}
+
+// One shape group of a graph-replayed batch: blocks `idx` (indices into the caller's arrays) of shape m x n.
+struct ShapeGroup { int m, n; std::vector<int> idx; double cost; };
+
+// capture(hh, m, n, stage, stage_bytes) must issue the whole per-block sequence on hh->stream against the staging area;
+// copy_in(hh, i, m, n, stage) / copy_out(hh, i, m, n, stage, ordinal) move block i in and out (ordinal = position in `big`).
+// Returns 0, an error code, or -100000 when capture is not possible (caller falls back to run_pooled).
+template <typename FC, typename FI, typename FO>
+static int run_graphed(makb200_handle_t* h, int kind, int dtype, int flags, std::vector<ShapeGroup>& groups, char* work,
+                       size_t lwork, size_t slot_bytes, FC capture, FI copy_in, FO copy_out) {
+    if (groups.empty()) return 0;
+    int np = graph_slots();
+    if ((size_t)np > groups.size()) np = (int)groups.size();
+    if (slot_bytes == 0 || lwork / slot_bytes < 1) return -100000;
+    if ((size_t)np > lwork / slot_bytes) np = (int)(lwork / slot_bytes);
+    const size_t slice = slot_bytes & ~(size_t)255;
+    // shapes -> slots, longest processing time first
+    std::sort(groups.begin(), groups.end(), [](const ShapeGroup& a, const ShapeGroup& b) { return a.cost > b.cost; });
+    std::vector<std::vector<int>> slot_groups(np);
+    {
+        std::vector<double> load(np, 0.0);
+        for (size_t g = 0; g < groups.size(); ++g) {
+            int best = 0;
+            for (int s = 1; s < np; ++s) if (load[s] < load[best]) best = s;
+            slot_groups[best].push_back((int)g);
+            load[best] += groups[g].cost;
+        }
+    }
+    cudaStream_t main = h->stream;
+    MAK_CUDA(h, cudaEventRecord(h->pool_ev[0], main));
+    for (int s = 0; s < np; ++s) MAK_CUDA(h, cudaStreamWaitEvent(h->pool[s], h->pool_ev[0], 0));
+    GraphCache* cache = graph_cache(h);
+    const int nthreads = pool_threads() < np ? pool_threads() : np;
+    std::vector<int> rcs(nthreads, 0);
+    std::vector<makb200_handle> hs(nthreads, *h);
+    auto worker = [&](int t) {
+        if (cudaSetDevice(h->device) != cudaSuccess) { rcs[t] = MAKB200_ERR_CUDA; return; }
+        makb200_handle* hh = &hs[t];
+        hh->no_lookahead = true;
+        hh->err[0] = 0;
+        for (int s = t; s < np && rcs[t] == 0; s += nthreads) {
+            hh->stream = h->pool[s];
+            char* stage = work + (size_t)s * slice;
+            for (int g : slot_groups[s]) {
+                const ShapeGroup& sg = groups[g];
+                const auto key = std::make_tuple(kind, dtype, sg.m, sg.n, flags, s);
+                cudaGraphExec_t exec = nullptr;
+                {
+                    std::lock_guard<std::mutex> lk(cache->mu);
+                    auto it = cache->map.find(key);
+                    if (it != cache->map.end()) {
+                        if (it->second.stage == (void*)stage) exec = it->second.exec;
+                        else { cudaGraphExecDestroy(it->second.exec); cache->map.erase(it); }   // the caller's workspace moved
+                    }
+                }
+                if (!exec) {
+                    cudaGraph_t graph = nullptr;
+                    if (cudaStreamBeginCapture(hh->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { rcs[t] = -100000; break; }
+                    const int rc = capture(hh, sg.m, sg.n, stage, slice);
+                    const cudaError_t ce = cudaStreamEndCapture(hh->stream, &graph);
+                    if (rc != 0 || ce != cudaSuccess || !graph) {
+                        if (graph) cudaGraphDestroy(graph);
+                        cudaGetLastError();
+                        rcs[t] = rc > 0 ? rc : -100000;
+                        break;
+                    }
+                    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+                    cudaGraphDestroy(graph);
+                    if (ie != cudaSuccess) { cudaGetLastError(); rcs[t] = -100000; break; }
+                    std::lock_guard<std::mutex> lk(cache->mu);
+                    cache->map[key] = GraphEntry{exec, (void*)stage};
+                }
+                for (size_t q = 0; q < sg.idx.size() && rcs[t] == 0; ++q) {
+                    int rc = copy_in(hh, sg.idx[q], sg.m, sg.n, stage);
+                    if (rc == 0 && cudaGraphLaunch(exec, hh->stream) != cudaSuccess) rc = mak::cuda_fail(hh, cudaGetLastError(), "cudaGraphLaunch");
+                    if (rc == 0) rc = copy_out(hh, sg.idx[q], sg.m, sg.n, stage);
+                    if (rc) rcs[t] = rc;
+                    else mak::count_launch();
+                }
+                if (rcs[t]) break;
+            }
+        }
+    };
+    if (nthreads > 1) {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t) th.emplace_back(worker, t);
+        for (auto& x : th) x.join();
+    } else {
+        worker(0);
+    }
+    int rc = 0;
+    for (int t = 0; t < nthreads && rc == 0; ++t)
+        if (rcs[t]) { rc = rcs[t]; memcpy(h->err, hs[t].err, sizeof(h->err)); }
+    // join the pool streams on the error path too: kernels of other blocks may still be running on them
+    for (int s = 0; s < np; ++s) {
+        if (cudaEventRecord(h->pool_ev[s], h->pool[s]) == cudaSuccess) cudaStreamWaitEvent(main, h->pool_ev[s], 0);
+    }
+    return rc;
 }
 
 // size classes of a batched QR: three warp-kernel classes (m,n <= 32 by row capacity), the one-CTA
@@ -956,10 +1108,91 @@ static int svd_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int
     // blocks too large for one CTA's shared memory: QDWH + D&C path, one block at a time
     char* wbig = (char*)work + ar.off;
     size_t lbig = lwork > ar.off ? lwork - ar.off : 0;
-    return run_pooled(h, big, wbig, lbig, [&](makb200_handle_t* hh, char* w, size_t lw, int i) {
+    auto per_block = [&](makb200_handle_t* hh, char* w, size_t lw, int i) {
         return mak::svd_t<T>(hh, m[i], n[i], (T*)A[i], lda[i], (double*)S[i], U ? (T*)U[i] : nullptr, ldu ? ldu[i] : 0,
                              Vh ? (T*)Vh[i] : nullptr, ldvh ? ldvh[i] : 0, fixgauge, 2.2e-16, w, lw, nullptr);
-    });
+    };
+    if (big.empty()) return 0;
+    const bool vectors = (U != nullptr && Vh != nullptr);
+    if (graphs_enabled() && big.size() >= 4) {
+        // graph replay: one captured svd_t per (shape, slot) against staging buffers
+        size_t st_a = 0, st_u = 0, st_v = 0, st_s = 0, wmax = 0;
+        std::map<std::pair<int, int>, int> gid;
+        std::vector<ShapeGroup> groups;
+        std::vector<int> ordinal(batch, -1);
+        for (size_t q = 0; q < big.size(); ++q) {
+            const int i = big[q], k = m[i] < n[i] ? m[i] : n[i];
+            ordinal[i] = (int)q;
+            st_a = std::max(st_a, (size_t)m[i] * n[i]);
+            st_u = std::max(st_u, (size_t)m[i] * k);
+            st_v = std::max(st_v, (size_t)k * n[i]);
+            st_s = std::max(st_s, (size_t)k);
+            wmax = std::max(wmax, mak::svd_worksize_t<T>(h, m[i], n[i]));
+            auto key = std::make_pair(m[i], n[i]);
+            auto it = gid.find(key);
+            if (it == gid.end()) {
+                gid[key] = (int)groups.size();
+                groups.push_back(ShapeGroup{m[i], n[i], {}, 0.0});
+                it = gid.find(key);
+            }
+            groups[it->second].idx.push_back(i);
+            groups[it->second].cost += (double)m[i] * n[i] * k + 2.0e5 * k;   // flops-ish + launch-chain term
+        }
+        const size_t oA = 0, oU = mak::align_up(st_a * sizeof(T), 256), oV = oU + mak::align_up(st_u * sizeof(T), 256),
+                     oS = oV + mak::align_up(st_v * sizeof(T), 256), oF = oS + mak::align_up(st_s * sizeof(double), 256),
+                     oW = oF + 256;
+        const size_t slot_bytes = oW + mak::align_up(wmax, 256) + 256;
+        // per-block rank-defect indicators, collected with ONE read after the batch
+        double* defects = nullptr;
+        size_t tail = mak::align_up(sizeof(double) * big.size(), 256);
+        if (lbig > tail) { defects = (double*)(wbig + lbig - tail); lbig -= tail; }
+        if (defects) {
+            MAK_CUDA(h, cudaMemsetAsync(defects, 0, sizeof(double) * big.size(), h->stream));
+            const size_t esz = sizeof(T);
+            int rc = run_graphed(h, /*kind*/ 0, std::is_same<T, double>::value ? 0 : 1, (fixgauge ? 1 : 0) | (vectors ? 2 : 0), groups,
+                wbig, lbig, slot_bytes,
+                [&](makb200_handle_t* hh, int mm, int nn, char* st, size_t) {
+                    const int k = mm < nn ? mm : nn;
+                    hh->defect_dev = (double*)(st + oF);
+                    const int r = mak::svd_t<T>(hh, mm, nn, (T*)(st + oA), mm, (double*)(st + oS), vectors ? (T*)(st + oU) : nullptr, mm,
+                                                vectors ? (T*)(st + oV) : nullptr, k, fixgauge, 2.2e-16, st + oW, slot_bytes - oW, nullptr);
+                    hh->defect_dev = nullptr;
+                    return r;
+                },
+                [&](makb200_handle_t* hh, int i, int mm, int nn, char* st) {
+                    MAK_CUDA(hh, cudaMemsetAsync(st + oF, 0, sizeof(double), hh->stream));
+                    MAK_CUDA(hh, cudaMemcpy2DAsync(st + oA, (size_t)mm * esz, A[i], (size_t)lda[i] * esz, (size_t)mm * esz, nn,
+                                                   cudaMemcpyDeviceToDevice, hh->stream));
+                    return 0;
+                },
+                [&](makb200_handle_t* hh, int i, int mm, int nn, char* st) {
+                    const int k = mm < nn ? mm : nn;
+                    MAK_CUDA(hh, cudaMemcpyAsync(S[i], st + oS, sizeof(double) * k, cudaMemcpyDeviceToDevice, hh->stream));
+                    if (vectors) {
+                        MAK_CUDA(hh, cudaMemcpy2DAsync(U[i], (size_t)ldu[i] * esz, st + oU, (size_t)mm * esz, (size_t)mm * esz, k,
+                                                       cudaMemcpyDeviceToDevice, hh->stream));
+                        MAK_CUDA(hh, cudaMemcpy2DAsync(Vh[i], (size_t)ldvh[i] * esz, st + oV, (size_t)k * esz, (size_t)k * esz, nn,
+                                                       cudaMemcpyDeviceToDevice, hh->stream));
+                        MAK_CUDA(hh, cudaMemcpyAsync(defects + ordinal[i], st + oF, sizeof(double), cudaMemcpyDeviceToDevice, hh->stream));
+                    }
+                    return 0;
+                });
+            if (rc == 0) {
+                if (!vectors) return 0;
+                // deficient blocks (U not isometric): redo through the uncaptured path, which repairs U
+                std::vector<double> hd(big.size());
+                MAK_CUDA(h, cudaMemcpyAsync(hd.data(), defects, sizeof(double) * big.size(), cudaMemcpyDeviceToHost, h->stream));
+                MAK_CUDA(h, cudaStreamSynchronize(h->stream));
+                std::vector<int> redo;
+                for (size_t q = 0; q < big.size(); ++q)
+                    if (hd[q] > 1e-6) redo.push_back(big[q]);
+                return run_pooled(h, redo, wbig, lbig, per_block);
+            }
+            if (rc != -100000) return rc;
+            // capture not possible here: fall through to the launch-per-kernel pool
+        }
+    }
+    return run_pooled(h, big, wbig, lbig, per_block);
 }
 
 extern "C" {
@@ -968,6 +1201,7 @@ size_t makb200_svd_batched_worksize(makb200_handle_t* h, int dtype, int batch, c
     if (!h || !dtype_ok(dtype) || batch < 0 || (batch > 0 && (!m || !n))) return 0;
     size_t esz = dtype == MAKB200_F64 ? sizeof(double) : sizeof(cplx);
     size_t bytes = mak::align_up(sizeof(mak::SvdBlockDesc<cplx>) * (size_t)(batch > 0 ? batch : 1), 256), big = 0, nbig = 0;
+    size_t st_a = 0, st_u = 0, st_v = 0, st_s = 0;
     for (int i = 0; i < batch; ++i) {
         if (m[i] <= 0 || n[i] <= 0) continue;
         if (mak::batched_svd_smem_bytes(m[i], n[i], esz) > mak::batched_svd_max_smem_bytes()) {
@@ -975,9 +1209,17 @@ size_t makb200_svd_batched_worksize(makb200_handle_t* h, int dtype, int batch, c
                                             : mak::svd_worksize_t<cplx>(h, m[i], n[i]);
             if (w > big) big = w;
             ++nbig;
+            const size_t k = (size_t)(m[i] < n[i] ? m[i] : n[i]);
+            st_a = std::max(st_a, (size_t)m[i] * n[i]);
+            st_u = std::max(st_u, (size_t)m[i] * k);
+            st_v = std::max(st_v, k * (size_t)n[i]);
+            st_s = std::max(st_s, k);
         }
     }
-    return bytes + pooled_worksize(big, nbig) + 256;
+    // graph-replayed path: staging copies of A, U, Vh, S per slot + one defect indicator per big block
+    const size_t staging = mak::align_up(st_a * esz, 256) + mak::align_up(st_u * esz, 256) + mak::align_up(st_v * esz, 256) +
+                           mak::align_up(st_s * 8, 256) + 1024;
+    return bytes + pooled_worksize(big, nbig, staging) + mak::align_up(sizeof(double) * nbig, 256) + 512;
 }
 
 int makb200_svd_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch, const int* m, const int* n,
@@ -1069,11 +1311,54 @@ static int eigh_batched_t(makb200_handle_t* h, int fixgauge, int batch, const in
     }
     char* wbig = (char*)work + ar.off;
     size_t lbig = lwork > ar.off ? lwork - ar.off : 0;
-    return run_pooled(h, big, wbig, lbig, [&](makb200_handle_t* hh, char* w, size_t lw, int i) {
+    auto per_block = [&](makb200_handle_t* hh, char* w, size_t lw, int i) {
         return mak::eigh_t<T>(hh, n[i], (T*)A[i], lda[i], (double*)W[i], V ? (T*)V[i] : (T*)nullptr, V ? ldv[i] : n[i],
                               fixgauge, w, lw, nullptr, 0,
                               pre[i].d ? &pre[i] : nullptr);   // V == NULL: values only (Sturm K-section)
-    });
+    };
+    if (graphs_enabled() && !bhetrd_enabled() && big.size() >= 4) {
+        // graph replay: one captured eigh_t per (n, slot) against staging buffers (see run_graphed)
+        size_t nmax = 0, wmax = 0;
+        std::map<int, int> gid;
+        std::vector<ShapeGroup> groups;
+        for (int i : big) {
+            nmax = std::max(nmax, (size_t)n[i]);
+            wmax = std::max(wmax, mak::eigh_worksize_t<T>(h, n[i]));
+            auto it = gid.find(n[i]);
+            if (it == gid.end()) {
+                gid[n[i]] = (int)groups.size();
+                groups.push_back(ShapeGroup{n[i], n[i], {}, 0.0});
+                it = gid.find(n[i]);
+            }
+            groups[it->second].idx.push_back(i);
+            groups[it->second].cost += (double)n[i] * n[i] * n[i] + 2.0e5 * n[i];
+        }
+        const size_t esz = sizeof(T);
+        const size_t oA = 0, oV = mak::align_up(nmax * nmax * esz, 256), oD = oV + mak::align_up(nmax * nmax * esz, 256),
+                     oW = oD + mak::align_up(nmax * 8, 256);
+        const size_t slot_bytes = oW + mak::align_up(wmax, 256) + 256;
+        const bool vectors = V != nullptr;
+        int rc = run_graphed(h, /*kind*/ 1, std::is_same<T, double>::value ? 0 : 1, (fixgauge ? 1 : 0) | (vectors ? 2 : 0), groups, wbig,
+            lbig, slot_bytes,
+            [&](makb200_handle_t* hh, int nn, int, char* st, size_t) {
+                return mak::eigh_t<T>(hh, nn, (T*)(st + oA), nn, (double*)(st + oD), vectors ? (T*)(st + oV) : (T*)nullptr, nn, fixgauge,
+                                      st + oW, slot_bytes - oW, nullptr, 0, nullptr);
+            },
+            [&](makb200_handle_t* hh, int i, int nn, int, char* st) {
+                MAK_CUDA(hh, cudaMemcpy2DAsync(st + oA, (size_t)nn * esz, A[i], (size_t)lda[i] * esz, (size_t)nn * esz, nn,
+                                               cudaMemcpyDeviceToDevice, hh->stream));
+                return 0;
+            },
+            [&](makb200_handle_t* hh, int i, int nn, int, char* st) {
+                MAK_CUDA(hh, cudaMemcpyAsync(W[i], st + oD, sizeof(double) * nn, cudaMemcpyDeviceToDevice, hh->stream));
+                if (vectors)
+                    MAK_CUDA(hh, cudaMemcpy2DAsync(V[i], (size_t)ldv[i] * esz, st + oV, (size_t)nn * esz, (size_t)nn * esz, nn,
+                                                   cudaMemcpyDeviceToDevice, hh->stream));
+                return 0;
+            });
+        if (rc != -100000) return rc;
+    }
+    return run_pooled(h, big, wbig, lbig, per_block);
 }
 
 extern "C" {
@@ -1082,6 +1367,7 @@ size_t makb200_eigh_batched_worksize(makb200_handle_t* h, int dtype, int batch, 
     if (!h || !dtype_ok(dtype) || batch < 0 || (batch > 0 && !n)) return 0;
     size_t esz = dtype == MAKB200_F64 ? sizeof(double) : sizeof(cplx);
     size_t bytes = mak::align_up(sizeof(mak::EighBlockDesc<cplx>) * (size_t)(batch > 0 ? batch : 1), 256), big = 0, nbig = 0;
+    size_t nmax_big = 0;
     bool any = false;
     for (int i = 0; i < batch; ++i) {
         if (n[i] <= 0) continue;
@@ -1090,12 +1376,15 @@ size_t makb200_eigh_batched_worksize(makb200_handle_t* h, int dtype, int batch, 
             if (w > big) big = w;
             any = true;
             ++nbig;
+            if ((size_t)n[i] > nmax_big) nmax_big = (size_t)n[i];
             // d, e, tau of the one-launch tridiagonalisation (MAKB200_BHETRD) + its descriptor
             bytes += 2 * mak::align_up(sizeof(double) * (size_t)n[i], 256) + mak::align_up(sizeof(cplx) * (size_t)n[i], 256) +
                      sizeof(mak::BhetrdDesc<cplx>);
         }
     }
-    return bytes + (any ? pooled_worksize(big, nbig) : 0) + 512;
+    // graph-replayed path: staging copies of A, V, W per slot
+    const size_t staging = 2 * mak::align_up(nmax_big * nmax_big * esz, 256) + mak::align_up(nmax_big * 8, 256) + 1024;
+    return bytes + (any ? pooled_worksize(big, nbig, staging) : 0) + 512;
 }
 
 int makb200_eigh_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch, const int* n, void* const* A,

@@ -17,7 +17,7 @@ namespace mak {
 // ---------------------------------------------------------------------------------------
 }  // namespace mak
 
-constexpr int MAK_NPOOL = 32;
+constexpr int MAK_NPOOL = 64;
 struct makb200_handle {
     int device;
     cudaStream_t stream;
@@ -25,12 +25,15 @@ struct makb200_handle {
     int max_cluster;  // largest usable cluster size for the panel kernel
     cudaStream_t aux_stream;   // internal second stream (look-ahead in the blocked QR)
     cudaEvent_t ev[8];         // fork/join and look-ahead events
-    cudaStream_t pool[32];     // stream pool: mid-size blocks of a batch run concurrently (MAK_NPOOL)
-    cudaEvent_t pool_ev[32];
+    cudaStream_t pool[MAK_NPOOL];     // stream pool: mid-size blocks of a batch run concurrently (MAK_NPOOL)
+    cudaEvent_t pool_ev[MAK_NPOOL];
     bool no_lookahead;         // set while a pooled call is in flight (aux stream/events are shared)
     void* stage;               // pinned host staging for descriptor uploads (batched entry points)
     size_t stage_bytes;
     cudaEvent_t stage_ev;      // recorded after the last upload out of `stage`
+    void* graph_cache;         // replayable CUDA graphs of the per-block paths (capi.cu: GraphCache), shared by handle copies
+    double* defect_dev;        // non-null (set while a per-block path is captured into a graph): svd_tall copies its rank
+                               // defect indicator here instead of reading it on the host
     char err[256];
 };
 

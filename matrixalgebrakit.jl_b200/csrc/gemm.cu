@@ -458,11 +458,9 @@ cudaError_t gemm(cudaStream_t stream, int num_sms, int opa, int opb, int m, int 
     }
     cudaError_t e = cudaSuccess;
     bool done = false;
-    if constexpr (!is_cplx<T>::value) {
-        // TMA-fed warp-specialised kernel when both operands can be described by a tensor map (16-byte aligned base
-        // and leading dimension); otherwise (odd leading dimension, e.g. a view starting at an odd row) cp.async
-        done = gemm_tma_try(stream, opa != MAKB200_OP_N, opb != MAKB200_OP_N, grid, p, splitk, (double*)ws, &e);
-    }
+    // TMA-fed warp-specialised kernel when both operands can be described by a tensor map (16-byte aligned base
+    // and leading dimension); otherwise (Float64 with an odd leading dimension or a view starting at an odd row) cp.async
+    done = gemm_tma_try(stream, opa != MAKB200_OP_N, opb != MAKB200_OP_N, grid, p, splitk, (T*)ws, &e);
     if (!done) e = dispatch<T>(stream, opa != MAKB200_OP_N, opb != MAKB200_OP_N, grid, p, nullptr, splitk, (T*)ws);
     if (e != cudaSuccess) return e;
     if (splitk > 1) {

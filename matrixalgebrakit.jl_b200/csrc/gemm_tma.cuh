@@ -233,6 +233,164 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// ComplexF64: the same pipeline on interleaved (re, im) operands.  One 16-byte swizzle chunk = one complex number, a
+// 128-byte row = 8 of them = BK.  64 x 128 x 8 tiles, 8 math warps (32 x 32 each, four real DMMAs per complex product).
+//   MN-major operand: boxes of 8 (mn) x 8 (k), box b = mn / 8, row = k, chunk = (mn % 8) ^ k
+//   K-major operand : one box of 8 (k) x BM|BN (mn), row = mn, chunk = k ^ (mn % 8)
+// The two DMMA steps of a stage take k = 2 lc + s: a quarter-warp (8 lanes, one 128-byte wavefront of LDS.128) then
+// reads 8 distinct chunks in both layouts.  The tensor maps describe the operands as Float64 with a doubled inner
+// dimension (there is no complex element type).
+constexpr int TGC_BM = 64, TGC_BN = 128, TGC_BK = 8, TGC_ST = 6;
+constexpr int TGC_MATH_WARPS = 8, TGC_THREADS = TGC_MATH_WARPS * 32;
+constexpr unsigned TGC_A_BYTES = TGC_BM * TGC_BK * 16, TGC_B_BYTES = TGC_BN * TGC_BK * 16;
+constexpr unsigned TGC_STAGE_BYTES = TGC_A_BYTES + TGC_B_BYTES;
+
+__device__ __forceinline__ cplx tg_lds_c(unsigned addr) {
+    cplx v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.re), "=d"(v.im) : "r"(addr));
+    return v;
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(TGC_THREADS, 1)
+gemm_tma_kernel_c(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const GemmProblem<cplx> p, int splitk, cplx* __restrict__ ws) {
+    constexpr int BM = TGC_BM, BN = TGC_BN, BK = TGC_BK, ST = TGC_ST;
+    constexpr int WM = 32, MT = 4, NT = 4, WARPS_M = BM / WM;
+    extern __shared__ __align__(1024) unsigned char tg_smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[ST], empty_bar[ST];
+    const unsigned ring = (tg_smem_u32(tg_smem_raw) + 1023u) & ~1023u;
+
+    const int M = p.m, N = p.n, K = p.k;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    if (m0 >= M || n0 >= N) return;
+    if (p.lower && n0 >= m0 + BM) return;
+    const int ktiles = (K + BK - 1) / BK;
+    int kt_beg = 0, kt_end = ktiles;
+    if (splitk > 1) {
+        const int per = (ktiles + splitk - 1) / splitk;
+        kt_beg = blockIdx.z * per;
+        kt_end = min(ktiles, kt_beg + per);
+        if (kt_end < kt_beg) kt_end = kt_beg;
+    }
+    const int nkt = kt_end - kt_beg;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int st = 0; st < ST; ++st) { tg_mbar_init(&full_bar[st], 1); tg_mbar_init(&empty_bar[st], TGC_MATH_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int it) {
+        const int st = it % ST;
+        tg_mbar_expect_tx(&full_bar[st], TGC_STAGE_BYTES);
+        const int k0 = (kt_beg + it) * BK;
+        const unsigned sa = ring + (unsigned)st * TGC_STAGE_BYTES, sb = sa + TGC_A_BYTES;
+        if (TA) tg_tma_2d(sa, &tmA, &full_bar[st], 2 * k0, m0);                    // K-major: {8 k, 64 m}
+        else {
+#pragma unroll
+            for (int b = 0; b < BM / 8; ++b) tg_tma_2d(sa + b * 1024, &tmA, &full_bar[st], 2 * (m0 + 8 * b), k0);
+        }
+        if (!TB) tg_tma_2d(sb, &tmB, &full_bar[st], 2 * k0, n0);                   // K-major: {8 k, 128 n}
+        else {
+#pragma unroll
+            for (int b = 0; b < BN / 8; ++b) tg_tma_2d(sb + b * 1024, &tmB, &full_bar[st], 2 * (n0 + 8 * b), k0);
+        }
+    };
+    if (tid == 0) {
+        for (int it = 0; it < ST - 1 && it < nkt; ++it) issue(it);
+    }
+
+    const int wm = (warp % WARPS_M) * WM, wn = (warp / WARPS_M) * 32;
+    const int lr = lane >> 2, lc = lane & 3;
+    unsigned offA[2], offB[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int k = 2 * lc + s;
+        offA[s] = TA ? (unsigned)((wm + lr) * 128 + ((k ^ lr) << 4)) : (unsigned)((wm / 8) * 1024 + k * 128 + ((lr ^ k) << 4));
+        offB[s] = !TB ? (unsigned)((wn + lr) * 128 + ((k ^ lr) << 4)) : (unsigned)((wn / 8) * 1024 + k * 128 + ((lr ^ k) << 4));
+    }
+    double acc[MT][NT][4];   // r0, r1, i0, i1
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.0;
+    const double sgnA = p.conja ? -1.0 : 1.0, sgnB = p.conjb ? -1.0 : 1.0;
+
+    for (int it = 0; it < nkt; ++it) {
+        const int st = it % ST, use = it / ST;
+        if (tid == 0) {
+            const int nx = it + ST - 1;
+            if (nx < nkt) {
+                if (nx >= ST) tg_mbar_wait(&empty_bar[nx % ST], (unsigned)(((nx / ST) - 1) & 1));
+                issue(nx);
+            }
+        }
+        __syncwarp();
+        tg_mbar_wait(&full_bar[st], (unsigned)(use & 1));
+        const unsigned sa = ring + (unsigned)st * TGC_STAGE_BYTES, sb = sa + TGC_A_BYTES;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            cplx af[MT], bf[NT];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) af[i] = tg_lds_c(sa + offA[s] + (unsigned)(i * 1024));   // 8 rows or one box further
+#pragma unroll
+            for (int j = 0; j < NT; ++j) bf[j] = tg_lds_c(sb + offB[s] + (unsigned)(j * 1024));
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                const double ar = af[i].re, ai = af[i].im * sgnA, nai = -ai;
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const double br = bf[j].re, bi = bf[j].im * sgnB;
+                    dmma(acc[i][j][0], acc[i][j][1], ar, br);
+                    dmma(acc[i][j][0], acc[i][j][1], nai, bi);
+                    dmma(acc[i][j][2], acc[i][j][3], ar, bi);
+                    dmma(acc[i][j][2], acc[i][j][3], ai, br);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) tg_mbar_arrive(&empty_bar[st]);
+    }
+
+    const bool partial = splitk > 1;
+    const bool beta0 = is_zero(p.beta);
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const int r = m0 + wm + i * 8 + lr;
+        if (r >= M) continue;
+        if (partial) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = n0 + wn + j * 8 + lc * 2 + e;
+                    if (c < N) ws[(size_t)blockIdx.z * M * N + (size_t)c * M + r] = cplx{acc[i][j][e], acc[i][j][2 + e]};
+                }
+            continue;
+        }
+        cplx old[NT][2];
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = n0 + wn + j * 8 + lc * 2 + e;
+                old[j][e] = (!beta0 && c < N) ? p.C[(size_t)c * p.ldc + r] : cplx{0.0, 0.0};
+            }
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = n0 + wn + j * 8 + lc * 2 + e;
+                if (c >= N) continue;
+                cplx out = mul_(p.alpha, cplx{acc[i][j][e], acc[i][j][2 + e]});
+                if (!beta0) out = add_(out, mul_(p.beta, old[j][e]));
+                p.C[(size_t)c * p.ldc + r] = out;
+            }
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 tg_encoder() {
     static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
@@ -299,6 +457,43 @@ static bool gemm_tma_try(cudaStream_t stream, bool ta, bool tb, dim3 grid, const
     else if (ta && !tb) *err = tg_launch<true, false>(stream, grid, tmA, tmB, p, splitk, ws);
     else if (!ta && tb) *err = tg_launch<false, true>(stream, grid, tmA, tmB, p, splitk, ws);
     else *err = tg_launch<true, true>(stream, grid, tmA, tmB, p, splitk, ws);
+    return true;
+}
+
+
+template <bool TA, bool TB>
+static cudaError_t tgc_launch(cudaStream_t stream, dim3 grid, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                              const GemmProblem<cplx>& p, int splitk, cplx* ws) {
+    constexpr size_t smem = (size_t)TGC_ST * TGC_STAGE_BYTES + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel_c<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    g_clock_gemm.begin(stream);
+    gemm_tma_kernel_c<TA, TB><<<grid, TGC_THREADS, smem, stream>>>(tmA, tmB, p, splitk, ws);
+    g_clock_gemm.end(stream);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ComplexF64 operands are always 16-byte aligned with a 16-byte multiple leading dimension
+static bool gemm_tma_try(cudaStream_t stream, bool ta, bool tb, dim3 grid, const GemmProblem<cplx>& p, int splitk,
+                         cplx* ws, cudaError_t* err) {
+    if (!tg_enabled() || p.lda <= 0 || p.ldb <= 0) return false;
+    if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.B) & 15)) return false;
+    CUtensorMap tmA, tmB;
+    // as Float64 with a doubled inner dimension; leading dimensions in doubles = 2 ld
+    const bool okA = ta ? tg_make_map(&tmA, (const double*)p.A, 2 * p.k, p.m, 2 * p.lda, 2 * TGC_BK, TGC_BM)
+                        : tg_make_map(&tmA, (const double*)p.A, 2 * p.m, p.k, 2 * p.lda, 16, TGC_BK);
+    const bool okB = tb ? tg_make_map(&tmB, (const double*)p.B, 2 * p.n, p.k, 2 * p.ldb, 16, TGC_BK)
+                        : tg_make_map(&tmB, (const double*)p.B, 2 * p.k, p.n, 2 * p.ldb, 2 * TGC_BK, TGC_BN);
+    if (!okA || !okB) return false;
+    if (!ta && !tb) *err = tgc_launch<false, false>(stream, grid, tmA, tmB, p, splitk, ws);
+    else if (ta && !tb) *err = tgc_launch<true, false>(stream, grid, tmA, tmB, p, splitk, ws);
+    else if (!ta && tb) *err = tgc_launch<false, true>(stream, grid, tmA, tmB, p, splitk, ws);
+    else *err = tgc_launch<true, true>(stream, grid, tmA, tmB, p, splitk, ws);
     return true;
 }
 

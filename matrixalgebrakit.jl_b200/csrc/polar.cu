@@ -58,6 +58,73 @@ __global__ void fro2_final_kernel(int np, const double* __restrict__ partial, do
     if (threadIdx.x == 0) out[0] = t;
 }
 
+// max |re|, |im| over the matrix (two-stage), for the overflow/underflow-safe scaling of X0: the plain sum of
+// squares underflows to 0 for ||A||_F < 1e-154 and overflows for entries > 1e154 (LAPACK's lassq scales; so do we)
+template <typename T>
+__global__ void absmax_partial_kernel(int m, int n, const T* __restrict__ A, int lda, double* __restrict__ partial) {
+    __shared__ double red[32];
+    size_t total = (size_t)m * n;
+    double mx = 0.0;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(idx % m), c = (int)(idx / m);
+        const T a = A[(size_t)c * lda + r];
+        const double v = fmax(fabs(real_(a)), fabs(imag_(a)));
+        mx = (v > mx || v != v) ? v : mx;     // NaN propagates
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t = fmax(t, red[i]);
+        partial[blockIdx.x] = t;
+    }
+}
+// out[0] = 1 / max (1 for a zero or non-finite matrix)
+__global__ void absmax_final_kernel(int np, const double* __restrict__ partial, double* out) {
+    __shared__ double red[32];
+    double mx = 0.0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) mx = fmax(mx, partial[i]);
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t = fmax(t, red[i]);
+        out[0] = (t > 0.0 && isfinite(t)) ? 1.0 / t : 1.0;
+    }
+}
+// sum |A_ij * pre[0]|^2 partials
+template <typename T>
+__global__ void fro2_pre_partial_kernel(int m, int n, const T* __restrict__ A, int lda, const double* __restrict__ pre,
+                                        double* __restrict__ partial) {
+    __shared__ double red[32];
+    const double f = pre[0];
+    size_t total = (size_t)m * n;
+    double s = 0.0;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(idx % m), c = (int)(idx / m);
+        s += abs2_(scale_(A[(size_t)c * lda + r], f));
+    }
+    double t = block_sum<double>(s, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+// X = (A * pre[0]) / sqrt(norm2[0])
+template <typename T>
+__global__ void scale_copy_pre_kernel(int m, int n, const T* __restrict__ A, int lda, T* __restrict__ X, int ldx,
+                                      const double* __restrict__ pre, const double* __restrict__ norm2) {
+    const double nn = norm2[0], f = pre[0];
+    const double inv = nn > 0.0 ? 1.0 / sqrt(nn) : 1.0;
+    size_t total = (size_t)m * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(idx % m), c = (int)(idx / m);
+        X[(size_t)c * ldx + r] = scale_(scale_(A[(size_t)c * lda + r], f), inv);
+    }
+}
+
 // X = A / sqrt(norm2[0])   (X0 = A / ||A||_F); a zero matrix is copied unchanged
 template <typename T>
 __global__ void scale_copy_kernel(int m, int n, const T* __restrict__ A, int lda, T* __restrict__ X, int ldx,
@@ -579,10 +646,14 @@ int polar_qdwh_t(makb200_handle* h, int m, int n, T* A, int lda, T* W, int ldw, 
         src = w.R0; lds = n; ms = n;
     }
     const int np = grid_for2((size_t)ms * n, h->num_sms) < 1024 ? grid_for2((size_t)ms * n, h->num_sms) : 1024;
-    fro2_partial_kernel<T><<<np, 256, 0, s>>>(ms, n, src, lds, w.partial);
+    // X0 = A / ||A||_F, with the entries pre-scaled by 1 / max|a_ij| (scal[7]) so that neither a tiny nor a huge A
+    // loses the sum of squares; W is scale-invariant and P is formed from the unscaled A, so nothing is undone later
+    absmax_partial_kernel<T><<<np, 256, 0, s>>>(ms, n, src, lds, w.partial);
+    absmax_final_kernel<<<1, 256, 0, s>>>(np, w.partial, w.scal + 7);
+    fro2_pre_partial_kernel<T><<<np, 256, 0, s>>>(ms, n, src, lds, w.scal + 7, w.partial);
     fro2_final_kernel<<<1, 256, 0, s>>>(np, w.partial, w.scal);
-    scale_copy_kernel<T><<<grid_for2((size_t)ms * n, h->num_sms), 256, 0, s>>>(ms, n, src, lds, w.X, ms, w.scal);
-    count_launch(3);
+    scale_copy_pre_kernel<T><<<grid_for2((size_t)ms * n, h->num_sms), 256, 0, s>>>(ms, n, src, lds, w.X, ms, w.scal + 7, w.scal);
+    count_launch(5);
     MAK_LAUNCH_CHECK(h, "scale_copy_kernel");
     pt.mark("prep");
     // ---- scaling and conditioning estimates (large matrices, default l0 only) -------------------
@@ -776,8 +847,14 @@ static int svd_tall(makb200_handle* h, int m, int n, int r, T* A, int lda, doubl
         count_launch();
         MAK_LAUNCH_CHECK(h, "col_norm_defect_kernel");
         double defect = 0.0;
-        MAK_CUDA(h, cudaMemcpyAsync(&defect, w.flag, sizeof(double), cudaMemcpyDeviceToHost, s));
-        MAK_CUDA(h, cudaStreamSynchronize(s));
+        if (h->defect_dev) {
+            // graph-replayed batched path (capi.cu): no host read inside the captured sequence; the caller collects the
+            // indicator of every block with one read and sends deficient blocks through this function again, uncaptured
+            MAK_CUDA(h, cudaMemcpyAsync(h->defect_dev, w.flag, sizeof(double), cudaMemcpyDeviceToDevice, s));
+        } else {
+            MAK_CUDA(h, cudaMemcpyAsync(&defect, w.flag, sizeof(double), cudaMemcpyDeviceToHost, s));
+            MAK_CUDA(h, cudaStreamSynchronize(s));
+        }
         if (defect > 1e-6) {
             rc = qr_fused_t<T>(h, MAKB200_QR_COMPACT, m, r, U, ldu, w.Wp, m, (T*)nullptr, 0, w.sub, w.sub_bytes);
             if (rc) return rc;

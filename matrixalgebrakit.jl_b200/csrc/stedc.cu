@@ -326,6 +326,26 @@ static void stedc_carve(AR& ar, int n, DcBuffers* b, double** Zw, double** Pack,
     *S = ar.template get<double>(nn * nn);
 }
 
+// The tree tables (leaf boundaries, cut positions, the merges of a level) depend on n only.  They are written by
+// kernels, not uploaded: a host-to-device copy of a stack/vector buffer captured into a CUDA graph would be re-read
+// from that (dead) host address at every replay (capi.cu replays this whole sequence per block).
+__global__ void dc_tree_kernel(int n, int nleaf, int* __restrict__ bnd, int* __restrict__ cuts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nleaf) return;
+    const int b = (int)((long long)i * n / nleaf);
+    bnd[i] = b;
+    if (i >= 1 && i < nleaf) cuts[i - 1] = b;
+}
+__global__ void dc_merge_fill_kernel(int nm, int step, const int* __restrict__ bnd, Merge* __restrict__ merges) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nm) return;
+    Merge m{};
+    m.lo = bnd[i * step];
+    m.mid = bnd[i * step + step / 2];
+    m.hi = bnd[(i + 1) * step];
+    merges[i] = m;
+}
+
 size_t stedc_worksize(int n) {
     ArenaSize ar;
     DcBuffers b;
@@ -349,9 +369,8 @@ int stedc(makb200_handle* h, int n, const double* d, const double* e, double* w,
     std::vector<int> bnd(nleaf + 1), cuts;
     for (int i = 0; i <= nleaf; ++i) bnd[i] = (int)((long long)i * n / nleaf);
     for (int i = 1; i < nleaf; ++i) cuts.push_back(bnd[i]);
-    MAK_CUDA(h, cudaMemcpyAsync(bnd_dev, bnd.data(), sizeof(int) * (nleaf + 1), cudaMemcpyHostToDevice, st));
-    if (!cuts.empty())
-        MAK_CUDA(h, cudaMemcpyAsync(cuts_dev, cuts.data(), sizeof(int) * cuts.size(), cudaMemcpyHostToDevice, st));
+    dc_tree_kernel<<<(nleaf + 1 + 127) / 128, 128, 0, st>>>(n, nleaf, bnd_dev, cuts_dev);
+    count_launch();
     MAK_CUDA(h, cudaMemsetAsync(b.info, 0, sizeof(int) * 4, st));
 
     dc_scale_kernel<<<1, 1024, 0, st>>>(n, d, e, b.ctx.D, b.E, b.scale);
@@ -383,8 +402,8 @@ int stedc(makb200_handle* h, int n, const double* d, const double* e, double* w,
             maxN = std::max(maxN, hm[i].hi - hm[i].lo);
             maxH = std::max(maxH, std::max(hm[i].mid - hm[i].lo, hm[i].hi - hm[i].mid));
         }
-        // the (pageable) host vector is consumed before cudaMemcpyAsync returns
-        MAK_CUDA(h, cudaMemcpyAsync(b.merges, hm.data(), sizeof(Merge) * nm, cudaMemcpyHostToDevice, st));
+        dc_merge_fill_kernel<<<(nm + 127) / 128, 128, 0, st>>>(nm, step, bnd_dev, b.merges);
+        count_launch();
         dc_merge_init_kernel<<<(nm + 127) / 128, 128, 0, st>>>(nm, b.merges, b.rho_cut, b.sgn_cut);
         const int bx = std::max(1, std::min((maxN + 255) / 256, 64));
         dim3 g2(bx, nm);

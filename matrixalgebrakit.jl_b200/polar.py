@@ -40,6 +40,10 @@ def left_polar_(A, WP=None, alg=None, **kw):
         return _left_polar_via_svd_(A, W, P, alg)
     if not isinstance(alg, Algorithm) or alg.name != "QDWH":
         raise ValueError(f"left_polar: algorithm {alg} is not provided by the B200 driver")
+    if alg.get("tol") is not None:
+        # the QDWH schedule (a, b, c per step) is fixed a priori from the lower bound l0 and always runs to |1 - l| <= 1e-15:
+        # there is no iteration tolerance to set.  Say so instead of silently ignoring the keyword.
+        raise ValueError("B200_QDWH runs an a-priori schedule to full precision: `tol` is not an option (use `maxiter` to cap the steps)")
     m, n = A.shape
     if m == 0 or n == 0:
         return W, P
@@ -56,7 +60,7 @@ def left_polar_(A, WP=None, alg=None, **kw):
     iters = C.c_int(0)
     rc = h.lib.makb200_polar_qdwh(h.h, dt, m, n, _core.ptr(A), _core.ld(A), _core.ptr(W), _core.ld(W),
                                   _core.ptr(P) if want_p else C.c_void_p(0), _core.ld(P) if want_p else 0,
-                                  float(alg.get("tol") or 0.0) * 0.0 + float(alg.get("l0", 0.0) or 0.0),
+                                  0.0,   # l0 <= 0: the library picks the lower bound (estimate for n >= 1024, eps otherwise)
                                   int(alg.get("maxiter") or 0), _core.ptr(work), work.numel(), C.byref(iters),
                                   C.c_void_p(0))
     h.check(rc, "makb200_polar_qdwh")

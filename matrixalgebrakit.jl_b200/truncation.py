@@ -143,11 +143,28 @@ def _find(values, s, svd):
         order = np.argsort(-np.abs(values), kind="stable")
         return order[: _truncerr_rank(values[order], s)]
     if isinstance(s, (TruncationIntersection, TruncationUnion)):
-        sets = [set(int(i) for i in _find(values, c, svd)) for c in s.components]
-        if not sets:
+        # the reference's _ind_intersect / _ind_union (implementations/truncation.jl:104-164) keep the order of the FIRST
+        # component: intersection = filter(in(rest), first); union = first, then the new entries of the rest in their order
+        # (Julia's intersect/union).  eigh_trunc with truncrank(r) & trunctol(...) therefore returns descending-|lambda| order.
+        inds = [np.asarray(_find(values, c, svd), dtype=np.int64) for c in s.components]
+        if not inds:
             return np.arange(n) if isinstance(s, TruncationIntersection) else np.arange(0)
-        out = set.intersection(*sets) if isinstance(s, TruncationIntersection) else set.union(*sets)
-        return np.array(sorted(out), dtype=np.int64)
+        out = inds[-1]
+        for first in reversed(inds[:-1]):        # right fold, as the reference recurses on Base.tail
+            rest = set(int(i) for i in out)
+            if isinstance(s, TruncationIntersection):
+                first_is_range = len(first) == 0 or np.array_equal(first, np.arange(first[0], first[0] + len(first)))
+                out_is_range = len(out) == 0 or np.array_equal(out, np.arange(out[0], out[0] + len(out)))
+                if first_is_range and not out_is_range:
+                    # _ind_intersect(::UnitRange, ::Vector) = filter(in(range), vector): the vector's order survives
+                    fs = set(int(i) for i in first)
+                    out = np.array([i for i in out if int(i) in fs], dtype=np.int64)
+                else:
+                    out = np.array([i for i in first if int(i) in rest], dtype=np.int64)
+            else:
+                seen = set(int(i) for i in first)
+                out = np.concatenate([first, np.array([i for i in out if int(i) not in seen], dtype=np.int64)])
+        return out
     raise ValueError(f"unknown truncation strategy {s}")
 
 

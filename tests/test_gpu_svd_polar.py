@@ -156,3 +156,34 @@ def test_svd_batched_pooled_threads(dtype):
     torch.cuda.synchronize()
     for a, (U, S, Vh) in zip(As0, outs):
         _check_svd(a, makb200.to_numpy(U), S.cpu().numpy(), makb200.to_numpy(Vh), vec_cmp=False)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+def test_svd_and_eigh_batched_graph_replay(dtype, monkeypatch):
+    """Opt-in CUDA-graph replay of the per-block path (capi.cu: run_graphed): one captured svd_t / eigh_t per shape and
+    stream slot, replayed per block between a staged copy-in and copy-out; rank-deficient blocks are redone uncaptured."""
+    import makb200
+    monkeypatch.setenv("MAKB200_BATCH_GRAPHS", "1")
+    rng = np.random.default_rng(5)
+    dims = [int(v) for v in rng.integers(90, 180, size=6)] * 3            # repeated shapes: the graphs are reused
+    sizes = [(d, d) for d in dims[:12]] + [(d, d - 20) for d in dims[12:15]] + [(d - 20, d) for d in dims[15:]]
+    As0 = [O.randn_matrix(m, n, dtype, seed=900 + i) for i, (m, n) in enumerate(sizes)]
+    As0[3] = np.asfortranarray(As0[3][:, :1] @ As0[3][:1, :])             # rank one: takes the redo path
+    for rep in range(2):                                                  # second call: cached graphs
+        outs = makb200.svd_compact_batched_([makb200.to_device(a) for a in As0])
+        torch.cuda.synchronize()
+        for a, (U, S, Vh) in zip(As0, outs):
+            Un, Sn, Vhn = makb200.to_numpy(U), S.cpu().numpy(), makb200.to_numpy(Vh)
+            tol = O.tol_for(*a.shape)
+            so = O.svd_vals(a)
+            assert np.max(np.abs(Sn - so)) <= tol * so[0]
+            assert np.linalg.norm(a - (Un * Sn) @ Vhn) <= tol * np.linalg.norm(a)
+            assert O.orth_err(Un) <= tol and O.orth_err(Vhn, "right") <= tol
+    Hs0 = [O.rand_hermitian(d, dtype, seed=950 + i) for i, d in enumerate(dims[:10])]
+    outs = makb200.eigh_full_batched_([makb200.to_device(a) for a in Hs0])
+    torch.cuda.synchronize()
+    for a, (D, V) in zip(Hs0, outs):
+        w, Vn = D.cpu().numpy(), makb200.to_numpy(V)
+        tol = O.tol_for(a.shape[0])
+        assert np.max(np.abs(w - O.eigh_vals(a))) <= tol * np.abs(w).max()
+        assert np.linalg.norm(a @ Vn - Vn * w) <= tol * np.linalg.norm(a) and O.orth_err(Vn) <= tol
