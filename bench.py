@@ -368,14 +368,14 @@ def run_c2(args):
         # (symmetric kernel: the lower triangle incl. diagonal, mt(mt+1)/2 elements)
         alg_bytes = ntrd * 8.0 * sum(float(n - c - 1) * (n - c) / 2 for c in range(n - 1))
         ach = alg_bytes / (kms.value * 1e-3) / 1e9
-        cands.append({"kernel": "trd_symv_kernel<double>", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+        cands.append({"kernel": "trd_symv2_kernel<double> (persistent TMA-fed tridiagonalisation column kernel)", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
                       "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "launches_per_step": kl.value,
                       "avg_launch_ms": kms.value / kl.value, "alg_bytes_per_launch": alg_bytes / kl.value,
                       "kernel_share_of_step": kms.value / step_ms, "peak_source": how})
     if gl.value > 0:
         pk = fp64_peak()
         ach = gflops / (gms.value * 1e-3) / 1e12
-        cands.append({"kernel": "gemm_kernel<double> (DMMA m8n8k4)", "bound": "tensor", "achieved": ach,
+        cands.append({"kernel": "gemm_tma_kernel<double> (TMA-fed DMMA m8n8k4; rank-k updates and unaligned operands: gemm_kernel)", "bound": "tensor", "achieved": ach,
                       "peak": pk[0], "unit": "TFLOP/s", "frac": ach / pk[0], "traffic": None,
                       "launches_per_step": gl.value, "avg_launch_ms": gms.value / gl.value,
                       "alg_flops_per_launch": gflops / gl.value, "kernel_share_of_step": gms.value / step_ms,
@@ -386,7 +386,7 @@ def run_c2(args):
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tk = json.load(f)["kernels"]
         for c in cands:
-            key = "gemm_kernel" if c["kernel"].startswith("gemm_kernel") else "trd_symv_kernel"
+            key = "gemm_kernel" if c["kernel"].startswith("gemm_") else "trd_symv_kernel"
             if key in tk and n == 8192 and set(ops) == {"eigh", "svd"}:
                 c["traffic"] = tk[key]["dram_bytes_per_launch"]
                 c["traffic_source"] = ("profiles/traffic.json: ncu dram__bytes_read+write, mean per launch over "
@@ -554,7 +554,7 @@ def run_tsqr(args):
     step_ms = ms / args.steps
     pk = fp64_peak()
     ach = gflops / (gms.value * 1e-3) / 1e12 if gms.value > 0 else 0.0
-    roofline = {"kernel": "gemm_kernel<double> (DMMA m8n8k4)", "bound": "tensor", "achieved": ach, "peak": pk[0],
+    roofline = {"kernel": "gemm_tma_kernel<double> (TMA-fed DMMA m8n8k4)", "bound": "tensor", "achieved": ach, "peak": pk[0],
                 "unit": "TFLOP/s", "frac": ach / pk[0], "traffic": None, "launches_per_step": gl.value,
                 "avg_launch_ms": gms.value / max(gl.value, 1), "alg_flops_per_launch": gflops / max(gl.value, 1),
                 "kernel_share_of_step": gms.value / step_ms, "peak_source": pk[1],

@@ -1068,6 +1068,19 @@ int makb200_tsqr(makb200_handle_t* h, void* comm, int dtype, int m, int n, void*
 }  // extern "C"
 
 // ---- batched svd --------------------------------------------------------------------------
+constexpr int SVD_PHASE_CHUNK = 192;     // blocks per one-launch tridiagonalisation (>= one CTA per SM)
+static bool phased_enabled() {
+    const char* e = getenv("MAKB200_SVD_PHASED");   // read per call: tests run both paths
+    return !(e && e[0] == '0');
+}
+// per-block storage that lives across the phases: W (m x n), P, V (n x n), tau, wv, d, e, flag
+template <typename T>
+static size_t svd_phase_persist_bytes(int m, int n) {
+    const size_t mm = (size_t)m, nn = (size_t)n;
+    return mak::align_up(mm * nn * sizeof(T), 256) + 2 * mak::align_up(nn * nn * sizeof(T), 256) + mak::align_up(nn * sizeof(T), 256) +
+           3 * mak::align_up(nn * 8, 256) + 256;
+}
+
 template <typename T>
 static int svd_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int* m, const int* n, void* const* A,
                          const int* lda, void* const* S, void* const* U, const int* ldu, void* const* Vh,
@@ -1114,6 +1127,80 @@ static int svd_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int
     };
     if (big.empty()) return 0;
     const bool vectors = (U != nullptr && Vh != nullptr);
+    // ---- phased path (default): the device dispatches only ~350 k kernels/s however many streams feed it
+    // (profiles/r2_batched_graphs.log), so what counts is kernels per block, and 2n of a block's ~3.5n launches are the
+    // per-column kernels of the tridiagonalisation of P.  Chunks of blocks go through
+    //   1. QDWH per block on the stream pool            -> W, P in per-block storage
+    //   2. ONE launch that tridiagonalises every P of the chunk (one CTA per block, csrc/bhetrd.cuh)
+    //   3. tridiagonal D&C, back-transformation, U = W V, gauge per block on the pool
+    if (vectors && phased_enabled() && !graphs_enabled()) {
+        std::vector<int> ph, rest;
+        for (int i : big) ((m[i] >= n[i] && n[i] >= 3 && n[i] <= mak::BHETRD_MAX_N) ? ph : rest).push_back(i);
+        size_t scratch = 0, persist = 0;
+        for (int i : ph) {
+            scratch = std::max(scratch, mak::svd_phase_scratch_t<T>(h, m[i], n[i]));
+            persist = std::max(persist, svd_phase_persist_bytes<T>(m[i], n[i]));
+        }
+        const size_t np_pool = (size_t)pool_streams();
+        const size_t pool_region = (scratch + 1024) * np_pool;
+        size_t chunk = 0;
+        if (!ph.empty() && lbig > pool_region + 4096) chunk = std::min<size_t>({(size_t)SVD_PHASE_CHUNK, ph.size(), (lbig - pool_region - 4096) / (persist + sizeof(mak::BhetrdDesc<T>) + 64)});
+        if (ph.size() >= 8 && chunk >= 8) {
+            char* pbase = wbig + pool_region;
+            mak::BhetrdDesc<T>* ddev = (mak::BhetrdDesc<T>*)pbase;
+            char* store = pbase + mak::align_up(sizeof(mak::BhetrdDesc<T>) * chunk, 256);
+            struct Blk { T *W, *P, *V, *tau; double *wv, *flag, *d, *e; };
+            std::vector<Blk> blk(chunk);
+            std::vector<mak::TrdPre<T>> pre(chunk);
+            std::vector<int> slot_of(batch, -1);
+            for (size_t c0 = 0; c0 < ph.size(); c0 += chunk) {
+                const size_t nc = std::min(chunk, ph.size() - c0);
+                std::vector<int> ids(ph.begin() + c0, ph.begin() + c0 + nc);
+                std::vector<mak::BhetrdDesc<T>> bd(nc);
+                int nmax = 0;
+                for (size_t q = 0; q < nc; ++q) {
+                    const int i = ids[q];
+                    const size_t mm = (size_t)m[i], nn = (size_t)n[i];
+                    char* pq = store + q * persist;
+                    Blk& b = blk[q];
+                    size_t off = 0;
+                    auto take = [&](size_t bytes) { char* r = pq + off; off += mak::align_up(bytes, 256); return r; };
+                    b.W = (T*)take(mm * nn * sizeof(T));
+                    b.P = (T*)take(nn * nn * sizeof(T));
+                    b.V = (T*)take(nn * nn * sizeof(T));
+                    b.tau = (T*)take(nn * sizeof(T));
+                    b.wv = (double*)take(nn * 8);
+                    b.d = (double*)take(nn * 8);
+                    b.e = (double*)take(nn * 8);
+                    b.flag = (double*)take(16);
+                    pre[q] = mak::TrdPre<T>{b.d, b.e, b.tau};
+                    bd[q] = mak::BhetrdDesc<T>{n[i], b.P, n[i], b.d, b.e, b.tau};
+                    slot_of[i] = (int)q;
+                    if (n[i] > nmax) nmax = n[i];
+                }
+                int rc = run_pooled(h, ids, wbig, pool_region, [&](makb200_handle_t* hh, char* w, size_t lw, int i) {
+                    const Blk& b = blk[slot_of[i]];
+                    return mak::svd_phase1_t<T>(hh, m[i], n[i], (T*)A[i], lda[i], b.W, b.P, 2.2e-16, w, lw);
+                });
+                if (rc) return rc;
+                {
+                    mak::Stager st(h, nc * sizeof(mak::BhetrdDesc<T>) + 1024);
+                    MAK_CUDA(h, st.put(ddev, bd.data(), nc * sizeof(mak::BhetrdDesc<T>), h->stream));
+                }
+                rc = mak::bhetrd_batched_t<T>(h, (int)nc, ddev, nmax);
+                if (rc) return rc;
+                rc = run_pooled(h, ids, wbig, pool_region, [&](makb200_handle_t* hh, char* w, size_t lw, int i) {
+                    const int q = slot_of[i];
+                    const Blk& b = blk[q];
+                    return mak::svd_phase2_t<T>(hh, m[i], n[i], b.W, b.P, b.V, b.wv, b.flag, &pre[q], (double*)S[i], (T*)U[i], ldu[i],
+                                                (T*)Vh[i], ldvh[i], fixgauge, w, lw);
+                });
+                if (rc) return rc;
+            }
+            if (rest.empty()) return 0;
+            return run_pooled(h, rest, wbig, lbig, per_block);
+        }
+    }
     if (graphs_enabled() && big.size() >= 4) {
         // graph replay: one captured svd_t per (shape, slot) against staging buffers
         size_t st_a = 0, st_u = 0, st_v = 0, st_s = 0, wmax = 0;
@@ -1219,7 +1306,17 @@ size_t makb200_svd_batched_worksize(makb200_handle_t* h, int dtype, int batch, c
     // graph-replayed path: staging copies of A, U, Vh, S per slot + one defect indicator per big block
     const size_t staging = mak::align_up(st_a * esz, 256) + mak::align_up(st_u * esz, 256) + mak::align_up(st_v * esz, 256) +
                            mak::align_up(st_s * 8, 256) + 1024;
-    return bytes + pooled_worksize(big, nbig, staging) + mak::align_up(sizeof(double) * nbig, 256) + 512;
+    // phased path: per-block W, P, V, ... of one chunk + its descriptors
+    size_t persist = 0;
+    for (int i = 0; i < batch; ++i) {
+        if (m[i] <= 0 || n[i] <= 0 || m[i] < n[i] || n[i] > mak::BHETRD_MAX_N) continue;
+        if (mak::batched_svd_smem_bytes(m[i], n[i], esz) <= mak::batched_svd_max_smem_bytes()) continue;
+        const size_t pb = dtype == MAKB200_F64 ? svd_phase_persist_bytes<double>(m[i], n[i]) : svd_phase_persist_bytes<cplx>(m[i], n[i]);
+        if (pb > persist) persist = pb;
+    }
+    const size_t chunk = nbig < (size_t)SVD_PHASE_CHUNK ? nbig : (size_t)SVD_PHASE_CHUNK;
+    const size_t phased = chunk * (persist + sizeof(mak::BhetrdDesc<cplx>) + 64) + 8192;
+    return bytes + pooled_worksize(big, nbig, staging) + phased + mak::align_up(sizeof(double) * nbig, 256) + 512;
 }
 
 int makb200_svd_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch, const int* m, const int* n,
@@ -1244,9 +1341,12 @@ int makb200_svd_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch,
 }  // extern "C"
 
 // ---- batched eigh -------------------------------------------------------------------------
+// One-launch tridiagonalisation of every mid-size block of a batch (one CTA per block, csrc/bhetrd.cuh).  Measured at
+// scale in round 2 (profiles/r2_bhetrd_scale.log, 600-2000 c128 blocks per bucket): eigh 65-128: 3327 -> 6377 blocks/s,
+// 129-256: 1412 -> 2826, 257-512: 708 -> 1365 - default on (MAKB200_BHETRD=0 disables).
 static bool bhetrd_enabled() {
-    const char* e = getenv("MAKB200_BHETRD");   // read per call: the bring-up tests toggle it
-    return e && e[0] == '1';
+    const char* e = getenv("MAKB200_BHETRD");   // read per call: the tests toggle it
+    return !(e && e[0] == '0');
 }
 template <typename T>
 static int eigh_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int* n, void* const* A, const int* lda,

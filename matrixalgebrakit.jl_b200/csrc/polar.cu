@@ -21,6 +21,7 @@ namespace mak {
 
 template <typename T> struct CholNB { static constexpr int value = 128; };
 template <> struct CholNB<cplx> { static constexpr int value = 64; };
+constexpr size_t POTRF_AUX_BYTES = (size_t)64 * 128 * 128 * sizeof(double);
 
 #define MAK_GEMM2(h, ...)                                              \
     do {                                                               \
@@ -402,24 +403,60 @@ int polar_init(makb200_handle* h) {
 }
 
 // left-looking blocked Cholesky: Z (n x n Hermitian, lower part read, destroyed) -> L (lower; only
-// blocks strictly below the block diagonal are referenced later) and Linv (nb x nb per block)
+// blocks strictly below the block diagonal are referenced later) and Linv (nb x nb per block).
+// Per block column: (a) update of the nb x nb diagonal block, (b) its one-CTA factorization + inverse (~150 us of
+// pure latency), (c) update of the panel below it, (d) panel times the inverse.  (b) is the serial chain: n/nb of them
+// were ~40 % of the 23 ms this took at n = 8192.  With look-ahead (a) and (b) run on the handle's high-priority
+// auxiliary stream while (c) - the bulk of the flops - runs on the caller's stream; (d) joins the two.
+static bool potrf_lookahead() {
+    static const bool v = []() { const char* e = getenv("MAKB200_POTRF_LOOKAHEAD"); return !(e && e[0] == '0'); }();
+    return v;
+}
 template <typename T>
 static int potrf_blocked(makb200_handle* h, int n, T* Z, int ldz, T* L, int ldl, T* Linv, int* info,
                          void* ws = nullptr, size_t ws_bytes = 0) {
     constexpr int nb = CholNB<T>::value;
     cudaStream_t s = h->stream;
     const T one_ = one<T>(), zero_ = zero<T>(), mone = neg_(one<T>());
+    // the diagonal-block product on the auxiliary stream is ONE tile with K up to n: it needs split-K, hence its own
+    // scratch - the tail of `ws` (the carve sites add POTRF_AUX_BYTES for it)
+    constexpr size_t aux_bytes = (size_t)64 * nb * nb * sizeof(T);
+    const bool la = potrf_lookahead() && !h->no_lookahead && n >= 8 * nb && ws && ws_bytes > 2 * aux_bytes;
+    void* ws_aux = nullptr;
+    if (la) { ws_bytes -= aux_bytes; ws_aux = (char*)ws + ws_bytes; }
+    cudaStream_t sA = la ? h->aux_stream : s;
     for (int j0 = 0, b = 0; j0 < n; j0 += nb, ++b) {
         const int jb = (n - j0 < nb) ? (n - j0) : nb;
-        if (j0 > 0)
-            MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, n - j0, jb, j0, mone, L + j0, ldl, L + j0, ldl,
-                      one_, Z + (size_t)j0 * ldz + j0, ldz, ws, ws_bytes);
-        potf2_inv_kernel<T, nb><<<1, 256, sizeof(T) * nb * (nb + 1), s>>>(jb, Z + (size_t)j0 * ldz + j0, ldz,
-                                                                      L + (size_t)j0 * ldl + j0, ldl,
-                                                                      Linv + (size_t)b * nb * nb, nb, info);
+        const int mr = n - j0 - jb;
+        if (la) {
+            // fork: everything queued so far (the previous column's L) is visible to the auxiliary stream
+            MAK_CUDA(h, cudaEventRecord(h->ev[6], s));
+            MAK_CUDA(h, cudaStreamWaitEvent(sA, h->ev[6], 0));
+        }
+        if (j0 > 0) {
+            if (la) {
+                // (a) diagonal block on the auxiliary stream (no split-K scratch: `ws` belongs to the main stream)
+                MAK_GEMM2(h, sA, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, jb, jb, j0, mone, L + j0, ldl, L + j0, ldl, one_,
+                          Z + (size_t)j0 * ldz + j0, ldz, ws_aux, aux_bytes);
+                // (c) panel below it on the caller's stream
+                if (mr > 0)
+                    MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, mr, jb, j0, mone, L + j0 + jb, ldl, L + j0, ldl, one_,
+                              Z + (size_t)j0 * ldz + j0 + jb, ldz, ws, ws_bytes);
+            } else {
+                MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, n - j0, jb, j0, mone, L + j0, ldl, L + j0, ldl,
+                          one_, Z + (size_t)j0 * ldz + j0, ldz, ws, ws_bytes);
+            }
+        }
+        potf2_inv_kernel<T, nb><<<1, 256, sizeof(T) * nb * (nb + 1), sA>>>(jb, Z + (size_t)j0 * ldz + j0, ldz,
+                                                                       L + (size_t)j0 * ldl + j0, ldl,
+                                                                       Linv + (size_t)b * nb * nb, nb, info);
         count_launch();
         MAK_LAUNCH_CHECK(h, "potf2_inv_kernel");
-        const int mr = n - j0 - jb;
+        if (la) {
+            // join before (d)
+            MAK_CUDA(h, cudaEventRecord(h->ev[7], sA));
+            MAK_CUDA(h, cudaStreamWaitEvent(s, h->ev[7], 0));
+        }
         if (mr > 0)
             MAK_GEMM2(h, s, h->num_sms, MAKB200_OP_N, MAKB200_OP_C, mr, jb, jb, one_, Z + (size_t)j0 * ldz + j0 + jb,
                       ldz, Linv + (size_t)b * nb * nb, nb, zero_, L + (size_t)j0 * ldl + j0 + jb, ldl, nullptr, 0);
@@ -527,6 +564,7 @@ static void polar_carve(makb200_handle* h, AR& ar, int m, int n, bool tall, Pola
     w->sub = ar.template get<char>(w->sub_bytes);
     w->ws_bytes = (size_t)h->num_sms * 128 * 128 * sizeof(double);
     if (nn <= 1024 && w->ws_bytes < 64 * nn * nn * sizeof(T)) w->ws_bytes = 64 * nn * nn * sizeof(T);   // split-K up to 64
+    w->ws_bytes += POTRF_AUX_BYTES;   // split-K scratch of the Cholesky look-ahead stream (potrf_blocked)
     w->ws = ar.template get<char>(w->ws_bytes);
 }
 
@@ -810,6 +848,10 @@ size_t svd_worksize_t(makb200_handle* h, int m, int n) {
     return ar.off + 256;
 }
 
+template <typename T>
+static int svd_tail(makb200_handle* h, int m, int n, int r, double* S, T* U, int ldu, T* Vh, int ldvh, int fixgauge,
+                    SvdWork<T>& w, const TrdPre<T>* pre, PhaseTimer& pt);
+
 // tall/square core: A (m x n, m >= n) -> U (m x r), S (n, always all values), Vh (r x n); U/Vh may be null
 // (values).  r = n is the compact SVD; r < n (svd_trunc! with a rank known up front) back-transforms
 // only the r leading eigenvectors of P and forms U with an m x r x n product.
@@ -823,9 +865,18 @@ static int svd_tall(makb200_handle* h, int m, int n, int r, T* A, int lda, doubl
     int rc = polar_qdwh_t<T>(h, m, n, A, lda, w.Wp, m, w.P, n, l0, 12, w.sub, w.sub_bytes, &iters, info_dev);
     if (rc) return rc;
     pt.mark("polar");
+    return svd_tail<T>(h, m, n, r, S, U, ldu, Vh, ldvh, fixgauge, w, nullptr, pt);
+}
+
+// second half of the SVD: W (w.Wp) and P (w.P) are in place; `pre`: P was already tridiagonalised (batched path)
+template <typename T>
+static int svd_tail(makb200_handle* h, int m, int n, int r, double* S, T* U, int ldu, T* Vh, int ldvh, int fixgauge,
+                    SvdWork<T>& w, const TrdPre<T>* pre, PhaseTimer& pt) {
+    cudaStream_t s = h->stream;
+    int rc = 0;
     const bool vectors = (U != nullptr && Vh != nullptr);
     // values only (job 'N'): eigenvalues of P by Sturm K-section, no eigenvectors
-    rc = eigh_t<T>(h, n, w.P, n, w.wv, vectors ? w.V : (T*)nullptr, n, 0, w.sub, w.sub_bytes, nullptr, r);
+    rc = eigh_t<T>(h, n, w.P, n, w.wv, vectors ? w.V : (T*)nullptr, n, 0, w.sub, w.sub_bytes, nullptr, r, pre);
     if (rc) return rc;
     pt.mark("eigh");
     int nb32 = (n + 31) / 32;
@@ -872,6 +923,39 @@ static int svd_tall(makb200_handle* h, int m, int n, int r, T* A, int lda, doubl
     pt.report("svd");
     return 0;
 }
+
+// ---- phased SVD of one block for the batched path (m >= n): phase 1 = QDWH into caller-held W (m x n, ld m) and P
+// (n x n, ld n); the caller then tridiagonalises the P of ALL blocks in one launch (bhetrd_batched_t); phase 2 = the
+// eigensolve from (d, e, tau) and U, S, Vh.  `scratch` is per stream slot, the W/P/V/wv/flag buffers are per block. ----
+template <typename T>
+size_t svd_phase_scratch_t(makb200_handle* h, int m, int n) {
+    size_t a = polar_worksize_t<T>(h, m, n), b = eigh_worksize_t<T>(h, n), c = qr_worksize_t<T>(h, m, n, n);
+    size_t v = a > b ? a : b;
+    return (v > c ? v : c) + 256;
+}
+template <typename T>
+int svd_phase1_t(makb200_handle* h, int m, int n, T* A, int lda, T* Wp, T* P, double l0, void* scratch, size_t lscratch) {
+    int iters = 0;
+    return polar_qdwh_t<T>(h, m, n, A, lda, Wp, m, P, n, l0, 12, scratch, lscratch, &iters, nullptr);
+}
+template <typename T>
+int svd_phase2_t(makb200_handle* h, int m, int n, T* Wp, T* P, T* V, double* wv, double* flag, const TrdPre<T>* pre,
+                 double* S, T* U, int ldu, T* Vh, int ldvh, int fixgauge, void* scratch, size_t lscratch) {
+    SvdWork<T> w{};
+    w.Wp = Wp; w.P = P; w.V = V; w.wv = wv; w.flag = flag;
+    w.sub = scratch; w.sub_bytes = lscratch;
+    PhaseTimer pt(h->stream);
+    pt.mark("start");
+    return svd_tail<T>(h, m, n, n, S, U, ldu, Vh, ldvh, fixgauge, w, pre, pt);
+}
+template size_t svd_phase_scratch_t<double>(makb200_handle*, int, int);
+template size_t svd_phase_scratch_t<cplx>(makb200_handle*, int, int);
+template int svd_phase1_t<double>(makb200_handle*, int, int, double*, int, double*, double*, double, void*, size_t);
+template int svd_phase1_t<cplx>(makb200_handle*, int, int, cplx*, int, cplx*, cplx*, double, void*, size_t);
+template int svd_phase2_t<double>(makb200_handle*, int, int, double*, double*, double*, double*, double*, const TrdPre<double>*,
+                                  double*, double*, int, double*, int, int, void*, size_t);
+template int svd_phase2_t<cplx>(makb200_handle*, int, int, cplx*, cplx*, cplx*, double*, double*, const TrdPre<cplx>*, double*,
+                                cplx*, int, cplx*, int, int, void*, size_t);
 
 template <typename T>
 int svd_t(makb200_handle* h, int m, int n, T* A, int lda, double* S, T* U, int ldu, T* Vh, int ldvh, int fixgauge,
@@ -999,6 +1083,7 @@ static void cqr_carve(makb200_handle* h, AR& ar, int m, int n, CqrWork<T>* w) {
     w->info = ar.template get<int>(4);
     w->ws_bytes = (size_t)h->num_sms * 128 * 128 * sizeof(double);
     if (nn <= 1024 && w->ws_bytes < 64 * nn * nn * sizeof(T)) w->ws_bytes = 64 * nn * nn * sizeof(T);   // split-K up to 64
+    w->ws_bytes += POTRF_AUX_BYTES;   // split-K scratch of the Cholesky look-ahead stream (potrf_blocked)
     w->ws = ar.template get<char>(w->ws_bytes);
 }
 

@@ -12,6 +12,14 @@ template <typename T> size_t svd_worksize_t(makb200_handle* h, int m, int n);
 template <typename T>
 int svd_t(makb200_handle* h, int m, int n, T* A, int lda, double* S, T* U, int ldu, T* Vh, int ldvh, int fixgauge,
           double l0, void* work, size_t lwork, int* info_dev, int r = 0);   // 0 < r < min(m,n): U m x r, Vh r x n
+// phased SVD of one block (batched path, m >= n): see polar.cu
+template <typename T> struct TrdPre;
+template <typename T> size_t svd_phase_scratch_t(makb200_handle* h, int m, int n);
+template <typename T>
+int svd_phase1_t(makb200_handle* h, int m, int n, T* A, int lda, T* Wp, T* P, double l0, void* scratch, size_t lscratch);
+template <typename T>
+int svd_phase2_t(makb200_handle* h, int m, int n, T* Wp, T* P, T* V, double* wv, double* flag, const TrdPre<T>* pre,
+                 double* S, T* U, int ldu, T* Vh, int ldvh, int fixgauge, void* scratch, size_t lscratch);
 // tall-skinny local QR (CholeskyQR2; nshift > 0: shifted CholeskyQR with that many preconditioning
 // passes) used by TSQR; A is overwritten, diag(R) > 0
 template <typename T> size_t cholqr2_worksize_t(makb200_handle* h, int m, int n);

@@ -10,7 +10,7 @@ from collections import defaultdict
 
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12,
         "ns": 1e-6, "nsecond": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3}
-CLASSES = {"gemm_kernel": "gemm_kernel", "trd_symv": "trd_symv_kernel", "trd_dots": "trd_dots_kernel",
+CLASSES = {"gemm_kernel": "gemm_kernel", "gemm_tma_kernel": "gemm_kernel", "trd_symv": "trd_symv_kernel", "trd_dots": "trd_dots_kernel",
            "trd_w_kernel": "trd_w_kernel", "panel_kernel": "panel_kernel"}
 
 with open(sys.argv[1], newline="") as f:
