@@ -619,8 +619,47 @@ def run_tsqr(args):
 
     if rank != 0:
         if world > 1:
+            dist.barrier()        # rank 0 measures the one-GPU time of the same matrix before everybody leaves
             dist.destroy_process_group()
         return
+    # ---- the SAME workload on ONE GPU (rank 0, after the timed regions): the base of the strong-scaling curve.
+    # `bench.py --gpus 1` runs configs[1] (the N = 1 headline), so the N > 1 line carries its own one-GPU reference.
+    one_gpu = None
+    if world > 1 and not args.no_one_gpu_ref:
+        try:
+            del A_src, A, Q, work, hin, hq
+            torch.cuda.empty_cache()
+            g1 = torch.Generator(device=dev)
+            g1.manual_seed(5)
+            S1 = torch.randn((n, M), dtype=torch.float64, device=dev, generator=g1).t()
+            A1 = makb200.colmajor_empty(M, n, torch.float64, dev)
+            Q1 = makb200.colmajor_empty(M, n, torch.float64, dev)
+            lw1 = lib.makb200_tsqr_worksize(h.h, 0, M, n, 1)
+            w1 = torch.empty(max(int(lw1), 1), dtype=torch.uint8, device=dev)
+
+            def step1():
+                A1.copy_(S1)
+                h2 = makb200.Handle.get(dev)
+                rc = lib.makb200_tsqr(h2.h, ctypes.c_void_p(0), 0, M, n, A1.data_ptr(), M, Q1.data_ptr(), M, R.data_ptr(), n,
+                                      w1.data_ptr(), w1.numel(), info.data_ptr())
+                h2.check(rc, "makb200_tsqr")
+            for _ in range(2):
+                step1()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                step1()
+            e1.record()
+            torch.cuda.synchronize()
+            ms1 = e0.elapsed_time(e1) / args.steps
+            one_gpu = {"ms_per_step": ms1, "value": fl / (ms1 * 1e-3) / 1e9, "unit": "GFLOP/s",
+                       "note": "same 16.7M x 256 matrix, one rank, measured by rank 0 in this run after the timed regions"}
+            del S1, A1, Q1, w1
+        except Exception as exc:  # noqa: BLE001  (out of memory on a smaller device: report, do not fail the line)
+            one_gpu = {"unavailable": repr(exc)[:200]}
+    if world > 1:
+        dist.barrier()
     cpu = None
     if world == 1 and not args.no_cpu:
         gcpu, scpu, desc = cpu_sample_tsqr(min(M, 1 << 20), n, M)
@@ -637,7 +676,8 @@ def run_tsqr(args):
                    "collective": ("binary tree over ranks: ncclSend/ncclRecv of one n x n R factor per round on the compute stream, "
                                   "ncclBroadcast of R; own communicator from makb200_comm_create") if world > 1 else "none (1 rank)",
                    "factorizations_per_s": args.steps / (ms * 1e-3),
-                   "hbm_floor_ms_per_rank": 16.0 * m_loc * n / (peaks()[0] * 1e9) * 1e3},
+                   "hbm_floor_ms_per_rank": 16.0 * m_loc * n / (peaks()[0] * 1e9) * 1e3,
+                   "same_workload_on_one_gpu": one_gpu},
         "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": bytes_io[0] * world,
                 "d2h_bytes_per_step": bytes_io[1] * world, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                 "host_buffer": f"pinned staging of {chunk} rows reused per slab"},
@@ -661,6 +701,7 @@ def main():
                     help="auto: configs[1] (eigh+svd 8192^2) at 1 GPU, configs[3] (TSQR 16.7M x 256, strong scaling) at N > 1")
     ap.add_argument("--tsqr-rows", type=int, default=16777216)
     ap.add_argument("--tsqr-cols", type=int, default=256)
+    ap.add_argument("--no-one-gpu-ref", action="store_true", help="N > 1: skip the one-GPU run of the same TSQR matrix on rank 0")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -1233,8 +1233,12 @@ static void tsqr_carve(makb200_handle* h, AR& ar, int m, int n, int nranks, Tsqr
     int levels = 0;
     for (int s = 1; s < nranks; s *= 2) ++levels;
     for (int l = 0; l < TSQR_MAX_LEVELS; ++l) w->Qs[l] = l < levels ? ar.template get<T>(2 * nn) : nullptr;
-    w->sub_bytes = nranks > 1 ? qr_worksize_t<T>(h, 2 * n, n, n) : 0;
+    w->sub_bytes = nranks > 1 ? cholqr2_worksize_t<T>(h, 2 * n, n) : 0;
     w->sub = ar.template get<char>(w->sub_bytes);
+}
+
+__global__ void info_or_kernel(int* __restrict__ dst, const int* __restrict__ src) {
+    if (src[0] != 0) dst[0] = src[0];
 }
 
 template <typename T>
@@ -1332,9 +1336,13 @@ int tsqr_t(makb200_handle* h, const NcclApi* api, ncclComm_t comm, int m, int n,
                 MAK_NCCL(h, api, api->Recv(w.Rb, cnt, ncclDouble, partner, comm, s));
                 stack2_kernel<T><<<grid_for2(2 * nn, h->num_sms), 256, 0, s>>>(n, w.Rcur, w.Rb, w.S);
                 count_launch();
-                rc = qr_fused_t<T>(h, MAKB200_QR_COMPACT, 2 * n, n, w.S, 2 * n, w.Qs[nfac], 2 * n, w.Rcur, n, w.sub,
-                                   w.sub_bytes);
+                // QR of the stacked pair: CholeskyQR2 again (kappa of the pair = kappa of the rows it stands for, the
+                // assumption the local step already makes): a dozen small launches, ~0.15 ms, where the blocked Householder
+                // QR of a 512 x 256 matrix took 1.7 ms per tree level - at 8 ranks that was 5 of the 6 ms over the ideal
+                rc = cholqr2_t<T>(h, 2 * n, n, w.S, 2 * n, w.Qs[nfac], 2 * n, w.Rcur, n, w.sub, w.sub_bytes, w.c.info + 2, 0);
                 if (rc) return rc;
+                info_or_kernel<<<1, 1, 0, s>>>(w.c.info, w.c.info + 2);
+                count_launch();
                 fac_partner[nfac++] = partner;
             }
         } else {
