@@ -296,6 +296,10 @@ __global__ void adjoint_kernel(int m, int n, const T* __restrict__ S, int lds, T
     }
 }
 
+__device__ __forceinline__ double shfl_xor_any(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+__device__ __forceinline__ cplx shfl_xor_any(cplx v, int o) {
+    return cplx{__shfl_xor_sync(0xffffffffu, v.re, o), __shfl_xor_sync(0xffffffffu, v.im, o)};
+}
 // ---------------------------------------------------------------------------------------
 // Cholesky building blocks
 // ---------------------------------------------------------------------------------------
@@ -375,15 +379,33 @@ potf2_inv_kernel(int nb, const T* __restrict__ Zb, int ldz, T* __restrict__ Lb, 
             }
         }
     __syncthreads();
-    // inverse: thread c solves L x = e_c by forward substitution
-    for (int c = tid; c < nb; c += blockDim.x) {
-        T* out = Linv + (size_t)c * ldi;
-        for (int r = 0; r < c; ++r) out[r] = zero<T>();
-        out[c] = mk<T>(1.0 / real_(S[c * lds + c]));
-        for (int r = c + 1; r < nb; ++r) {
-            T s = zero<T>();
-            for (int p = c; p < r; ++p) fma_(s, S[p * lds + r], out[p]);
-            out[r] = scale_(neg_(s), 1.0 / real_(S[r * lds + r]));
+    // inverse, in place in shared memory (S is a private copy of L), one column per step from the last to the first:
+    //   X[j,j] = 1 / L[j,j],   X[j+1:, j] = -(X[j+1:, j+1:] L[j+1:, j]) X[j,j]
+    // Row-parallel: thread pair (r, half) takes half of row r's dot product (S is column-major with an odd leading
+    // dimension: consecutive rows hit consecutive banks, L[p,j] is a broadcast).  The r1 version gave every thread a whole
+    // forward substitution through GLOBAL memory (8 k dependent steps for column 0): ~170 us of the ~200 us this kernel
+    // took, and n/128 of them are the serial chain of the blocked Cholesky.
+    {
+        const int r = tid >> 1, hf = tid & 1;
+        for (int j = nb - 1; j >= 0; --j) {
+            T acc = zero<T>();
+            const double dinv = 1.0 / real_(S[j * lds + j]);   // (read before the barrier: row j's thread overwrites it below)
+            if (r > j && r < nb) {
+                // p in (j, r]: X[r,p] * L[p,j]; the two halves interleave p
+                for (int pp = j + 1 + hf; pp <= r; pp += 2) fma_(acc, S[pp * lds + r], S[j * lds + pp]);
+            }
+            // combine the halves (lanes 2q and 2q+1 of the same warp)
+            acc = add_(acc, shfl_xor_any(acc, 1));
+            __syncthreads();                       // everybody has read column j of L
+            if (hf == 0) {
+                if (r == j) S[j * lds + j] = mk<T>(dinv);
+                else if (r > j && r < nb) S[j * lds + r] = scale_(neg_(acc), dinv);
+            }
+            __syncthreads();
+        }
+        for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
+            const int c = idx / nb, rr = idx - c * nb;
+            Linv[(size_t)c * ldi + rr] = (rr >= c) ? S[c * lds + rr] : zero<T>();
         }
     }
 }
