@@ -824,6 +824,10 @@ __global__ void trd_last_d_kernel(TrdCtx<T> x) {
 
 // grid of the persistent column kernel: one wave of two CTAs per SM
 static int trd2_grid(makb200_handle* h) { return 2 * h->num_sms; }
+static bool trd2_early() {
+    static const bool v = []() { const char* e = getenv("MAKB200_SYMV_EARLY"); return !(e && e[0] == '0'); }();
+    return v;
+}
 static bool trd2_enabled() {
     static const bool v = []() { const char* e = getenv("MAKB200_SYMV_V2"); return !(e && e[0] == '0'); }();
     return v;
@@ -920,9 +924,9 @@ static int hetrd(makb200_handle* h, TrdCtx<T>& x) {
                 const bool pdl2 = trd_pdl() && !g_clock_dots.on;
                 g_clock_dots.begin(s);
                 if (pdl2) {
-                    cudaError_t e = launch_pdl(trd_symv2_kernel<T>, dim3(G2), dim3(288), v2_smem, s, tmap2, x, c, i, npn);
+                    cudaError_t e = launch_pdl(trd_symv2_kernel<T>, dim3(G2), dim3(288), v2_smem, s, tmap2, x, c, i, npn, (i > 0 && trd2_early()) ? 1 : 0);
                     if (e != cudaSuccess) return cuda_fail(h, e, "trd_symv2_kernel (PDL)");
-                } else trd_symv2_kernel<T><<<G2, 288, v2_smem, s>>>(tmap2, x, c, i, npn);
+                } else trd_symv2_kernel<T><<<G2, 288, v2_smem, s>>>(tmap2, x, c, i, npn, 0);
                 g_clock_dots.end(s);
                 g_clock_w.begin(s);
                 if (pdl2) {

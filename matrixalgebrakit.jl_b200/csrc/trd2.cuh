@@ -85,7 +85,7 @@ __device__ __forceinline__ T trd2_v(const T* __restrict__ Acol, int g, int row0,
 
 template <typename T>
 __global__ void __launch_bounds__(288, 2)
-trd_symv2_kernel(const __grid_constant__ CUtensorMap tmap, TrdCtx<T> x, int c, int i, int npn) {
+trd_symv2_kernel(const __grid_constant__ CUtensorMap tmap, TrdCtx<T> x, int c, int i, int npn, int early) {
     constexpr int CW = SymvCW<T>::value;
     constexpr int BH = TRD2_BH;
     constexpr int NBOX = sizeof(T) / 8;
@@ -93,11 +93,17 @@ trd_symv2_kernel(const __grid_constant__ CUtensorMap tmap, TrdCtx<T> x, int c, i
     constexpr unsigned STAGE_BYTES = BH * CW * sizeof(T);
     constexpr int SV = Trd2SV<T>::value;
     constexpr int SVT = SV / CW;                   // tiles per staged run of v
-    pdl_wait_then_trigger();
+    // `early` (set for every column but the first of a panel): the previous kernel is the w kernel of column c - 1, which
+    // writes only column c of A and the panel buffers - not the trailing block the tiles cover (the one stored column of
+    // a boundary strip that it does touch is masked out of the sums).  The producer may then fill the ring BEFORE the
+    // programmatic dependency resolves: ~190 KB per SM stream in under the w kernel, and the consumers find their first
+    // tiles waiting.  The consumers - who read what the w kernel wrote - wait as before.
+    if (!early) pdl_wait_then_trigger();
     extern __shared__ __align__(128) unsigned char trd2_smem_raw[];
     unsigned char* ring = trd2_smem_raw + ((128u - (smem_u32(trd2_smem_raw) & 127u)) & 127u);
     __shared__ T s_v[SV];
     __shared__ T s_col[2][8][CW];
+    __shared__ T s_vb[TRD2_BH];                    // v over the rows of the current band (column pass)
     __shared__ double s_q[8];
     __shared__ __align__(8) uint64_t full_bar[TRD2_NST], empty_bar[TRD2_NST];
 
@@ -135,55 +141,87 @@ trd_symv2_kernel(const __grid_constant__ CUtensorMap tmap, TrdCtx<T> x, int c, i
     }
 
     // ---- consumers ----
-    // reflector scalars: every warp sums the partial norms itself in the same fixed order
-    double sigma = 0.0;
-    for (int q = lane; q < npn; q += 32) sigma += x.pn[q];
-    sigma = warp_sum(sigma);
+    if (early) pdl_wait_then_trigger();
+    // The launch is a chain of L2 latencies before the first tile is touched (ncu: 12 % of the stall samples sat in this
+    // prologue), so every load whose ADDRESS is known is put in flight first: the partial norms, alpha, the raw column
+    // entries this thread will scale into v (its row of the first band, its entries of the first staged run of strips,
+    // its row of the V(:, i) slice) and the panel-dot partials; the scale-dependent arithmetic follows.
     const T* Acol = x.A + (size_t)c * x.lda;
+    {
+        const int J1 = (t_beg < t_end) ? trd_tile_band(tl, t_beg) : tl.J0;
+        const int S1 = (t_beg < t_end) ? tl.S0 + (t_beg - trd_band_first_tile(tl, J1)) : tl.S0;
+        const int g1 = BH * J1 + tid;
+        if (g1 > row0 && g1 < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(Acol + g1));
+        for (int e = tid; e < SV; e += 256) {
+            const int gcol = CW * S1 + e;
+            if (gcol > row0 && gcol < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(Acol + gcol));
+        }
+    }
+    // reflector scalars: every warp sums the partial norms itself in the same fixed order (loads first, then the sum)
+    double sigma = 0.0;
+    {
+        constexpr int PU = 8;
+        for (int q0 = 0; q0 < npn; q0 += 32 * PU) {
+            double pv[PU];
+#pragma unroll
+            for (int u = 0; u < PU; ++u) {
+                const int q = q0 + lane + 32 * u;
+                pv[u] = q < npn ? x.pn[q] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < PU; ++u) sigma += pv[u];
+        }
+    }
     const T alpha = Acol[row0];
+    // panel dot product number g: the partials of the previous w kernel's CTAs (rows >= row0 + 1 of the unscaled column)
+    const bool tdot = g < 2 * i;
+    const bool isw = g < i;
+    const int tp = isw ? g : g - i;
+    T tacc = zero<T>(), tfirst = zero<T>();
+    if (tdot) {
+        const T* src = x.tpart + (size_t)(isw ? tp : TRD_NB + tp) * x.tpld;
+        for (int b = tid; b < npn; b += 256) tacc = add_(tacc, src[b]);
+        if (tid == 0) tfirst = conj_(x.P[(size_t)(isw ? x.pw + tp : tp) * x.ldp + row0]);
+    }
+    int r_lo, r_hi;
+    trd_slice(tl, g, r_lo, r_hi);
+    const int slen = r_hi - r_lo;                  // <= 64 (G >= mt / 64 is checked on the host)
+    const int sgr = row0 + r_lo + tid;
+    T sraw = zero<T>();
+    if (tid < slen && sgr > row0 && sgr < n) sraw = Acol[sgr];
+    sigma = warp_sum(sigma);
     double beta; T tau, scale;
     larfgp_scalars<T>(alpha, sigma, beta, tau, scale);
 
     // V(:, i) over this CTA's row slice (two copies in the panel buffer)
-    {
-        int r_lo, r_hi;
-        trd_slice(tl, g, r_lo, r_hi);
-        const int len = r_hi - r_lo;               // <= 64 (G >= mt / 64 is checked on the host)
-        if (tid < len) {
-            const int gr = row0 + r_lo + tid;
-            const T vq = trd2_v<T>(Acol, gr, row0, n, scale);
-            x.P[(size_t)i * x.ldp + gr] = vq;
-            x.P[(size_t)(2 * x.pw + i) * x.ldp + gr] = vq;
-        }
+    if (tid < slen) {
+        const T vq = (sgr == row0) ? one<T>() : ((sgr > row0 && sgr < n) ? mul_(sraw, scale) : zero<T>());
+        x.P[(size_t)i * x.ldp + sgr] = vq;
+        x.P[(size_t)(2 * x.pw + i) * x.ldp + sgr] = vq;
     }
-    // panel dot product number g: sum of the partials of the previous w kernel's CTAs (rows >= row0 + 1 of the
-    // unscaled column), times scale, plus the row-row0 term (v[row0] = 1)
-    if (g < 2 * i) {
-        const bool isw = g < i;
-        const int p = isw ? g : g - i;
-        const T* src = x.tpart + (size_t)(isw ? p : TRD_NB + p) * x.tpld;
-        T acc = zero<T>();
-        for (int b = tid; b < npn; b += 256) acc = add_(acc, src[b]);
-        acc = warp_sum(acc);
-        if (lane == 0) s_col[0][warp][0] = acc;
+    // ... times scale, plus the row-row0 term (v[row0] = 1)
+    if (tdot) {
+        tacc = warp_sum(tacc);
+        if (lane == 0) s_col[0][warp][0] = tacc;
         bar_consumers();
         if (tid == 0) {
             T tot = s_col[0][0][0];
 #pragma unroll
             for (int w = 1; w < 8; ++w) tot = add_(tot, s_col[0][w][0]);
-            const T first = conj_(x.P[(size_t)(isw ? x.pw + p : p) * x.ldp + row0]);
-            x.t[isw ? p : TRD_NB + p] = add_(first, mul_(scale, tot));
+            x.t[isw ? tp : TRD_NB + tp] = add_(tfirst, mul_(scale, tot));
         }
-        bar_consumers();                           // s_col is reused by the tile loop
     }
 
     double qacc = 0.0;
     if (t_beg < t_end) {
+        constexpr int CPW = CW / 8;                  // tile columns owned by a warp in the column pass
+        constexpr int RPL = BH / 32;                 // rows per lane in the column pass
         int J = trd_tile_band(tl, t_beg);
         int S = tl.S0 + (t_beg - trd_band_first_tile(tl, J));
         int Slast = trd_band_last_strip(tl, J);
-        const int rr = tid;                          // row inside the tile (warp w owns rows 32w..32w+31)
+        const int rr = tid;                          // row pass: thread = row of the tile
         T vr = zero<T>(), rowacc = zero<T>();
+        T vcol[RPL];                                 // column pass: v at rows lane + 32 i of the band
         double adiag = 0.0;
         bool band_open = false;
         int run_left = 0, sv_base = 0;               // staged strips of v: global columns [sv_base, sv_base + CW*run)
@@ -195,6 +233,11 @@ trd_symv2_kernel(const __grid_constant__ CUtensorMap tmap, TrdCtx<T> x, int c, i
                 adiag = 0.0;
                 band_open = true;
                 run_left = 0;
+                bar_consumers();                     // previous band's s_vb has been read by everybody
+                s_vb[tid] = vr;
+                bar_consumers();
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) vcol[q] = s_vb[lane + 32 * q];
             }
             if (run_left == 0) {
                 // stage v for the next strips of this band inside the chunk
@@ -211,43 +254,42 @@ trd_symv2_kernel(const __grid_constant__ CUtensorMap tmap, TrdCtx<T> x, int c, i
             const T* src = tile + (size_t)(rr / RB) * (CW * RB) + (rr % RB);
             const T* sv = s_v + (CW * S - sv_base);
             const int gc0 = CW * S;
-            T colacc[CW];
-            if (gc0 + CW - 1 < BH * J) {
-                // every column of the strip is left of every row of the band: no triangle mask
+            const bool interior = gc0 + CW - 1 < BH * J;   // every column of the strip is left of every row of the band
+            // ---- row pass: y_row[r] += sum_k A[r,k] v[k]  (two accumulators: half the dependent chain) ----
+            T racc2 = zero<T>();
+            if (interior) {
 #pragma unroll
-                for (int k = 0; k < CW; ++k) {
-                    const T a = src[k * RB];
-                    fma_(rowacc, a, sv[k]);
-                    colacc[k] = zero<T>();
-                    fmac_(colacc[k], a, vr);
+                for (int k = 0; k < CW; k += 2) {
+                    fma_(rowacc, src[k * RB], sv[k]);
+                    fma_(racc2, src[(k + 1) * RB], sv[k + 1]);
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < CW; ++k) {
                     const int gc = gc0 + k;
-                    colacc[k] = zero<T>();
-                    if (gr > gc) {
-                        const T a = src[k * RB];
-                        fma_(rowacc, a, sv[k]);
-                        fmac_(colacc[k], a, vr);
-                    } else if (gr == gc) {
-                        adiag = real_(src[k * RB]);   // Hermitian: real diagonal
-                    }
+                    if (gr > gc) fma_(rowacc, src[k * RB], sv[k]);
+                    else if (gr == gc) adiag = real_(src[k * RB]);   // Hermitian: real diagonal
                 }
+            }
+            rowacc = add_(rowacc, racc2);
+            // ---- column pass: warp w owns tile columns [w CPW, (w+1) CPW): y_col[k] = sum_r conj(A[r,k]) v[r] over the
+            // band's 256 rows, 8 per lane, one warp reduction per column and NO cross-warp step: the warps never meet
+            // inside a run of strips, each releases the stage when it is done with it ----
+#pragma unroll
+            for (int kk = 0; kk < CPW; ++kk) {
+                const int k = warp * CPW + kk, gc = gc0 + k;
+                T cacc = zero<T>();
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) {
+                    const int r2 = lane + 32 * q;
+                    const T a = tile[(size_t)(r2 / RB) * (CW * RB) + k * RB + (r2 % RB)];
+                    if (interior || BH * J + r2 > gc) fmac_(cacc, a, vcol[q]);
+                }
+                cacc = warp_sum(cacc);
+                if (lane == 0 && gc < n) x.ycolp[(size_t)J * x.ldy + gc] = cacc;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[st]);
-            // column parts of this tile: lanes -> warps -> ycol[J][gc0 .. gc0+CW)
-            MultiReduce<T, CW, 16>::run(colacc, lane);
-            const int par = it & 1;
-            if (trd2_owner_lane<CW>(lane)) s_col[par][warp][trd2_owned<CW>(lane)] = colacc[0];
-            bar_consumers();
-            if (tid < CW) {
-                T v = s_col[par][0][tid];
-#pragma unroll
-                for (int w = 1; w < 8; ++w) v = add_(v, s_col[par][w][tid]);
-                if (gc0 + tid < n) x.ycolp[(size_t)J * x.ldy + gc0 + tid] = v;
-            }
             --run_left;
             const bool band_end = (S == Slast) || (t + 1 == t_end);
             if (band_end) {
@@ -336,8 +378,20 @@ trd_w2_kernel(TrdCtx<T> x, int c, int i, int G, int do_next) {
     }
     T yhv = zero<T>(), y0 = zero<T>();
     if (scalar_warp) {
-        for (int q = lane; q < G; q += 32) yhv = add_(yhv, x.pyv[q]);
+        // (loads first, then the sums: a fused loop is one L2 round trip per iteration, and this warp's chain - G / 32
+        // of them - is the critical path of the launch)
+        constexpr int PU = 8;
         y0 = trd2_ysum<T>(x, tl, row0, lane, 32);
+        for (int q0 = 0; q0 < G; q0 += 32 * PU) {
+            T pv[PU];
+#pragma unroll
+            for (int u = 0; u < PU; ++u) {
+                const int q = q0 + lane + 32 * u;
+                pv[u] = q < G ? x.pyv[q] : zero<T>();
+            }
+#pragma unroll
+            for (int u = 0; u < PU; ++u) yhv = add_(yhv, pv[u]);
+        }
     }
     __syncthreads();
     T part = zero<T>(), part2 = zero<T>();
