@@ -339,7 +339,7 @@ static int gemm_variant() {
 // K at or below which the two-CTA-per-SM configuration is used (0 disables)
 static int gemm_shortk() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("MAKB200_GEMM_SHORTK"); v = e ? atoi(e) : 256; if (v < 0) v = 0; }
+    if (v < 0) { const char* e = getenv("MAKB200_GEMM_SHORTK"); v = e ? atoi(e) : 0; if (v < 0) v = 0; }
     return v;
 }
 

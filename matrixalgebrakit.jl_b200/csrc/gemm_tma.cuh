@@ -88,15 +88,21 @@ __device__ __forceinline__ unsigned tg_lane_off(int s, int lr, int lc, int half)
     }
 }
 
-template <bool TA, bool TB>
+// CST: the C tile goes through shared memory by TMA in both directions (rank-k updates on a large C, K <= 1024): the
+// load of the old tile (beta != 0) is issued before the main loop and lands under it; the epilogue reads and rewrites
+// the tile in shared memory and ONE lane stores it with cp.async.bulk.tensor (SASS UTMASTG) - full-line coalesced
+// writes, no per-thread global round trips.  With the 128 KB tile the ring has ST = 3 stages (enough for <= 64 k-tiles).
+template <bool TA, bool TB, int ST, bool CST>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const GemmProblem<double> p, int splitk, double* __restrict__ ws) {
-    constexpr int BM = TG_BM, BN = TG_BN, BK = TG_BK, ST = TG_ST;
+                const __grid_constant__ CUtensorMap tmC, const GemmProblem<double> p, int splitk, double* __restrict__ ws) {
+    constexpr int BM = TG_BM, BN = TG_BN, BK = TG_BK;
     constexpr int WM = 32, WN = 32, MT = 4, NT = 4, WARPS_M = BM / WM;
     extern __shared__ __align__(1024) unsigned char tg_smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[ST], empty_bar[ST];
+    __shared__ __align__(8) uint64_t c_bar;
     const unsigned ring = (tg_smem_u32(tg_smem_raw) + 1023u) & ~1023u;
+    const unsigned sC = ring + (unsigned)ST * TG_STAGE_BYTES;      // CST: 128 x 128 doubles, [n][m] dense
 
     const int M = p.m, N = p.n, K = p.k;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -105,7 +111,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     const int ktiles = (K + BK - 1) / BK;
     int kt_beg = 0, kt_end = ktiles;
-    if (splitk > 1) {
+    if (!CST && splitk > 1) {
         const int per = (ktiles + splitk - 1) / splitk;
         kt_beg = blockIdx.z * per;
         kt_end = min(ktiles, kt_beg + per);
@@ -114,11 +120,19 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int nkt = kt_end - kt_beg;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+    const bool beta0 = (p.beta == 0.0);
     if (tid == 0) {
         for (int st = 0; st < ST; ++st) { tg_mbar_init(&full_bar[st], 1); tg_mbar_init(&empty_bar[st], TG_MATH_WARPS); }
+        if (CST) tg_mbar_init(&c_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
+    if (CST && tid == 0 && !beta0) {
+        // old C tile: four boxes of 128 (m) x 32 (n), under the main loop
+        tg_mbar_expect_tx(&c_bar, BM * BN * 8);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) tg_tma_2d(sC + b * (BM * 32 * 8), &tmC, &c_bar, m0, n0 + 32 * b);
+    }
 
     // ---- loads: stage `it` of this CTA's k range (issued by thread 0) ----
     auto issue = [&](int it) {
@@ -196,11 +210,40 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (lane == 0) tg_mbar_arrive(&empty_bar[st]);
     }
 
+    if constexpr (CST) {
+        // ---- staged epilogue: combine with the old tile in shared memory, one bulk store of the tile ----
+        if (!beta0) tg_mbar_wait(&c_bar, 0);
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const int rl = wm + i * 8 + lr;
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int cl = wn + j * 8 + lc * 2 + e;
+                    const unsigned a = sC + (unsigned)((cl * BM + rl) * 8);
+                    double v = p.alpha * acc[i][j][e];
+                    if (!beta0) v = fma(p.beta, tg_lds(a), v);
+                    asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(a), "d"(v) : "memory");
+                }
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the TMA store
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(&tmC),
+                             "r"(sC + b * (BM * 32 * 8)), "r"(m0), "r"(n0 + 32 * b)
+                             : "memory");
+            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // the tile must outlive the reads of the store
+        }
+        return;
+    }
     // ---- epilogue: thread holds C[row = lr][cols = 2*lc, 2*lc+1] of each 8x8 tile; the C values of one row block
     // are loaded together before any store (beta != 0: the loads of a read-modify-write chain would otherwise
     // serialise behind the stores, 32 L2 round trips per thread) ----
     const bool partial = splitk > 1;
-    const bool beta0 = (p.beta == 0.0);
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
         const int r = m0 + wm + i * 8 + lr;
@@ -407,7 +450,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 tg_encoder() {
 }
 // Tensor map over a column-major operand stored as (rows x cols, leading dimension ld): dim 0 = rows (contiguous).
 // box0 x box1 elements per TMA box.
-static bool tg_make_map(CUtensorMap* tm, const double* base, int rows, int cols, int ld, int box0, int box1) {
+static bool tg_make_map(CUtensorMap* tm, const double* base, int rows, int cols, int ld, int box0, int box1, bool swizzle = true) {
     PFN_cuTensorMapEncodeTiled_v12000 enc = tg_encoder();
     if (!enc) return false;
     cuuint64_t gdim[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
@@ -415,7 +458,8 @@ static bool tg_make_map(CUtensorMap* tm, const double* base, int rows, int cols,
     cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
     cuuint32_t estr[2] = {1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 static bool tg_enabled() {
     static const bool v = []() { const char* e = getenv("MAKB200_GEMM_TMA"); return !(e && e[0] == '0'); }();
@@ -426,40 +470,52 @@ static bool tg_operand_ok(const double* p, int ld) {
     return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((ld & 1) == 0) && ld > 0;
 }
 
-template <bool TA, bool TB>
-static cudaError_t tg_launch(cudaStream_t stream, dim3 grid, const CUtensorMap& tmA, const CUtensorMap& tmB,
+template <bool TA, bool TB, int ST, bool CST>
+static cudaError_t tg_launch(cudaStream_t stream, dim3 grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                              const GemmProblem<double>& p, int splitk, double* ws) {
-    constexpr size_t smem = (size_t)TG_ST * TG_STAGE_BYTES + 1024;
+    constexpr size_t smem = (size_t)ST * TG_STAGE_BYTES + (CST ? (size_t)TG_BM * TG_BN * 8 : 0) + 1024;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel<TA, TB, ST, CST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     g_clock_gemm.begin(stream);
-    gemm_tma_kernel<TA, TB><<<grid, TG_THREADS, smem, stream>>>(tmA, tmB, p, splitk, ws);
+    gemm_tma_kernel<TA, TB, ST, CST><<<grid, TG_THREADS, smem, stream>>>(tmA, tmB, tmC, p, splitk, ws);
     g_clock_gemm.end(stream);
     count_launch();
     return cudaGetLastError();
+}
+static int tg_cstage_maxk() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MAKB200_GEMM_CSTAGE_MAXK"); v = e ? atoi(e) : 1024; if (v < 0) v = 0; }
+    return v;
 }
 
 // returns false when the TMA path does not apply (the caller then takes the cp.async kernel)
 static bool gemm_tma_try(cudaStream_t stream, bool ta, bool tb, dim3 grid, const GemmProblem<double>& p, int splitk,
                          double* ws, cudaError_t* err) {
     if (!tg_enabled() || !tg_operand_ok(p.A, p.lda) || !tg_operand_ok(p.B, p.ldb)) return false;
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmC;
     // A as stored: op N -> M x K (M contiguous, MN-major boxes 16 x 16); op T/C -> K x M (K contiguous, box 16 x 128)
     const bool okA = ta ? tg_make_map(&tmA, p.A, p.k, p.m, p.lda, TG_BK, TG_BM) : tg_make_map(&tmA, p.A, p.m, p.k, p.lda, 16, TG_BK);
     // B as stored: op N -> K x N (K contiguous, box 16 x 128); op T/C -> N x K (N contiguous, boxes 16 x 16)
     const bool okB = tb ? tg_make_map(&tmB, p.B, p.n, p.k, p.ldb, 16, TG_BK) : tg_make_map(&tmB, p.B, p.k, p.n, p.ldb, TG_BK, TG_BN);
     if (!okA || !okB) return false;
-    if (!ta && !tb) *err = tg_launch<false, false>(stream, grid, tmA, tmB, p, splitk, ws);
-    else if (ta && !tb) *err = tg_launch<true, false>(stream, grid, tmA, tmB, p, splitk, ws);
-    else if (!ta && tb) *err = tg_launch<false, true>(stream, grid, tmA, tmB, p, splitk, ws);
-    else *err = tg_launch<true, true>(stream, grid, tmA, tmB, p, splitk, ws);
+    // staged C tile: a rank-k update (short K, no split-K) whose C a tensor map can describe
+    const bool cst = splitk == 1 && p.k <= tg_cstage_maxk() && tg_operand_ok(p.C, p.ldc) &&
+                     tg_make_map(&tmC, p.C, p.m, p.n, p.ldc, TG_BM, 32, false);
+    if (!cst) tmC = tmA;   // unused
+#define TG_DISPATCH(TA_, TB_)                                                                                  \
+    (cst ? tg_launch<TA_, TB_, 3, true>(stream, grid, tmA, tmB, tmC, p, splitk, ws)                            \
+         : tg_launch<TA_, TB_, TG_ST, false>(stream, grid, tmA, tmB, tmC, p, splitk, ws))
+    if (!ta && !tb) *err = TG_DISPATCH(false, false);
+    else if (ta && !tb) *err = TG_DISPATCH(true, false);
+    else if (!ta && tb) *err = TG_DISPATCH(false, true);
+    else *err = TG_DISPATCH(true, true);
+#undef TG_DISPATCH
     return true;
 }
-
 
 template <bool TA, bool TB>
 static cudaError_t tgc_launch(cudaStream_t stream, dim3 grid, const CUtensorMap& tmA, const CUtensorMap& tmB,
