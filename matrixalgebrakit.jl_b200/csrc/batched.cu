@@ -227,8 +227,11 @@ batched_svd_kernel(const SvdBlockDesc<T>* __restrict__ descs, int* __restrict__ 
                     fmac_(ga, xv, yv);  // x^H y
                 }
                 al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
-                double ag = sqrt(abs2_(ga));
-                if (ag > tol * sqrt(al * be) && ag > 0.0) {
+                // |x^H y| against ||x|| ||y||: no product of squared norms and no squared inner product, so blocks scaled
+                // by 1e-100 or 1e+100 rotate exactly as the same block at unit scale (al * be and |ga|^2 are 4th-order
+                // quantities: they left the double range beyond 1e+-77 and the sweep either never rotated or never ended)
+                double ag = abs_(ga);
+                if (ag > tol * (sqrt(al) * sqrt(be)) && ag > 0.0) {
                     if (lane == 0) s_rot = 1;
                     double zeta = (be - al) / (2.0 * ag);
                     double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
@@ -460,7 +463,7 @@ batched_eigh_kernel(const EighBlockDesc<T>* __restrict__ descs, int* __restrict_
                 T ph = one<T>();
                 if (q < n) {
                     const T g = S[(size_t)q * ld + p];           // a_pq
-                    const double ag = sqrt(abs2_(g));
+                    const double ag = abs_(g);
                     if (ag > thr) {
                         const double al = real_(S[(size_t)p * ld + p]), be = real_(S[(size_t)q * ld + q]);
                         const double zeta = (be - al) / (2.0 * ag);

@@ -1067,6 +1067,34 @@ int makb200_tsqr(makb200_handle_t* h, void* comm, int dtype, int m, int n, void*
 
 }  // extern "C"
 
+#include "polar_lockstep.cuh"
+// ---- lock-step QDWH of a chunk of mid-size blocks (phase 1 of the phased batched SVD) -------------------------
+static bool lockstep_enabled() {
+    const char* e = getenv("MAKB200_SVD_LOCKSTEP");   // read per call: tests run both paths
+    return !(e && e[0] == '0');
+}
+// workspace of the lock-step phase for `chunk` blocks no larger than mmax x nmax: tables, per-block buffers and the
+// batched QR of the stacked [sqrt(c) X; I] (and of the tall blocks)
+template <typename T>
+static size_t svd_lockstep_bytes(makb200_handle_t* h, size_t chunk, int mmax, int nmax, bool any_tall, size_t* blocks_bytes,
+                                 size_t* tables_bytes, size_t* qr_bytes) {
+    constexpr int nb = mak::CholNB<T>::value;
+    const size_t tb = mak::ls_tables_bytes<T>((int)chunk, nmax, any_tall);
+    const int mrow = any_tall ? std::max(mmax, nmax + 1) : nmax;
+    const size_t bb = chunk * mak::align_up(mak::ls_block_elems<T>(mrow, nmax, nb) * sizeof(T), 256);
+    std::vector<int> m2(chunk, 2 * nmax), nn(chunk, nmax);
+    size_t qb = qr_batched_worksize_t<T>(h, (int)chunk, m2.data(), nn.data());
+    if (any_tall) {
+        std::vector<int> mt(chunk, mrow);
+        qb = std::max(qb, qr_batched_worksize_t<T>(h, (int)chunk, mt.data(), nn.data()));
+    }
+    qb = mak::align_up(qb, 256) + 4096;
+    if (blocks_bytes) *blocks_bytes = bb;
+    if (tables_bytes) *tables_bytes = tb;
+    if (qr_bytes) *qr_bytes = qb;
+    return tb + bb + qb + 1024;
+}
+
 // ---- batched svd --------------------------------------------------------------------------
 constexpr int SVD_PHASE_CHUNK = 192;     // blocks per one-launch tridiagonalisation (>= one CTA per SM)
 static bool phased_enabled() {
@@ -1136,17 +1164,33 @@ static int svd_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int
     if (vectors && phased_enabled() && !graphs_enabled()) {
         std::vector<int> ph, rest;
         for (int i : big) ((m[i] >= n[i] && n[i] >= 3 && n[i] <= mak::BHETRD_MAX_N) ? ph : rest).push_back(i);
+        // n descending: a chunk holds blocks of similar size (the lock-step launches are sized by the largest)
+        std::stable_sort(ph.begin(), ph.end(), [&](int a, int b) { return n[a] > n[b]; });
         size_t scratch = 0, persist = 0;
+        int ls_mmax = 0, ls_nmax = 0;
+        bool ls_tall = false;
         for (int i : ph) {
             scratch = std::max(scratch, mak::svd_phase_scratch_t<T>(h, m[i], n[i]));
             persist = std::max(persist, svd_phase_persist_bytes<T>(m[i], n[i]));
+            ls_mmax = std::max(ls_mmax, m[i]); ls_nmax = std::max(ls_nmax, n[i]);
+            ls_tall = ls_tall || m[i] > n[i];
         }
         const size_t np_pool = (size_t)pool_streams();
         const size_t pool_region = (scratch + 1024) * np_pool;
+        // lock-step phase 1 (default): its region sits at the end of the workspace; without room for it the chunk's
+        // QDWH runs block by block on the pool as before
+        size_t ls_total = 0, ls_bb = 0, ls_tb = 0, ls_qb = 0;
+        bool lockstep = lockstep_enabled() && ph.size() >= 8;
+        if (lockstep) {
+            const size_t c0 = std::min<size_t>((size_t)SVD_PHASE_CHUNK, ph.size());
+            ls_total = svd_lockstep_bytes<T>(h, c0, ls_mmax, ls_nmax, ls_tall, &ls_bb, &ls_tb, &ls_qb);
+            if (lbig < pool_region + 4096 + ls_total + c0 * (persist + sizeof(mak::BhetrdDesc<T>) + 64)) { lockstep = false; ls_total = 0; }
+        }
         size_t chunk = 0;
-        if (!ph.empty() && lbig > pool_region + 4096) chunk = std::min<size_t>({(size_t)SVD_PHASE_CHUNK, ph.size(), (lbig - pool_region - 4096) / (persist + sizeof(mak::BhetrdDesc<T>) + 64)});
+        if (!ph.empty() && lbig > pool_region + 4096 + ls_total) chunk = std::min<size_t>({(size_t)SVD_PHASE_CHUNK, ph.size(), (lbig - pool_region - 4096 - ls_total) / (persist + sizeof(mak::BhetrdDesc<T>) + 64)});
         if (ph.size() >= 8 && chunk >= 8) {
             char* pbase = wbig + pool_region;
+            char* ls_base = wbig + lbig - ls_total;   // [tables | per-block buffers | batched-QR workspace]
             mak::BhetrdDesc<T>* ddev = (mak::BhetrdDesc<T>*)pbase;
             char* store = pbase + mak::align_up(sizeof(mak::BhetrdDesc<T>) * chunk, 256);
             struct Blk { T *W, *P, *V, *tau; double *wv, *flag, *d, *e; };
@@ -1178,11 +1222,51 @@ static int svd_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int
                     slot_of[i] = (int)q;
                     if (n[i] > nmax) nmax = n[i];
                 }
-                int rc = run_pooled(h, ids, wbig, pool_region, [&](makb200_handle_t* hh, char* w, size_t lw, int i) {
-                    const Blk& b = blk[slot_of[i]];
-                    return mak::svd_phase1_t<T>(hh, m[i], n[i], (T*)A[i], lda[i], b.W, b.P, 2.2e-16, w, lw);
-                });
-                if (rc) return rc;
+                int rc = 0;
+                bool ls_done = false;
+                if (lockstep) {
+                    // phase 1 in lock-step: every block of the chunk advances through the same QDWH schedule, one grouped
+                    // GEMM / batched kernel per step (csrc/polar_lockstep_plan.h)
+                    constexpr int lnb = mak::CholNB<T>::value;
+                    std::vector<mak::LsBlk<T>> lb(nc);
+                    char* ls_tables = (char*)mak::align_up((size_t)(uintptr_t)ls_base, 256);
+                    T* bp = (T*)(ls_tables + ls_tb);
+                    char* ls_qr = (char*)bp + ls_bb;
+                    std::vector<int> m2(nc), nn(nc), mt, nt;
+                    for (size_t q = 0; q < nc; ++q) {
+                        const int i = ids[q];
+                        mak::LsBlk<T>& l = lb[q];
+                        l = mak::LsBlk<T>{};
+                        l.m = m[i]; l.n = n[i];
+                        l.A = (const T*)A[i]; l.lda = lda[i];
+                        l.W = blk[q].W; l.P = blk[q].P;
+                        mak::ls_carve_block<T>(l, bp, lnb);
+                        bp = (T*)mak::align_up((size_t)(uintptr_t)bp, 256);
+                        m2[q] = 2 * n[i]; nn[q] = n[i];
+                        if (m[i] > n[i]) { mt.push_back(m[i]); nt.push_back(n[i]); }
+                    }
+                    size_t qneed = qr_batched_worksize_t<T>(h, (int)nc, m2.data(), nn.data());
+                    if (!mt.empty()) qneed = std::max(qneed, qr_batched_worksize_t<T>(h, (int)mt.size(), mt.data(), nt.data()));
+                    if ((char*)bp <= ls_qr && qneed <= ls_qb) {
+                        rc = mak::polar_lockstep_run<T>(h, lb, ls_tables, ls_tb,
+                            [&](int nbat, const int* qm, const int* qn, void* const* qA, const int* qlda, void* const* qQ,
+                                const int* qldq, void* const* qR, const int* qldr) {
+                                return qr_batched_t<T>(h, nbat, qm, qn, qA, qlda, qQ, qldq, qR, qldr, nullptr, ls_qr, ls_qb);
+                            });
+                        if (rc) return rc;
+                        ls_done = true;
+                    }
+                }
+                if (getenv("MAKB200_LOCKSTEP_VERBOSE"))
+                    fprintf(stderr, "[makb200] batched svd chunk of %zu blocks (n <= %d): QDWH %s\n", nc, n[ids[0]],
+                            ls_done ? "in lock-step" : "per block on the stream pool");
+                if (!ls_done) {
+                    rc = run_pooled(h, ids, wbig, pool_region, [&](makb200_handle_t* hh, char* w, size_t lw, int i) {
+                        const Blk& b = blk[slot_of[i]];
+                        return mak::svd_phase1_t<T>(hh, m[i], n[i], (T*)A[i], lda[i], b.W, b.P, 2.2e-16, w, lw);
+                    });
+                    if (rc) return rc;
+                }
                 {
                     mak::Stager st(h, nc * sizeof(mak::BhetrdDesc<T>) + 1024);
                     MAK_CUDA(h, st.put(ddev, bd.data(), nc * sizeof(mak::BhetrdDesc<T>), h->stream));
@@ -1306,16 +1390,25 @@ size_t makb200_svd_batched_worksize(makb200_handle_t* h, int dtype, int batch, c
     // graph-replayed path: staging copies of A, U, Vh, S per slot + one defect indicator per big block
     const size_t staging = mak::align_up(st_a * esz, 256) + mak::align_up(st_u * esz, 256) + mak::align_up(st_v * esz, 256) +
                            mak::align_up(st_s * 8, 256) + 1024;
-    // phased path: per-block W, P, V, ... of one chunk + its descriptors
+    // phased path: per-block W, P, V, ... of one chunk + its descriptors, and the lock-step QDWH region
     size_t persist = 0;
+    int ls_mmax = 0, ls_nmax = 0;
+    bool ls_tall = false;
     for (int i = 0; i < batch; ++i) {
         if (m[i] <= 0 || n[i] <= 0 || m[i] < n[i] || n[i] > mak::BHETRD_MAX_N) continue;
         if (mak::batched_svd_smem_bytes(m[i], n[i], esz) <= mak::batched_svd_max_smem_bytes()) continue;
         const size_t pb = dtype == MAKB200_F64 ? svd_phase_persist_bytes<double>(m[i], n[i]) : svd_phase_persist_bytes<cplx>(m[i], n[i]);
         if (pb > persist) persist = pb;
+        if (n[i] >= 3) {
+            ls_mmax = std::max(ls_mmax, m[i]); ls_nmax = std::max(ls_nmax, n[i]);
+            ls_tall = ls_tall || m[i] > n[i];
+        }
     }
     const size_t chunk = nbig < (size_t)SVD_PHASE_CHUNK ? nbig : (size_t)SVD_PHASE_CHUNK;
-    const size_t phased = chunk * (persist + sizeof(mak::BhetrdDesc<cplx>) + 64) + 8192;
+    size_t phased = chunk * (persist + sizeof(mak::BhetrdDesc<cplx>) + 64) + 8192;
+    if (ls_nmax > 0 && chunk >= 8)
+        phased += (dtype == MAKB200_F64 ? svd_lockstep_bytes<double>(h, chunk, ls_mmax, ls_nmax, ls_tall, nullptr, nullptr, nullptr)
+                                        : svd_lockstep_bytes<cplx>(h, chunk, ls_mmax, ls_nmax, ls_tall, nullptr, nullptr, nullptr)) + 512;
     return bytes + pooled_worksize(big, nbig, staging) + phased + mak::align_up(sizeof(double) * nbig, 256) + 512;
 }
 

@@ -6,22 +6,10 @@
 // Complex products are 4 real DMMAs on the interleaved (re,im) tiles.
 #pragma once
 #include "common.cuh"
+#include "batched_desc.h"   // GemmProblem<T>
 
 namespace mak {
 
-template <typename T>
-struct GemmProblem {
-    int m, n, k;
-    const T* A;
-    int lda;
-    const T* B;
-    int ldb;
-    T* C;
-    int ldc;
-    T alpha, beta;
-    int conja, conjb;
-    int lower;  // 1: C is only needed on/below the diagonal (tiles above are skipped)
-};
 
 // Host-side launcher.  opa/opb: MAKB200_OP_{N,T,C}.  `ws`/`ws_bytes`: optional split-K
 // scratch (may be null -> no split-K).  Asynchronous on `stream`.

@@ -9,6 +9,7 @@
 // The iteration schedule (a,b,c per step) depends only on the scalar lower bound l0 and is
 // computed on the host, so the device loop runs without a host round trip.
 #include "polar.cuh"
+#include "potf2.cuh"
 #include "eigh.cuh"
 #include "gemm.cuh"
 #include "qr.cuh"
@@ -19,8 +20,6 @@
 
 namespace mak {
 
-template <typename T> struct CholNB { static constexpr int value = 128; };
-template <> struct CholNB<cplx> { static constexpr int value = 64; };
 constexpr size_t POTRF_AUX_BYTES = (size_t)64 * 128 * 128 * sizeof(double);
 
 #define MAK_GEMM2(h, ...)                                              \
@@ -296,120 +295,6 @@ __global__ void adjoint_kernel(int m, int n, const T* __restrict__ S, int lds, T
     }
 }
 
-__device__ __forceinline__ double shfl_xor_any(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
-__device__ __forceinline__ cplx shfl_xor_any(cplx v, int o) {
-    return cplx{__shfl_xor_sync(0xffffffffu, v.re, o), __shfl_xor_sync(0xffffffffu, v.im, o)};
-}
-// ---------------------------------------------------------------------------------------
-// Cholesky building blocks
-// ---------------------------------------------------------------------------------------
-// one CTA: L = chol(Zblk) (nb x nb, lower) and Linv = L^-1; both written with zeros above the
-// diagonal.  info[0] set to 1 if a pivot is not positive.
-// The block is held in REGISTERS, 2-D cyclic over a 16 x 16 thread grid (thread (ti,tj) owns rows
-// ti+16a, columns tj+16b); per column k: pivot -> scaled column to shared memory -> rank-1 update
-// of the register tile.  Two block barriers per column, no shared-memory traffic for the matrix.
-template <typename T, int NB>
-__global__ void __launch_bounds__(256)
-potf2_inv_kernel(int nb, const T* __restrict__ Zb, int ldz, T* __restrict__ Lb, int ldl, T* __restrict__ Linv,
-                 int ldi, int* info) {
-    constexpr int E = NB / 16;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* S = reinterpret_cast<T*>(smem_raw);  // [NB][NB+1] column-major: S[c*(NB+1)+r] (L for the inverse)
-    __shared__ T s_col[NB];
-    __shared__ double s_piv;
-    const int lds = NB + 1, tid = threadIdx.x, ti = tid & 15, tj = tid >> 4;
-    T a[E][E];
-#pragma unroll
-    for (int ia = 0; ia < E; ++ia)
-#pragma unroll
-        for (int ib = 0; ib < E; ++ib) {
-            const int r = ti + 16 * ia, c = tj + 16 * ib;
-            a[ia][ib] = (r < nb && c < nb && r >= c) ? Zb[(size_t)c * ldz + r] : zero<T>();
-        }
-#pragma unroll
-    for (int kb = 0; kb < E; ++kb) {
-        for (int kk = 0; kk < 16; ++kk) {
-            const int k = kb * 16 + kk;
-            if (k >= nb) break;
-            if (ti == kk && tj == kk) {
-                double akk = real_(a[kb][kb]);
-                if (!(akk > 0.0)) { atomicExch(info, 1); akk = 1.0; }
-                s_piv = sqrt(akk);
-            }
-            __syncthreads();
-            const double piv = s_piv, inv = 1.0 / piv;
-            if (tj == kk) {
-#pragma unroll
-                for (int ia = 0; ia < E; ++ia) {
-                    const int r = ti + 16 * ia;
-                    if (r > k) {
-                        T v = scale_(a[ia][kb], inv);
-                        a[ia][kb] = v;
-                        s_col[r] = v;
-                    } else if (r == k) {
-                        a[ia][kb] = mk<T>(piv);
-                    }
-                }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int ia = 0; ia < E; ++ia) {
-                const int r = ti + 16 * ia;
-                if (r > k && r < nb) {
-                    const T lr = s_col[r];
-#pragma unroll
-                    for (int ib = 0; ib < E; ++ib) {
-                        const int c = tj + 16 * ib;
-                        if (c > k && c <= r) a[ia][ib] = sub_(a[ia][ib], mul_(lr, conj_(s_col[c])));
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int ia = 0; ia < E; ++ia)
-#pragma unroll
-        for (int ib = 0; ib < E; ++ib) {
-            const int r = ti + 16 * ia, c = tj + 16 * ib;
-            if (r < nb && c < nb) {
-                T v = (r >= c) ? a[ia][ib] : zero<T>();
-                S[c * lds + r] = v;
-                Lb[(size_t)c * ldl + r] = v;
-            }
-        }
-    __syncthreads();
-    // inverse, in place in shared memory (S is a private copy of L), one column per step from the last to the first:
-    //   X[j,j] = 1 / L[j,j],   X[j+1:, j] = -(X[j+1:, j+1:] L[j+1:, j]) X[j,j]
-    // Row-parallel: thread pair (r, half) takes half of row r's dot product (S is column-major with an odd leading
-    // dimension: consecutive rows hit consecutive banks, L[p,j] is a broadcast).  The r1 version gave every thread a whole
-    // forward substitution through GLOBAL memory (8 k dependent steps for column 0): ~170 us of the ~200 us this kernel
-    // took, and n/128 of them are the serial chain of the blocked Cholesky.
-    {
-        const int r = tid >> 1, hf = tid & 1;
-        for (int j = nb - 1; j >= 0; --j) {
-            T acc = zero<T>();
-            const double dinv = 1.0 / real_(S[j * lds + j]);   // (read before the barrier: row j's thread overwrites it below)
-            if (r > j && r < nb) {
-                // p in (j, r]: X[r,p] * L[p,j]; the two halves interleave p
-                for (int pp = j + 1 + hf; pp <= r; pp += 2) fma_(acc, S[pp * lds + r], S[j * lds + pp]);
-            }
-            // combine the halves (lanes 2q and 2q+1 of the same warp)
-            acc = add_(acc, shfl_xor_any(acc, 1));
-            __syncthreads();                       // everybody has read column j of L
-            if (hf == 0) {
-                if (r == j) S[j * lds + j] = mk<T>(dinv);
-                else if (r > j && r < nb) S[j * lds + r] = scale_(neg_(acc), dinv);
-            }
-            __syncthreads();
-        }
-        for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
-            const int c = idx / nb, rr = idx - c * nb;
-            Linv[(size_t)c * ldi + rr] = (rr >= c) ? S[c * lds + rr] : zero<T>();
-        }
-    }
-}
-
 template <typename T>
 static int potf2_init(makb200_handle* h) {
     constexpr int nb = CholNB<T>::value;
@@ -523,32 +408,6 @@ static int trsm_right(makb200_handle* h, bool conjtrans, int m, int n, const T* 
 // ---------------------------------------------------------------------------------------
 // QDWH
 // ---------------------------------------------------------------------------------------
-struct QdwhStep { double a, b, c; bool qr; };
-constexpr double QDWH_CHOLQR_MAX_C = 1e12;
-
-// QR-type step when c > cmax.  The Cholesky-type step forms X Z^-1 with kappa(Z) <= 1 + c, i.e. an error of
-// ~ c*eps in X; the classical threshold is c > 100.  The parity bound on this path is 10*n*eps, so for
-// large n the threshold is raised to n/8 (error <= n*eps/8): on Gaussian 8192^2 input the second
-// iteration (c ~ 2e2) becomes a Cholesky step, 90 ms instead of 227 ms.
-static std::vector<QdwhStep> qdwh_schedule(double l, int maxiter, double cmax = 100.0) {
-    std::vector<QdwhStep> v;
-    for (int it = 0; it < maxiter; ++it) {
-        if (fabs(1.0 - l) <= 1e-15) {
-            // one Halley step past the nominal convergence point costs little and polishes X^H X = I
-            if (!v.empty() && v.back().c > 3.0 + 1e-6) v.push_back(QdwhStep{3.0, 1.0, 3.0, false});
-            break;
-        }
-        double l2 = l * l;
-        double dd = cbrt(4.0 * (1.0 - l2) / (l2 * l2));
-        double a = sqrt(1.0 + dd) + 0.5 * sqrt(8.0 - 4.0 * dd + 8.0 * (2.0 - l2) / (l2 * sqrt(1.0 + dd)));
-        double b = (a - 1.0) * (a - 1.0) / 4.0, c = a + b - 1.0;
-        v.push_back(QdwhStep{a, b, c, c > cmax});
-        l = l * (a + b * l2) / (1.0 + c * l2);
-        if (l > 1.0) l = 1.0;
-    }
-    return v;
-}
-
 template <typename T>
 struct PolarWork {
     T *X, *B, *Q, *Z, *L, *Linv, *Y, *Y2, *Tmp, *R0, *Q0;

@@ -1,6 +1,7 @@
 #pragma once
 #include "common.cuh"
 #include "nccl_dl.h"
+#include "qdwh_schedule.h"
 namespace mak {
 int polar_init(makb200_handle* h);
 template <typename T> size_t polar_worksize_t(makb200_handle* h, int m, int n);

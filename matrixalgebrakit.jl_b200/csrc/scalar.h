@@ -46,6 +46,9 @@ __host__ __device__ __forceinline__ double imag_(double) { return 0.0; }
 __host__ __device__ __forceinline__ double imag_(cplx a) { return a.im; }
 __host__ __device__ __forceinline__ double abs2_(double a) { return a * a; }
 __host__ __device__ __forceinline__ double abs2_(cplx a) { return a.re * a.re + a.im * a.im; }
+// |a| without forming the square (no underflow / overflow for |a| outside [1e-154, 1e154])
+__host__ __device__ __forceinline__ double abs_(double a) { return fabs(a); }
+__host__ __device__ __forceinline__ double abs_(cplx a) { return hypot(a.re, a.im); }
 __host__ __device__ __forceinline__ double add_(double a, double b) { return a + b; }
 __host__ __device__ __forceinline__ cplx add_(cplx a, cplx b) { return cplx{a.re + b.re, a.im + b.im}; }
 __host__ __device__ __forceinline__ double sub_(double a, double b) { return a - b; }

@@ -187,3 +187,41 @@ def test_svd_and_eigh_batched_graph_replay(dtype, monkeypatch):
         tol = O.tol_for(a.shape[0])
         assert np.max(np.abs(w - O.eigh_vals(a))) <= tol * np.abs(w).max()
         assert np.linalg.norm(a @ Vn - Vn * w) <= tol * np.linalg.norm(a) and O.orth_err(Vn) <= tol
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("lockstep", ["1", "0"])
+def test_svd_batched_lockstep_qdwh(dtype, lockstep, monkeypatch, capfd):
+    """Mid-size blocks (beyond the one-CTA Jacobi kernel) in a chunk of >= 8: phase 1 of the phased batched SVD is the
+    lock-step QDWH (csrc/polar_lockstep_plan.h: one grouped GEMM / batched kernel per step for ALL blocks); with
+    MAKB200_SVD_LOCKSTEP=0 the same blocks take the per-block chain.  Ragged square and tall blocks, odd sizes (unaligned
+    Float64 leading dimensions), and the hard cases: rank one, zero, graded kappa = 1e10, tiny and huge scale."""
+    import makb200
+    monkeypatch.setenv("MAKB200_SVD_LOCKSTEP", lockstep)
+    monkeypatch.setenv("MAKB200_LOCKSTEP_VERBOSE", "1")
+    rng = np.random.default_rng(21)
+    dims = [int(v) for v in rng.integers(90, 330, size=14)] + [129, 257, 300]
+    sizes = [(d, d) for d in dims] + [(260, 200), (331, 97), (150, 140)]
+    As0 = [O.randn_matrix(m, n, dtype, seed=1100 + i) for i, (m, n) in enumerate(sizes)]
+    n0 = 120
+    Uq, _ = O.qr_compact(O.randn_matrix(n0, n0, dtype, 5))
+    Vq, _ = O.qr_compact(O.randn_matrix(n0, n0, dtype, 6))
+    As0.append(np.asfortranarray((Uq * 10.0 ** (-10 * np.arange(n0) / n0)) @ Vq))              # graded
+    As0.append(np.asfortranarray(As0[0][:, :1] @ As0[0][:1, :]))                                # rank one
+    As0.append(np.asfortranarray(np.zeros((100, 100), dtype=As0[0].dtype)))                     # zero
+    As0.append(np.asfortranarray(1e-100 * O.randn_matrix(111, 111, dtype, 7)))                  # tiny
+    As0.append(np.asfortranarray(1e100 * O.randn_matrix(96, 96, dtype, 8)))                     # huge
+    outs = makb200.svd_compact_batched_([makb200.to_device(a) for a in As0])
+    torch.cuda.synchronize()
+    err = capfd.readouterr().err
+    assert ("in lock-step" in err) == (lockstep == "1"), err
+    for a, (U, S, Vh) in zip(As0, outs):
+        Un, Sn, Vhn = makb200.to_numpy(U), S.cpu().numpy(), makb200.to_numpy(Vh)
+        tol = O.tol_for(*a.shape)
+        so = O.svd_vals(a)
+        nrm = np.linalg.norm(a)
+        assert np.all(np.isfinite(Un)) and np.all(np.isfinite(Vhn))
+        assert np.all(Sn >= 0) and np.all(np.diff(Sn) <= 0)
+        assert np.max(np.abs(Sn - so)) <= tol * max(so[0], 1e-300)
+        assert np.linalg.norm(a - (Un * Sn) @ Vhn) <= tol * nrm
+        assert O.orth_err(Un) <= tol and O.orth_err(Vhn, "right") <= tol
