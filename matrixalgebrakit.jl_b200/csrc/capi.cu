@@ -1068,6 +1068,7 @@ int makb200_tsqr(makb200_handle_t* h, void* comm, int dtype, int m, int n, void*
 }  // extern "C"
 
 #include "polar_lockstep.cuh"
+#include "eigh_lockstep.cuh"
 // ---- lock-step QDWH of a chunk of mid-size blocks (phase 1 of the phased batched SVD) -------------------------
 static bool lockstep_enabled() {
     const char* e = getenv("MAKB200_SVD_LOCKSTEP");   // read per call: tests run both paths
@@ -1092,7 +1093,9 @@ static size_t svd_lockstep_bytes(makb200_handle_t* h, size_t chunk, int mmax, in
     if (blocks_bytes) *blocks_bytes = bb;
     if (tables_bytes) *tables_bytes = tb;
     if (qr_bytes) *qr_bytes = qb;
-    return tb + bb + qb + 1024;
+    // the same region then serves the lock-step eigensolve and SVD tail of the chunk
+    const size_t phase3 = mak::eigh_lockstep_bytes<T>((int)chunk, nmax) + mak::svd_tail_lockstep_bytes<T>((int)chunk) + 1024;
+    return std::max(tb + bb + qb, phase3) + 1024;
 }
 
 // ---- batched svd --------------------------------------------------------------------------
@@ -1273,13 +1276,51 @@ static int svd_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int
                 }
                 rc = mak::bhetrd_batched_t<T>(h, (int)nc, ddev, nmax);
                 if (rc) return rc;
-                rc = run_pooled(h, ids, wbig, pool_region, [&](makb200_handle_t* hh, char* w, size_t lw, int i) {
-                    const int q = slot_of[i];
-                    const Blk& b = blk[q];
-                    return mak::svd_phase2_t<T>(hh, m[i], n[i], b.W, b.P, b.V, b.wv, b.flag, &pre[q], (double*)S[i], (T*)U[i], ldu[i],
-                                                (T*)Vh[i], ldvh[i], fixgauge, w, lw);
-                });
-                if (rc) return rc;
+                bool tail_done = false;
+                if (lockstep) {
+                    // phases 2-3 in lock-step too: batched D&C, batched back-transformation, then reorder / U = W V /
+                    // defect check / gauge for the whole chunk (csrc/eigh_lockstep.cuh); the region of phase 1 is reused
+                    std::vector<int> nn(nc);
+                    for (size_t q = 0; q < nc; ++q) nn[q] = n[ids[q]];
+                    const size_t e_bytes = mak::eigh_lockstep_layout<T>((int)nc, nn.data()).total;
+                    const size_t t_bytes = mak::svd_tail_lockstep_bytes<T>((int)nc);
+                    if (e_bytes + t_bytes + 512 <= ls_total) {
+                        std::vector<mak::EighLsBlk<T>> eb(nc);
+                        std::vector<mak::SvdTailBlk<T>> tb(nc);
+                        for (size_t q = 0; q < nc; ++q) {
+                            const int i = ids[q];
+                            const Blk& b = blk[q];
+                            eb[q] = mak::EighLsBlk<T>{n[i], b.P, n[i], b.d, b.e, b.tau, b.wv, b.V, n[i]};
+                            tb[q] = mak::SvdTailBlk<T>{m[i], n[i], b.W, b.wv, b.V, n[i], (double*)S[i], (T*)U[i], ldu[i], (T*)Vh[i], ldvh[i], nullptr};
+                        }
+                        char* lsb = (char*)mak::align_up((size_t)(uintptr_t)ls_base, 256);
+                        rc = mak::eigh_lockstep_run<T>(h, (int)nc, eb.data(), 0, lsb, e_bytes);
+                        if (rc) return rc;
+                        rc = mak::svd_tail_lockstep_run<T>(h, (int)nc, tb.data(), fixgauge, lsb + mak::align_up(e_bytes, 256), t_bytes,
+                            [&](int q) {
+                                // rank-deficient block: U <- Q of its positive-diagonal Householder QR (polar.cu: svd_tail)
+                                const int i = ids[q];
+                                const Blk& b = blk[q];
+                                int r2 = mak::qr_fused_t<T>(h, MAKB200_QR_COMPACT, m[i], n[i], (T*)U[i], ldu[i], b.W, m[i], (T*)nullptr, 0,
+                                                            wbig, pool_region);
+                                if (r2) return r2;
+                                MAK_CUDA(h, cudaMemcpy2DAsync(U[i], (size_t)ldu[i] * sizeof(T), b.W, (size_t)m[i] * sizeof(T),
+                                                              (size_t)m[i] * sizeof(T), n[i], cudaMemcpyDeviceToDevice, h->stream));
+                                return 0;
+                            });
+                        if (rc) return rc;
+                        tail_done = true;
+                    }
+                }
+                if (!tail_done) {
+                    rc = run_pooled(h, ids, wbig, pool_region, [&](makb200_handle_t* hh, char* w, size_t lw, int i) {
+                        const int q = slot_of[i];
+                        const Blk& b = blk[q];
+                        return mak::svd_phase2_t<T>(hh, m[i], n[i], b.W, b.P, b.V, b.wv, b.flag, &pre[q], (double*)S[i], (T*)U[i], ldu[i],
+                                                    (T*)Vh[i], ldvh[i], fixgauge, w, lw);
+                    });
+                    if (rc) return rc;
+                }
             }
             if (rest.empty()) return 0;
             return run_pooled(h, rest, wbig, lbig, per_block);
@@ -1441,6 +1482,7 @@ static bool bhetrd_enabled() {
     const char* e = getenv("MAKB200_BHETRD");   // read per call: the tests toggle it
     return !(e && e[0] == '0');
 }
+constexpr int EIGH_LS_CHUNK = 192;       // blocks per lock-step eigensolve
 template <typename T>
 static int eigh_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int* n, void* const* A, const int* lda,
                           void* const* W, void* const* V, const int* ldv, int* info, void* work, size_t lwork) {
@@ -1504,6 +1546,36 @@ static int eigh_batched_t(makb200_handle_t* h, int fixgauge, int batch, const in
     }
     char* wbig = (char*)work + ar.off;
     size_t lbig = lwork > ar.off ? lwork - ar.off : 0;
+    // lock-step eigensolve (default): every tridiagonalised block goes through ONE batched D&C and ONE batched
+    // back-transformation per chunk instead of ~100 launches per block on the pool (csrc/eigh_lockstep.cuh)
+    if (V && lockstep_enabled() && bhetrd_enabled() && !graphs_enabled()) {
+        std::vector<int> ls;
+        for (int i : big) if (pre[i].d && n[i] >= 3) ls.push_back(i);
+        if (ls.size() >= 8) {
+            std::stable_sort(ls.begin(), ls.end(), [&](int a, int b) { return n[a] > n[b]; });
+            const size_t chunk = std::min<size_t>((size_t)EIGH_LS_CHUNK, ls.size());
+            const size_t need = mak::eigh_lockstep_bytes<T>((int)chunk, n[ls[0]]);
+            if (need + 512 <= lbig) {
+                char* lsb = (char*)mak::align_up((size_t)(uintptr_t)wbig, 256);
+                for (size_t c0 = 0; c0 < ls.size(); c0 += chunk) {
+                    const size_t nc = std::min(chunk, ls.size() - c0);
+                    std::vector<mak::EighLsBlk<T>> eb(nc);
+                    for (size_t q = 0; q < nc; ++q) {
+                        const int i = ls[c0 + q];
+                        eb[q] = mak::EighLsBlk<T>{n[i], (T*)A[i], lda[i], pre[i].d, pre[i].e, pre[i].tau, (double*)W[i], (T*)V[i], ldv[i]};
+                    }
+                    int rc = mak::eigh_lockstep_run<T>(h, (int)nc, eb.data(), fixgauge, lsb, need);
+                    if (rc) return rc;
+                }
+                if (getenv("MAKB200_LOCKSTEP_VERBOSE"))
+                    fprintf(stderr, "[makb200] batched eigh: %zu blocks (n <= %d) solved in lock-step\n", ls.size(), n[ls[0]]);
+                std::vector<int> rest;
+                for (int i : big) if (!(pre[i].d && n[i] >= 3)) rest.push_back(i);
+                big.swap(rest);
+                if (big.empty()) return 0;
+            }
+        }
+    }
     auto per_block = [&](makb200_handle_t* hh, char* w, size_t lw, int i) {
         return mak::eigh_t<T>(hh, n[i], (T*)A[i], lda[i], (double*)W[i], V ? (T*)V[i] : (T*)nullptr, V ? ldv[i] : n[i],
                               fixgauge, w, lw, nullptr, 0,
@@ -1560,7 +1632,7 @@ size_t makb200_eigh_batched_worksize(makb200_handle_t* h, int dtype, int batch, 
     if (!h || !dtype_ok(dtype) || batch < 0 || (batch > 0 && !n)) return 0;
     size_t esz = dtype == MAKB200_F64 ? sizeof(double) : sizeof(cplx);
     size_t bytes = mak::align_up(sizeof(mak::EighBlockDesc<cplx>) * (size_t)(batch > 0 ? batch : 1), 256), big = 0, nbig = 0;
-    size_t nmax_big = 0;
+    size_t nmax_big = 0, nmax_ls = 0;
     bool any = false;
     for (int i = 0; i < batch; ++i) {
         if (n[i] <= 0) continue;
@@ -1570,6 +1642,7 @@ size_t makb200_eigh_batched_worksize(makb200_handle_t* h, int dtype, int batch, 
             any = true;
             ++nbig;
             if ((size_t)n[i] > nmax_big) nmax_big = (size_t)n[i];
+            if (n[i] <= mak::BHETRD_MAX_N && (size_t)n[i] > nmax_ls) nmax_ls = (size_t)n[i];
             // d, e, tau of the one-launch tridiagonalisation (MAKB200_BHETRD) + its descriptor
             bytes += 2 * mak::align_up(sizeof(double) * (size_t)n[i], 256) + mak::align_up(sizeof(cplx) * (size_t)n[i], 256) +
                      sizeof(mak::BhetrdDesc<cplx>);
@@ -1577,7 +1650,15 @@ size_t makb200_eigh_batched_worksize(makb200_handle_t* h, int dtype, int batch, 
     }
     // graph-replayed path: staging copies of A, V, W per slot
     const size_t staging = 2 * mak::align_up(nmax_big * nmax_big * esz, 256) + mak::align_up(nmax_big * 8, 256) + 1024;
-    return bytes + (any ? pooled_worksize(big, nbig, staging) : 0) + 512;
+    size_t pooled = any ? pooled_worksize(big, nbig, staging) : 0;
+    // lock-step eigensolve of the tridiagonalised blocks (shares the region of the pooled slices)
+    if (nbig >= 8 && nmax_ls > 0) {
+        const size_t chunk = nbig < (size_t)EIGH_LS_CHUNK ? nbig : (size_t)EIGH_LS_CHUNK;
+        const size_t ls = (dtype == MAKB200_F64 ? mak::eigh_lockstep_bytes<double>((int)chunk, (int)nmax_ls)
+                                                : mak::eigh_lockstep_bytes<cplx>((int)chunk, (int)nmax_ls)) + 1024;
+        if (ls > pooled) pooled = ls;
+    }
+    return bytes + pooled + 512;
 }
 
 int makb200_eigh_batched(makb200_handle_t* h, int dtype, int fixgauge, int batch, const int* n, void* const* A,

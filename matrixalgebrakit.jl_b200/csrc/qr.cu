@@ -10,6 +10,8 @@
 //    through the DMMA GEMM in gemm.cu.
 #include <cooperative_groups.h>
 #include <type_traits>
+#include <vector>
+#include <algorithm>
 #include "qr.cuh"
 #include "projections.cuh"
 #include "gemm.cuh"
@@ -581,8 +583,8 @@ int geqrf_t(makb200_handle* h, int m, int n, T* A, int lda, T* tau, void* work, 
 // back substitution  x_j = tau_j,  x_i = -tau_i * sum_{p=i+1..j} G[i,p] x_p   (no division: tau_i = 0
 // gives a zero row, as larft does).  One thread per column, strictly-upper G packed in shared memory.
 template <typename T>
-__global__ void larft_diag_kernel(int jb, const T* __restrict__ tau, T* __restrict__ Tm, int ldt,
-                                  const T* __restrict__ G, int ldg) {
+__device__ __forceinline__ void larft_diag_body(int jb, const T* __restrict__ tau, T* __restrict__ Tm, int ldt,
+                                                const T* __restrict__ G, int ldg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* Gs = reinterpret_cast<T*>(smem_raw);          // packed: (i,p), i<p  ->  p(p-1)/2 + i
     T* ts = Gs + (size_t)jb * (jb - 1) / 2;          // tau
@@ -601,6 +603,11 @@ __global__ void larft_diag_kernel(int jb, const T* __restrict__ tau, T* __restri
             col[i] = neg_(mul_(ts[i], s));
         }
     }
+}
+template <typename T>
+__global__ void larft_diag_kernel(int jb, const T* __restrict__ tau, T* __restrict__ Tm, int ldt,
+                                  const T* __restrict__ G, int ldg) {
+    larft_diag_body<T>(jb, tau, Tm, ldt, G, ldg);
 }
 template <typename T> static size_t larft_smem(int jb) { return sizeof(T) * ((size_t)jb * (jb - 1) / 2 + jb + 2); }
 template <typename T>
@@ -690,6 +697,133 @@ int ormqr_left_t(makb200_handle* h, int m, int k, const T* A, int lda, const T* 
         int rc = apply_block_reflector<T>(h, adjoint, mp, nc, jb, w.Vw, mp, Tb, nb, C + j0, ldc, w);
         if (rc) return rc;
     }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// C_i <- H_0 ... H_{k_i - 1} C_i for MANY blocks in lock-step (back-transformation of the batched eigh / svd of
+// mid-size blocks): per panel of BORM_NB reflectors ONE kernel builds the explicit unit-lower V panel of every active
+// block, one grouped GEMM forms V^H V, one kernel (a CTA per block) the compact-WY T, three grouped GEMMs apply
+// I - V T V^H.  Blocks are sorted by k descending, so the blocks that own panel b are a prefix.  The single-matrix
+// routine above costs ~8 launches per panel PER BLOCK.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void bormqr_prep_kernel(const OrmqrBatchBlk<T>* __restrict__ blks, int j0) {
+    const OrmqrBatchBlk<T> b = blks[blockIdx.y];
+    const int jb = (b.k - j0 < BORM_NB) ? (b.k - j0) : BORM_NB, mp = b.m - j0;
+    if (jb <= 0) return;
+    const T* A = b.A + (size_t)j0 * b.lda + j0;
+    const size_t start = blockIdx.x * (size_t)blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+    const size_t total = (size_t)mp * jb;
+    for (size_t idx = start; idx < total; idx += step) {
+        const int r = (int)(idx % mp), c = (int)(idx / mp);
+        T v = A[(size_t)c * b.lda + r];
+        if (r < c) v = zero<T>();
+        else if (r == c) v = one<T>();
+        b.Vw[idx] = v;
+    }
+    for (size_t idx = start; idx < (size_t)BORM_NB * BORM_NB; idx += step) b.Tb[idx] = zero<T>();
+}
+template <typename T>
+__global__ void __launch_bounds__(128) bormqr_larft_kernel(const OrmqrBatchBlk<T>* __restrict__ blks, int j0) {
+    const OrmqrBatchBlk<T> b = blks[blockIdx.x];
+    const int jb = (b.k - j0 < BORM_NB) ? (b.k - j0) : BORM_NB;
+    if (jb <= 0) return;
+    larft_diag_body<T>(jb, b.tau + j0, b.Tb, BORM_NB, b.G, BORM_NB);
+}
+
+template <typename T>
+size_t ormqr_batched_block_elems(int m, int nc) {
+    auto ev = [](size_t e) { return (e + 1) & ~(size_t)1; };
+    return ev((size_t)(m > 0 ? m : 1) * BORM_NB) + 2 * ev((size_t)BORM_NB * BORM_NB) + 2 * ev((size_t)BORM_NB * (nc > 0 ? nc : 1));
+}
+template <typename T>
+void ormqr_batched_carve(OrmqrBatchBlk<T>& b, T*& p) {
+    auto take = [&](size_t e) { T* r = p; p += (e + 1) & ~(size_t)1; return r; };
+    b.Vw = take((size_t)(b.m > 0 ? b.m : 1) * BORM_NB);
+    b.G = take((size_t)BORM_NB * BORM_NB);
+    b.Tb = take((size_t)BORM_NB * BORM_NB);
+    b.W = take((size_t)BORM_NB * (b.nc > 0 ? b.nc : 1));
+    b.W2 = take((size_t)BORM_NB * (b.nc > 0 ? b.nc : 1));
+}
+template <typename T>
+size_t ormqr_batched_table_bytes(int count, int kmax) {
+    const size_t panels = (size_t)((kmax + BORM_NB - 1) / BORM_NB);
+    return align_up(sizeof(OrmqrBatchBlk<T>) * (size_t)count, 256) + align_up(sizeof(GemmProblem<T>) * 4 * panels * (size_t)count, 256) + 512;
+}
+
+template <typename T>
+int ormqr_left_batched(makb200_handle* h, int count, const OrmqrBatchBlk<T>* blks, char* tables, size_t tables_bytes) {
+    if (count <= 0) return 0;
+    cudaStream_t s = h->stream;
+    int kmax = 0, mmax = 0, ncmax = 0;
+    for (int i = 0; i < count; ++i) {
+        if (i > 0 && blks[i].k > blks[i - 1].k) return -2;   // k descending
+        kmax = std::max(kmax, blks[i].k); mmax = std::max(mmax, blks[i].m); ncmax = std::max(ncmax, blks[i].nc);
+    }
+    if (kmax <= 0) return 0;
+    const int npanel = (kmax + BORM_NB - 1) / BORM_NB;
+    struct Launch { int opa, opb, count, max_m, max_n; size_t off; };
+    std::vector<GemmProblem<T>> probs;
+    std::vector<Launch> launches;   // 4 per panel, in order
+    std::vector<int> actives;
+    auto prob = [](int m, int n, int k, const T* A, int lda, const T* B, int ldb, T* C, int ldc, double al, double be, int ca) {
+        GemmProblem<T> p;
+        p.m = m; p.n = n; p.k = k; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
+        p.alpha = mk<T>(al); p.beta = mk<T>(be); p.conja = ca; p.conjb = 0; p.lower = 0;
+        return p;
+    };
+    for (int bb = npanel - 1; bb >= 0; --bb) {
+        const int j0 = bb * BORM_NB;
+        int na = 0;
+        while (na < count && blks[na].k > j0) ++na;
+        actives.push_back(na);
+        Launch l[4] = {{MAKB200_OP_C, MAKB200_OP_N, na, 0, 0, 0}, {MAKB200_OP_C, MAKB200_OP_N, na, 0, 0, 0},
+                       {MAKB200_OP_N, MAKB200_OP_N, na, 0, 0, 0}, {MAKB200_OP_N, MAKB200_OP_N, na, 0, 0, 0}};
+        for (int g = 0; g < 4; ++g) {
+            l[g].off = probs.size();
+            for (int i = 0; i < na; ++i) {
+                const OrmqrBatchBlk<T>& b = blks[i];
+                const int jb = std::min(BORM_NB, b.k - j0), mp = b.m - j0;
+                GemmProblem<T> p;
+                if (g == 0) p = prob(jb, jb, mp, b.Vw, mp, b.Vw, mp, b.G, BORM_NB, 1.0, 0.0, 1);                  // G = V^H V
+                else if (g == 1) p = prob(jb, b.nc, mp, b.Vw, mp, b.C + j0, b.ldc, b.W, jb, 1.0, 0.0, 1);           // W = V^H C
+                else if (g == 2) p = prob(jb, b.nc, jb, b.Tb, BORM_NB, b.W, jb, b.W2, jb, 1.0, 0.0, 0);             // W2 = T W
+                else p = prob(mp, b.nc, jb, b.Vw, mp, b.W2, jb, b.C + j0, b.ldc, -1.0, 1.0, 0);                     // C -= V W2
+                l[g].max_m = std::max(l[g].max_m, p.m); l[g].max_n = std::max(l[g].max_n, p.n);
+                probs.push_back(p);
+            }
+            launches.push_back(l[g]);
+        }
+    }
+    OrmqrBatchBlk<T>* bdev = (OrmqrBatchBlk<T>*)tables;
+    GemmProblem<T>* pdev = (GemmProblem<T>*)(tables + align_up(sizeof(OrmqrBatchBlk<T>) * (size_t)count, 256));
+    if (align_up(sizeof(OrmqrBatchBlk<T>) * (size_t)count, 256) + sizeof(GemmProblem<T>) * probs.size() > tables_bytes)
+        return MAKB200_ERR_WORKSPACE;
+    {
+        Stager st(h, sizeof(OrmqrBatchBlk<T>) * (size_t)count + sizeof(GemmProblem<T>) * probs.size() + 1024);
+        MAK_CUDA(h, st.put(bdev, blks, sizeof(OrmqrBatchBlk<T>) * (size_t)count, s));
+        MAK_CUDA(h, st.put(pdev, probs.data(), sizeof(GemmProblem<T>) * probs.size(), s));
+    }
+    static_assert(sizeof(cplx) * ((size_t)BORM_NB * (BORM_NB - 1) / 2 + BORM_NB + 2) <= 48 * 1024, "larft panel must fit default smem");
+    size_t li = 0;
+    for (int bb = npanel - 1, pi = 0; bb >= 0; --bb, ++pi) {
+        const int j0 = bb * BORM_NB, na = actives[pi];
+        if (na <= 0) { li += 4; continue; }
+        const int gx = std::max(1, std::min((mmax * BORM_NB + 255) / 256, 32));
+        bormqr_prep_kernel<T><<<dim3(gx, na), 256, 0, s>>>(bdev, j0);
+        count_launch();
+        for (int g = 0; g < 4; ++g, ++li) {
+            if (g == 1) {
+                bormqr_larft_kernel<T><<<na, 128, larft_smem<T>(BORM_NB), s>>>(bdev, j0);
+                count_launch();
+            }
+            const Launch& l = launches[li];
+            cudaError_t e = gemm_grouped<T>(s, l.opa, l.opb, l.count, l.max_m, l.max_n, pdev + l.off);
+            if (e != cudaSuccess) return cuda_fail(h, e, "ormqr_left_batched: grouped gemm");
+        }
+    }
+    MAK_LAUNCH_CHECK(h, "ormqr_left_batched");
     return 0;
 }
 
@@ -836,7 +970,11 @@ int sy2sb_t(makb200_handle* h, int n, int b, T* A, int lda, T* tau1, void* work,
     template int geqrf_t<T>(makb200_handle*, int, int, T*, int, T*, void*, size_t);                        \
     template int orgqr_t<T>(makb200_handle*, int, int, int, const T*, int, const T*, T*, int, void*, size_t); \
     template size_t ormqr_worksize_t<T>(makb200_handle*, int, int, int);                                   \
-    template int ormqr_left_t<T>(makb200_handle*, int, int, const T*, int, const T*, T*, int, int, void*, size_t, bool);
+    template int ormqr_left_t<T>(makb200_handle*, int, int, const T*, int, const T*, T*, int, int, void*, size_t, bool); \
+    template size_t ormqr_batched_block_elems<T>(int, int);                                                 \
+    template void ormqr_batched_carve<T>(OrmqrBatchBlk<T>&, T*&);                                           \
+    template size_t ormqr_batched_table_bytes<T>(int, int);                                                 \
+    template int ormqr_left_batched<T>(makb200_handle*, int, const OrmqrBatchBlk<T>*, char*, size_t);
 INST(double)
 INST(cplx)
 

@@ -439,4 +439,241 @@ int stedc(makb200_handle* h, int n, const double* d, const double* e, double* w,
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// Many tridiagonals in ONE pass of the same kernels (lock-step batched eigh / svd of mid-size blocks).
+//
+// The blocks are laid end to end as one block-diagonal tridiagonal of order Ntot = sum n_i (the couplings between
+// blocks are zero), each with its own binary tree, so a level's launches cover the merges of EVERY block that still has
+// that level.  The kernels above address the eigenvector matrix as Z[(lo + c) * ld + lo + r] with global positions and
+// only ever touch diagonal sub-blocks, so the "Ntot x Ntot" matrices are stored as strips with ld = nmax: block i
+// (global offset o_i) owns the addresses o_i (ld + 1) + [0, n_i ld), disjoint from every other block since ld >= n_i.
+// A block with L_i levels ends in ping-pong buffer L_i mod 2 (eigenvalues and vectors alike); the finishing kernel
+// reads each block from its own buffer, rescales the eigenvalues and writes V_i (Float64 or ComplexF64).
+// ---------------------------------------------------------------------------------------
+struct StedcBlkDev {
+    int n, off, par, ldv;
+    const double* d;
+    const double* e;
+    double* w;
+    void* V;
+};
+
+__global__ void dc_scale_batched_kernel(const StedcBlkDev* __restrict__ blks, double* D, double* E, double* scale) {
+    __shared__ double red[32];
+    const StedcBlkDev b = blks[blockIdx.x];
+    const int n = b.n;
+    double m = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, fabs(b.d[i]));
+    for (int i = threadIdx.x; i < n - 1; i += blockDim.x) m = fmax(m, fabs(b.e[i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t = fmax(t, red[i]);
+    const double sc = t > 0.0 ? t : 1.0;
+    if (threadIdx.x == 0) scale[blockIdx.x] = sc;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        D[b.off + i] = b.d[i] / sc;
+        E[b.off + i] = (i < n - 1) ? b.e[i] / sc : 0.0;
+    }
+}
+
+template <typename T>
+__global__ void dc_finish_batched_kernel(const StedcBlkDev* __restrict__ blks, const double* __restrict__ D0,
+                                         const double* __restrict__ D1, const double* __restrict__ Z0,
+                                         const double* __restrict__ Z1, int ld, const double* __restrict__ scale) {
+    const StedcBlkDev b = blks[blockIdx.y];
+    const int n = b.n;
+    const double* D = b.par ? D1 : D0;
+    const double* Z = (b.par ? Z1 : Z0) + (size_t)b.off * ((size_t)ld + 1);
+    T* V = reinterpret_cast<T*>(b.V);
+    const size_t start = blockIdx.x * (size_t)blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+    const double sc = scale[blockIdx.y];
+    for (size_t i = start; i < (size_t)n; i += step) b.w[i] = D[b.off + i] * sc;
+    const size_t total = (size_t)n * n;
+    for (size_t idx = start; idx < total; idx += step) {
+        const int r = (int)(idx % n), c = (int)(idx / n);
+        V[(size_t)c * b.ldv + r] = mk<T>(Z[(size_t)c * ld + r]);
+    }
+}
+
+struct DcBatchLayout {
+    Ctx ctx;
+    Merge* merges;
+    GemmProblem<double>* gemms;
+    double *E, *rho_cut, *sgn_cut, *scale;
+    int *info, *bnd, *cuts;
+    StedcBlkDev* blks;
+    double *Z0, *Z1, *Pack, *S;
+};
+template <typename AR>
+static void stedc_batched_carve(AR& ar, int nblk, size_t ntot, int nmax, size_t nleaves, DcBatchLayout* b) {
+    const size_t nn = ntot > 0 ? ntot : 1;
+    b->ctx.n = (int)ntot;
+    b->ctx.D = ar.template get<double>(nn);
+    b->ctx.Dn = ar.template get<double>(nn);
+    b->ctx.z = ar.template get<double>(nn);
+    b->ctx.perm = ar.template get<int>(nn);
+    b->ctx.dl = ar.template get<double>(nn);
+    b->ctx.zl = ar.template get<double>(nn);
+    b->ctx.src = ar.template get<int>(nn);
+    b->ctx.ctype = ar.template get<int>(nn);
+    b->ctx.rowpos = ar.template get<int>(nn);
+    b->ctx.rot_p = ar.template get<int>(nn);
+    b->ctx.rot_q = ar.template get<int>(nn);
+    b->ctx.rot_c = ar.template get<double>(nn);
+    b->ctx.rot_s = ar.template get<double>(nn);
+    b->ctx.rot_tp = ar.template get<int>(nn);
+    b->ctx.rot_tq = ar.template get<int>(nn);
+    b->ctx.tau = ar.template get<double>(nn);
+    b->ctx.orig = ar.template get<int>(nn);
+    b->ctx.zhat = ar.template get<double>(nn);
+    b->ctx.pos = ar.template get<int>(nn);
+    b->merges = ar.template get<Merge>(nleaves + 1);          // all levels: sum over levels of merges < leaves
+    b->gemms = ar.template get<GemmProblem<double>>(nleaves + 2);
+    b->E = ar.template get<double>(nn);
+    b->rho_cut = ar.template get<double>(nn + 1);
+    b->sgn_cut = ar.template get<double>(nn + 1);
+    b->scale = ar.template get<double>((size_t)nblk + 1);
+    b->info = ar.template get<int>(4);
+    b->bnd = ar.template get<int>(nleaves + 1);
+    b->cuts = ar.template get<int>(nleaves + 1);
+    b->blks = ar.template get<StedcBlkDev>((size_t)nblk + 1);
+    const size_t strip = nn * ((size_t)nmax + 1);
+    b->Z0 = ar.template get<double>(strip);
+    b->Z1 = ar.template get<double>(strip);
+    b->Pack = ar.template get<double>(strip);
+    b->S = ar.template get<double>(strip);
+}
+
+size_t stedc_batched_worksize(int nblk, const int* n) {
+    size_t ntot = 0, nleaves = 0;
+    int nmax = 1;
+    for (int i = 0; i < nblk; ++i) {
+        ntot += (size_t)n[i];
+        nleaves += (size_t)1 << dc_levels(n[i]);
+        nmax = std::max(nmax, n[i]);
+    }
+    ArenaSize ar;
+    DcBatchLayout b;
+    stedc_batched_carve(ar, nblk, ntot, nmax, nleaves, &b);
+    return ar.off + 256;
+}
+
+template <typename T>
+int stedc_batched(makb200_handle* h, int nblk, const StedcBlk* blks, void* work, size_t lwork, int* info_dev) {
+    if (nblk <= 0) return 0;
+    cudaStream_t st = h->stream;
+    size_t ntot = 0, nleaves = 0;
+    int nmax = 1, Lmax = 0;
+    std::vector<int> lev(nblk), off(nblk);
+    for (int i = 0; i < nblk; ++i) {
+        if (blks[i].n <= 0) return -2;
+        off[i] = (int)ntot;
+        ntot += (size_t)blks[i].n;
+        lev[i] = dc_levels(blks[i].n);
+        nleaves += (size_t)1 << lev[i];
+        nmax = std::max(nmax, blks[i].n);
+        Lmax = std::max(Lmax, lev[i]);
+    }
+    if (ntot * ((size_t)nmax + 1) > (size_t)0x7fffffff * 64) return -3;
+    Arena ar(work, lwork);
+    DcBatchLayout b;
+    stedc_batched_carve(ar, nblk, ntot, nmax, nleaves, &b);
+    if (!ar.ok) return MAKB200_ERR_WORKSPACE;
+    // host tables: leaf boundaries (global), cuts, the merges of every level, block descriptors
+    std::vector<int> bnd, cuts;
+    std::vector<StedcBlkDev> bd(nblk);
+    std::vector<std::vector<int>> lb(nblk);     // per-block leaf boundaries (global positions)
+    for (int i = 0; i < nblk; ++i) {
+        const int n = blks[i].n, nl = 1 << lev[i];
+        lb[i].resize(nl + 1);
+        for (int k = 0; k <= nl; ++k) lb[i][k] = off[i] + (int)((long long)k * n / nl);
+        for (int k = 0; k < nl; ++k) bnd.push_back(lb[i][k]);
+        for (int k = 1; k < nl; ++k) cuts.push_back(lb[i][k]);
+        bd[i] = StedcBlkDev{n, off[i], lev[i] & 1, blks[i].ldv, blks[i].d, blks[i].e, blks[i].w, blks[i].V};
+    }
+    bnd.push_back((int)ntot);
+    struct LevelInfo { size_t first; int nm, maxN, maxH; };
+    std::vector<LevelInfo> levels;
+    std::vector<Merge> merges;
+    for (int l = 1; l <= Lmax; ++l) {
+        LevelInfo li{merges.size(), 0, 0, 0};
+        const int step = 1 << l;
+        for (int i = 0; i < nblk; ++i) {
+            if (lev[i] < l) continue;
+            const int nm = (1 << lev[i]) / step;
+            for (int k = 0; k < nm; ++k) {
+                Merge m{};
+                m.lo = lb[i][k * step]; m.mid = lb[i][k * step + step / 2]; m.hi = lb[i][(k + 1) * step];
+                merges.push_back(m);
+                li.maxN = std::max(li.maxN, m.hi - m.lo);
+                li.maxH = std::max(li.maxH, std::max(m.mid - m.lo, m.hi - m.mid));
+                ++li.nm;
+            }
+        }
+        levels.push_back(li);
+    }
+    if (merges.size() > nleaves + 1) return -4;
+    {
+        Stager sg(h, (bnd.size() + cuts.size()) * sizeof(int) + merges.size() * sizeof(Merge) + bd.size() * sizeof(StedcBlkDev) + 4096);
+        MAK_CUDA(h, sg.put(b.bnd, bnd.data(), bnd.size() * sizeof(int), st));
+        MAK_CUDA(h, sg.put(b.cuts, cuts.data(), cuts.size() * sizeof(int), st));
+        MAK_CUDA(h, sg.put(b.merges, merges.data(), merges.size() * sizeof(Merge), st));
+        MAK_CUDA(h, sg.put(b.blks, bd.data(), bd.size() * sizeof(StedcBlkDev), st));
+    }
+    MAK_CUDA(h, cudaMemsetAsync(b.info, 0, sizeof(int) * 4, st));
+    dc_scale_batched_kernel<<<nblk, 256, 0, st>>>(b.blks, b.ctx.D, b.E, b.scale);
+    if (!cuts.empty())
+        dc_tear_kernel<<<(int)(cuts.size() + 127) / 128, 128, 0, st>>>((int)cuts.size(), b.cuts, b.ctx.D, b.E, b.rho_cut, b.sgn_cut);
+    const int ld = nmax;
+    double *Zin = b.Z0, *Zout = b.Z1;
+    double *D0 = b.ctx.D, *D1 = b.ctx.Dn;
+    const int nl_all = (int)nleaves;
+    dc_leaf_kernel<<<(nl_all + LEAF_WARPS - 1) / LEAF_WARPS, LEAF_WARPS * 32, 0, st>>>(nl_all, b.bnd, b.ctx.D, b.E, Zin, ld, b.info);
+    count_launch(3);
+    MAK_LAUNCH_CHECK(h, "dc_leaf_kernel (batched)");
+    for (const LevelInfo& li : levels) {
+        const int nm = li.nm, maxN = li.maxN, maxH = li.maxH;
+        if (nm == 0) continue;
+        Merge* mg = b.merges + li.first;
+        for (int m0 = 0; m0 < nm; m0 += 32768) {      // grid.y / grid.z limit
+            const int nmc = std::min(32768, nm - m0);
+            Merge* mgc = mg + m0;
+            dc_merge_init_kernel<<<(nmc + 127) / 128, 128, 0, st>>>(nmc, mgc, b.rho_cut, b.sgn_cut);
+            const int bx = std::max(1, std::min((maxN + 255) / 256, 64));
+            dim3 g2(bx, nmc);
+            dc_z_rank_kernel<<<g2, 256, 0, st>>>(b.ctx, mgc, Zin, ld, 0);
+            dc_z_rank_kernel<<<g2, 256, 0, st>>>(b.ctx, mgc, Zin, ld, 1);
+            dc_deflate_kernel<<<nmc, 32, 0, st>>>(b.ctx, mgc, b.gemms, b.Pack, ld, b.S, ld, Zin, ld);
+            dc_rotate_kernel<<<g2, 256, 0, st>>>(b.ctx, mgc, Zin, ld);
+            dim3 gs(std::max(1, std::min((maxN + 127) / 128, 128)), nmc);
+            dc_secular_kernel<<<gs, 128, 0, st>>>(b.ctx, mgc);
+            dc_zhat_pos_kernel<<<gs, 128, 0, st>>>(b.ctx, mgc);
+            dim3 gv(std::min(maxN, 4096), nmc);
+            dc_svec_kernel<<<gv, 256, 0, st>>>(b.ctx, mgc, b.S, ld);
+            dim3 gp(std::max(1, std::min((maxN + 255) / 256, 8)), std::min(maxN, 8192), nmc);
+            dc_pack_kernel<<<gp, 256, 0, st>>>(b.ctx, mgc, Zin, ld, b.Pack, ld, Zout, ld);
+            MAK_LAUNCH_CHECK(h, "dc_pack_kernel (batched)");
+            cudaError_t ge = gemm_grouped<double>(st, MAKB200_OP_N, MAKB200_OP_N, 2 * nmc, maxH, maxN, b.gemms);
+            if (ge != cudaSuccess) return cuda_fail(h, ge, "dc gemm_grouped (batched)");
+            dc_scatter_kernel<<<gp, 256, 0, st>>>(b.ctx, mgc, Zin, ld, Zout, ld);
+            MAK_LAUNCH_CHECK(h, "dc_scatter_kernel (batched)");
+            count_launch(9);
+        }
+        std::swap(Zin, Zout);
+        std::swap(b.ctx.D, b.ctx.Dn);
+    }
+    {
+        const int gx = std::max(1, std::min((nmax * nmax + 255) / 256, 64));
+        dc_finish_batched_kernel<T><<<dim3(gx, nblk), 256, 0, st>>>(b.blks, D0, D1, b.Z0, b.Z1, ld, b.scale);
+        count_launch();
+        MAK_LAUNCH_CHECK(h, "dc_finish_batched_kernel");
+    }
+    if (info_dev) MAK_CUDA(h, cudaMemcpyAsync(info_dev, b.info, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+template int stedc_batched<double>(makb200_handle*, int, const StedcBlk*, void*, size_t, int*);
+template int stedc_batched<cplx>(makb200_handle*, int, const StedcBlk*, void*, size_t, int*);
+
 }  // namespace mak

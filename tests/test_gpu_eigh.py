@@ -194,6 +194,35 @@ def test_eigh_batched_pooled_threads(dtype):
 
 
 @pytest.mark.parametrize("dtype", ["f64", "c128"])
+@pytest.mark.parametrize("lockstep", ["1", "0"])
+def test_eigh_batched_lockstep(dtype, lockstep, monkeypatch, capfd):
+    """>= 8 blocks beyond the one-CTA limit: after the one-launch tridiagonalisation the eigensolve runs in lock-step
+    (ONE batched D&C over the block-diagonal union of the tridiagonals + ONE batched back-transformation,
+    csrc/eigh_lockstep.cuh); MAKB200_SVD_LOCKSTEP=0 keeps the per-block chain.  Ragged sizes (different tree depths
+    in one pass), odd sizes, and spectra that deflate heavily: identity, zero, +-1 pairs, four clusters, graded."""
+    import makb200
+    monkeypatch.setenv("MAKB200_SVD_LOCKSTEP", lockstep)
+    monkeypatch.setenv("MAKB200_LOCKSTEP_VERBOSE", "1")
+    rng = np.random.default_rng(14)
+    ns = [int(v) for v in rng.integers(128, 340, size=14)] + [129, 257, 260, 300, 333, 511, 512]
+    As0 = [O.rand_hermitian(n, dtype, seed=1300 + i) for i, n in enumerate(ns)]
+    nq = 160
+    Q, _ = O.qr_compact(O.randn_matrix(nq, nq, dtype, seed=3))
+    specials = [np.zeros((150, 150)), np.eye(140), (Q * np.repeat([-1.0, 1.0], nq // 2)) @ Q.conj().T,
+                (Q * np.repeat(np.arange(4.0), nq // 4)) @ Q.conj().T, (Q * 10.0 ** (-12 * np.arange(nq) / nq)) @ Q.conj().T,
+                1e-100 * O.rand_hermitian(131, dtype, seed=5), 1e100 * O.rand_hermitian(137, dtype, seed=6)]
+    for S in specials:
+        S = (S + S.conj().T) / 2
+        As0.append(np.asfortranarray(S.astype(np.complex128) if dtype == "c128" else np.ascontiguousarray(S.real)))
+    DVs = makb200.eigh_full_batched_([makb200.to_device(a) for a in As0], check=False)
+    torch.cuda.synchronize()
+    err = capfd.readouterr().err
+    assert ("solved in lock-step" in err) == (lockstep == "1"), err
+    for i, (a, (D, V)) in enumerate(zip(As0, DVs)):
+        _check(a, D.cpu().numpy(), makb200.to_numpy(V), vec_cmp=(i < len(ns)))
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c128"])
 def test_eigh_persistent_column_kernels_small_n_sweep(dtype, monkeypatch):
     """The persistent TMA column kernels (csrc/trd2.cuh) are the default from n = 1536 up; here the switch is moved to
     n = 2 so that every tile-geometry corner (one tile, partial bands, chunks with no work, odd n -> unaligned lda ->
