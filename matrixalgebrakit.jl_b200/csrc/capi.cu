@@ -316,12 +316,14 @@ static int run_pooled(makb200_handle_t* h, const std::vector<int>& big, char* wo
     }
     h->stream = main;
     h->no_lookahead = false;
-    if (rc) return rc;
+    // join on the error path too: blocks of other streams may still be running, and the caller is about to reuse (or
+    // free) the workspace and the outputs
     for (int s = 0; s < np; ++s) {
-        MAK_CUDA(h, cudaEventRecord(h->pool_ev[s], h->pool[s]));
-        MAK_CUDA(h, cudaStreamWaitEvent(main, h->pool_ev[s], 0));
+        const cudaError_t e1 = cudaEventRecord(h->pool_ev[s], h->pool[s]);
+        const cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(main, h->pool_ev[s], 0) : e1;
+        if (e2 != cudaSuccess && rc == 0) rc = mak::cuda_fail(h, e2, "run_pooled: join");
     }
-    return 0;
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1112,6 +1114,55 @@ static size_t svd_phase_persist_bytes(int m, int n) {
            3 * mak::align_up(nn * 8, 256) + 256;
 }
 
+// ---- chunks of the phased / lock-step batched SVD ---------------------------------------------------------------
+// `ph` (phased blocks: m >= n, 3 <= n <= BHETRD_MAX_N) is sorted by n descending.  A chunk takes blocks while its
+// per-block buffers stay under SVD_LS_BUDGET (at least SVD_PHASE_CHUNK, at most SVD_LS_MAX_CHUNK blocks): 192 blocks of
+// 512 x 512 but ~2000 of 100 x 100, because a chunk costs ~700 launches whatever its size and the small-block buckets
+// were bound by exactly that.  Used by the workspace query and the run, so both see the same chunks.
+constexpr size_t SVD_LS_BUDGET = (size_t)8 << 30;
+constexpr size_t SVD_LS_MAX_CHUNK = 2048;
+struct SvdChunk { size_t c0, nc; int mmax, nmax; bool tall; size_t persist, ls_total, ls_bb, ls_tb, ls_qb; };
+template <typename T>
+static std::vector<SvdChunk> svd_chunk_plan(makb200_handle_t* h, const std::vector<int>& ph, const int* m, const int* n,
+                                            size_t* region) {
+    constexpr int lnb = mak::CholNB<T>::value;
+    std::vector<SvdChunk> plan;
+    size_t reg = 0;
+    for (size_t c0 = 0; c0 < ph.size();) {
+        SvdChunk c{};
+        c.c0 = c0;
+        size_t bytes = 0;
+        while (c0 + c.nc < ph.size() && c.nc < SVD_LS_MAX_CHUNK) {
+            const int i = ph[c0 + c.nc];
+            const size_t bi = mak::ls_block_elems<T>(m[i], n[i], lnb) * sizeof(T) + svd_phase_persist_bytes<T>(m[i], n[i]);
+            if (c.nc >= (size_t)SVD_PHASE_CHUNK && bytes + bi > SVD_LS_BUDGET) break;
+            bytes += bi;
+            c.mmax = std::max(c.mmax, m[i]); c.nmax = std::max(c.nmax, n[i]);
+            c.tall = c.tall || m[i] > n[i];
+            c.persist = std::max(c.persist, svd_phase_persist_bytes<T>(m[i], n[i]));
+            ++c.nc;
+        }
+        c.ls_total = svd_lockstep_bytes<T>(h, c.nc, c.mmax, c.nmax, c.tall, &c.ls_bb, &c.ls_tb, &c.ls_qb);
+        reg = std::max(reg, c.nc * (c.persist + sizeof(mak::BhetrdDesc<T>) + 64) + 512 + c.ls_total);
+        plan.push_back(c);
+        c0 += c.nc;
+    }
+    if (region) *region = reg;
+    return plan;
+}
+// the phased blocks of a batch (indices), n descending
+template <typename T>
+static std::vector<int> svd_phased_blocks(int batch, const int* m, const int* n) {
+    std::vector<int> ph;
+    for (int i = 0; i < batch; ++i) {
+        if (m[i] <= 0 || n[i] <= 0) continue;
+        if (mak::batched_svd_smem_bytes(m[i], n[i], sizeof(T)) <= mak::batched_svd_max_smem_bytes()) continue;
+        if (m[i] >= n[i] && n[i] >= 3 && n[i] <= mak::BHETRD_MAX_N) ph.push_back(i);
+    }
+    std::stable_sort(ph.begin(), ph.end(), [&](int a, int b) { return n[a] > n[b]; });
+    return ph;
+}
+
 template <typename T>
 static int svd_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int* m, const int* n, void* const* A,
                          const int* lda, void* const* S, void* const* U, const int* ldu, void* const* Vh,
@@ -1170,38 +1221,44 @@ static int svd_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int
         // n descending: a chunk holds blocks of similar size (the lock-step launches are sized by the largest)
         std::stable_sort(ph.begin(), ph.end(), [&](int a, int b) { return n[a] > n[b]; });
         size_t scratch = 0, persist = 0;
-        int ls_mmax = 0, ls_nmax = 0;
-        bool ls_tall = false;
         for (int i : ph) {
             scratch = std::max(scratch, mak::svd_phase_scratch_t<T>(h, m[i], n[i]));
             persist = std::max(persist, svd_phase_persist_bytes<T>(m[i], n[i]));
-            ls_mmax = std::max(ls_mmax, m[i]); ls_nmax = std::max(ls_nmax, n[i]);
-            ls_tall = ls_tall || m[i] > n[i];
         }
         const size_t np_pool = (size_t)pool_streams();
         const size_t pool_region = (scratch + 1024) * np_pool;
-        // lock-step phase 1 (default): its region sits at the end of the workspace; without room for it the chunk's
-        // QDWH runs block by block on the pool as before
-        size_t ls_total = 0, ls_bb = 0, ls_tb = 0, ls_qb = 0;
+        // lock-step phases (default): chunks sized by their buffers, the lock-step region at the end of the workspace;
+        // without room for it every chunk is SVD_PHASE_CHUNK blocks and runs block by block on the pool as before
+        std::vector<SvdChunk> plan;
         bool lockstep = lockstep_enabled() && ph.size() >= 8;
         if (lockstep) {
-            const size_t c0 = std::min<size_t>((size_t)SVD_PHASE_CHUNK, ph.size());
-            ls_total = svd_lockstep_bytes<T>(h, c0, ls_mmax, ls_nmax, ls_tall, &ls_bb, &ls_tb, &ls_qb);
-            if (lbig < pool_region + 4096 + ls_total + c0 * (persist + sizeof(mak::BhetrdDesc<T>) + 64)) { lockstep = false; ls_total = 0; }
+            size_t region = 0;
+            plan = svd_chunk_plan<T>(h, ph, m, n, &region);
+            if (lbig < pool_region + 4096 + region) { lockstep = false; plan.clear(); }
         }
-        size_t chunk = 0;
-        if (!ph.empty() && lbig > pool_region + 4096 + ls_total) chunk = std::min<size_t>({(size_t)SVD_PHASE_CHUNK, ph.size(), (lbig - pool_region - 4096 - ls_total) / (persist + sizeof(mak::BhetrdDesc<T>) + 64)});
-        if (ph.size() >= 8 && chunk >= 8) {
+        if (!lockstep && !ph.empty() && lbig > pool_region + 4096) {
+            const size_t chunk = std::min<size_t>({(size_t)SVD_PHASE_CHUNK, ph.size(), (lbig - pool_region - 4096) / (persist + sizeof(mak::BhetrdDesc<T>) + 64)});
+            if (chunk >= 8)
+                for (size_t c0 = 0; c0 < ph.size(); c0 += chunk) {
+                    SvdChunk c{};
+                    c.c0 = c0; c.nc = std::min(chunk, ph.size() - c0); c.persist = persist;
+                    plan.push_back(c);
+                }
+        }
+        if (ph.size() >= 8 && !plan.empty()) {
+            size_t chunk_max = 0;
+            for (const SvdChunk& c : plan) chunk_max = std::max(chunk_max, c.nc);
             char* pbase = wbig + pool_region;
-            char* ls_base = wbig + lbig - ls_total;   // [tables | per-block buffers | batched-QR workspace]
             mak::BhetrdDesc<T>* ddev = (mak::BhetrdDesc<T>*)pbase;
-            char* store = pbase + mak::align_up(sizeof(mak::BhetrdDesc<T>) * chunk, 256);
             struct Blk { T *W, *P, *V, *tau; double *wv, *flag, *d, *e; };
-            std::vector<Blk> blk(chunk);
-            std::vector<mak::TrdPre<T>> pre(chunk);
+            std::vector<Blk> blk(chunk_max);
+            std::vector<mak::TrdPre<T>> pre(chunk_max);
             std::vector<int> slot_of(batch, -1);
-            for (size_t c0 = 0; c0 < ph.size(); c0 += chunk) {
-                const size_t nc = std::min(chunk, ph.size() - c0);
+            for (const SvdChunk& ck : plan) {
+                const size_t c0 = ck.c0, nc = ck.nc, persist = ck.persist;
+                const size_t ls_total = ck.ls_total, ls_bb = ck.ls_bb, ls_tb = ck.ls_tb, ls_qb = ck.ls_qb;
+                char* store = pbase + mak::align_up(sizeof(mak::BhetrdDesc<T>) * nc, 256);
+                char* ls_base = wbig + lbig - ls_total;   // [tables | per-block buffers | batched-QR workspace]
                 std::vector<int> ids(ph.begin() + c0, ph.begin() + c0 + nc);
                 std::vector<mak::BhetrdDesc<T>> bd(nc);
                 int nmax = 0;
@@ -1431,25 +1488,28 @@ size_t makb200_svd_batched_worksize(makb200_handle_t* h, int dtype, int batch, c
     // graph-replayed path: staging copies of A, U, Vh, S per slot + one defect indicator per big block
     const size_t staging = mak::align_up(st_a * esz, 256) + mak::align_up(st_u * esz, 256) + mak::align_up(st_v * esz, 256) +
                            mak::align_up(st_s * 8, 256) + 1024;
-    // phased path: per-block W, P, V, ... of one chunk + its descriptors, and the lock-step QDWH region
+    // phased path: per-block W, P, V, ... of one chunk + its descriptors (fixed chunks: the fallback), or the chunk plan
+    // of the lock-step path with its region (svd_chunk_plan: the run walks the same chunks)
     size_t persist = 0;
-    int ls_mmax = 0, ls_nmax = 0;
-    bool ls_tall = false;
     for (int i = 0; i < batch; ++i) {
         if (m[i] <= 0 || n[i] <= 0 || m[i] < n[i] || n[i] > mak::BHETRD_MAX_N) continue;
         if (mak::batched_svd_smem_bytes(m[i], n[i], esz) <= mak::batched_svd_max_smem_bytes()) continue;
         const size_t pb = dtype == MAKB200_F64 ? svd_phase_persist_bytes<double>(m[i], n[i]) : svd_phase_persist_bytes<cplx>(m[i], n[i]);
         if (pb > persist) persist = pb;
-        if (n[i] >= 3) {
-            ls_mmax = std::max(ls_mmax, m[i]); ls_nmax = std::max(ls_nmax, n[i]);
-            ls_tall = ls_tall || m[i] > n[i];
-        }
     }
     const size_t chunk = nbig < (size_t)SVD_PHASE_CHUNK ? nbig : (size_t)SVD_PHASE_CHUNK;
     size_t phased = chunk * (persist + sizeof(mak::BhetrdDesc<cplx>) + 64) + 8192;
-    if (ls_nmax > 0 && chunk >= 8)
-        phased += (dtype == MAKB200_F64 ? svd_lockstep_bytes<double>(h, chunk, ls_mmax, ls_nmax, ls_tall, nullptr, nullptr, nullptr)
-                                        : svd_lockstep_bytes<cplx>(h, chunk, ls_mmax, ls_nmax, ls_tall, nullptr, nullptr, nullptr)) + 512;
+    {
+        size_t region = 0;
+        if (dtype == MAKB200_F64) {
+            const std::vector<int> ph = svd_phased_blocks<double>(batch, m, n);
+            if (ph.size() >= 8) svd_chunk_plan<double>(h, ph, m, n, &region);
+        } else {
+            const std::vector<int> ph = svd_phased_blocks<cplx>(batch, m, n);
+            if (ph.size() >= 8) svd_chunk_plan<cplx>(h, ph, m, n, &region);
+        }
+        phased = std::max(phased, region + 8192);
+    }
     return bytes + pooled_worksize(big, nbig, staging) + phased + mak::align_up(sizeof(double) * nbig, 256) + 512;
 }
 
@@ -1482,7 +1542,26 @@ static bool bhetrd_enabled() {
     const char* e = getenv("MAKB200_BHETRD");   // read per call: the tests toggle it
     return !(e && e[0] == '0');
 }
-constexpr int EIGH_LS_CHUNK = 192;       // blocks per lock-step eigensolve
+constexpr int EIGH_LS_CHUNK = 192;       // least blocks per lock-step eigensolve (when that many are left)
+constexpr size_t EIGH_LS_BUDGET = (size_t)4 << 30, EIGH_LS_MAX_CHUNK = 4096;
+// chunks of the lock-step eigensolve over block orders sorted descending: as many blocks as fit EIGH_LS_BUDGET bytes of
+// workspace (bounded below / above); returns (first, count) pairs and the largest workspace any chunk needs
+template <typename T>
+static std::vector<std::pair<size_t, size_t>> eigh_ls_chunks(const std::vector<int>& ns, size_t* region) {
+    std::vector<std::pair<size_t, size_t>> out;
+    size_t reg = 0;
+    for (size_t c0 = 0; c0 < ns.size();) {
+        const int nmax = ns[c0];
+        const size_t per = mak::eigh_lockstep_bytes<T>(64, nmax) / 64 + 1;
+        size_t nc = std::min<size_t>(std::max<size_t>(EIGH_LS_BUDGET / per, (size_t)EIGH_LS_CHUNK), EIGH_LS_MAX_CHUNK);
+        nc = std::min(nc, ns.size() - c0);
+        reg = std::max(reg, mak::eigh_lockstep_bytes<T>((int)nc, nmax));
+        out.emplace_back(c0, nc);
+        c0 += nc;
+    }
+    if (region) *region = reg;
+    return out;
+}
 template <typename T>
 static int eigh_batched_t(makb200_handle_t* h, int fixgauge, int batch, const int* n, void* const* A, const int* lda,
                           void* const* W, void* const* V, const int* ldv, int* info, void* work, size_t lwork) {
@@ -1553,12 +1632,14 @@ static int eigh_batched_t(makb200_handle_t* h, int fixgauge, int batch, const in
         for (int i : big) if (pre[i].d && n[i] >= 3) ls.push_back(i);
         if (ls.size() >= 8) {
             std::stable_sort(ls.begin(), ls.end(), [&](int a, int b) { return n[a] > n[b]; });
-            const size_t chunk = std::min<size_t>((size_t)EIGH_LS_CHUNK, ls.size());
-            const size_t need = mak::eigh_lockstep_bytes<T>((int)chunk, n[ls[0]]);
+            std::vector<int> lsn(ls.size());
+            for (size_t q = 0; q < ls.size(); ++q) lsn[q] = n[ls[q]];
+            size_t need = 0;
+            const std::vector<std::pair<size_t, size_t>> chunks = eigh_ls_chunks<T>(lsn, &need);
             if (need + 512 <= lbig) {
                 char* lsb = (char*)mak::align_up((size_t)(uintptr_t)wbig, 256);
-                for (size_t c0 = 0; c0 < ls.size(); c0 += chunk) {
-                    const size_t nc = std::min(chunk, ls.size() - c0);
+                for (const auto& ck : chunks) {
+                    const size_t c0 = ck.first, nc = ck.second;
                     std::vector<mak::EighLsBlk<T>> eb(nc);
                     for (size_t q = 0; q < nc; ++q) {
                         const int i = ls[c0 + q];
@@ -1653,10 +1734,15 @@ size_t makb200_eigh_batched_worksize(makb200_handle_t* h, int dtype, int batch, 
     size_t pooled = any ? pooled_worksize(big, nbig, staging) : 0;
     // lock-step eigensolve of the tridiagonalised blocks (shares the region of the pooled slices)
     if (nbig >= 8 && nmax_ls > 0) {
-        const size_t chunk = nbig < (size_t)EIGH_LS_CHUNK ? nbig : (size_t)EIGH_LS_CHUNK;
-        const size_t ls = (dtype == MAKB200_F64 ? mak::eigh_lockstep_bytes<double>((int)chunk, (int)nmax_ls)
-                                                : mak::eigh_lockstep_bytes<cplx>((int)chunk, (int)nmax_ls)) + 1024;
-        if (ls > pooled) pooled = ls;
+        std::vector<int> lsn;
+        for (int i = 0; i < batch; ++i)
+            if (n[i] >= 3 && n[i] <= mak::BHETRD_MAX_N && mak::batched_eigh_smem_bytes(n[i], esz) > mak::batched_eigh_max_smem_bytes())
+                lsn.push_back(n[i]);
+        std::sort(lsn.begin(), lsn.end(), [](int a, int b) { return a > b; });
+        size_t ls = 0;
+        if (dtype == MAKB200_F64) eigh_ls_chunks<double>(lsn, &ls);
+        else eigh_ls_chunks<cplx>(lsn, &ls);
+        if (ls + 1024 > pooled) pooled = ls + 1024;
     }
     return bytes + pooled + 512;
 }
