@@ -2,7 +2,9 @@
 (per launch, of `python bench.py --steps 1 --warmup 0 --no-cpu`) into profiles/traffic.json:
 per kernel class the launch count, mean DRAM bytes per launch and total device time.
 bench.py reads that file to fill roofline.traffic.
-  python tools/traffic_summ.py gpurun_out/traffic.csv profiles/traffic.json"""
+  python tools/traffic_summ.py gpurun_out/traffic.csv profiles/traffic.json [n] [sample note]
+With n given, the sampled column-kernel launches are taken to be columns 0..k-1 of the first tridiagonalisation and
+their algorithmic bytes (lower triangle of the trailing matrix once per column) are stored beside the measured ones."""
 import csv
 import json
 import sys
@@ -38,5 +40,15 @@ for cls, a in agg.items():
     out["kernels"][cls] = {"launches": n, "dram_bytes_per_launch": (a["read"] + a["write"]) / max(n, 1),
                            "dram_read_bytes_total": a["read"], "dram_write_bytes_total": a["write"],
                            "ncu_ms_total": a["ms"]}
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+note = sys.argv[4] if len(sys.argv) > 4 else ""
+for cls, k in out["kernels"].items():
+    if note:
+        k["sample"] = note
+    if cls == "trd_symv_kernel" and n > 0:
+        cnt = k["launches"]
+        alg = sum(8.0 * (n - c - 1) * (n - c) / 2 for c in range(cnt)) / max(cnt, 1)
+        k["alg_bytes_per_launch_same_sample"] = alg
+        k["traffic_over_algorithmic"] = k["dram_bytes_per_launch"] / alg
 json.dump(out, open(sys.argv[2], "w"), indent=1)
 print(json.dumps(out, indent=1))
