@@ -60,8 +60,9 @@ struct LsBlk {
     T* Q0;                   // m x n   (m > n only)
     T* R0;                   // n x n   (m > n only)
 };
+constexpr int LS_NPROBE = 8;   // Hutchinson probes of the sigma_min estimate
 enum LsBuf { LS_X = 0, LS_B, LS_Q, LS_T2, LS_Z, LS_L, LS_W, LS_A };
-enum LsKind { LS_GEMM = 0, LS_PREP, LS_STACK, LS_ADDDIAG, LS_AXPBY, LS_COPY, LS_SYMM, LS_POTF2, LS_QR_STACK, LS_QR_TALL };
+enum LsKind { LS_GEMM = 0, LS_PREP, LS_STACK, LS_ADDDIAG, LS_AXPBY, LS_COPY, LS_SYMM, LS_POTF2, LS_QR_STACK, LS_QR_TALL, LS_PROBE, LS_FRO };
 // one launch of the lock-step sequence.  `count` blocks take part (a prefix of the n-descending order).
 struct LsAct {
     int kind;
@@ -70,5 +71,6 @@ struct LsAct {
     size_t off;                   // LS_GEMM: first descriptor
     int a0, a1, a2;               // LS_COPY: src buffer, dst buffer, row multiple (1: n rows, 2: 2n rows); LS_POTF2: j0, block index
     double p0, p1;                // LS_STACK: sqrt(c); LS_AXPBY: X = p0 X + p1 B
+                                  // LS_PROBE: T2 (LS_NPROBE x n, ld LS_NPROBE) = +-1 entries; LS_FRO: est[i] = ||Q (LS_NPROBE x n)||_F^2
 };
 }  // namespace mak

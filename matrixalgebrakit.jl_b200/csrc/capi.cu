@@ -1121,6 +1121,13 @@ static size_t svd_phase_persist_bytes(int m, int n) {
 // were bound by exactly that.  Used by the workspace query and the run, so both see the same chunks.
 constexpr size_t SVD_LS_BUDGET = (size_t)8 << 30;
 constexpr size_t SVD_LS_MAX_CHUNK = 2048;
+constexpr int SVD_LS_MIN_CHUNK_DEFAULT = 296;   // 2 x 148 SMs: 2412 -> 2300 ms on the 257-512 bucket of config 3 (192 blocks = 1.3 waves of the one-launch tridiagonalisation)
+// least blocks per lock-step chunk: two CTAs of the one-launch tridiagonalisation per SM (MAKB200_SVD_CHUNK_MIN overrides)
+static size_t svd_ls_min_chunk() {
+    const char* e = getenv("MAKB200_SVD_CHUNK_MIN");   // read per call (workspace query and run see the same value)
+    const int v = e ? atoi(e) : SVD_LS_MIN_CHUNK_DEFAULT;
+    return (size_t)(v < 8 ? 8 : v);
+}
 struct SvdChunk { size_t c0, nc; int mmax, nmax; bool tall; size_t persist, ls_total, ls_bb, ls_tb, ls_qb; };
 template <typename T>
 static std::vector<SvdChunk> svd_chunk_plan(makb200_handle_t* h, const std::vector<int>& ph, const int* m, const int* n,
@@ -1135,7 +1142,7 @@ static std::vector<SvdChunk> svd_chunk_plan(makb200_handle_t* h, const std::vect
         while (c0 + c.nc < ph.size() && c.nc < SVD_LS_MAX_CHUNK) {
             const int i = ph[c0 + c.nc];
             const size_t bi = mak::ls_block_elems<T>(m[i], n[i], lnb) * sizeof(T) + svd_phase_persist_bytes<T>(m[i], n[i]);
-            if (c.nc >= (size_t)SVD_PHASE_CHUNK && bytes + bi > SVD_LS_BUDGET) break;
+            if (c.nc >= svd_ls_min_chunk() && bytes + bi > SVD_LS_BUDGET) break;
             bytes += bi;
             c.mmax = std::max(c.mmax, m[i]); c.nmax = std::max(c.nmax, n[i]);
             c.tall = c.tall || m[i] > n[i];

@@ -106,6 +106,12 @@ __global__ void ls_ew_kernel(const LsBlk<T>* __restrict__ blks, int kind, int a0
             for (size_t idx = start; idx < total; idx += step) dst[idx] = src[idx];
             break;
         }
+        case LS_PROBE: {   // T2 (LS_NPROBE x n, ld LS_NPROBE) = Rademacher probes of the sigma_min estimate
+            const size_t total = (size_t)LS_NPROBE * n;
+            for (size_t idx = start; idx < total; idx += step)
+                b.T2[idx] = mk<T>(ls_probe_entry((int)(idx % LS_NPROBE), (int)(idx / LS_NPROBE)));
+            break;
+        }
         case LS_SYMM: {   // P = (Z + Z^H) / 2, real diagonal
             const size_t total = (size_t)n * n;
             for (size_t idx = start; idx < total; idx += step) {
@@ -118,6 +124,18 @@ __global__ void ls_ew_kernel(const LsBlk<T>* __restrict__ blks, int kind, int a0
         }
         default: break;
     }
+}
+
+// est[i] = ||Q_i (LS_NPROBE x n)||_F^2  (the solved probes of the sigma_min estimate), one CTA per block
+template <typename T>
+__global__ void __launch_bounds__(256) ls_fro_kernel(const LsBlk<T>* __restrict__ blks, double* __restrict__ est) {
+    __shared__ double red[32];
+    const LsBlk<T> b = blks[blockIdx.x];
+    const size_t total = (size_t)LS_NPROBE * b.n;
+    double s = 0.0;
+    for (size_t idx = threadIdx.x; idx < total; idx += blockDim.x) s += abs2_(b.Q[idx]);
+    const double t = block_sum<double>(s, red);
+    if (threadIdx.x == 0) est[blockIdx.x] = t;
 }
 
 // diagonal block (column j0, index bi) of every active block: L_jj and its inverse, one CTA per block
@@ -148,29 +166,24 @@ inline size_t ls_tables_bytes(int count, int nmax, bool any_tall) {
     const std::vector<QdwhStep> sched = qdwh_schedule(2.2e-16, 12, 100.0);
     const size_t launches = (size_t)ls_gemm_launch_bound<T>(nmax, nb, any_tall, sched);
     return align_up(sizeof(LsBlk<T>) * (size_t)count, 256) + align_up(sizeof(int) * (size_t)count, 256) +
-           align_up(sizeof(GemmProblem<T>) * launches * (size_t)count, 256) + 1024;
+           align_up(sizeof(double) * (size_t)count, 256) + align_up(sizeof(GemmProblem<T>) * launches * (size_t)count, 256) + 1024;
 }
 
-// Replays the plan.  `blk`: host copy of the blocks (n descending, buffers carved); tables: device region of
-// ls_tables_bytes; qr(batch, m, n, A, lda, Q, ldq, R, ldr): the batched QR of capi.cu (A overwritten, R may be null).
+// sigma_min estimate per chunk (default on): MAKB200_LS_ESTIMATE=0 runs the fixed l0 = eps schedule
+inline bool ls_estimate_enabled() {
+    const char* e = getenv("MAKB200_LS_ESTIMATE");   // read per call: tests run both
+    return !(e && e[0] == '0');
+}
+
+// Uploads one plan (blocks + descriptors) and replays it.  qr(batch, m, n, A, lda, Q, ldq, R, ldr): the batched QR of
+// capi.cu (A overwritten, R may be null).
 template <typename T, typename QRF>
-int polar_lockstep_run(makb200_handle* h, const std::vector<LsBlk<T>>& blk, char* tables, size_t tables_bytes, QRF qr) {
+int polar_lockstep_replay(makb200_handle* h, const std::vector<LsBlk<T>>& blk, const LsPlan<T>& pl, LsBlk<T>* bdev, int* info,
+                          double* est, GemmProblem<T>* pdev, size_t pcap, QRF& qr) {
     constexpr int nb = CholNB<T>::value;
     const int count = (int)blk.size();
-    if (count == 0) return 0;
-    int rc = ls_init<T>(h);
-    if (rc) return rc;
     cudaStream_t s = h->stream;
-    LsPlan<T> pl;
-    {
-        LsPlanner<T> planner(blk, nb, pl);
-        planner.build(qdwh_schedule(2.2e-16, 12, 100.0));
-    }
-    size_t off = 0;
-    LsBlk<T>* bdev = (LsBlk<T>*)(tables + off); off += align_up(sizeof(LsBlk<T>) * (size_t)count, 256);
-    int* info = (int*)(tables + off); off += align_up(sizeof(int) * (size_t)count, 256);
-    GemmProblem<T>* pdev = (GemmProblem<T>*)(tables + off); off += align_up(sizeof(GemmProblem<T>) * pl.probs.size(), 256);
-    if (off > tables_bytes) return MAKB200_ERR_WORKSPACE;
+    if (pl.probs.size() > pcap) return MAKB200_ERR_WORKSPACE;
     {
         Stager st(h, sizeof(LsBlk<T>) * (size_t)count + sizeof(GemmProblem<T>) * pl.probs.size() + 1024);
         MAK_CUDA(h, st.put(bdev, blk.data(), sizeof(LsBlk<T>) * (size_t)count, s));
@@ -181,6 +194,7 @@ int polar_lockstep_run(makb200_handle* h, const std::vector<LsBlk<T>>& blk, char
         ls_ew_kernel<T><<<dim3(gx, a.count), 256, 0, s>>>(bdev, a.kind, a.a0, a.a1, a.a2, a.p0, a.p1);
         count_launch();
     };
+    int rc = 0;
     for (const LsAct& a : pl.acts) {
         switch (a.kind) {
             case LS_GEMM: {
@@ -195,8 +209,12 @@ int polar_lockstep_run(makb200_handle* h, const std::vector<LsBlk<T>>& blk, char
             case LS_STACK: case LS_AXPBY: case LS_COPY: case LS_SYMM:
                 ew(a, 32);
                 break;
-            case LS_ADDDIAG:
+            case LS_ADDDIAG: case LS_PROBE:
                 ew(a, 1);
+                break;
+            case LS_FRO:
+                ls_fro_kernel<T><<<a.count, 256, 0, s>>>(bdev, est);
+                count_launch();
                 break;
             case LS_POTF2:
                 ls_potf2_kernel<T, nb><<<a.count, 256, sizeof(T) * nb * (nb + 1), s>>>(bdev, a.a0, a.a1, info);
@@ -234,7 +252,71 @@ int polar_lockstep_run(makb200_handle* h, const std::vector<LsBlk<T>>& blk, char
             default: break;
         }
     }
-    MAK_LAUNCH_CHECK(h, "polar_lockstep_run");
+    MAK_LAUNCH_CHECK(h, "polar_lockstep_replay");
+    return 0;
+}
+
+// The lock-step polar decomposition of a chunk.  `blk`: host copy of the blocks (n descending, buffers carved); tables:
+// device region of ls_tables_bytes.
+//   1. X0 and, unless MAKB200_LS_ESTIMATE=0, the sigma_min estimate of every block (one plan, ONE device-to-host read)
+//   2. blocks with a usable estimate run the QDWH schedule of the SMALLEST l0 among them (a lower bound for each: the
+//      schedule converges for all; for well-conditioned blocks it has no Householder step and one step fewer);
+//      the others (Cholesky of X0^H X0 broke down, l0 <= 1e-7: rank-deficient or kappa > ~1e6) run the l0 = eps schedule
+template <typename T, typename QRF>
+int polar_lockstep_run(makb200_handle* h, const std::vector<LsBlk<T>>& blk, char* tables, size_t tables_bytes, QRF qr) {
+    constexpr int nb = CholNB<T>::value;
+    const int count = (int)blk.size();
+    if (count == 0) return 0;
+    int rc = ls_init<T>(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    size_t off = 0;
+    LsBlk<T>* bdev = (LsBlk<T>*)(tables + off); off += align_up(sizeof(LsBlk<T>) * (size_t)count, 256);
+    int* info = (int*)(tables + off); off += align_up(sizeof(int) * (size_t)count, 256);
+    double* est = (double*)(tables + off); off += align_up(sizeof(double) * (size_t)count, 256);
+    if (off + 1024 > tables_bytes) return MAKB200_ERR_WORKSPACE;
+    GemmProblem<T>* pdev = (GemmProblem<T>*)(tables + off);
+    const size_t pcap = (tables_bytes - off) / sizeof(GemmProblem<T>);
+    const bool estimate = ls_estimate_enabled();
+    {
+        LsPlan<T> pl;
+        LsPlanner<T> planner(blk, nb, pl);
+        planner.build_prepare(estimate);
+        rc = polar_lockstep_replay<T>(h, blk, pl, bdev, info, est, pdev, pcap, qr);
+        if (rc) return rc;
+    }
+    std::vector<LsBlk<T>> fast, slow;
+    double l0_fast = 0.9;
+    if (estimate) {
+        std::vector<double> hest(count);
+        std::vector<int> hinfo(count);
+        MAK_CUDA(h, cudaMemcpyAsync(hest.data(), est, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, s));
+        MAK_CUDA(h, cudaMemcpyAsync(hinfo.data(), info, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, s));
+        MAK_CUDA(h, cudaStreamSynchronize(s));
+        for (int i = 0; i < count; ++i) {
+            const double l0 = ls_l0_from_estimate(hest[i], hinfo[i]);
+            if (l0 > 1e-7) { fast.push_back(blk[i]); l0_fast = std::min(l0_fast, l0); }
+            else slow.push_back(blk[i]);
+        }
+    } else {
+        slow = blk;
+    }
+    if (getenv("MAKB200_LOCKSTEP_VERBOSE"))
+        fprintf(stderr, "[makb200] lock-step QDWH: %zu blocks on the l0 = %.2e schedule, %zu on l0 = eps\n", fast.size(), l0_fast, slow.size());
+    if (!fast.empty()) {
+        LsPlan<T> pl;
+        LsPlanner<T> planner(fast, nb, pl);
+        planner.build_iterate(qdwh_schedule(l0_fast, 12, 100.0));
+        rc = polar_lockstep_replay<T>(h, fast, pl, bdev, info, est, pdev, pcap, qr);
+        if (rc) return rc;
+    }
+    if (!slow.empty()) {
+        LsPlan<T> pl;
+        LsPlanner<T> planner(slow, nb, pl);
+        planner.build_iterate(qdwh_schedule(2.2e-16, 12, 100.0));
+        rc = polar_lockstep_replay<T>(h, slow, pl, bdev, info, est, pdev, pcap, qr);
+        if (rc) return rc;
+    }
     return 0;
 }
 

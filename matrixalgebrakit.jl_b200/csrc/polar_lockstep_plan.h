@@ -150,9 +150,10 @@ struct LsPlanner {
             gemm(0, 2, g);
         }
     }
-    // dst = src L^-H (conj) or src L^-1; src, dst, T2 hold rowmult * n rows
-    void trsm(bool conj, int rowmult, int src, int dst) {
-        act(LS_COPY, count, src, LS_T2, rowmult);
+    // dst = src L^-H (conj) or src L^-1; src, dst, T2 hold rowmult * n rows, or `rows` rows when rows > 0 (then the
+    // right-hand side is already in T2)
+    void trsm(bool conj, int rowmult, int src, int dst, int rows = 0) {
+        if (rows <= 0) act(LS_COPY, count, src, LS_T2, rowmult);
         const int nblk = (nmax + nb - 1) / nb;
         for (int bb = 0; bb < nblk; ++bb) {
             const int bi = conj ? bb : nblk - 1 - bb, j0 = bi * nb;
@@ -160,7 +161,7 @@ struct LsPlanner {
             std::vector<GemmProblem<T>> g1, g2;
             for (int i = 0; i < na; ++i) {
                 const auto& b = blk[i];
-                const int n = b.n, mr = rowmult * n, jb = std::min(nb, n - j0);
+                const int n = b.n, mr = rows > 0 ? rows : rowmult * n, jb = std::min(nb, n - j0);
                 T* Y = buf(b, dst);
                 T* Tj = b.T2 + (size_t)j0 * mr;
                 const T* Li = b.Linv + (size_t)bi * nb * nb;
@@ -189,11 +190,25 @@ struct LsPlanner {
         }
         gemm(0, 2, g);
     }
-    void build(const std::vector<QdwhStep>& sched) {
+    // part 1: X0 = S / ||S||_F (after A = Q0 R0 for tall blocks) and the sigma_min estimate of every block:
+    // Z = X0^H X0 = L L^H, est_i = ||G L^-H||_F^2 for LS_NPROBE Rademacher rows G  (= sum_k g_k^T Z^-1 g_k ~ NPROBE tr(Z^-1),
+    // and sigma_min(X0) >= 1 / sqrt(tr(Z^-1))): ls_l0_from_estimate turns (est_i, Cholesky info_i) into l0
+    void build_prepare(bool estimate) {
         bool any_tall = false;
         for (const auto& b : blk) any_tall = any_tall || b.m > b.n;
         if (any_tall) act(LS_QR_TALL, count);
         act(LS_PREP, count);
+        if (!estimate) return;
+        gram(LS_X, 1, 1.0);
+        potrf();
+        act(LS_PROBE, count);
+        trsm(true, 1, LS_T2, LS_Q, LS_NPROBE);
+        act(LS_FRO, count);
+    }
+    // part 2: the QDWH steps of `sched` and W, P
+    void build_iterate(const std::vector<QdwhStep>& sched) {
+        bool any_tall = false;
+        for (const auto& b : blk) any_tall = any_tall || b.m > b.n;
         for (const QdwhStep& st : sched) {
             if (st.qr) {
                 act(LS_STACK, count, 0, 0, 0, sqrt(st.c));
@@ -239,7 +254,32 @@ struct LsPlanner {
         }
         act(LS_SYMM, count);
     }
+    void build(const std::vector<QdwhStep>& sched) {
+        build_prepare(false);
+        build_iterate(sched);
+    }
 };
+
+// l0 of a block from its estimate (est = ||G L^-H||_F^2 over LS_NPROBE probes; info != 0: the Cholesky of X0^H X0 broke
+// down).  Same rule as the single-matrix driver (polar.cu): l0 = 0.3 / sqrt(tr) when that exceeds 1e-7, else eps.
+inline double ls_l0_from_estimate(double est, int info) {
+    const double eps_l0 = 2.2e-16;
+    const double tr = est / LS_NPROBE;
+    if (info != 0 || !(tr > 0.0) || !std::isfinite(tr)) return eps_l0;
+    const double l0 = 0.3 / std::sqrt(tr);
+    if (!(l0 > 1e-7)) return eps_l0;
+    return l0 < 0.9 ? l0 : 0.9;
+}
+// +-1 entry (row r, column c) of a block's probe matrix: a hash of the position, the same on the device and in the CPU replay
+inline
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+double ls_probe_entry(int r, int c) {
+    unsigned h = ((unsigned)c * LS_NPROBE + (unsigned)r) * 2654435761u + 777u;
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    return (h & 1u) ? 1.0 : -1.0;
+}
 
 // GEMM launches of the plan for the largest block (bound for the descriptor storage: launches * blocks)
 template <typename T>
@@ -251,7 +291,8 @@ inline int ls_gemm_launch_bound(int nmax, int nb, bool any_tall, const std::vect
     one[0].lda = one[0].m;
     LsPlan<T> pl;
     LsPlanner<T> p(one, nb, pl);
-    p.build(sched);
+    p.build_prepare(true);
+    p.build_iterate(sched);
     return pl.gemm_launches;
 }
 

@@ -85,31 +85,11 @@ static int host_potf2(int jb, const T* Z, int ldz, T* L, int ldl, T* Linv, int n
 template <typename T>
 static T* host_buf(const LsBlk<T>& b, int id) { return LsPlanner<T>::buf(b, id); }
 
+// executes one plan on the host; info[i] / est[i] per block of `blk`
 template <typename T>
-static int replay(int count, const int* m, const int* n, void* const* A, void* const* W, void* const* P, int nb, int* n_acts,
-                  int* n_gemm) {
-    std::vector<LsBlk<T>> blk(count);
-    size_t elems = 0;
-    for (int i = 0; i < count; ++i) elems += ls_block_elems<T>(m[i], n[i], nb);
-    const double nan = std::numeric_limits<double>::quiet_NaN();
-    std::vector<T> store(elems, mk<T>(nan));
-    T* p = store.data();
-    for (int i = 0; i < count; ++i) {
-        if (i > 0 && n[i] > n[i - 1]) return -1;   // the caller sorts by n descending
-        LsBlk<T>& b = blk[i];
-        b = LsBlk<T>{};
-        b.m = m[i]; b.n = n[i];
-        b.A = (const T*)A[i]; b.lda = m[i];
-        b.W = (T*)W[i]; b.P = (T*)P[i];
-        ls_carve_block<T>(b, p, nb);
-    }
-    if ((size_t)(p - store.data()) > elems) return -2;
-    LsPlan<T> pl;
-    LsPlanner<T> planner(blk, nb, pl);
-    planner.build(qdwh_schedule(2.2e-16, 12, 100.0));
-    if (n_acts) *n_acts = (int)pl.acts.size();
-    if (n_gemm) *n_gemm = pl.gemm_launches;
-    int info = 0;
+static int exec_plan(const std::vector<LsBlk<T>>& blk, const LsPlan<T>& pl, int nb, std::vector<int>& info, std::vector<double>& est) {
+    info.assign(blk.size(), 0);
+    est.assign(blk.size(), 0.0);
     for (const LsAct& a : pl.acts) {
         switch (a.kind) {
             case LS_GEMM:
@@ -180,8 +160,20 @@ static int replay(int count, const int* m, const int* n, void* const* A, void* c
                     const LsBlk<T>& b = blk[i];
                     const int nn = b.n, j0 = a.a0, jb = std::min(nb, nn - j0);
                     if (jb <= 0) return -4;   // inactive block inside the active prefix
-                    info |= host_potf2<T>(jb, b.Z + (size_t)j0 * nn + j0, nn, b.L + (size_t)j0 * nn + j0, nn,
-                                          b.Linv + (size_t)a.a1 * nb * nb, nb);
+                    info[i] |= host_potf2<T>(jb, b.Z + (size_t)j0 * nn + j0, nn, b.L + (size_t)j0 * nn + j0, nn,
+                                             b.Linv + (size_t)a.a1 * nb * nb, nb);
+                }
+                break;
+            case LS_PROBE:
+                for (int i = 0; i < a.count; ++i)
+                    for (int c = 0; c < blk[i].n; ++c)
+                        for (int r = 0; r < LS_NPROBE; ++r) blk[i].T2[(size_t)c * LS_NPROBE + r] = mk<T>(ls_probe_entry(r, c));
+                break;
+            case LS_FRO:
+                for (int i = 0; i < a.count; ++i) {
+                    double s = 0.0;
+                    for (size_t e = 0; e < (size_t)LS_NPROBE * blk[i].n; ++e) s += abs2_(blk[i].Q[e]);
+                    est[i] = s;
                 }
                 break;
             case LS_QR_TALL:
@@ -204,13 +196,76 @@ static int replay(int count, const int* m, const int* n, void* const* A, void* c
             default: return -5;
         }
     }
-    return info;
+    return 0;
+}
+
+// the driver of csrc/polar_lockstep.cuh: polar_lockstep_run, on the host
+template <typename T>
+static int replay(int count, const int* m, const int* n, void* const* A, void* const* W, void* const* P, int nb, int estimate,
+                  int* n_acts, int* n_gemm, int* n_fast, double* l0_out) {
+    std::vector<LsBlk<T>> blk(count);
+    size_t elems = 0;
+    for (int i = 0; i < count; ++i) elems += ls_block_elems<T>(m[i], n[i], nb);
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    std::vector<T> store(elems, mk<T>(nan));
+    T* p = store.data();
+    for (int i = 0; i < count; ++i) {
+        if (i > 0 && n[i] > n[i - 1]) return -1;   // the caller sorts by n descending
+        LsBlk<T>& b = blk[i];
+        b = LsBlk<T>{};
+        b.m = m[i]; b.n = n[i];
+        b.A = (const T*)A[i]; b.lda = m[i];
+        b.W = (T*)W[i]; b.P = (T*)P[i];
+        ls_carve_block<T>(b, p, nb);
+    }
+    if ((size_t)(p - store.data()) > elems) return -2;
+    std::vector<int> info;
+    std::vector<double> est;
+    int acts = 0, gemms = 0;
+    {
+        LsPlan<T> pl;
+        LsPlanner<T> planner(blk, nb, pl);
+        planner.build_prepare(estimate != 0);
+        int rc = exec_plan<T>(blk, pl, nb, info, est);
+        if (rc) return rc;
+        acts += (int)pl.acts.size(); gemms += pl.gemm_launches;
+    }
+    std::vector<LsBlk<T>> fast, slow;
+    double l0_fast = 0.9;
+    if (estimate) {
+        for (int i = 0; i < count; ++i) {
+            const double l0 = ls_l0_from_estimate(est[i], info[i]);
+            if (l0 > 1e-7) { fast.push_back(blk[i]); l0_fast = std::min(l0_fast, l0); }
+            else slow.push_back(blk[i]);
+        }
+    } else {
+        slow = blk;
+    }
+    int bad = 0;
+    for (int g = 0; g < 2; ++g) {
+        const std::vector<LsBlk<T>>& grp = g == 0 ? fast : slow;
+        if (grp.empty()) continue;
+        LsPlan<T> pl;
+        LsPlanner<T> planner(grp, nb, pl);
+        planner.build_iterate(qdwh_schedule(g == 0 ? l0_fast : 2.2e-16, 12, 100.0));
+        std::vector<int> info2;
+        std::vector<double> est2;
+        int rc = exec_plan<T>(grp, pl, nb, info2, est2);
+        if (rc) return rc;
+        for (int v : info2) bad |= v;   // the iteration's matrices I + c X^H X are positive definite
+        acts += (int)pl.acts.size(); gemms = std::max(gemms, pl.gemm_launches);
+    }
+    if (n_acts) *n_acts = acts;
+    if (n_gemm) *n_gemm = gemms;
+    if (n_fast) *n_fast = (int)fast.size();
+    if (l0_out) *l0_out = l0_fast;
+    return bad;
 }
 
 extern "C" int lockstep_replay(int dtype, int count, const int* m, const int* n, void* const* A, void* const* W, void* const* P,
-                               int nb, int* n_acts, int* n_gemm) {
-    return dtype == 0 ? replay<double>(count, m, n, A, W, P, nb, n_acts, n_gemm)
-                      : replay<cplx>(count, m, n, A, W, P, nb, n_acts, n_gemm);
+                               int nb, int estimate, int* n_acts, int* n_gemm, int* n_fast, double* l0) {
+    return dtype == 0 ? replay<double>(count, m, n, A, W, P, nb, estimate, n_acts, n_gemm, n_fast, l0)
+                      : replay<cplx>(count, m, n, A, W, P, nb, estimate, n_acts, n_gemm, n_fast, l0);
 }
 extern "C" int lockstep_launch_bound(int dtype, int nmax, int nb, int any_tall) {
     const std::vector<QdwhStep> sched = qdwh_schedule(2.2e-16, 12, 100.0);

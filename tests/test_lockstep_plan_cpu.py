@@ -30,7 +30,7 @@ def _rand(m, n, cplx, rng):
     return np.asfortranarray(a)
 
 
-def _run(lib, mats, cplx, nb):
+def _run(lib, mats, cplx, nb, estimate=1):
     order = sorted(range(len(mats)), key=lambda i: -mats[i].shape[1])
     mats = [mats[i] for i in order]
     count = len(mats)
@@ -43,9 +43,11 @@ def _run(lib, mats, cplx, nb):
     pa = (vp * count)(*[a.ctypes.data for a in mats])
     pw = (vp * count)(*[a.ctypes.data for a in W])
     pp = (vp * count)(*[a.ctypes.data for a in P])
-    na, ng = ctypes.c_int(), ctypes.c_int()
-    rc = lib.lockstep_replay(1 if cplx else 0, count, m, n, pa, pw, pp, nb, ctypes.byref(na), ctypes.byref(ng))
+    na, ng, nf, l0 = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+    rc = lib.lockstep_replay(1 if cplx else 0, count, m, n, pa, pw, pp, nb, estimate, ctypes.byref(na), ctypes.byref(ng),
+                             ctypes.byref(nf), ctypes.byref(l0))
     assert rc == 0
+    _run.last = (nf.value, l0.value)
     return mats, W, P, na.value, ng.value
 
 
@@ -63,13 +65,21 @@ def _check(a, w, p, cond_scale=1.0):
 
 @pytest.mark.parametrize("cplx", [False, True])
 @pytest.mark.parametrize("nb", [4, 8])
-def test_square_ragged_chunk(lib, cplx, nb):
+@pytest.mark.parametrize("estimate", [1, 0])
+def test_square_ragged_chunk(lib, cplx, nb, estimate):
     rng = np.random.default_rng(3 + nb)
     sizes = [3, 5, 8, 9, 16, 17, 23, 24, 31, 7, 12]
     mats = [_rand(s, s, cplx, rng) for s in sizes]
-    mats, W, P, na, ng = _run(lib, mats, cplx, nb)
+    mats, W, P, na, ng = _run(lib, mats, cplx, nb, estimate)
     for a, w, p in zip(mats, W, P):
         _check(a, w, p, max(1.0, np.linalg.cond(a) / 100))
+    if estimate:
+        # every Gaussian block has a usable estimate; the chunk's l0 is a lower bound of every block's sigma_min(X0)
+        nf, l0 = _run.last
+        assert nf == len(sizes)
+        assert all(l0 <= np.linalg.svd(a, compute_uv=False)[-1] / np.linalg.norm(a) for a in mats)
+    else:
+        assert _run.last[0] == 0
     # the descriptor storage bound used by the workspace query covers the plan
     assert ng <= lib.lockstep_launch_bound(1 if cplx else 0, max(sizes), nb, 0)
 
@@ -93,7 +103,10 @@ def test_graded_and_rank_deficient(lib):
     graded = np.asfortranarray((q1 * 10.0 ** (-10 * np.arange(n) / n)) @ q2)       # kappa = 1e10
     lowrank = np.asfortranarray(rng.standard_normal((n, 3)) @ rng.standard_normal((3, n)))
     tiny = np.asfortranarray(1e-200 * rng.standard_normal((n, n)))
-    mats, W, P, _, _ = _run(lib, [graded, lowrank, tiny], False, 8)
+    easy = _rand(n, n, False, rng)
+    mats, W, P, _, _ = _run(lib, [graded, lowrank, tiny, easy], False, 8)
+    # kappa = 1e10 and rank 3 fall back to the l0 = eps schedule; the tiny-norm Gaussian block and the plain one do not
+    assert _run.last[0] == 2
     tol = 10 * n * EPS
     for a, w, p in zip(mats, W, P):
         assert np.all(np.isfinite(w)) and np.all(np.isfinite(p))
