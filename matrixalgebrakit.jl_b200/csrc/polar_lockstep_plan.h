@@ -6,10 +6,14 @@
 // descriptors, csrc/gemm.cu: gemm_grouped) or ONE batched kernel with a CTA (or CTA column) per block, so a chunk of
 // 192 blocks costs ~600 launches instead of ~100 000.
 //
-// With l0 = eps (no conditioning estimate below n = 1024, polar.cu) the QDWH schedule is the same for every block:
-//   step 1  (c ~ 1e21)  Householder QR of [sqrt(c) X; I]            -> the lock-step batched QR (batched_blocked.cu)
-//   step 2  (c ~ 4e6)   CholeskyQR2 of [sqrt(c) X; I]               -> Gram, Cholesky, triangular solve, twice
-//   steps 3-6           Z = I + c X^H X = L L^H,  X <- (b/c) X + (a - b/c) (X L^-H) L^-1
+// One QDWH schedule serves a whole group of blocks:
+//   part 1 (build_prepare)  X0 = S / ||S||_F and a sigma_min estimate per block (Gram, Cholesky, LS_NPROBE Rademacher
+//                           probes solved against L; the rule of the single-matrix driver, polar.cu); one D2H read
+//   part 2 (build_iterate)  the blocks with a usable estimate run the schedule of the smallest l0 among them, e.g.
+//                             step 1  (c ~ 1e6)   CholeskyQR2 of [sqrt(c) X; I]   -> Gram, Cholesky, triangular solve, twice
+//                             steps 2-5           Z = I + c X^H X = L L^H,  X <- (b/c) X + (a - b/c) (X L^-H) L^-1
+//                           the others the l0 = eps schedule, whose first step (c ~ 1e21) is a Householder QR of
+//                           [sqrt(c) X; I] -> the lock-step batched QR (batched_blocked.cu)
 // and then P = sym(X^H A), W = X (or Q0 X for a tall block, A = Q0 R0 first as the single-matrix driver does).
 // Blocks are sorted by n descending, so the blocks still active at column j0 of a blocked sweep are a prefix.
 //
@@ -253,10 +257,6 @@ struct LsPlanner {
             gemm(2, 0, g);
         }
         act(LS_SYMM, count);
-    }
-    void build(const std::vector<QdwhStep>& sched) {
-        build_prepare(false);
-        build_iterate(sched);
     }
 };
 

@@ -190,13 +190,17 @@ def test_svd_and_eigh_batched_graph_replay(dtype, monkeypatch):
 
 
 @pytest.mark.parametrize("dtype", ["f64", "c128"])
-@pytest.mark.parametrize("lockstep", ["1", "0"])
+@pytest.mark.parametrize("lockstep", ["1", "0", "noest"])
 def test_svd_batched_lockstep_qdwh(dtype, lockstep, monkeypatch, capfd):
     """Mid-size blocks (beyond the one-CTA Jacobi kernel) in a chunk of >= 8: phase 1 of the phased batched SVD is the
-    lock-step QDWH (csrc/polar_lockstep_plan.h: one grouped GEMM / batched kernel per step for ALL blocks); with
-    MAKB200_SVD_LOCKSTEP=0 the same blocks take the per-block chain.  Ragged square and tall blocks, odd sizes (unaligned
+    lock-step QDWH (csrc/polar_lockstep_plan.h: one grouped GEMM / batched kernel per step for ALL blocks; the graded,
+    rank-one and zero blocks fall back to the l0 = eps schedule, the others share the schedule of the chunk's smallest
+    sigma_min estimate); with MAKB200_SVD_LOCKSTEP=0 the same blocks take the per-block chain.  Ragged square and tall blocks, odd sizes (unaligned
     Float64 leading dimensions), and the hard cases: rank one, zero, graded kappa = 1e10, tiny and huge scale."""
     import makb200
+    if lockstep == "noest":      # lock-step on the fixed l0 = eps schedule (no per-chunk sigma_min estimate)
+        monkeypatch.setenv("MAKB200_LS_ESTIMATE", "0")
+        lockstep = "1"
     monkeypatch.setenv("MAKB200_SVD_LOCKSTEP", lockstep)
     monkeypatch.setenv("MAKB200_LOCKSTEP_VERBOSE", "1")
     rng = np.random.default_rng(21)
