@@ -170,7 +170,11 @@ int makb200_stedc(makb200_handle_t* h, int n, const double* d, const double* e, 
  * polar.jl:59-166; contract = its result: A = W P, W isometric m x n, P Hermitian PSD n x n).
  * m >= n required (polar.jl:9-10).  P == NULL or ldp == 0: P not requested (zero-length P,
  * polar.jl:14,64,102).  l0: lower bound for sigma_min(A/||A||_F), <= 0 selects eps (valid for
- * every kappa <= 1e16).  A is destroyed.  iters_host: optional HOST int (QDWH steps scheduled). */
+ * every kappa <= 1e16).  A is destroyed.  iters_host: optional HOST int (QDWH steps scheduled).
+ * Host synchronisation: none for n < 1024 or a caller-supplied l0 > 0 (the schedule is a function of l0 alone and is
+ * computed on the host before the first launch).  For n >= 1024 with l0 <= 0 the sigma_max / sigma_min estimates are
+ * formed on the device and ONE 24-byte device-to-host read (the reference's `info`-style read, yacusolver.jl:101-181)
+ * picks the schedule; MAKB200_QDWH_ESTIMATE=0 or l0 > 0 avoids it. */
 size_t makb200_polar_worksize(makb200_handle_t* h, int dtype, int m, int n);
 int makb200_polar_qdwh(makb200_handle_t* h, int dtype, int m, int n, void* A, int lda, void* W,
                        int ldw, void* P, int ldp, double l0, int maxiter, void* work, size_t lwork,
