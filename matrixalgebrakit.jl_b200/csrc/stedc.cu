@@ -4,6 +4,7 @@
 // counts) are produced on the device, so the whole solver runs without a host round trip.
 #include "stedc.cuh"
 #include "stedc_core.h"
+#include "stedc_batch_tables.h"
 #include "gemm.cuh"
 #include <vector>
 
@@ -551,7 +552,7 @@ size_t stedc_batched_worksize(int nblk, const int* n) {
     int nmax = 1;
     for (int i = 0; i < nblk; ++i) {
         ntot += (size_t)n[i];
-        nleaves += (size_t)1 << dc_levels(n[i]);
+        nleaves += (size_t)1 << dc_tree_levels(n[i]);
         nmax = std::max(nmax, n[i]);
     }
     ArenaSize ar;
@@ -564,56 +565,25 @@ template <typename T>
 int stedc_batched(makb200_handle* h, int nblk, const StedcBlk* blks, void* work, size_t lwork, int* info_dev) {
     if (nblk <= 0) return 0;
     cudaStream_t st = h->stream;
-    size_t ntot = 0, nleaves = 0;
-    int nmax = 1, Lmax = 0;
-    std::vector<int> lev(nblk), off(nblk);
+    std::vector<int> ns(nblk);
     for (int i = 0; i < nblk; ++i) {
         if (blks[i].n <= 0) return -2;
-        off[i] = (int)ntot;
-        ntot += (size_t)blks[i].n;
-        lev[i] = dc_levels(blks[i].n);
-        nleaves += (size_t)1 << lev[i];
-        nmax = std::max(nmax, blks[i].n);
-        Lmax = std::max(Lmax, lev[i]);
+        ns[i] = blks[i].n;
     }
+    // host tables: leaf boundaries (global), cuts, the merges of every level (stedc_batch_tables.h), block descriptors
+    const BatchTables tb = dc_batch_tables(nblk, ns.data());
+    const size_t ntot = tb.ntot, nleaves = tb.nleaves;
+    const int nmax = tb.nmax;
+    const std::vector<int>&bnd = tb.bnd, &cuts = tb.cuts;
+    const std::vector<Merge>& merges = tb.merges;
     if (ntot * ((size_t)nmax + 1) > (size_t)0x7fffffff * 64) return -3;
     Arena ar(work, lwork);
     DcBatchLayout b;
     stedc_batched_carve(ar, nblk, ntot, nmax, nleaves, &b);
     if (!ar.ok) return MAKB200_ERR_WORKSPACE;
-    // host tables: leaf boundaries (global), cuts, the merges of every level, block descriptors
-    std::vector<int> bnd, cuts;
     std::vector<StedcBlkDev> bd(nblk);
-    std::vector<std::vector<int>> lb(nblk);     // per-block leaf boundaries (global positions)
-    for (int i = 0; i < nblk; ++i) {
-        const int n = blks[i].n, nl = 1 << lev[i];
-        lb[i].resize(nl + 1);
-        for (int k = 0; k <= nl; ++k) lb[i][k] = off[i] + (int)((long long)k * n / nl);
-        for (int k = 0; k < nl; ++k) bnd.push_back(lb[i][k]);
-        for (int k = 1; k < nl; ++k) cuts.push_back(lb[i][k]);
-        bd[i] = StedcBlkDev{n, off[i], lev[i] & 1, blks[i].ldv, blks[i].d, blks[i].e, blks[i].w, blks[i].V};
-    }
-    bnd.push_back((int)ntot);
-    struct LevelInfo { size_t first; int nm, maxN, maxH; };
-    std::vector<LevelInfo> levels;
-    std::vector<Merge> merges;
-    for (int l = 1; l <= Lmax; ++l) {
-        LevelInfo li{merges.size(), 0, 0, 0};
-        const int step = 1 << l;
-        for (int i = 0; i < nblk; ++i) {
-            if (lev[i] < l) continue;
-            const int nm = (1 << lev[i]) / step;
-            for (int k = 0; k < nm; ++k) {
-                Merge m{};
-                m.lo = lb[i][k * step]; m.mid = lb[i][k * step + step / 2]; m.hi = lb[i][(k + 1) * step];
-                merges.push_back(m);
-                li.maxN = std::max(li.maxN, m.hi - m.lo);
-                li.maxH = std::max(li.maxH, std::max(m.mid - m.lo, m.hi - m.mid));
-                ++li.nm;
-            }
-        }
-        levels.push_back(li);
-    }
+    for (int i = 0; i < nblk; ++i)
+        bd[i] = StedcBlkDev{blks[i].n, tb.off[i], tb.lev[i] & 1, blks[i].ldv, blks[i].d, blks[i].e, blks[i].w, blks[i].V};
     if (merges.size() > nleaves + 1) return -4;
     {
         Stager sg(h, (bnd.size() + cuts.size()) * sizeof(int) + merges.size() * sizeof(Merge) + bd.size() * sizeof(StedcBlkDev) + 4096);
@@ -633,7 +603,7 @@ int stedc_batched(makb200_handle* h, int nblk, const StedcBlk* blks, void* work,
     dc_leaf_kernel<<<(nl_all + LEAF_WARPS - 1) / LEAF_WARPS, LEAF_WARPS * 32, 0, st>>>(nl_all, b.bnd, b.ctx.D, b.E, Zin, ld, b.info);
     count_launch(3);
     MAK_LAUNCH_CHECK(h, "dc_leaf_kernel (batched)");
-    for (const LevelInfo& li : levels) {
+    for (const BatchLevel& li : tb.levels) {
         const int nm = li.nm, maxN = li.maxN, maxH = li.maxH;
         if (nm == 0) continue;
         Merge* mg = b.merges + li.first;
