@@ -1,7 +1,7 @@
 """Round-2 BRING-UP tests: kernels written after the round-1 GPU budget was spent.  Their logic is
 validated on the CPU emulator (tests/test_emu_kernels_cpu.py, all CTAs as co-resident fibers) but they
 have not run on a B200 yet, so they are opt-in at run time (MAKB200_CHASE_PERSISTENT, MAKB200_Q2_FUSED)
-and these tests only run with MAKB200_BRINGUP=1 (tools/job_r2a.sh sets it).  Sorted last on purpose."""
+and these tests only run with MAKB200_BRINGUP=1 (tools/jobs_r2/job_r2a.sh sets it).  Sorted last on purpose."""
 import os
 
 import numpy as np

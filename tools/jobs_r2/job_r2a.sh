@@ -3,7 +3,7 @@
 # Ordered by risk: (1) ungated kernels that already run in `pytest -m gpu`, (2) gated kernels without
 # inter-CTA waits, (3) the fused Q2 slab kernel, (4) the persistent (spin-waiting) chase kernel LAST and
 # under a short timeout, then the timings that decide which opt-in paths become defaults.
-#   gpurun --timeout 2400 -- 'bash tools/job_r2a.sh'      (log: gpurun_out/r2a.log)
+#   gpurun --timeout 2400 -- 'bash tools/jobs_r2/job_r2a.sh'      (log: gpurun_out/r2a.log)
 set -u
 mkdir -p gpurun_out
 {
